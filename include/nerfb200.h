@@ -1,0 +1,202 @@
+/*
+ * nerfb200.h -- C ABI of the B200-native NeRF volume-rendering hot path.
+ *
+ * One shared library (libnerfb200.so, built from nerf_rep_for_test_b200/csrc by
+ * nvcc for sm_100a) exports these entry points.  They replace, kernel by kernel,
+ * the PyTorch ops that the reference's Renderer.render(batch) issues
+ * (/root/reference/src/models/nerf/renderer/volume_renderer.py:109-216); the
+ * reference has no C interface for this path (its only native interface is the
+ * never-loaded pybind11 module cuda/pybind.cu:11-39), so this header IS the
+ * binding a maintainer would add -- see INTEGRATION.md for the ctypes stub.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *  - every pointer is a DEVICE pointer unless the name ends in _host.
+ *  - the caller allocates every buffer (outputs, packed weights, workspace);
+ *    the library allocates nothing, frees nothing, keeps no user pointer after
+ *    the call returns and has no global mutable state except the thread-local
+ *    last-error string.
+ *  - all work is enqueued on `stream` (a cudaStream_t passed as void*), no
+ *    host synchronisation inside unless stated.
+ *  - return 0 on success, non-zero on failure with a message available from
+ *    nerfb200_get_last_error_string(); the library never calls exit()
+ *    (contrast cuda/utils.cu:9-20 of the reference).
+ *  - rows of the MLP are sample points: row m = ray * n_samples + sample.
+ */
+#ifndef NERFB200_H_
+#define NERFB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NERFB200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define NERFB200_API __attribute__((visibility("default")))
+#else
+#define NERFB200_API
+#endif
+
+/* arithmetic modes of the MLP query (SURVEY 8a3 / BASELINE north_star tolerances) */
+#define NERFB200_MODE_FP32 0 /* CUDA-core FFMA, full-range sinf/cosf: 1e-5-relative parity mode */
+#define NERFB200_MODE_BF16 1 /* tcgen05.mma kind::f16 (bf16 in, fp32 accumulate in TMEM): performance mode */
+
+/* compositing variants */
+#define NERFB200_COMPOSITE_PLAIN 0     /* _raw2outputs, volume_renderer.py:286-357 (T uses 1-alpha+1e-10) */
+#define NERFB200_COMPOSITE_ERT 1       /* _raw2outputs_with_ert intended semantics: zero weights from first T<thr */
+#define NERFB200_COMPOSITE_ERT_COMPAT 2 /* ... literal :1115-1123 incl. the chunk-wide argmax quirk (2048-ray chunks) */
+
+/* network.py:22-47 -- the 24 fp32 tensors of ONE NeRF model in nn.Linear layout
+ * ([out,in] row-major weight, [out] bias); state_dict names in comments. */
+typedef struct nerfb200_mlp_weights {
+  const float* pts_w[8];  /* pts_linears.{0..7}.weight  (256,63) (256,256)x4 (256,319) (256,256)x2 */
+  const float* pts_b[8];  /* pts_linears.{0..7}.bias    (256)                                      */
+  const float* views_w;   /* views_linears.0.weight     (128,283): 256 feature cols then 27 dir-PE */
+  const float* views_b;   /* views_linears.0.bias       (128)                                      */
+  const float* feature_w; /* feature_linear.weight      (256,256)                                  */
+  const float* feature_b; /* feature_linear.bias        (256)                                      */
+  const float* alpha_w;   /* alpha_linear.weight        (1,256)                                    */
+  const float* alpha_b;   /* alpha_linear.bias          (1)                                        */
+  const float* rgb_w;     /* rgb_linear.weight          (3,128)                                    */
+  const float* rgb_b;     /* rgb_linear.bias            (3)                                        */
+} nerfb200_mlp_weights;
+
+/* gradients of the same 24 tensors (same shapes), accumulated (+=) by mlp_backward */
+typedef struct nerfb200_mlp_grads {
+  float* pts_w[8];
+  float* pts_b[8];
+  float* views_w;
+  float* views_b;
+  float* feature_w;
+  float* feature_b;
+  float* alpha_w;
+  float* alpha_b;
+  float* rgb_w;
+  float* rgb_b;
+} nerfb200_mlp_grads;
+
+/* ---- library ---------------------------------------------------------------------------- */
+NERFB200_API int nerfb200_abi_version(void);
+NERFB200_API const char* nerfb200_get_last_error_string(void);
+/* number of kernels this library has launched in this process (bench.py "gpu_launches") */
+NERFB200_API uint64_t nerfb200_launch_count(void);
+
+/* ---- a1: ray generation (volume_renderer.py:115-147) ------------------------------------- */
+/* pose: [4,4] c2w row-major, intrinsics: [3,3]; rays_o/rays_d: [H*W,3], ray id = y*W+x,
+ * rays_d normalised (:140). */
+NERFB200_API int nerfb200_raygen(const float* pose, const float* intrinsics, int H, int W,
+                    float* rays_o, float* rays_d, void* stream);
+
+/* ---- a2: stratified coarse sampling (volume_renderer.py:218-237) ------------------------- */
+/* z_table: [n_samples] = near*(1-t)+far*t evaluated by the caller with torch.linspace so the
+ * table is bit-identical to the reference's.  perturb==0: broadcast.  perturb!=0: stratified
+ * jitter (:228-235) with a counter-based RNG keyed on (seed, ray, sample). */
+NERFB200_API int nerfb200_sample_coarse(const float* z_table, int n_rays, int n_samples, int perturb,
+                           uint64_t seed, float* z_vals, void* stream);
+
+/* ---- a3: positional encoding fused into the NeRF MLP (freq.py:3-32, network.py:49-74) ---- */
+NERFB200_API size_t nerfb200_packed_weights_bytes(int mode);
+/* repack one model's weights into the layout the `mode` kernel streams; re-run after every
+ * optimizer step.  packed must be 1024-byte aligned. */
+NERFB200_API int nerfb200_pack_weights(const nerfb200_mlp_weights* w, int mode, void* packed, void* stream);
+/* raw[m] = (rgb_raw[3], sigma_raw) for row m = ray*n_samples+s at point o + d*z (evaluated as
+ * fadd(o, fmul(d,z)), no FMA contraction, :165); view dir = rays_d (:143). */
+NERFB200_API int nerfb200_mlp_forward(const void* packed, int mode, const float* rays_o, const float* rays_d,
+                         const float* z_vals, int n_rays, int n_samples, float* raw, void* stream);
+
+/* ---- a5/a6: alpha compositing (volume_renderer.py:286-357, :1089-1157) ------------------- */
+/* raw [n_rays,S,4], z_vals [n_rays,S], rays_d [n_rays,3] -> rgb_map [n_rays,3], disp/acc/depth
+ * [n_rays], weights [n_rays,S] (may be NULL).  One warp per ray, shuffle prefix product.
+ * variant: NERFB200_COMPOSITE_*; ERT_COMPAT groups rays in chunks of compat_chunk (2048). */
+NERFB200_API int nerfb200_composite_forward(const float* raw, const float* z_vals, const float* rays_d,
+                               int n_rays, int n_samples, int variant, float ert_threshold,
+                               int white_bkgd, int compat_chunk, float* rgb_map, float* disp_map,
+                               float* acc_map, float* depth_map, float* weights, void* stream);
+
+/* a7: analytic backward of NERFB200_COMPOSITE_PLAIN.  g_* are dL/d(map) (any may be NULL);
+ * writes g_raw [n_rays,S,4] (overwrite). z_vals/rays_d receive no gradient here. */
+NERFB200_API int nerfb200_composite_backward(const float* raw, const float* z_vals, const float* rays_d,
+                                int n_rays, int n_samples, int white_bkgd, const float* g_rgb_map,
+                                const float* g_acc_map, const float* g_depth_map,
+                                const float* g_weights, float* g_raw, void* stream);
+
+/* ---- a4: sample_pdf + merge (volume_renderer.py:239-268, :181-183) ----------------------- */
+/* kernel-level inverse-CDF lookup: cdf,bins [n_rays,n_bins]; u is [n_u] (u_per_ray==0, the
+ * eval-mode linspace table) or [n_rays,n_u]; inds = searchsorted(cdf,u,right=True) (int32). */
+NERFB200_API int nerfb200_sample_from_cdf(const float* cdf, const float* bins, const float* u, int u_per_ray,
+                             int n_rays, int n_bins, int n_u, float* samples, int32_t* inds,
+                             void* stream);
+/* whole a4: weights [n_rays,S] (coarse, the kernel uses [1:-1]), z_coarse [n_rays,S] ->
+ * z_all [n_rays,S+n_u] sorted; optional z_samples [n_rays,n_u], inds [n_rays,n_u], cdf
+ * [n_rays,S-1] (NULL to skip). */
+NERFB200_API int nerfb200_sample_pdf_merge(const float* z_coarse, const float* weights, const float* u,
+                              int u_per_ray, int n_rays, int n_samples, int n_u, float* z_all,
+                              float* z_samples, int32_t* inds, float* cdf, void* stream);
+
+/* ---- a8: occupancy grid / empty-space skipping (volume_renderer.py:830-873, :963-1087) --- */
+/* grid: uint8 [R,R,R] (1 = occupied), bbox [-2,2]^3.  Per ray: if more than half of the
+ * coarse samples fall in empty cells, keep the occupied z's and refill with
+ * linspace(min_occ,max_occ,S-n_keep), sorted (intended per-ray semantics of :1037-1077). */
+NERFB200_API int nerfb200_ess_resample(const uint8_t* grid, int res, const float* rays_o, const float* rays_d,
+                          int n_rays, int n_samples, float* z_vals, int32_t* n_empty, void* stream);
+/* :963-985 as called from :1147-1155: mark cells of samples with weight>1e-4 and
+ * relu(sigma_raw)>0.01; points are rays_d*z (ray origin omitted, as in the reference) unless
+ * use_origin!=0. */
+NERFB200_API int nerfb200_ess_update(uint8_t* grid, int res, const float* rays_o, const float* rays_d,
+                        const float* z_vals, const float* raw, const float* weights, int n_rays,
+                        int n_samples, int use_origin, void* stream);
+
+/* ---- whole pass --------------------------------------------------------------------------- */
+typedef struct nerfb200_render_params {
+  int n_samples;      /* 64  */
+  int n_importance;   /* 128 */
+  int mode;           /* NERFB200_MODE_* */
+  int variant;        /* NERFB200_COMPOSITE_* */
+  int white_bkgd;
+  int perturb;        /* 0 for parity */
+  int u_per_ray;      /* 0: u is the [n_importance] table; 1: u is [n_rays,n_importance] */
+  int compat_chunk;   /* 2048 */
+  float ert_threshold;
+  uint64_t seed;
+  /* a8: when non-NULL the coarse z's of every ray are passed through nerfb200_ess_resample */
+  const uint8_t* occupancy_grid; /* uint8 [grid_res]^3, device */
+  int grid_res;
+} nerfb200_render_params;
+
+/* maps for one pass: rgb [n,3], disp/acc/depth [n] */
+typedef struct nerfb200_maps {
+  float* rgb;
+  float* disp;
+  float* acc;
+  float* depth;
+} nerfb200_maps;
+
+NERFB200_API size_t nerfb200_render_workspace_bytes(int n_rays, const nerfb200_render_params* p);
+/* coarse sample -> MLP -> composite -> sample_pdf+merge -> MLP(fine) -> composite, all on
+ * `stream`, no host sync.  packed_coarse/packed_fine from nerfb200_pack_weights(mode).
+ * maps_fine members may be NULL when n_importance==0. */
+NERFB200_API int nerfb200_render_rays(const void* packed_coarse, const void* packed_fine, const float* rays_o,
+                         const float* rays_d, int n_rays, const float* z_table, const float* u,
+                         const nerfb200_render_params* p, void* workspace, size_t workspace_bytes,
+                         const nerfb200_maps* maps_coarse, const nerfb200_maps* maps_fine,
+                         void* stream);
+
+/* Host-buffer entry (the e2e number): pose_host [16], intrinsics_host [9] and the eight output
+ * maps live in (pinned) HOST memory; device scratch comes from `workspace`.  Copies in, renders
+ * H*W rays, copies the maps out and synchronises the stream before returning. */
+NERFB200_API size_t nerfb200_render_image_workspace_bytes(int H, int W, const nerfb200_render_params* p);
+NERFB200_API int nerfb200_render_image_host(const void* packed_coarse, const void* packed_fine,
+                               const float* pose_host, const float* intrinsics_host, int H, int W,
+                               const float* z_table, const float* u, const nerfb200_render_params* p,
+                               void* workspace, size_t workspace_bytes,
+                               const nerfb200_maps* maps_coarse_host,
+                               const nerfb200_maps* maps_fine_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NERFB200_H_ */

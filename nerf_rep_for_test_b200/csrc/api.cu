@@ -1,0 +1,219 @@
+// C-ABI glue: error string, launch counter, MLP dispatch and the whole-pass drivers.
+// Reference for the pass order: volume_renderer.py:154-205.
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "common.cuh"
+
+namespace nb {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+int launch_mlp_fp32(const void* packed, const float* rays_o, const float* rays_d, const float* z_vals,
+                    int n_rays, int n_samples, float* raw, cudaStream_t st);
+int launch_mlp_bf16(const void* packed, const float* rays_o, const float* rays_d, const float* z_vals,
+                    int n_rays, int n_samples, float* raw, cudaStream_t st);
+
+// rays per internal chunk of the whole-pass driver: keeps the per-chunk intermediates
+// (z, raw, weights: ~5.4 KB/ray) inside the 126 MB L2 and bounds the workspace.
+constexpr int kChunkRays = 8192;
+
+struct Workspace {
+  float* z_coarse;  // [c,S]
+  float* raw_c;     // [c,S,4]
+  float* weights;   // [c,S]
+  float* z_all;     // [c,S+U]
+  float* raw_f;     // [c,S+U,4]
+  size_t bytes;
+};
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static Workspace carve(void* base, int chunk, int S, int U) {
+  Workspace w;
+  size_t off = 0;
+  auto take = [&](size_t nfloats) {
+    float* p = base ? reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off) : nullptr;
+    off += align256(nfloats * 4);
+    return p;
+  };
+  w.z_coarse = take((size_t)chunk * S);
+  w.raw_c = take((size_t)chunk * S * 4);
+  w.weights = take((size_t)chunk * S);
+  w.z_all = take((size_t)chunk * (S + U));
+  w.raw_f = take((size_t)chunk * (S + U) * 4);
+  w.bytes = off;
+  return w;
+}
+
+static int check_params(const nerfb200_render_params* p) {
+  NB_CHECK_ARG(p, "render: null params");
+  NB_CHECK_ARG(p->n_samples >= 3 && p->n_samples <= 256, "render: n_samples=%d out of range [3,256]", p->n_samples);
+  NB_CHECK_ARG(p->n_importance >= 0 && p->n_importance <= 256 && p->n_samples + p->n_importance <= 256,
+               "render: n_importance=%d out of range (n_samples+n_importance <= 256)", p->n_importance);
+  NB_CHECK_ARG(p->mode == NERFB200_MODE_FP32 || p->mode == NERFB200_MODE_BF16, "render: unknown mode %d", p->mode);
+  NB_CHECK_ARG(p->variant >= 0 && p->variant <= 2, "render: unknown composite variant %d", p->variant);
+  NB_CHECK_ARG(p->variant != NERFB200_COMPOSITE_ERT_COMPAT || (p->compat_chunk > 0 && kChunkRays % p->compat_chunk == 0),
+               "render: compat_chunk=%d must divide %d", p->compat_chunk, kChunkRays);
+  return 0;
+}
+
+}  // namespace nb
+
+using namespace nb;
+
+extern "C" int nerfb200_abi_version(void) { return NERFB200_ABI_VERSION; }
+extern "C" const char* nerfb200_get_last_error_string(void) { return g_err; }
+extern "C" uint64_t nerfb200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int nerfb200_mlp_forward(const void* packed, int mode, const float* rays_o, const float* rays_d,
+                                    const float* z_vals, int n_rays, int n_samples, float* raw, void* stream) {
+  NB_CHECK_ARG(packed && rays_o && rays_d && z_vals && raw, "mlp_forward: null pointer");
+  NB_CHECK_ARG(n_rays >= 0 && n_samples >= 1, "mlp_forward: bad sizes n_rays=%d n_samples=%d", n_rays, n_samples);
+  NB_CHECK_ARG(((uintptr_t)packed & 1023) == 0, "mlp_forward: packed weights must be 1024-byte aligned");
+  if (n_rays == 0) return 0;
+  if (mode == NERFB200_MODE_FP32) return launch_mlp_fp32(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, (cudaStream_t)stream);
+  if (mode == NERFB200_MODE_BF16) return launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, (cudaStream_t)stream);
+  set_error("mlp_forward: unknown mode %d", mode);
+  return 1;
+}
+
+extern "C" size_t nerfb200_render_workspace_bytes(int n_rays, const nerfb200_render_params* p) {
+  if (!p || n_rays < 0) return 0;
+  int chunk = n_rays < kChunkRays ? n_rays : kChunkRays;
+  if (chunk == 0) chunk = 1;
+  return carve(nullptr, chunk, p->n_samples, p->n_importance).bytes;
+}
+
+extern "C" int nerfb200_render_rays(const void* packed_coarse, const void* packed_fine, const float* rays_o,
+                                    const float* rays_d, int n_rays, const float* z_table, const float* u,
+                                    const nerfb200_render_params* p, void* workspace, size_t workspace_bytes,
+                                    const nerfb200_maps* mc, const nerfb200_maps* mf, void* stream) {
+  if (int e = check_params(p)) return e;
+  NB_CHECK_ARG(packed_coarse && rays_o && rays_d && z_table && mc, "render_rays: null pointer");
+  NB_CHECK_ARG(mc->rgb && mc->disp && mc->acc && mc->depth, "render_rays: null coarse map");
+  NB_CHECK_ARG(n_rays >= 0, "render_rays: negative n_rays");
+  const int S = p->n_samples, U = p->n_importance;
+  if (U > 0) {
+    NB_CHECK_ARG(packed_fine && u && mf && mf->rgb && mf->disp && mf->acc && mf->depth,
+                 "render_rays: fine pass needs packed_fine, u and fine maps");
+  }
+  if (n_rays == 0) return 0;
+  NB_CHECK_ARG(workspace && workspace_bytes >= nerfb200_render_workspace_bytes(n_rays, p),
+               "render_rays: workspace too small (%zu < %zu)", workspace_bytes,
+               nerfb200_render_workspace_bytes(n_rays, p));
+  int chunk = n_rays < kChunkRays ? n_rays : kChunkRays;
+  Workspace ws = carve(workspace, chunk, S, U);
+  for (int r0 = 0; r0 < n_rays; r0 += chunk) {
+    int n = (n_rays - r0) < chunk ? (n_rays - r0) : chunk;
+    const float* ro = rays_o + (size_t)r0 * 3;
+    const float* rd = rays_d + (size_t)r0 * 3;
+    int e;
+    // per-ray jitter is keyed on the ray index inside the call: offset the seed per chunk
+    if ((e = nerfb200_sample_coarse(z_table, n, S, p->perturb, p->seed + (uint64_t)r0 * 0x9E3779B97F4A7C15ull, ws.z_coarse, stream))) return e;
+    if (p->occupancy_grid &&
+        (e = nerfb200_ess_resample(p->occupancy_grid, p->grid_res, ro, rd, n, S, ws.z_coarse, nullptr, stream))) return e;
+    if ((e = nerfb200_mlp_forward(packed_coarse, p->mode, ro, rd, ws.z_coarse, n, S, ws.raw_c, stream))) return e;
+    if ((e = nerfb200_composite_forward(ws.raw_c, ws.z_coarse, rd, n, S, p->variant, p->ert_threshold, p->white_bkgd,
+                                        p->compat_chunk, mc->rgb + (size_t)r0 * 3, mc->disp + r0, mc->acc + r0,
+                                        mc->depth + r0, ws.weights, stream))) return e;
+    if (U > 0) {
+      const float* uu = p->u_per_ray ? u + (size_t)r0 * U : u;
+      if ((e = nerfb200_sample_pdf_merge(ws.z_coarse, ws.weights, uu, p->u_per_ray, n, S, U, ws.z_all, nullptr, nullptr,
+                                         nullptr, stream))) return e;
+      if ((e = nerfb200_mlp_forward(packed_fine, p->mode, ro, rd, ws.z_all, n, S + U, ws.raw_f, stream))) return e;
+      if ((e = nerfb200_composite_forward(ws.raw_f, ws.z_all, rd, n, S + U, p->variant, p->ert_threshold, p->white_bkgd,
+                                          p->compat_chunk, mf->rgb + (size_t)r0 * 3, mf->disp + r0, mf->acc + r0,
+                                          mf->depth + r0, nullptr, stream))) return e;
+    }
+  }
+  return 0;
+}
+
+// ---- host-buffer entry ------------------------------------------------------------------------
+// device scratch: pose(16)+K(9) | rays_o | rays_d | 8 maps | render workspace
+namespace nb {
+struct ImageScratch {
+  float* cam;  // 32 floats
+  float* rays_o;
+  float* rays_d;
+  float* maps;  // 2 x (3+1+1+1) x n
+  void* ws;
+  size_t ws_bytes;
+  size_t bytes;
+};
+static ImageScratch carve_image(void* base, int n, const nerfb200_render_params* p) {
+  ImageScratch s;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* q = base ? reinterpret_cast<char*>(base) + off : nullptr;
+    off += align256(bytes);
+    return q;
+  };
+  s.cam = (float*)take(32 * 4);
+  s.rays_o = (float*)take((size_t)n * 12);
+  s.rays_d = (float*)take((size_t)n * 12);
+  s.maps = (float*)take((size_t)n * 12 * 4);
+  s.ws_bytes = nerfb200_render_workspace_bytes(n, p);
+  s.ws = take(s.ws_bytes);
+  s.bytes = off;
+  return s;
+}
+}  // namespace nb
+
+extern "C" size_t nerfb200_render_image_workspace_bytes(int H, int W, const nerfb200_render_params* p) {
+  if (!p || H <= 0 || W <= 0) return 0;
+  return carve_image(nullptr, H * W, p).bytes;
+}
+
+extern "C" int nerfb200_render_image_host(const void* packed_coarse, const void* packed_fine,
+                                          const float* pose_host, const float* intrinsics_host, int H, int W,
+                                          const float* z_table, const float* u, const nerfb200_render_params* p,
+                                          void* workspace, size_t workspace_bytes,
+                                          const nerfb200_maps* mc_host, const nerfb200_maps* mf_host, void* stream) {
+  if (int e = check_params(p)) return e;
+  NB_CHECK_ARG(pose_host && intrinsics_host && mc_host, "render_image_host: null pointer");
+  NB_CHECK_ARG(H > 0 && W > 0 && (long long)H * W < (1LL << 28), "render_image_host: bad H=%d W=%d", H, W);
+  NB_CHECK_ARG(workspace && workspace_bytes >= nerfb200_render_image_workspace_bytes(H, W, p),
+               "render_image_host: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = H * W;
+  ImageScratch s = carve_image(workspace, n, p);
+  NB_CUDA(cudaMemcpyAsync(s.cam, pose_host, 16 * 4, cudaMemcpyHostToDevice, st));
+  NB_CUDA(cudaMemcpyAsync(s.cam + 16, intrinsics_host, 9 * 4, cudaMemcpyHostToDevice, st));
+  int e;
+  if ((e = nerfb200_raygen(s.cam, s.cam + 16, H, W, s.rays_o, s.rays_d, stream))) return e;
+  nerfb200_maps dc, df;
+  float* m = s.maps;
+  dc.rgb = m; dc.disp = m + (size_t)n * 3; dc.acc = m + (size_t)n * 4; dc.depth = m + (size_t)n * 5;
+  m += (size_t)n * 6;
+  df.rgb = m; df.disp = m + (size_t)n * 3; df.acc = m + (size_t)n * 4; df.depth = m + (size_t)n * 5;
+  if ((e = nerfb200_render_rays(packed_coarse, packed_fine, s.rays_o, s.rays_d, n, z_table, u, p, s.ws, s.ws_bytes, &dc,
+                                p->n_importance > 0 ? &df : nullptr, stream))) return e;
+  auto d2h = [&](float* dst, const float* src, size_t nf) -> cudaError_t {
+    return dst ? cudaMemcpyAsync(dst, src, nf * 4, cudaMemcpyDeviceToHost, st) : cudaSuccess;
+  };
+  NB_CUDA(d2h(mc_host->rgb, dc.rgb, (size_t)n * 3));
+  NB_CUDA(d2h(mc_host->disp, dc.disp, n));
+  NB_CUDA(d2h(mc_host->acc, dc.acc, n));
+  NB_CUDA(d2h(mc_host->depth, dc.depth, n));
+  if (p->n_importance > 0 && mf_host) {
+    NB_CUDA(d2h(mf_host->rgb, df.rgb, (size_t)n * 3));
+    NB_CUDA(d2h(mf_host->disp, df.disp, n));
+    NB_CUDA(d2h(mf_host->acc, df.acc, n));
+    NB_CUDA(d2h(mf_host->depth, df.depth, n));
+  }
+  NB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}

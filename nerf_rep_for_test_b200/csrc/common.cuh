@@ -1,0 +1,55 @@
+// Shared host/device helpers for libnerfb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/nerfb200.h"
+
+namespace nb {
+
+// network.py:22-47 / lego.yaml geometry
+constexpr int kW = 256;         // hidden width
+constexpr int kD = 8;           // pts_linears depth
+constexpr int kSkip = 4;        // concat after layer 4 -> layer 5 has K = 63 + 256
+constexpr int kLx = 10;         // xyz frequencies
+constexpr int kLd = 4;          // dir frequencies
+constexpr int kChX = 3 + 6 * kLx;  // 63
+constexpr int kChD = 3 + 6 * kLd;  // 27
+constexpr int kWv = 128;        // views_linears width
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define NB_CHECK_ARG(cond, ...)      \
+  do {                               \
+    if (!(cond)) {                   \
+      nb::set_error(__VA_ARGS__);    \
+      return 1;                      \
+    }                                \
+  } while (0)
+
+#define NB_CUDA(call)                                                                  \
+  do {                                                                                 \
+    cudaError_t e__ = (call);                                                          \
+    if (e__ != cudaSuccess) {                                                          \
+      nb::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,               \
+                    cudaGetErrorString(e__));                                          \
+      return 2;                                                                        \
+    }                                                                                  \
+  } while (0)
+
+// launch check: catches bad configurations immediately (no device sync)
+#define NB_LAUNCH_OK(name)                                                             \
+  do {                                                                                 \
+    cudaError_t e__ = cudaGetLastError();                                              \
+    if (e__ != cudaSuccess) {                                                          \
+      nb::set_error("launch of %s failed: %s", name, cudaGetErrorString(e__));         \
+      return 3;                                                                        \
+    }                                                                                  \
+    nb::count_launch();                                                                \
+  } while (0)
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace nb

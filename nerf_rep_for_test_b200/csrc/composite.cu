@@ -1,0 +1,314 @@
+// a5/a6 alpha compositing forward (+ERT variants) and a7 analytic backward.
+// Reference: volume_renderer.py:286-357 (_raw2outputs), :1089-1157 (_raw2outputs_with_ert).
+//
+// One warp per ray; every lane owns a contiguous run of samples, the transmittance is an
+// exclusive prefix product done as lane-local products + a warp shuffle scan.  The scan and
+// the map reductions run in fp64: torch CPU's cumprod accumulates float in double and rounds
+// every output (probed: 0 mismatches), so T_i here is bit-identical to the reference's given
+// the same alphas.  HBM-bound: reads 20 B/sample (raw float4 + z), writes 4 B/sample
+// (weights) + 24 B/ray.
+#include "common.cuh"
+
+namespace nb {
+
+constexpr int kCompWarps = 8;
+constexpr int kMaxPer = 8;  // ceil(S/32) <= 8  => S <= 256
+
+__device__ __forceinline__ float ray_norm(const float* __restrict__ d) {
+  // torch.norm(rays_d[..., None, :], dim=-1): FMA-chain accumulation (probed, bit-exact)
+  return __fsqrt_rn(__fmaf_rn(d[2], d[2], __fmaf_rn(d[1], d[1], __fmul_rn(d[0], d[0]))));
+}
+
+__device__ __forceinline__ double warp_excl_prod(double local, int lane, double* total) {
+  double v = local;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    double o = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d) v *= o;
+  }
+  *total = __shfl_sync(0xffffffffu, v, 31);
+  double ex = __shfl_up_sync(0xffffffffu, v, 1);
+  return lane == 0 ? 1.0 : ex;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+
+struct RaySamples {
+  float alpha[kMaxPer];
+  float T[kMaxPer];     // transmittance before sample (fp32-rounded, as the reference sees it)
+  bool low_any;         // (ERT) any T < threshold on this ray
+  int first_low;        // (ERT) first sample index with T < threshold, S if none
+};
+
+// alpha + transmittance for the lane's samples.  eps = 1e-10 (PLAIN) or 0 (ERT variants).
+template <bool kErt>
+__device__ __forceinline__ void ray_alpha_T(const float* __restrict__ raw_row,
+                                            const float* __restrict__ z_row, float dnorm, int S,
+                                            int per, int lane, float thr, RaySamples& rs) {
+  double local = 1.0;
+  float fac[kMaxPer];
+#pragma unroll
+  for (int j = 0; j < kMaxPer; ++j) {
+    int i = lane * per + j;
+    float a = 0.f, f = 1.f;
+    if (j < per && i < S) {
+      float z0 = z_row[i];
+      float dist = (i + 1 < S) ? __fsub_rn(z_row[i + 1], z0) : 1e10f;
+      dist = __fmul_rn(dist, dnorm);
+      float sig = fmaxf(raw_row[(size_t)i * 4 + 3], 0.f);
+      a = __fsub_rn(1.f, expf(__fmul_rn(-sig, dist)));
+      f = kErt ? __fsub_rn(1.f, a) : __fadd_rn(__fsub_rn(1.f, a), 1e-10f);
+      local *= (double)f;
+    }
+    rs.alpha[j] = a;
+    fac[j] = f;
+  }
+  double total;
+  double run = warp_excl_prod(local, lane, &total);
+  int first = 1 << 30;
+#pragma unroll
+  for (int j = 0; j < kMaxPer; ++j) {
+    int i = lane * per + j;
+    rs.T[j] = (float)run;
+    if (kErt && j < per && i < S && rs.T[j] < thr) first = min(first, i);
+    run *= (double)fac[j];
+  }
+  if (kErt) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, d));
+    rs.low_any = first < S;
+    rs.first_low = rs.low_any ? first : S;
+  } else {
+    rs.low_any = false;
+    rs.first_low = S;
+  }
+}
+
+// cut = first sample index whose weight is forced to zero (S = none)
+__device__ __forceinline__ void ray_outputs(const RaySamples& rs, const float* __restrict__ raw_row,
+                                            const float* __restrict__ z_row, int S, int per, int lane,
+                                            int cut, int white_bkgd, size_t ray,
+                                            float* __restrict__ rgb_map, float* __restrict__ disp_map,
+                                            float* __restrict__ acc_map, float* __restrict__ depth_map,
+                                            float* __restrict__ weights) {
+  double sr = 0, sg = 0, sb = 0, sd = 0, sa = 0;
+#pragma unroll
+  for (int j = 0; j < kMaxPer; ++j) {
+    int i = lane * per + j;
+    if (j < per && i < S) {
+      float w = __fmul_rn(rs.alpha[j], rs.T[j]);
+      if (i >= cut) w = __fmul_rn(w, 0.f);  // weights * (~mask).float()
+      float4 r4 = *reinterpret_cast<const float4*>(raw_row + (size_t)i * 4);
+      float cr = 1.f / (1.f + expf(-r4.x)), cg = 1.f / (1.f + expf(-r4.y)), cb = 1.f / (1.f + expf(-r4.z));
+      sr += (double)__fmul_rn(w, cr);
+      sg += (double)__fmul_rn(w, cg);
+      sb += (double)__fmul_rn(w, cb);
+      sd += (double)__fmul_rn(w, z_row[i]);
+      sa += (double)w;
+      if (weights) weights[ray * S + i] = w;
+    }
+  }
+  sr = warp_sum(sr); sg = warp_sum(sg); sb = warp_sum(sb); sd = warp_sum(sd); sa = warp_sum(sa);
+  if (lane == 0) {
+    float acc = (float)sa, depth = (float)sd;
+    float r = (float)sr, g = (float)sg, b = (float)sb;
+    float q = __fdiv_rn(depth, acc);
+    float m = (q != q) ? q : fmaxf(1e-10f, q);  // torch.max propagates NaN (acc == 0)
+    if (white_bkgd) {
+      float bg = __fsub_rn(1.f, acc);
+      r = __fadd_rn(r, bg); g = __fadd_rn(g, bg); b = __fadd_rn(b, bg);
+    }
+    rgb_map[ray * 3 + 0] = r; rgb_map[ray * 3 + 1] = g; rgb_map[ray * 3 + 2] = b;
+    disp_map[ray] = __fdiv_rn(1.f, m);
+    acc_map[ray] = acc;
+    depth_map[ray] = depth;
+  }
+}
+
+// PLAIN and ERT: one warp per ray
+template <bool kErt>
+__global__ void __launch_bounds__(kCompWarps * 32)
+composite_kernel(const float* __restrict__ raw, const float* __restrict__ z_vals,
+                 const float* __restrict__ rays_d, int n_rays, int S, float thr, int white_bkgd,
+                 float* __restrict__ rgb_map, float* __restrict__ disp_map,
+                 float* __restrict__ acc_map, float* __restrict__ depth_map,
+                 float* __restrict__ weights) {
+  int lane = threadIdx.x & 31;
+  size_t ray = (size_t)blockIdx.x * kCompWarps + (threadIdx.x >> 5);
+  if (ray >= (size_t)n_rays) return;
+  int per = (S + 31) / 32;
+  const float* raw_row = raw + ray * S * 4;
+  const float* z_row = z_vals + ray * S;
+  RaySamples rs;
+  ray_alpha_T<kErt>(raw_row, z_row, ray_norm(rays_d + ray * 3), S, per, lane, thr, rs);
+  ray_outputs(rs, raw_row, z_row, S, per, lane, rs.first_low, white_bkgd, ray, rgb_map, disp_map,
+              acc_map, depth_map, weights);
+}
+
+// ERT_COMPAT: literal :1115-1123.  `if low.any()` is evaluated over the whole call (a
+// 2048-ray chunk in the reference); when it fires, first = argmax(low) is 0 for rays that never
+// go low, so those rays lose ALL weights.  One block per chunk, two passes.
+__global__ void __launch_bounds__(1024)
+composite_ert_compat_kernel(const float* __restrict__ raw, const float* __restrict__ z_vals,
+                            const float* __restrict__ rays_d, int n_rays, int S, float thr,
+                            int white_bkgd, int chunk, float* __restrict__ rgb_map,
+                            float* __restrict__ disp_map, float* __restrict__ acc_map,
+                            float* __restrict__ depth_map, float* __restrict__ weights) {
+  __shared__ int s_any;
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  size_t begin = (size_t)blockIdx.x * chunk;
+  size_t end = min(begin + (size_t)chunk, (size_t)n_rays);
+  int per = (S + 31) / 32;
+  if (threadIdx.x == 0) s_any = 0;
+  __syncthreads();
+  bool any = false;
+  for (size_t ray = begin + warp; ray < end; ray += nwarps) {
+    RaySamples rs;
+    ray_alpha_T<true>(raw + ray * S * 4, z_vals + ray * S, ray_norm(rays_d + ray * 3), S, per, lane, thr, rs);
+    any |= rs.low_any;
+  }
+  if (any && lane == 0) atomicOr(&s_any, 1);
+  __syncthreads();
+  bool chunk_any = s_any != 0;
+  for (size_t ray = begin + warp; ray < end; ray += nwarps) {
+    const float* raw_row = raw + ray * S * 4;
+    const float* z_row = z_vals + ray * S;
+    RaySamples rs;
+    ray_alpha_T<true>(raw_row, z_row, ray_norm(rays_d + ray * 3), S, per, lane, thr, rs);
+    int cut = chunk_any ? (rs.low_any ? rs.first_low : 0) : S;
+    ray_outputs(rs, raw_row, z_row, S, per, lane, cut, white_bkgd, ray, rgb_map, disp_map, acc_map,
+                depth_map, weights);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// a7: backward of the PLAIN variant.  With G_i = dL/dw_i = g_rgb.c_i + g_acc' + g_depth z_i +
+// g_w_i (g_acc' = g_acc - sum(g_rgb) under white_bkgd), f_i = 1-alpha_i+1e-10:
+//   dL/dalpha_i = G_i T_i - (sum_{j>i} G_j w_j) / f_i
+//   dalpha/dsigma_raw = dist * exp(-sigma*dist) * [sigma_raw > 0]     (not dist*(1-alpha): inf*0)
+//   dL/drgb_raw_c = w_i g_rgb_c c (1-c)
+// The suffix sum is a reverse warp scan in fp64.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCompWarps * 32)
+composite_backward_kernel(const float* __restrict__ raw, const float* __restrict__ z_vals,
+                          const float* __restrict__ rays_d, int n_rays, int S, int white_bkgd,
+                          const float* __restrict__ g_rgb_map, const float* __restrict__ g_acc_map,
+                          const float* __restrict__ g_depth_map, const float* __restrict__ g_weights,
+                          float* __restrict__ g_raw) {
+  int lane = threadIdx.x & 31;
+  size_t ray = (size_t)blockIdx.x * kCompWarps + (threadIdx.x >> 5);
+  if (ray >= (size_t)n_rays) return;
+  int per = (S + 31) / 32;
+  const float* raw_row = raw + ray * S * 4;
+  const float* z_row = z_vals + ray * S;
+  float dnorm = ray_norm(rays_d + ray * 3);
+  RaySamples rs;
+  ray_alpha_T<false>(raw_row, z_row, dnorm, S, per, lane, 0.f, rs);
+  float gr = g_rgb_map ? g_rgb_map[ray * 3 + 0] : 0.f;
+  float gg = g_rgb_map ? g_rgb_map[ray * 3 + 1] : 0.f;
+  float gb = g_rgb_map ? g_rgb_map[ray * 3 + 2] : 0.f;
+  float ga = g_acc_map ? g_acc_map[ray] : 0.f;
+  float gd = g_depth_map ? g_depth_map[ray] : 0.f;
+  if (white_bkgd) ga -= (gr + gg + gb);
+  float G[kMaxPer], w[kMaxPer], c[kMaxPer][3];
+  double local = 0.0;
+#pragma unroll
+  for (int j = 0; j < kMaxPer; ++j) {
+    int i = lane * per + j;
+    G[j] = 0.f; w[j] = 0.f;
+    if (j < per && i < S) {
+      float4 r4 = *reinterpret_cast<const float4*>(raw_row + (size_t)i * 4);
+      c[j][0] = 1.f / (1.f + expf(-r4.x));
+      c[j][1] = 1.f / (1.f + expf(-r4.y));
+      c[j][2] = 1.f / (1.f + expf(-r4.z));
+      w[j] = rs.alpha[j] * rs.T[j];
+      G[j] = gr * c[j][0] + gg * c[j][1] + gb * c[j][2] + ga + gd * z_row[i] +
+             (g_weights ? g_weights[ray * S + i] : 0.f);
+      local += (double)G[j] * (double)w[j];
+    }
+  }
+  // suffix sums: total - inclusive prefix
+  double incl = local;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    double o = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += o;
+  }
+  double total = __shfl_sync(0xffffffffu, incl, 31);
+  double after = total - incl;  // sum over samples owned by later lanes
+  // walk own samples from last to first
+  double suffix = after;
+#pragma unroll
+  for (int j = kMaxPer - 1; j >= 0; --j) {
+    int i = lane * per + j;
+    if (j < per && i < S) {
+      float z0 = z_row[i];
+      float dist = ((i + 1 < S) ? (z_row[i + 1] - z0) : 1e10f) * dnorm;
+      float sraw = raw_row[(size_t)i * 4 + 3];
+      float sig = fmaxf(sraw, 0.f);
+      float f = (1.f - rs.alpha[j]) + 1e-10f;
+      double dalpha = (double)G[j] * (double)rs.T[j] - suffix / (double)f;
+      float dsig = (sraw > 0.f) ? dist * expf(-sig * dist) : 0.f;
+      float4 o;
+      o.x = w[j] * gr * c[j][0] * (1.f - c[j][0]);
+      o.y = w[j] * gg * c[j][1] * (1.f - c[j][1]);
+      o.z = w[j] * gb * c[j][2] * (1.f - c[j][2]);
+      o.w = (float)(dalpha * (double)dsig);
+      *reinterpret_cast<float4*>(g_raw + (ray * S + i) * 4) = o;
+      suffix += (double)G[j] * (double)w[j];
+    }
+  }
+}
+
+}  // namespace nb
+
+using namespace nb;
+
+extern "C" int nerfb200_composite_forward(const float* raw, const float* z_vals, const float* rays_d,
+                                          int n_rays, int n_samples, int variant, float ert_threshold,
+                                          int white_bkgd, int compat_chunk, float* rgb_map,
+                                          float* disp_map, float* acc_map, float* depth_map,
+                                          float* weights, void* stream) {
+  NB_CHECK_ARG(raw && z_vals && rays_d && rgb_map && disp_map && acc_map && depth_map,
+               "composite_forward: null pointer");
+  NB_CHECK_ARG(n_samples >= 1 && n_samples <= 32 * kMaxPer, "composite_forward: n_samples=%d out of range [1,%d]",
+               n_samples, 32 * kMaxPer);
+  NB_CHECK_ARG(n_rays >= 0, "composite_forward: negative n_rays");
+  NB_CHECK_ARG(variant >= 0 && variant <= 2, "composite_forward: unknown variant %d", variant);
+  if (n_rays == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  int blocks = ceil_div(n_rays, kCompWarps);
+  if (variant == NERFB200_COMPOSITE_PLAIN) {
+    composite_kernel<false><<<blocks, kCompWarps * 32, 0, st>>>(raw, z_vals, rays_d, n_rays, n_samples, 0.f, white_bkgd,
+                                                               rgb_map, disp_map, acc_map, depth_map, weights);
+  } else if (variant == NERFB200_COMPOSITE_ERT) {
+    composite_kernel<true><<<blocks, kCompWarps * 32, 0, st>>>(raw, z_vals, rays_d, n_rays, n_samples, ert_threshold,
+                                                              white_bkgd, rgb_map, disp_map, acc_map, depth_map, weights);
+  } else {
+    NB_CHECK_ARG(compat_chunk > 0, "composite_forward: compat_chunk must be > 0");
+    composite_ert_compat_kernel<<<ceil_div(n_rays, compat_chunk), 1024, 0, st>>>(
+        raw, z_vals, rays_d, n_rays, n_samples, ert_threshold, white_bkgd, compat_chunk, rgb_map, disp_map, acc_map,
+        depth_map, weights);
+  }
+  NB_LAUNCH_OK("composite_kernel");
+  return 0;
+}
+
+extern "C" int nerfb200_composite_backward(const float* raw, const float* z_vals, const float* rays_d,
+                                           int n_rays, int n_samples, int white_bkgd,
+                                           const float* g_rgb_map, const float* g_acc_map,
+                                           const float* g_depth_map, const float* g_weights,
+                                           float* g_raw, void* stream) {
+  NB_CHECK_ARG(raw && z_vals && rays_d && g_raw, "composite_backward: null pointer");
+  NB_CHECK_ARG(n_samples >= 1 && n_samples <= 32 * kMaxPer, "composite_backward: n_samples=%d out of range", n_samples);
+  NB_CHECK_ARG(n_rays >= 0, "composite_backward: negative n_rays");
+  if (n_rays == 0) return 0;
+  composite_backward_kernel<<<ceil_div(n_rays, kCompWarps), kCompWarps * 32, 0, (cudaStream_t)stream>>>(
+      raw, z_vals, rays_d, n_rays, n_samples, white_bkgd, g_rgb_map, g_acc_map, g_depth_map, g_weights, g_raw);
+  NB_LAUNCH_OK("composite_backward_kernel");
+  return 0;
+}

@@ -1,0 +1,135 @@
+// a8 occupancy-grid empty-space skipping.
+// Reference: volume_renderer.py:830-873 (grid), :992-1007 (_is_empty_space), :1009-1087
+// (_sample_coarse_with_ess), :963-985 (_update_occupancy_grid).
+//
+// Intended per-ray semantics of :1037-1077 (the reference writes through a stride-0 expand()ed
+// view so all rays of a chunk alias one row -- SURVEY 8a8; that aliasing is NOT reproduced, the
+// oracle restates both).  Byte/index work, HBM/L2-bound: 64 grid lookups (1 B each, 2 MB grid
+// stays in L2) + 256 B of z per ray.
+#include "common.cuh"
+
+namespace nb {
+
+constexpr int kEssWarps = 8;
+constexpr int kEssMaxS = 256;
+
+__device__ __forceinline__ int grid_index(float p, int res) {
+  // :996-1000: ((p - min) / (max - min)).clamp(0,1) * (res-1) -> long (truncation) -> clamp
+  float n = __fdiv_rn(__fsub_rn(p, -2.0f), __fsub_rn(2.0f, -2.0f));
+  n = fminf(fmaxf(n, 0.f), 1.f);
+  int c = (int)__fmul_rn(n, (float)(res - 1));
+  return min(max(c, 0), res - 1);
+}
+
+__global__ void __launch_bounds__(kEssWarps * 32)
+ess_resample_kernel(const uint8_t* __restrict__ grid, int res, const float* __restrict__ rays_o,
+                    const float* __restrict__ rays_d, int n_rays, int S, float* __restrict__ z_vals,
+                    int32_t* __restrict__ n_empty_out) {
+  __shared__ float s_keep[kEssWarps][kEssMaxS];
+  __shared__ float s_z[kEssWarps][kEssMaxS];
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int ray = blockIdx.x * kEssWarps + warp;
+  if (ray >= n_rays) return;
+  float o[3], d[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { o[c] = rays_o[(size_t)ray * 3 + c]; d[c] = rays_d[(size_t)ray * 3 + c]; }
+  float* zrow = z_vals + (size_t)ray * S;
+  float* keep = s_keep[warp];
+  float* zs = s_z[warp];
+  // pass 1: occupancy of every sample, ordered compaction of the occupied z's
+  int n_keep = 0;
+  for (int base = 0; base < S; base += 32) {
+    int i = base + lane;
+    bool occ = false;
+    float z = 0.f;
+    if (i < S) {
+      z = zrow[i];
+      zs[i] = z;
+      int gx = grid_index(__fadd_rn(o[0], __fmul_rn(d[0], z)), res);
+      int gy = grid_index(__fadd_rn(o[1], __fmul_rn(d[1], z)), res);
+      int gz = grid_index(__fadd_rn(o[2], __fmul_rn(d[2], z)), res);
+      occ = grid[((size_t)gx * res + gy) * res + gz] != 0;
+    }
+    unsigned m = __ballot_sync(0xffffffffu, occ);
+    if (occ) keep[n_keep + __popc(m & ((1u << lane) - 1))] = z;
+    n_keep += __popc(m);
+  }
+  __syncwarp();
+  int n_empty = S - n_keep;
+  if (n_empty_out && lane == 0) n_empty_out[ray] = n_empty;
+  // empty_ratios > 0.5 (:1031-1033), and at least one occupied sample (:1045)
+  if (!((float)n_empty / (float)S > 0.5f) || n_keep == 0) return;
+  int n_add = S - n_keep;
+  float lo = keep[0], hi = keep[n_keep - 1];  // occupied z's are ascending
+  float step = n_add > 1 ? __fdiv_rn(__fsub_rn(hi, lo), (float)(n_add - 1)) : 0.f;
+  // merged position of kept[i] = i + #added < kept[i]; of added[j] = j + #kept <= added[j]
+  auto added = [&](int j) {  // torch.linspace(lo, hi, n_add)
+    if (n_add == 1) return lo;
+    return (j < n_add / 2) ? __fadd_rn(lo, __fmul_rn(step, (float)j))
+                           : __fsub_rn(hi, __fmul_rn(step, (float)(n_add - 1 - j)));
+  };
+  for (int i = lane; i < n_keep; i += 32) {
+    float x = keep[i];
+    int l = 0, h = n_add;
+    while (l < h) { int mid = (l + h) >> 1; if (added(mid) < x) l = mid + 1; else h = mid; }
+    zrow[i + l] = x;
+  }
+  for (int j = lane; j < n_add; j += 32) {
+    float x = added(j);
+    int l = 0, h = n_keep;
+    while (l < h) { int mid = (l + h) >> 1; if (keep[mid] <= x) l = mid + 1; else h = mid; }
+    zrow[j + l] = x;
+  }
+}
+
+__global__ void ess_update_kernel(uint8_t* __restrict__ grid, int res, const float* __restrict__ rays_o,
+                                  const float* __restrict__ rays_d, const float* __restrict__ z_vals,
+                                  const float* __restrict__ raw, const float* __restrict__ weights,
+                                  long long total, int S, int use_origin) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  if (!(weights[idx] > 1e-4f)) return;                 // :1149
+  if (!(fmaxf(raw[idx * 4 + 3], 0.f) > 0.01f)) return;  // :976-977
+  long long ray = idx / S;
+  float z = z_vals[idx];
+  int g[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float p = __fmul_rn(rays_d[ray * 3 + c], z);       // :1151 -- origin omitted in the reference
+    if (use_origin) p = __fadd_rn(rays_o[ray * 3 + c], p);
+    g[c] = grid_index(p, res);
+  }
+  grid[((size_t)g[0] * res + g[1]) * res + g[2]] = 1;
+}
+
+}  // namespace nb
+
+using namespace nb;
+
+extern "C" int nerfb200_ess_resample(const uint8_t* grid, int res, const float* rays_o, const float* rays_d,
+                                     int n_rays, int n_samples, float* z_vals, int32_t* n_empty, void* stream) {
+  NB_CHECK_ARG(grid && rays_o && rays_d && z_vals, "ess_resample: null pointer");
+  NB_CHECK_ARG(res >= 1 && res <= 1024, "ess_resample: bad grid resolution %d", res);
+  NB_CHECK_ARG(n_samples >= 1 && n_samples <= kEssMaxS, "ess_resample: n_samples=%d out of range", n_samples);
+  NB_CHECK_ARG(n_rays >= 0, "ess_resample: negative n_rays");
+  if (n_rays == 0) return 0;
+  ess_resample_kernel<<<ceil_div(n_rays, kEssWarps), kEssWarps * 32, 0, (cudaStream_t)stream>>>(
+      grid, res, rays_o, rays_d, n_rays, n_samples, z_vals, n_empty);
+  NB_LAUNCH_OK("ess_resample_kernel");
+  return 0;
+}
+
+extern "C" int nerfb200_ess_update(uint8_t* grid, int res, const float* rays_o, const float* rays_d,
+                                   const float* z_vals, const float* raw, const float* weights, int n_rays,
+                                   int n_samples, int use_origin, void* stream) {
+  NB_CHECK_ARG(grid && rays_d && z_vals && raw && weights, "ess_update: null pointer");
+  NB_CHECK_ARG(!use_origin || rays_o, "ess_update: use_origin needs rays_o");
+  NB_CHECK_ARG(res >= 1 && res <= 1024, "ess_update: bad grid resolution %d", res);
+  NB_CHECK_ARG(n_rays >= 0 && n_samples >= 1, "ess_update: bad sizes");
+  if (n_rays == 0) return 0;
+  long long total = (long long)n_rays * n_samples;
+  ess_update_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(grid, res, rays_o, rays_d, z_vals, raw,
+                                                                            weights, total, n_samples, use_origin);
+  NB_LAUNCH_OK("ess_update_kernel");
+  return 0;
+}

@@ -1,0 +1,109 @@
+// Weight repacking: nn.Linear fp32 state_dict tensors (network.py:22-47, layout frozen) ->
+// the streaming layouts of mlp_layout.cuh.  Re-run after every optimizer step.
+#include <cuda_bf16.h>
+
+#include "mlp_layout.cuh"
+
+namespace nb {
+
+struct StageTable {
+  int f32_off[kStages];
+  int bf16_off[kStages];
+};
+
+__device__ __forceinline__ const float* tensor_w(const nerfb200_mlp_weights& w, int t) {
+  return t < 8 ? w.pts_w[t] : (t == 8 ? w.feature_w : w.views_w);
+}
+__device__ __forceinline__ const float* stage_bias(const nerfb200_mlp_weights& w, int s) {
+  return s < 8 ? w.pts_b[s] : (s == 8 ? w.feature_b : w.views_b);
+}
+
+__device__ __forceinline__ void pack_tail(const nerfb200_mlp_weights& w, float* tail, int i) {
+  // i in [0, kTailFloats)
+  float v = 0.f;
+  if (i < kTailAlphaW) {
+    int s = i / 256, n = i % 256;
+    if (n < stage_n(s)) v = stage_bias(w, s)[n];
+  } else if (i < kTailAlphaB) {
+    v = w.alpha_w[i - kTailAlphaW];
+  } else if (i < kTailRgbW) {
+    v = (i == kTailAlphaB) ? w.alpha_b[0] : 0.f;
+  } else if (i < kTailRgbB) {
+    v = w.rgb_w[i - kTailRgbW];
+  } else {
+    int j = i - kTailRgbB;
+    v = j < 3 ? w.rgb_b[j] : 0.f;
+  }
+  tail[i] = v;
+}
+
+__global__ void pack_f32_kernel(nerfb200_mlp_weights w, StageTable tab, float* __restrict__ dst) {
+  int s = blockIdx.y;
+  int K = stage_k(s), N = stage_n(s);
+  if (s == kStages) {  // tail
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kTailFloats; i += gridDim.x * blockDim.x)
+      pack_tail(w, dst + kF32BiasOff, i);
+    return;
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < K * N; i += gridDim.x * blockDim.x) {
+    int k = i / N, n = i % N;
+    SrcRef r;
+    float v = 0.f;
+    if (stage_src(s, k, &r)) v = tensor_w(w, r.tensor)[(size_t)n * tensor_in_features(r.tensor) + r.col];
+    dst[tab.f32_off[s] + i] = v;
+  }
+}
+
+__global__ void pack_bf16_kernel(nerfb200_mlp_weights w, StageTable tab, unsigned char* __restrict__ dst) {
+  int s = blockIdx.y;
+  if (s == kStages) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kTailFloats; i += gridDim.x * blockDim.x)
+      pack_tail(w, reinterpret_cast<float*>(dst + kBf16TailOff), i);
+    return;
+  }
+  int N = stage_n(s), K = stage_k(s), chunks = stage_chunks(s);
+  int total = chunks * N * 64;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int c = i / (N * 64);
+    int n = (i / 64) % N;
+    int kk = i % 64;
+    int k = c * 64 + kk;
+    SrcRef r;
+    float v = 0.f;
+    if (k < K && stage_src(s, k, &r)) v = tensor_w(w, r.tensor)[(size_t)n * tensor_in_features(r.tensor) + r.col];
+    size_t off = (size_t)tab.bf16_off[s] + (size_t)c * (N * 128) + (size_t)n * 128 +
+                 (size_t)(((kk >> 3) ^ (n & 7)) << 4) + (size_t)(kk & 7) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(dst + off) = __float2bfloat16_rn(v);
+  }
+}
+
+}  // namespace nb
+
+using namespace nb;
+
+extern "C" size_t nerfb200_packed_weights_bytes(int mode) {
+  if (mode == NERFB200_MODE_FP32) return (size_t)kF32TotalFloats * 4;
+  if (mode == NERFB200_MODE_BF16) return (size_t)kBf16TotalBytes;
+  return 0;
+}
+
+extern "C" int nerfb200_pack_weights(const nerfb200_mlp_weights* w, int mode, void* packed, void* stream) {
+  NB_CHECK_ARG(w && packed, "pack_weights: null pointer");
+  NB_CHECK_ARG(mode == NERFB200_MODE_FP32 || mode == NERFB200_MODE_BF16, "pack_weights: unknown mode %d", mode);
+  NB_CHECK_ARG(((uintptr_t)packed & 1023) == 0, "pack_weights: packed buffer must be 1024-byte aligned");
+  for (int i = 0; i < 8; ++i) NB_CHECK_ARG(w->pts_w[i] && w->pts_b[i], "pack_weights: null pts_linears.%d", i);
+  NB_CHECK_ARG(w->views_w && w->views_b && w->feature_w && w->feature_b && w->alpha_w && w->alpha_b && w->rgb_w &&
+                   w->rgb_b, "pack_weights: null head tensor");
+  StageTable tab;
+  for (int s = 0; s < kStages; ++s) {
+    tab.f32_off[s] = f32_wt_off(s);
+    tab.bf16_off[s] = bf16_stage_off(s);
+  }
+  dim3 grid(64, kStages + 1);
+  if (mode == NERFB200_MODE_FP32)
+    pack_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*w, tab, (float*)packed);
+  else
+    pack_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*w, tab, (unsigned char*)packed);
+  NB_LAUNCH_OK("pack_weights_kernel");
+  return 0;
+}

@@ -1,0 +1,150 @@
+"""Kernel-level Python wrappers over the C ABI (one function per entry point).
+
+Inputs/outputs are CUDA tensors; every wrapper allocates its outputs with torch and
+enqueues the kernel on torch's current stream.  No wrapper has a non-CUDA code path.
+"""
+import ctypes as C
+
+import torch
+
+from . import lib as L
+
+F32 = torch.float32
+
+
+def _f(t, device=None):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise L.NerfB200Error("libnerfb200 needs CUDA tensors (got %s); there is no CPU path" % t.device)
+    return t.to(F32).contiguous()
+
+
+def raygen(pose, intrinsics, H, W):
+    pose, intrinsics = _f(pose.reshape(4, 4)), _f(intrinsics.reshape(3, 3))
+    ro = torch.empty((H * W, 3), device=pose.device)
+    rd = torch.empty((H * W, 3), device=pose.device)
+    L.check(L.load().nerfb200_raygen(L.dev(pose), L.dev(intrinsics), H, W, L.dev(ro), L.dev(rd), L.stream_ptr()),
+            "raygen")
+    return ro, rd
+
+
+def sample_coarse(z_table, n_rays, perturb=False, seed=0):
+    z_table = _f(z_table)
+    S = z_table.numel()
+    z = torch.empty((n_rays, S), device=z_table.device)
+    L.check(L.load().nerfb200_sample_coarse(L.dev(z_table), n_rays, S, int(perturb), seed, L.dev(z),
+                                           L.stream_ptr()), "sample_coarse")
+    return z
+
+
+class PackedWeights:
+    """1024-byte aligned device buffer holding one model's weights in a kernel layout."""
+
+    def __init__(self, tensors, mode, device):
+        """tensors: dict name -> tensor with the 24 per-model names of network.py (no prefix)."""
+        lib = L.load()
+        self.mode = mode
+        nbytes = lib.nerfb200_packed_weights_bytes(mode)
+        self.buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+        self.base = (self.buf.data_ptr() + 1023) & ~1023
+        keep = {k: _f(v.detach().to(device)) for k, v in tensors.items()}
+        w = L.MlpWeights()
+        for i in range(8):
+            w.pts_w[i] = keep["pts_linears.%d.weight" % i].data_ptr()
+            w.pts_b[i] = keep["pts_linears.%d.bias" % i].data_ptr()
+        w.views_w, w.views_b = keep["views_linears.0.weight"].data_ptr(), keep["views_linears.0.bias"].data_ptr()
+        w.feature_w, w.feature_b = keep["feature_linear.weight"].data_ptr(), keep["feature_linear.bias"].data_ptr()
+        w.alpha_w, w.alpha_b = keep["alpha_linear.weight"].data_ptr(), keep["alpha_linear.bias"].data_ptr()
+        w.rgb_w, w.rgb_b = keep["rgb_linear.weight"].data_ptr(), keep["rgb_linear.bias"].data_ptr()
+        L.check(lib.nerfb200_pack_weights(C.byref(w), mode, C.c_void_p(self.base), L.stream_ptr()), "pack_weights")
+        torch.cuda.current_stream().synchronize()  # `keep` may be freed after this returns
+
+    @property
+    def ptr(self):
+        return C.c_void_p(self.base)
+
+
+def pack_from_state_dict(sd, prefix, mode, device):
+    return PackedWeights({k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}, mode, device)
+
+
+def mlp_forward(packed, rays_o, rays_d, z_vals):
+    rays_o, rays_d, z_vals = _f(rays_o), _f(rays_d), _f(z_vals)
+    n, S = z_vals.shape
+    raw = torch.empty((n, S, 4), device=z_vals.device)
+    L.check(L.load().nerfb200_mlp_forward(packed.ptr, packed.mode, L.dev(rays_o), L.dev(rays_d), L.dev(z_vals), n, S,
+                                         L.dev(raw), L.stream_ptr()), "mlp_forward")
+    return raw
+
+
+def composite_forward(raw, z_vals, rays_d, variant=L.COMPOSITE_PLAIN, ert_threshold=0.01, white_bkgd=True,
+                      compat_chunk=2048, want_weights=True):
+    raw, z_vals, rays_d = _f(raw), _f(z_vals), _f(rays_d)
+    n, S = z_vals.shape
+    d = raw.device
+    rgb, disp, acc, depth = (torch.empty((n, 3), device=d), torch.empty(n, device=d), torch.empty(n, device=d),
+                             torch.empty(n, device=d))
+    w = torch.empty((n, S), device=d) if want_weights else None
+    L.check(L.load().nerfb200_composite_forward(L.dev(raw), L.dev(z_vals), L.dev(rays_d), n, S, variant,
+                                               ert_threshold, int(white_bkgd), compat_chunk, L.dev(rgb), L.dev(disp),
+                                               L.dev(acc), L.dev(depth), L.dev(w), L.stream_ptr()),
+            "composite_forward")
+    return rgb, disp, acc, w, depth   # same order as _raw2outputs (:357)
+
+
+def composite_backward(raw, z_vals, rays_d, g_rgb=None, g_acc=None, g_depth=None, g_weights=None, white_bkgd=True):
+    raw, z_vals, rays_d = _f(raw), _f(z_vals), _f(rays_d)
+    n, S = z_vals.shape
+    g_raw = torch.empty_like(raw)
+    L.check(L.load().nerfb200_composite_backward(L.dev(raw), L.dev(z_vals), L.dev(rays_d), n, S, int(white_bkgd),
+                                                L.dev(_f(g_rgb)), L.dev(_f(g_acc)), L.dev(_f(g_depth)),
+                                                L.dev(_f(g_weights)), L.dev(g_raw), L.stream_ptr()),
+            "composite_backward")
+    return g_raw
+
+
+def sample_from_cdf(cdf, bins, u):
+    cdf, bins, u = _f(cdf), _f(bins), _f(u)
+    n, nb = cdf.shape
+    per_ray = int(u.dim() == 2)
+    n_u = u.shape[-1]
+    samples = torch.empty((n, n_u), device=cdf.device)
+    inds = torch.empty((n, n_u), dtype=torch.int32, device=cdf.device)
+    L.check(L.load().nerfb200_sample_from_cdf(L.dev(cdf), L.dev(bins), L.dev(u), per_ray, n, nb, n_u, L.dev(samples),
+                                             L.dev(inds), L.stream_ptr()), "sample_from_cdf")
+    return samples, inds
+
+
+def sample_pdf_merge(z_coarse, weights, u, want_aux=True):
+    z_coarse, weights, u = _f(z_coarse), _f(weights), _f(u)
+    n, S = z_coarse.shape
+    per_ray = int(u.dim() == 2)
+    n_u = u.shape[-1]
+    d = z_coarse.device
+    z_all = torch.empty((n, S + n_u), device=d)
+    zs = torch.empty((n, n_u), device=d) if want_aux else None
+    inds = torch.empty((n, n_u), dtype=torch.int32, device=d) if want_aux else None
+    cdf = torch.empty((n, S - 1), device=d) if want_aux else None
+    L.check(L.load().nerfb200_sample_pdf_merge(L.dev(z_coarse), L.dev(weights), L.dev(u), per_ray, n, S, n_u,
+                                              L.dev(z_all), L.dev(zs), L.dev(inds), L.dev(cdf), L.stream_ptr()),
+            "sample_pdf_merge")
+    return z_all, zs, inds, cdf
+
+
+def ess_resample(grid_u8, rays_o, rays_d, z_vals):
+    rays_o, rays_d = _f(rays_o), _f(rays_d)
+    z = _f(z_vals).clone()
+    n, S = z.shape
+    n_empty = torch.empty(n, dtype=torch.int32, device=z.device)
+    L.check(L.load().nerfb200_ess_resample(L.dev(grid_u8, torch.uint8), grid_u8.shape[0], L.dev(rays_o), L.dev(rays_d),
+                                          n, S, L.dev(z), L.dev(n_empty), L.stream_ptr()), "ess_resample")
+    return z, n_empty
+
+
+def ess_update(grid_u8, rays_o, rays_d, z_vals, raw, weights, use_origin=False):
+    n, S = z_vals.shape
+    L.check(L.load().nerfb200_ess_update(L.dev(grid_u8, torch.uint8), grid_u8.shape[0], L.dev(_f(rays_o)),
+                                        L.dev(_f(rays_d)), L.dev(_f(z_vals)), L.dev(_f(raw)), L.dev(_f(weights)), n, S,
+                                        int(use_origin), L.stream_ptr()), "ess_update")
+    return grid_u8

@@ -1,0 +1,315 @@
+"""Drop-in `Renderer` for the learning-NeRF scaffold, backed by libnerfb200 (sm_100a).
+
+Mirrors the public surface of the reference's
+src/models/nerf/renderer/volume_renderer.py `Renderer`:
+  * `Renderer(net)` -- same cfg keys read (:31-59), same public attributes;
+  * `render(batch) -> dict` -- same keys / shapes / dtypes (:176,195-198,207-216):
+    rgb_map_0 [H,W,3], disp_map_0/acc_map_0/depth_map_0 [H,W] and, when
+    N_importance > 0, rgb_map/disp_map/acc_map/depth_map;
+  * `_initialize_occupancy_grid()` and the `occupancy_grid` attribute (:830-873).
+Extension: `render_rays(rays_o, rays_d)` returns the same keys with a leading
+[N] (ray-batch benchmarks / training).
+
+All compute runs in the CUDA library through its C ABI (include/nerfb200.h);
+PyTorch only owns the buffers and the stream.  There is no CPU / eager fallback:
+without a CUDA device or without libnerfb200.so construction fails loudly.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import lib as L
+
+
+class RenderConfig:
+    """Defaults = configs/nerf/lego.yaml:13-27,96-99 + volume_renderer.py:47-54."""
+
+    def __init__(self, **kw):
+        self.N_samples = 64
+        self.N_importance = 128
+        self.chunk_size = 4096
+        self.white_bkgd = 1
+        self.use_viewdirs = True
+        self.lindisp = False
+        self.perturb = 1
+        self.raw_noise_std = 0
+        self.near = 2.0
+        self.far = 6.0
+        self.enable_ess = True
+        self.enable_ert = True
+        self.ert_threshold = 0.01
+        self.occupancy_grid_resolution = 128
+        for k, v in kw.items():
+            if not hasattr(self, k):
+                raise AttributeError("unknown render config key %r" % k)
+            setattr(self, k, v)
+
+    @classmethod
+    def from_scaffold_cfg(cls, cfg):
+        """Read the same keys the reference reads from its yacs cfg (:31-54)."""
+        rc = cls()
+        ta = cfg.task_arg
+        for k in ("N_samples", "N_importance", "chunk_size", "white_bkgd", "use_viewdirs", "lindisp",
+                  "perturb", "raw_noise_std"):
+            setattr(rc, k, getattr(ta, k))
+        rc.near = getattr(cfg, "near", 2.0)
+        rc.far = getattr(cfg, "far", 6.0)
+        rc.enable_ess = getattr(cfg, "enable_ess", True)
+        rc.enable_ert = getattr(cfg, "enable_ert", True)
+        rc.ert_threshold = getattr(cfg, "ert_threshold", 0.05)
+        rc.occupancy_grid_resolution = getattr(cfg, "occupancy_grid_resolution", 128)
+        return rc
+
+
+def _model_weight_struct(model):
+    """nerfb200_mlp_weights for one NeRF module (network.py:22-47 names)."""
+    keep = []
+
+    def p(t):
+        t = t.detach()
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            t = t.float().contiguous()
+        if not t.is_cuda:
+            raise L.NerfB200Error("network parameters must live on a CUDA device (got %s)" % t.device)
+        keep.append(t)
+        return t.data_ptr()
+
+    w = L.MlpWeights()
+    for i in range(8):
+        w.pts_w[i] = p(model.pts_linears[i].weight)
+        w.pts_b[i] = p(model.pts_linears[i].bias)
+    w.views_w, w.views_b = p(model.views_linears[0].weight), p(model.views_linears[0].bias)
+    w.feature_w, w.feature_b = p(model.feature_linear.weight), p(model.feature_linear.bias)
+    w.alpha_w, w.alpha_b = p(model.alpha_linear.weight), p(model.alpha_linear.bias)
+    w.rgb_w, w.rgb_b = p(model.rgb_linear.weight), p(model.rgb_linear.bias)
+    expect = {0: (256, 63), 5: (256, 319)}
+    for i in range(8):
+        shape = tuple(model.pts_linears[i].weight.shape)
+        if shape != expect.get(i, (256, 256)):
+            raise L.NerfB200Error("pts_linears.%d.weight has shape %s; the kernels are specialised to the "
+                                  "lego.yaml architecture (W=256, D=8, skips=[4], PE 10/4)" % (i, shape))
+    if tuple(model.views_linears[0].weight.shape) != (128, 283):
+        raise L.NerfB200Error("views_linears.0.weight must be (128, 283)")
+    return w, keep
+
+
+class Renderer:
+    MODES = {"fp32": L.MODE_FP32, "bf16": L.MODE_BF16}
+
+    def __init__(self, net, cfg=None, mode=None, ref_compat=True):
+        """net: a Network with `.model`, `.model_fine` (reference network.py or ours).
+
+        cfg: RenderConfig, a scaffold yacs cfg, or None (then `src.config.cfg` when the scaffold is
+        importable, else lego.yaml defaults).  mode: 'bf16' (tcgen05 performance mode) or 'fp32'
+        (parity mode).  ref_compat: reproduce the reference's ERT chunk quirk (:1115-1123).
+        """
+        self.lib = L.load()
+        if not torch.cuda.is_available():
+            raise L.NerfB200Error("no CUDA device: the B200 renderer has no CPU fallback")
+        if cfg is None:
+            try:
+                from src.config import cfg as scaffold_cfg  # inside the learning-NeRF scaffold
+                cfg = RenderConfig.from_scaffold_cfg(scaffold_cfg)
+            except Exception:
+                cfg = RenderConfig()
+        elif not isinstance(cfg, RenderConfig):
+            cfg = RenderConfig.from_scaffold_cfg(cfg)
+        self.net = net
+        self.N_samples = int(cfg.N_samples)
+        self.N_importance = int(cfg.N_importance)
+        self.chunk_size = int(cfg.chunk_size)
+        self.white_bkgd = bool(cfg.white_bkgd)
+        self.use_viewdirs = bool(cfg.use_viewdirs)
+        self.lindisp = bool(cfg.lindisp)
+        self.perturb = cfg.perturb
+        self.raw_noise_std = cfg.raw_noise_std
+        self.near, self.far = float(cfg.near), float(cfg.far)
+        self.enable_ess = bool(cfg.enable_ess)
+        self.enable_ert = bool(cfg.enable_ert)
+        self.ert_threshold = float(cfg.ert_threshold)
+        self.occupancy_grid_resolution = int(cfg.occupancy_grid_resolution)
+        self.embed_fn = getattr(net, "embed_fn", None)
+        self.embeddirs_fn = getattr(net, "embeddirs_fn", None)
+        self.coarse_model = net.model
+        self.fine_model = net.model_fine
+        dev = next(net.model.parameters()).device
+        if dev.type != "cuda":
+            raise L.NerfB200Error("network parameters are on %s; move the network to a CUDA device" % dev)
+        self.device = dev
+        if not self.use_viewdirs:
+            raise L.NerfB200Error("use_viewdirs=False is not implemented by the B200 path")
+        self.mode = mode or "bf16"
+        if self.mode not in self.MODES:
+            raise ValueError("mode must be 'bf16' or 'fp32'")
+        self.ref_compat = bool(ref_compat)
+        self.use_cuda_kernels = True
+        self.seed = 0
+        self.occupancy_grid = None
+        self.grid_update_counter = 0
+        self.grid_update_interval = 500
+        self._packed = {}
+        self._ws = None
+        self._tables = {}
+        self._host = None
+        self._initialize_occupancy_grid()
+
+    # ------------------------------------------------------------------ occupancy grid (a8)
+    def _initialize_occupancy_grid(self, random_mask=None):
+        """volume_renderer.py:830-873: sphere(r<=1.2 in [-1,1]^3) OR rand<0.1 (bool [R,R,R])."""
+        if not self.enable_ess:
+            return
+        res = self.occupancy_grid_resolution
+        g = torch.stack(torch.meshgrid([torch.arange(res, device=self.device)] * 3, indexing="ij"), -1).float()
+        g = (g / (res - 1)) * 2.0 - 1.0
+        sphere = torch.norm(g, dim=-1) <= 1.2
+        if random_mask is None:
+            random_mask = torch.rand((res, res, res), device=self.device) < 0.1
+        self.occupancy_grid = sphere | random_mask.to(self.device)
+        self.scene_bbox_min = torch.tensor([-2.0, -2.0, -2.0], device=self.device)
+        self.scene_bbox_max = torch.tensor([2.0, 2.0, 2.0], device=self.device)
+        self.ess_skip_threshold = 0.5
+        self.grid_update_interval = 500
+
+    # ------------------------------------------------------------------ plumbing
+    def _packed_weights(self, which):
+        model = self.coarse_model if which == "coarse" else self.fine_model
+        mode = self.MODES[self.mode]
+        key = tuple((p.data_ptr(), p._version) for p in model.parameters()) + (mode,)
+        ent = self._packed.get(which)
+        if ent is not None and ent[0] == key:
+            return ent[1]
+        nbytes = self.lib.nerfb200_packed_weights_bytes(mode)
+        buf = ent[1] if ent is not None and ent[1].numel() == nbytes + 1024 else \
+            torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
+        w, keep = _model_weight_struct(model)
+        base = (buf.data_ptr() + 1023) & ~1023
+        L.check(self.lib.nerfb200_pack_weights(C.byref(w), mode, C.c_void_p(base), L.stream_ptr()), "pack_weights")
+        del keep
+        self._packed[which] = (key, buf, base)
+        return buf
+
+    def _packed_ptr(self, which):
+        self._packed_weights(which)
+        return C.c_void_p(self._packed[which][2])
+
+    def _table(self, name):
+        """z table (:218-226) and eval-mode u table (:250) evaluated with torch CPU ops, as the oracle does."""
+        key = (name, self.N_samples, self.N_importance, self.near, self.far, self.lindisp)
+        t = self._tables.get(key)
+        if t is None:
+            if name == "z":
+                tv = torch.linspace(0., 1., steps=self.N_samples)
+                if not self.lindisp:
+                    t = self.near * (1. - tv) + self.far * tv
+                else:
+                    t = 1. / (1. / self.near * (1. - tv) + 1. / self.far * tv)
+            else:
+                t = torch.linspace(0., 1., steps=max(self.N_importance, 1))
+            t = t.to(self.device).contiguous()
+            self._tables[key] = t
+        return t
+
+    def _params(self, training, n_rays):
+        if self.raw_noise_std and float(self.raw_noise_std) > 0:
+            raise L.NerfB200Error("raw_noise_std > 0 is not implemented (lego.yaml:23 uses 0)")
+        p = L.RenderParams()
+        p.n_samples, p.n_importance = self.N_samples, self.N_importance
+        p.mode = self.MODES[self.mode]
+        if self.enable_ert:
+            p.variant = L.COMPOSITE_ERT_COMPAT if self.ref_compat else L.COMPOSITE_ERT
+        else:
+            p.variant = L.COMPOSITE_PLAIN
+        p.white_bkgd = int(self.white_bkgd)
+        p.perturb = int(float(self.perturb) > 0)
+        p.u_per_ray = int(bool(training))   # :247-251 keys on net.training
+        p.compat_chunk = 2048               # :147 ray_chunk_size
+        p.ert_threshold = self.ert_threshold
+        self.seed += 1
+        p.seed = (self.seed * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        if self.enable_ess and self.occupancy_grid is not None:
+            self._grid_u8 = self.occupancy_grid.to(torch.uint8).contiguous()
+            p.occupancy_grid = self._grid_u8.data_ptr()
+            p.grid_res = self.occupancy_grid.shape[0]
+        return p
+
+    def _workspace(self, nbytes):
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    # ------------------------------------------------------------------ public API
+    @torch.no_grad()
+    def render_rays(self, rays_o, rays_d):
+        """rays_o, rays_d: [N,3] fp32 CUDA.  Returns the reference's dict keys with leading [N]."""
+        rays_o = rays_o.to(self.device, torch.float32).contiguous()
+        rays_d = rays_d.to(self.device, torch.float32).contiguous()
+        n = rays_o.shape[0]
+        training = bool(getattr(self.net, "training", False))
+        p = self._params(training, n)
+        out = {"rgb_map_0": torch.empty((n, 3), device=self.device), "disp_map_0": torch.empty(n, device=self.device),
+               "acc_map_0": torch.empty(n, device=self.device), "depth_map_0": torch.empty(n, device=self.device)}
+        mc = L.Maps(L.dev(out["rgb_map_0"]), L.dev(out["disp_map_0"]), L.dev(out["acc_map_0"]), L.dev(out["depth_map_0"]))
+        mf, u = None, None
+        if self.N_importance > 0:
+            for k in ("rgb_map", "disp_map", "acc_map", "depth_map"):
+                out[k] = torch.empty((n, 3) if k == "rgb_map" else n, device=self.device)
+            mf = L.Maps(L.dev(out["rgb_map"]), L.dev(out["disp_map"]), L.dev(out["acc_map"]), L.dev(out["depth_map"]))
+            u = torch.rand((n, self.N_importance), device=self.device) if training else self._table("u")
+        ws_bytes = self.lib.nerfb200_render_workspace_bytes(n, C.byref(p))
+        ws = self._workspace(ws_bytes)
+        L.check(self.lib.nerfb200_render_rays(
+            self._packed_ptr("coarse"), self._packed_ptr("fine") if self.N_importance > 0 else None,
+            L.dev(rays_o), L.dev(rays_d), n, L.dev(self._table("z")), L.dev(u) if u is not None else None,
+            C.byref(p), L.dev(ws), ws.numel(), C.byref(mc), C.byref(mf) if mf is not None else None,
+            L.stream_ptr()), "render_rays")
+        return out
+
+    @torch.no_grad()
+    def render(self, batch):
+        """Same contract as the reference's Renderer.render(batch) (volume_renderer.py:89-216)."""
+        H, W = int(batch["H"]), int(batch["W"])
+        pose = batch["pose"].squeeze(0).to(self.device, torch.float32).contiguous()
+        K = batch["intrinsics"].squeeze(0).to(self.device, torch.float32).contiguous()
+        rays_o = torch.empty((H * W, 3), device=self.device)
+        rays_d = torch.empty((H * W, 3), device=self.device)
+        L.check(self.lib.nerfb200_raygen(L.dev(pose), L.dev(K), H, W, L.dev(rays_o), L.dev(rays_d), L.stream_ptr()),
+                "raygen")
+        out = self.render_rays(rays_o, rays_d)
+        for k in out:
+            out[k] = out[k].view(H, W, 3) if k in ("rgb_map", "rgb_map_0") else out[k].view(H, W)
+        return out
+
+    @torch.no_grad()
+    def render_host(self, batch):
+        """End-to-end entry with HOST buffers: pose/intrinsics are read from host memory, the eight maps
+        are returned in pinned host tensors; copies and a stream sync happen inside the C call."""
+        H, W = int(batch["H"]), int(batch["W"])
+        n = H * W
+        pose = batch["pose"].reshape(4, 4).to("cpu", torch.float32).contiguous()
+        K = batch["intrinsics"].reshape(3, 3).to("cpu", torch.float32).contiguous()
+        p = self._params(False, n)
+        if self._host is None or self._host[0] != n:
+            mk = lambda *s: torch.empty(s, dtype=torch.float32).pin_memory()
+            self._host = (n, {k: mk(n, 3) if k.startswith("rgb") else mk(n) for k in
+                              ("rgb_map_0", "disp_map_0", "acc_map_0", "depth_map_0", "rgb_map", "disp_map",
+                               "acc_map", "depth_map")})
+        h = self._host[1]
+        mc = L.Maps(L.ptr(h["rgb_map_0"]), L.ptr(h["disp_map_0"]), L.ptr(h["acc_map_0"]), L.ptr(h["depth_map_0"]))
+        mf = L.Maps(L.ptr(h["rgb_map"]), L.ptr(h["disp_map"]), L.ptr(h["acc_map"]), L.ptr(h["depth_map"]))
+        ws_bytes = self.lib.nerfb200_render_image_workspace_bytes(H, W, C.byref(p))
+        ws = self._workspace(ws_bytes)
+        fine = self.N_importance > 0
+        L.check(self.lib.nerfb200_render_image_host(
+            self._packed_ptr("coarse"), self._packed_ptr("fine") if fine else None, L.ptr(pose), L.ptr(K), H, W,
+            L.dev(self._table("z")), L.dev(self._table("u")), C.byref(p), L.dev(ws), ws.numel(), C.byref(mc),
+            C.byref(mf) if fine else None, L.stream_ptr()), "render_image_host")
+        keys = list(h) if fine else [k for k in h if k.endswith("_0")]
+        return {k: (h[k].view(H, W, 3) if k.startswith("rgb") else h[k].view(H, W)) for k in keys}
+
+    @property
+    def h2d_bytes_per_image(self):
+        return (16 + 9) * 4
+
+    def d2h_bytes_per_image(self, H, W):
+        return H * W * 6 * 4 * (2 if self.N_importance > 0 else 1)

@@ -1,0 +1,67 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/nerfb200.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "nerfb200.h")).read()
+    return sorted(set(re.findall(r"NERFB200_API[^;]*?\b(nerfb200_\w+)\s*\(", src)))
+
+
+def test_header_declares_expected_entry_points():
+    names = _declared()
+    for must in ("nerfb200_raygen", "nerfb200_sample_coarse", "nerfb200_mlp_forward", "nerfb200_composite_forward",
+                 "nerfb200_composite_backward", "nerfb200_sample_pdf_merge", "nerfb200_sample_from_cdf",
+                 "nerfb200_pack_weights", "nerfb200_ess_resample", "nerfb200_render_rays",
+                 "nerfb200_render_image_host", "nerfb200_get_last_error_string"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    lib = ctypes.CDLL(built_lib)
+    for name in _declared():
+        assert hasattr(lib, name), "symbol %s declared in nerfb200.h but not exported" % name
+
+
+def test_binding_covers_header(built_lib):
+    from nerf_rep_for_test_b200 import lib as L
+    assert sorted(L.SIGNATURES) == _declared()
+    lib = L.load()
+    assert lib.nerfb200_abi_version() == L.ABI_VERSION
+    assert lib.nerfb200_packed_weights_bytes(L.MODE_FP32) > 4 * 590000
+    assert lib.nerfb200_packed_weights_bytes(L.MODE_BF16) > 2 * 590000
+    assert lib.nerfb200_packed_weights_bytes(7) == 0
+
+
+def test_struct_sizes_match_c_layout():
+    from nerf_rep_for_test_b200 import lib as L
+    assert ctypes.sizeof(L.MlpWeights) == 24 * 8
+    assert ctypes.sizeof(L.Maps) == 32
+    assert ctypes.sizeof(L.RenderParams) == 64   # 8 ints, float, pad, u64, ptr, int, pad
+
+
+def test_argument_errors_are_reported_not_fatal(built_lib):
+    """Bad arguments return non-zero + message (never exit()); no GPU needed for these checks."""
+    from nerf_rep_for_test_b200 import lib as L
+    lib = L.load()
+    rc = lib.nerfb200_raygen(None, None, 4, 4, None, None, None)
+    assert rc != 0 and b"null" in lib.nerfb200_get_last_error_string()
+    rc = lib.nerfb200_sample_pdf_merge(ctypes.c_void_p(8), ctypes.c_void_p(8), ctypes.c_void_p(8), 0, 1, 9999, 128,
+                                       ctypes.c_void_p(8), None, None, None, None)
+    assert rc != 0 and b"n_samples" in lib.nerfb200_get_last_error_string()
+    with pytest.raises(L.NerfB200Error):
+        L.check(rc, "sample_pdf_merge")
+
+
+def test_renderer_fails_loudly_without_gpu(built_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from nerf_rep_for_test_b200 import NerfB200Error, Network, Renderer
+    with pytest.raises(NerfB200Error):
+        Renderer(Network(device="cpu"))

@@ -1,0 +1,404 @@
+"""GPU parity tests: every CUDA kernel, called through the C ABI, against the CPU oracle on the
+same seeded inputs and against the golden vectors frozen from the real reference.
+
+Tolerances (BASELINE.json north_star): bin indices bit-exact; rgb/depth/acc within 1e-5 relative
+in fp32 mode (evaluated as rtol 1e-5 + the atol SURVEY 8c' shows plain fp32 rounding needs).
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from oracle import nerf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from nerf_rep_for_test_b200 import lib as L
+    from nerf_rep_for_test_b200 import ops
+    DEV = torch.device("cuda:0")
+
+
+def cuda(x):
+    return torch.as_tensor(x).to(DEV)
+
+
+def bits_equal(a, b):
+    a = torch.nan_to_num(a.detach().cpu().float(), nan=-7.0)
+    b = torch.nan_to_num(torch.as_tensor(b).detach().cpu().float(), nan=-7.0)
+    return torch.equal(a, b)
+
+
+def rel_close(a, b, rtol, atol):
+    a = a.detach().cpu().double()
+    b = torch.as_tensor(b).detach().cpu().double()
+    nan_a, nan_b = torch.isnan(a), torch.isnan(b)
+    assert torch.equal(nan_a, nan_b), "NaN pattern differs"
+    a, b = torch.nan_to_num(a), torch.nan_to_num(b)
+    err = (a - b).abs()
+    bound = atol + rtol * b.abs()
+    bad = err > bound
+    assert not bad.any(), "max err %.3e (bound %.3e) on %d of %d" % (
+        float(err.max()), float(bound[err.argmax()] if err.numel() else 0), int(bad.sum()), err.numel())
+
+
+# ------------------------------------------------------------------------------- a1 rays
+@pytest.mark.parametrize("H,W", [(16, 16), (37, 53), (800, 800)])
+def test_raygen_bit_exact(H, W):
+    rs = np.random.RandomState(H)
+    Q, _ = np.linalg.qr(rs.randn(3, 3))
+    pose = np.eye(4, dtype=np.float32)
+    pose[:3, :3] = Q
+    pose[:3, 3] = [0.3, -3.1, 2.2]
+    for p in (O.LEGO_TEST_POSE0, pose.tolist()):
+        b = O.lego_batch(H, W, p)
+        ro_ref, rd_ref = O.get_rays(H, W, b["pose"][0], b["intrinsics"][0])
+        ro, rd = ops.raygen(cuda(b["pose"]), cuda(b["intrinsics"]), H, W)
+        assert bits_equal(ro, ro_ref)
+        assert bits_equal(rd, rd_ref)
+
+
+# ------------------------------------------------------------------------------- a2 coarse z
+def test_sample_coarse_no_perturb_bit_exact():
+    for n in (1, 7, 2048):
+        z = ops.sample_coarse(cuda(O.coarse_t_table()), n)
+        assert bits_equal(z, O.sample_coarse(n))
+
+
+def test_sample_coarse_perturb_is_stratified():
+    tab = O.coarse_t_table()
+    z = ops.sample_coarse(cuda(tab), 4096, perturb=True, seed=123).cpu()
+    mids = .5 * (tab[1:] + tab[:-1])
+    lower = torch.cat([tab[:1], mids])
+    upper = torch.cat([mids, tab[-1:]])
+    assert bool((z >= lower).all()) and bool((z <= upper).all())
+    assert bool((z[:, 1:] >= z[:, :-1]).all())
+    t = ((z - lower) / (upper - lower))[:, 1:-1]
+    assert abs(float(t.mean()) - 0.5) < 0.01 and 0.07 < float(t.var()) < 0.1    # U(0,1): var 1/12
+    z2 = ops.sample_coarse(cuda(tab), 4096, perturb=True, seed=123).cpu()
+    assert torch.equal(z, z2)                                                      # reproducible
+    assert not torch.equal(z, ops.sample_coarse(cuda(tab), 4096, perturb=True, seed=124).cpu())
+
+
+# ------------------------------------------------------------------------------- a4 sample_pdf
+def _random_weights(n, S, seed, peaked):
+    g = torch.Generator().manual_seed(seed)
+    w = torch.rand(n, S, generator=g)
+    if peaked:
+        w = w ** 8
+        w[:, : S // 3] *= 1e-6
+    w[n // 2] = 0.0           # all-zero weights row -> uniform pdf, denom guard
+    return w
+
+
+@pytest.mark.parametrize("peaked", [False, True])
+def test_sample_from_cdf_indices_bit_exact(peaked):
+    """Given IDENTICAL cdf/u inputs the bin indices and the samples are bit-exact."""
+    n, S = 1000, 64
+    w = _random_weights(n, S, 0, peaked)
+    z = O.sample_coarse(n)
+    t_mid = .5 * (z[..., 1:] + z[..., :-1])
+    cdf = O.pdf_to_cdf(w[..., 1:-1])
+    for u in (O.fine_u_table(128), torch.rand(n, 128, generator=torch.Generator().manual_seed(1)),
+              torch.tensor([0.0, 1.0, 0.5, 1e-9])):
+        uu = u if u.dim() == 2 else u.expand(n, u.shape[0])
+        ref_s, ref_i = O.sample_from_cdf(t_mid.contiguous(), cdf, uu.contiguous())
+        s, i = ops.sample_from_cdf(cuda(cdf), cuda(t_mid.contiguous()), cuda(u))
+        assert torch.equal(i.cpu().long(), ref_i), "bin indices differ"
+        assert bits_equal(s, ref_s)
+
+
+@pytest.mark.parametrize("peaked", [False, True])
+def test_sample_pdf_merge_vs_oracle(peaked):
+    n, S, U = 777, 64, 128
+    w = _random_weights(n, S, 3, peaked)
+    z = O.sample_coarse(n)
+    t_mid = .5 * (z[..., 1:] + z[..., :-1])
+    ref_s, ref_i, ref_cdf = O.sample_fine(t_mid, w[..., 1:-1])
+    ref_all, _ = torch.sort(torch.cat([z, ref_s], -1), -1)
+    z_all, zs, inds, cdf = ops.sample_pdf_merge(cuda(z), cuda(w), cuda(O.fine_u_table(U)))
+    # cdf: fp64 cumsum as torch CPU; only the normaliser's summation order can differ (<= 1 ulp)
+    rel_close(cdf, ref_cdf, 3e-7, 1e-7)
+    mism = (inds.cpu().long() != ref_i)
+    assert mism.float().mean() < 5e-3, "too many index flips: %d" % int(mism.sum())
+    rel_close(zs, ref_s, 1e-6, 1e-6)
+    rel_close(z_all, ref_all, 1e-6, 1e-6)
+    za = z_all.cpu()
+    assert bool((za[:, 1:] >= za[:, :-1]).all()), "merged z not sorted"
+    # the merged row is a permutation of coarse + samples
+    assert torch.equal(torch.sort(torch.cat([z, zs.cpu()], -1), -1)[0], za)
+
+
+def test_sample_pdf_merge_random_u_sorted_permutation():
+    n, S, U = 300, 64, 128
+    w = _random_weights(n, S, 4, True)
+    z = O.sample_coarse(n)
+    u = torch.rand(n, U, generator=torch.Generator().manual_seed(9))
+    z_all, zs, inds, cdf = ops.sample_pdf_merge(cuda(z), cuda(w), cuda(u))
+    ref_s, ref_i = O.sample_from_cdf((.5 * (z[..., 1:] + z[..., :-1])).contiguous(), cdf.cpu(), u)
+    assert torch.equal(inds.cpu().long(), ref_i)            # same cdf in -> same bins out
+    assert bits_equal(zs, ref_s)
+    assert torch.equal(torch.sort(torch.cat([z, zs.cpu()], -1), -1)[0], z_all.cpu())
+
+
+def test_sample_pdf_merge_ragged_sizes():
+    for (n, S, U) in ((1, 3, 1), (5, 17, 33), (9, 128, 128), (33, 64, 0 + 7)):
+        w = torch.rand(n, S)
+        z = O.sample_coarse(n, S)
+        z_all, zs, inds, cdf = ops.sample_pdf_merge(cuda(z), cuda(w), cuda(torch.linspace(0, 1, U)))
+        assert torch.equal(torch.sort(torch.cat([z, zs.cpu()], -1), -1)[0], z_all.cpu())
+        assert int(inds.min()) >= 1 and int(inds.max()) <= S - 1
+
+
+# ------------------------------------------------------------------------------- a5/a6 compositing
+def _composite_inputs(name):
+    g = golden(name)
+    return g, torch.from_numpy(g["aux_raw_fine"]), torch.from_numpy(g["aux_z_all"]), torch.from_numpy(g["rays_d"])
+
+
+@pytest.mark.parametrize("name", ["lego16_randinit", "lego8_dense"])
+def test_composite_plain_vs_reference_golden(name):
+    g, raw, z, d = _composite_inputs(name)
+    rgb, disp, acc, w, depth = ops.composite_forward(cuda(raw), cuda(z), cuda(d), L.COMPOSITE_PLAIN)
+    rel_close(w, g["aux_weights_fine"], 1e-5, 1e-7)
+    rel_close(rgb, g["out_rgb_map"].reshape(-1, 3), 1e-5, 1e-6)
+    rel_close(acc, g["out_acc_map"].reshape(-1), 1e-5, 1e-6)
+    rel_close(depth, g["out_depth_map"].reshape(-1), 1e-5, 1e-6)
+    rel_close(disp, g["out_disp_map"].reshape(-1), 1e-5, 1e-6)
+    # coarse pass too (64 samples)
+    rgb0, disp0, acc0, w0, depth0 = ops.composite_forward(cuda(g["aux_raw_coarse"]), cuda(g["aux_z_coarse"]), cuda(d))
+    rel_close(w0, g["aux_weights_coarse"], 1e-5, 1e-7)
+    rel_close(rgb0, g["out_rgb_map_0"].reshape(-1, 3), 1e-5, 1e-6)
+    rel_close(depth0, g["out_depth_map_0"].reshape(-1), 1e-5, 1e-6)
+
+
+def test_composite_ert_compat_vs_reference_golden():
+    g, raw, z, d = _composite_inputs("lego8_dense_ert")
+    rgb, disp, acc, w, depth = ops.composite_forward(cuda(raw), cuda(z), cuda(d), L.COMPOSITE_ERT_COMPAT, 0.01)
+    rel_close(w, g["aux_weights_fine"], 1e-5, 1e-7)
+    rel_close(rgb, g["out_rgb_map"].reshape(-1, 3), 1e-5, 1e-6)
+    rel_close(acc, g["out_acc_map"].reshape(-1), 1e-5, 1e-6)
+    rel_close(depth, g["out_depth_map"].reshape(-1), 1e-5, 1e-6)
+    rel_close(disp, g["out_disp_map"].reshape(-1), 1e-5, 1e-6)
+
+
+def test_composite_ert_quirk_and_intended_semantics():
+    n, S = 5000, 192        # spans three 2048-ray chunks
+    g = torch.Generator().manual_seed(0)
+    raw = torch.randn(n, S, 4, generator=g)
+    raw[..., 3] = raw[..., 3] * 0.02
+    raw[100, :, 3] = 40.0     # one terminating ray in chunk 0 only
+    z, _ = torch.sort(torch.rand(n, S, generator=g) * 4 + 2, -1)
+    d = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1)
+    for compat, variant in ((True, L.COMPOSITE_ERT_COMPAT), (False, L.COMPOSITE_ERT)):
+        refs = [O.raw2outputs_ert(raw[s:s + 2048], z[s:s + 2048], d[s:s + 2048], 0.01, True, ref_compat=compat)
+                for s in range(0, n, 2048)]
+        ref = [torch.cat([r[i] for r in refs]) for i in range(5)]
+        out = ops.composite_forward(cuda(raw), cuda(z), cuda(d), variant, 0.01)
+        for a, b in zip(out, ref):
+            rel_close(a, b, 1e-5, 1e-6)
+    # compat: rays of chunk 0 that never terminate lost everything; chunks 1,2 untouched
+    acc = ops.composite_forward(cuda(raw), cuda(z), cuda(d), L.COMPOSITE_ERT_COMPAT, 0.01)[2].cpu()
+    assert float(acc[0]) == 0.0 and float(acc[3000]) > 0.0
+
+
+def test_composite_edge_cases():
+    d = cuda([[0., 0., 1.]])
+    # single sample, zero density -> acc 0, disp NaN (0/0), white background rgb 1
+    rgb, disp, acc, w, depth = ops.composite_forward(cuda(torch.zeros(1, 1, 4)), cuda([[3.0]]), d)
+    assert float(acc) == 0 and torch.isnan(disp).all() and bits_equal(rgb, torch.ones(1, 3))
+    ref = O.raw2outputs(torch.zeros(1, 1, 4), torch.tensor([[3.0]]), torch.tensor([[0., 0., 1.]]))
+    assert bits_equal(disp, ref[1])
+    # n_rays == 0 is a no-op
+    out = ops.composite_forward(cuda(torch.zeros(0, 64, 4)), cuda(torch.zeros(0, 64)), cuda(torch.zeros(0, 3)))
+    assert out[0].shape == (0, 3)
+    # maximum supported samples per ray, ragged counts
+    for S in (2, 31, 33, 255, 256):
+        g = torch.Generator().manual_seed(S)
+        raw = torch.randn(9, S, 4, generator=g)
+        z, _ = torch.sort(torch.rand(9, S, generator=g) * 4 + 2, -1)
+        dd = torch.nn.functional.normalize(torch.randn(9, 3, generator=g), dim=-1)
+        out = ops.composite_forward(cuda(raw), cuda(z), cuda(dd))
+        for a, b in zip(out, O.raw2outputs(raw, z, dd)):
+            rel_close(a, b, 1e-5, 1e-6)
+    with pytest.raises(L.NerfB200Error):
+        ops.composite_forward(cuda(torch.zeros(1, 257, 4)), cuda(torch.zeros(1, 257)), d)
+
+
+# ------------------------------------------------------------------------------- a7 backward
+def test_composite_backward_vs_autograd():
+    n, S = 257, 64
+    g = torch.Generator().manual_seed(2)
+    raw = torch.randn(n, S, 4, generator=g)
+    raw[..., 3] = raw[..., 3] * 3.0
+    z, _ = torch.sort(torch.rand(n, S, generator=g) * 4 + 2, -1)
+    d = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1)
+    g_rgb, g_acc, g_depth = torch.randn(n, 3, generator=g), torch.randn(n, generator=g), torch.randn(n, generator=g)
+    g_w = torch.randn(n, S, generator=g) * 0.1
+    rawd = raw.double().requires_grad_(True)
+    # fp64 autograd of the oracle's formula = exact gradient of the reference graph
+    dists = torch.cat([z[..., 1:] - z[..., :-1], torch.full((n, 1), 1e10)], -1).double() * torch.norm(d, dim=-1, keepdim=True).double()
+    alpha = 1. - torch.exp(-torch.relu(rawd[..., 3]) * dists)
+    T = torch.cumprod(torch.cat([torch.ones(n, 1, dtype=torch.double), 1. - alpha + 1e-10], -1), -1)[:, :-1]
+    w = alpha * T
+    rgb = torch.sigmoid(rawd[..., :3])
+    acc = w.sum(-1)
+    rgb_map = (w[..., None] * rgb).sum(-2) + (1. - acc[..., None])
+    depth = (w * z.double()).sum(-1)
+    loss = (rgb_map * g_rgb.double()).sum() + (acc * g_acc.double()).sum() + (depth * g_depth.double()).sum() + (w * g_w.double()).sum()
+    loss.backward()
+    got = ops.composite_backward(cuda(raw), cuda(z), cuda(d), cuda(g_rgb), cuda(g_acc), cuda(g_depth), cuda(g_w))
+    ref = rawd.grad.float()
+    scale = ref.abs().max()
+    err = (got.cpu() - ref).abs().max()
+    assert float(err) <= 2e-5 * float(scale), "backward err %.3e vs scale %.3e" % (err, scale)
+    # only rgb gradient given (the training loss), others NULL
+    got2 = ops.composite_backward(cuda(raw), cuda(z), cuda(d), cuda(g_rgb))
+    rawd.grad = None
+    alpha = 1. - torch.exp(-torch.relu(rawd[..., 3]) * dists)
+    T = torch.cumprod(torch.cat([torch.ones(n, 1, dtype=torch.double), 1. - alpha + 1e-10], -1), -1)[:, :-1]
+    w = alpha * T
+    rgb_map = (w[..., None] * torch.sigmoid(rawd[..., :3])).sum(-2) + (1. - w.sum(-1)[..., None])
+    (rgb_map * g_rgb.double()).sum().backward()
+    ref2 = rawd.grad.float()
+    assert float((got2.cpu() - ref2).abs().max()) <= 2e-5 * float(ref2.abs().max())
+
+
+# ------------------------------------------------------------------------------- a3 MLP (fp32 mode)
+def _mlp_ref(sd, prefix, ro, rd, z):
+    pts = ro[..., None, :] + rd[..., None, :] * z[..., :, None]
+    with torch.no_grad():
+        return O.query_network(sd, prefix, pts, rd)
+
+
+@pytest.mark.parametrize("prefix,n,S", [("model.", 64, 64), ("model_fine.", 37, 192), ("model.", 3, 5)])
+def test_mlp_fp32_vs_oracle(prefix, n, S):
+    sd = O.make_state_dict(0)
+    b = O.lego_batch(16, 16)
+    ro, rd = O.get_rays(16, 16, b["pose"][0], b["intrinsics"][0])
+    ro, rd = ro[:n].contiguous(), rd[:n].contiguous()
+    z, _ = torch.sort(torch.rand(n, S, generator=torch.Generator().manual_seed(S)) * 4 + 2, -1)
+    packed = ops.pack_from_state_dict(sd, prefix, L.MODE_FP32, DEV)
+    raw = ops.mlp_forward(packed, cuda(ro), cuda(rd), cuda(z))
+    ref = _mlp_ref(sd, prefix, ro, rd, z)
+    # fp32 FFMA vs MKL sgemm: different summation order only
+    rel_close(raw, ref, 2e-5, 2e-6)
+
+
+def test_mlp_fp32_vs_reference_golden_raw():
+    g = golden("lego16_randinit")
+    sd = O.make_state_dict(0)
+    packed = ops.pack_from_state_dict(sd, "model_fine.", L.MODE_FP32, DEV)
+    raw = ops.mlp_forward(packed, cuda(g["rays_o"]), cuda(g["rays_d"]), cuda(g["aux_z_all"]))
+    rel_close(raw, g["aux_raw_fine"], 2e-5, 2e-6)
+
+
+# ------------------------------------------------------------------------------- a8 ESS
+def test_ess_resample_vs_oracle():
+    torch.manual_seed(0)
+    res = 128
+    grid = O.init_occupancy_grid(res, torch.rand(res, res, res) < 0.02)
+    grid[:, :, :40] = False            # carve empty space so that rays are "highly empty"
+    # wide-FOV quick-test camera (quick_test_ess_ert.py:96-110): many rays miss the box
+    pose = torch.eye(4)
+    pose[2, 3] = 4.0
+    K = torch.tensor([[100., 0, 50], [0, 100., 50], [0, 0, 1]])
+    ro, rd = O.get_rays(100, 100, pose, K)
+    sel = torch.randperm(10000)[:1500]
+    ro, rd = ro[sel].contiguous(), rd[sel].contiguous()
+    ref = O.sample_coarse_ess(grid, ro, rd, ref_compat=False)
+    z0 = O.sample_coarse(ro.shape[0])
+    z, n_empty = ops.ess_resample(cuda(grid.to(torch.uint8)), cuda(ro), cuda(rd), cuda(z0))
+    pts = ro[..., None, :] + rd[..., None, :] * z0[..., :, None]
+    ref_empty = O.is_empty_space(grid, pts.reshape(-1, 3)).reshape(-1, 64).sum(-1)
+    assert torch.equal(n_empty.cpu().long(), ref_empty), "grid lookups differ"
+    changed = (ref != z0).any(-1)
+    assert int(changed.sum()) > 50, "test does not exercise resampling"
+    rel_close(z, ref, 0, 2e-6)          # linspace refill: same formula, <= 1-2 ulp
+    assert bool((z.cpu()[:, 1:] >= z.cpu()[:, :-1]).all())
+
+
+def test_ess_update_vs_oracle():
+    torch.manual_seed(1)
+    res = 64
+    n, S = 500, 64
+    grid = torch.zeros(res, res, res, dtype=torch.bool)
+    rd = torch.nn.functional.normalize(torch.randn(n, 3), dim=-1)
+    ro = torch.randn(n, 3)
+    z = O.sample_coarse(n)
+    raw = torch.randn(n, S, 4)
+    w = torch.rand(n, S) * 3e-4
+    ref = O.ess_update(grid.clone(), rd, z, raw, w)
+    got = ops.ess_update(cuda(grid.to(torch.uint8)), cuda(ro), cuda(rd), cuda(z), cuda(raw), cuda(w))
+    assert torch.equal(got.cpu().bool(), ref)
+    assert int(ref.sum()) > 100
+
+
+# ------------------------------------------------------------------------------- whole path, fp32 mode
+def _renderer(sd, mode, **cfg):
+    from nerf_rep_for_test_b200 import Network, RenderConfig, Renderer
+    net = Network(device=DEV)
+    net.load_state_dict(sd)
+    net.to(DEV).eval()
+    base = dict(perturb=0, enable_ess=False, enable_ert=False)
+    base.update(cfg)
+    return Renderer(net, RenderConfig(**base), mode=mode)
+
+
+MAPS = ["rgb_map_0", "depth_map_0", "acc_map_0", "disp_map_0", "rgb_map", "depth_map", "acc_map", "disp_map"]
+
+
+@pytest.mark.parametrize("name", ["lego16_randinit", "lego16_randinit_ert", "lego8_dense", "lego8_dense_ert"])
+def test_render_fp32_vs_reference_golden(name):
+    g = golden(name)
+    H, W, seed, gain, bias, ert = g["meta"]
+    sd = O.make_state_dict(int(seed), float(gain), float(bias))
+    r = _renderer(sd, "fp32", enable_ert=bool(ert))
+    out = r.render({"pose": cuda(g["pose"]), "intrinsics": cuda(g["intrinsics"]), "H": int(H), "W": int(W)})
+    assert sorted(out) == sorted(MAPS)
+    assert out["rgb_map"].shape == (int(H), int(W), 3) and out["depth_map"].shape == (int(H), int(W))
+    assert out["rgb_map"].dtype == torch.float32 and out["rgb_map"].device.type == "cuda"
+    for k in MAPS:
+        ref = torch.from_numpy(g["out_" + k])
+        a = out[k].cpu()
+        err = (torch.nan_to_num(a) - torch.nan_to_num(ref)).abs()
+        rel = err / ref.abs().clamp_min(1e-3)
+        # north_star: 1e-5 relative; report median/p99/max (SURVEY 8c': the fp32 oracle's own
+        # rounding noise is up to 4.6e-5 on a few rays, so the hard gate is p99 1e-5 / max 2e-4)
+        med, p99, mx = float(rel.median()), float(rel.flatten().kthvalue(max(1, int(0.99 * rel.numel())))[0]), float(rel.max())
+        print("%s %-12s rel err median %.2e p99 %.2e max %.2e" % (name, k, med, p99, mx))
+        if "disp" in k:
+            continue    # 1/(depth/acc): conditioning amplified when acc ~ 0; reported only
+        assert p99 <= 1e-5 and mx <= 2e-4, (k, med, p99, mx)
+
+
+def test_render_fp32_vs_oracle_rays_and_host_entry():
+    sd = O.make_state_dict(2, 30.0, 0.2)
+    b = O.lego_batch(12, 20)
+    r = _renderer(sd, "fp32")
+    out = r.render({k: (cuda(v) if torch.is_tensor(v) else v) for k, v in b.items()})
+    with torch.no_grad():
+        ref = O.render(sd, b)
+    for k in MAPS:
+        if "disp" in k:
+            continue
+        rel_close(out[k], ref[k], 1e-5, 2e-6)
+    host = r.render_host(b)      # host buffers in, pinned host maps out
+    for k in MAPS:
+        assert not host[k].is_cuda
+        assert bits_equal(host[k], out[k]), k
+    # ray-batch extension: ragged count, not a multiple of anything
+    ro, rd = O.get_rays(12, 20, b["pose"][0], b["intrinsics"][0])
+    part = r.render_rays(cuda(ro[:101]), cuda(rd[:101]))
+    assert bits_equal(part["rgb_map"], out["rgb_map"].reshape(-1, 3)[:101])
+
+
+def test_render_ess_noop_on_lego_pose():
+    """with the initial grid no ray of a lego pose is highly empty -> identical output."""
+    sd = O.make_state_dict(0)
+    b = O.lego_batch(16, 16)
+    bc = {k: (cuda(v) if torch.is_tensor(v) else v) for k, v in b.items()}
+    plain = _renderer(sd, "fp32").render(bc)
+    ess = _renderer(sd, "fp32", enable_ess=True).render(bc)
+    for k in MAPS:
+        assert bits_equal(plain[k], ess[k]), k
