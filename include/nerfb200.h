@@ -108,6 +108,13 @@ NERFB200_API int nerfb200_pack_weights(const nerfb200_mlp_weights* w, int mode, 
 NERFB200_API int nerfb200_mlp_forward(const void* packed, int mode, const float* rays_o, const float* rays_d,
                          const float* z_vals, int n_rays, int n_samples, float* raw, void* stream);
 
+/* diagnostic twin of mlp_forward (BF16 mode): additionally writes the fp32 post-activation output
+ * of each of the ten stages (mlp_layout.cuh) for rows 0..127 into stage_dump [10][128][256];
+ * used by the stage-level parity tests. */
+NERFB200_API int nerfb200_mlp_forward_stages(const void* packed, int mode, const float* rays_o,
+                                const float* rays_d, const float* z_vals, int n_rays, int n_samples,
+                                float* raw, float* stage_dump, void* stream);
+
 /* ---- a5/a6: alpha compositing (volume_renderer.py:286-357, :1089-1157) ------------------- */
 /* raw [n_rays,S,4], z_vals [n_rays,S], rays_d [n_rays,3] -> rgb_map [n_rays,3], disp/acc/depth
  * [n_rays], weights [n_rays,S] (may be NULL).  One warp per ray, shuffle prefix product.

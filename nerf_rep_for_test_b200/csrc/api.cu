@@ -23,7 +23,7 @@ void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_r
 int launch_mlp_fp32(const void* packed, const float* rays_o, const float* rays_d, const float* z_vals,
                     int n_rays, int n_samples, float* raw, cudaStream_t st);
 int launch_mlp_bf16(const void* packed, const float* rays_o, const float* rays_d, const float* z_vals,
-                    int n_rays, int n_samples, float* raw, cudaStream_t st);
+                    int n_rays, int n_samples, float* raw, float* stage_dump, cudaStream_t st);
 
 // rays per internal chunk of the whole-pass driver: keeps the per-chunk intermediates
 // (z, raw, weights: ~5.4 KB/ray) inside the 126 MB L2 and bounds the workspace.
@@ -79,14 +79,24 @@ extern "C" uint64_t nerfb200_launch_count(void) { return g_launches.load(std::me
 
 extern "C" int nerfb200_mlp_forward(const void* packed, int mode, const float* rays_o, const float* rays_d,
                                     const float* z_vals, int n_rays, int n_samples, float* raw, void* stream) {
-  NB_CHECK_ARG(packed && rays_o && rays_d && z_vals && raw, "mlp_forward: null pointer");
+  NB_CHECK_ARG(n_rays <= 0 || (packed && rays_o && rays_d && z_vals && raw), "mlp_forward: null pointer");
   NB_CHECK_ARG(n_rays >= 0 && n_samples >= 1, "mlp_forward: bad sizes n_rays=%d n_samples=%d", n_rays, n_samples);
   NB_CHECK_ARG(((uintptr_t)packed & 1023) == 0, "mlp_forward: packed weights must be 1024-byte aligned");
   if (n_rays == 0) return 0;
   if (mode == NERFB200_MODE_FP32) return launch_mlp_fp32(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, (cudaStream_t)stream);
-  if (mode == NERFB200_MODE_BF16) return launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, (cudaStream_t)stream);
+  if (mode == NERFB200_MODE_BF16) return launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, nullptr, (cudaStream_t)stream);
   set_error("mlp_forward: unknown mode %d", mode);
   return 1;
+}
+
+extern "C" int nerfb200_mlp_forward_stages(const void* packed, int mode, const float* rays_o, const float* rays_d,
+                                           const float* z_vals, int n_rays, int n_samples, float* raw,
+                                           float* stage_dump, void* stream) {
+  NB_CHECK_ARG(packed && rays_o && rays_d && z_vals && raw && stage_dump, "mlp_forward_stages: null pointer");
+  NB_CHECK_ARG(n_rays >= 1 && n_samples >= 1, "mlp_forward_stages: bad sizes");
+  NB_CHECK_ARG(mode == NERFB200_MODE_BF16, "mlp_forward_stages: only NERFB200_MODE_BF16 has a stage dump");
+  NB_CHECK_ARG(((uintptr_t)packed & 1023) == 0, "mlp_forward_stages: packed weights must be 1024-byte aligned");
+  return launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, stage_dump, (cudaStream_t)stream);
 }
 
 extern "C" size_t nerfb200_render_workspace_bytes(int n_rays, const nerfb200_render_params* p) {
@@ -101,6 +111,7 @@ extern "C" int nerfb200_render_rays(const void* packed_coarse, const void* packe
                                     const nerfb200_render_params* p, void* workspace, size_t workspace_bytes,
                                     const nerfb200_maps* mc, const nerfb200_maps* mf, void* stream) {
   if (int e = check_params(p)) return e;
+  if (n_rays == 0) return 0;
   NB_CHECK_ARG(packed_coarse && rays_o && rays_d && z_table && mc, "render_rays: null pointer");
   NB_CHECK_ARG(mc->rgb && mc->disp && mc->acc && mc->depth, "render_rays: null coarse map");
   NB_CHECK_ARG(n_rays >= 0, "render_rays: negative n_rays");

@@ -14,6 +14,15 @@ namespace nb {
 constexpr int kCompWarps = 8;
 constexpr int kMaxPer = 8;  // ceil(S/32) <= 8  => S <= 256
 
+// exp / sigmoid as the reference's CPU sees them: torch CPU evaluates exp with SLEEF (<= 1 ulp);
+// rounding the fp64 exp matches it on 96.5-99% of arguments while CUDA's expf matches only
+// 60-70% (scripts/probe_exp.py on the B200 box).  alpha = 1 - exp(-x) cancels, so each mismatch
+// costs ulp(1) absolute on alpha.  sigmoid on CPU is 1/(1+exp(-x)) in fp32 steps.
+__device__ __forceinline__ float exp_cr(float x) { return (float)exp((double)x); }
+__device__ __forceinline__ float sigmoid_ref(float x) {
+  return __fdiv_rn(1.f, __fadd_rn(1.f, exp_cr(-x)));
+}
+
 __device__ __forceinline__ float ray_norm(const float* __restrict__ d) {
   // torch.norm(rays_d[..., None, :], dim=-1): FMA-chain accumulation (probed, bit-exact)
   return __fsqrt_rn(__fmaf_rn(d[2], d[2], __fmaf_rn(d[1], d[1], __fmul_rn(d[0], d[0]))));
@@ -60,7 +69,7 @@ __device__ __forceinline__ void ray_alpha_T(const float* __restrict__ raw_row,
       float dist = (i + 1 < S) ? __fsub_rn(z_row[i + 1], z0) : 1e10f;
       dist = __fmul_rn(dist, dnorm);
       float sig = fmaxf(raw_row[(size_t)i * 4 + 3], 0.f);
-      a = __fsub_rn(1.f, expf(__fmul_rn(-sig, dist)));
+      a = __fsub_rn(1.f, exp_cr(__fmul_rn(-sig, dist)));
       f = kErt ? __fsub_rn(1.f, a) : __fadd_rn(__fsub_rn(1.f, a), 1e-10f);
       local *= (double)f;
     }
@@ -103,7 +112,7 @@ __device__ __forceinline__ void ray_outputs(const RaySamples& rs, const float* _
       float w = __fmul_rn(rs.alpha[j], rs.T[j]);
       if (i >= cut) w = __fmul_rn(w, 0.f);  // weights * (~mask).float()
       float4 r4 = *reinterpret_cast<const float4*>(raw_row + (size_t)i * 4);
-      float cr = 1.f / (1.f + expf(-r4.x)), cg = 1.f / (1.f + expf(-r4.y)), cb = 1.f / (1.f + expf(-r4.z));
+      float cr = sigmoid_ref(r4.x), cg = sigmoid_ref(r4.y), cb = sigmoid_ref(r4.z);
       sr += (double)__fmul_rn(w, cr);
       sg += (double)__fmul_rn(w, cg);
       sb += (double)__fmul_rn(w, cb);
@@ -222,9 +231,9 @@ composite_backward_kernel(const float* __restrict__ raw, const float* __restrict
     G[j] = 0.f; w[j] = 0.f;
     if (j < per && i < S) {
       float4 r4 = *reinterpret_cast<const float4*>(raw_row + (size_t)i * 4);
-      c[j][0] = 1.f / (1.f + expf(-r4.x));
-      c[j][1] = 1.f / (1.f + expf(-r4.y));
-      c[j][2] = 1.f / (1.f + expf(-r4.z));
+      c[j][0] = sigmoid_ref(r4.x);
+      c[j][1] = sigmoid_ref(r4.y);
+      c[j][2] = sigmoid_ref(r4.z);
       w[j] = rs.alpha[j] * rs.T[j];
       G[j] = gr * c[j][0] + gg * c[j][1] + gb * c[j][2] + ga + gd * z_row[i] +
              (g_weights ? g_weights[ray * S + i] : 0.f);
@@ -273,7 +282,7 @@ extern "C" int nerfb200_composite_forward(const float* raw, const float* z_vals,
                                           int white_bkgd, int compat_chunk, float* rgb_map,
                                           float* disp_map, float* acc_map, float* depth_map,
                                           float* weights, void* stream) {
-  NB_CHECK_ARG(raw && z_vals && rays_d && rgb_map && disp_map && acc_map && depth_map,
+  NB_CHECK_ARG(n_rays <= 0 || (raw && z_vals && rays_d && rgb_map && disp_map && acc_map && depth_map),
                "composite_forward: null pointer");
   NB_CHECK_ARG(n_samples >= 1 && n_samples <= 32 * kMaxPer, "composite_forward: n_samples=%d out of range [1,%d]",
                n_samples, 32 * kMaxPer);
@@ -303,7 +312,7 @@ extern "C" int nerfb200_composite_backward(const float* raw, const float* z_vals
                                            const float* g_rgb_map, const float* g_acc_map,
                                            const float* g_depth_map, const float* g_weights,
                                            float* g_raw, void* stream) {
-  NB_CHECK_ARG(raw && z_vals && rays_d && g_raw, "composite_backward: null pointer");
+  NB_CHECK_ARG(n_rays <= 0 || (raw && z_vals && rays_d && g_raw), "composite_backward: null pointer");
   NB_CHECK_ARG(n_samples >= 1 && n_samples <= 32 * kMaxPer, "composite_backward: n_samples=%d out of range", n_samples);
   NB_CHECK_ARG(n_rays >= 0, "composite_backward: negative n_rays");
   if (n_rays == 0) return 0;

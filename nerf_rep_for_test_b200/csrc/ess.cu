@@ -108,7 +108,7 @@ using namespace nb;
 
 extern "C" int nerfb200_ess_resample(const uint8_t* grid, int res, const float* rays_o, const float* rays_d,
                                      int n_rays, int n_samples, float* z_vals, int32_t* n_empty, void* stream) {
-  NB_CHECK_ARG(grid && rays_o && rays_d && z_vals, "ess_resample: null pointer");
+  NB_CHECK_ARG(n_rays <= 0 || (grid && rays_o && rays_d && z_vals), "ess_resample: null pointer");
   NB_CHECK_ARG(res >= 1 && res <= 1024, "ess_resample: bad grid resolution %d", res);
   NB_CHECK_ARG(n_samples >= 1 && n_samples <= kEssMaxS, "ess_resample: n_samples=%d out of range", n_samples);
   NB_CHECK_ARG(n_rays >= 0, "ess_resample: negative n_rays");
@@ -122,7 +122,7 @@ extern "C" int nerfb200_ess_resample(const uint8_t* grid, int res, const float* 
 extern "C" int nerfb200_ess_update(uint8_t* grid, int res, const float* rays_o, const float* rays_d,
                                    const float* z_vals, const float* raw, const float* weights, int n_rays,
                                    int n_samples, int use_origin, void* stream) {
-  NB_CHECK_ARG(grid && rays_d && z_vals && raw && weights, "ess_update: null pointer");
+  NB_CHECK_ARG(n_rays <= 0 || (grid && rays_d && z_vals && raw && weights), "ess_update: null pointer");
   NB_CHECK_ARG(!use_origin || rays_o, "ess_update: use_origin needs rays_o");
   NB_CHECK_ARG(res >= 1 && res <= 1024, "ess_update: bad grid resolution %d", res);
   NB_CHECK_ARG(n_rays >= 0 && n_samples >= 1, "ess_update: bad sizes");

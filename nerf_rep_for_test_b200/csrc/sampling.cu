@@ -270,7 +270,7 @@ extern "C" int nerfb200_raygen(const float* pose, const float* intrinsics, int H
 
 extern "C" int nerfb200_sample_coarse(const float* z_table, int n_rays, int n_samples, int perturb,
                                       uint64_t seed, float* z_vals, void* stream) {
-  NB_CHECK_ARG(z_table && z_vals, "sample_coarse: null pointer");
+  NB_CHECK_ARG(n_rays <= 0 || (z_table && z_vals), "sample_coarse: null pointer");
   NB_CHECK_ARG(n_rays >= 0 && n_samples >= 2, "sample_coarse: bad sizes n_rays=%d S=%d", n_rays, n_samples);
   if (n_rays == 0) return 0;
   long long total = (long long)n_rays * n_samples;
@@ -282,7 +282,7 @@ extern "C" int nerfb200_sample_coarse(const float* z_table, int n_rays, int n_sa
 extern "C" int nerfb200_sample_from_cdf(const float* cdf, const float* bins, const float* u,
                                         int u_per_ray, int n_rays, int n_bins, int n_u,
                                         float* samples, int32_t* inds, void* stream) {
-  NB_CHECK_ARG(cdf && bins && u && samples, "sample_from_cdf: null pointer");
+  NB_CHECK_ARG(n_rays <= 0 || n_u <= 0 || (cdf && bins && u && samples), "sample_from_cdf: null pointer");
   NB_CHECK_ARG(n_bins >= 1 && n_bins <= kMaxBins, "sample_from_cdf: n_bins=%d out of range [1,%d]", n_bins, kMaxBins);
   NB_CHECK_ARG(n_rays >= 0 && n_u >= 0, "sample_from_cdf: negative size");
   if (n_rays == 0 || n_u == 0) return 0;
@@ -296,7 +296,7 @@ extern "C" int nerfb200_sample_pdf_merge(const float* z_coarse, const float* wei
                                          int u_per_ray, int n_rays, int n_samples, int n_u,
                                          float* z_all, float* z_samples, int32_t* inds, float* cdf,
                                          void* stream) {
-  NB_CHECK_ARG(z_coarse && weights && u && z_all, "sample_pdf_merge: null pointer");
+  NB_CHECK_ARG(n_rays <= 0 || (z_coarse && weights && u && z_all), "sample_pdf_merge: null pointer");
   NB_CHECK_ARG(n_samples >= 3 && n_samples <= kMaxS, "sample_pdf_merge: n_samples=%d out of range [3,%d]", n_samples, kMaxS);
   NB_CHECK_ARG(n_u >= 1 && n_u <= kMaxU, "sample_pdf_merge: n_u=%d out of range [1,%d]", n_u, kMaxU);
   NB_CHECK_ARG(n_rays >= 0, "sample_pdf_merge: negative n_rays");

@@ -78,6 +78,17 @@ def mlp_forward(packed, rays_o, rays_d, z_vals):
     return raw
 
 
+def mlp_forward_stages(packed, rays_o, rays_d, z_vals):
+    """BF16 mode diagnostic: (raw, stage_dump [10,128,256]) -- fp32 stage outputs of rows 0..127."""
+    rays_o, rays_d, z_vals = _f(rays_o), _f(rays_d), _f(z_vals)
+    n, S = z_vals.shape
+    raw = torch.empty((n, S, 4), device=z_vals.device)
+    dump = torch.zeros((10, 128, 256), device=z_vals.device)
+    L.check(L.load().nerfb200_mlp_forward_stages(packed.ptr, packed.mode, L.dev(rays_o), L.dev(rays_d), L.dev(z_vals),
+                                                n, S, L.dev(raw), L.dev(dump), L.stream_ptr()), "mlp_forward_stages")
+    return raw, dump
+
+
 def composite_forward(raw, z_vals, rays_d, variant=L.COMPOSITE_PLAIN, ert_threshold=0.01, white_bkgd=True,
                       compat_chunk=2048, want_weights=True):
     raw, z_vals, rays_d = _f(raw), _f(z_vals), _f(rays_d)
