@@ -1,0 +1,113 @@
+"""GPU parity of the BF16 (tcgen05) mode.
+
+north_star: rgb/acc within 1e-3 absolute, depth within 1e-3 relative to its range, < 0.05 dB PSNR
+against the reference renderer on identical rays and weights.  The kernel itself is additionally
+pinned, stage by stage, against a CPU emulation of its exact arithmetic (tests/bf16_emul.py)."""
+import pytest
+import torch
+
+from conftest import golden
+from oracle import nerf_oracle as O
+from bf16_emul import mlp_bf16_stages
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from nerf_rep_for_test_b200 import lib as L
+    from nerf_rep_for_test_b200 import ops
+    DEV = torch.device("cuda:0")
+
+
+def _rays(n, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    b = O.lego_batch(64, 64)
+    ro, rd = O.get_rays(64, 64, b["pose"][0], b["intrinsics"][0])
+    sel = torch.randperm(ro.shape[0], generator=g)[:n]
+    return ro[sel].contiguous(), rd[sel].contiguous()
+
+
+def test_stage_outputs_match_bf16_emulation():
+    sd = O.make_state_dict(0)
+    ro, rd = _rays(2)
+    z = O.sample_coarse(2)
+    packed = ops.pack_from_state_dict(sd, "model_fine.", L.MODE_BF16, DEV)
+    raw, dump = ops.mlp_forward_stages(packed, ro.to(DEV), rd.to(DEV), z.to(DEV))
+    pts = (ro[:, None, :] + rd[:, None, :] * z[..., None]).reshape(-1, 3)
+    dirs = rd[:, None, :].expand(2, 64, 3).reshape(-1, 3)
+    ref_raw, stages = mlp_bf16_stages(sd, "model_fine.", pts, dirs)
+    for i, st in enumerate(stages):
+        err = (dump[i, :128, : st.shape[1]].cpu() - st).abs().max()
+        # differences come only from bf16 roundings that flip on last-bit input differences
+        assert float(err) < 2e-3 * max(1.0, float(st.abs().max())), (i, float(err))
+    assert float((raw.cpu().reshape(-1, 4) - ref_raw).abs().max()) < 5e-4
+
+
+@pytest.mark.parametrize("n,S", [(1, 1), (3, 5), (2, 64), (5, 192), (700, 64), (1300, 192)])
+def test_mlp_bf16_vs_emulation_and_oracle(n, S):
+    """ragged sizes: partial tiles, odd tile counts, several tile pairs per CTA (1300x192 = 1950 tiles)."""
+    sd = O.make_state_dict(1)
+    ro, rd = _rays(n, seed=S)
+    z, _ = torch.sort(torch.rand(n, S, generator=torch.Generator().manual_seed(n)) * 4 + 2, -1)
+    packed = ops.pack_from_state_dict(sd, "model.", L.MODE_BF16, DEV)
+    raw = ops.mlp_forward(packed, ro.to(DEV), rd.to(DEV), z.to(DEV)).cpu()
+    pts = (ro[:, None, :] + rd[:, None, :] * z[..., None]).reshape(-1, 3)
+    dirs = rd[:, None, :].expand(n, S, 3).reshape(-1, 3)
+    with torch.no_grad():
+        emu, _ = mlp_bf16_stages(sd, "model.", pts, dirs)
+        ref = O.nerf_mlp(sd, "model.", torch.cat([O.pos_enc(pts, 10), O.pos_enc(dirs, 4)], -1))
+    e_emu = (raw.reshape(-1, 4) - emu).abs()
+    e_ref = (raw.reshape(-1, 4) - ref).abs()
+    print("n=%d S=%d  vs emulation max %.2e  vs fp32 oracle max %.2e median %.2e" % (
+        n, S, float(e_emu.max()), float(e_ref.max()), float(e_ref.median())))
+    assert float(e_emu.max()) < 1e-3
+    assert float(e_ref.max()) < 5e-3
+    # same inputs twice -> bit-identical (no race between the two tile slots)
+    raw2 = ops.mlp_forward(packed, ro.to(DEV), rd.to(DEV), z.to(DEV)).cpu()
+    assert torch.equal(raw, raw2)
+
+
+def _renderer(sd, **cfg):
+    from nerf_rep_for_test_b200 import Network, RenderConfig, Renderer
+    net = Network(device=DEV)
+    net.load_state_dict(sd)
+    net.to(DEV).eval()
+    base = dict(perturb=0, enable_ess=False, enable_ert=False)
+    base.update(cfg)
+    return Renderer(net, RenderConfig(**base), mode="bf16")
+
+
+def _psnr(a, b):
+    return float(-10.0 * torch.log10(((a - b) ** 2).mean().clamp_min(1e-20)))
+
+
+@pytest.mark.parametrize("name", ["lego16_randinit", "lego8_dense"])
+def test_render_bf16_vs_reference_golden(name):
+    g = golden(name)
+    H, W, seed, gain, bias, ert = g["meta"]
+    sd = O.make_state_dict(int(seed), float(gain), float(bias))
+    out = _renderer(sd).render({"pose": torch.from_numpy(g["pose"]).to(DEV),
+                                "intrinsics": torch.from_numpy(g["intrinsics"]).to(DEV), "H": int(H), "W": int(W)})
+    # outlier rule (SURVEY 8c' item 3): the last interval is 1e10 wide, so alpha_last = [sigma_last > 0]
+    # is a step function of an MLP output; rays whose reference |sigma_raw_last| is below the bf16
+    # sigma error bound (2e-3) can flip acc by ~1 and are excluded and counted.
+    sig_last_f = torch.from_numpy(g["aux_raw_fine"])[:, -1, 3].abs()
+    sig_last_c = torch.from_numpy(g["aux_raw_coarse"])[:, -1, 3].abs()
+    for k in ("rgb_map_0", "acc_map_0", "depth_map_0", "rgb_map", "acc_map", "depth_map"):
+        ref = torch.from_numpy(g["out_" + k])
+        a = out[k].cpu()
+        stable = ((sig_last_c if k.endswith("_0") else sig_last_f) > 2e-3).reshape(ref.shape[:2])
+        err = (a - ref).abs()
+        if err.dim() == 3:
+            err = err.max(-1)[0]
+        scale = 6.0 if "depth" in k else 1.0
+        print("%s %-11s abs err/scale median %.2e p99 %.2e max(stable) %.2e  excluded %d of %d rays" % (
+            name, k, float(err.median()) / scale, float(err.flatten().kthvalue(int(0.99 * err.numel()))[0]) / scale,
+            float(err[stable].max()) / scale, int((~stable).sum()), stable.numel()))
+        assert float(err[stable].max()) <= 1e-3 * scale, k
+        assert int((~stable).sum()) <= 0.15 * stable.numel()
+    ref_rgb = torch.from_numpy(g["out_rgb_map"])
+    stable = (sig_last_f > 2e-3).reshape(ref_rgb.shape[:2])
+    # PSNR of our image against the reference's image; "< 0.05 dB" is about PSNR vs ground truth,
+    # which needs a trained checkpoint (absent); the image-to-image PSNR is reported instead
+    print("%s PSNR(ours, reference) over stable rays: %.1f dB" % (name, _psnr(out["rgb_map"].cpu()[stable], ref_rgb[stable])))
+    assert _psnr(out["rgb_map"].cpu()[stable], ref_rgb[stable]) > 60.0
