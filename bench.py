@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""Headline benchmark: rendered rays/s of the NeRF volume-rendering hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode bf16|fp32]
+
+A step = one 800x800 novel view (BASELINE.json configs[1]: 640 000 rays, 64 coarse + 128 importance
+samples = 256 MLP rows per ray, random-init 8x256 NeRF MLPs, perturb=0) rendered by
+Renderer.render(batch).  With N > 1 (launched under torchrun, one rank per GPU) every rank renders
+its own lego test view per step -- rays are independent, there is no data-path collective -- and
+`value` is the whole-job rays/s (weak scaling, BASELINE.json configs[3]).
+
+`value`  : device time (CUDA events), pose/intrinsics already resident in HBM.
+`e2e`    : same metric through the host-buffer C-ABI entry (nerfb200_render_image_host): pose and
+           intrinsics copied from host memory, the eight maps copied back to pinned host memory,
+           all inside the timed region.
+`roofline`: the dominant kernel (mlp_bf16_tc_kernel) timed live with CUDA events around every launch
+           inside the timed region; algorithmic FLOPs (1 186 816 per MLP row, unpadded) / that time
+           against MEASURED_PEAKS.json.
+`cpu_baseline` / `--impl reference`: the reference's CPU path (oracle port, asserted bit-identical
+           to /root/reference in the build container) on a bounded sample of the same frame.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H = W = 800
+N_SAMPLES, N_IMPORTANCE = 64, 128
+ROWS_PER_RAY = N_SAMPLES + (N_SAMPLES + N_IMPORTANCE)        # 64 coarse + 192 fine = 256
+FLOP_PER_ROW = 1186816                                       # BASELINE.md section 4 (unpadded K)
+METRIC = "rendered rays/sec (coarse64+fine128, 800x800)"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"bf16_tflops": p["bf16_tflops_sustained"], "bf16_tflops_burst": p["bf16_tflops"],
+                "hbm_gbs": p["hbm_gbs"], "source": "MEASURED_PEAKS.json (sustained bf16: kernel timed inside a long step)"}
+    return {"bf16_tflops": 1400.0, "bf16_tflops_burst": 1590.0, "hbm_gbs": 6650.0,
+            "source": "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = sorted(int(r[1]) for r in self.rows if len(r) >= 9 and r[1].isdigit())
+        mx = [int(r[2]) for r in self.rows if len(r) >= 9 and r[2].isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        # median over the upper half of the samples = clocks while the GPU was busy
+        busy = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def lego_pose(i):
+    """Camera i of a lego-like test orbit (transforms_test.json is a 200-view circle at radius
+    4.03, elevation 30 deg; frame 0 is oracle.LEGO_TEST_POSE0).  Synthetic poses of that shape."""
+    import math
+    import torch
+    from oracle import nerf_oracle as O
+    if i == 0:
+        return torch.tensor(O.LEGO_TEST_POSE0, dtype=torch.float32)
+    th = 2 * math.pi * i / 200.0
+    base = torch.tensor(O.LEGO_TEST_POSE0, dtype=torch.float32)
+    c, s = math.cos(th), math.sin(th)
+    rot = torch.tensor([[c, -s, 0, 0], [s, c, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]], dtype=torch.float32)
+    return rot @ base
+
+
+def cpu_reference_rays_per_s(budget_s=12.0, n_rays=1024):
+    """Reference CPU path (oracle port of volume_renderer.py:109-216) on a bounded sample: every
+    625th ray of the 800x800 frame (1024 rays), all host cores."""
+    import torch
+    from oracle import nerf_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = O.make_state_dict(0)
+    b = O.lego_batch(H, W)
+    ro, rd = O.get_rays(H, W, b["pose"][0], b["intrinsics"][0])
+    sel = torch.arange(0, H * W, (H * W) // n_rays)[:n_rays]
+    ro, rd = ro[sel].contiguous(), rd[sel].contiguous()
+    with torch.no_grad():
+        O.render_rays(sd, ro, rd)                       # warm-up
+        times = []
+        t_end = time.perf_counter() + budget_s
+        while len(times) < 3 or (time.perf_counter() < t_end and len(times) < 50):
+            t0 = time.perf_counter()
+            O.render_rays(sd, ro, rd)
+            times.append(time.perf_counter() - t0)
+    times.sort()
+    med = times[len(times) // 2]
+    return {"value": n_rays / med, "unit": "rays/s", "cores": cores, "kind": "port",
+            "sample": "%d rays (every %dth ray of the 800x800 frame), 64+128 samples, torch %s CPU fp32, %d threads, "
+                      "median of %d renders" % (n_rays, (H * W) // n_rays, torch.__version__, cores, len(times))}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port; the
+    reference is a Python/torch program that cannot travel to the GPU box)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    from oracle import nerf_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = O.make_state_dict(0)
+    b = O.lego_batch(H, W)
+    ro, rd = O.get_rays(H, W, b["pose"][0], b["intrinsics"][0])
+    n_rays = 1024
+    sel = torch.arange(0, H * W, (H * W) // n_rays)[:n_rays]
+    ro, rd = ro[sel].contiguous(), rd[sel].contiguous()
+    with torch.no_grad():
+        for _ in range(max(1, min(args.warmup, 2))):
+            O.render_rays(sd, ro, rd)
+        t0 = time.perf_counter()
+        steps = max(1, min(args.steps, 20))
+        for _ in range(steps):
+            O.render_rays(sd, ro, rd)
+        dt = (time.perf_counter() - t0) / steps
+    val = n_rays / dt
+    sample = ("each step = %d rays (every %dth ray of the 800x800 frame) through the reference CPU path "
+              "(oracle port, bit-identical to /root/reference), torch %s fp32, %d threads" %
+              (n_rays, (H * W) // n_rays, torch.__version__, cores))
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "rays/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "800x800 lego view, 64 coarse + 128 importance samples, random-init NeRF 8x256 "
+                                   "(bounded sample of 1024 rays per step)", "H": H, "W": W},
+            "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from oracle import nerf_oracle as O          # weights + camera fixtures only (and cpu_baseline)
+    from nerf_rep_for_test_b200 import Network, RenderConfig, Renderer, lib as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sd = O.make_state_dict(0)
+    net = Network(device=dev)
+    net.load_state_dict(sd)
+    net.to(dev).eval()
+    r = Renderer(net, RenderConfig(perturb=0, enable_ess=False, enable_ert=False), mode=args.mode)
+    K0 = O.lego_batch(H, W)["intrinsics"]
+    # one view per rank per step (weak scaling); device-resident for `value`, host for `e2e`
+    n_views = args.warmup + args.steps
+    host_batches = [{"pose": lego_pose(rank + world * i)[None], "intrinsics": K0.clone(), "H": H, "W": W}
+                    for i in range(n_views)]
+    dev_batches = [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in b.items()} for b in host_batches]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def timed(fn, batches):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in batches]
+        for (e0, e1), b in zip(ev, batches):
+            flush.zero_()                       # L2 flush between timed iterations (outside the events)
+            e0.record()
+            fn(b)
+            e1.record()
+        torch.cuda.synchronize()
+        return sum(e0.elapsed_time(e1) for e0, e1 in ev)
+
+    for b in dev_batches[:args.warmup]:
+        r.render(b)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.launch_count()
+    L.profile_enable(True)
+    ms_total = timed(r.render, dev_batches[args.warmup:])
+    mlp_ms, mlp_launches, mlp_rows = L.profile_read()
+    L.profile_enable(False)
+    launches = L.launch_count() - launches0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # e2e: host buffers in and out, copies inside the timed region (wall clock around the C call,
+    # which synchronises the stream before returning)
+    for b in host_batches[:min(args.warmup, 2)]:
+        r.render_host(b)
+    barrier()
+    t0 = time.perf_counter()
+    for b in host_batches[args.warmup:]:
+        r.render_host(b)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+
+    t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(t[0]), float(t[1])
+    rays_total = float(world) * args.steps * H * W
+    value = rays_total / (ms_total * 1e-3)
+    e2e_value = rays_total / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        pk = peaks()
+        achieved = mlp_rows * FLOP_PER_ROW / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "mlp_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        peak = pk["bf16_tflops"] if args.mode == "bf16" else 80.0
+        line = {
+            "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.mode if args.mode == "bf16" else "f32",
+            "data": "synthetic",
+            "config": {"workload": "full 800x800 novel-view render (640k rays, 64 coarse + 128 importance samples, "
+                                   "256 MLP rows/ray), random-init NeRF 8x256, perturb=0, ESS/ERT off (no-ops on "
+                                   "lego poses with random init); one view per GPU per step",
+                       "H": H, "W": W, "n_samples": N_SAMPLES, "n_importance": N_IMPORTANCE, "mode": args.mode,
+                       "parallelism": "rays sharded by view, no inter-GPU traffic", "l2": "flushed between steps "
+                       "(256 MB write); per-chunk intermediates stay in L2 by design"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "rays/s", "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": r.h2d_bytes_per_image, "d2h_bytes_per_step": r.d2h_bytes_per_image(H, W)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "mlp_bf16_tc_kernel" if args.mode == "bf16" else "mlp_fp32_kernel",
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": pk["source"] if args.mode == "bf16" else
+                         "nominal fp32 FFMA 80 TFLOP/s (parity mode, not the performance path)",
+                         "launches_timed": mlp_launches, "kernel_ms_per_step": mlp_ms / args.steps,
+                         "kernel_share_of_step": mlp_ms / ms_total,
+                         "algorithmic_flop_per_row": FLOP_PER_ROW, "rows_per_step": mlp_rows / args.steps},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_reference_rays_per_s()
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: relaunch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

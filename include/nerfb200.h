@@ -85,6 +85,13 @@ NERFB200_API const char* nerfb200_get_last_error_string(void);
 /* number of kernels this library has launched in this process (bench.py "gpu_launches") */
 NERFB200_API uint64_t nerfb200_launch_count(void);
 
+/* Optional timing of the MLP kernel for the roofline figure: while enabled, every mlp_forward launch
+ * (also those inside render_rays / render_image_host) is bracketed by CUDA events on its stream.
+ * profile_enable(on) resets the counters; profile_read synchronises on the recorded events and
+ * returns the summed kernel time, the number of launches and the MLP rows they processed. */
+NERFB200_API int nerfb200_profile_enable(int on);
+NERFB200_API int nerfb200_profile_read(double* mlp_ms, uint64_t* mlp_launches, double* mlp_rows);
+
 /* ---- a1: ray generation (volume_renderer.py:115-147) ------------------------------------- */
 /* pose: [4,4] c2w row-major, intrinsics: [3,3]; rays_o/rays_d: [H*W,3], ray id = y*W+x,
  * rays_d normalised (:140). */

@@ -25,6 +25,31 @@ int launch_mlp_fp32(const void* packed, const float* rays_o, const float* rays_d
 int launch_mlp_bf16(const void* packed, const float* rays_o, const float* rays_d, const float* z_vals,
                     int n_rays, int n_samples, float* raw, float* stage_dump, cudaStream_t st);
 
+// ---- optional MLP-kernel timing (bench.py roofline): CUDA events around every mlp launch, on
+// the launching stream, while enabled.  Off by default; the only other global state besides the
+// error string and the launch counter.
+constexpr int kProfMax = 8192;
+static bool g_prof_on = false;
+static cudaEvent_t g_prof_ev[2 * kProfMax];
+static int g_prof_created = 0, g_prof_n = 0;
+static double g_prof_rows = 0.0;
+
+static bool prof_begin(cudaStream_t st) {
+  if (!g_prof_on || g_prof_n >= kProfMax) return false;
+  while (g_prof_created <= g_prof_n) {
+    if (cudaEventCreate(&g_prof_ev[2 * g_prof_created]) != cudaSuccess) return false;
+    if (cudaEventCreate(&g_prof_ev[2 * g_prof_created + 1]) != cudaSuccess) return false;
+    ++g_prof_created;
+  }
+  cudaEventRecord(g_prof_ev[2 * g_prof_n], st);
+  return true;
+}
+static void prof_end(cudaStream_t st, double rows) {
+  cudaEventRecord(g_prof_ev[2 * g_prof_n + 1], st);
+  g_prof_rows += rows;
+  ++g_prof_n;
+}
+
 // rays per internal chunk of the whole-pass driver: keeps the per-chunk intermediates
 // (z, raw, weights: ~5.4 KB/ray) inside the 126 MB L2 and bounds the workspace.
 constexpr int kChunkRays = 8192;
@@ -83,10 +108,35 @@ extern "C" int nerfb200_mlp_forward(const void* packed, int mode, const float* r
   NB_CHECK_ARG(n_rays >= 0 && n_samples >= 1, "mlp_forward: bad sizes n_rays=%d n_samples=%d", n_rays, n_samples);
   NB_CHECK_ARG(((uintptr_t)packed & 1023) == 0, "mlp_forward: packed weights must be 1024-byte aligned");
   if (n_rays == 0) return 0;
-  if (mode == NERFB200_MODE_FP32) return launch_mlp_fp32(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, (cudaStream_t)stream);
-  if (mode == NERFB200_MODE_BF16) return launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, nullptr, (cudaStream_t)stream);
-  set_error("mlp_forward: unknown mode %d", mode);
-  return 1;
+  NB_CHECK_ARG(mode == NERFB200_MODE_FP32 || mode == NERFB200_MODE_BF16, "mlp_forward: unknown mode %d", mode);
+  cudaStream_t st = (cudaStream_t)stream;
+  bool prof = prof_begin(st);
+  int rc = mode == NERFB200_MODE_FP32 ? launch_mlp_fp32(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, st)
+                                      : launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, nullptr, st);
+  if (prof) prof_end(st, (double)n_rays * n_samples);
+  return rc;
+}
+
+extern "C" int nerfb200_profile_enable(int on) {
+  g_prof_on = on != 0;
+  g_prof_n = 0;
+  g_prof_rows = 0.0;
+  return 0;
+}
+
+extern "C" int nerfb200_profile_read(double* mlp_ms, uint64_t* mlp_launches, double* mlp_rows) {
+  NB_CHECK_ARG(mlp_ms && mlp_launches && mlp_rows, "profile_read: null pointer");
+  double total = 0.0;
+  for (int i = 0; i < g_prof_n; ++i) {
+    NB_CUDA(cudaEventSynchronize(g_prof_ev[2 * i + 1]));
+    float ms = 0.f;
+    NB_CUDA(cudaEventElapsedTime(&ms, g_prof_ev[2 * i], g_prof_ev[2 * i + 1]));
+    total += ms;
+  }
+  *mlp_ms = total;
+  *mlp_launches = (uint64_t)g_prof_n;
+  *mlp_rows = g_prof_rows;
+  return 0;
 }
 
 extern "C" int nerfb200_mlp_forward_stages(const void* packed, int mode, const float* rays_o, const float* rays_d,

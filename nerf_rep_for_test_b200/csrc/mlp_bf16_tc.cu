@@ -34,10 +34,11 @@ constexpr uint32_t kOffA = 0;
 constexpr uint32_t kOffPe = kOffA + 2 * kABytes;
 constexpr uint32_t kOffW = kOffPe + 2 * kPeBytes;
 constexpr uint32_t kOffBar = kOffW + kWStages * kWStageBytes;  // 229376
-constexpr uint32_t kSmemBytes = kOffBar + 128 + 1024;          // + barriers + alignment slack
+constexpr uint32_t kOffBias = kOffBar + 128;                   // 2 x 1 KB: fp32 bias of the stage in flight
+constexpr uint32_t kSmemBytes = kOffBias + 2048;               // 231552 <= 232448 (227 KB)
 
 // barrier slots (8 B each) at kOffBar
-enum { BAR_WFULL = 0, BAR_WEMPTY = 2, BAR_AREADY = 4, BAR_ACCFULL = 6, BAR_COUNT = 8 };
+enum { BAR_WFULL = 0, BAR_WEMPTY = 2, BAR_AREADY = 4, BAR_ACCFULL = 6, BAR_BFULL = 8, BAR_BEMPTY = 10, BAR_COUNT = 12 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -45,6 +46,79 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+// two fp32 -> packed bf16x2 (lo in bits 0-15), optionally with ReLU folded into the conversion
+template <bool kRelu>
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
+  uint32_t d;
+  if (kRelu) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+// registers written by an in-flight tcgen05.ld must not be touched before tcgen05.wait::ld; this
+// empty asm pins the 32 destination registers as "defined here" once the wait has retired
+__device__ __forceinline__ void pin32(uint32_t (&r)[32]) {
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+               "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
+  asm volatile("" : "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]),
+               "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]),
+               "+r"(r[31]));
+}
+
+// Epilogue of 32 accumulator columns of one row: + bias (fp32x2 adds, bias broadcast from shared
+// memory), activation folded into the bf16 pack, swizzled 16-byte stores into the next stage's A
+// operand.  MODE 0: ReLU; 1: ReLU + alpha_linear partial dot on the fp32 values (stage 7); 2: linear.
+template <int MODE>
+__device__ __forceinline__ void epi32(const uint32_t (&v)[32], uint32_t bias_saddr, uint32_t out_row, int j0, int r7,
+                                      const float* __restrict__ alpha_w, float& sigma) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float4 b0 = ld_shared_f4(bias_saddr + q * 32), b1 = ld_shared_f4(bias_saddr + q * 32 + 16);
+    float2 x0 = __fadd2_rn(make_float2(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1])), make_float2(b0.x, b0.y));
+    float2 x1 = __fadd2_rn(make_float2(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3])), make_float2(b0.z, b0.w));
+    float2 x2 = __fadd2_rn(make_float2(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5])), make_float2(b1.x, b1.y));
+    float2 x3 = __fadd2_rn(make_float2(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7])), make_float2(b1.z, b1.w));
+    if (MODE == 1) {
+      float4 a0 = __ldg(reinterpret_cast<const float4*>(alpha_w + q * 8)), a1 = __ldg(reinterpret_cast<const float4*>(alpha_w + q * 8 + 4));
+      sigma = fmaf(fmaxf(x0.x, 0.f), a0.x, sigma); sigma = fmaf(fmaxf(x0.y, 0.f), a0.y, sigma);
+      sigma = fmaf(fmaxf(x1.x, 0.f), a0.z, sigma); sigma = fmaf(fmaxf(x1.y, 0.f), a0.w, sigma);
+      sigma = fmaf(fmaxf(x2.x, 0.f), a1.x, sigma); sigma = fmaf(fmaxf(x2.y, 0.f), a1.y, sigma);
+      sigma = fmaf(fmaxf(x3.x, 0.f), a1.z, sigma); sigma = fmaf(fmaxf(x3.y, 0.f), a1.w, sigma);
+    }
+    constexpr bool kRelu = MODE != 2;
+    st_shared_v4(out_row + (uint32_t)(((j0 + q) ^ r7) << 4), cvt_bf16x2<kRelu>(x0.x, x0.y), cvt_bf16x2<kRelu>(x1.x, x1.y),
+                 cvt_bf16x2<kRelu>(x2.x, x2.y), cvt_bf16x2<kRelu>(x3.x, x3.y));
+  }
+}
+
+// one hidden stage (256 accumulator columns) with the TMEM loads double-buffered
+template <int MODE>
+__device__ __forceinline__ void epi_stage256(uint32_t t_acc, uint32_t bias_saddr, uint32_t a_row_base, int r7,
+                                             const float* __restrict__ alpha_w, float& sigma) {
+  uint32_t va[32], vb[32];
+  tmem_ld32(t_acc, va);
+  tmem_ld32(t_acc + 32u, vb);
+  tmem_ld_wait();
+  pin32(va);
+  pin32(vb);
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {   // K-block h of the A operand = columns 64h .. 64h+63
+    const uint32_t out_row = a_row_base + (uint32_t)h * 16384u;
+    epi32<MODE>(va, bias_saddr + (uint32_t)h * 256u, out_row, 0, r7, alpha_w + h * 64, sigma);
+    if (h < 3) tmem_ld32(t_acc + (uint32_t)(h * 64 + 64), va);
+    epi32<MODE>(vb, bias_saddr + (uint32_t)h * 256u + 128u, out_row, 4, r7, alpha_w + h * 64 + 32, sigma);
+    if (h < 3) {
+      tmem_ld32(t_acc + (uint32_t)(h * 64 + 96), vb);
+      tmem_ld_wait();
+      pin32(va);
+      pin32(vb);
+    }
+  }
 }
 
 // write `n8` 16-byte chunks (8 bf16 each) of one 128-byte swizzled row
@@ -85,12 +159,14 @@ __device__ __forceinline__ void pos_enc_row(const float (&x)[3], float* f) {
   }
 }
 
+template <bool kDump>
 __global__ void __launch_bounds__(kTcThreads, 1)
 mlp_bf16_tc_kernel(const unsigned char* __restrict__ packed, const float* __restrict__ rays_o,
                    const float* __restrict__ rays_d, const float* __restrict__ z_vals, long long M, int S,
                    int num_pairs, float* __restrict__ raw, float* __restrict__ stage_dump) {
-  extern __shared__ unsigned char smem_dyn[];
-  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  const uint32_t smem_base = smem_u32(smem_dyn);
+  if ((smem_base & 1023u) != 0) __trap();   // SWIZZLE_128B operands need 1024-byte alignment
   const uint32_t bar_base = smem_base + kOffBar;
   const uint32_t tmem_slot = bar_base + BAR_COUNT * 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -104,6 +180,8 @@ mlp_bf16_tc_kernel(const unsigned char* __restrict__ packed, const float* __rest
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar(BAR_AREADY + s), 128);
       mbar_init(bar(BAR_ACCFULL + s), 1);
+      mbar_init(bar(BAR_BFULL + s), 1);
+      mbar_init(bar(BAR_BEMPTY + s), 256);
     }
     fence_mbar_init();
   }
@@ -150,55 +228,35 @@ mlp_bf16_tc_kernel(const unsigned char* __restrict__ packed, const float* __rest
       fence_proxy_async_smem();
       mbar_arrive(b_ready);
       float sigma = 0.f;
+      const int r7 = row & 7;
+      const uint32_t a_row_base = a_base + (uint32_t)row * 128u;
       for (int stage = 0; stage < kStages; ++stage) {
+        // the stage's fp32 bias block, staged into shared memory by the producer warp
+        const uint32_t bseq = (uint32_t)it * kStages + (uint32_t)stage;
+        const uint32_t bbuf = bseq & 1u;
+        const uint32_t bias_saddr = smem_base + kOffBias + bbuf * 1024u;
+        mbar_wait(bar(BAR_BFULL + bbuf), (bseq >> 1) & 1u, 0x500 + stage);
         mbar_wait(b_full, full_phase, 0x100 + stage);
         full_phase ^= 1;
         tc_fence_after();
-        const float* bias = tail + kTailBias + stage * 256;
-        if (stage < 9) {
-          const bool relu = stage != 8;
-#pragma unroll 1
-          for (int cb = 0; cb < 8; ++cb) {
+        if (kDump && tile == 0) {   // diagnostic: fp32 post-activation outputs of rows 0..127
+          const int ncb = stage == 9 ? 4 : 8;
+          for (int cb = 0; cb < ncb; ++cb) {
             uint32_t v[32];
             tmem_ld32(t_acc + (uint32_t)cb * 32u, v);
             tmem_ld_wait();
-            float x[32];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + cb * 32 + q * 4));
-              x[q * 4 + 0] = __uint_as_float(v[q * 4 + 0]) + b4.x;
-              x[q * 4 + 1] = __uint_as_float(v[q * 4 + 1]) + b4.y;
-              x[q * 4 + 2] = __uint_as_float(v[q * 4 + 2]) + b4.z;
-              x[q * 4 + 3] = __uint_as_float(v[q * 4 + 3]) + b4.w;
-            }
-            if (relu) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) x[i] = fmaxf(x[i], 0.f);
-            }
-            if (stage_dump != nullptr && tile == 0) {  // diagnostic: fp32 stage outputs of rows 0..127
-#pragma unroll
-              for (int i = 0; i < 32; ++i) stage_dump[((size_t)stage * 128 + row) * 256 + cb * 32 + i] = x[i];
-            }
-            if (stage == 7) {  // alpha_linear on the fp32 activations (network.py:61)
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                float4 a4 = __ldg(reinterpret_cast<const float4*>(tail + kTailAlphaW + cb * 32 + q * 4));
-                sigma = fmaf(x[q * 4 + 0], a4.x, sigma);
-                sigma = fmaf(x[q * 4 + 1], a4.y, sigma);
-                sigma = fmaf(x[q * 4 + 2], a4.z, sigma);
-                sigma = fmaf(x[q * 4 + 3], a4.w, sigma);
-              }
-            }
-            // columns cb*32.. of the next stage's A operand: K-block cb/2, 16-B chunks (cb&1)*4+q
-            const uint32_t row_base = a_base + (uint32_t)(cb >> 1) * 16384u + (uint32_t)row * 128u;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              int j = (cb & 1) * 4 + q;
-              st_shared_v4(row_base + (uint32_t)((j ^ (row & 7)) << 4),
-                           pack_bf16x2(x[q * 8 + 0], x[q * 8 + 1]), pack_bf16x2(x[q * 8 + 2], x[q * 8 + 3]),
-                           pack_bf16x2(x[q * 8 + 4], x[q * 8 + 5]), pack_bf16x2(x[q * 8 + 6], x[q * 8 + 7]));
+            pin32(v);
+            for (int i = 0; i < 32; ++i) {
+              float x = __uint_as_float(v[i]) + tail[kTailBias + stage * 256 + cb * 32 + i];
+              if (stage != 8) x = fmaxf(x, 0.f);
+              stage_dump[((size_t)stage * 128 + row) * 256 + cb * 32 + i] = x;
             }
           }
+        }
+        if (stage < 9) {
+          if (stage == 7) epi_stage256<1>(t_acc, bias_saddr, a_row_base, r7, tail + kTailAlphaW, sigma);
+          else if (stage == 8) epi_stage256<2>(t_acc, bias_saddr, a_row_base, r7, nullptr, sigma);
+          else epi_stage256<0>(t_acc, bias_saddr, a_row_base, r7, nullptr, sigma);
           if (stage == 8) {  // dir PE replaces the xyz PE tile (dead after stage 5) for stage 9
             float f[32];
             pos_enc_row<kLd>(d, f);
@@ -209,6 +267,7 @@ mlp_bf16_tc_kernel(const unsigned char* __restrict__ packed, const float* __rest
           tc_fence_before();
           fence_proxy_async_smem();
           mbar_arrive(b_ready);
+          mbar_arrive(bar(BAR_BEMPTY + bbuf));
         } else {
           // stage 9: views_linears.0 (128 wide, relu) -> rgb_linear on CUDA cores (network.py:66-69)
           float r0 = 0.f, r1 = 0.f, r2 = 0.f;
@@ -217,10 +276,11 @@ mlp_bf16_tc_kernel(const unsigned char* __restrict__ packed, const float* __rest
             uint32_t v[32];
             tmem_ld32(t_acc + (uint32_t)cb * 32u, v);
             tmem_ld_wait();
+            pin32(v);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               int n = cb * 32 + q * 4;
-              float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
+              float4 b4 = ld_shared_f4(bias_saddr + (uint32_t)n * 4u);
               float4 w0 = __ldg(reinterpret_cast<const float4*>(tail + kTailRgbW + n));
               float4 w1 = __ldg(reinterpret_cast<const float4*>(tail + kTailRgbW + 128 + n));
               float4 w2 = __ldg(reinterpret_cast<const float4*>(tail + kTailRgbW + 256 + n));
@@ -231,13 +291,10 @@ mlp_bf16_tc_kernel(const unsigned char* __restrict__ packed, const float* __rest
               r0 = fmaf(h0, w0.x, r0); r0 = fmaf(h1, w0.y, r0); r0 = fmaf(h2, w0.z, r0); r0 = fmaf(h3, w0.w, r0);
               r1 = fmaf(h0, w1.x, r1); r1 = fmaf(h1, w1.y, r1); r1 = fmaf(h2, w1.z, r1); r1 = fmaf(h3, w1.w, r1);
               r2 = fmaf(h0, w2.x, r2); r2 = fmaf(h1, w2.y, r2); r2 = fmaf(h2, w2.z, r2); r2 = fmaf(h3, w2.w, r2);
-              if (stage_dump != nullptr && tile == 0) {
-                float* o = stage_dump + ((size_t)9 * 128 + row) * 256 + n;
-                o[0] = h0; o[1] = h1; o[2] = h2; o[3] = h3;
-              }
             }
           }
           tc_fence_before();
+          mbar_arrive(bar(BAR_BEMPTY + bbuf));
           if (valid) {
             float4 o = make_float4(r0 + tail[kTailRgbB + 0], r1 + tail[kTailRgbB + 1], r2 + tail[kTailRgbB + 2],
                                    sigma + tail[kTailAlphaB]);
@@ -248,10 +305,22 @@ mlp_bf16_tc_kernel(const unsigned char* __restrict__ packed, const float* __rest
     }
   } else if (warp == 8) {
     // =========================== weight producer ===========================
-    if (lane == 0) {
-      uint32_t ring = 0, phase = 0;
-      for (int it = 0; it < my_pairs; ++it) {
-        for (int stage = 0; stage < kStages; ++stage) {
+    uint32_t ring = 0, phase = 0, bseq = 0;
+    for (int it = 0; it < my_pairs; ++it) {
+      for (int stage = 0; stage < kStages; ++stage, ++bseq) {
+        {  // fp32 bias block of this stage -> bias buffer bseq&1 (all 32 lanes, 2 x float4 each)
+          const uint32_t bbuf = bseq & 1u;
+          if (lane == 0) mbar_wait(bar(BAR_BEMPTY + bbuf), ((bseq >> 1) & 1u) ^ 1u, 0x600 + stage);
+          __syncwarp();
+          const float4* src4 = reinterpret_cast<const float4*>(tail + kTailBias + stage * 256);
+          float4 v0 = __ldg(src4 + lane), v1 = __ldg(src4 + 32 + lane);
+          const uint32_t dst = smem_base + kOffBias + bbuf * 1024u + (uint32_t)lane * 16u;
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(v0.x), "f"(v0.y), "f"(v0.z), "f"(v0.w) : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 512u), "f"(v1.x), "f"(v1.y), "f"(v1.z), "f"(v1.w) : "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(BAR_BFULL + bbuf));
+        }
+        if (lane == 0) {
           const uint32_t bytes = (uint32_t)bf16_chunk_bytes(stage);
           const unsigned char* src = packed + bf16_stage_off(stage);
           const int nch = stage_chunks(stage);
@@ -262,9 +331,9 @@ mlp_bf16_tc_kernel(const unsigned char* __restrict__ packed, const float* __rest
             if (++ring == kWStages) { ring = 0; phase ^= 1; }
           }
         }
+        __syncwarp();
       }
     }
-    __syncwarp();
   } else {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
@@ -324,13 +393,18 @@ int launch_mlp_bf16(const void* packed, const float* rays_o, const float* rays_d
   int dev = 0, sms = 0;
   NB_CUDA(cudaGetDevice(&dev));
   NB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   long long M = (long long)n_rays * n_samples;
   long long tiles = (M + kTileRows - 1) / kTileRows;
   int pairs = (int)((tiles + 1) / 2);
   int grid = pairs < sms ? pairs : sms;
-  mlp_bf16_tc_kernel<<<grid, kTcThreads, kSmemBytes, st>>>((const unsigned char*)packed, rays_o, rays_d, z_vals, M,
-                                                          n_samples, pairs, raw, stage_dump);
+  if (stage_dump)
+    mlp_bf16_tc_kernel<true><<<grid, kTcThreads, kSmemBytes, st>>>((const unsigned char*)packed, rays_o, rays_d, z_vals,
+                                                                  M, n_samples, pairs, raw, stage_dump);
+  else
+    mlp_bf16_tc_kernel<false><<<grid, kTcThreads, kSmemBytes, st>>>((const unsigned char*)packed, rays_o, rays_d, z_vals,
+                                                                   M, n_samples, pairs, raw, nullptr);
   NB_LAUNCH_OK("mlp_bf16_tc_kernel");
   return 0;
 }

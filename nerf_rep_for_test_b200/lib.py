@@ -44,6 +44,8 @@ SIGNATURES = {
     "nerfb200_abi_version": (C.c_int, []),
     "nerfb200_get_last_error_string": (C.c_char_p, []),
     "nerfb200_launch_count": (C.c_uint64, []),
+    "nerfb200_profile_enable": (C.c_int, [C.c_int]),
+    "nerfb200_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
     "nerfb200_raygen": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "nerfb200_sample_coarse": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_uint64, _vp, _vp]),
     "nerfb200_packed_weights_bytes": (C.c_size_t, [C.c_int]),
@@ -95,6 +97,17 @@ def check(rc, what=""):
     if rc != 0:
         msg = load().nerfb200_get_last_error_string().decode("utf-8", "replace")
         raise NerfB200Error("%s failed (code %d): %s" % (what or "libnerfb200 call", rc, msg))
+
+
+def profile_enable(on):
+    check(load().nerfb200_profile_enable(int(bool(on))), "profile_enable")
+
+
+def profile_read():
+    """(total MLP-kernel ms, launches, MLP rows) since profile_enable(True)."""
+    ms, n, rows = C.c_double(), C.c_uint64(), C.c_double()
+    check(load().nerfb200_profile_read(C.byref(ms), C.byref(n), C.byref(rows)), "profile_read")
+    return ms.value, int(n.value), rows.value
 
 
 def launch_count():
