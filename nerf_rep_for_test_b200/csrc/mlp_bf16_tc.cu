@@ -19,6 +19,7 @@
 //   PE[slot]  16 KB  [128][64] bf16: xyz PE for stages 0 and 5, later reused for the dir PE
 //   W[2]      32 KB  weight ring stages, each one K-chunk [N rows][64 k] of the packed image
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "mlp_layout.cuh"
 #include "tc_ptx.cuh"
@@ -73,33 +74,44 @@ __device__ __forceinline__ void pin32(uint32_t (&r)[32]) {
 // Epilogue of 32 accumulator columns of one row: + bias (fp32x2 adds, bias broadcast from shared
 // memory), activation folded into the bf16 pack, swizzled 16-byte stores into the next stage's A
 // operand.  MODE 0: ReLU; 1: ReLU + alpha_linear partial dot on the fp32 values (stage 7); 2: linear.
+// Plain C++ shared-memory accesses (not volatile asm) so the compiler batches the bias loads.
 template <int MODE>
-__device__ __forceinline__ void epi32(const uint32_t (&v)[32], uint32_t bias_saddr, uint32_t out_row, int j0, int r7,
-                                      const float* __restrict__ alpha_w, float& sigma) {
+__device__ __forceinline__ void epi32(const uint32_t (&v)[32], const float4* __restrict__ bias4, unsigned char* out_row,
+                                      int j0, int r7, const float* __restrict__ alpha_w, float& sigma) {
+  float4 b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = bias4[i];
+  float4 aw[8];
+  if (MODE == 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) aw[i] = __ldg(reinterpret_cast<const float4*>(alpha_w) + i);
+  }
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    float4 b0 = ld_shared_f4(bias_saddr + q * 32), b1 = ld_shared_f4(bias_saddr + q * 32 + 16);
+    const float4 b0 = b[2 * q], b1 = b[2 * q + 1];
     float2 x0 = __fadd2_rn(make_float2(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1])), make_float2(b0.x, b0.y));
     float2 x1 = __fadd2_rn(make_float2(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3])), make_float2(b0.z, b0.w));
     float2 x2 = __fadd2_rn(make_float2(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5])), make_float2(b1.x, b1.y));
     float2 x3 = __fadd2_rn(make_float2(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7])), make_float2(b1.z, b1.w));
     if (MODE == 1) {
-      float4 a0 = __ldg(reinterpret_cast<const float4*>(alpha_w + q * 8)), a1 = __ldg(reinterpret_cast<const float4*>(alpha_w + q * 8 + 4));
+      const float4 a0 = aw[2 * q], a1 = aw[2 * q + 1];
       sigma = fmaf(fmaxf(x0.x, 0.f), a0.x, sigma); sigma = fmaf(fmaxf(x0.y, 0.f), a0.y, sigma);
       sigma = fmaf(fmaxf(x1.x, 0.f), a0.z, sigma); sigma = fmaf(fmaxf(x1.y, 0.f), a0.w, sigma);
       sigma = fmaf(fmaxf(x2.x, 0.f), a1.x, sigma); sigma = fmaf(fmaxf(x2.y, 0.f), a1.y, sigma);
       sigma = fmaf(fmaxf(x3.x, 0.f), a1.z, sigma); sigma = fmaf(fmaxf(x3.y, 0.f), a1.w, sigma);
     }
     constexpr bool kRelu = MODE != 2;
-    st_shared_v4(out_row + (uint32_t)(((j0 + q) ^ r7) << 4), cvt_bf16x2<kRelu>(x0.x, x0.y), cvt_bf16x2<kRelu>(x1.x, x1.y),
-                 cvt_bf16x2<kRelu>(x2.x, x2.y), cvt_bf16x2<kRelu>(x3.x, x3.y));
+    uint4 o;
+    o.x = cvt_bf16x2<kRelu>(x0.x, x0.y); o.y = cvt_bf16x2<kRelu>(x1.x, x1.y);
+    o.z = cvt_bf16x2<kRelu>(x2.x, x2.y); o.w = cvt_bf16x2<kRelu>(x3.x, x3.y);
+    *reinterpret_cast<uint4*>(out_row + (((j0 + q) ^ r7) << 4)) = o;
   }
 }
 
 // one hidden stage (256 accumulator columns) with the TMEM loads double-buffered
 template <int MODE>
-__device__ __forceinline__ void epi_stage256(uint32_t t_acc, uint32_t bias_saddr, uint32_t a_row_base, int r7,
-                                             const float* __restrict__ alpha_w, float& sigma) {
+__device__ __forceinline__ void epi_stage256(uint32_t t_acc, const float4* __restrict__ bias4, unsigned char* a_row_base,
+                                             int r7, const float* __restrict__ alpha_w, float& sigma) {
   uint32_t va[32], vb[32];
   tmem_ld32(t_acc, va);
   tmem_ld32(t_acc + 32u, vb);
@@ -108,10 +120,10 @@ __device__ __forceinline__ void epi_stage256(uint32_t t_acc, uint32_t bias_saddr
   pin32(vb);
 #pragma unroll
   for (int h = 0; h < 4; ++h) {   // K-block h of the A operand = columns 64h .. 64h+63
-    const uint32_t out_row = a_row_base + (uint32_t)h * 16384u;
-    epi32<MODE>(va, bias_saddr + (uint32_t)h * 256u, out_row, 0, r7, alpha_w + h * 64, sigma);
+    unsigned char* out_row = a_row_base + h * 16384;
+    epi32<MODE>(va, bias4 + h * 16, out_row, 0, r7, alpha_w + h * 64, sigma);
     if (h < 3) tmem_ld32(t_acc + (uint32_t)(h * 64 + 64), va);
-    epi32<MODE>(vb, bias_saddr + (uint32_t)h * 256u + 128u, out_row, 4, r7, alpha_w + h * 64 + 32, sigma);
+    epi32<MODE>(vb, bias4 + h * 16 + 8, out_row, 4, r7, alpha_w + h * 64 + 32, sigma);
     if (h < 3) {
       tmem_ld32(t_acc + (uint32_t)(h * 64 + 96), vb);
       tmem_ld_wait();
@@ -163,7 +175,8 @@ template <bool kDump>
 __global__ void __launch_bounds__(kTcThreads, 1)
 mlp_bf16_tc_kernel(const unsigned char* __restrict__ packed, const float* __restrict__ rays_o,
                    const float* __restrict__ rays_d, const float* __restrict__ z_vals, long long M, int S,
-                   int num_pairs, float* __restrict__ raw, float* __restrict__ stage_dump) {
+                   int num_pairs, float* __restrict__ raw, float* __restrict__ stage_dump, int dbg,
+                   unsigned long long* __restrict__ tl) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   const uint32_t smem_base = smem_u32(smem_dyn);
   if ((smem_base & 1023u) != 0) __trap();   // SWIZZLE_128B operands need 1024-byte alignment
@@ -229,16 +242,17 @@ mlp_bf16_tc_kernel(const unsigned char* __restrict__ packed, const float* __rest
       mbar_arrive(b_ready);
       float sigma = 0.f;
       const int r7 = row & 7;
-      const uint32_t a_row_base = a_base + (uint32_t)row * 128u;
+      unsigned char* a_row_base = smem_dyn + kOffA + (uint32_t)slot * kABytes + (uint32_t)row * 128u;
       for (int stage = 0; stage < kStages; ++stage) {
         // the stage's fp32 bias block, staged into shared memory by the producer warp
         const uint32_t bseq = (uint32_t)it * kStages + (uint32_t)stage;
         const uint32_t bbuf = bseq & 1u;
-        const uint32_t bias_saddr = smem_base + kOffBias + bbuf * 1024u;
+        const float4* bias4 = reinterpret_cast<const float4*>(smem_dyn + kOffBias + bbuf * 1024u);
         mbar_wait(bar(BAR_BFULL + bbuf), (bseq >> 1) & 1u, 0x500 + stage);
         mbar_wait(b_full, full_phase, 0x100 + stage);
         full_phase ^= 1;
         tc_fence_after();
+        if (tl && blockIdx.x == 0 && it < 4 && row == 0) tl[((it * 10 + stage) * 2 + slot) * 4 + 2] = clock64();
         if (kDump && tile == 0) {   // diagnostic: fp32 post-activation outputs of rows 0..127
           const int ncb = stage == 9 ? 4 : 8;
           for (int cb = 0; cb < ncb; ++cb) {
@@ -253,10 +267,16 @@ mlp_bf16_tc_kernel(const unsigned char* __restrict__ packed, const float* __rest
             }
           }
         }
+        if ((dbg & 2) && it > 0) {
+          tc_fence_before();
+          if (stage < 9) { fence_proxy_async_smem(); mbar_arrive(b_ready); }
+          mbar_arrive(bar(BAR_BEMPTY + bbuf));
+          continue;
+        }
         if (stage < 9) {
-          if (stage == 7) epi_stage256<1>(t_acc, bias_saddr, a_row_base, r7, tail + kTailAlphaW, sigma);
-          else if (stage == 8) epi_stage256<2>(t_acc, bias_saddr, a_row_base, r7, nullptr, sigma);
-          else epi_stage256<0>(t_acc, bias_saddr, a_row_base, r7, nullptr, sigma);
+          if (stage == 7) epi_stage256<1>(t_acc, bias4, a_row_base, r7, tail + kTailAlphaW, sigma);
+          else if (stage == 8) epi_stage256<2>(t_acc, bias4, a_row_base, r7, nullptr, sigma);
+          else epi_stage256<0>(t_acc, bias4, a_row_base, r7, nullptr, sigma);
           if (stage == 8) {  // dir PE replaces the xyz PE tile (dead after stage 5) for stage 9
             float f[32];
             pos_enc_row<kLd>(d, f);
@@ -268,10 +288,11 @@ mlp_bf16_tc_kernel(const unsigned char* __restrict__ packed, const float* __rest
           fence_proxy_async_smem();
           mbar_arrive(b_ready);
           mbar_arrive(bar(BAR_BEMPTY + bbuf));
+          if (tl && blockIdx.x == 0 && it < 4 && row == 0) tl[((it * 10 + stage) * 2 + slot) * 4 + 3] = clock64();
         } else {
           // stage 9: views_linears.0 (128 wide, relu) -> rgb_linear on CUDA cores (network.py:66-69)
           float r0 = 0.f, r1 = 0.f, r2 = 0.f;
-#pragma unroll 1
+#pragma unroll 2
           for (int cb = 0; cb < 4; ++cb) {
             uint32_t v[32];
             tmem_ld32(t_acc + (uint32_t)cb * 32u, v);
@@ -280,7 +301,7 @@ mlp_bf16_tc_kernel(const unsigned char* __restrict__ packed, const float* __rest
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               int n = cb * 32 + q * 4;
-              float4 b4 = ld_shared_f4(bias_saddr + (uint32_t)n * 4u);
+              float4 b4 = bias4[cb * 8 + q];
               float4 w0 = __ldg(reinterpret_cast<const float4*>(tail + kTailRgbW + n));
               float4 w1 = __ldg(reinterpret_cast<const float4*>(tail + kTailRgbW + 128 + n));
               float4 w2 = __ldg(reinterpret_cast<const float4*>(tail + kTailRgbW + 256 + n));
@@ -326,8 +347,11 @@ mlp_bf16_tc_kernel(const unsigned char* __restrict__ packed, const float* __rest
           const int nch = stage_chunks(stage);
           for (int c = 0; c < nch; ++c) {
             mbar_wait(bar(BAR_WEMPTY + ring), phase ^ 1, 0x200 + stage);
+            if ((dbg & 1) && it > 0) { mbar_arrive(bar(BAR_WFULL + ring)); }
+            else {
             mbar_arrive_expect_tx(bar(BAR_WFULL + ring), bytes);
             bulk_g2s(smem_base + kOffW + ring * kWStageBytes, src + (size_t)c * bytes, bytes, bar(BAR_WFULL + ring));
+            }
             if (++ring == kWStages) { ring = 0; phase ^= 1; }
           }
         }
@@ -357,8 +381,10 @@ mlp_bf16_tc_kernel(const unsigned char* __restrict__ packed, const float* __rest
 #pragma unroll 1
             for (int slot = 0; slot < 2; ++slot) {
               if (c == 0) {
+                if (tl && blockIdx.x == 0 && it < 4) tl[((it * 10 + stage) * 2 + slot) * 4 + 0] = clock64();
                 mbar_wait(bar(BAR_AREADY + slot), ready_phase, 0x400 + stage * 2 + slot);
                 tc_fence_after();
+                if (tl && blockIdx.x == 0 && it < 4) tl[((it * 10 + stage) * 2 + slot) * 4 + 1] = clock64();
               }
               const uint32_t a_addr = from_pe ? (smem_base + kOffPe + (uint32_t)slot * kPeBytes)
                                               : (smem_base + kOffA + (uint32_t)slot * kABytes + (uint32_t)kblock * 16384u);
@@ -395,16 +421,36 @@ int launch_mlp_bf16(const void* packed, const float* rays_o, const float* rays_d
   NB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  const char* tl_env = getenv("NERFB200_TIMELINE");
+  unsigned long long* tl = nullptr;
+  if (tl_env && !stage_dump) {
+    cudaMalloc(&tl, 4 * 10 * 2 * 4 * 8);
+    cudaMemset(tl, 0, 4 * 10 * 2 * 4 * 8);
+  }
+  const char* dbg_env = getenv("NERFB200_DEBUG_FLAGS");
+  int dbg = dbg_env ? atoi(dbg_env) : 0;
   long long M = (long long)n_rays * n_samples;
   long long tiles = (M + kTileRows - 1) / kTileRows;
   int pairs = (int)((tiles + 1) / 2);
   int grid = pairs < sms ? pairs : sms;
   if (stage_dump)
     mlp_bf16_tc_kernel<true><<<grid, kTcThreads, kSmemBytes, st>>>((const unsigned char*)packed, rays_o, rays_d, z_vals,
-                                                                  M, n_samples, pairs, raw, stage_dump);
+                                                                  M, n_samples, pairs, raw, stage_dump, dbg, nullptr);
   else
     mlp_bf16_tc_kernel<false><<<grid, kTcThreads, kSmemBytes, st>>>((const unsigned char*)packed, rays_o, rays_d, z_vals,
-                                                                   M, n_samples, pairs, raw, nullptr);
+                                                                   M, n_samples, pairs, raw, nullptr, dbg, tl);
+  if (tl) {   // debug only (NERFB200_TIMELINE=<file>): dump CTA 0's handshake timestamps
+    unsigned long long host[4 * 10 * 2 * 4];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(host, tl, sizeof(host), cudaMemcpyDeviceToHost);
+    cudaFree(tl);
+    FILE* f = fopen(tl_env, "w");
+    if (f) {
+      for (int i = 0; i < 4 * 10 * 2; ++i)
+        fprintf(f, "%d %d %d %llu %llu %llu %llu\n", i / 20, (i / 2) % 10, i % 2, host[i * 4], host[i * 4 + 1], host[i * 4 + 2], host[i * 4 + 3]);
+      fclose(f);
+    }
+  }
   NB_LAUNCH_OK("mlp_bf16_tc_kernel");
   return 0;
 }
