@@ -44,7 +44,7 @@ __device__ __forceinline__ void chunk_src(int stage, int c, bool& from_pe, int& 
   else { from_pe = false; kblock = c; }
 }
 
-template <bool kDump>
+template <bool kDump, bool kTimeline>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __restrict__ rays_o,
                     const float* __restrict__ rays_d, const float* __restrict__ z_vals, long long M, int S,
@@ -147,7 +147,7 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
         mbar_wait(b_full, full_phase, 0x100 + stage);
         full_phase ^= 1;
         tc_fence_after();
-        if (tl && blockIdx.x == 0 && it < 4 && row == 0) tl[((it * 10 + stage) * 2 + slot) * 4 + 2] = clock64();
+        if (kTimeline && tl && blockIdx.x == 0 && it < 4 && row == 0) tl[((it * 10 + stage) * 2 + slot) * 4 + 2] = clock64();
         if (kDump) {   // diagnostic: fp32 post-activation outputs of rows 0..127 of the whole problem
           if (m_cur - row == 0) {
             const int ncb = stage == 9 ? 4 : 8;
@@ -179,7 +179,7 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
           fence_proxy_async_smem();
           mbar_arrive_remote(b_ready_leader);
           mbar_arrive(bar(BAR_BEMPTY + bbuf));
-          if (tl && blockIdx.x == 0 && it < 4 && row == 0) tl[((it * 10 + stage) * 2 + slot) * 4 + 3] = clock64();
+          if (kTimeline && tl && blockIdx.x == 0 && it < 4 && row == 0) tl[((it * 10 + stage) * 2 + slot) * 4 + 3] = clock64();
         } else {
           // stage 9: views_linears.0 (128 wide, relu) -> rgb_linear on CUDA cores (network.py:66-69)
           float r0 = 0.f, r1 = 0.f, r2 = 0.f;
@@ -264,54 +264,65 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
     __syncwarp();
   } else {
     // =========================== MMA issuer (leader CTA) ===========================
-    if (lane == 0) {
-      uint32_t seq = 0, ready_phase = 0;
-      for (int it = 0; it < my_quads; ++it) {
-        for (int stage = 0; stage < kStages; ++stage) {
-          const int nch = stage_chunks(stage);
-          const uint32_t idesc = umma_idesc_bf16(256, stage_n(stage));
-          // chunk groups of at most kRing chunks: slot 0 runs the group, then slot 1 runs it and releases it
-          for (int g0 = 0; g0 < nch; g0 += kRing) {
-            const int g1 = (g0 + kRing < nch) ? g0 + kRing : nch;
+    // The whole warp walks the schedule (waits are warp-uniform); one elected lane issues the MMAs and
+    // commits.  A single thread's instruction latency is the limit here (measured: ~200 cycles per MMA
+    // when every descriptor is rebuilt with shifts/masks inside a divergent lane-0 region), so the
+    // descriptors are reduced to "constant high word + precomputed low word + 2*kstep".
+    uint32_t seq = 0, ready_phase = 0;
+    const uint32_t desc_hi = (uint32_t)(umma_desc_sw128(0) >> 32);
+    const uint32_t lo_flags = (uint32_t)(umma_desc_sw128(0) & 0xFFFFFFFFu);   // LBO field
+    const uint32_t a_lo0 = lo_flags | ((smem_base + kOffA) >> 4);     // + slot*4096 + kblock*1024 + 2*k
+    const uint32_t pe_lo0 = lo_flags | ((smem_base + kOffPe) >> 4);   // + slot*1024 + 2*k
+    const uint32_t w_lo0 = lo_flags | ((smem_base + kOffW) >> 4);     // + pos*1024 + 2*k
+    for (int it = 0; it < my_quads; ++it) {
+      for (int stage = 0; stage < kStages; ++stage) {
+        const int nch = stage_chunks(stage);
+        const uint32_t idesc = umma_idesc_bf16(256, stage_n(stage));
+        // chunk groups of at most kRing chunks: slot 0 runs the group, then slot 1 runs it and releases it
+        for (int g0 = 0; g0 < nch; g0 += kRing) {
+          const int g1 = (g0 + kRing < nch) ? g0 + kRing : nch;
 #pragma unroll 1
-            for (int slot = 0; slot < 2; ++slot) {
-              if (g0 == 0) {
-                if (tl && blockIdx.x == 0 && it < 4) tl[((it * 10 + stage) * 2 + slot) * 4 + 0] = clock64();
-                mbar_wait_cluster(bar(BAR_AREADY + slot), ready_phase, 0x400 + stage * 2 + slot);
-                tc_fence_after();
-                if (tl && blockIdx.x == 0 && it < 4) tl[((it * 10 + stage) * 2 + slot) * 4 + 1] = clock64();
-              }
-              const uint32_t d_tmem = tmem_base + (uint32_t)slot * 256u;
-              for (int c = g0; c < g1; ++c) {
-                const uint32_t cs = seq + (uint32_t)(c - g0);
-                const uint32_t pos = cs % kRing, phase = (cs / kRing) & 1u;
-                if (slot == 0) {
-                  mbar_wait_cluster(bar(BAR_WFULL + pos), phase, 0x300 + stage);
-                  tc_fence_after();
-                }
-                bool from_pe;
-                int kblock, ksteps;
-                chunk_src(stage, c, from_pe, kblock, ksteps);
-                const uint32_t w_addr = smem_base + kOffW + pos * kWStageBytes;
-                const uint32_t a_addr = from_pe ? (smem_base + kOffPe + (uint32_t)slot * kPeBytes)
-                                                : (smem_base + kOffA + (uint32_t)slot * kABytes + (uint32_t)kblock * 16384u);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  if (k < ksteps)
-                    umma_bf16_ss_2cta(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(w_addr + k * 32), idesc,
-                                      (c > 0 || k > 0) ? 1u : 0u);
-                }
-                if (slot == 1) umma_commit_2cta(bar(BAR_WEMPTY + pos), 3);   // both CTAs' producers
-              }
-              if (g1 == nch) umma_commit_2cta(bar(BAR_ACCFULL + slot), 3);   // both CTAs' epilogue groups
+          for (int slot = 0; slot < 2; ++slot) {
+            if (g0 == 0) {
+              if (kTimeline && tl && blockIdx.x == 0 && it < 4 && lane == 0) tl[((it * 10 + stage) * 2 + slot) * 4 + 0] = clock64();
+              mbar_wait_cluster(bar(BAR_AREADY + slot), ready_phase, 0x400 + stage * 2 + slot);
+              tc_fence_after();
+              if (kTimeline && tl && blockIdx.x == 0 && it < 4 && lane == 0) tl[((it * 10 + stage) * 2 + slot) * 4 + 1] = clock64();
             }
-            seq += (uint32_t)(g1 - g0);
+            const uint32_t d_tmem = tmem_base + (uint32_t)slot * 256u;
+#pragma unroll 1
+            for (int c = g0; c < g1; ++c) {
+              const uint32_t cs = seq + (uint32_t)(c - g0);
+              const uint32_t pos = cs % kRing, phase = (cs / kRing) & 1u;
+              if (slot == 0) {
+                mbar_wait_cluster(bar(BAR_WFULL + pos), phase, 0x300 + stage);
+                tc_fence_after();
+              }
+              bool from_pe;
+              int kblock, ksteps;
+              chunk_src(stage, c, from_pe, kblock, ksteps);
+              const uint32_t a_lo = from_pe ? (pe_lo0 + (uint32_t)slot * (kPeBytes >> 4))
+                                            : (a_lo0 + (uint32_t)slot * (kABytes >> 4) + (uint32_t)kblock * 1024u);
+              const uint32_t b_lo = w_lo0 + pos * (kWStageBytes >> 4);
+              if (elect_one()) {
+                const uint64_t hi64 = (uint64_t)desc_hi << 32;
+                umma_bf16_ss_2cta(d_tmem, hi64 | (a_lo + 0u), hi64 | (b_lo + 0u), idesc, c > 0 ? 1u : 0u);
+                umma_bf16_ss_2cta(d_tmem, hi64 | (a_lo + 2u), hi64 | (b_lo + 2u), idesc, 1u);
+                if (ksteps == 4) {
+                  umma_bf16_ss_2cta(d_tmem, hi64 | (a_lo + 4u), hi64 | (b_lo + 4u), idesc, 1u);
+                  umma_bf16_ss_2cta(d_tmem, hi64 | (a_lo + 6u), hi64 | (b_lo + 6u), idesc, 1u);
+                }
+                if (slot == 1) umma_commit_2cta(bar(BAR_WEMPTY + pos), 3);                 // both CTAs' producers
+                if (c == nch - 1) umma_commit_2cta(bar(BAR_ACCFULL + slot), 3);           // both CTAs' epilogue groups
+              }
+              __syncwarp();
+            }
           }
-          ready_phase ^= 1;
+          seq += (uint32_t)(g1 - g0);
         }
+        ready_phase ^= 1;
       }
     }
-    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
@@ -336,8 +347,9 @@ int launch_mlp_bf16(const void* packed, const float* rays_o, const float* rays_d
   int dev = 0, sms = 0;
   NB_CUDA(cudaGetDevice(&dev));
   NB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-  NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   const char* tl_env = getenv("NERFB200_TIMELINE");
   unsigned long long* tl = nullptr;
   if (tl_env && !stage_dump) {
@@ -347,12 +359,19 @@ int launch_mlp_bf16(const void* packed, const float* rays_o, const float* rays_d
   long long M = (long long)n_rays * n_samples;
   long long quads = (M + 511) / 512;
   int clusters = (int)(quads < sms / 2 ? quads : sms / 2);
+  if (const char* mc = getenv("NERFB200_MAX_CLUSTERS")) {   // debug: restrict the number of active TPCs
+    int v = atoi(mc);
+    if (v > 0 && v < clusters) clusters = v;
+  }
   if (stage_dump)
-    mlp_bf16_tc2_kernel<true><<<2 * clusters, kThreads, kSmemBytes, st>>>((const unsigned char*)packed, rays_o, rays_d,
-                                                                         z_vals, M, n_samples, (int)quads, raw, stage_dump, nullptr);
+    mlp_bf16_tc2_kernel<true, false><<<2 * clusters, kThreads, kSmemBytes, st>>>(
+        (const unsigned char*)packed, rays_o, rays_d, z_vals, M, n_samples, (int)quads, raw, stage_dump, nullptr);
+  else if (tl)
+    mlp_bf16_tc2_kernel<false, true><<<2 * clusters, kThreads, kSmemBytes, st>>>(
+        (const unsigned char*)packed, rays_o, rays_d, z_vals, M, n_samples, (int)quads, raw, nullptr, tl);
   else
-    mlp_bf16_tc2_kernel<false><<<2 * clusters, kThreads, kSmemBytes, st>>>((const unsigned char*)packed, rays_o, rays_d,
-                                                                          z_vals, M, n_samples, (int)quads, raw, nullptr, tl);
+    mlp_bf16_tc2_kernel<false, false><<<2 * clusters, kThreads, kSmemBytes, st>>>(
+        (const unsigned char*)packed, rays_o, rays_d, z_vals, M, n_samples, (int)quads, raw, nullptr, nullptr);
   NB_LAUNCH_OK("mlp_bf16_tc2_kernel");
   if (tl) {   // debug only (NERFB200_TIMELINE=<file>): dump cluster 0's handshake timestamps
     unsigned long long host[4 * 10 * 2 * 4];
