@@ -295,8 +295,14 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
               const uint32_t cs = seq + (uint32_t)(c - g0);
               const uint32_t pos = cs % kRing, phase = (cs / kRing) & 1u;
               if (slot == 0) {
+                long long tw0 = 0;
+                if (kTimeline && tl && blockIdx.x == 0 && it < 4 && lane == 0) tw0 = clock64();
                 mbar_wait_cluster(bar(BAR_WFULL + pos), phase, 0x300 + stage);
                 tc_fence_after();
+                if (kTimeline && tl && blockIdx.x == 0 && it < 4 && lane == 0) {
+                  tl[320 + ((it * 10 + stage) * 5 + c) * 2 + 0] = tw0;
+                  tl[320 + ((it * 10 + stage) * 5 + c) * 2 + 1] = clock64();
+                }
               }
               bool from_pe;
               int kblock, ksteps;
@@ -353,8 +359,8 @@ int launch_mlp_bf16(const void* packed, const float* rays_o, const float* rays_d
   const char* tl_env = getenv("NERFB200_TIMELINE");
   unsigned long long* tl = nullptr;
   if (tl_env && !stage_dump) {
-    cudaMalloc(&tl, 4 * 10 * 2 * 4 * 8);
-    cudaMemset(tl, 0, 4 * 10 * 2 * 4 * 8);
+    cudaMalloc(&tl, (320 + 400) * 8);
+    cudaMemset(tl, 0, (320 + 400) * 8);
   }
   long long M = (long long)n_rays * n_samples;
   long long quads = (M + 511) / 512;
@@ -374,7 +380,7 @@ int launch_mlp_bf16(const void* packed, const float* rays_o, const float* rays_d
         (const unsigned char*)packed, rays_o, rays_d, z_vals, M, n_samples, (int)quads, raw, nullptr, nullptr);
   NB_LAUNCH_OK("mlp_bf16_tc2_kernel");
   if (tl) {   // debug only (NERFB200_TIMELINE=<file>): dump cluster 0's handshake timestamps
-    unsigned long long host[4 * 10 * 2 * 4];
+    unsigned long long host[320 + 400];
     cudaStreamSynchronize(st);
     cudaMemcpy(host, tl, sizeof(host), cudaMemcpyDeviceToHost);
     cudaFree(tl);
@@ -383,6 +389,8 @@ int launch_mlp_bf16(const void* packed, const float* rays_o, const float* rays_d
       for (int i = 0; i < 4 * 10 * 2; ++i)
         fprintf(f, "%d %d %d %llu %llu %llu %llu\n", i / 20, (i / 2) % 10, i % 2, host[i * 4], host[i * 4 + 1],
                 host[i * 4 + 2], host[i * 4 + 3]);
+      for (int i = 0; i < 200; ++i)   // weight-chunk waits of slot 0's pass: it stage 9 chunk start end 0 0
+        fprintf(f, "%d %d 9%d %llu %llu 0 0\n", i / 50, (i / 5) % 10, i % 5, host[320 + i * 2], host[320 + i * 2 + 1]);
       fclose(f);
     }
   }
