@@ -1,0 +1,63 @@
+"""CPU, world_size 2 over gloo: ray/view sharding partitions the work exactly, timing reduction is a
+max over ranks, and the flat-gradient all-reduce averages like DistributedDataParallel would."""
+import os
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from nerf_rep_for_test_b200 import parallel as P
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n = 640000 + 7
+        lo, hi = P.shard_range(n, rank, world)
+        cover = torch.zeros(n, dtype=torch.int32)
+        cover[lo:hi] += 1
+        dist.all_reduce(cover)
+        assert int(cover.min()) == 1 and int(cover.max()) == 1          # exact partition, no overlap
+        views = torch.zeros(200, dtype=torch.int32)
+        views[P.views_for_rank(200, rank, world)] += 1
+        dist.all_reduce(views)
+        assert bool((views == 1).all())
+        t = P.max_over_ranks([10.0 + rank, 5.0 - rank], torch.device("cpu"))
+        assert t == [10.0 + world - 1, 5.0]
+        # gradient averaging
+        torch.manual_seed(0)
+        lin = torch.nn.Linear(7, 3)
+        x = torch.full((4, 7), float(rank + 1))
+        lin(x).sum().backward()
+        local = [p.grad.clone() for p in lin.parameters()]
+        P.FlatGradAllReduce(lin.parameters())()
+        mean_scale = sum(range(1, world + 1)) / world / (rank + 1)
+        for g, l in zip([p.grad for p in lin.parameters()], local):
+            expect = l * mean_scale if l.dim() == 2 else l        # bias grad does not depend on x
+            assert torch.allclose(g, expect, atol=1e-6), (g, expect)
+        out.put((rank, "ok"))
+    except Exception as e:      # pragma: no cover
+        out.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharding_and_grad_allreduce_world2():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    world, port = 2, 29533
+    procs = [ctx.Process(target=_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def test_shard_range_edges():
+    assert P.shard_range(0, 0, 4) == (0, 0)
+    assert P.shard_range(3, 3, 4) == (3, 3)
+    assert [P.shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 9), (9, 10)]
