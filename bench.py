@@ -13,7 +13,7 @@ its own lego test view per step -- rays are independent, there is no data-path c
 `e2e`    : same metric through the host-buffer C-ABI entry (nerfb200_render_image_host): pose and
            intrinsics copied from host memory, the eight maps copied back to pinned host memory,
            all inside the timed region.
-`roofline`: the dominant kernel (mlp_bf16_tc_kernel) timed live with CUDA events around every launch
+`roofline`: the dominant kernel (mlp_bf16_tc2_kernel) timed live with CUDA events around every launch
            inside the timed region; algorithmic FLOPs (1 186 816 per MLP row, unpadded) / that time
            against MEASURED_PEAKS.json.
 `cpu_baseline` / `--impl reference`: the reference's CPU path (oracle port, asserted bit-identical
@@ -244,10 +244,37 @@ def run_ours(args):
     e2e_ms = (time.perf_counter() - t0) * 1e3
     barrier()
 
-    t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)
+    # ---- training step (BASELINE.json configs[2]): 4096 rays per GPU, fwd + bwd + gradient all-reduce +
+    # clip + Adam; stratified jitter and random u (net.train()); random target colours
+    train_ms = 0.0
+    if args.train_steps > 0:
+        from nerf_rep_for_test_b200 import training as T
+        net.train()
+        r.perturb = 1
+        step = T.TrainStep(r)
+        g = torch.Generator().manual_seed(rank)
+        ro_all, rd_all = O.get_rays(H, W, lego_pose(rank), K0[0])
+        sel = torch.randint(0, H * W, (args.train_rays,), generator=g)
+        tro, trd = ro_all[sel].to(dev), rd_all[sel].to(dev)
+        target = torch.rand(args.train_rays, 3, generator=g).to(dev)
+        for _ in range(args.train_warmup):
+            step(tro, trd, target)
+        barrier()
+        te0, te1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        te0.record()
+        for _ in range(args.train_steps):
+            step(tro, trd, target)
+        te1.record()
+        torch.cuda.synchronize()
+        train_ms = te0.elapsed_time(te1)
+        barrier()
+        net.eval()
+        r.perturb = 0
+
+    t = torch.tensor([ms_total, e2e_ms, train_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = float(t[0]), float(t[1])
+    ms_total, e2e_ms, train_ms = float(t[0]), float(t[1]), float(t[2])
     rays_total = float(world) * args.steps * H * W
     value = rays_total / (ms_total * 1e-3)
     e2e_value = rays_total / (e2e_ms * 1e-3)
@@ -275,7 +302,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "rays/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": r.h2d_bytes_per_image, "d2h_bytes_per_step": r.d2h_bytes_per_image(H, W)},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "mlp_bf16_tc_kernel" if args.mode == "bf16" else "mlp_fp32_kernel",
+            "roofline": {"bound": "tensor", "kernel": "mlp_bf16_tc2_kernel" if args.mode == "bf16" else "mlp_fp32_kernel",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": pk["source"] if args.mode == "bf16" else
                          "nominal fp32 FFMA 80 TFLOP/s (parity mode, not the performance path)",
@@ -283,6 +310,18 @@ def run_ours(args):
                          "kernel_share_of_step": mlp_ms / ms_total,
                          "algorithmic_flop_per_row": FLOP_PER_ROW, "rows_per_step": mlp_rows / args.steps},
         }
+        if args.train_steps > 0:
+            it_ms = train_ms / args.train_steps
+            line["train"] = {
+                "metric": "train iters/sec (4096-ray batch per GPU: fwd+bwd through sampling, MLP and compositing, "
+                          "NCCL gradient all-reduce, clip, Adam)",
+                "value": 1e3 / it_ms, "unit": "it/s", "ms_per_iter": it_ms, "steps": args.train_steps,
+                "warmup": args.train_warmup, "rays_per_iter_per_gpu": args.train_rays,
+                "rays_per_s_total": world * args.train_rays * 1e3 / it_ms, "scaling": "weak",
+                "allreduce_bytes": 1191688 * 4,
+                "algorithmic_tflops": 3 * args.train_rays * ROWS_PER_RAY * FLOP_PER_ROW / (it_ms * 1e-3) / 1e12,
+                "note": "forward and compositing backward are this repo's kernels; the MLP dgrad/wgrad GEMMs are "
+                        "cuBLAS bf16 (round-1 status, DESIGN.md section 8)"}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_rays_per_s()
         print(json.dumps(line))
@@ -299,6 +338,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--train-steps", type=int, default=20)
+    ap.add_argument("--train-warmup", type=int, default=5)
+    ap.add_argument("--train-rays", type=int, default=4096)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -115,6 +115,13 @@ NERFB200_API int nerfb200_pack_weights(const nerfb200_mlp_weights* w, int mode, 
 NERFB200_API int nerfb200_mlp_forward(const void* packed, int mode, const float* rays_o, const float* rays_d,
                          const float* z_vals, int n_rays, int n_samples, float* raw, void* stream);
 
+/* training twin of mlp_forward (BF16 mode): additionally stores the bf16 output of each of the ten
+ * stages (mlp_layout.cuh: relu(h0..h7), feature (linear), relu(views); stage 9 fills columns 0..127)
+ * as acts [10][n_rays*n_samples][256] bf16 for the backward pass. */
+NERFB200_API int nerfb200_mlp_forward_train(const void* packed, int mode, const float* rays_o,
+                               const float* rays_d, const float* z_vals, int n_rays, int n_samples,
+                               float* raw, void* acts, void* stream);
+
 /* diagnostic twin of mlp_forward (BF16 mode): additionally writes the fp32 post-activation output
  * of each of the ten stages (mlp_layout.cuh) for rows 0..127 into stage_dump [10][128][256];
  * used by the stage-level parity tests. */

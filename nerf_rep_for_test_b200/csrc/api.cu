@@ -23,7 +23,7 @@ void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_r
 int launch_mlp_fp32(const void* packed, const float* rays_o, const float* rays_d, const float* z_vals,
                     int n_rays, int n_samples, float* raw, cudaStream_t st);
 int launch_mlp_bf16(const void* packed, const float* rays_o, const float* rays_d, const float* z_vals,
-                    int n_rays, int n_samples, float* raw, float* stage_dump, cudaStream_t st);
+                    int n_rays, int n_samples, float* raw, float* stage_dump, void* acts, cudaStream_t st);
 
 // ---- optional MLP-kernel timing (bench.py roofline): CUDA events around every mlp launch, on
 // the launching stream, while enabled.  Off by default; the only other global state besides the
@@ -112,9 +112,20 @@ extern "C" int nerfb200_mlp_forward(const void* packed, int mode, const float* r
   cudaStream_t st = (cudaStream_t)stream;
   bool prof = prof_begin(st);
   int rc = mode == NERFB200_MODE_FP32 ? launch_mlp_fp32(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, st)
-                                      : launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, nullptr, st);
+                                      : launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, nullptr, nullptr, st);
   if (prof) prof_end(st, (double)n_rays * n_samples);
   return rc;
+}
+
+extern "C" int nerfb200_mlp_forward_train(const void* packed, int mode, const float* rays_o, const float* rays_d,
+                                          const float* z_vals, int n_rays, int n_samples, float* raw, void* acts,
+                                          void* stream) {
+  NB_CHECK_ARG(n_rays <= 0 || (packed && rays_o && rays_d && z_vals && raw && acts), "mlp_forward_train: null pointer");
+  NB_CHECK_ARG(n_rays >= 0 && n_samples >= 1, "mlp_forward_train: bad sizes");
+  NB_CHECK_ARG(mode == NERFB200_MODE_BF16, "mlp_forward_train: only NERFB200_MODE_BF16 saves activations");
+  NB_CHECK_ARG(((uintptr_t)packed & 1023) == 0 && ((uintptr_t)acts & 15) == 0, "mlp_forward_train: misaligned buffer");
+  if (n_rays == 0) return 0;
+  return launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, nullptr, acts, (cudaStream_t)stream);
 }
 
 extern "C" int nerfb200_profile_enable(int on) {
@@ -146,7 +157,7 @@ extern "C" int nerfb200_mlp_forward_stages(const void* packed, int mode, const f
   NB_CHECK_ARG(n_rays >= 1 && n_samples >= 1, "mlp_forward_stages: bad sizes");
   NB_CHECK_ARG(mode == NERFB200_MODE_BF16, "mlp_forward_stages: only NERFB200_MODE_BF16 has a stage dump");
   NB_CHECK_ARG(((uintptr_t)packed & 1023) == 0, "mlp_forward_stages: packed weights must be 1024-byte aligned");
-  return launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, stage_dump, (cudaStream_t)stream);
+  return launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, stage_dump, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" size_t nerfb200_render_workspace_bytes(int n_rays, const nerfb200_render_params* p) {

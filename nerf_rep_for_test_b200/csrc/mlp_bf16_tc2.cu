@@ -44,12 +44,12 @@ __device__ __forceinline__ void chunk_src(int stage, int c, bool& from_pe, int& 
   else { from_pe = false; kblock = c; }
 }
 
-template <bool kDump, bool kTimeline>
+template <bool kDump, bool kTimeline, bool kSave>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __restrict__ rays_o,
                     const float* __restrict__ rays_d, const float* __restrict__ z_vals, long long M, int S,
                     int num_quads, float* __restrict__ raw, float* __restrict__ stage_dump,
-                    unsigned long long* __restrict__ tl) {
+                    unsigned long long* __restrict__ tl, __nv_bfloat16* __restrict__ acts) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   const uint32_t smem_base = smem_u32(smem_dyn);
   if ((smem_base & 1023u) != 0) __trap();
@@ -168,6 +168,16 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
           if (stage == 7) epi_stage256<1>(t_acc, bias4, a_row_base, r7, tail + kTailAlphaW, sigma);
           else if (stage == 8) epi_stage256<2>(t_acc, bias4, a_row_base, r7, nullptr, sigma);
           else epi_stage256<0>(t_acc, bias4, a_row_base, r7, nullptr, sigma);
+          if (kSave && valid_cur) {
+            // training: keep this stage's bf16 output [stage][M][256] for the backward pass; re-read the
+            // row this thread just wrote (same thread, program order) and stream it out
+            uint4* dst = reinterpret_cast<uint4*>(acts + ((size_t)stage * (size_t)M + (size_t)m_cur) * 256);
+#pragma unroll
+            for (int h = 0; h < 4; ++h)
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                dst[h * 8 + j] = *reinterpret_cast<const uint4*>(a_row_base + h * 16384 + ((j ^ r7) << 4));
+          }
           if (stage == 8) {  // dir PE replaces the xyz PE tile (dead after stage 5) for stage 9
             float f[32];
             pos_enc_row<kLd>(d_cur, f);
@@ -203,6 +213,10 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
               r0 = fmaf(h0, w0.x, r0); r0 = fmaf(h1, w0.y, r0); r0 = fmaf(h2, w0.z, r0); r0 = fmaf(h3, w0.w, r0);
               r1 = fmaf(h0, w1.x, r1); r1 = fmaf(h1, w1.y, r1); r1 = fmaf(h2, w1.z, r1); r1 = fmaf(h3, w1.w, r1);
               r2 = fmaf(h0, w2.x, r2); r2 = fmaf(h1, w2.y, r2); r2 = fmaf(h2, w2.z, r2); r2 = fmaf(h3, w2.w, r2);
+              if (kSave && valid_cur) {
+                uint2 pk = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+                *reinterpret_cast<uint2*>(acts + ((size_t)9 * (size_t)M + (size_t)m_cur) * 256 + n) = pk;
+              }
             }
           }
           tc_fence_before();
@@ -345,20 +359,21 @@ int launch_mlp_bf16_1cta(const void* packed, const float* rays_o, const float* r
                          int n_rays, int n_samples, float* raw, float* stage_dump, cudaStream_t st);
 
 int launch_mlp_bf16(const void* packed, const float* rays_o, const float* rays_d, const float* z_vals, int n_rays,
-                    int n_samples, float* raw, float* stage_dump, cudaStream_t st) {
+                    int n_samples, float* raw, float* stage_dump, void* acts, cudaStream_t st) {
   const char* variant = getenv("NERFB200_TC_VARIANT");
-  if (variant && atoi(variant) == 1)
+  if (variant && atoi(variant) == 1 && !acts)
     return launch_mlp_bf16_1cta(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, stage_dump, st);
   using namespace tc2;
   int dev = 0, sms = 0;
   NB_CUDA(cudaGetDevice(&dev));
   NB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-  NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-  NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   const char* tl_env = getenv("NERFB200_TIMELINE");
   unsigned long long* tl = nullptr;
-  if (tl_env && !stage_dump) {
+  if (tl_env && !stage_dump && !acts) {
     cudaMalloc(&tl, (320 + 400) * 8);
     cudaMemset(tl, 0, (320 + 400) * 8);
   }
@@ -369,15 +384,19 @@ int launch_mlp_bf16(const void* packed, const float* rays_o, const float* rays_d
     int v = atoi(mc);
     if (v > 0 && v < clusters) clusters = v;
   }
-  if (stage_dump)
-    mlp_bf16_tc2_kernel<true, false><<<2 * clusters, kThreads, kSmemBytes, st>>>(
-        (const unsigned char*)packed, rays_o, rays_d, z_vals, M, n_samples, (int)quads, raw, stage_dump, nullptr);
+  if (acts)
+    mlp_bf16_tc2_kernel<false, false, true><<<2 * clusters, kThreads, kSmemBytes, st>>>(
+        (const unsigned char*)packed, rays_o, rays_d, z_vals, M, n_samples, (int)quads, raw, nullptr, nullptr,
+        (__nv_bfloat16*)acts);
+  else if (stage_dump)
+    mlp_bf16_tc2_kernel<true, false, false><<<2 * clusters, kThreads, kSmemBytes, st>>>(
+        (const unsigned char*)packed, rays_o, rays_d, z_vals, M, n_samples, (int)quads, raw, stage_dump, nullptr, nullptr);
   else if (tl)
-    mlp_bf16_tc2_kernel<false, true><<<2 * clusters, kThreads, kSmemBytes, st>>>(
-        (const unsigned char*)packed, rays_o, rays_d, z_vals, M, n_samples, (int)quads, raw, nullptr, tl);
+    mlp_bf16_tc2_kernel<false, true, false><<<2 * clusters, kThreads, kSmemBytes, st>>>(
+        (const unsigned char*)packed, rays_o, rays_d, z_vals, M, n_samples, (int)quads, raw, nullptr, tl, nullptr);
   else
-    mlp_bf16_tc2_kernel<false, false><<<2 * clusters, kThreads, kSmemBytes, st>>>(
-        (const unsigned char*)packed, rays_o, rays_d, z_vals, M, n_samples, (int)quads, raw, nullptr, nullptr);
+    mlp_bf16_tc2_kernel<false, false, false><<<2 * clusters, kThreads, kSmemBytes, st>>>(
+        (const unsigned char*)packed, rays_o, rays_d, z_vals, M, n_samples, (int)quads, raw, nullptr, nullptr, nullptr);
   NB_LAUNCH_OK("mlp_bf16_tc2_kernel");
   if (tl) {   // debug only (NERFB200_TIMELINE=<file>): dump cluster 0's handshake timestamps
     unsigned long long host[320 + 400];

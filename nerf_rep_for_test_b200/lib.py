@@ -51,6 +51,7 @@ SIGNATURES = {
     "nerfb200_packed_weights_bytes": (C.c_size_t, [C.c_int]),
     "nerfb200_pack_weights": (C.c_int, [C.POINTER(MlpWeights), C.c_int, _vp, _vp]),
     "nerfb200_mlp_forward": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp]),
+    "nerfb200_mlp_forward_train": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "nerfb200_mlp_forward_stages": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "nerfb200_composite_forward": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
                                              C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -78,6 +78,17 @@ def mlp_forward(packed, rays_o, rays_d, z_vals):
     return raw
 
 
+def mlp_forward_train(packed, rays_o, rays_d, z_vals):
+    """BF16 mode: (raw [n,S,4] fp32, acts [10, n*S, 256] bf16) -- stage outputs kept for backward."""
+    rays_o, rays_d, z_vals = _f(rays_o), _f(rays_d), _f(z_vals)
+    n, S = z_vals.shape
+    raw = torch.empty((n, S, 4), device=z_vals.device)
+    acts = torch.empty((10, n * S, 256), dtype=torch.bfloat16, device=z_vals.device)
+    L.check(L.load().nerfb200_mlp_forward_train(packed.ptr, packed.mode, L.dev(rays_o), L.dev(rays_d), L.dev(z_vals),
+                                               n, S, L.dev(raw), L.dev(acts), L.stream_ptr()), "mlp_forward_train")
+    return raw, acts
+
+
 def mlp_forward_stages(packed, rays_o, rays_d, z_vals):
     """BF16 mode diagnostic: (raw, stage_dump [10,128,256]) -- fp32 stage outputs of rows 0..127."""
     rays_o, rays_d, z_vals = _f(rays_o), _f(rays_d), _f(z_vals)

@@ -193,6 +193,21 @@ class Renderer:
         self._packed_weights(which)
         return C.c_void_p(self._packed[which][2])
 
+    def packed(self, which, mode=None):
+        """(ptr, mode) handle accepted by ops.mlp_forward*; repacked lazily when parameters change."""
+        class _Handle:
+            pass
+        old_mode = self.mode
+        if mode is not None:
+            self.mode = mode
+        try:
+            h = _Handle()
+            h.ptr = self._packed_ptr(which)
+            h.mode = self.MODES[self.mode]
+        finally:
+            self.mode = old_mode
+        return h
+
     def _table(self, name):
         """z table (:218-226) and eval-mode u table (:250) evaluated with torch CPU ops, as the oracle does."""
         key = (name, self.N_samples, self.N_importance, self.near, self.far, self.lindisp)

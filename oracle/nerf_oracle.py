@@ -357,7 +357,7 @@ def sample_coarse_ess(grid, rays_o, rays_d, n_samples=N_SAMPLES, near=NEAR, far=
 # ---------------------------------------------------------------------------
 def render_rays(sd, rays_o, rays_d, white_bkgd=True, use_ert=False, ert_threshold=0.01,
                 ref_compat=True, ray_chunk=2048, mlp_chunk=4096, return_aux=False,
-                n_samples=N_SAMPLES, n_importance=N_IMPORTANCE, near=NEAR, far=FAR):
+                n_samples=N_SAMPLES, n_importance=N_IMPORTANCE, near=NEAR, far=FAR, detach_sampler=False):
     """perturb=0, net.eval() (deterministic u), ESS off.  Returns dict of [N,...] maps."""
     outs = {}
     aux = {}
@@ -377,6 +377,8 @@ def render_rays(sd, rays_o, rays_d, white_bkgd=True, use_ert=False, ert_threshol
         put(outs, "acc_map_0", acc0), put(outs, "depth_map_0", depth0)
         t_mid = .5 * (t_vals[..., 1:] + t_vals[..., :-1])
         t_fine, inds, cdf = sample_fine(t_mid, weights[..., 1:-1], None, n_importance)
+        if detach_sampler:      # original-NeRF semantics; the reference does NOT detach (:181-183)
+            t_fine = t_fine.detach()
         z_all, _ = torch.sort(torch.cat([t_vals, t_fine], -1), -1)
         pts_f = ro[..., None, :] + rd[..., None, :] * z_all[..., :, None]
         raw_f = query_network(sd, "model_fine.", pts_f, rd, mlp_chunk)

@@ -1,0 +1,109 @@
+"""GPU: gradients of the training path against autograd through the CPU oracle (fp32), and one
+optimisation smoke run."""
+import pytest
+import torch
+
+from oracle import nerf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from nerf_rep_for_test_b200 import Network, RenderConfig, Renderer
+    from nerf_rep_for_test_b200 import training as T
+    DEV = torch.device("cuda:0")
+
+
+def _setup(seed=3, gain=30.0, bias=0.2, n=96):
+    sd = O.make_state_dict(seed, gain, bias)
+    net = Network(device=DEV)
+    net.load_state_dict(sd)
+    net.to(DEV).eval()
+    r = Renderer(net, RenderConfig(perturb=0, enable_ess=False, enable_ert=False), mode="bf16")
+    b = O.lego_batch(32, 32)
+    ro, rd = O.get_rays(32, 32, b["pose"][0], b["intrinsics"][0])
+    sel = torch.randperm(ro.shape[0], generator=torch.Generator().manual_seed(0))[:n]
+    target = torch.rand(n, 3, generator=torch.Generator().manual_seed(1))
+    return sd, net, r, ro[sel].contiguous(), rd[sel].contiguous(), target
+
+
+def _oracle_grads(sd, ro, rd, target, z_all=None):
+    """fp32 autograd through the oracle with the sampler detached.  With `z_all` given, the fine pass
+    is evaluated at exactly those sample positions: sin(2^9 p) turns a 1e-3 shift of a fine sample
+    (caused by bf16 coarse weights) into a 0.5 rad phase change, which would decorrelate the layer-0
+    weight gradients of the two pipelines without saying anything about the backward itself."""
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    if z_all is None:
+        out = O.render_rays(sdg, ro, rd, detach_sampler=True)
+    else:
+        z_c = O.sample_coarse(ro.shape[0])
+        raw_c = O.query_network(sdg, "model.", ro[:, None, :] + rd[:, None, :] * z_c[..., None], rd)
+        rgb0 = O.raw2outputs(raw_c, z_c, rd)[0]
+        raw_f = O.query_network(sdg, "model_fine.", ro[:, None, :] + rd[:, None, :] * z_all[..., None], rd)
+        out = {"rgb_map_0": rgb0, "rgb_map": O.raw2outputs(raw_f, z_all, rd)[0]}
+    loss = torch.nn.functional.mse_loss(out["rgb_map_0"], target) + torch.nn.functional.mse_loss(out["rgb_map"], target)
+    loss.backward()
+    return float(loss.detach()), {k: v.grad for k, v in sdg.items()}
+
+
+def test_mlp_backward_formulas_fp32():
+    """The dgrad/wgrad algebra of training.mlp_backward, in fp32 on oracle activations, vs autograd."""
+    torch.manual_seed(0)
+    sd = O.make_state_dict(4)
+    M = 200
+    pts, dirs = torch.randn(M, 3), torch.nn.functional.normalize(torch.randn(M, 3), dim=-1)
+    pe, dpe = O.pos_enc(pts, 10), O.pos_enc(dirs, 4)
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k.startswith("model.")}
+    raw, hidden = O.nerf_mlp(sdg, "model.", torch.cat([pe, dpe], -1), return_hidden=True)
+    g_raw = torch.randn(M, 4)
+    (raw * g_raw).sum().backward()
+    with torch.no_grad():
+        h7 = hidden[7]
+        feat = torch.nn.functional.linear(h7, sd["model.feature_linear.weight"], sd["model.feature_linear.bias"])
+        hv = torch.relu(torch.nn.functional.linear(torch.cat([feat, dpe], -1), sd["model.views_linears.0.weight"],
+                                                   sd["model.views_linears.0.bias"]))
+        acts = torch.zeros(10, M, 256)
+        for i in range(8):
+            acts[i] = hidden[i]
+        acts[8] = feat
+        acts[9, :, :128] = hv
+    params = [sd["model." + n] for n in T._NAMES]
+    grads = T.mlp_backward([p.to(DEV) for p in params], acts.to(DEV), pe.to(DEV), dpe.to(DEV), g_raw.to(DEV),
+                           compute_dtype=torch.float32)
+    for name, g in zip(T._NAMES, grads):
+        ref = sdg["model." + name].grad
+        assert torch.allclose(g.cpu(), ref, rtol=2e-4, atol=2e-5 * float(ref.abs().max() + 1e-12)), name
+
+
+def test_training_gradients_vs_oracle_autograd():
+    sd, net, r, ro, rd, target = _setup()
+    # the fine sample positions our (bf16) forward uses, rebuilt with the same kernels
+    from nerf_rep_for_test_b200 import lib as L, ops
+    z_c = ops.sample_coarse(r._table("z"), ro.shape[0])
+    raw_c = ops.mlp_forward(r.packed("coarse"), ro.to(DEV), rd.to(DEV), z_c)
+    w_c = ops.composite_forward(raw_c, z_c, rd.to(DEV))[3]
+    z_all = ops.sample_pdf_merge(z_c, w_c, r._table("u"), want_aux=False)[0].cpu()
+    loss_ref, gref = _oracle_grads(sd, ro, rd, target, z_all)
+    out = T.render_rays_train(r, ro.to(DEV), rd.to(DEV))
+    loss = T.nerf_loss(out, target.to(DEV))
+    loss.backward()
+    assert abs(float(loss) - loss_ref) < 2e-3 * max(1.0, abs(loss_ref))
+    worst = 1.0
+    for name, p in net.state_dict(keep_vars=True).items():
+        g, ref = p.grad.float().cpu(), gref[name]
+        cos = float((g * ref).sum() / (g.norm() * ref.norm() + 1e-20))
+        rel = float((g - ref).norm() / (ref.norm() + 1e-20))
+        worst = min(worst, cos)
+        print("%-36s cos %.5f  rel %.4f" % (name, cos, rel))
+        # bf16 operands in forward and backward GEMMs: a few 1e-2 relative on the gradient norm
+        assert cos > 0.995 and rel < 0.1, (name, cos, rel)
+    print("worst gradient cosine vs fp32 reference autograd: %.5f" % worst)
+
+
+def test_train_steps_reduce_loss():
+    sd, net, r, ro, rd, target = _setup(seed=5, gain=10.0, bias=0.0, n=256)
+    net.train()
+    step = T.TrainStep(r)
+    r.perturb = 1
+    losses = [float(step(ro.to(DEV), rd.to(DEV), target.to(DEV))) for _ in range(30)]
+    assert losses[-1] < 0.7 * losses[0], losses[::5]
+    assert all(torch.isfinite(p).all() for p in net.parameters())
