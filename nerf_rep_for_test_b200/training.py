@@ -40,48 +40,74 @@ def model_params(model):
     return ps
 
 
+def _mm_f32(a, b):
+    """a @ b with fp32 accumulation AND fp32 output (weight gradients)."""
+    if a.dtype == torch.float32:
+        return torch.mm(a, b)
+    try:
+        return torch.mm(a, b, out_dtype=torch.float32)
+    except TypeError:      # older torch: bf16 output, widened afterwards
+        return torch.mm(a, b).float()
+
+
+def _pad_cols(t, n):
+    """zero-pad the last dim to n columns (tensor-core GEMM kernels want multiples of 8 bf16 elements;
+    K = 3 / 27 / 63 fall back to slow paths otherwise)."""
+    if t.shape[-1] == n:
+        return t.contiguous()
+    out = t.new_zeros(t.shape[:-1] + (n,))
+    out[..., : t.shape[-1]] = t
+    return out
+
+
 def mlp_backward(params, acts, pe, dpe, g_raw, compute_dtype=torch.bfloat16):
     """Gradients of the 24 tensors given dL/draw.
 
     params: list from model_params(); acts: [10, M, 256] stage outputs (relu(h0..h7), feature, relu(views));
     pe [M,63], dpe [M,27]: MLP inputs; g_raw [M,4] = dL/d(rgb_raw, sigma_raw).
-    Matmuls run in `compute_dtype` with fp32 accumulation (cuBLAS); results are returned in fp32.
+    Activation gradients and GEMM operands are kept in `compute_dtype` (bf16: one [M,256] tensor is
+    0.5 GB at 4096 rays x 256 samples); GEMMs accumulate in fp32; weight/bias gradients come out fp32.
     """
     cd = compute_dtype
-    W = [p.detach() for p in params]
-    g = g_raw.to(torch.float32)
-    g_rgb, g_sig = g[:, :3], g[:, 3:4]
-    h = [acts[i] for i in range(8)]                     # post-relu hidden activations
+    W = [p.detach().to(cd) for p in params]
+    acts = acts.to(cd)
+    pe, dpe = _pad_cols(pe.to(cd), 64), _pad_cols(dpe.to(cd), 32)
+    g8 = _pad_cols(g_raw.to(cd), 8)                       # [M,8]: rgb(3) sigma(1) 0000
+    h = [acts[i] for i in range(8)]                       # post-relu hidden activations
     feat, hv = acts[8], acts[9][:, :128]
-    mm = lambda a, b: torch.matmul(a.to(cd), b.to(cd)).float()
+    relu_bwd = torch.ops.aten.threshold_backward          # grad * (act > 0), one pass
+    colsum = lambda t: t.sum(0, dtype=torch.float32)
     grads = [None] * 24
-    # rgb_linear: raw_rgb = hv @ Wrgb^T + b
-    grads[22] = mm(g_rgb.t(), hv)
-    grads[23] = g_rgb.sum(0)
-    d_hv = mm(g_rgb, W[22]) * (hv > 0)
+    # heads: raw = [hv @ Wrgb^T + b_rgb | h7 @ w_alpha^T + b_alpha]
+    g_hv = _mm_f32(g8.t(), hv)                            # [8,128]: rows 0-2 = dW_rgb
+    g_h7 = _mm_f32(g8.t(), h[7])                          # [8,256]: row 3 = dw_alpha
+    gsum = colsum(g8)
+    grads[22], grads[23] = g_hv[:3].contiguous(), gsum[:3].contiguous()
+    grads[20], grads[21] = g_h7[3:4].contiguous(), gsum[3:4].contiguous()
+    w_heads_hv = torch.zeros(8, 128, dtype=cd, device=g8.device)
+    w_heads_hv[:3] = W[22]
+    w_heads_h7 = torch.zeros(8, 256, dtype=cd, device=g8.device)
+    w_heads_h7[3] = W[20][0]
+    d_hv = relu_bwd(torch.mm(g8, w_heads_hv), hv, 0.0)
     # views_linears.0 on [feature | dpe]
-    grads[16] = torch.cat([mm(d_hv.t(), feat), mm(d_hv.t(), dpe)], 1)
-    grads[17] = d_hv.sum(0)
-    d_feat = mm(d_hv, W[16][:, :256])
-    # feature_linear (linear) and alpha_linear, both on h7
-    grads[18] = mm(d_feat.t(), h[7])
-    grads[19] = d_feat.sum(0)
-    grads[20] = mm(g_sig.t(), h[7])
-    grads[21] = g_sig.sum(0)
-    d_h = mm(d_feat, W[18]) + g_sig * W[20].float()
+    grads[16] = torch.cat([_mm_f32(d_hv.t(), feat), _mm_f32(d_hv.t(), dpe)[:, :CH_DIR]], 1)
+    grads[17] = colsum(d_hv)
+    d_feat = torch.mm(d_hv, W[16][:, :256].contiguous())
+    # feature_linear (linear, no activation) on h7
+    grads[18] = _mm_f32(d_feat.t(), h[7])
+    grads[19] = colsum(d_feat)
+    d_h = torch.addmm(torch.mm(g8, w_heads_h7), d_feat, W[18])   # d_feat @ Wf + g_sigma * w_alpha
     for i in range(7, -1, -1):
-        d_pre = d_h * (h[i] > 0)
+        d_pre = relu_bwd(d_h, h[i], 0.0)
         if i == 0:
-            inp = pe
-        elif i == 5:
-            inp = torch.cat([pe.to(cd), h[4].to(cd)], 1)    # skip concat: [pe | h4]  (network.py:57-58)
+            grads[0] = _mm_f32(d_pre.t(), pe)[:, :CH_XYZ].contiguous()
+        elif i == 5:                                      # skip concat: input = [pe | h4]  (network.py:57-58)
+            grads[10] = torch.cat([_mm_f32(d_pre.t(), pe)[:, :CH_XYZ], _mm_f32(d_pre.t(), h[4])], 1)
         else:
-            inp = h[i - 1]
-        grads[2 * i] = mm(d_pre.t(), inp)
-        grads[2 * i + 1] = d_pre.sum(0)
+            grads[2 * i] = _mm_f32(d_pre.t(), h[i - 1])
+        grads[2 * i + 1] = colsum(d_pre)
         if i > 0:
-            d_in = mm(d_pre, W[2 * i])
-            d_h = d_in[:, CH_XYZ:] if i == 5 else d_in
+            d_h = torch.mm(d_pre, W[2 * i][:, CH_XYZ:].contiguous() if i == 5 else W[2 * i])
     return grads
 
 
