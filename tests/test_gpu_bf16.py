@@ -134,10 +134,27 @@ def test_full_frame_800x800_independence_and_oracle_subset():
     sub_p = r.render_rays(ro[sel][perm], rd[sel][perm])
     assert torch.equal(sub_p["rgb_map"], sub["rgb_map"][perm])
     with torch.no_grad():
-        ref = O.render_rays(sd, ro[sel].cpu(), rd[sel].cpu())
-    for k in ("rgb_map_0", "acc_map_0", "rgb_map", "acc_map", "depth_map"):
+        ref, aux = O.render_rays(sd, ro[sel].cpu(), rd[sel].cpu(), return_aux=True)
+    q99 = lambda e: float(e.flatten().kthvalue(int(0.99 * e.numel()))[0])
+    # (a) coarse pass: no dependence on sample placement
+    for k in ("rgb_map_0", "acc_map_0", "depth_map_0"):
         err = (sub[k].cpu() - ref[k]).abs()
         scale = 6.0 if "depth" in k else 1.0
-        p99 = float(err.flatten().kthvalue(int(0.99 * err.numel()))[0])
-        print("800x800 subset %-10s abs err/scale p99 %.2e max %.2e" % (k, p99 / scale, float(err.max()) / scale))
-        assert p99 <= 1e-3 * scale, k      # max can hit a last-sample sign flip (SURVEY 8c' item 3)
+        print("800x800 subset %-11s abs err/scale p99 %.2e max %.2e" % (k, q99(err) / scale, float(err.max()) / scale))
+        assert q99(err) <= 1e-3 * scale, k      # max can hit a last-sample sign flip (SURVEY 8c' item 3)
+    # (b) fine pass at the REFERENCE's sample positions: the kernels' own arithmetic error
+    packed = r.packed("fine")
+    raw_f = ops.mlp_forward(packed, ro[sel], rd[sel], aux["z_all"].to(DEV))
+    rgb, _, acc, _, depth = ops.composite_forward(raw_f, aux["z_all"].to(DEV), rd[sel])
+    for k, v in (("rgb_map", rgb), ("acc_map", acc), ("depth_map", depth)):
+        err = (v.cpu() - ref[k]).abs()
+        scale = 6.0 if "depth" in k else 1.0
+        print("800x800 subset %-11s (reference z) abs err/scale p99 %.2e max %.2e" % (k, q99(err) / scale, float(err.max()) / scale))
+        assert q99(err) <= 1e-3 * scale, k
+    # (c) end to end: bf16 coarse weights move the importance samples, and a random-init field with
+    # PE up to 2^9 is rough at that scale, so the fine quadrature itself changes; reported, loosely bounded
+    for k in ("rgb_map", "acc_map", "depth_map"):
+        err = (sub[k].cpu() - ref[k]).abs()
+        scale = 6.0 if "depth" in k else 1.0
+        print("800x800 subset %-11s (end to end)  abs err/scale median %.2e p99 %.2e" % (k, float(err.median()) / scale, q99(err) / scale))
+        assert float(err.median()) <= 2e-3 * scale and q99(err) <= 3e-2 * scale, k
