@@ -271,6 +271,40 @@ def run_ours(args):
         net.eval()
         r.perturb = 0
 
+    # ---- BASELINE.json configs[4]: occupancy-grid empty-space skipping + early ray termination vs dense
+    # sampling, on a synthetic dense blob (opaque field, occupancy = sphere of radius 0.7 world units):
+    # the skip path never sends empty / terminated samples through the MLP.
+    cfg5 = None
+    if args.config5 and rank == 0:
+        sd5 = O.make_state_dict(6, 300.0, 6.0)
+        for k in list(sd5):
+            if k.startswith("model_fine."):
+                sd5[k] = sd5["model." + k[len("model_fine."):]].clone()
+        net5 = Network(device=dev)
+        net5.load_state_dict(sd5)
+        net5.to(dev).eval()
+        res = 128
+        gc = torch.stack(torch.meshgrid([torch.arange(res, device=dev)] * 3, indexing="ij"), -1).float() / (res - 1) * 2 - 1
+        blob = torch.norm(gc, dim=-1) <= 0.35
+        r_dense = Renderer(net5, RenderConfig(perturb=0, enable_ess=False, enable_ert=False), mode="bf16")
+        r_skip = Renderer(net5, RenderConfig(perturb=0, enable_ess=True, enable_ert=True), mode="bf16")
+        r_skip.occupancy_grid = blob
+        r_skip.ess_mode = "skip"
+        res5 = {}
+        for name, rr in (("dense", r_dense), ("skip", r_skip)):
+            for _ in range(2):
+                rr.render(dev_batches[0])
+            if rr.eval_counts is not None:
+                rr.eval_counts.zero_()
+            res5[name] = timed(rr.render, dev_batches[:3]) / 3
+        ev = r_skip.eval_counts.cpu().tolist()
+        cfg5 = {"workload": "800x800 view of a synthetic opaque blob (sphere r=0.7 in a [-2,2]^3 128^3 occupancy grid), "
+                            "ESS skipping + ERT vs dense 64+128 sampling, bf16",
+                "dense_ms": res5["dense"], "skip_ms": res5["skip"], "speedup": res5["dense"] / res5["skip"],
+                "mlp_rows_per_ray_dense": ROWS_PER_RAY,
+                "mlp_rows_per_ray_skip": (ev[0] + ev[1]) / (3.0 * H * W),
+                "note": "throughput comparison only; the reference has no runnable skipping path (SURVEY 8a8/a9)"}
+
     t = torch.tensor([ms_total, e2e_ms, train_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -322,6 +356,8 @@ def run_ours(args):
                 "algorithmic_tflops": 3 * args.train_rays * ROWS_PER_RAY * FLOP_PER_ROW / (it_ms * 1e-3) / 1e12,
                 "note": "forward and compositing backward are this repo's kernels; the MLP dgrad/wgrad GEMMs are "
                         "cuBLAS bf16 (round-1 status, DESIGN.md section 8)"}
+        if cfg5 is not None:
+            line["ess_ert"] = cfg5
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_rays_per_s()
         print(json.dumps(line))
@@ -338,6 +374,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config5", dest="config5", action="store_false", help="skip the ESS/ERT vs dense comparison")
     ap.add_argument("--train-steps", type=int, default=20)
     ap.add_argument("--train-warmup", type=int, default=5)
     ap.add_argument("--train-rays", type=int, default=4096)

@@ -171,6 +171,24 @@ NERFB200_API int nerfb200_ess_update(uint8_t* grid, int res, const float* rays_o
                         const float* z_vals, const float* raw, const float* weights, int n_rays,
                         int n_samples, int use_origin, void* stream);
 
+/* Empty-space skipping proper (BASELINE.json configs[4]): list the rows m = ray*n_samples+s whose sample
+ * lies in an occupied cell (and, when z_term != NULL, has z <= z_term[ray]) into row_ids (order
+ * unspecified) and write their number to *n_active (device int32). */
+NERFB200_API int nerfb200_ess_compact(const uint8_t* grid, int res, const float* rays_o, const float* rays_d,
+                         const float* z_vals, const float* z_term, int n_rays, int n_samples,
+                         int32_t* row_ids, int32_t* n_active, void* stream);
+/* MLP on the listed rows only (BF16 mode); every other row of raw is set to 0 (zero density).  The
+ * row count is read on the device: no host synchronisation. */
+NERFB200_API int nerfb200_mlp_forward_sparse(const void* packed, int mode, const float* rays_o,
+                                const float* rays_d, const float* z_vals, int n_rays, int n_samples,
+                                const int32_t* row_ids, const int32_t* n_active, float* raw, void* stream);
+/* depth at which the transmittance implied by `weights` (T_i = 1 - sum_{j<i} w_j) first drops below
+ * thr; +inf when it never does.  Used to cut the fine pass behind opaque surfaces (ERT). */
+NERFB200_API int nerfb200_ert_depth(const float* weights, const float* z_vals, int n_rays, int n_samples,
+                       float thr, float* z_term, void* stream);
+/* totals[0..1] += counts[0..1] (device side; statistics of the sparse passes) */
+NERFB200_API int nerfb200_accumulate_counts(const int32_t* counts, int64_t* totals, void* stream);
+
 /* ---- whole pass --------------------------------------------------------------------------- */
 typedef struct nerfb200_render_params {
   int n_samples;      /* 64  */
@@ -186,6 +204,12 @@ typedef struct nerfb200_render_params {
   /* a8: when non-NULL the coarse z's of every ray are passed through nerfb200_ess_resample */
   const uint8_t* occupancy_grid; /* uint8 [grid_res]^3, device */
   int grid_res;
+  /* ess_skip = 0: reference semantics (resample highly-empty rays, nerfb200_ess_resample).
+   * ess_skip = 1: empty-space SKIPPING -- samples in empty cells (and, with an ERT variant, fine
+   * samples behind the coarse termination depth) are not evaluated by the MLP at all; their density
+   * is 0.  eval_counts (device int64[2], may be NULL) accumulates the evaluated coarse / fine rows. */
+  int ess_skip;
+  int64_t* eval_counts;
 } nerfb200_render_params;
 
 /* maps for one pass: rgb [n,3], disp/acc/depth [n] */

@@ -7,6 +7,11 @@
 
 #include "common.cuh"
 
+// the ctypes binding (nerf_rep_for_test_b200/lib.py) mirrors these layouts field by field
+static_assert(sizeof(nerfb200_render_params) == 72, "nerfb200_render_params layout changed: update lib.py");
+static_assert(sizeof(nerfb200_mlp_weights) == 24 * sizeof(void*), "nerfb200_mlp_weights layout changed");
+static_assert(sizeof(nerfb200_maps) == 4 * sizeof(void*), "nerfb200_maps layout changed");
+
 namespace nb {
 
 static thread_local char g_err[512] = "";
@@ -23,7 +28,8 @@ void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_r
 int launch_mlp_fp32(const void* packed, const float* rays_o, const float* rays_d, const float* z_vals,
                     int n_rays, int n_samples, float* raw, cudaStream_t st);
 int launch_mlp_bf16(const void* packed, const float* rays_o, const float* rays_d, const float* z_vals,
-                    int n_rays, int n_samples, float* raw, float* stage_dump, void* acts, cudaStream_t st);
+                    int n_rays, int n_samples, float* raw, float* stage_dump, void* acts, const int* row_ids,
+                    const int* n_active, cudaStream_t st);
 
 // ---- optional MLP-kernel timing (bench.py roofline): CUDA events around every mlp launch, on
 // the launching stream, while enabled.  Off by default; the only other global state besides the
@@ -60,6 +66,9 @@ struct Workspace {
   float* weights;   // [c,S]
   float* z_all;     // [c,S+U]
   float* raw_f;     // [c,S+U,4]
+  int32_t* row_ids; // [c,S+U] compacted active rows (sparse ESS mode)
+  int32_t* counters;// [2] active-row counts of the coarse / fine pass
+  float* z_term;    // [c] ERT depth from the coarse pass
   size_t bytes;
 };
 
@@ -78,6 +87,9 @@ static Workspace carve(void* base, int chunk, int S, int U) {
   w.weights = take((size_t)chunk * S);
   w.z_all = take((size_t)chunk * (S + U));
   w.raw_f = take((size_t)chunk * (S + U) * 4);
+  w.row_ids = reinterpret_cast<int32_t*>(take((size_t)chunk * (S + U)));
+  w.counters = reinterpret_cast<int32_t*>(take(64));
+  w.z_term = take((size_t)chunk);
   w.bytes = off;
   return w;
 }
@@ -112,7 +124,7 @@ extern "C" int nerfb200_mlp_forward(const void* packed, int mode, const float* r
   cudaStream_t st = (cudaStream_t)stream;
   bool prof = prof_begin(st);
   int rc = mode == NERFB200_MODE_FP32 ? launch_mlp_fp32(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, st)
-                                      : launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, nullptr, nullptr, st);
+                                      : launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, nullptr, nullptr, nullptr, nullptr, st);
   if (prof) prof_end(st, (double)n_rays * n_samples);
   return rc;
 }
@@ -125,7 +137,25 @@ extern "C" int nerfb200_mlp_forward_train(const void* packed, int mode, const fl
   NB_CHECK_ARG(mode == NERFB200_MODE_BF16, "mlp_forward_train: only NERFB200_MODE_BF16 saves activations");
   NB_CHECK_ARG(((uintptr_t)packed & 1023) == 0 && ((uintptr_t)acts & 15) == 0, "mlp_forward_train: misaligned buffer");
   if (n_rays == 0) return 0;
-  return launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, nullptr, acts, (cudaStream_t)stream);
+  return launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, nullptr, acts, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int nerfb200_mlp_forward_sparse(const void* packed, int mode, const float* rays_o, const float* rays_d,
+                                           const float* z_vals, int n_rays, int n_samples, const int32_t* row_ids,
+                                           const int32_t* n_active, float* raw, void* stream) {
+  NB_CHECK_ARG(n_rays <= 0 || (packed && rays_o && rays_d && z_vals && raw && row_ids && n_active),
+               "mlp_forward_sparse: null pointer");
+  NB_CHECK_ARG(n_rays >= 0 && n_samples >= 1, "mlp_forward_sparse: bad sizes");
+  NB_CHECK_ARG(mode == NERFB200_MODE_BF16, "mlp_forward_sparse: only NERFB200_MODE_BF16 has the sparse launch");
+  NB_CHECK_ARG(((uintptr_t)packed & 1023) == 0, "mlp_forward_sparse: packed weights must be 1024-byte aligned");
+  if (n_rays == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  // skipped rows keep raw = 0: sigma_raw = 0 -> alpha = 0 -> no contribution (and rgb_raw is never used)
+  NB_CUDA(cudaMemsetAsync(raw, 0, (size_t)n_rays * n_samples * 16, st));
+  bool prof = prof_begin(st);
+  int rc = launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, nullptr, nullptr, row_ids, n_active, st);
+  if (prof) prof_end(st, 0.0);   // evaluated rows are data dependent; counted by the caller from n_active
+  return rc;
 }
 
 extern "C" int nerfb200_profile_enable(int on) {
@@ -157,7 +187,7 @@ extern "C" int nerfb200_mlp_forward_stages(const void* packed, int mode, const f
   NB_CHECK_ARG(n_rays >= 1 && n_samples >= 1, "mlp_forward_stages: bad sizes");
   NB_CHECK_ARG(mode == NERFB200_MODE_BF16, "mlp_forward_stages: only NERFB200_MODE_BF16 has a stage dump");
   NB_CHECK_ARG(((uintptr_t)packed & 1023) == 0, "mlp_forward_stages: packed weights must be 1024-byte aligned");
-  return launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, stage_dump, nullptr, (cudaStream_t)stream);
+  return launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, stage_dump, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" size_t nerfb200_render_workspace_bytes(int n_rays, const nerfb200_render_params* p) {
@@ -194,9 +224,15 @@ extern "C" int nerfb200_render_rays(const void* packed_coarse, const void* packe
     int e;
     // per-ray jitter is keyed on the ray index inside the call: offset the seed per chunk
     if ((e = nerfb200_sample_coarse(z_table, n, S, p->perturb, p->seed + (uint64_t)r0 * 0x9E3779B97F4A7C15ull, ws.z_coarse, stream))) return e;
-    if (p->occupancy_grid &&
+    const bool sparse = p->occupancy_grid && p->ess_skip;
+    if (p->occupancy_grid && !sparse &&
         (e = nerfb200_ess_resample(p->occupancy_grid, p->grid_res, ro, rd, n, S, ws.z_coarse, nullptr, stream))) return e;
-    if ((e = nerfb200_mlp_forward(packed_coarse, p->mode, ro, rd, ws.z_coarse, n, S, ws.raw_c, stream))) return e;
+    if (sparse) {
+      if ((e = nerfb200_ess_compact(p->occupancy_grid, p->grid_res, ro, rd, ws.z_coarse, nullptr, n, S, ws.row_ids,
+                                    ws.counters + 0, stream))) return e;
+      if ((e = nerfb200_mlp_forward_sparse(packed_coarse, p->mode, ro, rd, ws.z_coarse, n, S, ws.row_ids, ws.counters + 0,
+                                           ws.raw_c, stream))) return e;
+    } else if ((e = nerfb200_mlp_forward(packed_coarse, p->mode, ro, rd, ws.z_coarse, n, S, ws.raw_c, stream))) return e;
     if ((e = nerfb200_composite_forward(ws.raw_c, ws.z_coarse, rd, n, S, p->variant, p->ert_threshold, p->white_bkgd,
                                         p->compat_chunk, mc->rgb + (size_t)r0 * 3, mc->disp + r0, mc->acc + r0,
                                         mc->depth + r0, ws.weights, stream))) return e;
@@ -204,7 +240,22 @@ extern "C" int nerfb200_render_rays(const void* packed_coarse, const void* packe
       const float* uu = p->u_per_ray ? u + (size_t)r0 * U : u;
       if ((e = nerfb200_sample_pdf_merge(ws.z_coarse, ws.weights, uu, p->u_per_ray, n, S, U, ws.z_all, nullptr, nullptr,
                                          nullptr, stream))) return e;
-      if ((e = nerfb200_mlp_forward(packed_fine, p->mode, ro, rd, ws.z_all, n, S + U, ws.raw_f, stream))) return e;
+      if (sparse) {
+        // fine pass: skip samples in empty cells and, with ERT, samples behind the depth at which the
+        // coarse transmittance fell below the threshold
+        const float* zt = nullptr;
+        if (p->variant != NERFB200_COMPOSITE_PLAIN) {
+          if ((e = nerfb200_ert_depth(ws.weights, ws.z_coarse, n, S, p->ert_threshold, ws.z_term, stream))) return e;
+          zt = ws.z_term;
+        }
+        if ((e = nerfb200_ess_compact(p->occupancy_grid, p->grid_res, ro, rd, ws.z_all, zt, n, S + U, ws.row_ids,
+                                      ws.counters + 1, stream))) return e;
+        if ((e = nerfb200_mlp_forward_sparse(packed_fine, p->mode, ro, rd, ws.z_all, n, S + U, ws.row_ids, ws.counters + 1,
+                                             ws.raw_f, stream))) return e;
+        if (p->eval_counts) {   // optional statistics: evaluated rows per pass, accumulated over the call
+          if ((e = nerfb200_accumulate_counts(ws.counters, p->eval_counts, stream))) return e;
+        }
+      } else if ((e = nerfb200_mlp_forward(packed_fine, p->mode, ro, rd, ws.z_all, n, S + U, ws.raw_f, stream))) return e;
       if ((e = nerfb200_composite_forward(ws.raw_f, ws.z_all, rd, n, S + U, p->variant, p->ert_threshold, p->white_bkgd,
                                           p->compat_chunk, mf->rgb + (size_t)r0 * 3, mf->disp + r0, mf->acc + r0,
                                           mf->depth + r0, nullptr, stream))) return e;

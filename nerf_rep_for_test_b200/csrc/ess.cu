@@ -102,9 +102,84 @@ __global__ void ess_update_kernel(uint8_t* __restrict__ grid, int res, const flo
   grid[((size_t)g[0] * res + g[1]) * res + g[2]] = 1;
 }
 
+// ---- empty-space skipping proper: stream compaction of the rows worth evaluating ----------------
+__global__ void ess_compact_kernel(const uint8_t* __restrict__ grid, int res, const float* __restrict__ rays_o,
+                                   const float* __restrict__ rays_d, const float* __restrict__ z_vals,
+                                   const float* __restrict__ z_term, long long total, int S,
+                                   int32_t* __restrict__ row_ids, int32_t* __restrict__ n_active) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  bool keep = false;
+  if (idx < total) {
+    long long ray = idx / S;
+    float z = z_vals[idx];
+    int g[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      g[c] = grid_index(__fadd_rn(rays_o[ray * 3 + c], __fmul_rn(rays_d[ray * 3 + c], z)), res);
+    keep = grid[((size_t)g[0] * res + g[1]) * res + g[2]] != 0;
+    if (keep && z_term != nullptr) keep = z <= z_term[ray];
+  }
+  // warp-aggregated append: one atomic per warp
+  unsigned m = __ballot_sync(0xffffffffu, keep);
+  int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == 0 && m) base = atomicAdd(n_active, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (keep) row_ids[base + __popc(m & ((1u << lane) - 1))] = (int32_t)idx;
+}
+
+__global__ void ert_depth_kernel(const float* __restrict__ weights, const float* __restrict__ z_vals, int n_rays,
+                                 int S, float thr, float* __restrict__ z_term) {
+  int ray = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ray >= n_rays) return;
+  float acc = 0.f, zt = __int_as_float(0x7f800000);
+  for (int i = 0; i < S; ++i) {
+    if (1.f - acc < thr) { zt = z_vals[(size_t)ray * S + i]; break; }
+    acc += weights[(size_t)ray * S + i];
+  }
+  z_term[ray] = zt;
+}
+
+__global__ void accumulate_counts_kernel(const int32_t* __restrict__ counts, long long* __restrict__ totals) {
+  if (threadIdx.x < 2) totals[threadIdx.x] += counts[threadIdx.x];
+}
+
 }  // namespace nb
 
 using namespace nb;
+
+extern "C" int nerfb200_ess_compact(const uint8_t* grid, int res, const float* rays_o, const float* rays_d,
+                                    const float* z_vals, const float* z_term, int n_rays, int n_samples,
+                                    int32_t* row_ids, int32_t* n_active, void* stream) {
+  NB_CHECK_ARG(n_active, "ess_compact: null counter");
+  NB_CHECK_ARG(n_rays <= 0 || (grid && rays_o && rays_d && z_vals && row_ids), "ess_compact: null pointer");
+  NB_CHECK_ARG(res >= 1 && res <= 1024, "ess_compact: bad grid resolution %d", res);
+  NB_CHECK_ARG(n_rays >= 0 && n_samples >= 1 && (long long)n_rays * n_samples < (1LL << 31), "ess_compact: bad sizes");
+  NB_CUDA(cudaMemsetAsync(n_active, 0, sizeof(int32_t), (cudaStream_t)stream));
+  if (n_rays == 0) return 0;
+  long long total = (long long)n_rays * n_samples;
+  ess_compact_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(grid, res, rays_o, rays_d, z_vals, z_term,
+                                                                             total, n_samples, row_ids, n_active);
+  NB_LAUNCH_OK("ess_compact_kernel");
+  return 0;
+}
+
+extern "C" int nerfb200_ert_depth(const float* weights, const float* z_vals, int n_rays, int n_samples, float thr,
+                                  float* z_term, void* stream) {
+  NB_CHECK_ARG(n_rays <= 0 || (weights && z_vals && z_term), "ert_depth: null pointer");
+  NB_CHECK_ARG(n_rays >= 0 && n_samples >= 1, "ert_depth: bad sizes");
+  if (n_rays == 0) return 0;
+  ert_depth_kernel<<<ceil_div(n_rays, 128), 128, 0, (cudaStream_t)stream>>>(weights, z_vals, n_rays, n_samples, thr, z_term);
+  NB_LAUNCH_OK("ert_depth_kernel");
+  return 0;
+}
+
+extern "C" int nerfb200_accumulate_counts(const int32_t* counts, int64_t* totals, void* stream) {
+  NB_CHECK_ARG(counts && totals, "accumulate_counts: null pointer");
+  accumulate_counts_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(counts, reinterpret_cast<long long*>(totals));
+  NB_LAUNCH_OK("accumulate_counts_kernel");
+  return 0;
+}
 
 extern "C" int nerfb200_ess_resample(const uint8_t* grid, int res, const float* rays_o, const float* rays_d,
                                      int n_rays, int n_samples, float* z_vals, int32_t* n_empty, void* stream) {

@@ -49,7 +49,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __restrict__ rays_o,
                     const float* __restrict__ rays_d, const float* __restrict__ z_vals, long long M, int S,
                     int num_quads, float* __restrict__ raw, float* __restrict__ stage_dump,
-                    unsigned long long* __restrict__ tl, __nv_bfloat16* __restrict__ acts) {
+                    unsigned long long* __restrict__ tl, __nv_bfloat16* __restrict__ acts,
+                    const int* __restrict__ row_ids, const int* __restrict__ n_active) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   const uint32_t smem_base = smem_u32(smem_dyn);
   if ((smem_base & 1023u) != 0) __trap();
@@ -81,7 +82,14 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  const int my_quads = (num_quads - cluster_id + num_clusters - 1) / num_clusters;
+  // sparse launch (empty-space skipping): only the rows listed in row_ids[0 .. *n_active) are evaluated;
+  // the count lives on the device, so the persistent grid derives its trip count from it (no host sync)
+  long long M_eff = M;
+  if (row_ids != nullptr) {
+    M_eff = *n_active;
+    num_quads = (int)((M_eff + 511) / 512);
+  }
+  const int my_quads = num_quads > cluster_id ? (num_quads - cluster_id + num_clusters - 1) / num_clusters : 0;
   const float* tail = reinterpret_cast<const float*>(packed + kBf16TailOff);
 
   if (warp < 8) {
@@ -105,7 +113,8 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
     auto prepare_tile = [&](int it) {
       const long long tile = 4LL * ((long long)cluster_id + (long long)it * num_clusters) + 2 * slot + (long long)rank;
       m = tile * 128 + row;
-      valid = m < M;
+      valid = m < M_eff;
+      if (valid && row_ids != nullptr) m = row_ids[m];   // compacted row -> original (ray, sample) row
       float p[3] = {0.f, 0.f, 0.f};
       d[0] = d[1] = d[2] = 0.f;
       if (valid) {
@@ -359,9 +368,10 @@ int launch_mlp_bf16_1cta(const void* packed, const float* rays_o, const float* r
                          int n_rays, int n_samples, float* raw, float* stage_dump, cudaStream_t st);
 
 int launch_mlp_bf16(const void* packed, const float* rays_o, const float* rays_d, const float* z_vals, int n_rays,
-                    int n_samples, float* raw, float* stage_dump, void* acts, cudaStream_t st) {
+                    int n_samples, float* raw, float* stage_dump, void* acts, const int* row_ids, const int* n_active,
+                    cudaStream_t st) {
   const char* variant = getenv("NERFB200_TC_VARIANT");
-  if (variant && atoi(variant) == 1 && !acts)
+  if (variant && atoi(variant) == 1 && !acts && !row_ids)
     return launch_mlp_bf16_1cta(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, stage_dump, st);
   using namespace tc2;
   int dev = 0, sms = 0;
@@ -387,16 +397,16 @@ int launch_mlp_bf16(const void* packed, const float* rays_o, const float* rays_d
   if (acts)
     mlp_bf16_tc2_kernel<false, false, true><<<2 * clusters, kThreads, kSmemBytes, st>>>(
         (const unsigned char*)packed, rays_o, rays_d, z_vals, M, n_samples, (int)quads, raw, nullptr, nullptr,
-        (__nv_bfloat16*)acts);
+        (__nv_bfloat16*)acts, nullptr, nullptr);
   else if (stage_dump)
     mlp_bf16_tc2_kernel<true, false, false><<<2 * clusters, kThreads, kSmemBytes, st>>>(
-        (const unsigned char*)packed, rays_o, rays_d, z_vals, M, n_samples, (int)quads, raw, stage_dump, nullptr, nullptr);
+        (const unsigned char*)packed, rays_o, rays_d, z_vals, M, n_samples, (int)quads, raw, stage_dump, nullptr, nullptr, nullptr, nullptr);
   else if (tl)
     mlp_bf16_tc2_kernel<false, true, false><<<2 * clusters, kThreads, kSmemBytes, st>>>(
-        (const unsigned char*)packed, rays_o, rays_d, z_vals, M, n_samples, (int)quads, raw, nullptr, tl, nullptr);
+        (const unsigned char*)packed, rays_o, rays_d, z_vals, M, n_samples, (int)quads, raw, nullptr, tl, nullptr, nullptr, nullptr);
   else
     mlp_bf16_tc2_kernel<false, false, false><<<2 * clusters, kThreads, kSmemBytes, st>>>(
-        (const unsigned char*)packed, rays_o, rays_d, z_vals, M, n_samples, (int)quads, raw, nullptr, nullptr, nullptr);
+        (const unsigned char*)packed, rays_o, rays_d, z_vals, M, n_samples, (int)quads, raw, nullptr, nullptr, nullptr, row_ids, n_active);
   NB_LAUNCH_OK("mlp_bf16_tc2_kernel");
   if (tl) {   // debug only (NERFB200_TIMELINE=<file>): dump cluster 0's handshake timestamps
     unsigned long long host[320 + 400];

@@ -32,7 +32,8 @@ class RenderParams(C.Structure):
     _fields_ = [("n_samples", C.c_int), ("n_importance", C.c_int), ("mode", C.c_int),
                 ("variant", C.c_int), ("white_bkgd", C.c_int), ("perturb", C.c_int),
                 ("u_per_ray", C.c_int), ("compat_chunk", C.c_int), ("ert_threshold", C.c_float),
-                ("seed", C.c_uint64), ("occupancy_grid", _vp), ("grid_res", C.c_int)]
+                ("seed", C.c_uint64), ("occupancy_grid", _vp), ("grid_res", C.c_int), ("ess_skip", C.c_int),
+                ("eval_counts", _vp)]
 
 
 class Maps(C.Structure):
@@ -62,6 +63,10 @@ SIGNATURES = {
                                             _vp, _vp]),
     "nerfb200_ess_resample": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "nerfb200_ess_update": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
+    "nerfb200_ess_compact": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "nerfb200_mlp_forward_sparse": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    "nerfb200_ert_depth": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_float, _vp, _vp]),
+    "nerfb200_accumulate_counts": (C.c_int, [_vp, _vp, _vp]),
     "nerfb200_render_workspace_bytes": (C.c_size_t, [C.c_int, C.POINTER(RenderParams)]),
     "nerfb200_render_rays": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp, C.POINTER(RenderParams), _vp,
                                        C.c_size_t, C.POINTER(Maps), C.POINTER(Maps), _vp]),

@@ -170,3 +170,34 @@ def ess_update(grid_u8, rays_o, rays_d, z_vals, raw, weights, use_origin=False):
                                         L.dev(_f(rays_d)), L.dev(_f(z_vals)), L.dev(_f(raw)), L.dev(_f(weights)), n, S,
                                         int(use_origin), L.stream_ptr()), "ess_update")
     return grid_u8
+
+
+def ess_compact(grid_u8, rays_o, rays_d, z_vals, z_term=None):
+    """(row_ids int32 [n*S] with the first n_active entries valid, n_active int32 [1] on the device)."""
+    rays_o, rays_d, z_vals = _f(rays_o), _f(rays_d), _f(z_vals)
+    n, S = z_vals.shape
+    row_ids = torch.empty(n * S, dtype=torch.int32, device=z_vals.device)
+    n_active = torch.zeros(1, dtype=torch.int32, device=z_vals.device)
+    L.check(L.load().nerfb200_ess_compact(L.dev(grid_u8, torch.uint8), grid_u8.shape[0], L.dev(rays_o), L.dev(rays_d),
+                                         L.dev(z_vals), L.dev(_f(z_term)), n, S, L.dev(row_ids), L.dev(n_active),
+                                         L.stream_ptr()), "ess_compact")
+    return row_ids, n_active
+
+
+def mlp_forward_sparse(packed, rays_o, rays_d, z_vals, row_ids, n_active):
+    rays_o, rays_d, z_vals = _f(rays_o), _f(rays_d), _f(z_vals)
+    n, S = z_vals.shape
+    raw = torch.empty((n, S, 4), device=z_vals.device)
+    L.check(L.load().nerfb200_mlp_forward_sparse(packed.ptr, packed.mode, L.dev(rays_o), L.dev(rays_d), L.dev(z_vals),
+                                                n, S, L.dev(row_ids), L.dev(n_active), L.dev(raw), L.stream_ptr()),
+            "mlp_forward_sparse")
+    return raw
+
+
+def ert_depth(weights, z_vals, thr):
+    weights, z_vals = _f(weights), _f(z_vals)
+    n, S = z_vals.shape
+    zt = torch.empty(n, device=z_vals.device)
+    L.check(L.load().nerfb200_ert_depth(L.dev(weights), L.dev(z_vals), n, S, float(thr), L.dev(zt), L.stream_ptr()),
+            "ert_depth")
+    return zt

@@ -143,6 +143,10 @@ class Renderer:
         if self.mode not in self.MODES:
             raise ValueError("mode must be 'bf16' or 'fp32'")
         self.ref_compat = bool(ref_compat)
+        # "resample" = the reference's ESS (:1009-1087); "skip" = samples in empty cells (and, with ERT,
+        # fine samples behind the coarse termination depth) are never sent through the MLP
+        self.ess_mode = "resample"
+        self.eval_counts = None
         self.use_cuda_kernels = True
         self.seed = 0
         self.occupancy_grid = None
@@ -246,6 +250,15 @@ class Renderer:
             self._grid_u8 = self.occupancy_grid.to(torch.uint8).contiguous()
             p.occupancy_grid = self._grid_u8.data_ptr()
             p.grid_res = self.occupancy_grid.shape[0]
+            if self.ess_mode == "skip":
+                if self.mode != "bf16":
+                    raise L.NerfB200Error("ess_mode='skip' needs mode='bf16' (sparse MLP launch)")
+                p.ess_skip = 1
+                if self.enable_ert:
+                    p.variant = L.COMPOSITE_ERT        # per-ray truncation; the chunk quirk has no meaning here
+                if self.eval_counts is None:
+                    self.eval_counts = torch.zeros(2, dtype=torch.int64, device=self.device)
+                p.eval_counts = self.eval_counts.data_ptr()
         return p
 
     def _workspace(self, nbytes):

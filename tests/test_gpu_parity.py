@@ -436,3 +436,84 @@ def test_render_ess_noop_on_lego_pose():
     ess = _renderer(sd, "fp32", enable_ess=True).render(bc)
     for k in MAPS:
         assert bits_equal(plain[k], ess[k]), k
+
+
+# ------------------------------------------------------------------------------- a8 skipping proper
+def _blob_grid(res=128, radius=0.35):
+    gc = torch.stack(torch.meshgrid([torch.arange(res)] * 3, indexing="ij"), -1).float() / (res - 1) * 2 - 1
+    return torch.norm(gc, dim=-1) <= radius
+
+
+def test_ess_skip_equals_masked_dense_and_skips_work():
+    """Empty-space skipping proper: the sparse MLP launch evaluates exactly the rows in occupied cells;
+    the result is bit-identical to the dense launch with the empty rows' raw set to 0."""
+    sd = O.make_state_dict(6, 40.0, 0.5)
+    grid = _blob_grid()
+    b = O.lego_batch(48, 48)
+    ro, rd = O.get_rays(48, 48, b["pose"][0], b["intrinsics"][0])
+    z = O.sample_coarse(ro.shape[0])
+    packed = ops.pack_from_state_dict(sd, "model.", L.MODE_BF16, DEV)
+    g8 = cuda(grid.to(torch.uint8))
+    row_ids, n_active = ops.ess_compact(g8, cuda(ro), cuda(rd), cuda(z))
+    pts = ro[..., None, :] + rd[..., None, :] * z[..., :, None]
+    occ = ~O.is_empty_space(grid, pts.reshape(-1, 3))
+    na = int(n_active)
+    assert na == int(occ.sum()) and 0 < na < occ.numel() // 2
+    assert torch.equal(torch.sort(row_ids[:na].cpu().long())[0], torch.nonzero(occ).flatten())
+    raw_s = ops.mlp_forward_sparse(packed, cuda(ro), cuda(rd), cuda(z), row_ids, n_active)
+    raw_d = ops.mlp_forward(packed, cuda(ro), cuda(rd), cuda(z))
+    raw_d = raw_d * cuda(occ.reshape(raw_d.shape[:2]).float())[..., None]
+    assert torch.equal(raw_s, raw_d)
+    # ERT depth: first z with T < thr from the coarse weights
+    w = ops.composite_forward(raw_d, cuda(z), cuda(rd))[3]
+    zt = ops.ert_depth(w, cuda(z), 0.01).cpu()
+    T = 1.0 - torch.cumsum(torch.cat([torch.zeros(w.shape[0], 1), w.cpu()[:, :-1]], 1), 1)
+    low = T < 0.01
+    ref = torch.where(low.any(1), z.gather(1, low.float().argmax(1, keepdim=True))[:, 0], torch.full((w.shape[0],), float("inf")))
+    # fp32 running sum vs torch.cumsum: allow disagreement only where T sits at the threshold
+    bad = (zt != ref) & ~((T - 0.01).abs().min(1)[0] < 1e-5)
+    assert not bad.any()
+
+
+def test_render_ess_skip_mode_structure_and_counts():
+    sd = O.make_state_dict(6, 300.0, 6.0)
+    for k in list(sd):                       # same (opaque) field for the coarse and the fine network
+        if k.startswith("model_fine."):
+            sd[k] = sd["model." + k[len("model_fine."):]].clone()
+    b = O.lego_batch(40, 40)
+    bc = {k: (cuda(v) if torch.is_tensor(v) else v) for k, v in b.items()}
+    from nerf_rep_for_test_b200 import Network, RenderConfig, Renderer
+    net = Network(device=DEV)
+    net.load_state_dict(sd)
+    net.to(DEV).eval()
+    n = 1600
+    counts = {}
+    outs = {}
+    for ert in (False, True):
+        skip = Renderer(net, RenderConfig(perturb=0, enable_ess=True, enable_ert=ert), mode="bf16")
+        skip.occupancy_grid = _blob_grid().to(DEV)
+        skip.ess_mode = "skip"
+        outs[ert] = skip.render(bc)
+        counts[ert] = skip.eval_counts.cpu().tolist()
+    # empty-space skipping removes most rows; ERT removes fine rows behind the surface on top of that
+    assert 0 < counts[False][0] < 0.5 * n * 64 and 0 < counts[False][1] < 0.5 * n * 192
+    assert counts[True][0] == counts[False][0] and counts[True][1] < counts[False][1]
+    # rays that miss the blob are pure white background, rays that cross it are opaque
+    ro, rd = O.get_rays(40, 40, b["pose"][0], b["intrinsics"][0])
+    z = O.sample_coarse(n)
+    pts = ro[..., None, :] + rd[..., None, :] * z[..., :, None]
+    n_occ = (~O.is_empty_space(_blob_grid(), pts.reshape(-1, 3))).reshape(n, 64).sum(1)
+    # closest approach of each ray to the blob centre (world radius 0.7; a grazing ray can still catch a
+    # fine sample in an occupied cell between two coarse samples, hence the margin of one cell diagonal)
+    t = -(ro * rd).sum(-1)
+    d_min = torch.norm(ro + rd * t[:, None], dim=-1)
+    miss = d_min > 0.7 + 0.06
+    assert int(miss.sum()) > 100 and int((n_occ >= 8).sum()) > 100
+    for ert in (False, True):
+        acc = outs[ert]["acc_map"].reshape(-1).cpu()
+        assert float(acc[miss].abs().max()) == 0.0
+        assert bits_equal(outs[ert]["rgb_map"].reshape(-1, 3)[miss], torch.ones(int(miss.sum()), 3))
+        assert float(acc[n_occ >= 8].min()) > 0.9
+    # ERT only drops samples whose transmittance is already below the threshold
+    d = (outs[True]["rgb_map"] - outs[False]["rgb_map"]).abs().max()
+    assert float(d) <= 0.011 + 1e-3
