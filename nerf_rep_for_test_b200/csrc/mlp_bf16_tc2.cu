@@ -36,15 +36,30 @@ constexpr uint32_t kSmemBytes = kOffBias + 2048;            // 231680 <= 232448
 enum { BAR_WFULL = 0, BAR_WEMPTY = 4, BAR_AREADY = 8, BAR_ACCFULL = 10, BAR_BFULL = 12, BAR_BEMPTY = 14, BAR_COUNT = 16 };
 
 // which on-chip buffer holds K-chunk c of a stage's input, and how many K=16 steps it has
-__device__ __forceinline__ void chunk_src(int stage, int c, bool& from_pe, int& kblock, int& ksteps) {
+// (`last` = the views stage: 9 in the unfused image, 8 = "8F" in the fused inference image)
+__device__ __forceinline__ void chunk_src(int stage, int last, int c, bool& from_pe, int& kblock, int& ksteps) {
   ksteps = 4;
   if (stage == 0) { from_pe = true; kblock = 0; }
   else if (stage == 5) { from_pe = (c == 0); kblock = c - 1; }
-  else if (stage == 9) { from_pe = (c == 4); kblock = c; if (c == 4) ksteps = 2; }
+  else if (stage == last) { from_pe = (c == 4); kblock = c; if (c == 4) ksteps = 2; }
   else { from_pe = false; kblock = c; }
 }
 
-template <bool kDump, bool kTimeline, bool kSave>
+// per-stage geometry of the packed image, unfused (10 stages) or fused (9 stages, mlp_layout.cuh)
+template <bool kFused> struct Img {
+  static constexpr int kN = kFused ? 9 : kStages;
+  static constexpr int kLast = kN - 1;
+  __device__ static __forceinline__ int chunks(int s) { return (kFused && s == 8) ? kFusedChunks : stage_chunks(s); }
+  __device__ static __forceinline__ int n(int s) { return (kFused && s == 8) ? kFusedN : stage_n(s); }
+  __device__ static __forceinline__ uint32_t chunk_bytes(int s) { return (kFused && s == 8) ? (uint32_t)kFusedChunkBytes : (uint32_t)bf16_chunk_bytes(s); }
+  __device__ static __forceinline__ size_t stage_off(int s) { return (kFused && s == 8) ? (size_t)kFusedStageOff : (size_t)bf16_stage_off(s); }
+  __device__ static __forceinline__ const float* bias(const unsigned char* packed, int s) {
+    return (kFused && s == 8) ? reinterpret_cast<const float*>(packed + kFusedTailOff)
+                              : reinterpret_cast<const float*>(packed + kBf16TailOff) + kTailBias + s * 256;
+  }
+};
+
+template <bool kDump, bool kTimeline, bool kSave, bool kFused>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __restrict__ rays_o,
                     const float* __restrict__ rays_d, const float* __restrict__ z_vals, long long M, int S,
@@ -89,6 +104,7 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
     M_eff = *n_active;
     num_quads = (int)((M_eff + 511) / 512);
   }
+  using I = Img<kFused>;
   const int my_quads = num_quads > cluster_id ? (num_quads - cluster_id + num_clusters - 1) / num_clusters : 0;
   const float* tail = reinterpret_cast<const float*>(packed + kBf16TailOff);
 
@@ -147,11 +163,11 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
       fence_proxy_async_smem();
       mbar_arrive_remote(b_ready_leader);
       float sigma = 0.f;
-      for (int stage = 0; stage < kStages; ++stage) {
-        const uint32_t bseq = (uint32_t)it * kStages + (uint32_t)stage;
+      for (int stage = 0; stage < I::kN; ++stage) {
+        const uint32_t bseq = (uint32_t)it * I::kN + (uint32_t)stage;
         const uint32_t bbuf = bseq & 1u;
         const float4* bias4 = reinterpret_cast<const float4*>(smem_dyn + kOffBias + bbuf * 1024u);
-        if (stage == 9 && it + 1 < my_quads) prepare_tile(it + 1);   // overlaps stage 9's MMAs
+        if (stage == I::kLast && it + 1 < my_quads) prepare_tile(it + 1);   // overlaps the last stage's MMAs
         mbar_wait(bar(BAR_BFULL + bbuf), (bseq >> 1) & 1u, 0x500 + stage);
         mbar_wait(b_full, full_phase, 0x100 + stage);
         full_phase ^= 1;
@@ -159,7 +175,7 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
         if (kTimeline && tl && blockIdx.x == 0 && it < 4 && row == 0) tl[((it * 10 + stage) * 2 + slot) * 4 + 2] = clock64();
         if (kDump) {   // diagnostic: fp32 post-activation outputs of rows 0..127 of the whole problem
           if (m_cur - row == 0) {
-            const int ncb = stage == 9 ? 4 : 8;
+            const int ncb = stage == I::kLast ? 4 : 8;
             for (int cb = 0; cb < ncb; ++cb) {
               uint32_t v[32];
               tmem_ld32(t_acc + (uint32_t)cb * 32u, v);
@@ -173,9 +189,9 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
             }
           }
         }
-        if (stage < 9) {
-          if (stage == 7) epi_stage256<1>(t_acc, bias4, a_row_base, r7, tail + kTailAlphaW, sigma);
-          else if (stage == 8) epi_stage256<2>(t_acc, bias4, a_row_base, r7, nullptr, sigma);
+        if (stage < I::kLast) {
+          if (!kFused && stage == 7) epi_stage256<1>(t_acc, bias4, a_row_base, r7, tail + kTailAlphaW, sigma);
+          else if (!kFused && stage == 8) epi_stage256<2>(t_acc, bias4, a_row_base, r7, nullptr, sigma);
           else epi_stage256<0>(t_acc, bias4, a_row_base, r7, nullptr, sigma);
           if (kSave && valid_cur) {
             // training: keep this stage's bf16 output [stage][M][256] for the backward pass; re-read the
@@ -187,7 +203,7 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
               for (int j = 0; j < 8; ++j)
                 dst[h * 8 + j] = *reinterpret_cast<const uint4*>(a_row_base + h * 16384 + ((j ^ r7) << 4));
           }
-          if (stage == 8) {  // dir PE replaces the xyz PE tile (dead after stage 5) for stage 9
+          if (stage == I::kLast - 1) {  // dir PE replaces the xyz PE tile (dead after stage 5) for the views stage
             float f[32];
             pos_enc_row<kLd>(d_cur, f);
 #pragma unroll
@@ -228,6 +244,13 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
               }
             }
           }
+          if (kFused) {   // sigma_raw = accumulator column 128 (+ alpha_b, staged as bias element 128)
+            uint32_t v[32];
+            tmem_ld32(t_acc + 128u, v);
+            tmem_ld_wait();
+            pin32(v);
+            sigma = __uint_as_float(v[0]) + bias4[32].x - tail[kTailAlphaB];   // alpha_b is added below
+          }
           tc_fence_before();
           mbar_arrive(bar(BAR_BEMPTY + bbuf));
           if (valid_cur) {
@@ -242,12 +265,12 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
     // =========================== producer: bias block + this CTA's half of every weight chunk ==========
     uint32_t seq = 0, bseq = 0;
     for (int it = 0; it < my_quads; ++it) {
-      for (int stage = 0; stage < kStages; ++stage, ++bseq) {
+      for (int stage = 0; stage < I::kN; ++stage, ++bseq) {
         {
           const uint32_t bbuf = bseq & 1u;
           if (lane == 0) mbar_wait(bar(BAR_BEMPTY + bbuf), ((bseq >> 1) & 1u) ^ 1u, 0x600 + stage);
           __syncwarp();
-          const float4* src4 = reinterpret_cast<const float4*>(tail + kTailBias + stage * 256);
+          const float4* src4 = reinterpret_cast<const float4*>(I::bias(packed, stage));
           float4 v0 = __ldg(src4 + lane), v1 = __ldg(src4 + 32 + lane);
           const uint32_t dst = smem_base + kOffBias + bbuf * 1024u + (uint32_t)lane * 16u;
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(v0.x), "f"(v0.y), "f"(v0.z), "f"(v0.w) : "memory");
@@ -256,10 +279,10 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
           if (lane == 0) mbar_arrive(bar(BAR_BFULL + bbuf));
         }
         if (lane == 0) {
-          const uint32_t chunk_bytes = (uint32_t)bf16_chunk_bytes(stage);   // full N rows
+          const uint32_t chunk_bytes = I::chunk_bytes(stage);               // full N rows
           const uint32_t half = chunk_bytes >> 1;                           // this CTA's N/2 rows
-          const unsigned char* src = packed + bf16_stage_off(stage) + (size_t)rank * half;
-          const int nch = stage_chunks(stage);
+          const unsigned char* src = packed + I::stage_off(stage) + (size_t)rank * half;
+          const int nch = I::chunks(stage);
           for (int c = 0; c < nch; ++c, ++seq) {
             const uint32_t pos = seq % kRing, phase = (seq / kRing) & 1u;
             mbar_wait(bar(BAR_WEMPTY + pos), phase ^ 1u, 0x200 + stage);
@@ -275,8 +298,8 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
     if (lane == 0) {
       uint32_t seq = 0;
       for (int it = 0; it < my_quads; ++it)
-        for (int stage = 0; stage < kStages; ++stage) {
-          const int nch = stage_chunks(stage);
+        for (int stage = 0; stage < I::kN; ++stage) {
+          const int nch = I::chunks(stage);
           for (int c = 0; c < nch; ++c, ++seq) {
             const uint32_t pos = seq % kRing, phase = (seq / kRing) & 1u;
             mbar_wait(bar(BAR_WFULL + pos), phase, 0x700 + stage);
@@ -298,9 +321,9 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
     const uint32_t pe_lo0 = lo_flags | ((smem_base + kOffPe) >> 4);   // + slot*1024 + 2*k
     const uint32_t w_lo0 = lo_flags | ((smem_base + kOffW) >> 4);     // + pos*1024 + 2*k
     for (int it = 0; it < my_quads; ++it) {
-      for (int stage = 0; stage < kStages; ++stage) {
-        const int nch = stage_chunks(stage);
-        const uint32_t idesc = umma_idesc_bf16(256, stage_n(stage));
+      for (int stage = 0; stage < I::kN; ++stage) {
+        const int nch = I::chunks(stage);
+        const uint32_t idesc = umma_idesc_bf16(256, I::n(stage));
         // chunk groups of at most kRing chunks: slot 0 runs the group, then slot 1 runs it and releases it
         for (int g0 = 0; g0 < nch; g0 += kRing) {
           const int g1 = (g0 + kRing < nch) ? g0 + kRing : nch;
@@ -329,7 +352,7 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
               }
               bool from_pe;
               int kblock, ksteps;
-              chunk_src(stage, c, from_pe, kblock, ksteps);
+              chunk_src(stage, I::kLast, c, from_pe, kblock, ksteps);
               const uint32_t a_lo = from_pe ? (pe_lo0 + (uint32_t)slot * (kPeBytes >> 4))
                                             : (a_lo0 + (uint32_t)slot * (kABytes >> 4) + (uint32_t)kblock * 1024u);
               const uint32_t b_lo = w_lo0 + pos * (kWStageBytes >> 4);
@@ -377,10 +400,10 @@ int launch_mlp_bf16(const void* packed, const float* rays_o, const float* rays_d
   int dev = 0, sms = 0;
   NB_CUDA(cudaGetDevice(&dev));
   NB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-  NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-  NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-  NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<true, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<false, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   const char* tl_env = getenv("NERFB200_TIMELINE");
   unsigned long long* tl = nullptr;
   if (tl_env && !stage_dump && !acts) {
@@ -395,17 +418,17 @@ int launch_mlp_bf16(const void* packed, const float* rays_o, const float* rays_d
     if (v > 0 && v < clusters) clusters = v;
   }
   if (acts)
-    mlp_bf16_tc2_kernel<false, false, true><<<2 * clusters, kThreads, kSmemBytes, st>>>(
+    mlp_bf16_tc2_kernel<false, false, true, false><<<2 * clusters, kThreads, kSmemBytes, st>>>(
         (const unsigned char*)packed, rays_o, rays_d, z_vals, M, n_samples, (int)quads, raw, nullptr, nullptr,
         (__nv_bfloat16*)acts, nullptr, nullptr);
   else if (stage_dump)
-    mlp_bf16_tc2_kernel<true, false, false><<<2 * clusters, kThreads, kSmemBytes, st>>>(
+    mlp_bf16_tc2_kernel<true, false, false, false><<<2 * clusters, kThreads, kSmemBytes, st>>>(
         (const unsigned char*)packed, rays_o, rays_d, z_vals, M, n_samples, (int)quads, raw, stage_dump, nullptr, nullptr, nullptr, nullptr);
   else if (tl)
-    mlp_bf16_tc2_kernel<false, true, false><<<2 * clusters, kThreads, kSmemBytes, st>>>(
+    mlp_bf16_tc2_kernel<false, true, false, true><<<2 * clusters, kThreads, kSmemBytes, st>>>(
         (const unsigned char*)packed, rays_o, rays_d, z_vals, M, n_samples, (int)quads, raw, nullptr, tl, nullptr, nullptr, nullptr);
   else
-    mlp_bf16_tc2_kernel<false, false, false><<<2 * clusters, kThreads, kSmemBytes, st>>>(
+    mlp_bf16_tc2_kernel<false, false, false, true><<<2 * clusters, kThreads, kSmemBytes, st>>>(
         (const unsigned char*)packed, rays_o, rays_d, z_vals, M, n_samples, (int)quads, raw, nullptr, nullptr, nullptr, row_ids, n_active);
   NB_LAUNCH_OK("mlp_bf16_tc2_kernel");
   if (tl) {   // debug only (NERFB200_TIMELINE=<file>): dump cluster 0's handshake timestamps

@@ -58,6 +58,19 @@ constexpr int kTailRgbB = kTailRgbW + 3 * 128;
 constexpr int kTailFloats = kTailRgbB + 4;
 constexpr int kBf16TotalBytes = kBf16TailOff + kTailFloats * 4;
 
+// ---- fused inference tail (BF16): feature_linear has no activation, so for inference it is folded
+// into views_linears.0 (W' = Wv[:, :256] * Wf, b' = Wv[:, :256] * bf + bv) and alpha_linear rides along
+// as output column 128 of the same MMA: stages 8 and 9 become ONE stage "8F" with
+//   in: h7(256) | dpe(32)  ->  N = 144 = 128 (views, relu) + 16 (column 128 = sigma_raw, rest 0).
+// This removes 65 536 of the 593 408 MACs per row and one accumulator drain.  Stages 0..7 are shared
+// with the unfused image; the 8F chunks and its fp32 bias row are appended after the unfused image.
+constexpr int kFusedN = 144;
+constexpr int kFusedChunks = 5;
+constexpr int kFusedChunkBytes = kFusedN * 128;                                   // 18432
+constexpr int kFusedStageOff = (kBf16TotalBytes + 1023) / 1024 * 1024;
+constexpr int kFusedTailOff = kFusedStageOff + kFusedChunks * kFusedChunkBytes;   // fp32 [256]: b'(128), alpha_b, 0...
+constexpr int kBf16PackedBytes = kFusedTailOff + 256 * 4;
+
 // source element of stage s, output n, padded input k (returns false when the slot is padding)
 struct SrcRef { int tensor; int col; };  // tensor: 0..7 pts, 8 feature, 9 views
 __host__ __device__ inline bool stage_src(int s, int k, SrcRef* r) {

@@ -77,13 +77,49 @@ __global__ void pack_bf16_kernel(nerfb200_mlp_weights w, StageTable tab, unsigne
   }
 }
 
+// fused stage 8F (mlp_layout.cuh): one thread per (n, k) of the [144][320] operand + the bias row
+__global__ void pack_bf16_fused_kernel(nerfb200_mlp_weights w, unsigned char* __restrict__ dst) {
+  const int total = kFusedN * kFusedChunks * 64;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total + 256; i += gridDim.x * blockDim.x) {
+    if (i >= total) {   // bias row
+      int n = i - total;
+      float v = 0.f;
+      if (n < 128) {
+        v = w.views_b[n];
+        for (int j = 0; j < 256; ++j) v = fmaf(w.views_w[(size_t)n * 283 + j], w.feature_b[j], v);
+      } else if (n == 128) {
+        v = w.alpha_b[0];
+      }
+      reinterpret_cast<float*>(dst + kFusedTailOff)[n] = v;
+      continue;
+    }
+    int c = i / (kFusedN * 64);
+    int n = (i / 64) % kFusedN;
+    int kk = i % 64;
+    int k = c * 64 + kk;
+    float v = 0.f;
+    if (n < 128) {
+      if (k < 256) {
+        for (int j = 0; j < 256; ++j) v = fmaf(w.views_w[(size_t)n * 283 + j], w.feature_w[(size_t)j * 256 + k], v);
+      } else if (k - 256 < kChD) {
+        v = w.views_w[(size_t)n * 283 + k];
+      }
+    } else if (n == 128 && k < 256) {
+      v = w.alpha_w[k];
+    }
+    size_t off = (size_t)kFusedStageOff + (size_t)c * kFusedChunkBytes + (size_t)n * 128 +
+                 (size_t)(((kk >> 3) ^ (n & 7)) << 4) + (size_t)(kk & 7) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(dst + off) = __float2bfloat16_rn(v);
+  }
+}
+
 }  // namespace nb
 
 using namespace nb;
 
 extern "C" size_t nerfb200_packed_weights_bytes(int mode) {
   if (mode == NERFB200_MODE_FP32) return (size_t)kF32TotalFloats * 4;
-  if (mode == NERFB200_MODE_BF16) return (size_t)kBf16TotalBytes;
+  if (mode == NERFB200_MODE_BF16) return (size_t)kBf16PackedBytes;
   return 0;
 }
 
@@ -102,8 +138,11 @@ extern "C" int nerfb200_pack_weights(const nerfb200_mlp_weights* w, int mode, vo
   dim3 grid(64, kStages + 1);
   if (mode == NERFB200_MODE_FP32)
     pack_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*w, tab, (float*)packed);
-  else
+  else {
     pack_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*w, tab, (unsigned char*)packed);
+    NB_LAUNCH_OK("pack_bf16_kernel");
+    pack_bf16_fused_kernel<<<96, 256, 0, (cudaStream_t)stream>>>(*w, (unsigned char*)packed);
+  }
   NB_LAUNCH_OK("pack_weights_kernel");
   return 0;
 }
