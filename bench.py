@@ -34,6 +34,9 @@ H = W = 800
 N_SAMPLES, N_IMPORTANCE = 64, 128
 ROWS_PER_RAY = N_SAMPLES + (N_SAMPLES + N_IMPORTANCE)        # 64 coarse + 192 fine = 256
 FLOP_PER_ROW = 1186816                                       # BASELINE.md section 4 (unpadded K)
+# MACs the bf16 inference kernel actually issues per row (padded K, feature_linear folded into
+# views_linears.0 with alpha as 16 extra columns): 64*256 + 4*256*256 + 320*256 + 2*256*256 + 288*144
+EXECUTED_FLOP_PER_ROW_BF16 = 2 * (64 * 256 + 4 * 65536 + 320 * 256 + 2 * 65536 + 288 * 144)
 METRIC = "rendered rays/sec (coarse64+fine128, 800x800)"
 
 
@@ -342,7 +345,12 @@ def run_ours(args):
                          "nominal fp32 FFMA 80 TFLOP/s (parity mode, not the performance path)",
                          "launches_timed": mlp_launches, "kernel_ms_per_step": mlp_ms / args.steps,
                          "kernel_share_of_step": mlp_ms / ms_total,
-                         "algorithmic_flop_per_row": FLOP_PER_ROW, "rows_per_step": mlp_rows / args.steps},
+                         "algorithmic_flop_per_row": FLOP_PER_ROW, "rows_per_step": mlp_rows / args.steps,
+                         "executed_flop_per_row": EXECUTED_FLOP_PER_ROW_BF16 if args.mode == "bf16" else 2 * 600064,
+                         "executed_tflops": (achieved * EXECUTED_FLOP_PER_ROW_BF16 / FLOP_PER_ROW) if args.mode == "bf16" else None,
+                         "note": "achieved = algorithmic FLOPs of the reference MLP / kernel time; the bf16 kernel "
+                                 "executes fewer (feature_linear is folded into views_linears.0 for inference): "
+                                 "executed_tflops is what the tensor pipe actually did"},
         }
         if args.train_steps > 0:
             it_ms = train_ms / args.train_steps

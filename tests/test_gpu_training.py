@@ -79,7 +79,7 @@ def test_training_gradients_vs_oracle_autograd():
     # the fine sample positions our (bf16) forward uses, rebuilt with the same kernels
     from nerf_rep_for_test_b200 import lib as L, ops
     z_c = ops.sample_coarse(r._table("z"), ro.shape[0])
-    raw_c = ops.mlp_forward(r.packed("coarse"), ro.to(DEV), rd.to(DEV), z_c)
+    raw_c, _ = ops.mlp_forward_train(r.packed("coarse"), ro.to(DEV), rd.to(DEV), z_c)   # the training forward
     w_c = ops.composite_forward(raw_c, z_c, rd.to(DEV))[3]
     z_all = ops.sample_pdf_merge(z_c, w_c, r._table("u"), want_aux=False)[0].cpu()
     loss_ref, gref = _oracle_grads(sd, ro, rd, target, z_all)
