@@ -517,3 +517,56 @@ def test_render_ess_skip_mode_structure_and_counts():
     # ERT only drops samples whose transmittance is already below the threshold
     d = (outs[True]["rgb_map"] - outs[False]["rgb_map"]).abs().max()
     assert float(d) <= 0.011 + 1e-3
+
+
+# ------------------------------------------------------------------------------- config switches of the reference
+@pytest.mark.parametrize("cfg", [dict(white_bkgd=0), dict(lindisp=True), dict(N_importance=0),
+                                 dict(N_samples=32, N_importance=64), dict(near=1.0, far=5.0)])
+def test_render_fp32_config_switches_vs_oracle(cfg):
+    """white_bkgd / lindisp / N_importance=0 / other sample counts and bounds (volume_renderer.py:31-48,
+    :223-224, :179, :352-354) against the oracle with the same switches."""
+    sd = O.make_state_dict(7, 30.0, 0.2)
+    b = O.lego_batch(10, 14)
+    r = _renderer(sd, "fp32", **cfg)
+    out = r.render({k: (cuda(v) if torch.is_tensor(v) else v) for k, v in b.items()})
+    ro, rd = O.get_rays(10, 14, b["pose"][0], b["intrinsics"][0])
+    S, U = cfg.get("N_samples", 64), cfg.get("N_importance", 128)
+    near, far = cfg.get("near", 2.0), cfg.get("far", 6.0)
+    wb = bool(cfg.get("white_bkgd", 1))
+    with torch.no_grad():
+        z = O.coarse_t_table(S, near, far, cfg.get("lindisp", False)).expand(ro.shape[0], S)
+        raw = O.query_network(sd, "model.", ro[:, None] + rd[:, None] * z[..., None], rd)
+        rgb0, disp0, acc0, w, depth0 = O.raw2outputs(raw, z, rd, wb)
+        ref = {"rgb_map_0": rgb0, "acc_map_0": acc0, "depth_map_0": depth0}
+        if U > 0:
+            t_fine, _, _ = O.sample_fine(.5 * (z[..., 1:] + z[..., :-1]), w[..., 1:-1], None, U)
+            z_all, _ = torch.sort(torch.cat([z, t_fine], -1), -1)
+            raw_f = O.query_network(sd, "model_fine.", ro[:, None] + rd[:, None] * z_all[..., None], rd)
+            rgb, _, acc, _, depth = O.raw2outputs(raw_f, z_all, rd, wb)
+            ref.update({"rgb_map": rgb, "acc_map": acc, "depth_map": depth})
+    assert ("rgb_map" in out) == (U > 0)
+    for k, v in ref.items():
+        rel_close(out[k].reshape(v.shape), v, 1e-5, 1e-5 * (far if "depth" in k else 1.0))
+
+
+def test_unsupported_switches_fail_loudly():
+    sd = O.make_state_dict(0)
+    with pytest.raises(L.NerfB200Error):
+        _renderer(sd, "fp32", use_viewdirs=False)
+    r = _renderer(sd, "fp32", raw_noise_std=1.0)
+    b = O.lego_batch(4, 4)
+    with pytest.raises(L.NerfB200Error):
+        r.render({k: (cuda(v) if torch.is_tensor(v) else v) for k, v in b.items()})
+    with pytest.raises(L.NerfB200Error):   # CPU tensors are rejected: there is no CPU path
+        ops.composite_forward(torch.zeros(1, 4, 4), torch.zeros(1, 4), torch.zeros(1, 3))
+
+
+def test_perturbed_render_is_stratified_and_seeded():
+    sd = O.make_state_dict(1, 30.0, 0.2)
+    b = O.lego_batch(12, 12)
+    bc = {k: (cuda(v) if torch.is_tensor(v) else v) for k, v in b.items()}
+    r = _renderer(sd, "fp32", perturb=1)
+    a, c = r.render(bc)["rgb_map"], r.render(bc)["rgb_map"]
+    assert not torch.equal(a, c)                       # jitter differs call to call (as the reference's does)
+    base = _renderer(sd, "fp32").render(bc)["rgb_map"]
+    assert float((a - base).abs().mean()) < 0.05       # ... but it is the same image up to sampling noise
