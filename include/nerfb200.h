@@ -65,7 +65,7 @@ typedef struct nerfb200_mlp_weights {
   const float* rgb_b;     /* rgb_linear.bias            (3)                                        */
 } nerfb200_mlp_weights;
 
-/* gradients of the same 24 tensors (same shapes), accumulated (+=) by mlp_backward */
+/* gradients of the same 24 tensors (same shapes), OVERWRITTEN by nerfb200_mlp_backward */
 typedef struct nerfb200_mlp_grads {
   float* pts_w[8];
   float* pts_b[8];
@@ -115,12 +115,30 @@ NERFB200_API int nerfb200_pack_weights(const nerfb200_mlp_weights* w, int mode, 
 NERFB200_API int nerfb200_mlp_forward(const void* packed, int mode, const float* rays_o, const float* rays_d,
                          const float* z_vals, int n_rays, int n_samples, float* raw, void* stream);
 
-/* training twin of mlp_forward (BF16 mode): additionally stores the bf16 output of each of the ten
- * stages (mlp_layout.cuh: relu(h0..h7), feature (linear), relu(views); stage 9 fills columns 0..127)
- * as acts [10][n_rays*n_samples][256] bf16 for the backward pass. */
+/* ---- a7: training twin of mlp_forward and the MLP backward (autograd through network.py:49-74) ---- */
+/* Buffer sizes for n_rows = n_rays*n_samples MLP rows.  acts / dacts are "tile images": per 128-row tile a
+ * sequence of 16 KB blocks, each the [128 rows][64 bf16] cut of one stage output in the shared-memory
+ * layout of tcgen05.mma (SWIZZLE_128B); layout in csrc/train_layout.cuh.  masks = relu sign bits. */
+NERFB200_API size_t nerfb200_train_acts_bytes(long long n_rows);
+NERFB200_API size_t nerfb200_train_masks_bytes(long long n_rows);
+NERFB200_API size_t nerfb200_mlp_backward_workspace_bytes(long long n_rows);
+/* BF16 mode forward that additionally keeps, for the backward pass, the bf16 inputs/outputs of the ten
+ * stages (PE, dir-PE, relu(h0..h7), feature, relu(views)) in `acts` (128-byte aligned) and the relu sign
+ * bits in `masks` (16-byte aligned). */
 NERFB200_API int nerfb200_mlp_forward_train(const void* packed, int mode, const float* rays_o,
                                const float* rays_d, const float* z_vals, int n_rays, int n_samples,
-                               float* raw, void* acts, void* stream);
+                               float* raw, void* acts, void* masks, void* stream);
+/* W^T image for the backward dgrad chain; re-run after every optimizer step (1024-byte aligned). */
+NERFB200_API size_t nerfb200_packed_bwd_bytes(void);
+NERFB200_API int nerfb200_pack_weights_bwd(const nerfb200_mlp_weights* w, void* packed_bwd, void* stream);
+/* Gradients of the 24 tensors of one model given g_raw = dL/d raw [n_rows,4] (fp32) and the acts/masks of
+ * nerfb200_mlp_forward_train on the same rows.  Two tcgen05 kernels: the activation-gradient chain
+ * (keeps every dL/d pre-activation in the workspace) and ten split-K weight-gradient GEMMs with the bias
+ * and head gradients riding along; bf16 operands, fp32 accumulation, fp32 results.  MLP inputs receive
+ * no gradient (the hierarchical sampler is detached).  workspace: 128-byte aligned. */
+NERFB200_API int nerfb200_mlp_backward(const void* packed_bwd, const float* g_raw, const void* acts,
+                          const void* masks, long long n_rows, void* workspace, size_t workspace_bytes,
+                          const nerfb200_mlp_grads* grads, void* stream);
 
 /* diagnostic twin of mlp_forward (BF16 mode): additionally writes the fp32 post-activation output
  * of each of the ten stages (mlp_layout.cuh) for rows 0..127 into stage_dump [10][128][256];

@@ -6,6 +6,7 @@
 #include <atomic>
 
 #include "common.cuh"
+#include "train_layout.cuh"
 
 // the ctypes binding (nerf_rep_for_test_b200/lib.py) mirrors these layouts field by field
 static_assert(sizeof(nerfb200_render_params) == 72, "nerfb200_render_params layout changed: update lib.py");
@@ -28,8 +29,12 @@ void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_r
 int launch_mlp_fp32(const void* packed, const float* rays_o, const float* rays_d, const float* z_vals,
                     int n_rays, int n_samples, float* raw, cudaStream_t st);
 int launch_mlp_bf16(const void* packed, const float* rays_o, const float* rays_d, const float* z_vals,
-                    int n_rays, int n_samples, float* raw, float* stage_dump, void* acts, const int* row_ids,
-                    const int* n_active, cudaStream_t st);
+                    int n_rays, int n_samples, float* raw, float* stage_dump, void* acts, void* masks,
+                    const int* row_ids, const int* n_active, cudaStream_t st);
+int launch_mlp_bwd_dgrad(const void* packed_bwd, const float* g_raw, const void* masks, void* dacts, long long M,
+                         cudaStream_t st);
+int launch_mlp_bwd_wgrad(const void* acts, const void* dacts, long long M, float* scratch, const nerfb200_mlp_grads* grads,
+                         cudaStream_t st);
 
 // ---- optional MLP-kernel timing (bench.py roofline): CUDA events around every mlp launch, on
 // the launching stream, while enabled.  Off by default; the only other global state besides the
@@ -124,20 +129,56 @@ extern "C" int nerfb200_mlp_forward(const void* packed, int mode, const float* r
   cudaStream_t st = (cudaStream_t)stream;
   bool prof = prof_begin(st);
   int rc = mode == NERFB200_MODE_FP32 ? launch_mlp_fp32(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, st)
-                                      : launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, nullptr, nullptr, nullptr, nullptr, st);
+                                      : launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, nullptr, nullptr, nullptr, nullptr, nullptr, st);
   if (prof) prof_end(st, (double)n_rays * n_samples);
   return rc;
 }
 
+extern "C" size_t nerfb200_train_acts_bytes(long long n_rows) {
+  return n_rows <= 0 ? 0 : (size_t)((n_rows + 127) / 128) * kActBlocks * kBlockBytes;
+}
+extern "C" size_t nerfb200_train_masks_bytes(long long n_rows) {
+  return n_rows <= 0 ? 0 : (size_t)((n_rows + 127) / 128) * 128 * kMaskWords * 4 * kMaskPlanes;
+}
+extern "C" size_t nerfb200_mlp_backward_workspace_bytes(long long n_rows) {
+  return n_rows <= 0 ? 0 : (size_t)((n_rows + 127) / 128) * kDactBlocks * kBlockBytes + kGradScratchFloats * sizeof(float);
+}
+
 extern "C" int nerfb200_mlp_forward_train(const void* packed, int mode, const float* rays_o, const float* rays_d,
                                           const float* z_vals, int n_rays, int n_samples, float* raw, void* acts,
-                                          void* stream) {
-  NB_CHECK_ARG(n_rays <= 0 || (packed && rays_o && rays_d && z_vals && raw && acts), "mlp_forward_train: null pointer");
+                                          void* masks, void* stream) {
+  NB_CHECK_ARG(n_rays <= 0 || (packed && rays_o && rays_d && z_vals && raw && acts && masks), "mlp_forward_train: null pointer");
   NB_CHECK_ARG(n_rays >= 0 && n_samples >= 1, "mlp_forward_train: bad sizes");
   NB_CHECK_ARG(mode == NERFB200_MODE_BF16, "mlp_forward_train: only NERFB200_MODE_BF16 saves activations");
-  NB_CHECK_ARG(((uintptr_t)packed & 1023) == 0 && ((uintptr_t)acts & 15) == 0, "mlp_forward_train: misaligned buffer");
+  NB_CHECK_ARG(((uintptr_t)packed & 1023) == 0 && ((uintptr_t)acts & 127) == 0 && ((uintptr_t)masks & 15) == 0,
+               "mlp_forward_train: misaligned buffer");
   if (n_rays == 0) return 0;
-  return launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, nullptr, acts, nullptr, nullptr, (cudaStream_t)stream);
+  return launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, nullptr, acts, masks, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int nerfb200_mlp_backward(const void* packed_bwd, const float* g_raw, const void* acts, const void* masks,
+                                     long long n_rows, void* workspace, size_t workspace_bytes,
+                                     const nerfb200_mlp_grads* grads, void* stream) {
+  NB_CHECK_ARG(n_rows >= 0, "mlp_backward: bad n_rows");
+  NB_CHECK_ARG(grads, "mlp_backward: null grads");
+  for (int i = 0; i < 8; ++i) NB_CHECK_ARG(grads->pts_w[i] && grads->pts_b[i], "mlp_backward: null gradient pts_linears.%d", i);
+  NB_CHECK_ARG(grads->views_w && grads->views_b && grads->feature_w && grads->feature_b && grads->alpha_w && grads->alpha_b &&
+                   grads->rgb_w && grads->rgb_b, "mlp_backward: null head gradient");
+  NB_CHECK_ARG(n_rows == 0 || (packed_bwd && g_raw && acts && masks && workspace), "mlp_backward: null pointer");
+  NB_CHECK_ARG(workspace_bytes >= nerfb200_mlp_backward_workspace_bytes(n_rows), "mlp_backward: workspace too small (%zu < %zu)",
+               workspace_bytes, nerfb200_mlp_backward_workspace_bytes(n_rows));
+  NB_CHECK_ARG(((uintptr_t)packed_bwd & 1023) == 0 && ((uintptr_t)acts & 127) == 0 && ((uintptr_t)workspace & 127) == 0 &&
+                   ((uintptr_t)masks & 15) == 0 && ((uintptr_t)g_raw & 15) == 0, "mlp_backward: misaligned buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t dacts_bytes = (size_t)((n_rows + 127) / 128) * kDactBlocks * kBlockBytes;
+  float* scratch = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + dacts_bytes);
+  if (n_rows > 0) {
+    int rc = launch_mlp_bwd_dgrad(packed_bwd, g_raw, masks, workspace, n_rows, st);
+    if (rc) return rc;
+  } else {
+    NB_CHECK_ARG(workspace && workspace_bytes >= kGradScratchFloats * sizeof(float), "mlp_backward: workspace too small");
+  }
+  return launch_mlp_bwd_wgrad(acts, workspace, n_rows, scratch, grads, st);
 }
 
 extern "C" int nerfb200_mlp_forward_sparse(const void* packed, int mode, const float* rays_o, const float* rays_d,
@@ -153,7 +194,7 @@ extern "C" int nerfb200_mlp_forward_sparse(const void* packed, int mode, const f
   // skipped rows keep raw = 0: sigma_raw = 0 -> alpha = 0 -> no contribution (and rgb_raw is never used)
   NB_CUDA(cudaMemsetAsync(raw, 0, (size_t)n_rays * n_samples * 16, st));
   bool prof = prof_begin(st);
-  int rc = launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, nullptr, nullptr, row_ids, n_active, st);
+  int rc = launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, nullptr, nullptr, nullptr, row_ids, n_active, st);
   if (prof) prof_end(st, 0.0);   // evaluated rows are data dependent; counted by the caller from n_active
   return rc;
 }
@@ -187,7 +228,7 @@ extern "C" int nerfb200_mlp_forward_stages(const void* packed, int mode, const f
   NB_CHECK_ARG(n_rays >= 1 && n_samples >= 1, "mlp_forward_stages: bad sizes");
   NB_CHECK_ARG(mode == NERFB200_MODE_BF16, "mlp_forward_stages: only NERFB200_MODE_BF16 has a stage dump");
   NB_CHECK_ARG(((uintptr_t)packed & 1023) == 0, "mlp_forward_stages: packed weights must be 1024-byte aligned");
-  return launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, stage_dump, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+  return launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, stage_dump, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" size_t nerfb200_render_workspace_bytes(int n_rays, const nerfb200_render_params* p) {

@@ -18,6 +18,7 @@
 #include <stdlib.h>
 
 #include "mlp_tc_common.cuh"
+#include "train_layout.cuh"
 
 namespace nb {
 namespace tc2 {
@@ -64,8 +65,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __restrict__ rays_o,
                     const float* __restrict__ rays_d, const float* __restrict__ z_vals, long long M, int S,
                     int num_quads, float* __restrict__ raw, float* __restrict__ stage_dump,
-                    unsigned long long* __restrict__ tl, __nv_bfloat16* __restrict__ acts,
-                    const int* __restrict__ row_ids, const int* __restrict__ n_active) {
+                    unsigned long long* __restrict__ tl, unsigned char* __restrict__ acts,
+                    uint32_t* __restrict__ masks, const int* __restrict__ row_ids, const int* __restrict__ n_active) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   const uint32_t smem_base = smem_u32(smem_dyn);
   if ((smem_base & 1023u) != 0) __trap();
@@ -122,12 +123,18 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
     uint32_t full_phase = 0;
 
     // rays / PE of a tile are computed one tile ahead so that only the stores sit on the critical path
-    long long m = 0;
+    long long m = 0, tile_next = 0;
     bool valid = false;
+    // training (kSave): finished operand tiles go to the activation store as tile images (train_layout.cuh)
+    // with one bulk store per tile, issued by the group's first thread behind a 128-thread named barrier
+    const long long n_tiles = (M + 127) / 128;
+    const bool save_leader = kSave && w4 == 0 && lane == 0;
+    const uint32_t a_tile_smem = smem_base + kOffA + (uint32_t)slot * kABytes;
     float d[3] = {0.f, 0.f, 0.f};
     uint32_t pe_pk[32];
     auto prepare_tile = [&](int it) {
       const long long tile = 4LL * ((long long)cluster_id + (long long)it * num_clusters) + 2 * slot + (long long)rank;
+      tile_next = tile;
       m = tile * 128 + row;
       valid = m < M_eff;
       if (valid && row_ids != nullptr) m = row_ids[m];   // compacted row -> original (ray, sample) row
@@ -153,7 +160,15 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
     for (int it = 0; it < my_quads; ++it) {
       const long long m_cur = m;
       const bool valid_cur = valid;
+      const bool tile_ok = kSave && tile_next < n_tiles;
+      unsigned char* acts_tile = kSave ? acts + (size_t)tile_next * ((size_t)kActBlocks * kBlockBytes) : nullptr;
+      const size_t mask_row = (size_t)tile_next * 128 + (size_t)row;
+      const size_t mask_plane = (size_t)n_tiles * 128 * kMaskWords;
       float d_cur[3] = {d[0], d[1], d[2]};
+      if (kSave) {   // the previous tile's stores must have finished reading the PE / A buffers
+        if (save_leader) bulk_wait_read0();
+        named_bar_sync(1 + slot, 128);
+      }
       {  // xyz PE tile -> shared memory (swizzled 16-byte chunks), then hand the slot to the MMA issuer
         const uint32_t row_base = pe_base + (uint32_t)row * 128u;
 #pragma unroll
@@ -161,6 +176,13 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
           st_shared_v4(row_base + (uint32_t)((j ^ r7) << 4), pe_pk[4 * j], pe_pk[4 * j + 1], pe_pk[4 * j + 2], pe_pk[4 * j + 3]);
       }
       fence_proxy_async_smem();
+      if (kSave) {
+        named_bar_sync(1 + slot, 128);
+        if (save_leader && tile_ok) {
+          bulk_s2g(acts_tile + (size_t)kActPe * kBlockBytes, pe_base, kBlockBytes);
+          bulk_commit();
+        }
+      }
       mbar_arrive_remote(b_ready_leader);
       float sigma = 0.f;
       for (int stage = 0; stage < I::kN; ++stage) {
@@ -189,19 +211,19 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
             }
           }
         }
+        if (kSave) {   // the previous stage's bulk store has finished reading the A tile we are about to rewrite
+          if (save_leader) bulk_wait_read0();
+          named_bar_sync(1 + slot, 128);
+        }
         if (stage < I::kLast) {
-          if (!kFused && stage == 7) epi_stage256<1>(t_acc, bias4, a_row_base, r7, tail + kTailAlphaW, sigma);
+          uint32_t mw[8];
+          if (!kFused && stage == 7) epi_stage256<1, kSave>(t_acc, bias4, a_row_base, r7, tail + kTailAlphaW, sigma, mw);
           else if (!kFused && stage == 8) epi_stage256<2>(t_acc, bias4, a_row_base, r7, nullptr, sigma);
-          else epi_stage256<0>(t_acc, bias4, a_row_base, r7, nullptr, sigma);
-          if (kSave && valid_cur) {
-            // training: keep this stage's bf16 output [stage][M][256] for the backward pass; re-read the
-            // row this thread just wrote (same thread, program order) and stream it out
-            uint4* dst = reinterpret_cast<uint4*>(acts + ((size_t)stage * (size_t)M + (size_t)m_cur) * 256);
-#pragma unroll
-            for (int h = 0; h < 4; ++h)
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                dst[h * 8 + j] = *reinterpret_cast<const uint4*>(a_row_base + h * 16384 + ((j ^ r7) << 4));
+          else epi_stage256<0, kSave>(t_acc, bias4, a_row_base, r7, nullptr, sigma, mw);
+          if (kSave && tile_ok && stage < 8) {   // relu sign bits of this stage for the dgrad epilogue
+            uint4* dst = reinterpret_cast<uint4*>(masks + (size_t)stage * mask_plane + mask_row * kMaskWords);
+            dst[0] = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+            dst[1] = make_uint4(mw[4], mw[5], mw[6], mw[7]);
           }
           if (stage == I::kLast - 1) {  // dir PE replaces the xyz PE tile (dead after stage 5) for the views stage
             float f[32];
@@ -212,14 +234,24 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
           }
           tc_fence_before();
           fence_proxy_async_smem();
+          if (kSave) {   // stage output (= next stage's A tile) -> activation store, 64 KB in one bulk store
+            named_bar_sync(1 + slot, 128);
+            if (save_leader && tile_ok) {
+              bulk_s2g(acts_tile + (size_t)(stage < 8 ? act_h(stage) : kActFeat) * kBlockBytes, a_tile_smem, 4 * kBlockBytes);
+              if (stage == I::kLast - 1) bulk_s2g(acts_tile + (size_t)kActDpe * kBlockBytes, pe_base, kBlockBytes);
+              bulk_commit();
+            }
+          }
           mbar_arrive_remote(b_ready_leader);
           mbar_arrive(bar(BAR_BEMPTY + bbuf));
           if (kTimeline && tl && blockIdx.x == 0 && it < 4 && row == 0) tl[((it * 10 + stage) * 2 + slot) * 4 + 3] = clock64();
         } else {
           // stage 9: views_linears.0 (128 wide, relu) -> rgb_linear on CUDA cores (network.py:66-69)
           float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+          uint32_t hvm[4] = {0u, 0u, 0u, 0u};
 #pragma unroll 2
           for (int cb = 0; cb < 4; ++cb) {
+            uint32_t ch[4] = {0u, 0u, 0u, 0u};
             uint32_t v[32];
             tmem_ld32(t_acc + (uint32_t)cb * 32u, v);
             tmem_ld_wait();
@@ -231,17 +263,33 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
               float4 w0 = __ldg(reinterpret_cast<const float4*>(tail + kTailRgbW + n));
               float4 w1 = __ldg(reinterpret_cast<const float4*>(tail + kTailRgbW + 128 + n));
               float4 w2 = __ldg(reinterpret_cast<const float4*>(tail + kTailRgbW + 256 + n));
-              float h0 = fmaxf(__uint_as_float(v[q * 4 + 0]) + b4.x, 0.f);
-              float h1 = fmaxf(__uint_as_float(v[q * 4 + 1]) + b4.y, 0.f);
-              float h2 = fmaxf(__uint_as_float(v[q * 4 + 2]) + b4.z, 0.f);
-              float h3 = fmaxf(__uint_as_float(v[q * 4 + 3]) + b4.w, 0.f);
+              const float x0 = __uint_as_float(v[q * 4 + 0]) + b4.x, x1 = __uint_as_float(v[q * 4 + 1]) + b4.y;
+              const float x2 = __uint_as_float(v[q * 4 + 2]) + b4.z, x3 = __uint_as_float(v[q * 4 + 3]) + b4.w;
+              float h0 = fmaxf(x0, 0.f);
+              float h1 = fmaxf(x1, 0.f);
+              float h2 = fmaxf(x2, 0.f);
+              float h3 = fmaxf(x3, 0.f);
               r0 = fmaf(h0, w0.x, r0); r0 = fmaf(h1, w0.y, r0); r0 = fmaf(h2, w0.z, r0); r0 = fmaf(h3, w0.w, r0);
               r1 = fmaf(h0, w1.x, r1); r1 = fmaf(h1, w1.y, r1); r1 = fmaf(h2, w1.z, r1); r1 = fmaf(h3, w1.w, r1);
               r2 = fmaf(h0, w2.x, r2); r2 = fmaf(h1, w2.y, r2); r2 = fmaf(h2, w2.z, r2); r2 = fmaf(h3, w2.w, r2);
-              if (kSave && valid_cur) {
+              if (kSave) {   // bf16 row of relu(views) into the (now dead) A tile, blocks 0..1, + its sign bits
+                ch[0] = __funnelshift_l(__float_as_uint(x0), ch[0], 1); ch[1] = __funnelshift_l(__float_as_uint(x1), ch[1], 1);
+                ch[2] = __funnelshift_l(__float_as_uint(x2), ch[2], 1); ch[3] = __funnelshift_l(__float_as_uint(x3), ch[3], 1);
                 uint2 pk = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
-                *reinterpret_cast<uint2*>(acts + ((size_t)9 * (size_t)M + (size_t)m_cur) * 256 + n) = pk;
+                const int col = n & 63;   // column inside block (n >> 6)
+                *reinterpret_cast<uint2*>(a_row_base + (n >> 6) * 16384 + (((col >> 3) ^ r7) << 4) + (col & 7) * 2) = pk;
               }
+            }
+            if (kSave) hvm[cb] = ch[0] | (ch[1] << 8) | (ch[2] << 16) | (ch[3] << 24);
+          }
+          if (kSave) {
+            if (tile_ok)
+              *reinterpret_cast<uint4*>(masks + (size_t)8 * mask_plane + mask_row * kMaskWords) = make_uint4(hvm[0], hvm[1], hvm[2], hvm[3]);
+            fence_proxy_async_smem();
+            named_bar_sync(1 + slot, 128);
+            if (save_leader && tile_ok) {
+              bulk_s2g(acts_tile + (size_t)kActHv * kBlockBytes, a_tile_smem, 2 * kBlockBytes);
+              bulk_commit();
             }
           }
           if (kFused) {   // sigma_raw = accumulator column 128 (+ alpha_b, staged as bias element 128)
@@ -376,6 +424,7 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
       }
     }
   }
+  if (kSave) bulk_wait0();   // outstanding activation stores (only the issuing threads hold groups)
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();   // no CTA may exit (or free TMEM) while its peer still multicasts into it
@@ -391,8 +440,8 @@ int launch_mlp_bf16_1cta(const void* packed, const float* rays_o, const float* r
                          int n_rays, int n_samples, float* raw, float* stage_dump, cudaStream_t st);
 
 int launch_mlp_bf16(const void* packed, const float* rays_o, const float* rays_d, const float* z_vals, int n_rays,
-                    int n_samples, float* raw, float* stage_dump, void* acts, const int* row_ids, const int* n_active,
-                    cudaStream_t st) {
+                    int n_samples, float* raw, float* stage_dump, void* acts, void* masks, const int* row_ids,
+                    const int* n_active, cudaStream_t st) {
   const char* variant = getenv("NERFB200_TC_VARIANT");
   if (variant && atoi(variant) == 1 && !acts && !row_ids)
     return launch_mlp_bf16_1cta(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, stage_dump, st);
@@ -420,16 +469,16 @@ int launch_mlp_bf16(const void* packed, const float* rays_o, const float* rays_d
   if (acts)
     mlp_bf16_tc2_kernel<false, false, true, false><<<2 * clusters, kThreads, kSmemBytes, st>>>(
         (const unsigned char*)packed, rays_o, rays_d, z_vals, M, n_samples, (int)quads, raw, nullptr, nullptr,
-        (__nv_bfloat16*)acts, nullptr, nullptr);
+        (unsigned char*)acts, (uint32_t*)masks, nullptr, nullptr);
   else if (stage_dump)
     mlp_bf16_tc2_kernel<true, false, false, false><<<2 * clusters, kThreads, kSmemBytes, st>>>(
-        (const unsigned char*)packed, rays_o, rays_d, z_vals, M, n_samples, (int)quads, raw, stage_dump, nullptr, nullptr, nullptr, nullptr);
+        (const unsigned char*)packed, rays_o, rays_d, z_vals, M, n_samples, (int)quads, raw, stage_dump, nullptr, nullptr, nullptr, nullptr, nullptr);
   else if (tl)
     mlp_bf16_tc2_kernel<false, true, false, true><<<2 * clusters, kThreads, kSmemBytes, st>>>(
-        (const unsigned char*)packed, rays_o, rays_d, z_vals, M, n_samples, (int)quads, raw, nullptr, tl, nullptr, nullptr, nullptr);
+        (const unsigned char*)packed, rays_o, rays_d, z_vals, M, n_samples, (int)quads, raw, nullptr, tl, nullptr, nullptr, nullptr, nullptr);
   else
     mlp_bf16_tc2_kernel<false, false, false, true><<<2 * clusters, kThreads, kSmemBytes, st>>>(
-        (const unsigned char*)packed, rays_o, rays_d, z_vals, M, n_samples, (int)quads, raw, nullptr, nullptr, nullptr, row_ids, n_active);
+        (const unsigned char*)packed, rays_o, rays_d, z_vals, M, n_samples, (int)quads, raw, nullptr, nullptr, nullptr, nullptr, row_ids, n_active);
   NB_LAUNCH_OK("mlp_bf16_tc2_kernel");
   if (tl) {   // debug only (NERFB200_TIMELINE=<file>): dump cluster 0's handshake timestamps
     unsigned long long host[320 + 400];

@@ -43,9 +43,13 @@ __device__ __forceinline__ void pin32(uint32_t (&r)[32]) {
 // memory), activation folded into the bf16 pack, swizzled 16-byte stores into the next stage's A
 // operand.  MODE 0: ReLU; 1: ReLU + alpha_linear partial dot on the fp32 values (stage 7); 2: linear.
 // Plain C++ shared-memory accesses (not volatile asm) so the compiler batches the bias loads.
-template <int MODE>
+// kMask (training forward): additionally returns the relu sign bits of the 32 columns in the bit order
+// of train_layout.cuh (column 4s+k -> bit 8k+7-s, set = negative), built with one funnel shift per value.
+template <int MODE, bool kMask = false>
 __device__ __forceinline__ void epi32(const uint32_t (&v)[32], const float4* __restrict__ bias4, unsigned char* out_row,
-                                      int j0, int r7, const float* __restrict__ alpha_w, float& sigma) {
+                                      int j0, int r7, const float* __restrict__ alpha_w, float& sigma,
+                                      uint32_t* mask_word = nullptr) {
+  uint32_t ch0 = 0, ch1 = 0, ch2 = 0, ch3 = 0;
   float4 b[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) b[i] = bias4[i];
@@ -68,18 +72,26 @@ __device__ __forceinline__ void epi32(const uint32_t (&v)[32], const float4* __r
       sigma = fmaf(fmaxf(x2.x, 0.f), a1.x, sigma); sigma = fmaf(fmaxf(x2.y, 0.f), a1.y, sigma);
       sigma = fmaf(fmaxf(x3.x, 0.f), a1.z, sigma); sigma = fmaf(fmaxf(x3.y, 0.f), a1.w, sigma);
     }
+    if (kMask) {
+      ch0 = __funnelshift_l(__float_as_uint(x0.x), ch0, 1); ch1 = __funnelshift_l(__float_as_uint(x0.y), ch1, 1);
+      ch2 = __funnelshift_l(__float_as_uint(x1.x), ch2, 1); ch3 = __funnelshift_l(__float_as_uint(x1.y), ch3, 1);
+      ch0 = __funnelshift_l(__float_as_uint(x2.x), ch0, 1); ch1 = __funnelshift_l(__float_as_uint(x2.y), ch1, 1);
+      ch2 = __funnelshift_l(__float_as_uint(x3.x), ch2, 1); ch3 = __funnelshift_l(__float_as_uint(x3.y), ch3, 1);
+    }
     constexpr bool kRelu = MODE != 2;
     uint4 o;
     o.x = cvt_bf16x2<kRelu>(x0.x, x0.y); o.y = cvt_bf16x2<kRelu>(x1.x, x1.y);
     o.z = cvt_bf16x2<kRelu>(x2.x, x2.y); o.w = cvt_bf16x2<kRelu>(x3.x, x3.y);
     *reinterpret_cast<uint4*>(out_row + (((j0 + q) ^ r7) << 4)) = o;
   }
+  if (kMask) *mask_word = ch0 | (ch1 << 8) | (ch2 << 16) | (ch3 << 24);
 }
 
 // one hidden stage (256 accumulator columns) with the TMEM loads double-buffered
-template <int MODE>
+template <int MODE, bool kMask = false>
 __device__ __forceinline__ void epi_stage256(uint32_t t_acc, const float4* __restrict__ bias4, unsigned char* a_row_base,
-                                             int r7, const float* __restrict__ alpha_w, float& sigma) {
+                                             int r7, const float* __restrict__ alpha_w, float& sigma,
+                                             uint32_t* mw = nullptr) {
   uint32_t va[32], vb[32];
   tmem_ld32(t_acc, va);
   tmem_ld32(t_acc + 32u, vb);
@@ -89,9 +101,9 @@ __device__ __forceinline__ void epi_stage256(uint32_t t_acc, const float4* __res
 #pragma unroll
   for (int h = 0; h < 4; ++h) {   // K-block h of the A operand = columns 64h .. 64h+63
     unsigned char* out_row = a_row_base + h * 16384;
-    epi32<MODE>(va, bias4 + h * 16, out_row, 0, r7, alpha_w + h * 64, sigma);
+    epi32<MODE, kMask>(va, bias4 + h * 16, out_row, 0, r7, alpha_w + h * 64, sigma, mw + 2 * h);
     if (h < 3) tmem_ld32(t_acc + (uint32_t)(h * 64 + 64), va);
-    epi32<MODE>(vb, bias4 + h * 16 + 8, out_row, 4, r7, alpha_w + h * 64 + 32, sigma);
+    epi32<MODE, kMask>(vb, bias4 + h * 16 + 8, out_row, 4, r7, alpha_w + h * 64 + 32, sigma, mw + 2 * h + 1);
     if (h < 3) {
       tmem_ld32(t_acc + (uint32_t)(h * 64 + 96), vb);
       tmem_ld_wait();

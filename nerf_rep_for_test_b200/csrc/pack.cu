@@ -3,6 +3,7 @@
 #include <cuda_bf16.h>
 
 #include "mlp_layout.cuh"
+#include "train_layout.cuh"
 
 namespace nb {
 
@@ -113,6 +114,32 @@ __global__ void pack_bf16_fused_kernel(nerfb200_mlp_weights w, unsigned char* __
   }
 }
 
+// backward image (train_layout.cuh): W^T chunks for the dgrad chain + fp32 head weights
+__global__ void pack_bf16_bwd_kernel(nerfb200_mlp_weights w, unsigned char* __restrict__ dst) {
+  const int b = blockIdx.y;
+  if (b == kBwdStages) {
+    float* tail = reinterpret_cast<float*>(dst + kBwdTailOff);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kBwdTailFloats; i += gridDim.x * blockDim.x)
+      tail[i] = i < kBwdTailAlphaW ? w.rgb_w[i] : w.alpha_w[i - kBwdTailAlphaW];
+    return;
+  }
+  const int total = bwd_chunks(b) * 256 * 64;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i / (256 * 64), n = (i / 64) % 256, kk = i % 64;
+    const int k = c * 64 + kk;   // output index of the layer = K of the dgrad GEMM
+    float v;
+    if (b == 0) v = w.views_w[(size_t)k * 283 + n];
+    else if (b == 1) v = w.feature_w[(size_t)k * 256 + n];
+    else {
+      const int layer = 9 - b;   // 7..1
+      v = layer == 5 ? w.pts_w[5][(size_t)k * 319 + kChX + n] : w.pts_w[layer][(size_t)k * 256 + n];
+    }
+    size_t off = (size_t)bwd_stage_off(b) + (size_t)c * kBwdChunkBytes + (size_t)n * 128 +
+                 (size_t)(((kk >> 3) ^ (n & 7)) << 4) + (size_t)(kk & 7) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(dst + off) = __float2bfloat16_rn(v);
+  }
+}
+
 }  // namespace nb
 
 using namespace nb;
@@ -144,5 +171,17 @@ extern "C" int nerfb200_pack_weights(const nerfb200_mlp_weights* w, int mode, vo
     pack_bf16_fused_kernel<<<96, 256, 0, (cudaStream_t)stream>>>(*w, (unsigned char*)packed);
   }
   NB_LAUNCH_OK("pack_weights_kernel");
+  return 0;
+}
+
+extern "C" size_t nerfb200_packed_bwd_bytes(void) { return (size_t)kBwdPackedBytes; }
+
+extern "C" int nerfb200_pack_weights_bwd(const nerfb200_mlp_weights* w, void* packed_bwd, void* stream) {
+  NB_CHECK_ARG(w && packed_bwd, "pack_weights_bwd: null pointer");
+  NB_CHECK_ARG(((uintptr_t)packed_bwd & 1023) == 0, "pack_weights_bwd: buffer must be 1024-byte aligned");
+  for (int i = 1; i < 8; ++i) NB_CHECK_ARG(w->pts_w[i], "pack_weights_bwd: null pts_linears.%d", i);
+  NB_CHECK_ARG(w->views_w && w->feature_w && w->alpha_w && w->rgb_w, "pack_weights_bwd: null head tensor");
+  pack_bf16_bwd_kernel<<<dim3(64, kBwdStages + 1), 256, 0, (cudaStream_t)stream>>>(*w, (unsigned char*)packed_bwd);
+  NB_LAUNCH_OK("pack_bf16_bwd_kernel");
   return 0;
 }

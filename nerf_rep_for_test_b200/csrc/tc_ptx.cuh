@@ -113,6 +113,25 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                : "memory");
 }
 
+// ---- bulk async copy shared -> global (TMA engine, 1-D) + its bulk-group bookkeeping -----------
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk stores of this thread have finished READING shared memory (source reusable)
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... have completed (writes performed)
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// named barrier among `n` threads (n multiple of 32); id 0 is __syncthreads
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t n) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+// fp32 x4 reduction into global memory (no return value)
+__device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // ---- TMEM ----------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
@@ -164,6 +183,24 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // Instruction descriptor for kind::f16: D fp32, A/B bf16, both K-major, dense, M x N.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// MN-major operand (the K dimension runs over the 128-byte ROWS of the same SWIZZLE_128B block image):
+// canonical layout ((8,8,m),(8,k)) : ((1,8,LBO),(64,SBO)) in elements -- a 64-element MN atom is one
+// 128-byte row, 8 K-rows make a 1024-byte swizzle atom (SBO = 1024 B), consecutive 64-wide MN atoms are
+// `lbo_bytes` apart (16384 B = one block of the tile images in train_layout.cuh).
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor with both operands MN-major (bits 15 / 16)
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_mn(int M, int N) {
+  return umma_idesc_bf16(M, N) | (1u << 15) | (1u << 16);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T, issued by ONE thread on behalf of the CTA

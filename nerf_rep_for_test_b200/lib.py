@@ -28,6 +28,10 @@ class MlpWeights(C.Structure):
                 ("alpha_w", _vp), ("alpha_b", _vp), ("rgb_w", _vp), ("rgb_b", _vp)]
 
 
+class MlpGrads(C.Structure):
+    _fields_ = MlpWeights._fields_
+
+
 class RenderParams(C.Structure):
     _fields_ = [("n_samples", C.c_int), ("n_importance", C.c_int), ("mode", C.c_int),
                 ("variant", C.c_int), ("white_bkgd", C.c_int), ("perturb", C.c_int),
@@ -52,7 +56,13 @@ SIGNATURES = {
     "nerfb200_packed_weights_bytes": (C.c_size_t, [C.c_int]),
     "nerfb200_pack_weights": (C.c_int, [C.POINTER(MlpWeights), C.c_int, _vp, _vp]),
     "nerfb200_mlp_forward": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp]),
-    "nerfb200_mlp_forward_train": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "nerfb200_train_acts_bytes": (C.c_size_t, [C.c_longlong]),
+    "nerfb200_train_masks_bytes": (C.c_size_t, [C.c_longlong]),
+    "nerfb200_mlp_backward_workspace_bytes": (C.c_size_t, [C.c_longlong]),
+    "nerfb200_mlp_forward_train": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    "nerfb200_packed_bwd_bytes": (C.c_size_t, []),
+    "nerfb200_pack_weights_bwd": (C.c_int, [C.POINTER(MlpWeights), _vp, _vp]),
+    "nerfb200_mlp_backward": (C.c_int, [_vp, _vp, _vp, _vp, C.c_longlong, _vp, C.c_size_t, C.POINTER(MlpGrads), _vp]),
     "nerfb200_mlp_forward_stages": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "nerfb200_composite_forward": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
                                              C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),

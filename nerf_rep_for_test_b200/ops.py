@@ -78,15 +78,77 @@ def mlp_forward(packed, rays_o, rays_d, z_vals):
     return raw
 
 
+class TrainStore:
+    """What the training forward keeps for nerfb200_mlp_backward: activation tile images + relu sign bits
+    (layout: csrc/train_layout.cuh)."""
+
+    # block index of each plane inside a 128-row tile of `acts`, and its width in 64-column blocks
+    PLANES = {"pe": (0, 1), "dpe": (1, 1), "feat": (34, 4), "hv": (38, 2)}
+    PLANES.update({"h%d" % i: (2 + 4 * i, 4) for i in range(8)})
+    BLOCKS, BLOCK_BYTES = 40, 16384
+
+    def __init__(self, n_rows, device):
+        lib = L.load()
+        self.n_rows = n_rows
+        self.acts = torch.empty(lib.nerfb200_train_acts_bytes(n_rows), dtype=torch.uint8, device=device)
+        self.masks = torch.empty(lib.nerfb200_train_masks_bytes(n_rows), dtype=torch.uint8, device=device)
+
+    def plane(self, name):
+        """[n_rows, 64*width] bf16 copy of one saved plane (tests / debugging only)."""
+        blk, width = self.PLANES[name]
+        return untile(self.acts, self.n_rows, self.BLOCKS, blk, width)
+
+
+def untile(buf, n_rows, blocks_per_tile, first_block, n_blocks):
+    """Undo the SWIZZLE_128B tile-image layout: uint8 buffer -> [n_rows, 64*n_blocks] bf16."""
+    n_tiles = (n_rows + 127) // 128
+    t = buf.view(torch.bfloat16).view(n_tiles, blocks_per_tile, 128, 8, 8)[:, first_block:first_block + n_blocks]
+    r = torch.arange(128, device=buf.device)
+    u = torch.arange(8, device=buf.device)
+    phys = (u[None, :] ^ (r[:, None] & 7))                       # [128, 8]: physical 16-byte unit of logical unit u
+    idx = phys[None, None, :, :, None].expand(n_tiles, n_blocks, 128, 8, 8)
+    t = torch.gather(t, 3, idx)                                  # logical unit order
+    return t.permute(0, 2, 1, 3, 4).reshape(n_tiles * 128, n_blocks * 64)[:n_rows].contiguous()
+
+
 def mlp_forward_train(packed, rays_o, rays_d, z_vals):
-    """BF16 mode: (raw [n,S,4] fp32, acts [10, n*S, 256] bf16) -- stage outputs kept for backward."""
+    """BF16 mode: (raw [n,S,4] fp32, TrainStore) -- stage outputs and relu sign bits kept for backward."""
     rays_o, rays_d, z_vals = _f(rays_o), _f(rays_d), _f(z_vals)
     n, S = z_vals.shape
     raw = torch.empty((n, S, 4), device=z_vals.device)
-    acts = torch.empty((10, n * S, 256), dtype=torch.bfloat16, device=z_vals.device)
+    store = TrainStore(n * S, z_vals.device)
     L.check(L.load().nerfb200_mlp_forward_train(packed.ptr, packed.mode, L.dev(rays_o), L.dev(rays_d), L.dev(z_vals),
-                                               n, S, L.dev(raw), L.dev(acts), L.stream_ptr()), "mlp_forward_train")
-    return raw, acts
+                                               n, S, L.dev(raw), L.dev(store.acts), L.dev(store.masks),
+                                               L.stream_ptr()), "mlp_forward_train")
+    return raw, store
+
+
+GRAD_SHAPES = [(256, 63), (256,)] + [(256, 256), (256,)] * 4 + [(256, 319), (256,)] + [(256, 256), (256,)] * 2 + \
+    [(128, 283), (128,), (256, 256), (256,), (1, 256), (1,), (3, 128), (3,)]
+
+
+def mlp_backward(packed_bwd_ptr, g_raw, store, keep_workspace=None):
+    """nerfb200_mlp_backward: the 24 gradients (order of training._NAMES) of one model given dL/draw.
+    `keep_workspace`: optional dict that receives the workspace tensor (tests read the dgrad planes)."""
+    g_raw = _f(g_raw).reshape(-1, 4)
+    lib = L.load()
+    n_rows = store.n_rows
+    if g_raw.shape[0] != n_rows:
+        raise L.NerfB200Error("mlp_backward: g_raw has %d rows, the forward saved %d" % (g_raw.shape[0], n_rows))
+    dev = g_raw.device
+    ws_bytes = lib.nerfb200_mlp_backward_workspace_bytes(n_rows)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    grads = [torch.empty(sh, device=dev) for sh in GRAD_SHAPES]
+    g = L.MlpGrads()
+    for i in range(8):
+        g.pts_w[i], g.pts_b[i] = grads[2 * i].data_ptr(), grads[2 * i + 1].data_ptr()
+    (g.views_w, g.views_b, g.feature_w, g.feature_b, g.alpha_w, g.alpha_b, g.rgb_w, g.rgb_b) = \
+        [t.data_ptr() for t in grads[16:24]]
+    L.check(lib.nerfb200_mlp_backward(packed_bwd_ptr, L.dev(g_raw), L.dev(store.acts), L.dev(store.masks), n_rows,
+                                      L.dev(ws), ws_bytes, C.byref(g), L.stream_ptr()), "mlp_backward")
+    if keep_workspace is not None:
+        keep_workspace["ws"] = ws
+    return grads
 
 
 def mlp_forward_stages(packed, rays_o, rays_d, z_vals):

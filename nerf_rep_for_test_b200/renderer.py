@@ -193,6 +193,22 @@ class Renderer:
         self._packed[which] = (key, buf, base)
         return buf
 
+    def packed_bwd(self, which):
+        """W^T image for nerfb200_mlp_backward (training), cached per parameter version like _packed_weights."""
+        model = self.coarse_model if which == "coarse" else self.fine_model
+        key = tuple((p.data_ptr(), p._version) for p in model.parameters())
+        ent = self._packed.get("bwd_" + which)
+        if ent is None or ent[0] != key:
+            nbytes = self.lib.nerfb200_packed_bwd_bytes()
+            buf = ent[1] if ent is not None else torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
+            w, keep = _model_weight_struct(model)
+            base = (buf.data_ptr() + 1023) & ~1023
+            L.check(self.lib.nerfb200_pack_weights_bwd(C.byref(w), C.c_void_p(base), L.stream_ptr()), "pack_weights_bwd")
+            del keep
+            ent = (key, buf, base)
+            self._packed["bwd_" + which] = ent
+        return C.c_void_p(ent[2])
+
     def _packed_ptr(self, which):
         self._packed_weights(which)
         return C.c_void_p(self._packed[which][2])

@@ -1,0 +1,175 @@
+"""GPU: the tcgen05 MLP backward (a7) -- activation store of the training forward, the dgrad chain and the
+split-K wgrad GEMMs -- against a torch restatement of the same arithmetic (bf16 operands, wide accumulate)
+evaluated on the activations the forward saved, and against fp32 autograd through the CPU oracle."""
+import pytest
+import torch
+
+from oracle import nerf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from nerf_rep_for_test_b200 import Network, RenderConfig, Renderer, ops
+    from nerf_rep_for_test_b200 import training as T
+    DEV = torch.device("cuda:0")
+
+
+def _renderer(seed=3, gain=30.0, bias=0.2):
+    sd = O.make_state_dict(seed, gain, bias)
+    net = Network(device=DEV)
+    net.load_state_dict(sd)
+    net.to(DEV).eval()
+    return sd, Renderer(net, RenderConfig(perturb=0, enable_ess=False, enable_ert=False), mode="bf16")
+
+
+def _rays(n, S, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    b = O.lego_batch(40, 40)
+    ro, rd = O.get_rays(40, 40, b["pose"][0], b["intrinsics"][0])
+    sel = torch.randperm(ro.shape[0], generator=g)[:n]
+    z = torch.sort(2.0 + 4.0 * torch.rand(n, S, generator=g), -1)[0]
+    return ro[sel].contiguous().to(DEV), rd[sel].contiguous().to(DEV), z.to(DEV)
+
+
+def _mask_bits(store, plane, n_rows, width):
+    """decode the sign-bit planes (train_layout.cuh): True where the gradient is blocked."""
+    n_tiles = (n_rows + 127) // 128
+    words = store.masks.view(torch.int32).view(9, n_tiles * 128, 8)[plane, :n_rows]
+    cols = torch.arange(width, device=DEV)
+    g, c = cols // 32, cols % 32
+    bit = 8 * (c % 4) + 7 - (c // 4)
+    return ((words[:, g] >> bit[None, :]) & 1).bool()
+
+
+@pytest.mark.parametrize("n,S", [(2, 64), (5, 64), (37, 192)])
+def test_train_store_matches_stage_outputs(n, S):
+    """tile images written by bulk stores == the stage outputs the diagnostic forward dumps (rows 0..127),
+    PE planes == torch PE, relu sign bits consistent with the saved activations; ragged last tile."""
+    sd, r = _renderer()
+    ro, rd, z = _rays(n, S)
+    pk = r.packed("coarse", "bf16")
+    raw, store = ops.mlp_forward_train(pk, ro, rd, z)
+    raw2, dump = ops.mlp_forward_stages(pk, ro, rd, z)
+    torch.cuda.synchronize()
+    M = n * S
+    assert torch.equal(raw, raw2)
+    rows = min(M, 128)
+    for i in range(8):
+        got = store.plane("h%d" % i)
+        assert got.shape == (M, 256)
+        assert torch.equal(got[:rows].float(), dump[i, :rows].bfloat16().float()), i
+    assert torch.equal(store.plane("feat")[:rows].float(), dump[8, :rows].bfloat16().float())
+    assert torch.equal(store.plane("hv")[:rows].float(), dump[9, :rows, :128].bfloat16().float())
+    pts = (ro[:, None, :] + rd[:, None, :] * z[..., None]).reshape(-1, 3)
+    pe = O.pos_enc(pts.cpu(), 10).to(DEV)
+    dpe = O.pos_enc(rd.cpu(), 4).to(DEV)[:, None, :].expand(n, S, 27).reshape(-1, 27)
+    # |x| reaches 6 and the top octave multiplies the fp32 argument error by 512: compare at bf16 + that slack
+    assert (store.plane("pe")[:, :63].float() - pe).abs().max() < 4e-2
+    assert (store.plane("pe")[:, 63].float()).abs().max() == 0
+    assert (store.plane("dpe")[:, :27].float() - dpe).abs().max() < 1e-2
+    assert (store.plane("dpe")[:, 27:32].float()).abs().max() == 0
+    for i in range(9):
+        act = store.plane("h%d" % i if i < 8 else "hv")
+        blocked = _mask_bits(store, i, M, act.shape[1])
+        assert not bool((blocked & (act > 0)).any()), i          # a positive activation never has its bit set
+        frac = float((~blocked & (act == 0)).float().mean())     # +0 / underflow only
+        assert frac < 1e-3, (i, frac)
+
+
+def _torch_backward(sd, prefix, store, g_raw):
+    """The arithmetic of mlp_bwd_dgrad.cu / mlp_bwd_wgrad.cu restated with torch (float64 accumulation) on
+    the saved planes: bf16 weights, every dL/d(pre-activation) rounded to bf16 before it is reused."""
+    f64 = torch.float64
+    bf = lambda t: t.to(torch.float32).to(torch.bfloat16).to(f64)
+    W = {k[len(prefix):]: v.to(DEV) for k, v in sd.items() if k.startswith(prefix)}
+    P = {k: store.plane(k).to(f64) for k in store.PLANES}
+    g = g_raw.reshape(-1, 4).to(f64)
+    on = lambda a: (a > 0).to(f64)
+    d_hv = bf(on(P["hv"]) * (g[:, :3].float() @ W["rgb_linear.weight"]).to(f64))
+    d_feat = bf(d_hv @ bf(W["views_linears.0.weight"][:, :256]))
+    d_pre = [None] * 8
+    d_pre[7] = bf(on(P["h7"]) * (d_feat @ bf(W["feature_linear.weight"]) + g[:, 3:4] * W["alpha_linear.weight"].to(f64)))
+    for i in range(7, 0, -1):
+        w = W["pts_linears.%d.weight" % i]
+        w = w[:, 63:] if i == 5 else w
+        d_pre[i - 1] = bf(on(P["h%d" % (i - 1)]) * (d_pre[i] @ bf(w)))
+    G = bf(g)
+    grads = {}
+    for i in range(8):
+        if i == 0:
+            gw = d_pre[0].t() @ P["pe"][:, :63]
+        elif i == 5:
+            gw = torch.cat([d_pre[5].t() @ P["pe"][:, :63], d_pre[5].t() @ P["h4"]], 1)
+        else:
+            gw = d_pre[i].t() @ P["h%d" % (i - 1)]
+        grads["pts_linears.%d.weight" % i] = gw
+        grads["pts_linears.%d.bias" % i] = d_pre[i].sum(0)
+    grads["views_linears.0.weight"] = torch.cat([d_hv.t() @ P["feat"], d_hv.t() @ P["dpe"][:, :27]], 1)
+    grads["views_linears.0.bias"] = d_hv.sum(0)
+    grads["feature_linear.weight"] = d_feat.t() @ P["h7"]
+    grads["feature_linear.bias"] = d_feat.sum(0)
+    grads["alpha_linear.weight"] = G[:, 3:4].t() @ P["h7"]
+    grads["alpha_linear.bias"] = G[:, 3].sum(0, keepdim=True)
+    grads["rgb_linear.weight"] = G[:, :3].t() @ P["hv"]
+    grads["rgb_linear.bias"] = G[:, :3].sum(0)
+    inter = {"d9": torch.cat([d_hv, G], 1), "dfeat": d_feat}
+    inter.update({"dpre%d" % i: d_pre[i] for i in range(8)})
+    return grads, inter
+
+
+@pytest.mark.parametrize("n,S,which", [(2, 64, "coarse"), (5, 64, "coarse"), (37, 192, "fine"), (600, 64, "coarse")])
+def test_mlp_backward_kernels_vs_torch(n, S, which):
+    sd, r = _renderer()
+    ro, rd, z = _rays(n, S, seed=1)
+    raw, store = ops.mlp_forward_train(r.packed(which, "bf16"), ro, rd, z)
+    M = n * S
+    g_raw = torch.randn(M, 4, generator=torch.Generator().manual_seed(7)).to(DEV) * 0.1
+    keep = {}
+    grads = ops.mlp_backward(r.packed_bwd(which), g_raw, store, keep_workspace=keep)
+    torch.cuda.synchronize()
+    ref, inter = _torch_backward(sd, "model." if which == "coarse" else "model_fine.", store, g_raw)
+    # dgrad planes first (they localise a failure)
+    n_tiles = (M + 127) // 128
+    dacts = keep["ws"][: n_tiles * 40 * 16384]
+    planes = {"d9": (36, 4), "dfeat": (32, 4)}
+    planes.update({"dpre%d" % i: (4 * i, 4) for i in range(8)})
+    for name in ["d9", "dfeat"] + ["dpre%d" % i for i in range(7, -1, -1)]:
+        blk, width = planes[name]
+        got = ops.untile(dacts, M, 40, blk, width).double()
+        want = inter[name]
+        if name == "d9":
+            assert float(got[:, 132:].abs().max()) == 0.0
+            got = got[:, :132]
+        scale = float(want.abs().max()) + 1e-30
+        err = float((got - want).abs().max()) / scale
+        bad = float(((got - want).abs() > 2e-2 * scale).double().mean())
+        print("%-6s max err / scale %.3e   frac > 2%%: %.2e" % (name, err, bad))
+        # a bf16 rounding tie or a relu sign flip at |x| ~ 0 moves single elements; the bulk must agree
+        assert bad < 2e-3, (name, err, bad)
+    for name, g in zip(T._NAMES, grads):
+        want = ref[name].reshape(g.shape)
+        rel = float((g.double() - want).norm() / (want.norm() + 1e-30))
+        print("%-26s rel %.3e" % (name, rel))
+        assert rel < 1e-2, (name, rel)
+
+
+def test_mlp_backward_vs_oracle_autograd():
+    """fp32 autograd through the oracle MLP on the same points: bf16 kernels agree to a few 1e-2."""
+    sd, r = _renderer(seed=4)
+    n, S = 6, 64
+    ro, rd, z = _rays(n, S, seed=2)
+    raw, store = ops.mlp_forward_train(r.packed("coarse", "bf16"), ro, rd, z)
+    g_raw = torch.randn(n * S, 4, generator=torch.Generator().manual_seed(3)) * 0.1
+    grads = ops.mlp_backward(r.packed_bwd("coarse"), g_raw.to(DEV), store)
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k.startswith("model.")}
+    pts = (ro[:, None, :] + rd[:, None, :] * z[..., None]).cpu()
+    raw_ref = O.query_network(sdg, "model.", pts, rd.cpu())
+    (raw_ref.reshape(-1, 4) * g_raw).sum().backward()
+    for name, g in zip(T._NAMES, grads):
+        want = sdg["model." + name].grad
+        cos = float((g.cpu() * want).sum() / (g.cpu().norm() * want.norm() + 1e-30))
+        rel = float((g.cpu() - want).norm() / (want.norm() + 1e-30))
+        print("%-26s cos %.5f rel %.4f" % (name, cos, rel))
+        # layer 0 is the end of the chain: eight bf16 roundings of dL/d(pre-activation) behind it (384 rows only)
+        lim = (0.99, 0.15) if name.startswith("pts_linears.0.") else (0.995, 0.1)
+        assert cos > lim[0] and rel < lim[1], (name, cos, rel)

@@ -45,35 +45,6 @@ def _oracle_grads(sd, ro, rd, target, z_all=None):
     return float(loss.detach()), {k: v.grad for k, v in sdg.items()}
 
 
-def test_mlp_backward_formulas_fp32():
-    """The dgrad/wgrad algebra of training.mlp_backward, in fp32 on oracle activations, vs autograd."""
-    torch.manual_seed(0)
-    sd = O.make_state_dict(4)
-    M = 200
-    pts, dirs = torch.randn(M, 3), torch.nn.functional.normalize(torch.randn(M, 3), dim=-1)
-    pe, dpe = O.pos_enc(pts, 10), O.pos_enc(dirs, 4)
-    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k.startswith("model.")}
-    raw, hidden = O.nerf_mlp(sdg, "model.", torch.cat([pe, dpe], -1), return_hidden=True)
-    g_raw = torch.randn(M, 4)
-    (raw * g_raw).sum().backward()
-    with torch.no_grad():
-        h7 = hidden[7]
-        feat = torch.nn.functional.linear(h7, sd["model.feature_linear.weight"], sd["model.feature_linear.bias"])
-        hv = torch.relu(torch.nn.functional.linear(torch.cat([feat, dpe], -1), sd["model.views_linears.0.weight"],
-                                                   sd["model.views_linears.0.bias"]))
-        acts = torch.zeros(10, M, 256)
-        for i in range(8):
-            acts[i] = hidden[i]
-        acts[8] = feat
-        acts[9, :, :128] = hv
-    params = [sd["model." + n] for n in T._NAMES]
-    grads = T.mlp_backward([p.to(DEV) for p in params], acts.to(DEV), pe.to(DEV), dpe.to(DEV), g_raw.to(DEV),
-                           compute_dtype=torch.float32)
-    for name, g in zip(T._NAMES, grads):
-        ref = sdg["model." + name].grad
-        assert torch.allclose(g.cpu(), ref, rtol=2e-4, atol=2e-5 * float(ref.abs().max() + 1e-12)), name
-
-
 def test_training_gradients_vs_oracle_autograd():
     sd, net, r, ro, rd, target = _setup()
     # the fine sample positions our (bf16) forward uses, rebuilt with the same kernels
