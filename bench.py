@@ -362,8 +362,9 @@ def run_ours(args):
                 "rays_per_s_total": world * args.train_rays * 1e3 / it_ms, "scaling": "weak",
                 "allreduce_bytes": 1191688 * 4,
                 "algorithmic_tflops": 3 * args.train_rays * ROWS_PER_RAY * FLOP_PER_ROW / (it_ms * 1e-3) / 1e12,
-                "note": "forward and compositing backward are this repo's kernels; the MLP dgrad/wgrad GEMMs are "
-                        "cuBLAS bf16 (round-1 status, DESIGN.md section 8)"}
+                "note": "every kernel on the path is this repo's: tcgen05 forward with activation store, compositing "
+                        "backward, tcgen05 dgrad chain + split-K wgrad GEMMs (nerfb200_mlp_backward); torch supplies "
+                        "Adam, clip_grad_value_ and the NCCL all-reduce"}
         if cfg5 is not None:
             line["ess_ert"] = cfg5
         if world == 1 and not args.no_cpu_baseline:

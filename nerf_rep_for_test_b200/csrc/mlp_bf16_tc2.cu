@@ -66,7 +66,8 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
                     const float* __restrict__ rays_d, const float* __restrict__ z_vals, long long M, int S,
                     int num_quads, float* __restrict__ raw, float* __restrict__ stage_dump,
                     unsigned long long* __restrict__ tl, unsigned char* __restrict__ acts,
-                    uint32_t* __restrict__ masks, const int* __restrict__ row_ids, const int* __restrict__ n_active) {
+                    uint32_t* __restrict__ masks, const int* __restrict__ row_ids, const int* __restrict__ n_active,
+                    int dbg = 0) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   const uint32_t smem_base = smem_u32(smem_dyn);
   if ((smem_base & 1023u) != 0) __trap();
@@ -83,7 +84,11 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
       mbar_init(bar(BAR_WEMPTY + i), 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bar(BAR_AREADY + s), 256);                // both CTAs' epilogue groups (leader's copy is used)
+      // both CTAs' epilogue groups signal the leader's copy: every thread in inference; in training only the
+      // group's first thread, behind the named barrier that precedes the bulk store (the release fence of
+      // the remote arrive waits for the warp's pending global stores, which is what made the first training
+      // forward 2x slower than inference)
+      mbar_init(bar(BAR_AREADY + s), kSave ? 2 : 256);
       mbar_init(bar(BAR_ACCFULL + s), 1);
       mbar_init(bar(BAR_BFULL + s), 1);
       mbar_init(bar(BAR_BEMPTY + s), 256);
@@ -125,11 +130,10 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
     // rays / PE of a tile are computed one tile ahead so that only the stores sit on the critical path
     long long m = 0, tile_next = 0;
     bool valid = false;
-    // training (kSave): finished operand tiles go to the activation store as tile images (train_layout.cuh)
-    // with one bulk store per tile, issued by the group's first thread behind a 128-thread named barrier
+    // training (kSave): finished operand tiles go to the activation store as tile images (train_layout.cuh);
+    // the group copies them out after the hand-off, behind a 128-thread named barrier (copy_tile_s2g)
     const long long n_tiles = (M + 127) / 128;
     const bool save_leader = kSave && w4 == 0 && lane == 0;
-    const uint32_t a_tile_smem = smem_base + kOffA + (uint32_t)slot * kABytes;
     float d[3] = {0.f, 0.f, 0.f};
     uint32_t pe_pk[32];
     auto prepare_tile = [&](int it) {
@@ -160,15 +164,13 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
     for (int it = 0; it < my_quads; ++it) {
       const long long m_cur = m;
       const bool valid_cur = valid;
-      const bool tile_ok = kSave && tile_next < n_tiles;
+      const bool tile_ok = kSave && tile_next < n_tiles && !(dbg & 1);
+      const bool mask_ok = kSave && tile_next < n_tiles && !(dbg & 2);
       unsigned char* acts_tile = kSave ? acts + (size_t)tile_next * ((size_t)kActBlocks * kBlockBytes) : nullptr;
       const size_t mask_row = (size_t)tile_next * 128 + (size_t)row;
       const size_t mask_plane = (size_t)n_tiles * 128 * kMaskWords;
       float d_cur[3] = {d[0], d[1], d[2]};
-      if (kSave) {   // the previous tile's stores must have finished reading the PE / A buffers
-        if (save_leader) bulk_wait_read0();
-        named_bar_sync(1 + slot, 128);
-      }
+      if (kSave) named_bar_sync(1 + slot, 128);   // every thread has finished copying the previous tile out
       {  // xyz PE tile -> shared memory (swizzled 16-byte chunks), then hand the slot to the MMA issuer
         const uint32_t row_base = pe_base + (uint32_t)row * 128u;
 #pragma unroll
@@ -176,14 +178,9 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
           st_shared_v4(row_base + (uint32_t)((j ^ r7) << 4), pe_pk[4 * j], pe_pk[4 * j + 1], pe_pk[4 * j + 2], pe_pk[4 * j + 3]);
       }
       fence_proxy_async_smem();
-      if (kSave) {
-        named_bar_sync(1 + slot, 128);
-        if (save_leader && tile_ok) {
-          bulk_s2g(acts_tile + (size_t)kActPe * kBlockBytes, pe_base, kBlockBytes);
-          bulk_commit();
-        }
-      }
-      mbar_arrive_remote(b_ready_leader);
+      if (kSave) named_bar_sync(1 + slot, 128);
+      if (!kSave || save_leader) mbar_arrive_remote(b_ready_leader);
+      if (kSave && tile_ok) copy_tile_s2g<kBlockBytes>(acts_tile + (size_t)kActPe * kBlockBytes, smem_dyn + kOffPe + slot * kPeBytes, row);
       float sigma = 0.f;
       for (int stage = 0; stage < I::kN; ++stage) {
         const uint32_t bseq = (uint32_t)it * I::kN + (uint32_t)stage;
@@ -211,20 +208,12 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
             }
           }
         }
-        if (kSave) {   // the previous stage's bulk store has finished reading the A tile we are about to rewrite
-          if (save_leader) bulk_wait_read0();
-          named_bar_sync(1 + slot, 128);
-        }
+        if (kSave) named_bar_sync(1 + slot, 128);   // all copies of the previous stage's tile are done: A may be rewritten
         if (stage < I::kLast) {
           uint32_t mw[8];
           if (!kFused && stage == 7) epi_stage256<1, kSave>(t_acc, bias4, a_row_base, r7, tail + kTailAlphaW, sigma, mw);
           else if (!kFused && stage == 8) epi_stage256<2>(t_acc, bias4, a_row_base, r7, nullptr, sigma);
           else epi_stage256<0, kSave>(t_acc, bias4, a_row_base, r7, nullptr, sigma, mw);
-          if (kSave && tile_ok && stage < 8) {   // relu sign bits of this stage for the dgrad epilogue
-            uint4* dst = reinterpret_cast<uint4*>(masks + (size_t)stage * mask_plane + mask_row * kMaskWords);
-            dst[0] = make_uint4(mw[0], mw[1], mw[2], mw[3]);
-            dst[1] = make_uint4(mw[4], mw[5], mw[6], mw[7]);
-          }
           if (stage == I::kLast - 1) {  // dir PE replaces the xyz PE tile (dead after stage 5) for the views stage
             float f[32];
             pos_enc_row<kLd>(d_cur, f);
@@ -234,16 +223,21 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
           }
           tc_fence_before();
           fence_proxy_async_smem();
-          if (kSave) {   // stage output (= next stage's A tile) -> activation store, 64 KB in one bulk store
-            named_bar_sync(1 + slot, 128);
-            if (save_leader && tile_ok) {
-              bulk_s2g(acts_tile + (size_t)(stage < 8 ? act_h(stage) : kActFeat) * kBlockBytes, a_tile_smem, 4 * kBlockBytes);
-              if (stage == I::kLast - 1) bulk_s2g(acts_tile + (size_t)kActDpe * kBlockBytes, pe_base, kBlockBytes);
-              bulk_commit();
-            }
-          }
-          mbar_arrive_remote(b_ready_leader);
+          if (kSave) named_bar_sync(1 + slot, 128);
+          if (!kSave || save_leader) mbar_arrive_remote(b_ready_leader);
           mbar_arrive(bar(BAR_BEMPTY + bbuf));
+          if (kSave && tile_ok) {   // stage output (= next stage's A tile) -> activation store, while the MMAs read it too
+            copy_tile_s2g<4 * kBlockBytes>(acts_tile + (size_t)(stage < 8 ? act_h(stage) : kActFeat) * kBlockBytes,
+                                           smem_dyn + kOffA + slot * kABytes, row);
+            if (stage == I::kLast - 1)
+              copy_tile_s2g<kBlockBytes>(acts_tile + (size_t)kActDpe * kBlockBytes, smem_dyn + kOffPe + slot * kPeBytes, row);
+          }
+          if (kSave && mask_ok && stage < 8) {   // relu sign bits of this stage for the dgrad epilogue (after the
+            // hand-off: a global store in front of the arrive would sit under its release fence)
+            uint4* dst = reinterpret_cast<uint4*>(masks + (size_t)stage * mask_plane + mask_row * kMaskWords);
+            dst[0] = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+            dst[1] = make_uint4(mw[4], mw[5], mw[6], mw[7]);
+          }
           if (kTimeline && tl && blockIdx.x == 0 && it < 4 && row == 0) tl[((it * 10 + stage) * 2 + slot) * 4 + 3] = clock64();
         } else {
           // stage 9: views_linears.0 (128 wide, relu) -> rgb_linear on CUDA cores (network.py:66-69)
@@ -283,14 +277,10 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
             if (kSave) hvm[cb] = ch[0] | (ch[1] << 8) | (ch[2] << 16) | (ch[3] << 24);
           }
           if (kSave) {
-            if (tile_ok)
+            if (mask_ok)
               *reinterpret_cast<uint4*>(masks + (size_t)8 * mask_plane + mask_row * kMaskWords) = make_uint4(hvm[0], hvm[1], hvm[2], hvm[3]);
-            fence_proxy_async_smem();
             named_bar_sync(1 + slot, 128);
-            if (save_leader && tile_ok) {
-              bulk_s2g(acts_tile + (size_t)kActHv * kBlockBytes, a_tile_smem, 2 * kBlockBytes);
-              bulk_commit();
-            }
+            if (tile_ok) copy_tile_s2g<2 * kBlockBytes>(acts_tile + (size_t)kActHv * kBlockBytes, smem_dyn + kOffA + slot * kABytes, row);
           }
           if (kFused) {   // sigma_raw = accumulator column 128 (+ alpha_b, staged as bias element 128)
             uint32_t v[32];
@@ -424,7 +414,6 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
       }
     }
   }
-  if (kSave) bulk_wait0();   // outstanding activation stores (only the issuing threads hold groups)
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();   // no CTA may exit (or free TMEM) while its peer still multicasts into it
@@ -453,9 +442,10 @@ int launch_mlp_bf16(const void* packed, const float* rays_o, const float* rays_d
   NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<true, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<false, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<false, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   const char* tl_env = getenv("NERFB200_TIMELINE");
   unsigned long long* tl = nullptr;
-  if (tl_env && !stage_dump && !acts) {
+  if (tl_env && !stage_dump) {
     cudaMalloc(&tl, (320 + 400) * 8);
     cudaMemset(tl, 0, (320 + 400) * 8);
   }
@@ -466,7 +456,11 @@ int launch_mlp_bf16(const void* packed, const float* rays_o, const float* rays_d
     int v = atoi(mc);
     if (v > 0 && v < clusters) clusters = v;
   }
-  if (acts)
+  if (acts && tl)
+    mlp_bf16_tc2_kernel<false, true, true, false><<<2 * clusters, kThreads, kSmemBytes, st>>>(
+        (const unsigned char*)packed, rays_o, rays_d, z_vals, M, n_samples, (int)quads, raw, nullptr, tl,
+        (unsigned char*)acts, (uint32_t*)masks, nullptr, nullptr, getenv("NERFB200_DBG") ? atoi(getenv("NERFB200_DBG")) : 0);
+  else if (acts)
     mlp_bf16_tc2_kernel<false, false, true, false><<<2 * clusters, kThreads, kSmemBytes, st>>>(
         (const unsigned char*)packed, rays_o, rays_d, z_vals, M, n_samples, (int)quads, raw, nullptr, nullptr,
         (unsigned char*)acts, (uint32_t*)masks, nullptr, nullptr);

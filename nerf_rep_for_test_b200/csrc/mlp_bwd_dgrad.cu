@@ -115,7 +115,7 @@ mlp_bwd_dgrad_kernel(const unsigned char* __restrict__ packed_bwd, const float* 
       mbar_init(bar(BAR_WEMPTY + i), 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bar(BAR_AREADY + s), 256);
+      mbar_init(bar(BAR_AREADY + s), 2);   // one arrival per epilogue group and CTA (its first thread, after the named barrier)
       mbar_init(bar(BAR_ACCFULL + s), 1);
     }
     fence_mbar_init();
@@ -143,7 +143,7 @@ mlp_bwd_dgrad_kernel(const unsigned char* __restrict__ packed_bwd, const float* 
     const int row = w4 * 32 + lane;
     const int r7 = row & 7;
     unsigned char* a_row_base = smem_dyn + kOffA + (uint32_t)slot * kABytes + (uint32_t)row * 128u;
-    const uint32_t a_tile_smem = smem_base + kOffA + (uint32_t)slot * kABytes;
+    const unsigned char* a_tile = smem_dyn + kOffA + (uint32_t)slot * kABytes;
     const uint32_t t_acc = tmem_base + ((uint32_t)(w4 * 32) << 16) + (uint32_t)slot * 256u;
     const uint32_t b_ready_leader = mapa(bar(BAR_AREADY + slot), 0);
     const uint32_t b_full = bar(BAR_ACCFULL + slot);
@@ -163,9 +163,7 @@ mlp_bwd_dgrad_kernel(const unsigned char* __restrict__ packed_bwd, const float* 
       if (m < M) g = __ldg(reinterpret_cast<const float4*>(g_raw) + m);
       uint4 hvm = make_uint4(0u, 0u, 0u, 0u);
       if (tile_ok) hvm = __ldg(reinterpret_cast<const uint4*>(masks + 8 * mask_plane + mask_row));
-      // the previous tile's last bulk store must have finished reading this A tile
-      if (leader) bulk_wait_read0();
-      named_bar_sync(1 + slot, 128);
+      named_bar_sync(1 + slot, 128);   // every thread has finished copying the previous tile's last stage out
       {  // D9 tile: d_hv (blocks 0,1) | g_raw as bf16 + zero pad (block 2) | zeros (block 3)
         const uint32_t hv_words[4] = {hvm.x, hvm.y, hvm.z, hvm.w};
 #pragma unroll
@@ -196,11 +194,8 @@ mlp_bwd_dgrad_kernel(const unsigned char* __restrict__ packed_bwd, const float* 
       }
       fence_proxy_async_smem();
       named_bar_sync(1 + slot, 128);
-      if (leader && tile_ok) {
-        bulk_s2g(dacts_tile + (size_t)kDactD9 * kBlockBytes, a_tile_smem, 4 * kBlockBytes);
-        bulk_commit();
-      }
-      mbar_arrive_remote(b_ready_leader);
+      if (leader) mbar_arrive_remote(b_ready_leader);
+      if (tile_ok) copy_tile_s2g<4 * kBlockBytes>(dacts_tile + (size_t)kDactD9 * kBlockBytes, a_tile, row);
 
       for (int bs = 0; bs < kBwdStages; ++bs) {
         uint32_t mw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
@@ -213,23 +208,18 @@ mlp_bwd_dgrad_kernel(const unsigned char* __restrict__ packed_bwd, const float* 
         mbar_wait(b_full, full_phase, 0x100 + bs);
         full_phase ^= 1;
         tc_fence_after();
-        if (leader) bulk_wait_read0();
-        named_bar_sync(1 + slot, 128);
+        named_bar_sync(1 + slot, 128);   // the previous stage's tile has been copied out by everyone
         if (bs == 0) depi_stage256<0>(t_acc, a_row_base, r7, mw, 0.f, alpha_w);
         else if (bs == 1) depi_stage256<1>(t_acc, a_row_base, r7, mw, g.w, alpha_w);
         else depi_stage256<2>(t_acc, a_row_base, r7, mw, 0.f, alpha_w);
         tc_fence_before();
         fence_proxy_async_smem();
         named_bar_sync(1 + slot, 128);
-        if (leader && tile_ok) {
-          const int blk = bs == 0 ? kDactFeat : dact_pre(8 - bs);
-          bulk_s2g(dacts_tile + (size_t)blk * kBlockBytes, a_tile_smem, 4 * kBlockBytes);
-          bulk_commit();
-        }
-        if (bs + 1 < kBwdStages) mbar_arrive_remote(b_ready_leader);
+        if (leader && bs + 1 < kBwdStages) mbar_arrive_remote(b_ready_leader);
+        if (tile_ok)   // while the next stage's MMAs read the same tile
+          copy_tile_s2g<4 * kBlockBytes>(dacts_tile + (size_t)(bs == 0 ? kDactFeat : dact_pre(8 - bs)) * kBlockBytes, a_tile, row);
       }
     }
-    if (leader) bulk_wait0();
   } else if (warp == 8) {
     // =========================== producer: this CTA's half of every W^T chunk ===========================
     if (lane == 0) {

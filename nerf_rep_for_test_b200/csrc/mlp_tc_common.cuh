@@ -113,6 +113,25 @@ __device__ __forceinline__ void epi_stage256(uint32_t t_acc, const float4* __res
   }
 }
 
+// Copy a finished operand tile (multiple of 2048 B) from shared memory to its tile image in global memory
+// with the 128 threads of one epilogue group: thread t moves 16 B at t*16 + k*2048, so a warp reads 512
+// contiguous bytes of shared memory (conflict-free) and writes four full 128-byte lines.  Done AFTER the
+// hand-off to the MMA issuer, while this group would otherwise wait for its next accumulator; a TMA bulk
+// store of the same tile kept the tile busy for > 2500 cycles (L2 path shared with the weight stream) and
+// stalled the next epilogue (measured: +2300 cycles per stage).
+template <int BYTES>
+__device__ __forceinline__ void copy_tile_s2g(unsigned char* __restrict__ gdst, const unsigned char* ssrc, int t128) {
+  static_assert(BYTES % 8192 == 0, "tile copy works in batches of 4 x 2048 B");
+#pragma unroll 1
+  for (int k = 0; k < BYTES / 8192; ++k) {
+    uint4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const uint4*>(ssrc + k * 8192 + j * 2048 + t128 * 16);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(gdst + k * 8192 + j * 2048 + t128 * 16) = v[j];
+  }
+}
+
 // write `n8` 16-byte chunks (8 bf16 each) of one 128-byte swizzled row
 template <int NCHUNK>
 __device__ __forceinline__ void store_row_chunks(uint32_t tile_base, int row, const float* f) {
