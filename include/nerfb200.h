@@ -207,6 +207,58 @@ NERFB200_API int nerfb200_ert_depth(const float* weights, const float* z_vals, i
 /* totals[0..1] += counts[0..1] (device side; statistics of the sparse passes) */
 NERFB200_API int nerfb200_accumulate_counts(const int32_t* counts, int64_t* totals, void* stream);
 
+/* ---- a9: KiloNeRF-style path (BASELINE configs[4] ii): occupancy-grid march, 32-wide micro-MLPs, -------
+ * integration with early ray termination.  Reference kernels (never built / run by the reference):
+ * cuda/generate_inputs.cu:11-35, :60-126, cuda/network_eval.cu:24-254, cuda/integrate.cu:9-57, :84-97. */
+typedef struct nerfb200_kilo_camera {
+  int H, W;
+  float cx, cy, fx, fy;
+  float c2w[9];    /* rotation part of the pose, row-major (generate_inputs.cu: c_c2w) */
+  float origin[3]; /* ray origin (generate_inputs.cu: c_origin) */
+} nerfb200_kilo_camera;
+typedef struct nerfb200_kilo_grid {
+  int res[3];      /* occupancy grid int16 [res0][res1][res2]: network id, -1 = empty space */
+  float gmin[3], gmax[3]; /* global domain */
+} nerfb200_kilo_grid;
+typedef struct nerfb200_kilo_march_params {
+  float distance_between_points; /* in units of the UNNORMALISED ray direction */
+  int max_samples_per_ray;       /* compacted queries per ray and pass */
+  int max_depth_index;
+  float min_distance;
+  float transmittance_threshold; /* early ray termination */
+  int white_bkgd;
+  int max_passes;                /* fixed pass count of kilo_render; passes with nothing left to do return at once */
+} nerfb200_kilo_march_params;
+/* floats per micro-MLP (network_eval.cu:48-52): 6212, per layer [bias(out) | W(in-major, out fastest)] */
+NERFB200_API int nerfb200_kilo_param_size(void);
+/* generate_inputs.cu:11-35: dirs [H*W,3], NOT normalised */
+NERFB200_API int nerfb200_kilo_rays_d(const nerfb200_kilo_camera* cam, float* dirs, void* stream);
+/* generate_inputs.cu:60-126: one marching pass.  query_indices [n_rays,S] (= ray*max_depth+depth), assigned
+ * [n_rays,S] (-1 = unfilled; query is then -1 too), active_ray_mask / depth_indices [n_rays] are the
+ * resumable state (read unless is_initial_query, always written). */
+NERFB200_API int nerfb200_kilo_march(const nerfb200_kilo_grid* g, const float* origin, const float* dirs, const int16_t* grid,
+                        int n_rays, float distance_between_points, int max_samples_per_ray, int max_depth_index,
+                        float min_distance, int is_initial_query, int32_t* query_indices, int16_t* assigned_networks,
+                        uint8_t* active_ray_mask, int32_t* depth_indices, void* stream);
+NERFB200_API size_t nerfb200_kilo_workspace_bytes(int n_rays, int max_samples_per_ray, int num_networks);
+/* network_eval.cu:24-254 on every filled slot: groups the queries by network on the device (counting sort,
+ * replaces cuda/reorder.cu), evaluates, and writes (sigmoid rgb, relu sigma) back to the slot; unfilled slots
+ * get 0.  params [num_networks,6212], domain_mins/maxs [num_networks,3]. */
+NERFB200_API int nerfb200_kilo_network_eval(const nerfb200_kilo_camera* cam, const nerfb200_kilo_march_params* mp,
+                               const int32_t* query_indices, const int16_t* assigned_networks, int n_rays,
+                               const float* params, const float* domain_mins, const float* domain_maxs, int num_networks,
+                               void* workspace, size_t workspace_bytes, float* rgb_sigma, void* stream);
+/* integrate.cu:9-57 over the filled slots of one pass (dists [n_rays] = step length per ray) */
+NERFB200_API int nerfb200_kilo_integrate(const float* rgb_sigma, const int16_t* assigned_networks, const float* dists, int n_rays,
+                            int samples_per_ray, float transmittance_threshold, int is_initial_query, float* rgb_map,
+                            float* acc_map, float* transmittance, uint8_t* active_ray_mask, void* stream);
+/* whole frame: rays, max_passes x (march, sort, eval, integrate), background; no host synchronisation.
+ * stats (device int64[2], may be NULL): += evaluated samples, += passes that had work. */
+NERFB200_API int nerfb200_kilo_render(const nerfb200_kilo_camera* cam, const nerfb200_kilo_grid* g, const nerfb200_kilo_march_params* mp,
+                         const int16_t* occupancy_grid, const float* params, const float* domain_mins,
+                         const float* domain_maxs, int num_networks, void* workspace, size_t workspace_bytes,
+                         float* rgb_map, float* acc_map, int64_t* stats, void* stream);
+
 /* ---- whole pass --------------------------------------------------------------------------- */
 typedef struct nerfb200_render_params {
   int n_samples;      /* 64  */

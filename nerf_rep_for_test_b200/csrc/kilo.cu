@@ -1,0 +1,624 @@
+// a9: the KiloNeRF-style path of BASELINE configs[4] -- occupancy-grid ray marching, thousands of
+// 32-wide micro-MLPs, integration with early ray termination -- rebuilt for B200.
+// Reference semantics: cuda/generate_inputs.cu:11-35 (ray directions), :60-126 (march),
+// cuda/network_eval.cu:24-254 (micro-MLP), cuda/integrate.cu:9-57 (integrate + ERT), :84-97 (background).
+// The reference's path never runs; what is kept is its arithmetic and its data contract
+// (query index = ray * max_depth + depth, occupancy grid of network ids, 6212 floats per network packed
+// [bias | W in-major] per layer, multi-pass state (depth_indices, transmittance, active mask)).
+//
+// What is different (B200-first):
+//  * no host round trips: the pass loop is a fixed sequence of launches on one stream; every kernel reads
+//    the device-side counters and returns at once when the previous pass left nothing to do;
+//  * grouping samples by network is a device-side counting sort (shared-memory histograms, one scan block,
+//    one scatter) instead of thrust::sort_by_key + gather/scatter (cuda/reorder.cu:12-48);
+//  * the micro-MLP kernel is persistent over (network, 256-sample chunk) work items, so a few crowded
+//    networks do not serialise on one block (the reference maps block i <-> network i); each thread carries
+//    TWO samples through the network so every weight fetched from shared memory feeds 2 FMAs x 32 outputs;
+//    results are written straight back to the ray-major slot (no scatter pass);
+//  * cos/sin by one accurate sincosf per coordinate + the double-angle recurrence instead of 20 fast-math
+//    intrinsics on arguments up to 512 rad.
+// The arithmetic is CUDA-core fp32 (12 160 FLOP per sample): the path is bounded by FFMA issue, not by HBM
+// (16 B in / 16 B out per sample), and by design evaluates ~10x fewer samples than the dense path.
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace nb {
+namespace kilo {
+
+constexpr int kHidden = 32;
+constexpr int kPosEmb = 63, kDirEmb = 27;
+constexpr int kParamSize = 6212;
+constexpr int kOffL0 = 0;                                   // bias[32] | W[63][32]
+constexpr int kOffL1 = kOffL0 + 32 + 63 * 32;               // bias[32] | W[32][32]
+constexpr int kOffL2 = kOffL1 + 32 + 32 * 32;               // bias[33] | W[32][33]
+constexpr int kOffL3 = kOffL2 + 33 + 32 * 33;               // bias[32] | W[59][32]
+constexpr int kOffL4 = kOffL3 + 32 + 59 * 32;               // bias[3]  | W[32][3]
+static_assert(kOffL4 + 3 + 32 * 3 == kParamSize, "micro-MLP parameter layout");
+
+// shared-memory copy of one network: same order, but the 33- and 3-wide rows are padded to 36 / 4 floats so
+// every weight row is 16-byte aligned and is read as broadcast float4s
+constexpr int kSmL0 = 0;                                    // bias[32] | W[63][32]
+constexpr int kSmL1 = kSmL0 + 32 + 63 * 32;                 // bias[32] | W[32][32]
+constexpr int kSmL2 = kSmL1 + 32 + 32 * 32;                 // bias[36] | W[32][36]
+constexpr int kSmL3 = kSmL2 + 36 + 32 * 36;                 // bias[32] | W[59][32]
+constexpr int kSmL4 = kSmL3 + 32 + 59 * 32;                 // bias[4]  | W[32][4]
+constexpr int kSmFloats = kSmL4 + 4 + 32 * 4;               // 6344
+
+constexpr int kChunk = 256;        // samples per work item of the eval kernel (128 threads x 2)
+constexpr int kEvalThreads = 128;
+
+// counters[] (device int32): 0 = queries of this pass, 1 = work items of this pass, 2 = rays still active
+// after this pass, 3 = rays active before this pass
+enum { C_QUERIES = 0, C_ITEMS = 1, C_ACTIVE_NEXT = 2, C_ACTIVE = 3, C_COUNT = 8 };
+
+__global__ void rays_d_kernel(nerfb200_kilo_camera cam, float* __restrict__ dirs, float* __restrict__ dists, float dbp) {
+  const int n = cam.H * cam.W;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int x = i % cam.W, y = i / cam.W;
+    const float v[3] = {__fdiv_rn((float)x - cam.cx, cam.fx), -__fdiv_rn((float)y - cam.cy, cam.fy), -1.f};
+    float d[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) d[k] = __fadd_rn(d[k], __fmul_rn(v[j], cam.c2w[k * 3 + j]));
+    dirs[i * 3 + 0] = d[0]; dirs[i * 3 + 1] = d[1]; dirs[i * 3 + 2] = d[2];
+    if (dists) dists[i] = __fmul_rn(dbp, sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2]))));
+  }
+}
+
+// generate_inputs.cu:60-126, one thread per ray.  Unfilled slots get assigned = -1 (and query = -1).
+__global__ void march_kernel(nerfb200_kilo_grid g, const float* __restrict__ origin3, const float* __restrict__ dirs,
+                             const int16_t* __restrict__ grid, int32_t* __restrict__ query, int16_t* __restrict__ assigned,
+                             uint8_t* __restrict__ active, int32_t* __restrict__ depth_idx, int n_rays, float dbp, int spp,
+                             int max_depth, float min_distance, int initial, int32_t* __restrict__ counters) {
+  if (!initial && counters && counters[C_ACTIVE] == 0) return;
+  const float o[3] = {origin3[0], origin3[1], origin3[2]};
+  float voxel[3];
+  int stride[3] = {g.res[1] * g.res[2], g.res[2], 1};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) voxel[c] = __fdiv_rn(__fsub_rn(g.gmax[c], g.gmin[c]), (float)g.res[c]);
+  int emitted = 0;
+  for (int ray = blockIdx.x * blockDim.x + threadIdx.x; ray < n_rays; ray += gridDim.x * blockDim.x) {
+    int out = 0;
+    const bool act = initial ? true : active[ray] != 0;
+    int32_t* q = query + (size_t)ray * spp;
+    int16_t* a = assigned + (size_t)ray * spp;
+    if (act) {
+      const float d[3] = {dirs[ray * 3], dirs[ray * 3 + 1], dirs[ray * 3 + 2]};
+      int depth = initial ? 0 : depth_idx[ray];
+      float dist = __fadd_rn(min_distance, __fmul_rn((float)depth, dbp));
+      while (depth < max_depth && out < spp) {
+        int flat = 0;
+        bool inside = true;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float p = __fadd_rn(o[c], __fmul_rn(dist, d[c]));
+          flat += (int)__fdiv_rn(__fsub_rn(p, g.gmin[c]), voxel[c]) * stride[c];
+          inside = inside && (__fadd_rn(g.gmin[c], 0.001f) < p) && (p < __fsub_rn(g.gmax[c], 0.001f));
+        }
+        const int net = inside ? (int)grid[flat] : -1;
+        if (net != -1) {
+          a[out] = (int16_t)net;
+          q[out] = ray * max_depth + depth;
+          ++out;
+        }
+        ++depth;
+        dist = __fadd_rn(dist, dbp);
+      }
+      if (out < spp) active[ray] = 0;
+      else { active[ray] = 1; depth_idx[ray] = depth; }
+    }
+    emitted += out;
+    for (; out < spp; ++out) { a[out] = -1; q[out] = -1; }
+  }
+  if (counters) {   // total queries of this pass (warp-aggregated)
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) emitted += __shfl_xor_sync(0xffffffffu, emitted, s);
+    if ((threadIdx.x & 31) == 0 && emitted) atomicAdd(&counters[C_QUERIES], emitted);
+  }
+}
+
+// ---- counting sort by network id ---------------------------------------------------------------
+__global__ void hist_kernel(const int16_t* __restrict__ assigned, size_t n_slots, int num_networks, int32_t* __restrict__ count,
+                            const int32_t* __restrict__ counters) {
+  if (counters[C_QUERIES] == 0) return;
+  extern __shared__ int32_t sh[];
+  for (int i = threadIdx.x; i < num_networks; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  const size_t per = (n_slots + gridDim.x - 1) / gridDim.x;
+  const size_t lo = (size_t)blockIdx.x * per, hi = lo + per < n_slots ? lo + per : n_slots;
+  for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const int net = assigned[i];
+    if (net >= 0) atomicAdd(&sh[net], 1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < num_networks; i += blockDim.x)
+    if (sh[i]) atomicAdd(&count[i], sh[i]);
+}
+
+// one block: exclusive scans of count[] (sample offsets) and of ceil(count/kChunk) (work-item offsets)
+__global__ void scan_kernel(const int32_t* __restrict__ count, int num_networks, int32_t* __restrict__ start,
+                            int32_t* __restrict__ cursor, int32_t* __restrict__ item_start, int32_t* __restrict__ counters) {
+  if (counters[C_QUERIES] == 0) { if (threadIdx.x == 0) counters[C_ITEMS] = 0; return; }
+  __shared__ int32_t s_tot[2][32];
+  __shared__ int32_t s_carry[2];
+  if (threadIdx.x == 0) s_carry[0] = s_carry[1] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int base = 0; base < num_networks; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int c = i < num_networks ? count[i] : 0;
+    int v0 = c, v1 = (c + kChunk - 1) / kChunk;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+      const int t0 = __shfl_up_sync(0xffffffffu, v0, s), t1 = __shfl_up_sync(0xffffffffu, v1, s);
+      if (lane >= s) { v0 += t0; v1 += t1; }
+    }
+    if (lane == 31) { s_tot[0][warp] = v0; s_tot[1][warp] = v1; }
+    __syncthreads();
+    int w0 = 0, w1 = 0;
+    for (int w = 0; w < warp; ++w) { w0 += s_tot[0][w]; w1 += s_tot[1][w]; }
+    const int c0 = s_carry[0], c1 = s_carry[1];
+    if (i < num_networks) {
+      start[i] = c0 + w0 + v0 - c;
+      cursor[i] = c0 + w0 + v0 - c;
+      item_start[i] = c1 + w1 + v1 - (c + kChunk - 1) / kChunk;
+    }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) {
+      int t0 = 0, t1 = 0;
+      for (int w = 0; w < nw; ++w) { t0 += s_tot[0][w]; t1 += s_tot[1][w]; }
+      s_carry[0] = c0 + t0;
+      s_carry[1] = c1 + t1;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    item_start[num_networks] = s_carry[1];
+    start[num_networks] = s_carry[0];
+    counters[C_ITEMS] = s_carry[1];
+  }
+}
+
+// sorted[start[net] + k] = slot, for every filled slot (order inside a network is irrelevant: results are
+// written back per slot).  Two shared-memory passes per block: local histogram -> one global cursor bump
+// per non-empty bin -> local ranks.
+__global__ void scatter_kernel(const int16_t* __restrict__ assigned, size_t n_slots, int num_networks, int32_t* __restrict__ cursor,
+                               int32_t* __restrict__ sorted, const int32_t* __restrict__ counters) {
+  if (counters[C_QUERIES] == 0) return;
+  extern __shared__ int32_t sh[];
+  int32_t* base = sh;                 // [num_networks]
+  for (int i = threadIdx.x; i < num_networks; i += blockDim.x) base[i] = 0;
+  __syncthreads();
+  const size_t per = (n_slots + gridDim.x - 1) / gridDim.x;
+  const size_t lo = (size_t)blockIdx.x * per, hi = lo + per < n_slots ? lo + per : n_slots;
+  for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const int net = assigned[i];
+    if (net >= 0) atomicAdd(&base[net], 1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < num_networks; i += blockDim.x) {
+    const int c = base[i];
+    base[i] = c ? atomicAdd(&cursor[i], c) : 0;
+  }
+  __syncthreads();
+  for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const int net = assigned[i];
+    if (net >= 0) sorted[atomicAdd(&base[net], 1)] = (int32_t)i;
+  }
+}
+
+// ---- micro-MLP ---------------------------------------------------------------------------------
+// [x, cos(2^0 x) .. cos(2^(L-1) x), sin(2^0 x) .. sin(2^(L-1) x)]  (network_eval.cu:127-140)
+template <int L>
+__device__ __forceinline__ void fourier(float x, float* e) {
+  float s, c;
+  sincosf(x, &s, &c);
+  e[0] = x;
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+    e[1 + l] = c;
+    e[1 + L + l] = s;
+    const float s2 = 2.f * s * c, c2 = 1.f - 2.f * s * s;
+    s = s2; c = c2;
+  }
+}
+
+// acc[s][0..NOUT) += in[s] * W[k][0..NOUT)  for the two samples of this thread; W row read as broadcast float4s
+template <int NOUT>
+__device__ __forceinline__ void fma_row(float (&acc)[2][NOUT], const float* __restrict__ wrow, float in0, float in1) {
+  static_assert(NOUT % 4 == 0, "padded row widths of the micro-MLP");
+  const float4* w4 = reinterpret_cast<const float4*>(wrow);
+#pragma unroll
+  for (int i = 0; i < NOUT / 4; ++i) {
+    const float4 w = w4[i];
+    acc[0][4 * i + 0] = fmaf(in0, w.x, acc[0][4 * i + 0]); acc[1][4 * i + 0] = fmaf(in1, w.x, acc[1][4 * i + 0]);
+    acc[0][4 * i + 1] = fmaf(in0, w.y, acc[0][4 * i + 1]); acc[1][4 * i + 1] = fmaf(in1, w.y, acc[1][4 * i + 1]);
+    acc[0][4 * i + 2] = fmaf(in0, w.z, acc[0][4 * i + 2]); acc[1][4 * i + 2] = fmaf(in1, w.z, acc[1][4 * i + 2]);
+    acc[0][4 * i + 3] = fmaf(in0, w.w, acc[0][4 * i + 3]); acc[1][4 * i + 3] = fmaf(in1, w.w, acc[1][4 * i + 3]);
+  }
+}
+// packed parameter index (network_eval.cu:48-52 order) -> padded shared-memory index
+__device__ __forceinline__ int sm_index(int i) {
+  if (i < kOffL2) return i;                                  // layers 0, 1 unchanged
+  if (i < kOffL3) { const int r = i - kOffL2; return kSmL2 + (r / 33) * 36 + r % 33; }   // bias row + 32 rows of 33
+  if (i < kOffL4) return kSmL3 + (i - kOffL3);
+  const int r = i - kOffL4;
+  return kSmL4 + (r / 3) * 4 + r % 3;
+}
+
+struct EvalCam {
+  float c2w[9];
+  float origin[3];
+  float cx, cy, fx, fy;
+  int W, max_depth;
+  float min_distance, dbp;
+};
+
+// persistent over work items (network, chunk); weights of the item's network staged in shared memory
+__global__ void __launch_bounds__(kEvalThreads, 3)
+eval_kernel(const int32_t* __restrict__ query, const int32_t* __restrict__ sorted, const int32_t* __restrict__ start,
+            const int32_t* __restrict__ item_start, int num_networks, const float* __restrict__ params,
+            const float* __restrict__ domain_mins, const float* __restrict__ domain_maxs, EvalCam cam,
+            float4* __restrict__ rgb_sigma, const int32_t* __restrict__ counters) {
+  __shared__ __align__(16) float w[kSmFloats];
+  __shared__ float dom[6];
+  const int n_items = counters[C_ITEMS];
+  int cached_net = -1;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    // network of this item: last n with item_start[n] <= item
+    int lo = 0, hi = num_networks;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (item_start[mid] <= item) lo = mid; else hi = mid;
+    }
+    const int net = lo;
+    if (net != cached_net) {
+      __syncthreads();
+      const float* src = params + (size_t)net * kParamSize;
+      for (int i = threadIdx.x; i < kSmFloats - kSmL2; i += kEvalThreads) w[kSmL2 + i] = 0.f;   // padding lanes
+      __syncthreads();
+      for (int i = threadIdx.x; i < kParamSize; i += kEvalThreads) w[sm_index(i)] = __ldg(src + i);
+      if (threadIdx.x < 3) dom[threadIdx.x] = domain_mins[net * 3 + threadIdx.x];
+      else if (threadIdx.x < 6) dom[threadIdx.x] = domain_maxs[net * 3 + threadIdx.x - 3];
+      __syncthreads();
+      cached_net = net;
+    }
+    const int first = start[net] + (item - item_start[net]) * kChunk;
+    const int end = start[net + 1];
+    int slot[2];
+    float pe[2][3], dir[2][3];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int idx = first + s * kEvalThreads + threadIdx.x;
+      slot[s] = idx < end ? sorted[idx] : -1;
+      int q = slot[s] >= 0 ? query[slot[s]] : 0;
+      const int depth = q % cam.max_depth;
+      q /= cam.max_depth;
+      const int x = q % cam.W, y = q / cam.W;
+      const float v[3] = {__fdiv_rn((float)x - cam.cx, cam.fx), -__fdiv_rn((float)y - cam.cy, cam.fy), -1.f};
+      float d[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) d[k] = __fadd_rn(d[k], __fmul_rn(v[j], cam.c2w[k * 3 + j]));
+      const float dist = __fadd_rn(cam.min_distance, __fmul_rn((float)depth, cam.dbp));
+      const float norm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float p = __fadd_rn(cam.origin[k], __fmul_rn(dist, d[k]));
+        pe[s][k] = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, __fsub_rn(p, dom[k])), __fsub_rn(dom[3 + k], dom[k])), 1.f);
+        dir[s][k] = __fdiv_rn(d[k], norm);
+      }
+    }
+    // layer 0: 63 -> 32
+    float h0[2][32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) h0[0][i] = h0[1][i] = w[kSmL0 + i];
+#pragma unroll 1
+    for (int j = 0; j < 3; ++j) {
+      float e0[21], e1[21];
+      fourier<10>(pe[0][j], e0);
+      fourier<10>(pe[1][j], e1);
+      const float* wr = w + kSmL0 + 32 + j * 21 * 32;
+#pragma unroll
+      for (int e = 0; e < 21; ++e) fma_row<32>(h0, wr + e * 32, e0[e], e1[e]);
+    }
+    // layer 1: 32 -> 32 (relu on the input)
+    float h1[2][32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) h1[0][i] = h1[1][i] = w[kSmL1 + i];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) fma_row<32>(h1, w + kSmL1 + 32 + k * 32, fmaxf(h0[0][k], 0.f), fmaxf(h0[1][k], 0.f));
+    // layer 2: 32 -> 33 (output 0 = density, 1..32 = feature, no activation on the feature)
+    float h2[2][36];
+#pragma unroll
+    for (int i = 0; i < 36; ++i) h2[0][i] = h2[1][i] = w[kSmL2 + i];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) fma_row<36>(h2, w + kSmL2 + 36 + k * 36, fmaxf(h1[0][k], 0.f), fmaxf(h1[1][k], 0.f));
+    // layer 3: feature(32) | dir embedding(27) -> 32
+    float (&h3)[2][32] = h0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) h3[0][i] = h3[1][i] = w[kSmL3 + i];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) fma_row<32>(h3, w + kSmL3 + 32 + k * 32, h2[0][k + 1], h2[1][k + 1]);
+#pragma unroll 1
+    for (int j = 0; j < 3; ++j) {
+      float e0[9], e1[9];
+      fourier<4>(dir[0][j], e0);
+      fourier<4>(dir[1][j], e1);
+      const float* wr = w + kSmL3 + 32 + (32 + j * 9) * 32;
+#pragma unroll
+      for (int e = 0; e < 9; ++e) fma_row<32>(h3, wr + e * 32, e0[e], e1[e]);
+    }
+    // layer 4: 32 -> 3, sigmoid; density relu
+    float rgb[2][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) rgb[0][i] = rgb[1][i] = w[kSmL4 + i];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) fma_row<4>(rgb, w + kSmL4 + 4 + k * 4, fmaxf(h3[0][k], 0.f), fmaxf(h3[1][k], 0.f));
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+      if (slot[s] >= 0)
+        rgb_sigma[slot[s]] = make_float4(1.f / (1.f + expf(-rgb[s][0])), 1.f / (1.f + expf(-rgb[s][1])),
+                                         1.f / (1.f + expf(-rgb[s][2])), fmaxf(h2[s][0], 0.f));
+  }
+}
+
+// integrate.cu:9-57, one thread per ray over the filled slots of this pass
+__global__ void integrate_kernel(const float4* __restrict__ rgb_sigma, const int16_t* __restrict__ assigned,
+                                 const float* __restrict__ dists, float* __restrict__ rgb_map, float* __restrict__ acc_map,
+                                 float* __restrict__ T, uint8_t* __restrict__ active, int n_rays, int spp, float thr, int initial,
+                                 int32_t* __restrict__ counters) {
+  if (!initial && counters && counters[C_ACTIVE] == 0) return;
+  int still = 0;
+  for (int ray = blockIdx.x * blockDim.x + threadIdx.x; ray < n_rays; ray += gridDim.x * blockDim.x) {
+    float t = initial ? 1.f : T[ray];
+    const bool act = t > thr;
+    float r = 0.f, g = 0.f, b = 0.f, acc = 0.f;
+    if (act) {
+      if (!initial) { r = rgb_map[ray * 3]; g = rgb_map[ray * 3 + 1]; b = rgb_map[ray * 3 + 2]; acc = acc_map[ray]; }
+      const float dist = dists[ray];
+      const size_t s0 = (size_t)ray * spp;
+      for (int s = 0; s < spp && assigned[s0 + s] >= 0; ++s) {
+        const float4 v = rgb_sigma[s0 + s];
+        const float alpha = __fsub_rn(1.f, expf(-__fmul_rn(v.w, dist)));
+        const float wgt = __fmul_rn(alpha, t);
+        t = __fmul_rn(t, __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f));
+        r = __fadd_rn(r, __fmul_rn(v.x, wgt));
+        g = __fadd_rn(g, __fmul_rn(v.y, wgt));
+        b = __fadd_rn(b, __fmul_rn(v.z, wgt));
+        acc = __fadd_rn(acc, wgt);
+      }
+      T[ray] = t;
+      if (t <= thr) active[ray] = 0;
+    } else if (initial) {
+      T[ray] = t;
+    }
+    if (act || initial) {
+      rgb_map[ray * 3] = r; rgb_map[ray * 3 + 1] = g; rgb_map[ray * 3 + 2] = b;
+      acc_map[ray] = acc;
+    }
+    still += active[ray] ? 1 : 0;
+  }
+  if (counters) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) still += __shfl_xor_sync(0xffffffffu, still, s);
+    if ((threadIdx.x & 31) == 0 && still) atomicAdd(&counters[C_ACTIVE_NEXT], still);
+  }
+}
+
+// integrate.cu:84-97
+__global__ void background_kernel(float* __restrict__ rgb_map, const float* __restrict__ acc_map, int n, float br, float bg, float bb) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float t = __fsub_rn(1.f, acc_map[i]);
+    rgb_map[i * 3] = __fadd_rn(rgb_map[i * 3], __fmul_rn(br, t));
+    rgb_map[i * 3 + 1] = __fadd_rn(rgb_map[i * 3 + 1], __fmul_rn(bg, t));
+    rgb_map[i * 3 + 2] = __fadd_rn(rgb_map[i * 3 + 2], __fmul_rn(bb, t));
+  }
+}
+
+// between passes: stats += queries; ACTIVE <- ACTIVE_NEXT; clear per-pass counters and the histogram
+__global__ void next_pass_kernel(int32_t* __restrict__ counters, int32_t* __restrict__ count, int num_networks, int64_t* __restrict__ stats) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < num_networks) count[i] = 0;
+  if (i == 0) {
+    if (stats) { stats[0] += counters[C_QUERIES]; stats[1] += counters[C_QUERIES] > 0 ? 1 : 0; }
+    counters[C_ACTIVE] = counters[C_ACTIVE_NEXT];
+    counters[C_ACTIVE_NEXT] = 0;
+    counters[C_QUERIES] = 0;
+    counters[C_ITEMS] = 0;
+  }
+}
+
+struct Work {
+  float* dirs; float* dists; float* T; float4* rgb_sigma; int32_t* query; int32_t* sorted; int32_t* depth_idx;
+  int32_t* count; int32_t* start; int32_t* cursor; int32_t* item_start; int32_t* counters; int16_t* assigned; uint8_t* active;
+  float* origin; size_t bytes;
+};
+static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+static Work carve(void* base, int n_rays, int spp, int num_networks) {
+  Work w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char* p = base ? (char*)base + off : nullptr; off += al(bytes); return p; };
+  const size_t slots = (size_t)n_rays * spp;
+  w.dirs = (float*)take((size_t)n_rays * 12);
+  w.dists = (float*)take((size_t)n_rays * 4);
+  w.T = (float*)take((size_t)n_rays * 4);
+  w.rgb_sigma = (float4*)take(slots * 16);
+  w.query = (int32_t*)take(slots * 4);
+  w.sorted = (int32_t*)take(slots * 4);
+  w.depth_idx = (int32_t*)take((size_t)n_rays * 4);
+  w.count = (int32_t*)take((size_t)(num_networks + 1) * 4);
+  w.start = (int32_t*)take((size_t)(num_networks + 1) * 4);
+  w.cursor = (int32_t*)take((size_t)(num_networks + 1) * 4);
+  w.item_start = (int32_t*)take((size_t)(num_networks + 1) * 4);
+  w.counters = (int32_t*)take(C_COUNT * 4);
+  w.assigned = (int16_t*)take(slots * 2);
+  w.active = (uint8_t*)take((size_t)n_rays);
+  w.origin = (float*)take(16);
+  w.bytes = off;
+  return w;
+}
+
+static int check_grid(const nerfb200_kilo_grid* g, const char* who) {
+  NB_CHECK_ARG(g, "%s: null grid description", who);
+  for (int c = 0; c < 3; ++c) NB_CHECK_ARG(g->res[c] >= 1 && g->res[c] <= 1024 && g->gmax[c] > g->gmin[c], "%s: bad grid axis %d", who, c);
+  return 0;
+}
+
+}  // namespace kilo
+}  // namespace nb
+
+using namespace nb;
+using namespace nb::kilo;
+
+static int grid_for(long long n, int threads) {
+  long long b = (n + threads - 1) / threads;
+  return (int)(b < 1 ? 1 : (b > 148 * 16 ? 148 * 16 : b));
+}
+
+extern "C" int nerfb200_kilo_param_size(void) { return kParamSize; }
+
+extern "C" int nerfb200_kilo_rays_d(const nerfb200_kilo_camera* cam, float* dirs, void* stream) {
+  NB_CHECK_ARG(cam && dirs && cam->H > 0 && cam->W > 0, "kilo_rays_d: bad arguments");
+  rays_d_kernel<<<grid_for((long long)cam->H * cam->W, 256), 256, 0, (cudaStream_t)stream>>>(*cam, dirs, nullptr, 0.f);
+  NB_LAUNCH_OK("kilo::rays_d_kernel");
+  return 0;
+}
+
+extern "C" int nerfb200_kilo_march(const nerfb200_kilo_grid* g, const float* origin, const float* dirs, const int16_t* grid,
+                                   int n_rays, float distance_between_points, int max_samples_per_ray, int max_depth_index,
+                                   float min_distance, int is_initial_query, int32_t* query_indices, int16_t* assigned_networks,
+                                   uint8_t* active_ray_mask, int32_t* depth_indices, void* stream) {
+  if (check_grid(g, "kilo_march")) return 1;
+  NB_CHECK_ARG(n_rays >= 0 && max_samples_per_ray >= 1 && max_depth_index >= 1, "kilo_march: bad sizes");
+  NB_CHECK_ARG((long long)n_rays * max_depth_index < (1LL << 31), "kilo_march: n_rays * max_depth_index overflows the int32 query index");
+  if (n_rays == 0) return 0;
+  NB_CHECK_ARG(origin && dirs && grid && query_indices && assigned_networks && active_ray_mask && depth_indices, "kilo_march: null pointer");
+  march_kernel<<<grid_for(n_rays, 128), 128, 0, (cudaStream_t)stream>>>(*g, origin, dirs, grid, query_indices, assigned_networks,
+                                                                       active_ray_mask, depth_indices, n_rays, distance_between_points,
+                                                                       max_samples_per_ray, max_depth_index, min_distance,
+                                                                       is_initial_query, nullptr);
+  NB_LAUNCH_OK("kilo::march_kernel");
+  return 0;
+}
+
+extern "C" int nerfb200_kilo_integrate(const float* rgb_sigma, const int16_t* assigned_networks, const float* dists, int n_rays,
+                                       int samples_per_ray, float transmittance_threshold, int is_initial_query, float* rgb_map,
+                                       float* acc_map, float* transmittance, uint8_t* active_ray_mask, void* stream) {
+  NB_CHECK_ARG(n_rays >= 0 && samples_per_ray >= 1, "kilo_integrate: bad sizes");
+  if (n_rays == 0) return 0;
+  NB_CHECK_ARG(rgb_sigma && assigned_networks && dists && rgb_map && acc_map && transmittance && active_ray_mask, "kilo_integrate: null pointer");
+  NB_CHECK_ARG(((uintptr_t)rgb_sigma & 15) == 0, "kilo_integrate: rgb_sigma must be 16-byte aligned");
+  integrate_kernel<<<grid_for(n_rays, 128), 128, 0, (cudaStream_t)stream>>>((const float4*)rgb_sigma, assigned_networks, dists, rgb_map,
+                                                                           acc_map, transmittance, active_ray_mask, n_rays,
+                                                                           samples_per_ray, transmittance_threshold, is_initial_query, nullptr);
+  NB_LAUNCH_OK("kilo::integrate_kernel");
+  return 0;
+}
+
+extern "C" size_t nerfb200_kilo_workspace_bytes(int n_rays, int max_samples_per_ray, int num_networks) {
+  if (n_rays <= 0 || max_samples_per_ray <= 0 || num_networks <= 0) return 0;
+  return carve(nullptr, n_rays, max_samples_per_ray, num_networks).bytes;
+}
+
+// sort + evaluate the queries sitting in (query, assigned): shared by the kernel-level entry and the renderer
+static int eval_pass(const Work& w, const nerfb200_kilo_camera* cam, const nerfb200_kilo_march_params* mp, int n_rays,
+                     int num_networks, const float* params, const float* domain_mins, const float* domain_maxs, cudaStream_t st) {
+  const size_t slots = (size_t)n_rays * mp->max_samples_per_ray;
+  const int sort_blocks = (int)(slots / 8192 < 1 ? 1 : (slots / 8192 > 592 ? 592 : slots / 8192));
+  const size_t sh = (size_t)num_networks * 4;
+  hist_kernel<<<sort_blocks, 256, sh, st>>>(w.assigned, slots, num_networks, w.count, w.counters);
+  NB_LAUNCH_OK("kilo::hist_kernel");
+  scan_kernel<<<1, 1024, 0, st>>>(w.count, num_networks, w.start, w.cursor, w.item_start, w.counters);
+  NB_LAUNCH_OK("kilo::scan_kernel");
+  scatter_kernel<<<sort_blocks, 256, sh, st>>>(w.assigned, slots, num_networks, w.cursor, w.sorted, w.counters);
+  NB_LAUNCH_OK("kilo::scatter_kernel");
+  EvalCam ec;
+  for (int i = 0; i < 9; ++i) ec.c2w[i] = cam->c2w[i];
+  for (int i = 0; i < 3; ++i) ec.origin[i] = cam->origin[i];
+  ec.cx = cam->cx; ec.cy = cam->cy; ec.fx = cam->fx; ec.fy = cam->fy;
+  ec.W = cam->W; ec.max_depth = mp->max_depth_index; ec.min_distance = mp->min_distance; ec.dbp = mp->distance_between_points;
+  int dev = 0, sms = 0;
+  NB_CUDA(cudaGetDevice(&dev));
+  NB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  eval_kernel<<<sms * 3, kEvalThreads, 0, st>>>(w.query, w.sorted, w.start, w.item_start, num_networks, params, domain_mins, domain_maxs, ec,
+                                                w.rgb_sigma, w.counters);
+  NB_LAUNCH_OK("kilo::eval_kernel");
+  return 0;
+}
+
+static int check_common(const nerfb200_kilo_camera* cam, const nerfb200_kilo_grid* g, const nerfb200_kilo_march_params* mp,
+                        int num_networks, const char* who) {
+  NB_CHECK_ARG(cam && mp, "%s: null parameter block", who);
+  if (check_grid(g, who)) return 1;
+  NB_CHECK_ARG(cam->H > 0 && cam->W > 0 && cam->fx != 0.f && cam->fy != 0.f, "%s: bad camera", who);
+  NB_CHECK_ARG(mp->max_samples_per_ray >= 1 && mp->max_depth_index >= 1 && mp->distance_between_points > 0.f, "%s: bad march parameters", who);
+  NB_CHECK_ARG(num_networks >= 1 && num_networks <= 8192, "%s: num_networks=%d out of range [1, 8192] (shared-memory histograms)", who, num_networks);
+  NB_CHECK_ARG((long long)cam->H * cam->W * mp->max_depth_index < (1LL << 31), "%s: H*W*max_depth_index overflows the int32 query index", who);
+  NB_CHECK_ARG((long long)cam->H * cam->W * mp->max_samples_per_ray < (1LL << 31), "%s: H*W*max_samples_per_ray overflows int32 slots", who);
+  return 0;
+}
+
+extern "C" int nerfb200_kilo_network_eval(const nerfb200_kilo_camera* cam, const nerfb200_kilo_march_params* mp,
+                                          const int32_t* query_indices, const int16_t* assigned_networks, int n_rays,
+                                          const float* params, const float* domain_mins, const float* domain_maxs, int num_networks,
+                                          void* workspace, size_t workspace_bytes, float* rgb_sigma, void* stream) {
+  nerfb200_kilo_grid dummy = {{1, 1, 1}, {0.f, 0.f, 0.f}, {1.f, 1.f, 1.f}};
+  if (check_common(cam, &dummy, mp, num_networks, "kilo_network_eval")) return 1;
+  if (n_rays <= 0) return 0;
+  NB_CHECK_ARG(query_indices && assigned_networks && params && domain_mins && domain_maxs && workspace && rgb_sigma, "kilo_network_eval: null pointer");
+  NB_CHECK_ARG(((uintptr_t)params & 15) == 0 && ((uintptr_t)rgb_sigma & 15) == 0 && ((uintptr_t)workspace & 255) == 0, "kilo_network_eval: misaligned buffer");
+  Work w = carve(workspace, n_rays, mp->max_samples_per_ray, num_networks);
+  NB_CHECK_ARG(workspace_bytes >= w.bytes, "kilo_network_eval: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t slots = (size_t)n_rays * mp->max_samples_per_ray;
+  w.query = const_cast<int32_t*>(query_indices);
+  w.assigned = const_cast<int16_t*>(assigned_networks);
+  w.rgb_sigma = reinterpret_cast<float4*>(rgb_sigma);
+  NB_CUDA(cudaMemsetAsync(w.count, 0, (size_t)(num_networks + 1) * 4, st));
+  NB_CUDA(cudaMemsetAsync(w.counters, 0, C_COUNT * 4, st));
+  NB_CUDA(cudaMemsetAsync(rgb_sigma, 0, slots * 16, st));
+  const int32_t one = 1;   // "there may be queries": the histogram decides
+  NB_CUDA(cudaMemcpyAsync(w.counters + C_QUERIES, &one, 4, cudaMemcpyHostToDevice, st));
+  return eval_pass(w, cam, mp, n_rays, num_networks, params, domain_mins, domain_maxs, st);
+}
+
+extern "C" int nerfb200_kilo_render(const nerfb200_kilo_camera* cam, const nerfb200_kilo_grid* g, const nerfb200_kilo_march_params* mp,
+                                    const int16_t* occupancy_grid, const float* params, const float* domain_mins,
+                                    const float* domain_maxs, int num_networks, void* workspace, size_t workspace_bytes,
+                                    float* rgb_map, float* acc_map, int64_t* stats, void* stream) {
+  if (check_common(cam, g, mp, num_networks, "kilo_render")) return 1;
+  NB_CHECK_ARG(mp->max_passes >= 1, "kilo_render: max_passes must be >= 1");
+  NB_CHECK_ARG(occupancy_grid && params && domain_mins && domain_maxs && workspace && rgb_map && acc_map, "kilo_render: null pointer");
+  NB_CHECK_ARG(((uintptr_t)params & 15) == 0 && ((uintptr_t)workspace & 255) == 0, "kilo_render: misaligned buffer");
+  const int n_rays = cam->H * cam->W, spp = mp->max_samples_per_ray;
+  Work w = carve(workspace, n_rays, spp, num_networks);
+  NB_CHECK_ARG(workspace_bytes >= w.bytes, "kilo_render: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  NB_CUDA(cudaMemsetAsync(w.count, 0, (size_t)(num_networks + 1) * 4, st));
+  NB_CUDA(cudaMemsetAsync(w.counters, 0, C_COUNT * 4, st));
+  NB_CUDA(cudaMemcpyAsync(w.origin, cam->origin, 12, cudaMemcpyHostToDevice, st));
+  rays_d_kernel<<<grid_for(n_rays, 256), 256, 0, st>>>(*cam, w.dirs, w.dists, mp->distance_between_points);
+  NB_LAUNCH_OK("kilo::rays_d_kernel");
+  for (int p = 0; p < mp->max_passes; ++p) {
+    march_kernel<<<grid_for(n_rays, 128), 128, 0, st>>>(*g, w.origin, w.dirs, occupancy_grid, w.query, w.assigned, w.active, w.depth_idx,
+                                                        n_rays, mp->distance_between_points, spp, mp->max_depth_index, mp->min_distance,
+                                                        p == 0, w.counters);
+    NB_LAUNCH_OK("kilo::march_kernel");
+    int rc = eval_pass(w, cam, mp, n_rays, num_networks, params, domain_mins, domain_maxs, st);
+    if (rc) return rc;
+    integrate_kernel<<<grid_for(n_rays, 128), 128, 0, st>>>(w.rgb_sigma, w.assigned, w.dists, rgb_map, acc_map, w.T, w.active, n_rays, spp,
+                                                            mp->transmittance_threshold, p == 0, w.counters);
+    NB_LAUNCH_OK("kilo::integrate_kernel");
+    next_pass_kernel<<<(num_networks + 255) / 256, 256, 0, st>>>(w.counters, w.count, num_networks, stats);
+    NB_LAUNCH_OK("kilo::next_pass_kernel");
+  }
+  if (mp->white_bkgd) {
+    background_kernel<<<grid_for(n_rays, 256), 256, 0, st>>>(rgb_map, acc_map, n_rays, 1.f, 1.f, 1.f);
+    NB_LAUNCH_OK("kilo::background_kernel");
+  }
+  return 0;
+}

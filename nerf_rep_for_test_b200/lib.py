@@ -40,6 +40,21 @@ class RenderParams(C.Structure):
                 ("eval_counts", _vp)]
 
 
+class KiloCamera(C.Structure):
+    _fields_ = [("H", C.c_int), ("W", C.c_int), ("cx", C.c_float), ("cy", C.c_float), ("fx", C.c_float),
+                ("fy", C.c_float), ("c2w", C.c_float * 9), ("origin", C.c_float * 3)]
+
+
+class KiloGrid(C.Structure):
+    _fields_ = [("res", C.c_int * 3), ("gmin", C.c_float * 3), ("gmax", C.c_float * 3)]
+
+
+class KiloMarchParams(C.Structure):
+    _fields_ = [("distance_between_points", C.c_float), ("max_samples_per_ray", C.c_int),
+                ("max_depth_index", C.c_int), ("min_distance", C.c_float), ("transmittance_threshold", C.c_float),
+                ("white_bkgd", C.c_int), ("max_passes", C.c_int)]
+
+
 class Maps(C.Structure):
     _fields_ = [("rgb", _vp), ("disp", _vp), ("acc", _vp), ("depth", _vp)]
 
@@ -77,6 +92,16 @@ SIGNATURES = {
     "nerfb200_mlp_forward_sparse": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "nerfb200_ert_depth": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_float, _vp, _vp]),
     "nerfb200_accumulate_counts": (C.c_int, [_vp, _vp, _vp]),
+    "nerfb200_kilo_param_size": (C.c_int, []),
+    "nerfb200_kilo_rays_d": (C.c_int, [C.POINTER(KiloCamera), _vp, _vp]),
+    "nerfb200_kilo_march": (C.c_int, [C.POINTER(KiloGrid), _vp, _vp, _vp, C.c_int, C.c_float, C.c_int, C.c_int, C.c_float,
+                                      C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "nerfb200_kilo_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "nerfb200_kilo_network_eval": (C.c_int, [C.POINTER(KiloCamera), C.POINTER(KiloMarchParams), _vp, _vp, C.c_int, _vp,
+                                             _vp, _vp, C.c_int, _vp, C.c_size_t, _vp, _vp]),
+    "nerfb200_kilo_integrate": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_float, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "nerfb200_kilo_render": (C.c_int, [C.POINTER(KiloCamera), C.POINTER(KiloGrid), C.POINTER(KiloMarchParams), _vp, _vp, _vp,
+                                       _vp, C.c_int, _vp, C.c_size_t, _vp, _vp, _vp, _vp]),
     "nerfb200_render_workspace_bytes": (C.c_size_t, [C.c_int, C.POINTER(RenderParams)]),
     "nerfb200_render_rays": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp, C.POINTER(RenderParams), _vp,
                                        C.c_size_t, C.POINTER(Maps), C.POINTER(Maps), _vp]),
