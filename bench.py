@@ -308,6 +308,41 @@ def run_ours(args):
                 "mlp_rows_per_ray_skip": (ev[0] + ev[1]) / (3.0 * H * W),
                 "note": "throughput comparison only; the reference has no runnable skipping path (SURVEY 8a8/a9)"}
 
+    # ---- BASELINE.json configs[4] part ii: the KiloNeRF-style path (a9): 16^3 micro-MLPs (32 wide, random
+    # weights), 128^3 occupancy grid of network ids, fixed-step march + early ray termination; same camera.
+    kilo_cfg = None
+    if args.config5 and rank == 0:
+        from oracle import kilo_oracle as KO
+        from nerf_rep_for_test_b200 import kilo
+        sc = KO.make_scene(seed=0, net_res=16, grid_res=128, blob_radius=1.0)
+        dbp, max_depth, min_d, spp = 4.0 / 384, 384, 2.0, 16
+        kr = kilo.KiloRenderer(sc["grid"], sc["params"], sc["domain_mins"], sc["domain_maxs"], sc["gmin"], sc["gmax"], dbp,
+                               max_depth, min_d, max_samples_per_ray=spp, device=dev)
+        for _ in range(2):
+            kr.render(dev_batches[0])
+        kr.stats.zero_()
+        l0 = L.launch_count()
+        kms = timed(kr.render, dev_batches[:3]) / 3
+        samples = float(kr.stats[0]) / 3
+        # CPU: the numpy oracle of the same kernels on a 64x64 view of the same scene
+        b64 = O.lego_batch(64, 64)
+        pose64, K64 = b64["pose"][0].numpy(), b64["intrinsics"][0].numpy()
+        t0 = time.perf_counter()
+        _, _, ev64 = KO.render(64, 64, float(K64[0, 2]), float(K64[1, 2]), float(K64[0, 0]), float(K64[1, 1]), pose64[:3, :3],
+                               pose64[:3, 3], sc["grid"], sc["params"], sc["domain_mins"], sc["domain_maxs"], sc["gmin"],
+                               sc["gmax"], dbp, max_depth, min_d, spp, 0.01)
+        cpu_s = time.perf_counter() - t0
+        kilo_cfg = {"workload": "800x800 view, 16^3 micro-MLPs (63->32->32->33->59->32->3, random weights), 128^3 occupancy "
+                                "grid (sphere r=1.0 in [-1.5,1.5]^3), 384 march steps, %d samples per ray and pass, ERT 0.01" % spp,
+                    "ms_per_frame": kms, "rays_per_s": H * W / (kms * 1e-3), "samples_per_ray": samples / (H * W),
+                    "samples_per_s": samples / (kms * 1e-3),
+                    "fp32_tflops": samples * 12160 / (kms * 1e-3) / 1e12,
+                    "fp32_peak_tflops_nominal": 148 * 128 * 2 * 1.965e9 / 1e12,
+                    "launches_per_frame": (L.launch_count() - l0) / 3.0,
+                    "cpu_oracle": {"rays_per_s": 64 * 64 / cpu_s, "samples_per_s": ev64 / cpu_s, "sample": "64x64 view, numpy, 1 thread"},
+                    "note": "throughput of the a9 path; the reference's kilonerf_cuda extension is never built or run "
+                            "(SURVEY 2.2), so there is no reference number for it"}
+
     t = torch.tensor([ms_total, e2e_ms, train_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -367,6 +402,8 @@ def run_ours(args):
                         "Adam, clip_grad_value_ and the NCCL all-reduce"}
         if cfg5 is not None:
             line["ess_ert"] = cfg5
+        if kilo_cfg is not None:
+            line["kilo"] = kilo_cfg
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_rays_per_s()
         print(json.dumps(line))
