@@ -15,8 +15,11 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libnerfb200.so")
+# experiments: NERFB200_VARIANT=<tag> NERFB200_NVCC_FLAGS="-D..." builds libnerfb200_<tag>.so next to the product
+# library (load it with NERFB200_LIB=<path>); the default build is the product
+_VAR = os.environ.get("NERFB200_VARIANT", "")
+OBJ = os.path.join(HERE, "build" + ("_" + _VAR if _VAR else ""))
+LIB = os.path.join(HERE, "libnerfb200%s.so" % ("_" + _VAR if _VAR else ""))
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
          "-Xptxas", "-v", "--expt-relaxed-constexpr"]
@@ -45,7 +48,7 @@ def _compile(src, force, log):
     if (not force and os.path.exists(obj)
             and os.path.getmtime(obj) > max(os.path.getmtime(spath), _newest_header())):
         return obj, ""
-    cmd = [nvcc()] + ARCH + FLAGS + ["-c", spath, "-o", obj]
+    cmd = [nvcc()] + ARCH + FLAGS + os.environ.get("NERFB200_NVCC_FLAGS", "").split() + ["-c", spath, "-o", obj]
     p = subprocess.run(cmd, capture_output=True, text=True)
     if p.returncode != 0:
         raise RuntimeError("nvcc failed on %s:\n%s\n%s" % (src, p.stdout, p.stderr))

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libnerfb200.so")
+LIB_PATH = os.environ.get("NERFB200_LIB") or os.path.join(HERE, "libnerfb200.so")   # env override: A/B experiments only
 
 MODE_FP32, MODE_BF16 = 0, 1
 COMPOSITE_PLAIN, COMPOSITE_ERT, COMPOSITE_ERT_COMPAT = 0, 1, 2
