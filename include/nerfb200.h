@@ -122,9 +122,9 @@ NERFB200_API int nerfb200_mlp_forward(const void* packed, int mode, const float*
 NERFB200_API size_t nerfb200_train_acts_bytes(long long n_rows);
 NERFB200_API size_t nerfb200_train_masks_bytes(long long n_rows);
 NERFB200_API size_t nerfb200_mlp_backward_workspace_bytes(long long n_rows);
-/* BF16 mode forward that additionally keeps, for the backward pass, the bf16 inputs/outputs of the ten
- * stages (PE, dir-PE, relu(h0..h7), feature, relu(views)) in `acts` (128-byte aligned) and the relu sign
- * bits in `masks` (16-byte aligned). */
+/* BF16 mode forward (fused tail, like inference) that additionally keeps, for the backward pass, the bf16
+ * inputs/outputs of its nine stages (PE, dir-PE, relu(h0..h7), relu(views)) in `acts` (128-byte aligned) and the
+ * relu sign bits in `masks` (16-byte aligned). */
 NERFB200_API int nerfb200_mlp_forward_train(const void* packed, int mode, const float* rays_o,
                                const float* rays_d, const float* z_vals, int n_rays, int n_samples,
                                float* raw, void* acts, void* masks, void* stream);
@@ -133,12 +133,14 @@ NERFB200_API size_t nerfb200_packed_bwd_bytes(void);
 NERFB200_API int nerfb200_pack_weights_bwd(const nerfb200_mlp_weights* w, void* packed_bwd, void* stream);
 /* Gradients of the 24 tensors of one model given g_raw = dL/d raw [n_rows,4] (fp32) and the acts/masks of
  * nerfb200_mlp_forward_train on the same rows.  Two tcgen05 kernels: the activation-gradient chain
- * (keeps every dL/d pre-activation in the workspace) and ten split-K weight-gradient GEMMs with the bias
- * and head gradients riding along; bf16 operands, fp32 accumulation, fp32 results.  MLP inputs receive
- * no gradient (the hierarchical sampler is detached).  workspace: 128-byte aligned. */
-NERFB200_API int nerfb200_mlp_backward(const void* packed_bwd, const float* g_raw, const void* acts,
-                          const void* masks, long long n_rows, void* workspace, size_t workspace_bytes,
-                          const nerfb200_mlp_grads* grads, void* stream);
+ * (keeps every dL/d pre-activation in the workspace) and nine split-K weight-gradient GEMMs with the bias
+ * and head gradients riding along; bf16 operands, fp32 accumulation, fp32 results.  The tail is fused like
+ * the forward (views_linears.0 o feature_linear = one linear map); `weights` (the same fp32 tensors that
+ * were packed) is read to split its gradient back into views_linears.0 / feature_linear by the chain rule.
+ * MLP inputs receive no gradient (the hierarchical sampler is detached).  workspace: 128-byte aligned. */
+NERFB200_API int nerfb200_mlp_backward(const void* packed_bwd, const nerfb200_mlp_weights* weights, const float* g_raw,
+                          const void* acts, const void* masks, long long n_rows, void* workspace,
+                          size_t workspace_bytes, const nerfb200_mlp_grads* grads, void* stream);
 
 /* diagnostic twin of mlp_forward (BF16 mode): additionally writes the fp32 post-activation output
  * of each of the ten stages (mlp_layout.cuh) for rows 0..127 into stage_dump [10][128][256];

@@ -33,8 +33,8 @@ int launch_mlp_bf16(const void* packed, const float* rays_o, const float* rays_d
                     const int* row_ids, const int* n_active, cudaStream_t st);
 int launch_mlp_bwd_dgrad(const void* packed_bwd, const float* g_raw, const void* masks, void* dacts, long long M,
                          cudaStream_t st);
-int launch_mlp_bwd_wgrad(const void* acts, const void* dacts, long long M, float* scratch, const nerfb200_mlp_grads* grads,
-                         cudaStream_t st);
+int launch_mlp_bwd_wgrad(const void* acts, const void* dacts, long long M, float* scratch, const nerfb200_mlp_weights* weights,
+                         const nerfb200_mlp_grads* grads, cudaStream_t st);
 
 // ---- optional MLP-kernel timing (bench.py roofline): CUDA events around every mlp launch, on
 // the launching stream, while enabled.  Off by default; the only other global state besides the
@@ -156,11 +156,13 @@ extern "C" int nerfb200_mlp_forward_train(const void* packed, int mode, const fl
   return launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, nullptr, acts, masks, nullptr, nullptr, (cudaStream_t)stream);
 }
 
-extern "C" int nerfb200_mlp_backward(const void* packed_bwd, const float* g_raw, const void* acts, const void* masks,
-                                     long long n_rows, void* workspace, size_t workspace_bytes,
-                                     const nerfb200_mlp_grads* grads, void* stream) {
+extern "C" int nerfb200_mlp_backward(const void* packed_bwd, const nerfb200_mlp_weights* weights, const float* g_raw,
+                                     const void* acts, const void* masks, long long n_rows, void* workspace,
+                                     size_t workspace_bytes, const nerfb200_mlp_grads* grads, void* stream) {
   NB_CHECK_ARG(n_rows >= 0, "mlp_backward: bad n_rows");
   NB_CHECK_ARG(grads, "mlp_backward: null grads");
+  NB_CHECK_ARG(weights && weights->views_w && weights->feature_w && weights->feature_b,
+               "mlp_backward: the fp32 views_linears.0 / feature_linear tensors are needed for the fused-tail chain rule");
   for (int i = 0; i < 8; ++i) NB_CHECK_ARG(grads->pts_w[i] && grads->pts_b[i], "mlp_backward: null gradient pts_linears.%d", i);
   NB_CHECK_ARG(grads->views_w && grads->views_b && grads->feature_w && grads->feature_b && grads->alpha_w && grads->alpha_b &&
                    grads->rgb_w && grads->rgb_b, "mlp_backward: null head gradient");
@@ -178,7 +180,7 @@ extern "C" int nerfb200_mlp_backward(const void* packed_bwd, const float* g_raw,
   } else {
     NB_CHECK_ARG(workspace && workspace_bytes >= kGradScratchFloats * sizeof(float), "mlp_backward: workspace too small");
   }
-  return launch_mlp_bwd_wgrad(acts, workspace, n_rows, scratch, grads, st);
+  return launch_mlp_bwd_wgrad(acts, workspace, n_rows, scratch, weights, grads, st);
 }
 
 extern "C" int nerfb200_mlp_forward_sparse(const void* packed, int mode, const float* rays_o, const float* rays_d,

@@ -221,14 +221,18 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
             for (int i = kChD; i < 32; ++i) f[i] = 0.f;
             store_row_chunks<4>(pe_base, row, f);
           }
+          const bool tl_on = kTimeline && kSave && tl && blockIdx.x == 0 && it < 4 && row == 0;
+          if (tl_on) tl[720 + ((it * 10 + stage) * 2 + slot) * 4 + 0] = clock64();
           tc_fence_before();
           fence_proxy_async_smem();
           if (kSave) named_bar_sync(1 + slot, 128);
+          if (tl_on) tl[720 + ((it * 10 + stage) * 2 + slot) * 4 + 1] = clock64();
           if (!kSave || save_leader) mbar_arrive_remote(b_ready_leader);
           mbar_arrive(bar(BAR_BEMPTY + bbuf));
+          if (tl_on) tl[720 + ((it * 10 + stage) * 2 + slot) * 4 + 2] = clock64();
           if (kSave && tile_ok) {   // stage output (= next stage's A tile) -> activation store, while the MMAs read it too
-            copy_tile_s2g<4 * kBlockBytes>(acts_tile + (size_t)(stage < 8 ? act_h(stage) : kActFeat) * kBlockBytes,
-                                           smem_dyn + kOffA + slot * kABytes, row);
+            copy_tile_s2g<4 * kBlockBytes>(acts_tile + (size_t)act_h(stage) * kBlockBytes,
+                                           smem_dyn + kOffA + slot * kABytes, row, dbg);
             if (stage == I::kLast - 1)
               copy_tile_s2g<kBlockBytes>(acts_tile + (size_t)kActDpe * kBlockBytes, smem_dyn + kOffPe + slot * kPeBytes, row);
           }
@@ -441,13 +445,13 @@ int launch_mlp_bf16(const void* packed, const float* rays_o, const float* rays_d
   NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<true, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-  NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<false, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-  NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<false, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<false, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   const char* tl_env = getenv("NERFB200_TIMELINE");
   unsigned long long* tl = nullptr;
   if (tl_env && !stage_dump) {
-    cudaMalloc(&tl, (320 + 400) * 8);
-    cudaMemset(tl, 0, (320 + 400) * 8);
+    cudaMalloc(&tl, (320 + 400 + 320) * 8);
+    cudaMemset(tl, 0, (320 + 400 + 320) * 8);
   }
   long long M = (long long)n_rays * n_samples;
   long long quads = (M + 511) / 512;
@@ -457,11 +461,11 @@ int launch_mlp_bf16(const void* packed, const float* rays_o, const float* rays_d
     if (v > 0 && v < clusters) clusters = v;
   }
   if (acts && tl)
-    mlp_bf16_tc2_kernel<false, true, true, false><<<2 * clusters, kThreads, kSmemBytes, st>>>(
+    mlp_bf16_tc2_kernel<false, true, true, true><<<2 * clusters, kThreads, kSmemBytes, st>>>(
         (const unsigned char*)packed, rays_o, rays_d, z_vals, M, n_samples, (int)quads, raw, nullptr, tl,
         (unsigned char*)acts, (uint32_t*)masks, nullptr, nullptr, getenv("NERFB200_DBG") ? atoi(getenv("NERFB200_DBG")) : 0);
   else if (acts)
-    mlp_bf16_tc2_kernel<false, false, true, false><<<2 * clusters, kThreads, kSmemBytes, st>>>(
+    mlp_bf16_tc2_kernel<false, false, true, true><<<2 * clusters, kThreads, kSmemBytes, st>>>(
         (const unsigned char*)packed, rays_o, rays_d, z_vals, M, n_samples, (int)quads, raw, nullptr, nullptr,
         (unsigned char*)acts, (uint32_t*)masks, nullptr, nullptr);
   else if (stage_dump)
@@ -475,7 +479,7 @@ int launch_mlp_bf16(const void* packed, const float* rays_o, const float* rays_d
         (const unsigned char*)packed, rays_o, rays_d, z_vals, M, n_samples, (int)quads, raw, nullptr, nullptr, nullptr, nullptr, row_ids, n_active);
   NB_LAUNCH_OK("mlp_bf16_tc2_kernel");
   if (tl) {   // debug only (NERFB200_TIMELINE=<file>): dump cluster 0's handshake timestamps
-    unsigned long long host[320 + 400];
+    unsigned long long host[320 + 400 + 320];
     cudaStreamSynchronize(st);
     cudaMemcpy(host, tl, sizeof(host), cudaMemcpyDeviceToHost);
     cudaFree(tl);
@@ -484,6 +488,8 @@ int launch_mlp_bf16(const void* packed, const float* rays_o, const float* rays_d
       for (int i = 0; i < 4 * 10 * 2; ++i)
         fprintf(f, "%d %d %d %llu %llu %llu %llu\n", i / 20, (i / 2) % 10, i % 2, host[i * 4], host[i * 4 + 1],
                 host[i * 4 + 2], host[i * 4 + 3]);
+      for (int i = 0; i < 4 * 10 * 2; ++i)   // training epilogue detail: it stage 8<slot> after-compute after-barrier after-arrive 0
+        fprintf(f, "%d %d 8%d %llu %llu %llu 0\n", i / 20, (i / 2) % 10, i % 2, host[720 + i * 4], host[720 + i * 4 + 1], host[720 + i * 4 + 2]);
       for (int i = 0; i < 200; ++i)   // weight-chunk waits of slot 0's pass: it stage 9 chunk start end 0 0
         fprintf(f, "%d %d 9%d %llu %llu 0 0\n", i / 50, (i / 5) % 10, i % 5, host[320 + i * 2], host[320 + i * 2 + 1]);
       fclose(f);

@@ -4,9 +4,9 @@
 // forward kernel (mlp_bf16_tc2.cu) walks it forward:
 //
 //   prologue (CUDA cores)   d_hv   = relu'(hv)  . (g_rgb  * rgb_linear.W)                     [128]
-//   bstage 0  (K = 128)     d_feat = d_hv . views_linears.0.W[:, :256]                         [256] (linear)
-//   bstage 1  (K = 256)     d_pre7 = relu'(h7) . (d_feat . feature_linear.W + g_sigma * alpha_linear.W)
-//   bstage 2..8             d_pre(i-1) = relu'(h(i-1)) . (d_pre(i) . pts_linears.i.W[:, hidden cols]),  i = 7..1
+//   bstage 0  (K = 128)     d_pre7 = relu'(h7) . (d_hv . W'[:, :256] + g_sigma * alpha_linear.W),  W' = Wv[:, :256] Wf
+//                           (the fused tail of train_layout.cuh: feature_linear is linear, so it never appears alone)
+//   bstage 1..7             d_pre(i-1) = relu'(h(i-1)) . (d_pre(i) . pts_linears.i.W[:, hidden cols]),  i = 7..1
 //
 // Every stage's output is (a) the next stage's A operand in shared memory and (b) the A operand of the
 // weight-gradient GEMM, so the finished 64 KB tile image is also bulk-stored to the `dacts` store
@@ -54,7 +54,7 @@ __device__ __forceinline__ uint4 pack8(const float (&x)[8], uint32_t mb, int q) 
   return o;
 }
 
-// MODE 0: linear (d_feat); 1: + g_sigma * alpha_w, masked (d_pre7); 2: masked (d_pre6..0)
+// MODE 0: linear (unused since the tail is fused); 1: + g_sigma * alpha_w, masked (d_pre7); 2: masked (d_pre6..0)
 template <int MODE>
 __device__ __forceinline__ void depi32(const uint32_t (&v)[32], unsigned char* out_row, int j0, int r7, uint32_t mb,
                                        float gs, const float* __restrict__ aw) {
@@ -199,8 +199,8 @@ mlp_bwd_dgrad_kernel(const unsigned char* __restrict__ packed_bwd, const float* 
 
       for (int bs = 0; bs < kBwdStages; ++bs) {
         uint32_t mw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-        if (bs >= 1 && tile_ok) {   // relu sign bits of h(8-bs), fetched before the wait to hide the latency
-          const uint4* mp = reinterpret_cast<const uint4*>(masks + (size_t)(8 - bs) * mask_plane + mask_row);
+        if (tile_ok) {   // relu sign bits of h(7-bs), fetched before the wait to hide the latency
+          const uint4* mp = reinterpret_cast<const uint4*>(masks + (size_t)(7 - bs) * mask_plane + mask_row);
           const uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
           mw[0] = m0.x; mw[1] = m0.y; mw[2] = m0.z; mw[3] = m0.w;
           mw[4] = m1.x; mw[5] = m1.y; mw[6] = m1.z; mw[7] = m1.w;
@@ -209,15 +209,14 @@ mlp_bwd_dgrad_kernel(const unsigned char* __restrict__ packed_bwd, const float* 
         full_phase ^= 1;
         tc_fence_after();
         named_bar_sync(1 + slot, 128);   // the previous stage's tile has been copied out by everyone
-        if (bs == 0) depi_stage256<0>(t_acc, a_row_base, r7, mw, 0.f, alpha_w);
-        else if (bs == 1) depi_stage256<1>(t_acc, a_row_base, r7, mw, g.w, alpha_w);
+        if (bs == 0) depi_stage256<1>(t_acc, a_row_base, r7, mw, g.w, alpha_w);
         else depi_stage256<2>(t_acc, a_row_base, r7, mw, 0.f, alpha_w);
         tc_fence_before();
         fence_proxy_async_smem();
         named_bar_sync(1 + slot, 128);
         if (leader && bs + 1 < kBwdStages) mbar_arrive_remote(b_ready_leader);
         if (tile_ok)   // while the next stage's MMAs read the same tile
-          copy_tile_s2g<4 * kBlockBytes>(dacts_tile + (size_t)(bs == 0 ? kDactFeat : dact_pre(8 - bs)) * kBlockBytes, a_tile, row);
+          copy_tile_s2g<4 * kBlockBytes>(dacts_tile + (size_t)dact_pre(7 - bs) * kBlockBytes, a_tile, row);
       }
     }
   } else if (warp == 8) {

@@ -1,4 +1,4 @@
-// a7, MLP backward part 2: weight and bias gradients of one NeRF model as ten split-K GEMMs on tcgen05.
+// a7, MLP backward part 2: weight and bias gradients of one NeRF model as nine split-K GEMMs on tcgen05.
 //   dW_s[out, in] = sum over rows  dpre_s[row, out] * x_s[row, in]
 // Both factors are the tile images the forward (x_s: `acts`) and the dgrad kernel (dpre_s: `dacts`) left in
 // HBM (train_layout.cuh).  The contraction runs over the ROWS of those images, so the very same bytes are
@@ -6,16 +6,18 @@
 // streaming 10.7 KB per row from HBM, the tensor pipe is about one third busy.
 //
 // One CTA pair (cta_group::2, M = 256 = the output index) per TPC, persistent over the 128-row tiles
-// t = cluster, cluster + n_clusters, ...; stage-major: for each of the ten stages the pair accumulates
+// t = cluster, cluster + n_clusters, ...; stage-major: for each of the nine stages the pair accumulates
 // its share of the rows in TMEM, then reduces the accumulator into a global fp32 scratch with
-// red.global.add (74 pairs x 10 stages, a few MB of atomics per model).  Per CTA (rank r):
+// red.global.add (74 pairs x 9 stages, a few MB of atomics per model).  Per CTA (rank r):
 //   A  = dpre_s blocks 2r, 2r+1      (its 128 output rows of D)
 //   B  = x_s    blocks 2r, 2r+1      (its half of D's 256 columns)
 // Small products ride along on extra accumulator columns instead of extra kernels:
 //   * bias gradients: B = a constant tile of ones, N = 16                   (every stage)
 //   * the PE / dir-PE input columns of pts_linears.0/.5 and views_linears.0: B = PE / DPE block
-//   * rgb_linear:   stage 9's A tile carries g_raw as rows 128..131, B = HV  -> rows 128..130 = dW_rgb
-//   * alpha_linear: stage 8, A = H7 (already on chip as B), B = g_raw block, N = 16 -> column 3 = dW_alpha
+//   * the tail stage (8): A = D9 = [d_hv | g_raw | 0], so with B = H7 rows 0..127 are dW' (fused views x feature
+//     weight, train_layout.cuh) and row 131 is dW_alpha; with B = HV rows 128..130 are dW_rgb
+// The gradients of views_linears.0[:, :256], feature_linear and their biases follow from dW', db' by the chain
+// rule in wgrad_tail_kernel (two 128x256x256 products on CUDA cores, once per step).
 // Narrow B operands are fed with N = 2 x (real width): both CTAs supply the same columns and the upper
 // half of the product is a duplicate that is never read (a CTA cannot start mid-row in a swizzled image).
 //
@@ -39,22 +41,20 @@ constexpr uint32_t kSmemBytes = kOffBar + 256;
 enum { BAR_FULL = 0, BAR_EMPTY = 2, BAR_ACCFULL = 4, BAR_ACCFREE = 5, BAR_COUNT = 6 };
 
 // TMEM accumulator columns
-constexpr uint32_t kColMain = 0, kColAux = 256, kColAux2 = 320, kColOnes = 448, kColHead = 464;
+constexpr uint32_t kColMain = 0, kColAux = 256, kColAux2 = 320, kColOnes = 448;
 
 struct StagePlan {
   int a_blk;      // dacts block of this CTA's A (2 blocks)
   int b_blk;      // acts block of this CTA's main B (2 blocks), -1: no main product
-  int x1_blk;     // extra block 1 (PE / DPE from acts, or the g_raw block from dacts), -1: none
-  bool x1_dacts;
+  int x1_blk;     // extra block 1 (PE / DPE from acts), -1: none
   int x2_blk;     // extra block 2 (HV block `rank`), -1: none
 };
 __device__ __forceinline__ StagePlan plan(int s, int rank) {
   StagePlan p;
-  p.a_blk = (s < 8 ? dact_pre(s) : (s == 8 ? kDactFeat : kDactD9)) + 2 * rank;
-  p.b_blk = s == 0 ? -1 : ((s < 8 ? act_h(s - 1) : (s == 8 ? act_h(7) : kActFeat)) + 2 * rank);
-  p.x1_blk = (s == 0 || s == 5) ? kActPe : (s == 8 ? kDactD9 + 2 : (s == 9 ? kActDpe : -1));
-  p.x1_dacts = s == 8;
-  p.x2_blk = s == 9 ? kActHv + rank : -1;
+  p.a_blk = (s < 8 ? dact_pre(s) : kDactD9) + 2 * rank;
+  p.b_blk = s == 0 ? -1 : ((s < 8 ? act_h(s - 1) : act_h(7)) + 2 * rank);
+  p.x1_blk = (s == 0 || s == 5) ? kActPe : (s == 8 ? kActDpe : -1);
+  p.x2_blk = s == 8 ? kActHv + rank : -1;
   return p;
 }
 
@@ -121,7 +121,7 @@ mlp_bwd_wgrad_kernel(const unsigned char* __restrict__ acts, const unsigned char
       // =========================== producer ===========================
       if (lane == 0) {
         uint32_t seq = 0;
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < kWgradStages; ++s) {
           const StagePlan p = plan(s, (int)rank);
           const uint32_t bytes = 32768u + (p.b_blk >= 0 ? 32768u : 0u) + (p.x1_blk >= 0 ? 16384u : 0u) + (p.x2_blk >= 0 ? 16384u : 0u);
           for (int i = 0; i < my_tiles; ++i, ++seq) {
@@ -132,9 +132,7 @@ mlp_bwd_wgrad_kernel(const unsigned char* __restrict__ acts, const unsigned char
             mbar_arrive_expect_tx(full, bytes);
             bulk_g2s(slot + kRegionA, dacts + t * dact_tile_bytes + (size_t)p.a_blk * kBlockBytes, 32768u, full);
             if (p.b_blk >= 0) bulk_g2s(slot + kRegionB, acts + t * act_tile_bytes + (size_t)p.b_blk * kBlockBytes, 32768u, full);
-            if (p.x1_blk >= 0)
-              bulk_g2s(slot + kRegionX1, (p.x1_dacts ? dacts + t * dact_tile_bytes : acts + t * act_tile_bytes) + (size_t)p.x1_blk * kBlockBytes,
-                       16384u, full);
+            if (p.x1_blk >= 0) bulk_g2s(slot + kRegionX1, acts + t * act_tile_bytes + (size_t)p.x1_blk * kBlockBytes, 16384u, full);
             if (p.x2_blk >= 0) bulk_g2s(slot + kRegionX2, acts + t * act_tile_bytes + (size_t)p.x2_blk * kBlockBytes, 16384u, full);
           }
         }
@@ -144,7 +142,7 @@ mlp_bwd_wgrad_kernel(const unsigned char* __restrict__ acts, const unsigned char
       // =========================== relay (peer CTA): my part of ring slot `pos` has landed ===========================
       if (lane == 0) {
         uint32_t seq = 0;
-        for (int s = 0; s < kStages; ++s)
+        for (int s = 0; s < kWgradStages; ++s)
           for (int i = 0; i < my_tiles; ++i, ++seq) {
             const uint32_t pos = seq % kRing, phase = (seq / kRing) & 1u;
             mbar_wait(bar(BAR_FULL + pos), phase, 0x700 + s);
@@ -156,7 +154,7 @@ mlp_bwd_wgrad_kernel(const unsigned char* __restrict__ acts, const unsigned char
       // =========================== MMA issuer (leader CTA) ===========================
       uint32_t seq = 0;
       const uint32_t ones_addr = smem_base + kOffOnes;
-      for (int s = 0; s < kStages; ++s) {
+      for (int s = 0; s < kWgradStages; ++s) {
         // the flush warps of both CTAs have drained the previous stage's accumulators
         mbar_wait_cluster(bar(BAR_ACCFREE), (uint32_t)(s & 1) ^ 1u, 0x400 + s);
         tc_fence_after();
@@ -180,10 +178,7 @@ mlp_bwd_wgrad_kernel(const unsigned char* __restrict__ acts, const unsigned char
               else if (s == 5)    // pts_linears.5: PE columns of the skip concat
                 umma_bf16_ss_2cta(tmem_base + kColAux, da, umma_desc_sw128_mn(slot + kRegionX1 + koff, 16384u),
                                   umma_idesc_bf16_mn(256, 128), acc);
-              else if (s == 8)    // alpha_linear: A = H7 (this slot's B region), B = g_raw block
-                umma_bf16_ss_2cta(tmem_base + kColHead, umma_desc_sw128_mn(slot + kRegionB + koff, 16384u),
-                                  umma_desc_sw128_mn(slot + kRegionX1 + koff, 16384u), umma_idesc_bf16_mn(256, 16), acc);
-              else if (s == 9) {  // views_linears.0 dir-PE columns (32, fed as 2 x 32) and rgb_linear (B = HV, 128)
+              else if (s == 8) {  // tail: views_linears.0 dir-PE columns (32, fed as 2 x 32) and rgb_linear (B = HV, 128)
                 umma_bf16_ss_2cta(tmem_base + kColAux, da, umma_desc_sw128_mn(slot + kRegionX1 + koff, 16384u),
                                   umma_idesc_bf16_mn(256, 64), acc);
                 umma_bf16_ss_2cta(tmem_base + kColAux2, da, umma_desc_sw128_mn(slot + kRegionX2 + koff, 16384u),
@@ -203,18 +198,17 @@ mlp_bwd_wgrad_kernel(const unsigned char* __restrict__ acts, const unsigned char
       const int out = (int)rank * 128 + q * 32 + lane;         // output index (row of D)
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
       const uint32_t acc_free_leader = mapa(bar(BAR_ACCFREE), 0);
-      for (int s = 0; s < kStages; ++s) {
+      for (int s = 0; s < kWgradStages; ++s) {
         mbar_wait(bar(BAR_ACCFULL), (uint32_t)(s & 1), 0x100 + s);
         tc_fence_after();
         float* dst = scratch + ((size_t)s * 256 + (size_t)out) * kGradCols;
         flush_cols(t_row, kColMain, s == 0 ? 4 : 16, dst + kGradMain);          // s = 0: PE columns only (64)
         if (s == 5) flush_cols(t_row, kColAux, 4, dst + kGradAux);
-        if (s == 9) {
+        if (s == 8) {
           flush_cols(t_row, kColAux, 2, dst + kGradAux);
           if (out >= 128) flush_cols(t_row, kColAux2, 8, dst + kGradAux2);       // rows 128..130 hold dW_rgb
         }
         flush_cols(t_row, kColOnes, 1, dst + kGradOnes);
-        if (s == 8) flush_cols(t_row, kColHead, 1, dst + kGradHead);
         tc_fence_before();
         mbar_arrive_remote(acc_free_leader);
       }
@@ -229,7 +223,7 @@ mlp_bwd_wgrad_kernel(const unsigned char* __restrict__ acts, const unsigned char
   }
 }
 
-// scratch -> the 24 gradient tensors of one model (nn.Linear layout), overwriting them
+// scratch -> the gradient tensors that are plain copies (everything except views_w[:, :256], feature_w/b)
 __global__ void wgrad_finalize_kernel(const float* __restrict__ scratch, nerfb200_mlp_grads g) {
   const int s = blockIdx.y;
   const float* sc = scratch + (size_t)s * 256 * kGradCols;
@@ -243,29 +237,59 @@ __global__ void wgrad_finalize_kernel(const float* __restrict__ scratch, nerfb20
         if (c < kChX) g.pts_w[5][out * 319 + c] = row[kGradAux + c];
         else if (c < 319) g.pts_w[5][out * 319 + c] = row[kGradMain + c - kChX];
       } else if (c < 256) g.pts_w[s][out * 256 + c] = row[kGradMain + c];
-    } else if (s == 8) {
-      if (c < 256) g.feature_w[out * 256 + c] = row[kGradMain + c];
-      else if (c == 256) g.feature_b[out] = row[kGradOnes];
-      else if (c == 257) g.alpha_w[out] = row[kGradHead + 3];
     } else {
       if (out < 128) {
-        if (c < 256) g.views_w[out * 283 + c] = row[kGradMain + c];
-        else if (c < 283) g.views_w[out * 283 + c] = row[kGradAux + c - 256];
-        else if (c == 283) g.views_b[out] = row[kGradOnes];
+        if (c >= 256 && c < 283) g.views_w[out * 283 + c] = row[kGradAux + c - 256];
+        else if (c == 283) g.views_b[out] = row[kGradOnes];               // b' = Wv_a bf + bv  ->  d bv = d b'
       } else if (out < 131) {
         if (c < 128) g.rgb_w[(out - 128) * 128 + c] = row[kGradAux2 + c];
         else if (c == 128) g.rgb_b[out - 128] = row[kGradOnes];
-      } else if (out == 131 && c == 0) {
-        g.alpha_b[0] = row[kGradOnes];
+      } else if (out == 131) {
+        if (c < 256) g.alpha_w[c] = row[kGradMain + c];
+        else if (c == 256) g.alpha_b[0] = row[kGradOnes];
       }
     }
   }
 }
 
+// chain rule through the fused tail W' = Wv_a Wf, b' = Wv_a bf + bv (Wv_a = views_linears.0.weight[:, :256]):
+//   d Wv_a[n][j] = sum_k dW'[n][k] Wf[j][k] + db'[n] bf[j]      (blocks 0..127, one output row n each)
+//   d Wf[j][k]   = sum_n Wv_a[n][j] dW'[n][k],  d bf[j] = sum_n Wv_a[n][j] db'[n]   (blocks 128..383, row j each)
+__global__ void __launch_bounds__(256) wgrad_tail_kernel(const float* __restrict__ scratch, nerfb200_mlp_weights w, nerfb200_mlp_grads g) {
+  const float* sc = scratch + (size_t)8 * 256 * kGradCols;     // rows 0..127: dW' in cols 0..255, db' in col kGradOnes
+  __shared__ float sh[256];
+  const int t = threadIdx.x;
+  if (blockIdx.x < 128) {
+    const int n = blockIdx.x;
+    sh[t] = sc[(size_t)n * kGradCols + kGradMain + t];
+    __syncthreads();
+    const float4* wf = reinterpret_cast<const float4*>(w.feature_w + (size_t)t * 256);   // row j = t of Wf
+    float acc = sc[(size_t)n * kGradCols + kGradOnes] * w.feature_b[t];
+#pragma unroll 4
+    for (int k4 = 0; k4 < 64; ++k4) {
+      const float4 v = __ldg(wf + k4);
+      acc = fmaf(sh[4 * k4], v.x, acc); acc = fmaf(sh[4 * k4 + 1], v.y, acc);
+      acc = fmaf(sh[4 * k4 + 2], v.z, acc); acc = fmaf(sh[4 * k4 + 3], v.w, acc);
+    }
+    g.views_w[(size_t)n * 283 + t] = acc;
+  } else {
+    const int j = blockIdx.x - 128;
+    if (t < 128) sh[t] = w.views_w[(size_t)t * 283 + j];      // column j of Wv_a
+    __syncthreads();
+    float acc = 0.f, accb = 0.f;
+    for (int n = 0; n < 128; ++n) {
+      acc = fmaf(sh[n], sc[(size_t)n * kGradCols + kGradMain + t], acc);
+      if (t == 0) accb = fmaf(sh[n], sc[(size_t)n * kGradCols + kGradOnes], accb);
+    }
+    g.feature_w[(size_t)j * 256 + t] = acc;
+    if (t == 0) g.feature_b[j] = accb;
+  }
+}
+
 }  // namespace wg
 
-int launch_mlp_bwd_wgrad(const void* acts, const void* dacts, long long M, float* scratch, const nerfb200_mlp_grads* grads,
-                         cudaStream_t st) {
+int launch_mlp_bwd_wgrad(const void* acts, const void* dacts, long long M, float* scratch, const nerfb200_mlp_weights* weights,
+                         const nerfb200_mlp_grads* grads, cudaStream_t st) {
   using namespace wg;
   int dev = 0, sms = 0;
   NB_CUDA(cudaGetDevice(&dev));
@@ -278,8 +302,10 @@ int launch_mlp_bwd_wgrad(const void* acts, const void* dacts, long long M, float
     mlp_bwd_wgrad_kernel<<<2 * clusters, kThreads, kSmemBytes, st>>>((const unsigned char*)acts, (const unsigned char*)dacts, n_tiles, scratch);
     NB_LAUNCH_OK("mlp_bwd_wgrad_kernel");
   }
-  wgrad_finalize_kernel<<<dim3(40, kStages), 256, 0, st>>>(scratch, *grads);
+  wgrad_finalize_kernel<<<dim3(40, kWgradStages), 256, 0, st>>>(scratch, *grads);
   NB_LAUNCH_OK("wgrad_finalize_kernel");
+  wgrad_tail_kernel<<<384, 256, 0, st>>>(scratch, *weights, *grads);
+  NB_LAUNCH_OK("wgrad_tail_kernel");
   return 0;
 }
 

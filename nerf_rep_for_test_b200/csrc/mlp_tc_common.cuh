@@ -120,13 +120,18 @@ __device__ __forceinline__ void epi_stage256(uint32_t t_acc, const float4* __res
 // store of the same tile kept the tile busy for > 2500 cycles (L2 path shared with the weight stream) and
 // stalled the next epilogue (measured: +2300 cycles per stage).
 template <int BYTES>
-__device__ __forceinline__ void copy_tile_s2g(unsigned char* __restrict__ gdst, const unsigned char* ssrc, int t128) {
+__device__ __forceinline__ void copy_tile_s2g(unsigned char* __restrict__ gdst, const unsigned char* ssrc, int t128, int dbg = 0) {
   static_assert(BYTES % 8192 == 0, "tile copy works in batches of 4 x 2048 B");
 #pragma unroll 1
   for (int k = 0; k < BYTES / 8192; ++k) {
     uint4 v[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const uint4*>(ssrc + k * 8192 + j * 2048 + t128 * 16);
+    for (int j = 0; j < 4; ++j)
+      v[j] = (dbg & 8) ? make_uint4(k, j, t128, 0) : *reinterpret_cast<const uint4*>(ssrc + k * 8192 + j * 2048 + t128 * 16);
+    if (dbg & 4) {   // experiment: no global stores (keep the loads alive)
+      if ((v[0].x ^ v[1].y ^ v[2].z ^ v[3].w) == 0x12345678u) gdst[0] = 1;
+      continue;
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(gdst + k * 8192 + j * 2048 + t128 * 16) = v[j];
   }

@@ -127,11 +127,11 @@ __global__ void pack_bf16_bwd_kernel(nerfb200_mlp_weights w, unsigned char* __re
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int c = i / (256 * 64), n = (i / 64) % 256, kk = i % 64;
     const int k = c * 64 + kk;   // output index of the layer = K of the dgrad GEMM
-    float v;
-    if (b == 0) v = w.views_w[(size_t)k * 283 + n];
-    else if (b == 1) v = w.feature_w[(size_t)k * 256 + n];
-    else {
-      const int layer = 9 - b;   // 7..1
+    float v = 0.f;
+    if (b == 0) {   // fused tail W'[k][n] = sum_j Wv[k][j] Wf[j][n]  (same fp32 chain as pack_bf16_fused_kernel)
+      for (int j = 0; j < 256; ++j) v = fmaf(w.views_w[(size_t)k * 283 + j], w.feature_w[(size_t)j * 256 + n], v);
+    } else {
+      const int layer = 8 - b;   // 7..1
       v = layer == 5 ? w.pts_w[5][(size_t)k * 319 + kChX + n] : w.pts_w[layer][(size_t)k * 256 + n];
     }
     size_t off = (size_t)bwd_stage_off(b) + (size_t)c * kBwdChunkBytes + (size_t)n * 128 +

@@ -83,9 +83,12 @@ class TrainStore:
     (layout: csrc/train_layout.cuh)."""
 
     # block index of each plane inside a 128-row tile of `acts`, and its width in 64-column blocks
-    PLANES = {"pe": (0, 1), "dpe": (1, 1), "feat": (34, 4), "hv": (38, 2)}
+    PLANES = {"pe": (0, 1), "dpe": (1, 1), "hv": (34, 2)}
     PLANES.update({"h%d" % i: (2 + 4 * i, 4) for i in range(8)})
-    BLOCKS, BLOCK_BYTES = 40, 16384
+    BLOCKS, BLOCK_BYTES = 36, 16384
+    DACT_PLANES = {"d9": (32, 4)}
+    DACT_PLANES.update({"dpre%d" % i: (4 * i, 4) for i in range(8)})
+    DACT_BLOCKS = 36
 
     def __init__(self, n_rows, device):
         lib = L.load()
@@ -127,9 +130,11 @@ GRAD_SHAPES = [(256, 63), (256,)] + [(256, 256), (256,)] * 4 + [(256, 319), (256
     [(128, 283), (128,), (256, 256), (256,), (1, 256), (1,), (3, 128), (3,)]
 
 
-def mlp_backward(packed_bwd_ptr, g_raw, store, keep_workspace=None):
+def mlp_backward(bwd, g_raw, store, keep_workspace=None):
     """nerfb200_mlp_backward: the 24 gradients (order of training._NAMES) of one model given dL/draw.
+    bwd = Renderer.packed_bwd(which): (packed W^T image pointer, nerfb200_mlp_weights struct of the fp32 tensors).
     `keep_workspace`: optional dict that receives the workspace tensor (tests read the dgrad planes)."""
+    packed_bwd_ptr, wstruct = bwd
     g_raw = _f(g_raw).reshape(-1, 4)
     lib = L.load()
     n_rows = store.n_rows
@@ -144,8 +149,9 @@ def mlp_backward(packed_bwd_ptr, g_raw, store, keep_workspace=None):
         g.pts_w[i], g.pts_b[i] = grads[2 * i].data_ptr(), grads[2 * i + 1].data_ptr()
     (g.views_w, g.views_b, g.feature_w, g.feature_b, g.alpha_w, g.alpha_b, g.rgb_w, g.rgb_b) = \
         [t.data_ptr() for t in grads[16:24]]
-    L.check(lib.nerfb200_mlp_backward(packed_bwd_ptr, L.dev(g_raw), L.dev(store.acts), L.dev(store.masks), n_rows,
-                                      L.dev(ws), ws_bytes, C.byref(g), L.stream_ptr()), "mlp_backward")
+    L.check(lib.nerfb200_mlp_backward(packed_bwd_ptr, C.byref(wstruct), L.dev(g_raw), L.dev(store.acts),
+                                      L.dev(store.masks), n_rows, L.dev(ws), ws_bytes, C.byref(g), L.stream_ptr()),
+            "mlp_backward")
     if keep_workspace is not None:
         keep_workspace["ws"] = ws
     return grads

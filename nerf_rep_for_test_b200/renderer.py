@@ -204,10 +204,9 @@ class Renderer:
             w, keep = _model_weight_struct(model)
             base = (buf.data_ptr() + 1023) & ~1023
             L.check(self.lib.nerfb200_pack_weights_bwd(C.byref(w), C.c_void_p(base), L.stream_ptr()), "pack_weights_bwd")
-            del keep
-            ent = (key, buf, base)
+            ent = (key, buf, base, w, keep)     # the struct (and its tensors) are read again by mlp_backward
             self._packed["bwd_" + which] = ent
-        return C.c_void_p(ent[2])
+        return C.c_void_p(ent[2]), ent[3]
 
     def _packed_ptr(self, which):
         self._packed_weights(which)

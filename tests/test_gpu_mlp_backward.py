@@ -49,17 +49,19 @@ def test_train_store_matches_stage_outputs(n, S):
     ro, rd, z = _rays(n, S)
     pk = r.packed("coarse", "bf16")
     raw, store = ops.mlp_forward_train(pk, ro, rd, z)
-    raw2, dump = ops.mlp_forward_stages(pk, ro, rd, z)
+    raw2, dump = ops.mlp_forward_stages(pk, ro, rd, z)          # unfused ten-stage diagnostic image
+    raw3 = ops.mlp_forward(pk, ro, rd, z)                       # fused inference image
     torch.cuda.synchronize()
     M = n * S
-    assert torch.equal(raw, raw2)
+    assert torch.equal(raw, raw3)                               # the training forward IS the inference forward
     rows = min(M, 128)
     for i in range(8):
         got = store.plane("h%d" % i)
         assert got.shape == (M, 256)
         assert torch.equal(got[:rows].float(), dump[i, :rows].bfloat16().float()), i
-    assert torch.equal(store.plane("feat")[:rows].float(), dump[8, :rows].bfloat16().float())
-    assert torch.equal(store.plane("hv")[:rows].float(), dump[9, :rows, :128].bfloat16().float())
+    # the tail is fused (W' = Wv Wf rounded once): relu(views) agrees with the two-step image to bf16 rounding
+    hv, hv_ref = store.plane("hv")[:rows].float(), dump[9, :rows, :128]
+    assert float((hv - hv_ref).abs().max()) <= 2e-2 * float(hv_ref.abs().max()) + 1e-3
     pts = (ro[:, None, :] + rd[:, None, :] * z[..., None]).reshape(-1, 3)
     pe = O.pos_enc(pts.cpu(), 10).to(DEV)
     dpe = O.pos_enc(rd.cpu(), 4).to(DEV)[:, None, :].expand(n, S, 27).reshape(-1, 27)
@@ -86,9 +88,10 @@ def _torch_backward(sd, prefix, store, g_raw):
     g = g_raw.reshape(-1, 4).to(f64)
     on = lambda a: (a > 0).to(f64)
     d_hv = bf(on(P["hv"]) * (g[:, :3].float() @ W["rgb_linear.weight"]).to(f64))
-    d_feat = bf(d_hv @ bf(W["views_linears.0.weight"][:, :256]))
+    Wva, Wf, bfeat = W["views_linears.0.weight"][:, :256], W["feature_linear.weight"], W["feature_linear.bias"]
+    Wp = bf(Wva @ Wf)                                            # fused tail weight, rounded once (pack_bf16_bwd_kernel)
     d_pre = [None] * 8
-    d_pre[7] = bf(on(P["h7"]) * (d_feat @ bf(W["feature_linear.weight"]) + g[:, 3:4] * W["alpha_linear.weight"].to(f64)))
+    d_pre[7] = bf(on(P["h7"]) * (d_hv @ Wp + g[:, 3:4] * W["alpha_linear.weight"].to(f64)))
     for i in range(7, 0, -1):
         w = W["pts_linears.%d.weight" % i]
         w = w[:, 63:] if i == 5 else w
@@ -104,15 +107,17 @@ def _torch_backward(sd, prefix, store, g_raw):
             gw = d_pre[i].t() @ P["h%d" % (i - 1)]
         grads["pts_linears.%d.weight" % i] = gw
         grads["pts_linears.%d.bias" % i] = d_pre[i].sum(0)
-    grads["views_linears.0.weight"] = torch.cat([d_hv.t() @ P["feat"], d_hv.t() @ P["dpe"][:, :27]], 1)
-    grads["views_linears.0.bias"] = d_hv.sum(0)
-    grads["feature_linear.weight"] = d_feat.t() @ P["h7"]
-    grads["feature_linear.bias"] = d_feat.sum(0)
+    dWp, dbp = d_hv.t() @ P["h7"], d_hv.sum(0)                   # gradient of the fused map, then the chain rule
+    grads["views_linears.0.weight"] = torch.cat([dWp @ Wf.to(f64).t() + dbp[:, None] * bfeat.to(f64)[None, :],
+                                                 d_hv.t() @ P["dpe"][:, :27]], 1)
+    grads["views_linears.0.bias"] = dbp
+    grads["feature_linear.weight"] = Wva.to(f64).t() @ dWp
+    grads["feature_linear.bias"] = Wva.to(f64).t() @ dbp
     grads["alpha_linear.weight"] = G[:, 3:4].t() @ P["h7"]
     grads["alpha_linear.bias"] = G[:, 3].sum(0, keepdim=True)
     grads["rgb_linear.weight"] = G[:, :3].t() @ P["hv"]
     grads["rgb_linear.bias"] = G[:, :3].sum(0)
-    inter = {"d9": torch.cat([d_hv, G], 1), "dfeat": d_feat}
+    inter = {"d9": torch.cat([d_hv, G], 1)}
     inter.update({"dpre%d" % i: d_pre[i] for i in range(8)})
     return grads, inter
 
@@ -130,12 +135,10 @@ def test_mlp_backward_kernels_vs_torch(n, S, which):
     ref, inter = _torch_backward(sd, "model." if which == "coarse" else "model_fine.", store, g_raw)
     # dgrad planes first (they localise a failure)
     n_tiles = (M + 127) // 128
-    dacts = keep["ws"][: n_tiles * 40 * 16384]
-    planes = {"d9": (36, 4), "dfeat": (32, 4)}
-    planes.update({"dpre%d" % i: (4 * i, 4) for i in range(8)})
-    for name in ["d9", "dfeat"] + ["dpre%d" % i for i in range(7, -1, -1)]:
-        blk, width = planes[name]
-        got = ops.untile(dacts, M, 40, blk, width).double()
+    dacts = keep["ws"][: n_tiles * store.DACT_BLOCKS * 16384]
+    for name in ["d9"] + ["dpre%d" % i for i in range(7, -1, -1)]:
+        blk, width = store.DACT_PLANES[name]
+        got = ops.untile(dacts, M, store.DACT_BLOCKS, blk, width).double()
         want = inter[name]
         if name == "d9":
             assert float(got[:, 132:].abs().max()) == 0.0
