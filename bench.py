@@ -343,10 +343,27 @@ def run_ours(args):
                     "note": "throughput of the a9 path; the reference's kilonerf_cuda extension is never built or run "
                             "(SURVEY 2.2), so there is no reference number for it"}
 
-    t = torch.tensor([ms_total, e2e_ms, train_ms], dtype=torch.float64, device=dev)
+    # ---- BASELINE.json configs[3]: the 200-view 800x800 test set, views dealt round-robin to the ranks (no
+    # inter-GPU traffic); time = device time of the slowest rank for its share, poses resident in HBM.
+    testset_ms = 0.0
+    if args.testset_views > 0:
+        mine = [{"pose": lego_pose(i)[None].to(dev), "intrinsics": K0.clone().to(dev), "H": H, "W": W}
+                for i in range(rank, args.testset_views, world)]
+        r.render(mine[0])
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for b in mine:
+            r.render(b)
+        s1.record()
+        torch.cuda.synchronize()
+        testset_ms = s0.elapsed_time(s1)
+        barrier()
+
+    t = torch.tensor([ms_total, e2e_ms, train_ms, testset_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, train_ms = float(t[0]), float(t[1]), float(t[2])
+    ms_total, e2e_ms, train_ms, testset_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     rays_total = float(world) * args.steps * H * W
     value = rays_total / (ms_total * 1e-3)
     e2e_value = rays_total / (e2e_ms * 1e-3)
@@ -400,6 +417,12 @@ def run_ours(args):
                 "note": "every kernel on the path is this repo's: tcgen05 forward with activation store, compositing "
                         "backward, tcgen05 dgrad chain + split-K wgrad GEMMs (nerfb200_mlp_backward); torch supplies "
                         "Adam, clip_grad_value_ and the NCCL all-reduce"}
+        if args.testset_views > 0:
+            line["testset"] = {"workload": "%d-view 800x800 test-set render, views dealt round-robin to %d GPU(s), "
+                                           "64+128 samples, bf16" % (args.testset_views, world),
+                               "views": args.testset_views, "total_ms": testset_ms,
+                               "rays_per_s": args.testset_views * H * W / (testset_ms * 1e-3),
+                               "ms_per_view_per_gpu": testset_ms / -(-args.testset_views // world)}
         if cfg5 is not None:
             line["ess_ert"] = cfg5
         if kilo_cfg is not None:
@@ -423,6 +446,8 @@ def main():
     ap.add_argument("--no-config5", dest="config5", action="store_false", help="skip the ESS/ERT vs dense comparison")
     ap.add_argument("--train-steps", type=int, default=20)
     ap.add_argument("--train-warmup", type=int, default=5)
+    ap.add_argument("--testset-views", type=int, default=0,
+                    help="also render this many test-set views sharded over the ranks (BASELINE configs[3]: 200)")
     ap.add_argument("--train-rays", type=int, default=4096)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -125,7 +125,8 @@ __global__ void pack_bf16_bwd_kernel(nerfb200_mlp_weights w, unsigned char* __re
   }
   const int total = bwd_chunks(b) * 256 * 64;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int c = i / (256 * 64), n = (i / 64) % 256, kk = i % 64;
+    int c = i / (256 * 64), n = (i / 64) % 256, kk = i % 64;
+    if (b == 0) { n = i % 256; kk = (i / 256) % 64; c = i / (256 * 64); }   // n fastest: coalesced reads of Wf rows
     const int k = c * 64 + kk;   // output index of the layer = K of the dgrad GEMM
     float v = 0.f;
     if (b == 0) {   // fused tail W'[k][n] = sum_j Wv[k][j] Wf[j][n]  (same fp32 chain as pack_bf16_fused_kernel)

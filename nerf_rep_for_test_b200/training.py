@@ -99,7 +99,7 @@ class TrainStep:
         from .parallel import FlatGradAllReduce
         self.r = renderer
         self.params = list(renderer.net.model.parameters()) + list(renderer.net.model_fine.parameters())
-        self.opt = torch.optim.Adam(self.params, lr=lr, eps=1e-8)
+        self.opt = torch.optim.Adam(self.params, lr=lr, eps=1e-8, fused=True)
         self.allreduce = FlatGradAllReduce(self.params)
 
     def __call__(self, rays_o, rays_d, target_rgb):
