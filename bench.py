@@ -183,6 +183,11 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: native libraries (NCCL prints its version banner on fd 1) are sent to
+    # stderr for the whole run and the line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
     torch.cuda.set_device(local)
@@ -429,7 +434,7 @@ def run_ours(args):
             line["kilo"] = kilo_cfg
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_rays_per_s()
-        print(json.dumps(line))
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -130,9 +130,10 @@ GRAD_SHAPES = [(256, 63), (256,)] + [(256, 256), (256,)] * 4 + [(256, 319), (256
     [(128, 283), (128,), (256, 256), (256,), (1, 256), (1,), (3, 128), (3,)]
 
 
-def mlp_backward(bwd, g_raw, store, keep_workspace=None):
+def mlp_backward(bwd, g_raw, store, keep_workspace=None, grads=None):
     """nerfb200_mlp_backward: the 24 gradients (order of training._NAMES) of one model given dL/draw.
     bwd = Renderer.packed_bwd(which): (packed W^T image pointer, nerfb200_mlp_weights struct of the fp32 tensors).
+    `grads`: optional list of 24 preallocated fp32 tensors (e.g. views of one flat gradient buffer) to overwrite.
     `keep_workspace`: optional dict that receives the workspace tensor (tests read the dgrad planes)."""
     packed_bwd_ptr, wstruct = bwd
     g_raw = _f(g_raw).reshape(-1, 4)
@@ -143,7 +144,12 @@ def mlp_backward(bwd, g_raw, store, keep_workspace=None):
     dev = g_raw.device
     ws_bytes = lib.nerfb200_mlp_backward_workspace_bytes(n_rows)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    grads = [torch.empty(sh, device=dev) for sh in GRAD_SHAPES]
+    if grads is None:
+        grads = [torch.empty(sh, device=dev) for sh in GRAD_SHAPES]
+    else:
+        for t, sh in zip(grads, GRAD_SHAPES):
+            if tuple(t.shape) != tuple(sh) or t.dtype != torch.float32 or not t.is_contiguous() or t.device != dev:
+                raise L.NerfB200Error("mlp_backward: gradient buffer %s does not match %s fp32 contiguous" % (tuple(t.shape), sh))
     g = L.MlpGrads()
     for i in range(8):
         g.pts_w[i], g.pts_b[i] = grads[2 * i].data_ptr(), grads[2 * i + 1].data_ptr()

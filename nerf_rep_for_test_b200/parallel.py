@@ -28,17 +28,25 @@ def max_over_ranks(values, device):
 
 class FlatGradAllReduce:
     """Averages the gradients of `params` over all ranks with ONE all-reduce of a flat fp32 buffer
-    (1 191 688 elements = 4.77 MB for the two NeRF MLPs)."""
+    (1 191 688 elements = 4.77 MB for the two NeRF MLPs).  With `flat` given, the parameters' .grad tensors are
+    expected to alias that buffer already (training.TrainStep) and nothing is copied."""
 
-    def __init__(self, params):
+    def __init__(self, params, flat=None):
         self.params = [p for p in params if p.requires_grad]
         n = sum(p.numel() for p in self.params)
         p0 = self.params[0]
-        self.flat = torch.zeros(n, dtype=torch.float32, device=p0.device)
+        self.aliased = flat is not None
+        self.flat = flat if flat is not None else torch.zeros(n, dtype=torch.float32, device=p0.device)
+        if self.flat.numel() != n:
+            raise ValueError("flat gradient buffer has %d elements, parameters have %d" % (self.flat.numel(), n))
 
     def __call__(self):
         world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         if world == 1:
+            return
+        if self.aliased:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.flat.mul_(1.0 / world)
             return
         off = 0
         for p in self.params:

@@ -193,6 +193,14 @@ class Renderer:
         self._packed[which] = (key, buf, base)
         return buf
 
+    def invalidate_weights(self):
+        """Force a repack on next use.  The caches key on (data_ptr, _version) of every parameter, which covers
+        load_state_dict and ordinary in-place updates; fused multi-tensor optimizers (torch.optim.Adam(fused=True))
+        write the parameters without bumping _version, so TrainStep calls this after every optimizer step."""
+        for k in list(self._packed):
+            ent = self._packed[k]
+            self._packed[k] = (None,) + tuple(ent[1:])
+
     def packed_bwd(self, which):
         """W^T image for nerfb200_mlp_backward (training), cached per parameter version like _packed_weights."""
         model = self.coarse_model if which == "coarse" else self.fine_model

@@ -93,21 +93,55 @@ def nerf_loss(out, target_rgb):
 
 class TrainStep:
     """One data-parallel training step: fwd + bwd + flat-gradient all-reduce + clip_grad_value_(40)
-    (trainer.py:59) + Adam(lr 5e-4, eps 1e-8) (src/train/optimizer.py:8-28)."""
+    (trainer.py:59) + Adam(lr 5e-4, eps 1e-8) (src/train/optimizer.py:8-28).
+
+    The step calls the kernels directly instead of going through autograd (render_rays_train above stays the
+    autograd entry for generic use): the loss is mse(rgb_map_0, t) + mse(rgb_map, t), so dL/d(rgb map) is an
+    elementwise expression, and nerfb200_mlp_backward writes every gradient straight into its slice of ONE flat
+    fp32 buffer that the parameters' .grad tensors alias -- the NCCL all-reduce, the clip and the fused Adam
+    all work on that buffer with no per-parameter copies."""
 
     def __init__(self, renderer, lr=5e-4):
         from .parallel import FlatGradAllReduce
         self.r = renderer
-        self.params = list(renderer.net.model.parameters()) + list(renderer.net.model_fine.parameters())
+        self.models = (("coarse", renderer.coarse_model), ("fine", renderer.fine_model))
+        self.params = [p for _, m in self.models for p in model_params(m)]
+        dev = self.params[0].device
+        self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.grad_views = {name: [p.grad for p in model_params(m)] for name, m in self.models}
         self.opt = torch.optim.Adam(self.params, lr=lr, eps=1e-8, fused=True)
-        self.allreduce = FlatGradAllReduce(self.params)
+        self.allreduce = FlatGradAllReduce(self.params, flat=self.flat)
 
     def __call__(self, rays_o, rays_d, target_rgb):
-        self.opt.zero_grad(set_to_none=True)
-        out = render_rays_train(self.r, rays_o, rays_d)
-        loss = nerf_loss(out, target_rgb)
-        loss.backward()
+        r = self.r
+        if r.enable_ess or r.enable_ert:
+            raise L.NerfB200Error("training path implements the plain compositor (enable_ess/enable_ert off)")
+        dev = r.device
+        rays_o = rays_o.to(dev, torch.float32).contiguous()
+        rays_d = rays_d.to(dev, torch.float32).contiguous()
+        n = rays_o.shape[0]
+        r.seed += 1
+        z_c = ops.sample_coarse(r._table("z"), n, perturb=float(r.perturb) > 0, seed=r.seed)
+        pk_c, pk_f = r.packed("coarse", "bf16"), r.packed("fine", "bf16")
+        raw_c, store_c = ops.mlp_forward_train(pk_c, rays_o, rays_d, z_c)
+        rgb0, _, _, w_c, _ = ops.composite_forward(raw_c, z_c, rays_d, L.COMPOSITE_PLAIN, white_bkgd=r.white_bkgd)
+        u = torch.rand((n, r.N_importance), device=dev) if r.net.training else r._table("u")
+        z_all = ops.sample_pdf_merge(z_c, w_c, u, want_aux=False)[0]
+        raw_f, store_f = ops.mlp_forward_train(pk_f, rays_o, rays_d, z_all)
+        rgb = ops.composite_forward(raw_f, z_all, rays_d, L.COMPOSITE_PLAIN, white_bkgd=r.white_bkgd, want_weights=False)[0]
+        # loss = mean((rgb0 - t)^2) + mean((rgb - t)^2)  (trainers/nerf.py:52-65)  ->  dL/d map = 2 (map - t) / (3 n)
+        d0, d1 = rgb0 - target_rgb, rgb - target_rgb
+        loss = (d0 * d0).mean() + (d1 * d1).mean()
+        scale = 2.0 / d0.numel()
+        for which, z, raw, store, d in (("coarse", z_c, raw_c, store_c, d0), ("fine", z_all, raw_f, store_f, d1)):
+            g_raw = ops.composite_backward(raw, z, rays_d, d * scale, None, None, None, white_bkgd=r.white_bkgd)
+            ops.mlp_backward(r.packed_bwd(which), g_raw, store, grads=self.grad_views[which])
         self.allreduce()
-        torch.nn.utils.clip_grad_value_(self.params, 40)
+        self.flat.clamp_(-40.0, 40.0)          # clip_grad_value_(params, 40) on the aliased buffer
         self.opt.step()
-        return loss.detach()
+        r.invalidate_weights()
+        return loss

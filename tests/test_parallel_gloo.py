@@ -37,6 +37,18 @@ def _worker(rank, world, port, out):
         for g, l in zip([p.grad for p in lin.parameters()], local):
             expect = l * mean_scale if l.dim() == 2 else l        # bias grad does not depend on x
             assert torch.allclose(g, expect, atol=1e-6), (g, expect)
+        # aliased variant (training.TrainStep): .grad tensors are views of one flat buffer, reduced in place
+        lin2 = torch.nn.Linear(7, 3)
+        ps = list(lin2.parameters())
+        flat = torch.zeros(sum(p.numel() for p in ps))
+        off = 0
+        for p in ps:
+            p.grad = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        flat.fill_(float(rank + 1))
+        P.FlatGradAllReduce(ps, flat=flat)()
+        assert torch.allclose(flat, torch.full_like(flat, sum(range(1, world + 1)) / world))
+        assert all(p.grad.data_ptr() >= flat.data_ptr() for p in ps)
         out.put((rank, "ok"))
     except Exception as e:      # pragma: no cover
         out.put((rank, repr(e)))
