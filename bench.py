@@ -320,7 +320,7 @@ def run_ours(args):
         from oracle import kilo_oracle as KO
         from nerf_rep_for_test_b200 import kilo
         sc = KO.make_scene(seed=0, net_res=16, grid_res=128, blob_radius=1.0)
-        dbp, max_depth, min_d, spp = 4.0 / 384, 384, 2.0, 16
+        dbp, max_depth, min_d, spp = 4.0 / 384, 384, 2.0, 32
         kr = kilo.KiloRenderer(sc["grid"], sc["params"], sc["domain_mins"], sc["domain_maxs"], sc["gmin"], sc["gmax"], dbp,
                                max_depth, min_d, max_samples_per_ray=spp, device=dev)
         for _ in range(2):

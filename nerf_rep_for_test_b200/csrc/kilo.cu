@@ -225,20 +225,31 @@ __device__ __forceinline__ void fourier(float x, float* e) {
   }
 }
 
-// acc[s][0..NOUT) += in[s] * W[k][0..NOUT)  for the two samples of this thread; W row read as broadcast float4s
+// acc[s][0..NOUT) += in[s] * W[k][0..NOUT)  for the two samples of this thread.  The W row is read as broadcast
+// float4s and consumed by packed FFMA2 (two fused multiply-adds per instruction, same rounding as FFMA): the
+// kernel was issue-bound at 53 % issue utilisation with scalar FFMA (ncu), FFMA2 halves the FMA issue slots.
 template <int NOUT>
-__device__ __forceinline__ void fma_row(float (&acc)[2][NOUT], const float* __restrict__ wrow, float in0, float in1) {
+__device__ __forceinline__ void fma_row(float2 (&acc)[2][NOUT / 2], const float* __restrict__ wrow, float in0, float in1) {
   static_assert(NOUT % 4 == 0, "padded row widths of the micro-MLP");
   const float4* w4 = reinterpret_cast<const float4*>(wrow);
+  const float2 a0 = make_float2(in0, in0), a1 = make_float2(in1, in1);
 #pragma unroll
   for (int i = 0; i < NOUT / 4; ++i) {
     const float4 w = w4[i];
-    acc[0][4 * i + 0] = fmaf(in0, w.x, acc[0][4 * i + 0]); acc[1][4 * i + 0] = fmaf(in1, w.x, acc[1][4 * i + 0]);
-    acc[0][4 * i + 1] = fmaf(in0, w.y, acc[0][4 * i + 1]); acc[1][4 * i + 1] = fmaf(in1, w.y, acc[1][4 * i + 1]);
-    acc[0][4 * i + 2] = fmaf(in0, w.z, acc[0][4 * i + 2]); acc[1][4 * i + 2] = fmaf(in1, w.z, acc[1][4 * i + 2]);
-    acc[0][4 * i + 3] = fmaf(in0, w.w, acc[0][4 * i + 3]); acc[1][4 * i + 3] = fmaf(in1, w.w, acc[1][4 * i + 3]);
+    const float2 wlo = make_float2(w.x, w.y), whi = make_float2(w.z, w.w);
+    acc[0][2 * i] = __ffma2_rn(a0, wlo, acc[0][2 * i]);
+    acc[1][2 * i] = __ffma2_rn(a1, wlo, acc[1][2 * i]);
+    acc[0][2 * i + 1] = __ffma2_rn(a0, whi, acc[0][2 * i + 1]);
+    acc[1][2 * i + 1] = __ffma2_rn(a1, whi, acc[1][2 * i + 1]);
   }
 }
+template <int NOUT>
+__device__ __forceinline__ void load_bias(float2 (&acc)[2][NOUT / 2], const float* __restrict__ b) {
+#pragma unroll
+  for (int i = 0; i < NOUT / 2; ++i) acc[0][i] = acc[1][i] = make_float2(b[2 * i], b[2 * i + 1]);
+}
+// element k of a float2-packed activation vector
+#define NB_EL(v, k) (((k) & 1) ? (v)[(k) >> 1].y : (v)[(k) >> 1].x)
 // packed parameter index (network_eval.cu:48-52 order) -> padded shared-memory index
 __device__ __forceinline__ int sm_index(int i) {
   if (i < kOffL2) return i;                                  // layers 0, 1 unchanged
@@ -266,7 +277,11 @@ eval_kernel(const int32_t* __restrict__ query, const int32_t* __restrict__ sorte
   __shared__ float dom[6];
   const int n_items = counters[C_ITEMS];
   int cached_net = -1;
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+  // contiguous item ranges per block: consecutive items mostly belong to the same network, so its 25 KB of
+  // weights are staged once per run of items instead of once per item (a grid-stride walk changed network every time)
+  const int per_block = (n_items + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int item_end = min(n_items, ((int)blockIdx.x + 1) * per_block);
+  for (int item = (int)blockIdx.x * per_block; item < item_end; ++item) {
     // network of this item: last n with item_start[n] <= item
     int lo = 0, hi = num_networks;
     while (hi - lo > 1) {
@@ -313,9 +328,8 @@ eval_kernel(const int32_t* __restrict__ query, const int32_t* __restrict__ sorte
       }
     }
     // layer 0: 63 -> 32
-    float h0[2][32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) h0[0][i] = h0[1][i] = w[kSmL0 + i];
+    float2 h0[2][16];
+    load_bias<32>(h0, w + kSmL0);
 #pragma unroll 1
     for (int j = 0; j < 3; ++j) {
       float e0[21], e1[21];
@@ -326,23 +340,20 @@ eval_kernel(const int32_t* __restrict__ query, const int32_t* __restrict__ sorte
       for (int e = 0; e < 21; ++e) fma_row<32>(h0, wr + e * 32, e0[e], e1[e]);
     }
     // layer 1: 32 -> 32 (relu on the input)
-    float h1[2][32];
+    float2 h1[2][16];
+    load_bias<32>(h1, w + kSmL1);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) h1[0][i] = h1[1][i] = w[kSmL1 + i];
-#pragma unroll
-    for (int k = 0; k < 32; ++k) fma_row<32>(h1, w + kSmL1 + 32 + k * 32, fmaxf(h0[0][k], 0.f), fmaxf(h0[1][k], 0.f));
+    for (int k = 0; k < 32; ++k) fma_row<32>(h1, w + kSmL1 + 32 + k * 32, fmaxf(NB_EL(h0[0], k), 0.f), fmaxf(NB_EL(h0[1], k), 0.f));
     // layer 2: 32 -> 33 (output 0 = density, 1..32 = feature, no activation on the feature)
-    float h2[2][36];
+    float2 h2[2][18];
+    load_bias<36>(h2, w + kSmL2);
 #pragma unroll
-    for (int i = 0; i < 36; ++i) h2[0][i] = h2[1][i] = w[kSmL2 + i];
-#pragma unroll
-    for (int k = 0; k < 32; ++k) fma_row<36>(h2, w + kSmL2 + 36 + k * 36, fmaxf(h1[0][k], 0.f), fmaxf(h1[1][k], 0.f));
+    for (int k = 0; k < 32; ++k) fma_row<36>(h2, w + kSmL2 + 36 + k * 36, fmaxf(NB_EL(h1[0], k), 0.f), fmaxf(NB_EL(h1[1], k), 0.f));
     // layer 3: feature(32) | dir embedding(27) -> 32
-    float (&h3)[2][32] = h0;
+    float2 (&h3)[2][16] = h0;
+    load_bias<32>(h3, w + kSmL3);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) h3[0][i] = h3[1][i] = w[kSmL3 + i];
-#pragma unroll
-    for (int k = 0; k < 32; ++k) fma_row<32>(h3, w + kSmL3 + 32 + k * 32, h2[0][k + 1], h2[1][k + 1]);
+    for (int k = 0; k < 32; ++k) fma_row<32>(h3, w + kSmL3 + 32 + k * 32, NB_EL(h2[0], k + 1), NB_EL(h2[1], k + 1));
 #pragma unroll 1
     for (int j = 0; j < 3; ++j) {
       float e0[9], e1[9];
@@ -353,16 +364,15 @@ eval_kernel(const int32_t* __restrict__ query, const int32_t* __restrict__ sorte
       for (int e = 0; e < 9; ++e) fma_row<32>(h3, wr + e * 32, e0[e], e1[e]);
     }
     // layer 4: 32 -> 3, sigmoid; density relu
-    float rgb[2][4];
+    float2 rgb[2][2];
+    load_bias<4>(rgb, w + kSmL4);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) rgb[0][i] = rgb[1][i] = w[kSmL4 + i];
-#pragma unroll
-    for (int k = 0; k < 32; ++k) fma_row<4>(rgb, w + kSmL4 + 4 + k * 4, fmaxf(h3[0][k], 0.f), fmaxf(h3[1][k], 0.f));
+    for (int k = 0; k < 32; ++k) fma_row<4>(rgb, w + kSmL4 + 4 + k * 4, fmaxf(NB_EL(h3[0], k), 0.f), fmaxf(NB_EL(h3[1], k), 0.f));
 #pragma unroll
     for (int s = 0; s < 2; ++s)
       if (slot[s] >= 0)
-        rgb_sigma[slot[s]] = make_float4(1.f / (1.f + expf(-rgb[s][0])), 1.f / (1.f + expf(-rgb[s][1])),
-                                         1.f / (1.f + expf(-rgb[s][2])), fmaxf(h2[s][0], 0.f));
+        rgb_sigma[slot[s]] = make_float4(1.f / (1.f + expf(-rgb[s][0].x)), 1.f / (1.f + expf(-rgb[s][0].y)),
+                                         1.f / (1.f + expf(-rgb[s][1].x)), fmaxf(h2[s][0].x, 0.f));
   }
 }
 
