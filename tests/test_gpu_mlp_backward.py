@@ -177,3 +177,29 @@ def test_mlp_backward_vs_oracle_autograd():
         # activations: ~1e-1 relative on a 4096-row batch; the heads see one rounding
         lim = (0.99, 0.15) if name.startswith("pts_linears.") else (0.995, 0.1)
         assert cos > lim[0] and rel < lim[1], (name, cos, rel)
+
+
+def test_mlp_backward_full_batch_is_additive_over_rays():
+    """BASELINE configs[2] size (4096 rays x 192 fine rows = 786 432 MLP rows, every CTA pair busy, thousands of
+    red.global.add flushes): the weight gradients of the whole batch equal the sum over two half batches run
+    separately -- a size-independent property of the split-K reduction (row-to-tile assignment differs)."""
+    sd, r = _renderer(seed=5)
+    n, S = 4096, 192
+    ro, rd, z = _rays(1600, S, seed=4)
+    idx = torch.arange(n, device=DEV) % 1600
+    ro, rd, z = ro[idx].contiguous(), rd[idx].contiguous(), (z[idx] + 0.001 * torch.rand(n, S, device=DEV)).contiguous()
+    g_raw = (torch.randn(n * S, 4, generator=torch.Generator().manual_seed(9)) * 0.05).to(DEV)
+    pk, bw = r.packed("fine", "bf16"), r.packed_bwd("fine")
+
+    def run(lo, hi):
+        raw, store = ops.mlp_forward_train(pk, ro[lo:hi], rd[lo:hi], z[lo:hi])
+        return ops.mlp_backward(bw, g_raw[lo * S:hi * S], store)
+
+    full = run(0, n)
+    a, b = run(0, 1999), run(1999, n)          # odd split: the second half starts in the middle of a 128-row tile
+    torch.cuda.synchronize()
+    for name, g, ga, gb in zip(T._NAMES, full, a, b):
+        want = ga + gb
+        rel = float((g - want).norm() / (want.norm() + 1e-30))
+        assert rel < 2e-4, (name, rel)
+        assert bool(torch.isfinite(g).all()), name
