@@ -97,11 +97,11 @@ def lego_pose(i):
     4.03, elevation 30 deg; frame 0 is oracle.LEGO_TEST_POSE0).  Synthetic poses of that shape."""
     import math
     import torch
-    from oracle import nerf_oracle as O
+    import fixtures as FX
     if i == 0:
-        return torch.tensor(O.LEGO_TEST_POSE0, dtype=torch.float32)
+        return torch.tensor(FX.LEGO_TEST_POSE0, dtype=torch.float32)
     th = 2 * math.pi * i / 200.0
-    base = torch.tensor(O.LEGO_TEST_POSE0, dtype=torch.float32)
+    base = torch.tensor(FX.LEGO_TEST_POSE0, dtype=torch.float32)
     c, s = math.cos(th), math.sin(th)
     rot = torch.tensor([[c, -s, 0, 0], [s, c, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]], dtype=torch.float32)
     return rot @ base
@@ -177,8 +177,8 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from oracle import nerf_oracle as O          # weights + camera fixtures only (and cpu_baseline)
-    from nerf_rep_for_test_b200 import Network, RenderConfig, Renderer, lib as L
+    import fixtures as FX                        # synthetic weights / cameras / scenes (data only, no oracle)
+    from nerf_rep_for_test_b200 import Network, RenderConfig, Renderer, lib as L, ops
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -202,12 +202,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    sd = O.make_state_dict(0)
+    sd = FX.make_state_dict(0)
     net = Network(device=dev)
     net.load_state_dict(sd)
     net.to(dev).eval()
     r = Renderer(net, RenderConfig(perturb=0, enable_ess=False, enable_ert=False), mode=args.mode)
-    K0 = O.lego_batch(H, W)["intrinsics"]
+    K0 = FX.lego_batch(H, W)["intrinsics"]
     # one view per rank per step (weak scaling); device-resident for `value`, host for `e2e`
     n_views = args.warmup + args.steps
     host_batches = [{"pose": lego_pose(rank + world * i)[None], "intrinsics": K0.clone(), "H": H, "W": W}
@@ -261,9 +261,9 @@ def run_ours(args):
         r.perturb = 1
         step = T.TrainStep(r)
         g = torch.Generator().manual_seed(rank)
-        ro_all, rd_all = O.get_rays(H, W, lego_pose(rank), K0[0])
-        sel = torch.randint(0, H * W, (args.train_rays,), generator=g)
-        tro, trd = ro_all[sel].to(dev), rd_all[sel].to(dev)
+        ro_all, rd_all = ops.raygen(lego_pose(rank).to(dev), K0[0].to(dev), H, W)
+        sel = torch.randint(0, H * W, (args.train_rays,), generator=g).to(dev)
+        tro, trd = ro_all[sel].contiguous(), rd_all[sel].contiguous()
         target = torch.rand(args.train_rays, 3, generator=g).to(dev)
         for _ in range(args.train_warmup):
             step(tro, trd, target)
@@ -284,7 +284,7 @@ def run_ours(args):
     # the skip path never sends empty / terminated samples through the MLP.
     cfg5 = None
     if args.config5 and rank == 0:
-        sd5 = O.make_state_dict(6, 300.0, 6.0)
+        sd5 = FX.make_state_dict(6, 300.0, 6.0)
         for k in list(sd5):
             if k.startswith("model_fine."):
                 sd5[k] = sd5["model." + k[len("model_fine."):]].clone()
@@ -317,9 +317,8 @@ def run_ours(args):
     # weights), 128^3 occupancy grid of network ids, fixed-step march + early ray termination; same camera.
     kilo_cfg = None
     if args.config5 and rank == 0:
-        from oracle import kilo_oracle as KO
         from nerf_rep_for_test_b200 import kilo
-        sc = KO.make_scene(seed=0, net_res=16, grid_res=128, blob_radius=1.0)
+        sc = FX.make_kilo_scene(seed=0, net_res=16, grid_res=128, blob_radius=1.0)
         dbp, max_depth, min_d, spp = 4.0 / 384, 384, 2.0, 32
         kr = kilo.KiloRenderer(sc["grid"], sc["params"], sc["domain_mins"], sc["domain_maxs"], sc["gmin"], sc["gmax"], dbp,
                                max_depth, min_d, max_samples_per_ray=spp, device=dev)
@@ -329,8 +328,9 @@ def run_ours(args):
         l0 = L.launch_count()
         kms = timed(kr.render, dev_batches[:3]) / 3
         samples = float(kr.stats[0]) / 3
-        # CPU: the numpy oracle of the same kernels on a 64x64 view of the same scene
-        b64 = O.lego_batch(64, 64)
+        # CPU leg: the numpy oracle of the same kernels on a 64x64 view of the same scene
+        from oracle import kilo_oracle as KO
+        b64 = FX.lego_batch(64, 64)
         pose64, K64 = b64["pose"][0].numpy(), b64["intrinsics"][0].numpy()
         t0 = time.perf_counter()
         _, _, ev64 = KO.render(64, 64, float(K64[0, 2]), float(K64[1, 2]), float(K64[0, 0]), float(K64[1, 1]), pose64[:3, :3],

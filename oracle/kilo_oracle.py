@@ -19,7 +19,12 @@ oracle/_ref/ so the GPU tests can run the reference's own kernels next to ours o
 Known, tolerated difference: the reference evaluates cos/sin with the fast __cosf/__sinf intrinsics on
 arguments up to 512 rad (network_eval.cu:136-139); this oracle uses exact float32 cos/sin.
 """
+import os as _os
+import sys as _sys
+
 import numpy as np
+
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
 
 F = np.float32
 HIDDEN = 32
@@ -198,30 +203,4 @@ def render(H, W, cx, cy, fx, fy, c2w, origin, grid, params, domain_mins, domain_
     return rgb_map, acc_map, evaluated
 
 
-def make_scene(seed=0, net_res=16, grid_res=128, blob_radius=0.7, sigma_scale=40.0):
-    """Synthetic config-5 scene: [-1.5,1.5]^3 domain, net_res^3 micro-MLPs with random weights, occupancy =
-    cells whose centre lies in a sphere (network id = the net_res^3 cell containing it), -1 elsewhere."""
-    rs = np.random.RandomState(seed)
-    gmin, gmax = np.array([-1.5, -1.5, -1.5], F), np.array([1.5, 1.5, 1.5], F)
-    nn = net_res ** 3
-    params = np.zeros((nn, PARAM_SIZE), F)
-    o = 0
-    for nin, nout in ((POS_EMB, HIDDEN), (HIDDEN, HIDDEN), (HIDDEN, HIDDEN + 1), (HIDDEN + DIR_EMB, HIDDEN), (HIDDEN, 3)):
-        bound = 1.0 / np.sqrt(nin)
-        size = nout + nin * nout
-        params[:, o:o + size] = rs.uniform(-bound, bound, size=(nn, size)).astype(F)
-        if nout == HIDDEN + 1:      # density output: positive and large so early termination happens
-            params[:, o] = F(0.5)
-            params[:, o + nout:o + size:nout] *= F(0.1)
-            params[:, o] *= F(sigma_scale)
-        o += size
-    c = (np.arange(grid_res, dtype=F) + F(0.5)) / F(grid_res)
-    g = np.stack(np.meshgrid(c, c, c, indexing="ij"), -1) * (gmax - gmin) + gmin
-    occ = np.sqrt((g * g).sum(-1)) <= blob_radius
-    cell = np.arange(grid_res) // (grid_res // net_res)
-    net_id = (cell[:, None, None] * net_res + cell[None, :, None]) * net_res + cell[None, None, :]
-    grid = np.where(occ, net_id, -1).astype(np.int16)
-    k = np.arange(net_res, dtype=F)
-    lo = np.stack(np.meshgrid(k, k, k, indexing="ij"), -1).reshape(-1, 3) / F(net_res) * (gmax - gmin) + gmin
-    hi = lo + (gmax - gmin) / F(net_res)
-    return dict(grid=grid, params=params, domain_mins=lo.astype(F), domain_maxs=hi.astype(F), gmin=gmin, gmax=gmax)
+from fixtures import make_kilo_scene as make_scene  # noqa: E402,F401  (synthetic scene: data only)

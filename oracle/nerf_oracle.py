@@ -27,61 +27,13 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-# lego.yaml / volume_renderer.py:31-54 defaults
-N_SAMPLES = 64
-N_IMPORTANCE = 128
-NEAR, FAR = 2.0, 6.0
-L_XYZ, L_DIR = 10, 4
-W_HID, D_LAYERS, SKIP = 256, 8, 4
-CH_XYZ = 3 + 3 * 2 * L_XYZ   # 63
-CH_DIR = 3 + 3 * 2 * L_DIR   # 27
+import os as _os
+import sys as _sys
 
-
-# ---------------------------------------------------------------------------
-# weights: same tensors / names / shapes as network.py:22-47 (state_dict frozen)
-# ---------------------------------------------------------------------------
-def state_dict_shapes():
-    shapes = {}
-    for prefix in ("model.", "model_fine."):
-        for i in range(D_LAYERS):
-            fin = CH_XYZ if i == 0 else (W_HID + CH_XYZ if i == SKIP + 1 else W_HID)
-            shapes[prefix + "pts_linears.%d.weight" % i] = (W_HID, fin)
-            shapes[prefix + "pts_linears.%d.bias" % i] = (W_HID,)
-        shapes[prefix + "views_linears.0.weight"] = (W_HID // 2, W_HID + CH_DIR)
-        shapes[prefix + "views_linears.0.bias"] = (W_HID // 2,)
-        shapes[prefix + "feature_linear.weight"] = (W_HID, W_HID)
-        shapes[prefix + "feature_linear.bias"] = (W_HID,)
-        shapes[prefix + "alpha_linear.weight"] = (1, W_HID)
-        shapes[prefix + "alpha_linear.bias"] = (1,)
-        shapes[prefix + "rgb_linear.weight"] = (3, W_HID // 2)
-        shapes[prefix + "rgb_linear.bias"] = (3,)
-    return shapes
-
-
-def make_state_dict(seed=0, sigma_gain=1.0, sigma_bias=0.0):
-    """Deterministic random-init weights, independent of torch's RNG.
-
-    Same distribution as nn.Linear's default init (U(-1/sqrt(fan_in), +), used by
-    network.py:22-47) but drawn from numpy's frozen legacy MT19937 stream so the
-    fixture is reproducible on any box.  `sigma_gain/sigma_bias` rescale
-    alpha_linear so density is large enough to exercise compositing / ERT /
-    a peaked sample_pdf (random init alone gives sigma ~ 0.02, SURVEY 8c').
-    """
-    rs = np.random.RandomState(seed)
-    sd = {}
-    for name, shape in state_dict_shapes().items():
-        fan_in = shape[1] if len(shape) == 2 else None
-        if fan_in is None:
-            wname = name.replace(".bias", ".weight")
-            fan_in = state_dict_shapes()[wname][1]
-        bound = 1.0 / math.sqrt(fan_in)
-        arr = rs.uniform(-bound, bound, size=shape).astype(np.float32)
-        if "alpha_linear" in name:
-            arr = arr * np.float32(sigma_gain)
-            if name.endswith("bias"):
-                arr = arr + np.float32(sigma_bias)
-        sd[name] = torch.from_numpy(arr)
-    return sd
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
+# synthetic inputs (weights, camera) live in fixtures.py so that the product benchmark never needs this module
+from fixtures import (CH_DIR, CH_XYZ, D_LAYERS, FAR, L_DIR, L_XYZ, LEGO_CAMERA_ANGLE_X, LEGO_TEST_POSE0, N_IMPORTANCE,  # noqa: E402,F401
+                      N_SAMPLES, NEAR, SKIP, W_HID, lego_batch, make_state_dict, state_dict_shapes)
 
 
 # ---------------------------------------------------------------------------
@@ -410,22 +362,3 @@ def render(sd, batch, **kw):
     for k in outs:
         outs[k] = outs[k].view(H, W, 3) if k in ("rgb_map", "rgb_map_0") else outs[k].view(H, W)
     return (outs, aux) if aux is not None else outs
-
-
-# lego transforms_test.json frame 0 (data/nerf_synthetic/lego/transforms_test.json),
-# camera_angle_x = 0.6911112070083618 -- the pose BASELINE.md section 3 names.
-LEGO_TEST_POSE0 = [
-    [-0.9999999403953552, 0.0, 0.0, 0.0],
-    [0.0, -0.7341099977493286, 0.6790305972099304, 2.737260103225708],
-    [0.0, 0.6790306568145752, 0.7341098785400391, 2.959291696548462],
-    [0.0, 0.0, 0.0, 1.0],
-]
-LEGO_CAMERA_ANGLE_X = 0.6911112070083618
-
-
-def lego_batch(H, W, pose=None):
-    """Batch dict as blender.py:42,120-124 builds it."""
-    pose = torch.tensor(LEGO_TEST_POSE0 if pose is None else pose, dtype=torch.float32)
-    focal = 0.5 * W / np.tan(0.5 * LEGO_CAMERA_ANGLE_X)
-    K = torch.tensor([[focal, 0, W / 2], [0, focal, H / 2], [0, 0, 1]], dtype=torch.float32)
-    return {"pose": pose[None], "intrinsics": K[None], "H": H, "W": W}
