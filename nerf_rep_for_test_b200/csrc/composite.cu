@@ -69,7 +69,8 @@ __device__ __forceinline__ void ray_alpha_T(const float* __restrict__ raw_row,
       float dist = (i + 1 < S) ? __fsub_rn(z_row[i + 1], z0) : 1e10f;
       dist = __fmul_rn(dist, dnorm);
       float sig = fmaxf(raw_row[(size_t)i * 4 + 3], 0.f);
-      a = __fsub_rn(1.f, exp_cr(__fmul_rn(-sig, dist)));
+      // sigma == 0 (empty / skipped sample): exp(-0) = 1 and alpha = 0 exactly -- no fp64 exp needed
+      a = sig == 0.f ? 0.f : __fsub_rn(1.f, exp_cr(__fmul_rn(-sig, dist)));
       f = kErt ? __fsub_rn(1.f, a) : __fadd_rn(__fsub_rn(1.f, a), 1e-10f);
       local *= (double)f;
     }
@@ -111,13 +112,15 @@ __device__ __forceinline__ void ray_outputs(const RaySamples& rs, const float* _
     if (j < per && i < S) {
       float w = __fmul_rn(rs.alpha[j], rs.T[j]);
       if (i >= cut) w = __fmul_rn(w, 0.f);  // weights * (~mask).float()
-      float4 r4 = *reinterpret_cast<const float4*>(raw_row + (size_t)i * 4);
-      float cr = sigmoid_ref(r4.x), cg = sigmoid_ref(r4.y), cb = sigmoid_ref(r4.z);
-      sr += (double)__fmul_rn(w, cr);
-      sg += (double)__fmul_rn(w, cg);
-      sb += (double)__fmul_rn(w, cb);
-      sd += (double)__fmul_rn(w, z_row[i]);
-      sa += (double)w;
+      if (w != 0.f) {   // w == +0: every product below is +0 exactly (sigmoid and z are finite), skip the three exps
+        float4 r4 = *reinterpret_cast<const float4*>(raw_row + (size_t)i * 4);
+        float cr = sigmoid_ref(r4.x), cg = sigmoid_ref(r4.y), cb = sigmoid_ref(r4.z);
+        sr += (double)__fmul_rn(w, cr);
+        sg += (double)__fmul_rn(w, cg);
+        sb += (double)__fmul_rn(w, cb);
+        sd += (double)__fmul_rn(w, z_row[i]);
+        sa += (double)w;
+      }
       if (weights) weights[ray * S + i] = w;
     }
   }
