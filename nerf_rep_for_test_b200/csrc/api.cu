@@ -69,7 +69,10 @@ constexpr int kChunkRays = 8192;
 // wave of the persistent kernel (measured: 22.9 ms per frame at 8192, 17.5 ms at 131 072 rays per chunk); the
 // dense path is insensitive to the chunk size (136.8 ms at 8192, 135.9 ms at 32 768).
 constexpr int kChunkRaysSparse = 131072;
-static int chunk_rays(const nerfb200_render_params* p) { return (p->occupancy_grid && p->ess_skip) ? kChunkRaysSparse : kChunkRays; }
+static int chunk_rays(const nerfb200_render_params* p) {
+  if (const char* e = getenv("NERFB200_CHUNK_RAYS")) { int c = atoi(e); if (c >= 2048 && c % 2048 == 0) return c; }   // tuning experiments
+  return (p->occupancy_grid && p->ess_skip) ? kChunkRaysSparse : kChunkRays;
+}
 
 struct Workspace {
   float* z_coarse;  // [c,S]
