@@ -1,0 +1,78 @@
+"""GPU: error behaviour of the C ABI entry points added for a7 / a9 -- a bad argument is a non-zero return with
+a message (NerfB200Error here), never a crash or a silent no-op; empty inputs are accepted."""
+import ctypes as C
+
+import pytest
+import torch
+
+import fixtures as FX
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from nerf_rep_for_test_b200 import Network, RenderConfig, Renderer, kilo, lib as L, ops
+    DEV = torch.device("cuda:0")
+
+
+def _renderer():
+    net = Network(device=DEV)
+    net.load_state_dict(FX.make_state_dict(1))
+    return Renderer(net.to(DEV).eval(), RenderConfig(perturb=0, enable_ess=False, enable_ert=False), mode="bf16")
+
+
+def test_mlp_backward_argument_checks():
+    r = _renderer()
+    ro = torch.zeros(3, 3, device=DEV); rd = torch.ones(3, 3, device=DEV) / 3 ** 0.5
+    z = torch.linspace(2, 6, 64, device=DEV).expand(3, 64).contiguous()
+    raw, store = ops.mlp_forward_train(r.packed("coarse", "bf16"), ro, rd, z)
+    with pytest.raises(L.NerfB200Error):                      # g_raw of the wrong batch
+        ops.mlp_backward(r.packed_bwd("coarse"), torch.zeros(5, 4, device=DEV), store)
+    with pytest.raises(L.NerfB200Error):                      # gradient buffers of the wrong shape
+        ops.mlp_backward(r.packed_bwd("coarse"), torch.zeros(192, 4, device=DEV), store,
+                         grads=[torch.zeros(7, device=DEV)] * 24)
+    with pytest.raises(L.NerfB200Error):                      # CPU tensors are rejected: there is no CPU path
+        ops.mlp_backward(r.packed_bwd("coarse"), torch.zeros(192, 4), store)
+    lib = L.load()
+    packed_bwd, w = r.packed_bwd("coarse")
+    g = L.MlpGrads()
+    # workspace too small / null gradient pointers -> error code + message, nothing launched
+    rc = lib.nerfb200_mlp_backward(packed_bwd, C.byref(w), L.dev(torch.zeros(192, 4, device=DEV)), L.dev(store.acts), L.dev(store.masks),
+                                   192, L.dev(torch.zeros(256, dtype=torch.uint8, device=DEV)), 256, C.byref(g), L.stream_ptr())
+    assert rc != 0 and b"null gradient" in lib.nerfb200_get_last_error_string()
+    grads = ops.mlp_backward(r.packed_bwd("coarse"), torch.zeros(192, 4, device=DEV), store)      # zero upstream gradient
+    torch.cuda.synchronize()
+    assert all(float(t.abs().max()) == 0.0 for t in grads)
+
+
+def test_mlp_forward_train_rejects_fp32_mode_and_accepts_empty():
+    r = _renderer()
+    lib = L.load()
+    z = torch.zeros(0, 64, device=DEV)
+    raw, store = ops.mlp_forward_train(r.packed("coarse", "bf16"), torch.zeros(0, 3, device=DEV), torch.zeros(0, 3, device=DEV), z)
+    assert raw.shape == (0, 64, 4) and store.acts.numel() == 0
+    pk = r.packed("coarse", "fp32")
+    rc = lib.nerfb200_mlp_forward_train(pk.ptr, L.MODE_FP32, None, None, None, 1, 64, None, None, None, L.stream_ptr())
+    assert rc != 0
+
+
+def test_kilo_argument_checks():
+    sc = FX.make_kilo_scene(seed=0, net_res=4, grid_res=16)
+    with pytest.raises(L.NerfB200Error):                      # parameter block of the wrong size
+        kilo.KiloRenderer(sc["grid"], sc["params"][:, :100], sc["domain_mins"], sc["domain_maxs"], sc["gmin"], sc["gmax"], 0.01, 384, 2.0, device=DEV)
+    r = kilo.KiloRenderer(sc["grid"], sc["params"], sc["domain_mins"], sc["domain_maxs"], sc["gmin"], sc["gmax"], 0.01, 384, 2.0, device=DEV)
+    b = FX.lego_batch(8, 8)
+    out = r.render({k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in b.items()})
+    torch.cuda.synchronize()
+    assert out["rgb_map"].shape == (8, 8, 3) and bool(torch.isfinite(out["rgb_map"]).all())
+    r.dbp = -1.0                                              # non-positive step
+    with pytest.raises(L.NerfB200Error):
+        r.render({k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in b.items()})
+    r.dbp, r.max_depth = 0.01, 1 << 22                        # H*W*max_depth overflows the int32 query index at 800x800
+    b800 = FX.lego_batch(800, 800)
+    with pytest.raises(L.NerfB200Error):
+        r.render({k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in b800.items()})
+    # grid on the wrong device / dtype
+    with pytest.raises(L.NerfB200Error):
+        kilo.generate_query_indices_on_ray([0, 0, 4], torch.zeros(4, 3, device=DEV), torch.zeros(4, 4, 4, dtype=torch.int32, device=DEV),
+                                           torch.ones(4, dtype=torch.uint8, device=DEV), torch.zeros(4, dtype=torch.int32, device=DEV),
+                                           [-1, -1, -1], [1, 1, 1], 0.01, 4, 16, 2.0, True)
