@@ -49,6 +49,9 @@ extern "C" {
 #define NERFB200_COMPOSITE_PLAIN 0     /* _raw2outputs, volume_renderer.py:286-357 (T uses 1-alpha+1e-10) */
 #define NERFB200_COMPOSITE_ERT 1       /* _raw2outputs_with_ert intended semantics: zero weights from first T<thr */
 #define NERFB200_COMPOSITE_ERT_COMPAT 2 /* ... literal :1115-1123 incl. the chunk-wide argmax quirk (2048-ray chunks) */
+/* OR-ed into PLAIN / ERT: fast exp / sigmoid (MUFU) instead of the fp64-exact ones that reproduce the CPU
+ * reference bit for bit; differences <= 1e-6 on the maps.  The bf16 mode uses it, the fp32 parity mode does not. */
+#define NERFB200_COMPOSITE_FAST_MATH 0x10
 
 /* network.py:22-47 -- the 24 fp32 tensors of ONE NeRF model in nn.Linear layout
  * ([out,in] row-major weight, [out] bias); state_dict names in comments. */

@@ -114,8 +114,9 @@ static int check_params(const nerfb200_render_params* p) {
   NB_CHECK_ARG(p->n_importance >= 0 && p->n_importance <= 256 && p->n_samples + p->n_importance <= 256,
                "render: n_importance=%d out of range (n_samples+n_importance <= 256)", p->n_importance);
   NB_CHECK_ARG(p->mode == NERFB200_MODE_FP32 || p->mode == NERFB200_MODE_BF16, "render: unknown mode %d", p->mode);
-  NB_CHECK_ARG(p->variant >= 0 && p->variant <= 2, "render: unknown composite variant %d", p->variant);
-  NB_CHECK_ARG(p->variant != NERFB200_COMPOSITE_ERT_COMPAT || (p->compat_chunk > 0 && kChunkRays % p->compat_chunk == 0),
+  NB_CHECK_ARG((p->variant & ~NERFB200_COMPOSITE_FAST_MATH) >= 0 && (p->variant & ~NERFB200_COMPOSITE_FAST_MATH) <= 2,
+               "render: unknown composite variant %d", p->variant);
+  NB_CHECK_ARG((p->variant & ~NERFB200_COMPOSITE_FAST_MATH) != NERFB200_COMPOSITE_ERT_COMPAT || (p->compat_chunk > 0 && kChunkRays % p->compat_chunk == 0),
                "render: compat_chunk=%d must divide %d", p->compat_chunk, kChunkRays);
   static_assert(kChunkRaysSparse % kChunkRays == 0, "chunk sizes");
   return 0;
@@ -297,7 +298,7 @@ extern "C" int nerfb200_render_rays(const void* packed_coarse, const void* packe
         // fine pass: skip samples in empty cells and, with ERT, samples behind the depth at which the
         // coarse transmittance fell below the threshold
         const float* zt = nullptr;
-        if (p->variant != NERFB200_COMPOSITE_PLAIN) {
+        if ((p->variant & ~NERFB200_COMPOSITE_FAST_MATH) != NERFB200_COMPOSITE_PLAIN) {
           if ((e = nerfb200_ert_depth(ws.weights, ws.z_coarse, n, S, p->ert_threshold, ws.z_term, stream))) return e;
           zt = ws.z_term;
         }

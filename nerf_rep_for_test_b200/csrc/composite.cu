@@ -18,9 +18,14 @@ constexpr int kMaxPer = 8;  // ceil(S/32) <= 8  => S <= 256
 // rounding the fp64 exp matches it on 96.5-99% of arguments while CUDA's expf matches only
 // 60-70% (scripts/probe_exp.py on the B200 box).  alpha = 1 - exp(-x) cancels, so each mismatch
 // costs ulp(1) absolute on alpha.  sigmoid on CPU is 1/(1+exp(-x)) in fp32 steps.
-__device__ __forceinline__ float exp_cr(float x) { return (float)exp((double)x); }
+// kFast (NERFB200_COMPOSITE_FAST_MATH, used by the bf16 mode whose MLP outputs carry 1e-3 already): MUFU-based
+// __expf / __fdividef instead of the fp64 exp -- the exact variant spends 4 fp64 exps per sample and reaches
+// only 0.22-0.26 of the HBM roofline at full-frame size (scripts/stream_kernels.py).
+template <bool kFast>
+__device__ __forceinline__ float exp_cr(float x) { return kFast ? __expf(x) : (float)exp((double)x); }
+template <bool kFast>
 __device__ __forceinline__ float sigmoid_ref(float x) {
-  return __fdiv_rn(1.f, __fadd_rn(1.f, exp_cr(-x)));
+  return kFast ? __fdividef(1.f, 1.f + __expf(-x)) : __fdiv_rn(1.f, __fadd_rn(1.f, exp_cr<false>(-x)));
 }
 
 __device__ __forceinline__ float ray_norm(const float* __restrict__ d) {
@@ -54,7 +59,7 @@ struct RaySamples {
 };
 
 // alpha + transmittance for the lane's samples.  eps = 1e-10 (PLAIN) or 0 (ERT variants).
-template <bool kErt>
+template <bool kErt, bool kFast = false>
 __device__ __forceinline__ void ray_alpha_T(const float* __restrict__ raw_row,
                                             const float* __restrict__ z_row, float dnorm, int S,
                                             int per, int lane, float thr, RaySamples& rs) {
@@ -70,7 +75,7 @@ __device__ __forceinline__ void ray_alpha_T(const float* __restrict__ raw_row,
       dist = __fmul_rn(dist, dnorm);
       float sig = fmaxf(raw_row[(size_t)i * 4 + 3], 0.f);
       // sigma == 0 (empty / skipped sample): exp(-0) = 1 and alpha = 0 exactly -- no fp64 exp needed
-      a = sig == 0.f ? 0.f : __fsub_rn(1.f, exp_cr(__fmul_rn(-sig, dist)));
+      a = sig == 0.f ? 0.f : __fsub_rn(1.f, exp_cr<kFast>(__fmul_rn(-sig, dist)));
       f = kErt ? __fsub_rn(1.f, a) : __fadd_rn(__fsub_rn(1.f, a), 1e-10f);
       local *= (double)f;
     }
@@ -99,6 +104,7 @@ __device__ __forceinline__ void ray_alpha_T(const float* __restrict__ raw_row,
 }
 
 // cut = first sample index whose weight is forced to zero (S = none)
+template <bool kFast = false>
 __device__ __forceinline__ void ray_outputs(const RaySamples& rs, const float* __restrict__ raw_row,
                                             const float* __restrict__ z_row, int S, int per, int lane,
                                             int cut, int white_bkgd, size_t ray,
@@ -114,7 +120,7 @@ __device__ __forceinline__ void ray_outputs(const RaySamples& rs, const float* _
       if (i >= cut) w = __fmul_rn(w, 0.f);  // weights * (~mask).float()
       if (w != 0.f) {   // w == +0: every product below is +0 exactly (sigmoid and z are finite), skip the three exps
         float4 r4 = *reinterpret_cast<const float4*>(raw_row + (size_t)i * 4);
-        float cr = sigmoid_ref(r4.x), cg = sigmoid_ref(r4.y), cb = sigmoid_ref(r4.z);
+        float cr = sigmoid_ref<kFast>(r4.x), cg = sigmoid_ref<kFast>(r4.y), cb = sigmoid_ref<kFast>(r4.z);
         sr += (double)__fmul_rn(w, cr);
         sg += (double)__fmul_rn(w, cg);
         sb += (double)__fmul_rn(w, cb);
@@ -142,7 +148,7 @@ __device__ __forceinline__ void ray_outputs(const RaySamples& rs, const float* _
 }
 
 // PLAIN and ERT: one warp per ray
-template <bool kErt>
+template <bool kErt, bool kFast>
 __global__ void __launch_bounds__(kCompWarps * 32)
 composite_kernel(const float* __restrict__ raw, const float* __restrict__ z_vals,
                  const float* __restrict__ rays_d, int n_rays, int S, float thr, int white_bkgd,
@@ -156,9 +162,9 @@ composite_kernel(const float* __restrict__ raw, const float* __restrict__ z_vals
   const float* raw_row = raw + ray * S * 4;
   const float* z_row = z_vals + ray * S;
   RaySamples rs;
-  ray_alpha_T<kErt>(raw_row, z_row, ray_norm(rays_d + ray * 3), S, per, lane, thr, rs);
-  ray_outputs(rs, raw_row, z_row, S, per, lane, rs.first_low, white_bkgd, ray, rgb_map, disp_map,
-              acc_map, depth_map, weights);
+  ray_alpha_T<kErt, kFast>(raw_row, z_row, ray_norm(rays_d + ray * 3), S, per, lane, thr, rs);
+  ray_outputs<kFast>(rs, raw_row, z_row, S, per, lane, rs.first_low, white_bkgd, ray, rgb_map, disp_map,
+                     acc_map, depth_map, weights);
 }
 
 // ERT_COMPAT: literal :1115-1123.  `if low.any()` is evaluated over the whole call (a
@@ -234,9 +240,9 @@ composite_backward_kernel(const float* __restrict__ raw, const float* __restrict
     G[j] = 0.f; w[j] = 0.f;
     if (j < per && i < S) {
       float4 r4 = *reinterpret_cast<const float4*>(raw_row + (size_t)i * 4);
-      c[j][0] = sigmoid_ref(r4.x);
-      c[j][1] = sigmoid_ref(r4.y);
-      c[j][2] = sigmoid_ref(r4.z);
+      c[j][0] = sigmoid_ref<false>(r4.x);
+      c[j][1] = sigmoid_ref<false>(r4.y);
+      c[j][2] = sigmoid_ref<false>(r4.z);
       w[j] = rs.alpha[j] * rs.T[j];
       G[j] = gr * c[j][0] + gg * c[j][1] + gb * c[j][2] + ga + gd * z_row[i] +
              (g_weights ? g_weights[ray * S + i] : 0.f);
@@ -290,16 +296,19 @@ extern "C" int nerfb200_composite_forward(const float* raw, const float* z_vals,
   NB_CHECK_ARG(n_samples >= 1 && n_samples <= 32 * kMaxPer, "composite_forward: n_samples=%d out of range [1,%d]",
                n_samples, 32 * kMaxPer);
   NB_CHECK_ARG(n_rays >= 0, "composite_forward: negative n_rays");
+  const bool fast = (variant & NERFB200_COMPOSITE_FAST_MATH) != 0;
+  variant &= ~NERFB200_COMPOSITE_FAST_MATH;
   NB_CHECK_ARG(variant >= 0 && variant <= 2, "composite_forward: unknown variant %d", variant);
   if (n_rays == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   int blocks = ceil_div(n_rays, kCompWarps);
+#define NB_COMPOSITE(ERT, FAST, THR)                                                                              \
+  composite_kernel<ERT, FAST><<<blocks, kCompWarps * 32, 0, st>>>(raw, z_vals, rays_d, n_rays, n_samples, THR, white_bkgd, \
+                                                                  rgb_map, disp_map, acc_map, depth_map, weights)
   if (variant == NERFB200_COMPOSITE_PLAIN) {
-    composite_kernel<false><<<blocks, kCompWarps * 32, 0, st>>>(raw, z_vals, rays_d, n_rays, n_samples, 0.f, white_bkgd,
-                                                               rgb_map, disp_map, acc_map, depth_map, weights);
+    if (fast) NB_COMPOSITE(false, true, 0.f); else NB_COMPOSITE(false, false, 0.f);
   } else if (variant == NERFB200_COMPOSITE_ERT) {
-    composite_kernel<true><<<blocks, kCompWarps * 32, 0, st>>>(raw, z_vals, rays_d, n_rays, n_samples, ert_threshold,
-                                                              white_bkgd, rgb_map, disp_map, acc_map, depth_map, weights);
+    if (fast) NB_COMPOSITE(true, true, ert_threshold); else NB_COMPOSITE(true, false, ert_threshold);
   } else {
     NB_CHECK_ARG(compat_chunk > 0, "composite_forward: compat_chunk must be > 0");
     composite_ert_compat_kernel<<<ceil_div(n_rays, compat_chunk), 1024, 0, st>>>(

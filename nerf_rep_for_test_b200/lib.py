@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get("NERFB200_LIB") or os.path.join(HERE, "libnerfb200.so"
 
 MODE_FP32, MODE_BF16 = 0, 1
 COMPOSITE_PLAIN, COMPOSITE_ERT, COMPOSITE_ERT_COMPAT = 0, 1, 2
+COMPOSITE_FAST_MATH = 0x10          # OR-ed into PLAIN / ERT (include/nerfb200.h)
 ABI_VERSION = 1
 
 _f = C.POINTER(C.c_float)

@@ -282,6 +282,8 @@ class Renderer:
                 if self.eval_counts is None:
                     self.eval_counts = torch.zeros(2, dtype=torch.int64, device=self.device)
                 p.eval_counts = self.eval_counts.data_ptr()
+        if self.mode == "bf16" and p.variant != L.COMPOSITE_ERT_COMPAT:
+            p.variant |= L.COMPOSITE_FAST_MATH     # the bf16 MLP output carries 1e-3 already: MUFU exp / sigmoid
         return p
 
     def _workspace(self, nbytes):

@@ -570,3 +570,20 @@ def test_perturbed_render_is_stratified_and_seeded():
     assert not torch.equal(a, c)                       # jitter differs call to call (as the reference's does)
     base = _renderer(sd, "fp32").render(bc)["rgb_map"]
     assert float((a - base).abs().mean()) < 0.05       # ... but it is the same image up to sampling noise
+
+
+def test_composite_fast_math_variant_matches_exact():
+    """NERFB200_COMPOSITE_FAST_MATH (MUFU exp / sigmoid, used by the bf16 mode) vs the fp64-exact compositor."""
+    g = torch.Generator().manual_seed(5)
+    n, S = 700, 192
+    raw = torch.cat([torch.randn(n, S, 3, generator=g), 3.0 * torch.randn(n, S, 1, generator=g)], -1).to(DEV)
+    z = torch.sort(2 + 4 * torch.rand(n, S, generator=g), -1)[0].to(DEV)
+    rd = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1).to(DEV)
+    for variant in (L.COMPOSITE_PLAIN, L.COMPOSITE_ERT):
+        exact = ops.composite_forward(raw, z, rd, variant)
+        fast = ops.composite_forward(raw, z, rd, variant | L.COMPOSITE_FAST_MATH)
+        for a, b, name in zip(exact, fast, ("rgb", "disp", "acc", "weights", "depth")):
+            if name == "disp":
+                continue                      # 1/(depth/acc): ill-conditioned where acc ~ 0, covered by depth and acc
+            scale = 6.0 if name == "depth" else 1.0
+            assert float((a - b).abs().max()) <= 4e-6 * scale, (variant, name, float((a - b).abs().max()))
