@@ -155,7 +155,8 @@ NERFB200_API int nerfb200_mlp_forward_stages(const void* packed, int mode, const
 /* ---- a5/a6: alpha compositing (volume_renderer.py:286-357, :1089-1157) ------------------- */
 /* raw [n_rays,S,4], z_vals [n_rays,S], rays_d [n_rays,3] -> rgb_map [n_rays,3], disp/acc/depth
  * [n_rays], weights [n_rays,S] (may be NULL).  One warp per ray, shuffle prefix product.
- * variant: NERFB200_COMPOSITE_*; ERT_COMPAT groups rays in chunks of compat_chunk (2048). */
+ * variant: NERFB200_COMPOSITE_* (PLAIN / ERT optionally OR-ed with NERFB200_COMPOSITE_FAST_MATH); ERT_COMPAT groups
+ * rays in chunks of compat_chunk (2048). */
 NERFB200_API int nerfb200_composite_forward(const float* raw, const float* z_vals, const float* rays_d,
                                int n_rays, int n_samples, int variant, float ert_threshold,
                                int white_bkgd, int compat_chunk, float* rgb_map, float* disp_map,
