@@ -291,7 +291,8 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
             tmem_ld32(t_acc + 128u, v);
             tmem_ld_wait();
             pin32(v);
-            sigma = __uint_as_float(v[0]) + bias4[32].x - tail[kTailAlphaB];   // alpha_b is added below
+            // columns 128 / 129 = h7 . (hi / lo bf16 parts of alpha_linear.weight), pack.cu
+            sigma = (__uint_as_float(v[0]) + __uint_as_float(v[1])) + bias4[32].x - tail[kTailAlphaB];   // alpha_b is added below
           }
           tc_fence_before();
           mbar_arrive(bar(BAR_BEMPTY + bbuf));

@@ -61,7 +61,8 @@ constexpr int kBf16TotalBytes = kBf16TailOff + kTailFloats * 4;
 // ---- fused inference tail (BF16): feature_linear has no activation, so for inference it is folded
 // into views_linears.0 (W' = Wv[:, :256] * Wf, b' = Wv[:, :256] * bf + bv) and alpha_linear rides along
 // as output column 128 of the same MMA: stages 8 and 9 become ONE stage "8F" with
-//   in: h7(256) | dpe(32)  ->  N = 144 = 128 (views, relu) + 16 (column 128 = sigma_raw, rest 0).
+//   in: h7(256) | dpe(32)  ->  N = 144 = 128 (views, relu) + 16 (columns 128 + 129 = sigma_raw, alpha_linear's
+//   weights split into a bf16 high and low part; rest 0).
 // This removes 65 536 of the 593 408 MACs per row and one accumulator drain.  Stages 0..7 are shared
 // with the unfused image; the 8F chunks and its fp32 bias row are appended after the unfused image.
 constexpr int kFusedN = 144;

@@ -107,6 +107,13 @@ __global__ void pack_bf16_fused_kernel(nerfb200_mlp_weights w, unsigned char* __
       }
     } else if (n == 128 && k < 256) {
       v = w.alpha_w[k];
+    } else if (n == 129 && k < 256) {
+      // low part of alpha_linear.weight: column 128 holds bf16(w), column 129 the residual, and the epilogue adds
+      // the two accumulator columns.  A rounded WEIGHT is a deterministic perturbation of the model (its error is
+      // correlated over all samples, unlike activation rounding) and sigma is the output the image is most
+      // sensitive to; two of the 16 pad columns of the N = 144 tail make alpha_linear's weights ~16-bit for free.
+      const float a = w.alpha_w[k];
+      v = a - __bfloat162float(__float2bfloat16_rn(a));
     }
     size_t off = (size_t)kFusedStageOff + (size_t)c * kFusedChunkBytes + (size_t)n * 128 +
                  (size_t)(((kk >> 3) ^ (n & 7)) << 4) + (size_t)(kk & 7) * 2;
