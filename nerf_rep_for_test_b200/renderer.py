@@ -20,6 +20,7 @@ import math
 import torch
 
 from . import lib as L
+from .path_rendering import PathRenderingMixin
 
 
 class RenderConfig:
@@ -94,7 +95,7 @@ def _model_weight_struct(model):
     return w, keep
 
 
-class Renderer:
+class Renderer(PathRenderingMixin):
     MODES = {"fp32": L.MODE_FP32, "bf16": L.MODE_BF16}
 
     def __init__(self, net, cfg=None, mode=None, ref_compat=True):

@@ -104,3 +104,36 @@ def test_ert_threshold_sweep_flow():
     assert float((accs[0] - accs[1]).min()) >= -1e-6 and float((accs[1] - accs[2]).min()) >= -1e-6
     assert float((accs[0] - accs[2]).abs().max()) <= 0.1 + 1e-6
     assert float(accs[0].max()) > 0.9                      # the field is opaque somewhere: truncation had something to do
+
+
+def test_novel_view_helpers(tmp_path):
+    """The callers the reference keeps on its Renderer (volume_renderer.py:359-616) and the evaluator invokes
+    (src/evaluators/nerf.py:605-640): spiral poses, render_path, render_novel_view_sequence + video."""
+    import math
+    import os
+    r = Renderer(_network(), RenderConfig(enable_ess=False, enable_ert=False, perturb=0))
+    base = torch.tensor(FX.LEGO_TEST_POSE0)
+    poses = []
+    for i in range(5):
+        th = 2 * math.pi * i / 5
+        rot = torch.tensor([[math.cos(th), -math.sin(th), 0, 0], [math.sin(th), math.cos(th), 0, 0], [0, 0, 1, 0], [0, 0, 0, 1.0]])
+        poses.append(rot @ base)
+    poses = torch.stack(poses)
+    sp = r.generate_spiral_poses(poses, n_frames=6)
+    assert sp.shape == (6, 4, 4) and sp.dtype == np.float64
+    rot = sp[:, :3, :3]
+    assert np.allclose(rot @ rot.transpose(0, 2, 1), np.eye(3)[None], atol=1e-6)           # orthonormal frames
+    center = poses[:, :3, 3].numpy().mean(0)
+    to_center = center[None] - sp[:, :3, 3]
+    assert np.allclose(sp[:, :3, 2], to_center / np.linalg.norm(to_center, axis=1, keepdims=True), atol=1e-6)   # look at the centre (:404-416)
+    hwf = [24, 32, 40.0]
+    rgbs, disps = r.render_path(sp[:3], hwf)
+    assert rgbs.shape == (3, 24, 32, 3) and disps.shape == (3, 24, 32) and rgbs.dtype == np.float32
+    assert rgbs.min() >= 0 and rgbs.max() <= 1 and np.isfinite(disps).all() and disps.min() >= 0
+    b = {"pose": torch.from_numpy(sp[0]).float()[None].to(DEV), "intrinsics": r._default_intrinsics(hwf)[None], "H": 24, "W": 32}
+    assert np.array_equal(rgbs[0], r.render(b)["rgb_map"].clamp(0, 1).cpu().numpy())       # render_path == render per pose
+    r.render_num = 4
+    images_dir, video = r.render_novel_view_sequence(poses, hwf, str(tmp_path), "lego", iteration=7)
+    names = sorted(os.listdir(images_dir))
+    assert names == sorted(["view%04d_%s.png" % (i, k) for i in range(4) for k in ("rgb", "disp")])
+    assert video.endswith("lego_spiral_000007.mp4") and os.path.getsize(video) > 0
