@@ -335,6 +335,13 @@ class Renderer(PathRenderingMixin):
         return out
 
     @torch.no_grad()
+    def render_cuda_parallel(self, batch):
+        """volume_renderer.py:1159-1413: the reference's "CUDA kernel" entry is a stub that returns self.render(batch)
+        whenever its extension is unavailable or anything raises (:1164-1166, :1230-1232) -- which is always (SURVEY
+        2.2).  Kept so that callers of that name land on the real path; the KiloNeRF-style renderer proper is
+        nerf_rep_for_test_b200.kilo.KiloRenderer."""
+        return self.render(batch)
+
     def render_host(self, batch):
         """End-to-end entry with HOST buffers: pose/intrinsics are read from host memory, the eight maps
         are returned in pinned host tensors; copies and a stream sync happen inside the C call."""
