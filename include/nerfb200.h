@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define NERFB200_ABI_VERSION 1
+#define NERFB200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define NERFB200_API __attribute__((visibility("default")))
@@ -162,6 +162,18 @@ NERFB200_API int nerfb200_composite_forward(const float* raw, const float* z_val
                                int white_bkgd, int compat_chunk, float* rgb_map, float* disp_map,
                                float* acc_map, float* depth_map, float* weights, void* stream);
 
+/* Same, for the sparse empty-space-skipping launch: keep_bits (may be NULL = every row) holds one bit per row
+ * m = ray*n_samples+s, as written by nerfb200_ess_compact.  A cleared bit means zero density and the row's raw entry
+ * is NOT read, so raw needs no zero fill.  PLAIN / ERT variants only. */
+NERFB200_API int nerfb200_composite_forward_masked(const float* raw, const float* z_vals, const float* rays_d,
+                                      const uint32_t* keep_bits, int n_rays, int n_samples, int variant,
+                                      float ert_threshold, int white_bkgd, int compat_chunk, float* rgb_map,
+                                      float* disp_map, float* acc_map, float* depth_map, float* weights, void* stream);
+/* raw_noise_std (volume_renderer.py:310-314, :1099-1103): raw[m,3] += N(0,1) * std for m < n_rows, in place, before
+ * compositing (forward and backward then see the same noisy density).  Counter-based generator keyed on
+ * (seed, m); the reference's torch.randn stream is not reproduced, only its distribution. */
+NERFB200_API int nerfb200_sigma_noise(float* raw, long long n_rows, float std, uint64_t seed, void* stream);
+
 /* a7: analytic backward of NERFB200_COMPOSITE_PLAIN.  g_* are dL/d(map) (any may be NULL);
  * writes g_raw [n_rays,S,4] (overwrite). z_vals/rays_d receive no gradient here. */
 NERFB200_API int nerfb200_composite_backward(const float* raw, const float* z_vals, const float* rays_d,
@@ -197,10 +209,11 @@ NERFB200_API int nerfb200_ess_update(uint8_t* grid, int res, const float* rays_o
 
 /* Empty-space skipping proper (BASELINE.json configs[4]): list the rows m = ray*n_samples+s whose sample
  * lies in an occupied cell (and, when z_term != NULL, has z <= z_term[ray]) into row_ids (order
- * unspecified) and write their number to *n_active (device int32). */
+ * unspecified) and write their number to *n_active (device int32).  keep_bits (may be NULL): uint32
+ * [ceil(n_rays*n_samples/32)], bit (m & 31) of word (m >> 5) = row m is listed. */
 NERFB200_API int nerfb200_ess_compact(const uint8_t* grid, int res, const float* rays_o, const float* rays_d,
                          const float* z_vals, const float* z_term, int n_rays, int n_samples,
-                         int32_t* row_ids, int32_t* n_active, void* stream);
+                         int32_t* row_ids, int32_t* n_active, uint32_t* keep_bits, void* stream);
 /* MLP on the listed rows only (BF16 mode); every other row of raw is set to 0 (zero density).  The
  * row count is read on the device: no host synchronisation. */
 NERFB200_API int nerfb200_mlp_forward_sparse(const void* packed, int mode, const float* rays_o,
@@ -276,6 +289,7 @@ typedef struct nerfb200_render_params {
   int u_per_ray;      /* 0: u is the [n_importance] table; 1: u is [n_rays,n_importance] */
   int compat_chunk;   /* 2048 */
   float ert_threshold;
+  float raw_noise_std; /* lego.yaml:23 uses 0; > 0: N(0,1)*std added to sigma_raw before the relu (:310-314) */
   uint64_t seed;
   /* a8: when non-NULL the coarse z's of every ray are passed through nerfb200_ess_resample */
   const uint8_t* occupancy_grid; /* uint8 [grid_res]^3, device */

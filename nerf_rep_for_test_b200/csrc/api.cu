@@ -83,6 +83,7 @@ struct Workspace {
   int32_t* row_ids; // [c,S+U] compacted active rows (sparse ESS mode)
   int32_t* counters;// [2] active-row counts of the coarse / fine pass
   float* z_term;    // [c] ERT depth from the coarse pass
+  uint32_t* keep_bits;  // [ceil(c*(S+U)/32)] bit m = row m was evaluated (sparse ESS mode)
   size_t bytes;
 };
 
@@ -104,6 +105,7 @@ static Workspace carve(void* base, int chunk, int S, int U) {
   w.row_ids = reinterpret_cast<int32_t*>(take((size_t)chunk * (S + U)));
   w.counters = reinterpret_cast<int32_t*>(take(64));
   w.z_term = take((size_t)chunk);
+  w.keep_bits = reinterpret_cast<uint32_t*>(take(((size_t)chunk * (S + U) + 31) / 32));
   w.bytes = off;
   return w;
 }
@@ -119,6 +121,9 @@ static int check_params(const nerfb200_render_params* p) {
   NB_CHECK_ARG((p->variant & ~NERFB200_COMPOSITE_FAST_MATH) != NERFB200_COMPOSITE_ERT_COMPAT || (p->compat_chunk > 0 && kChunkRays % p->compat_chunk == 0),
                "render: compat_chunk=%d must divide %d", p->compat_chunk, kChunkRays);
   static_assert(kChunkRaysSparse % kChunkRays == 0, "chunk sizes");
+  NB_CHECK_ARG(p->raw_noise_std >= 0.f, "render: raw_noise_std=%g must be >= 0", (double)p->raw_noise_std);
+  NB_CHECK_ARG(!(p->raw_noise_std > 0.f && p->occupancy_grid && p->ess_skip),
+               "render: raw_noise_std > 0 (a training regulariser) cannot be combined with ess_skip (skipped rows have zero density)");
   return 0;
 }
 
@@ -194,9 +199,10 @@ extern "C" int nerfb200_mlp_backward(const void* packed_bwd, const nerfb200_mlp_
   return launch_mlp_bwd_wgrad(acts, workspace, n_rows, scratch, weights, grads, st);
 }
 
-extern "C" int nerfb200_mlp_forward_sparse(const void* packed, int mode, const float* rays_o, const float* rays_d,
-                                           const float* z_vals, int n_rays, int n_samples, const int32_t* row_ids,
-                                           const int32_t* n_active, float* raw, void* stream) {
+// zero_fill = false: rows outside row_ids keep whatever raw held; the caller composites with the keep-bit mask
+static int mlp_forward_sparse_impl(const void* packed, int mode, const float* rays_o, const float* rays_d,
+                                   const float* z_vals, int n_rays, int n_samples, const int32_t* row_ids,
+                                   const int32_t* n_active, float* raw, bool zero_fill, void* stream) {
   NB_CHECK_ARG(n_rays <= 0 || (packed && rays_o && rays_d && z_vals && raw && row_ids && n_active),
                "mlp_forward_sparse: null pointer");
   NB_CHECK_ARG(n_rays >= 0 && n_samples >= 1, "mlp_forward_sparse: bad sizes");
@@ -205,11 +211,17 @@ extern "C" int nerfb200_mlp_forward_sparse(const void* packed, int mode, const f
   if (n_rays == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   // skipped rows keep raw = 0: sigma_raw = 0 -> alpha = 0 -> no contribution (and rgb_raw is never used)
-  NB_CUDA(cudaMemsetAsync(raw, 0, (size_t)n_rays * n_samples * 16, st));
+  if (zero_fill) NB_CUDA(cudaMemsetAsync(raw, 0, (size_t)n_rays * n_samples * 16, st));
   bool prof = prof_begin(st);
   int rc = launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, nullptr, nullptr, nullptr, row_ids, n_active, st);
   if (prof) prof_end(st, 0.0);   // evaluated rows are data dependent; counted by the caller from n_active
   return rc;
+}
+
+extern "C" int nerfb200_mlp_forward_sparse(const void* packed, int mode, const float* rays_o, const float* rays_d,
+                                           const float* z_vals, int n_rays, int n_samples, const int32_t* row_ids,
+                                           const int32_t* n_active, float* raw, void* stream) {
+  return mlp_forward_sparse_impl(packed, mode, rays_o, rays_d, z_vals, n_rays, n_samples, row_ids, n_active, raw, true, stream);
 }
 
 extern "C" int nerfb200_profile_enable(int on) {
@@ -281,15 +293,23 @@ extern "C" int nerfb200_render_rays(const void* packed_coarse, const void* packe
     const bool sparse = p->occupancy_grid && p->ess_skip;
     if (p->occupancy_grid && !sparse &&
         (e = nerfb200_ess_resample(p->occupancy_grid, p->grid_res, ro, rd, n, S, ws.z_coarse, nullptr, stream))) return e;
+    // sparse: the compaction leaves one keep bit per row; the MLP writes only the listed rows and the masked
+    // compositor never touches the others (no zero fill of raw, no 16 B read per skipped row)
+    // (the literal ERT_COMPAT compositor has no masked form: that combination keeps the zero fill)
+    const bool masked = sparse && (p->variant & ~NERFB200_COMPOSITE_FAST_MATH) != NERFB200_COMPOSITE_ERT_COMPAT;
+    const uint32_t* keep = masked ? ws.keep_bits : nullptr;
+    const uint64_t noise_seed = p->seed ^ ((uint64_t)r0 * 0xD6E8FEB86659FD93ull);
     if (sparse) {
       if ((e = nerfb200_ess_compact(p->occupancy_grid, p->grid_res, ro, rd, ws.z_coarse, nullptr, n, S, ws.row_ids,
-                                    ws.counters + 0, stream))) return e;
-      if ((e = nerfb200_mlp_forward_sparse(packed_coarse, p->mode, ro, rd, ws.z_coarse, n, S, ws.row_ids, ws.counters + 0,
-                                           ws.raw_c, stream))) return e;
+                                    ws.counters + 0, ws.keep_bits, stream))) return e;
+      if ((e = mlp_forward_sparse_impl(packed_coarse, p->mode, ro, rd, ws.z_coarse, n, S, ws.row_ids, ws.counters + 0,
+                                       ws.raw_c, !masked, stream))) return e;
     } else if ((e = nerfb200_mlp_forward(packed_coarse, p->mode, ro, rd, ws.z_coarse, n, S, ws.raw_c, stream))) return e;
-    if ((e = nerfb200_composite_forward(ws.raw_c, ws.z_coarse, rd, n, S, p->variant, p->ert_threshold, p->white_bkgd,
-                                        p->compat_chunk, mc->rgb + (size_t)r0 * 3, mc->disp + r0, mc->acc + r0,
-                                        mc->depth + r0, ws.weights, stream))) return e;
+    if (p->raw_noise_std > 0.f &&
+        (e = nerfb200_sigma_noise(ws.raw_c, (long long)n * S, p->raw_noise_std, noise_seed + 0x632BE59BD9B4E019ull, stream))) return e;
+    if ((e = nerfb200_composite_forward_masked(ws.raw_c, ws.z_coarse, rd, keep, n, S, p->variant, p->ert_threshold,
+                                               p->white_bkgd, p->compat_chunk, mc->rgb + (size_t)r0 * 3, mc->disp + r0,
+                                               mc->acc + r0, mc->depth + r0, ws.weights, stream))) return e;
     if (U > 0) {
       const float* uu = p->u_per_ray ? u + (size_t)r0 * U : u;
       if ((e = nerfb200_sample_pdf_merge(ws.z_coarse, ws.weights, uu, p->u_per_ray, n, S, U, ws.z_all, nullptr, nullptr,
@@ -303,16 +323,18 @@ extern "C" int nerfb200_render_rays(const void* packed_coarse, const void* packe
           zt = ws.z_term;
         }
         if ((e = nerfb200_ess_compact(p->occupancy_grid, p->grid_res, ro, rd, ws.z_all, zt, n, S + U, ws.row_ids,
-                                      ws.counters + 1, stream))) return e;
-        if ((e = nerfb200_mlp_forward_sparse(packed_fine, p->mode, ro, rd, ws.z_all, n, S + U, ws.row_ids, ws.counters + 1,
-                                             ws.raw_f, stream))) return e;
+                                      ws.counters + 1, ws.keep_bits, stream))) return e;
+        if ((e = mlp_forward_sparse_impl(packed_fine, p->mode, ro, rd, ws.z_all, n, S + U, ws.row_ids, ws.counters + 1,
+                                         ws.raw_f, !masked, stream))) return e;
         if (p->eval_counts) {   // optional statistics: evaluated rows per pass, accumulated over the call
           if ((e = nerfb200_accumulate_counts(ws.counters, p->eval_counts, stream))) return e;
         }
       } else if ((e = nerfb200_mlp_forward(packed_fine, p->mode, ro, rd, ws.z_all, n, S + U, ws.raw_f, stream))) return e;
-      if ((e = nerfb200_composite_forward(ws.raw_f, ws.z_all, rd, n, S + U, p->variant, p->ert_threshold, p->white_bkgd,
-                                          p->compat_chunk, mf->rgb + (size_t)r0 * 3, mf->disp + r0, mf->acc + r0,
-                                          mf->depth + r0, nullptr, stream))) return e;
+      if (p->raw_noise_std > 0.f &&
+          (e = nerfb200_sigma_noise(ws.raw_f, (long long)n * (S + U), p->raw_noise_std, noise_seed + 0x94D049BB133111EBull, stream))) return e;
+      if ((e = nerfb200_composite_forward_masked(ws.raw_f, ws.z_all, rd, keep, n, S + U, p->variant, p->ert_threshold,
+                                                 p->white_bkgd, p->compat_chunk, mf->rgb + (size_t)r0 * 3, mf->disp + r0,
+                                                 mf->acc + r0, mf->depth + r0, nullptr, stream))) return e;
     }
   }
   return 0;

@@ -52,4 +52,19 @@ void count_launch(int n = 1);
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Counter-based RNG shared by the stratified jitter (a2) and the density noise (a5): a uniform in
+// [0,1) keyed on (seed, a, b).  The reference draws from torch's global generator, whose stream a
+// kernel cannot reproduce; only the distribution is matched.
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ float uniform01(uint64_t seed, uint32_t a, uint32_t b) {
+  uint32_t h = mix32((uint32_t)seed ^ mix32(a * 0x9E3779B9U + 0x85ebca6bU));
+  h = mix32(h ^ (uint32_t)(seed >> 32) ^ mix32(b + 0xc2b2ae35U));
+  return (float)(h >> 8) * (1.0f / 16777216.0f);  // [0,1)
+}
+#endif
+
 }  // namespace nb

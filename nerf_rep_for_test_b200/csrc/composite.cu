@@ -59,10 +59,14 @@ struct RaySamples {
 };
 
 // alpha + transmittance for the lane's samples.  eps = 1e-10 (PLAIN) or 0 (ERT variants).
+// keep_bits (may be NULL): bit m of the array says whether row m = ray*S+i went through the MLP (sparse
+// empty-space-skipping launch, nerfb200_ess_compact).  A cleared bit means zero density, and the row's raw
+// entry is never read -- so the sparse path neither zero-fills raw nor streams the skipped rows (16 B each).
 template <bool kErt, bool kFast = false>
 __device__ __forceinline__ void ray_alpha_T(const float* __restrict__ raw_row,
                                             const float* __restrict__ z_row, float dnorm, int S,
-                                            int per, int lane, float thr, RaySamples& rs) {
+                                            int per, int lane, float thr, RaySamples& rs,
+                                            const uint32_t* __restrict__ keep_bits = nullptr, size_t bit_base = 0) {
   double local = 1.0;
   float fac[kMaxPer];
 #pragma unroll
@@ -73,7 +77,12 @@ __device__ __forceinline__ void ray_alpha_T(const float* __restrict__ raw_row,
       float z0 = z_row[i];
       float dist = (i + 1 < S) ? __fsub_rn(z_row[i + 1], z0) : 1e10f;
       dist = __fmul_rn(dist, dnorm);
-      float sig = fmaxf(raw_row[(size_t)i * 4 + 3], 0.f);
+      bool kept = true;
+      if (keep_bits != nullptr) {
+        const size_t b = bit_base + (size_t)i;
+        kept = (keep_bits[b >> 5] >> (b & 31)) & 1u;
+      }
+      float sig = kept ? fmaxf(raw_row[(size_t)i * 4 + 3], 0.f) : 0.f;
       // sigma == 0 (empty / skipped sample): exp(-0) = 1 and alpha = 0 exactly -- no fp64 exp needed
       a = sig == 0.f ? 0.f : __fsub_rn(1.f, exp_cr<kFast>(__fmul_rn(-sig, dist)));
       f = kErt ? __fsub_rn(1.f, a) : __fadd_rn(__fsub_rn(1.f, a), 1e-10f);
@@ -154,7 +163,7 @@ composite_kernel(const float* __restrict__ raw, const float* __restrict__ z_vals
                  const float* __restrict__ rays_d, int n_rays, int S, float thr, int white_bkgd,
                  float* __restrict__ rgb_map, float* __restrict__ disp_map,
                  float* __restrict__ acc_map, float* __restrict__ depth_map,
-                 float* __restrict__ weights) {
+                 float* __restrict__ weights, const uint32_t* __restrict__ keep_bits) {
   int lane = threadIdx.x & 31;
   size_t ray = (size_t)blockIdx.x * kCompWarps + (threadIdx.x >> 5);
   if (ray >= (size_t)n_rays) return;
@@ -162,7 +171,7 @@ composite_kernel(const float* __restrict__ raw, const float* __restrict__ z_vals
   const float* raw_row = raw + ray * S * 4;
   const float* z_row = z_vals + ray * S;
   RaySamples rs;
-  ray_alpha_T<kErt, kFast>(raw_row, z_row, ray_norm(rays_d + ray * 3), S, per, lane, thr, rs);
+  ray_alpha_T<kErt, kFast>(raw_row, z_row, ray_norm(rays_d + ray * 3), S, per, lane, thr, rs, keep_bits, ray * S);
   ray_outputs<kFast>(rs, raw_row, z_row, S, per, lane, rs.first_low, white_bkgd, ray, rgb_map, disp_map,
                      acc_map, depth_map, weights);
 }
@@ -282,15 +291,47 @@ composite_backward_kernel(const float* __restrict__ raw, const float* __restrict
   }
 }
 
+// raw_noise_std (volume_renderer.py:310-314, :1099-1103): sigma_raw += randn * std before the relu.  Applied in
+// place to the MLP output, so the compositing forward AND backward see the noisy density (d noisy / d raw = 1).
+// Box-Muller on two counter-based uniforms keyed on (seed, row).
+__global__ void sigma_noise_kernel(float* __restrict__ raw, long long n_rows, float std, uint64_t seed) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_rows) return;
+  const uint32_t lo = (uint32_t)idx, hi = (uint32_t)(idx >> 32);
+  float u1 = 1.0f - uniform01(seed, lo, 2u * hi);         // (0,1]
+  float u2 = uniform01(seed ^ 0xD1B54A32D192ED03ull, lo, 2u * hi + 1u);
+  float g = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+  raw[idx * 4 + 3] += std * g;
+}
+
 }  // namespace nb
 
 using namespace nb;
+
+extern "C" int nerfb200_sigma_noise(float* raw, long long n_rows, float std, uint64_t seed, void* stream) {
+  NB_CHECK_ARG(n_rows <= 0 || raw, "sigma_noise: null pointer");
+  NB_CHECK_ARG(n_rows >= 0 && std >= 0.f, "sigma_noise: bad arguments (n_rows=%lld, std=%g)", n_rows, (double)std);
+  if (n_rows == 0 || std == 0.f) return 0;
+  sigma_noise_kernel<<<ceil_div(n_rows, 256), 256, 0, (cudaStream_t)stream>>>(raw, n_rows, std, seed);
+  NB_LAUNCH_OK("sigma_noise_kernel");
+  return 0;
+}
 
 extern "C" int nerfb200_composite_forward(const float* raw, const float* z_vals, const float* rays_d,
                                           int n_rays, int n_samples, int variant, float ert_threshold,
                                           int white_bkgd, int compat_chunk, float* rgb_map,
                                           float* disp_map, float* acc_map, float* depth_map,
                                           float* weights, void* stream) {
+  return nerfb200_composite_forward_masked(raw, z_vals, rays_d, nullptr, n_rays, n_samples, variant, ert_threshold,
+                                           white_bkgd, compat_chunk, rgb_map, disp_map, acc_map, depth_map, weights,
+                                           stream);
+}
+
+extern "C" int nerfb200_composite_forward_masked(const float* raw, const float* z_vals, const float* rays_d,
+                                                 const uint32_t* keep_bits, int n_rays, int n_samples, int variant,
+                                                 float ert_threshold, int white_bkgd, int compat_chunk,
+                                                 float* rgb_map, float* disp_map, float* acc_map, float* depth_map,
+                                                 float* weights, void* stream) {
   NB_CHECK_ARG(n_rays <= 0 || (raw && z_vals && rays_d && rgb_map && disp_map && acc_map && depth_map),
                "composite_forward: null pointer");
   NB_CHECK_ARG(n_samples >= 1 && n_samples <= 32 * kMaxPer, "composite_forward: n_samples=%d out of range [1,%d]",
@@ -304,13 +345,14 @@ extern "C" int nerfb200_composite_forward(const float* raw, const float* z_vals,
   int blocks = ceil_div(n_rays, kCompWarps);
 #define NB_COMPOSITE(ERT, FAST, THR)                                                                              \
   composite_kernel<ERT, FAST><<<blocks, kCompWarps * 32, 0, st>>>(raw, z_vals, rays_d, n_rays, n_samples, THR, white_bkgd, \
-                                                                  rgb_map, disp_map, acc_map, depth_map, weights)
+                                                                  rgb_map, disp_map, acc_map, depth_map, weights, keep_bits)
   if (variant == NERFB200_COMPOSITE_PLAIN) {
     if (fast) NB_COMPOSITE(false, true, 0.f); else NB_COMPOSITE(false, false, 0.f);
   } else if (variant == NERFB200_COMPOSITE_ERT) {
     if (fast) NB_COMPOSITE(true, true, ert_threshold); else NB_COMPOSITE(true, false, ert_threshold);
   } else {
     NB_CHECK_ARG(compat_chunk > 0, "composite_forward: compat_chunk must be > 0");
+    NB_CHECK_ARG(keep_bits == nullptr, "composite_forward: the ERT_COMPAT variant has no masked form");
     composite_ert_compat_kernel<<<ceil_div(n_rays, compat_chunk), 1024, 0, st>>>(
         raw, z_vals, rays_d, n_rays, n_samples, ert_threshold, white_bkgd, compat_chunk, rgb_map, disp_map, acc_map,
         depth_map, weights);

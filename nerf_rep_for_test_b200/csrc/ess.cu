@@ -103,29 +103,65 @@ __global__ void ess_update_kernel(uint8_t* __restrict__ grid, int res, const flo
 }
 
 // ---- empty-space skipping proper: stream compaction of the rows worth evaluating ----------------
-__global__ void ess_compact_kernel(const uint8_t* __restrict__ grid, int res, const float* __restrict__ rays_o,
-                                   const float* __restrict__ rays_d, const float* __restrict__ z_vals,
-                                   const float* __restrict__ z_term, long long total, int S,
-                                   int32_t* __restrict__ row_ids, int32_t* __restrict__ n_active) {
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  bool keep = false;
-  if (idx < total) {
-    long long ray = idx / S;
-    float z = z_vals[idx];
-    int g[3];
+// A block handles 32 words of 32 consecutive rows (each warp four of them, so four independent z / grid loads
+// are in flight per thread), counts its survivors with ballots + one 32-entry warp scan, and reserves its run of
+// row_ids with ONE atomicAdd: the first version did one atomic per warp on the single counter and was bound by
+// same-address atomic throughput (1.1 ms per 800x800 frame for 164 M rows, 0.55 rows per clock and SM).
+// keep_bits (optional): the ballot words themselves, bit m = row m kept -- read by the masked compositor.
+constexpr int kCompactThreads = 256;
+constexpr int kCompactWords = 4;                                      // 32-row words per warp
+constexpr int kCompactRows = kCompactThreads * kCompactWords;         // 1024 rows per block
+static_assert(kCompactThreads / 32 * kCompactWords == 32, "the per-block scan is one warp wide");
+
+__global__ void __launch_bounds__(kCompactThreads)
+ess_compact_kernel(const uint8_t* __restrict__ grid, int res, const float* __restrict__ rays_o,
+                   const float* __restrict__ rays_d, const float* __restrict__ z_vals,
+                   const float* __restrict__ z_term, long long total, int S,
+                   int32_t* __restrict__ row_ids, int32_t* __restrict__ n_active,
+                   uint32_t* __restrict__ keep_bits) {
+  __shared__ int s_off[32];
+  __shared__ int s_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long row0 = (long long)blockIdx.x * kCompactRows + (long long)warp * (kCompactWords * 32) + lane;
+  unsigned m[kCompactWords];
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
-      g[c] = grid_index(__fadd_rn(rays_o[ray * 3 + c], __fmul_rn(rays_d[ray * 3 + c], z)), res);
-    keep = grid[((size_t)g[0] * res + g[1]) * res + g[2]] != 0;
-    if (keep && z_term != nullptr) keep = z <= z_term[ray];
+  for (int j = 0; j < kCompactWords; ++j) {
+    const long long idx = row0 + j * 32;
+    bool keep = false;
+    if (idx < total) {
+      long long ray = idx / S;
+      float z = z_vals[idx];
+      int g[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        g[c] = grid_index(__fadd_rn(rays_o[ray * 3 + c], __fmul_rn(rays_d[ray * 3 + c], z)), res);
+      keep = grid[((size_t)g[0] * res + g[1]) * res + g[2]] != 0;
+      if (keep && z_term != nullptr) keep = z <= z_term[ray];
+    }
+    m[j] = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) {
+      s_off[warp * kCompactWords + j] = __popc(m[j]);
+      if (keep_bits != nullptr && idx < total) keep_bits[idx >> 5] = m[j];
+    }
   }
-  // warp-aggregated append: one atomic per warp
-  unsigned m = __ballot_sync(0xffffffffu, keep);
-  int lane = threadIdx.x & 31;
-  int base = 0;
-  if (lane == 0 && m) base = atomicAdd(n_active, __popc(m));
-  base = __shfl_sync(0xffffffffu, base, 0);
-  if (keep) row_ids[base + __popc(m & ((1u << lane) - 1))] = (int32_t)idx;
+  __syncthreads();
+  if (warp == 0) {   // exclusive scan of the 32 word counts, one reservation for the block
+    const int c = s_off[lane];
+    int incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
+    }
+    s_off[lane] = incl - c;
+    if (lane == 31) s_base = incl ? atomicAdd(n_active, incl) : 0;
+  }
+  __syncthreads();
+  const int base = s_base;
+#pragma unroll
+  for (int j = 0; j < kCompactWords; ++j)
+    if ((m[j] >> lane) & 1u)
+      row_ids[base + s_off[warp * kCompactWords + j] + __popc(m[j] & ((1u << lane) - 1))] = (int32_t)(row0 + j * 32);
 }
 
 __global__ void ert_depth_kernel(const float* __restrict__ weights, const float* __restrict__ z_vals, int n_rays,
@@ -150,7 +186,7 @@ using namespace nb;
 
 extern "C" int nerfb200_ess_compact(const uint8_t* grid, int res, const float* rays_o, const float* rays_d,
                                     const float* z_vals, const float* z_term, int n_rays, int n_samples,
-                                    int32_t* row_ids, int32_t* n_active, void* stream) {
+                                    int32_t* row_ids, int32_t* n_active, uint32_t* keep_bits, void* stream) {
   NB_CHECK_ARG(n_active, "ess_compact: null counter");
   NB_CHECK_ARG(n_rays <= 0 || (grid && rays_o && rays_d && z_vals && row_ids), "ess_compact: null pointer");
   NB_CHECK_ARG(res >= 1 && res <= 1024, "ess_compact: bad grid resolution %d", res);
@@ -158,8 +194,8 @@ extern "C" int nerfb200_ess_compact(const uint8_t* grid, int res, const float* r
   NB_CUDA(cudaMemsetAsync(n_active, 0, sizeof(int32_t), (cudaStream_t)stream));
   if (n_rays == 0) return 0;
   long long total = (long long)n_rays * n_samples;
-  ess_compact_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(grid, res, rays_o, rays_d, z_vals, z_term,
-                                                                             total, n_samples, row_ids, n_active);
+  ess_compact_kernel<<<ceil_div(total, kCompactRows), kCompactThreads, 0, (cudaStream_t)stream>>>(
+      grid, res, rays_o, rays_d, z_vals, z_term, total, n_samples, row_ids, n_active, keep_bits);
   NB_LAUNCH_OK("ess_compact_kernel");
   return 0;
 }

@@ -48,16 +48,6 @@ __global__ void raygen_kernel(const float* __restrict__ pose, const float* __res
 // linspace arithmetic).  perturb!=0: mids/upper/lower as :228-235 with a counter-based hash
 // RNG (the reference's torch.rand stream cannot be reproduced by a kernel).
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t mix32(uint32_t x) {
-  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
-  return x;
-}
-__device__ __forceinline__ float uniform01(uint64_t seed, uint32_t a, uint32_t b) {
-  uint32_t h = mix32((uint32_t)seed ^ mix32(a * 0x9E3779B9U + 0x85ebca6bU));
-  h = mix32(h ^ (uint32_t)(seed >> 32) ^ mix32(b + 0xc2b2ae35U));
-  return (float)(h >> 8) * (1.0f / 16777216.0f);  // [0,1)
-}
-
 __global__ void sample_coarse_kernel(const float* __restrict__ z_table, long long total, int S,
                                      int perturb, uint64_t seed, float* __restrict__ z_vals) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;

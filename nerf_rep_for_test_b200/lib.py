@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("NERFB200_LIB") or os.path.join(HERE, "libnerfb200.so"
 MODE_FP32, MODE_BF16 = 0, 1
 COMPOSITE_PLAIN, COMPOSITE_ERT, COMPOSITE_ERT_COMPAT = 0, 1, 2
 COMPOSITE_FAST_MATH = 0x10          # OR-ed into PLAIN / ERT (include/nerfb200.h)
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _f = C.POINTER(C.c_float)
 _vp = C.c_void_p
@@ -37,7 +37,7 @@ class RenderParams(C.Structure):
     _fields_ = [("n_samples", C.c_int), ("n_importance", C.c_int), ("mode", C.c_int),
                 ("variant", C.c_int), ("white_bkgd", C.c_int), ("perturb", C.c_int),
                 ("u_per_ray", C.c_int), ("compat_chunk", C.c_int), ("ert_threshold", C.c_float),
-                ("seed", C.c_uint64), ("occupancy_grid", _vp), ("grid_res", C.c_int), ("ess_skip", C.c_int),
+                ("raw_noise_std", C.c_float), ("seed", C.c_uint64), ("occupancy_grid", _vp), ("grid_res", C.c_int), ("ess_skip", C.c_int),
                 ("eval_counts", _vp)]
 
 
@@ -83,6 +83,9 @@ SIGNATURES = {
     "nerfb200_mlp_forward_stages": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "nerfb200_composite_forward": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
                                              C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "nerfb200_composite_forward_masked": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
+                                                    C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "nerfb200_sigma_noise": (C.c_int, [_vp, C.c_longlong, C.c_float, C.c_uint64, _vp]),
     "nerfb200_composite_backward": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp,
                                               _vp, _vp]),
     "nerfb200_sample_from_cdf": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
@@ -90,7 +93,7 @@ SIGNATURES = {
                                             _vp, _vp]),
     "nerfb200_ess_resample": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "nerfb200_ess_update": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
-    "nerfb200_ess_compact": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "nerfb200_ess_compact": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "nerfb200_mlp_forward_sparse": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "nerfb200_ert_depth": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_float, _vp, _vp]),
     "nerfb200_accumulate_counts": (C.c_int, [_vp, _vp, _vp]),

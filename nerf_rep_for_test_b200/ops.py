@@ -175,18 +175,37 @@ def mlp_forward_stages(packed, rays_o, rays_d, z_vals):
 
 
 def composite_forward(raw, z_vals, rays_d, variant=L.COMPOSITE_PLAIN, ert_threshold=0.01, white_bkgd=True,
-                      compat_chunk=2048, want_weights=True):
+                      compat_chunk=2048, want_weights=True, keep_bits=None):
+    """keep_bits (int32/uint32 words from ess_compact, optional): rows with a cleared bit have zero density and
+    their raw entries are never read (nerfb200_composite_forward_masked)."""
     raw, z_vals, rays_d = _f(raw), _f(z_vals), _f(rays_d)
     n, S = z_vals.shape
     d = raw.device
     rgb, disp, acc, depth = (torch.empty((n, 3), device=d), torch.empty(n, device=d), torch.empty(n, device=d),
                              torch.empty(n, device=d))
     w = torch.empty((n, S), device=d) if want_weights else None
+    if keep_bits is not None:
+        if keep_bits.numel() * 32 < n * S:
+            raise L.NerfB200Error("composite_forward: keep_bits has %d words, need %d" % (keep_bits.numel(), (n * S + 31) // 32))
+        L.check(L.load().nerfb200_composite_forward_masked(
+            L.dev(raw), L.dev(z_vals), L.dev(rays_d), L.dev(keep_bits, torch.int32), n, S, variant, ert_threshold,
+            int(white_bkgd), compat_chunk, L.dev(rgb), L.dev(disp), L.dev(acc), L.dev(depth), L.dev(w), L.stream_ptr()),
+            "composite_forward_masked")
+        return rgb, disp, acc, w, depth
     L.check(L.load().nerfb200_composite_forward(L.dev(raw), L.dev(z_vals), L.dev(rays_d), n, S, variant,
                                                ert_threshold, int(white_bkgd), compat_chunk, L.dev(rgb), L.dev(disp),
                                                L.dev(acc), L.dev(depth), L.dev(w), L.stream_ptr()),
             "composite_forward")
     return rgb, disp, acc, w, depth   # same order as _raw2outputs (:357)
+
+
+def sigma_noise(raw, std, seed=0):
+    """raw[..., 3] += N(0,1) * std in place (raw_noise_std, volume_renderer.py:310-314); returns raw."""
+    if raw.dtype != torch.float32 or not raw.is_contiguous() or raw.shape[-1] != 4:
+        raise L.NerfB200Error("sigma_noise: raw must be a contiguous fp32 [..., 4] tensor")
+    L.check(L.load().nerfb200_sigma_noise(L.dev(raw), raw.numel() // 4, float(std), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                         L.stream_ptr()), "sigma_noise")
+    return raw
 
 
 def composite_backward(raw, z_vals, rays_d, g_rgb=None, g_acc=None, g_depth=None, g_weights=None, white_bkgd=True):
@@ -246,16 +265,19 @@ def ess_update(grid_u8, rays_o, rays_d, z_vals, raw, weights, use_origin=False):
     return grid_u8
 
 
-def ess_compact(grid_u8, rays_o, rays_d, z_vals, z_term=None):
-    """(row_ids int32 [n*S] with the first n_active entries valid, n_active int32 [1] on the device)."""
+def ess_compact(grid_u8, rays_o, rays_d, z_vals, z_term=None, want_bits=False):
+    """(row_ids int32 [n*S] with the first n_active entries valid, n_active int32 [1] on the device); with
+    want_bits also the keep-bit words (int32 [ceil(n*S/32)], bit m&31 of word m>>5 = row m listed)."""
     rays_o, rays_d, z_vals = _f(rays_o), _f(rays_d), _f(z_vals)
     n, S = z_vals.shape
     row_ids = torch.empty(n * S, dtype=torch.int32, device=z_vals.device)
     n_active = torch.zeros(1, dtype=torch.int32, device=z_vals.device)
+    bits = torch.empty((n * S + 31) // 32, dtype=torch.int32, device=z_vals.device) if want_bits else None
     L.check(L.load().nerfb200_ess_compact(L.dev(grid_u8, torch.uint8), grid_u8.shape[0], L.dev(rays_o), L.dev(rays_d),
                                          L.dev(z_vals), L.dev(_f(z_term)), n, S, L.dev(row_ids), L.dev(n_active),
+                                         L.dev(bits, torch.int32) if bits is not None else None,
                                          L.stream_ptr()), "ess_compact")
-    return row_ids, n_active
+    return (row_ids, n_active, bits) if want_bits else (row_ids, n_active)
 
 
 def mlp_forward_sparse(packed, rays_o, rays_d, z_vals, row_ids, n_active):

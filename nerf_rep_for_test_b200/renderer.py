@@ -254,9 +254,8 @@ class Renderer(PathRenderingMixin):
         return t
 
     def _params(self, training, n_rays):
-        if self.raw_noise_std and float(self.raw_noise_std) > 0:
-            raise L.NerfB200Error("raw_noise_std > 0 is not implemented (lego.yaml:23 uses 0)")
         p = L.RenderParams()
+        p.raw_noise_std = max(float(self.raw_noise_std or 0.0), 0.0)   # :310-314 (lego.yaml:23 uses 0)
         p.n_samples, p.n_importance = self.N_samples, self.N_importance
         p.mode = self.MODES[self.mode]
         if self.enable_ert:
@@ -277,6 +276,9 @@ class Renderer(PathRenderingMixin):
             if self.ess_mode == "skip":
                 if self.mode != "bf16":
                     raise L.NerfB200Error("ess_mode='skip' needs mode='bf16' (sparse MLP launch)")
+                if p.raw_noise_std > 0:
+                    raise L.NerfB200Error("raw_noise_std > 0 cannot be combined with ess_mode='skip' "
+                                          "(skipped samples have zero density by definition)")
                 p.ess_skip = 1
                 if self.enable_ert:
                     p.variant = L.COMPOSITE_ERT        # per-ray truncation; the chunk quirk has no meaning here

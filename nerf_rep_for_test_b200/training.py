@@ -30,6 +30,14 @@ def model_params(model):
     return ps
 
 
+def _density_noise(renderer, raw, which):
+    """raw_noise_std (volume_renderer.py:310-314): sigma_raw += N(0,1)*std, in place on the MLP output, so the
+    compositing forward and its analytic backward see the same noisy density."""
+    std = float(renderer.raw_noise_std or 0.0)
+    if std > 0.0:
+        ops.sigma_noise(raw, std, seed=renderer.seed * 0x9E3779B97F4A7C15 + which)
+
+
 class _RenderRays(torch.autograd.Function):
     @staticmethod
     def forward(ctx, renderer, rays_o, rays_d, *params):
@@ -41,11 +49,13 @@ class _RenderRays(torch.autograd.Function):
         z_c = ops.sample_coarse(r._table("z"), n, perturb=float(r.perturb) > 0, seed=r.seed)
         pk_c, pk_f = r.packed("coarse", "bf16"), r.packed("fine", "bf16")   # cached per parameter version
         raw_c, store_c = ops.mlp_forward_train(pk_c, rays_o, rays_d, z_c)
+        _density_noise(r, raw_c, 1)
         rgb0, disp0, acc0, w_c, depth0 = ops.composite_forward(raw_c, z_c, rays_d, L.COMPOSITE_PLAIN,
                                                                white_bkgd=r.white_bkgd)
         u = torch.rand((n, U), device=dev) if r.net.training else r._table("u")
         z_all, _, _, _ = ops.sample_pdf_merge(z_c, w_c, u, want_aux=False)
         raw_f, store_f = ops.mlp_forward_train(pk_f, rays_o, rays_d, z_all)
+        _density_noise(r, raw_f, 2)
         rgb, disp, acc, _, depth = ops.composite_forward(raw_f, z_all, rays_d, L.COMPOSITE_PLAIN,
                                                          white_bkgd=r.white_bkgd, want_weights=False)
         ctx.renderer = r
@@ -128,10 +138,12 @@ class TrainStep:
         z_c = ops.sample_coarse(r._table("z"), n, perturb=float(r.perturb) > 0, seed=r.seed)
         pk_c, pk_f = r.packed("coarse", "bf16"), r.packed("fine", "bf16")
         raw_c, store_c = ops.mlp_forward_train(pk_c, rays_o, rays_d, z_c)
+        _density_noise(r, raw_c, 1)
         rgb0, _, _, w_c, _ = ops.composite_forward(raw_c, z_c, rays_d, L.COMPOSITE_PLAIN, white_bkgd=r.white_bkgd)
         u = torch.rand((n, r.N_importance), device=dev) if r.net.training else r._table("u")
         z_all = ops.sample_pdf_merge(z_c, w_c, u, want_aux=False)[0]
         raw_f, store_f = ops.mlp_forward_train(pk_f, rays_o, rays_d, z_all)
+        _density_noise(r, raw_f, 2)
         rgb = ops.composite_forward(raw_f, z_all, rays_d, L.COMPOSITE_PLAIN, white_bkgd=r.white_bkgd, want_weights=False)[0]
         # loss = mean((rgb0 - t)^2) + mean((rgb - t)^2)  (trainers/nerf.py:52-65)  ->  dL/d map = 2 (map - t) / (3 n)
         d0, d1 = rgb0 - target_rgb, rgb - target_rgb

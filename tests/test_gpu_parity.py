@@ -475,6 +475,84 @@ def test_ess_skip_equals_masked_dense_and_skips_work():
     assert not bad.any()
 
 
+
+def test_ess_compact_keep_bits_and_masked_compositor():
+    """The ballot words of the compaction are exactly the set of listed rows, and the masked compositor (which never
+    reads a skipped row) is bit-identical to the plain compositor on a zero-filled raw -- even when the skipped rows
+    of its input hold NaNs.  Ragged sizes: the row count is not a multiple of 32 or of the 1024-row block."""
+    torch.manual_seed(5)
+    grid = _blob_grid()
+    g8 = cuda(grid.to(torch.uint8))
+    for (H, W, S) in ((48, 48, 64), (19, 23, 67), (5, 7, 192)):
+        b = O.lego_batch(H, W)
+        ro, rd = O.get_rays(H, W, b["pose"][0], b["intrinsics"][0])
+        n = ro.shape[0]
+        z = torch.sort(2.0 + 4.0 * torch.rand(n, S), dim=1)[0]
+        zt = 2.0 + 4.0 * torch.rand(n)
+        zt[::3] = float("inf")
+        for z_term in (None, zt):
+            row_ids, n_active, bits = ops.ess_compact(g8, cuda(ro), cuda(rd), cuda(z), None if z_term is None else cuda(z_term),
+                                                      want_bits=True)
+            pts = ro[..., None, :] + rd[..., None, :] * z[..., :, None]
+            occ = ~O.is_empty_space(grid, pts.reshape(-1, 3))
+            if z_term is not None:
+                occ &= (z <= z_term[:, None]).reshape(-1)
+            na = int(n_active)
+            assert na == int(occ.sum())
+            listed = torch.sort(row_ids[:na].cpu().long())[0]
+            assert torch.equal(listed, torch.nonzero(occ).flatten())
+            words = bits.cpu().long() & 0xFFFFFFFF
+            m = torch.arange(n * S)
+            bit = (words[m >> 5] >> (m & 31)) & 1
+            assert torch.equal(bit.bool(), occ)
+            raw = torch.randn(n, S, 4) * 2.0
+            keep = occ.reshape(n, S)
+            raw_zero = raw * keep[..., None].float()
+            raw_nan = torch.where(keep[..., None], raw, torch.full_like(raw, float("nan")))
+            for variant in (L.COMPOSITE_PLAIN, L.COMPOSITE_ERT, L.COMPOSITE_PLAIN | L.COMPOSITE_FAST_MATH):
+                ref = ops.composite_forward(cuda(raw_zero), cuda(z), cuda(rd), variant, 0.01)
+                got = ops.composite_forward(cuda(raw_nan), cuda(z), cuda(rd), variant, 0.01, keep_bits=bits)
+                for a, c in zip(ref, got):
+                    assert bits_equal(a.cpu(), c.cpu())
+    with pytest.raises(L.NerfB200Error):
+        ops.composite_forward(cuda(raw_nan), cuda(z), cuda(rd), L.COMPOSITE_ERT_COMPAT, 0.01, keep_bits=bits)
+
+
+def test_sigma_noise_distribution_and_render_switch():
+    """raw_noise_std (volume_renderer.py:310-314): N(0, std^2) added to the density channel only, seeded; the
+    renderer switch perturbs the maps, is reproducible for a fixed seed and refuses the skipping mode."""
+    raw = torch.zeros(1 << 20, 4, device=DEV)
+    ops.sigma_noise(raw, 0.5, seed=7)
+    g = raw[:, 3].double()
+    assert float(raw[:, :3].abs().max()) == 0.0
+    assert abs(float(g.mean())) < 3e-3 and abs(float(g.std()) - 0.5) < 3e-3
+    assert abs(float((g ** 4).mean()) / 0.5 ** 4 - 3.0) < 0.05            # kurtosis of a normal
+    assert abs(float((g[1:] * g[:-1]).mean())) < 2e-3                      # neighbouring rows uncorrelated
+    again = torch.zeros_like(raw)
+    ops.sigma_noise(again, 0.5, seed=7)
+    other = torch.zeros_like(raw)
+    ops.sigma_noise(other, 0.5, seed=8)
+    assert torch.equal(again, raw) and not torch.equal(other, raw)
+    from nerf_rep_for_test_b200 import Network, RenderConfig, Renderer
+    net = Network(device=DEV)
+    net.load_state_dict(O.make_state_dict(3, 30.0, 0.0))
+    net.to(DEV).eval()
+    b = O.lego_batch(24, 24)
+    bc = {k: (cuda(v) if torch.is_tensor(v) else v) for k, v in b.items()}
+    clean = Renderer(net, RenderConfig(perturb=0), mode="fp32").render(bc)
+    outs = []
+    for _ in range(2):
+        r = Renderer(net, RenderConfig(perturb=0, raw_noise_std=1.0), mode="fp32")
+        outs.append(r.render(bc))
+    assert torch.equal(outs[0]["rgb_map"], outs[1]["rgb_map"])              # same seed sequence -> same noise
+    d = (outs[0]["acc_map"] - clean["acc_map"]).abs()
+    assert float(d.max()) > 1e-3 and torch.isfinite(outs[0]["rgb_map"]).all()
+    r = Renderer(net, RenderConfig(perturb=0, raw_noise_std=1.0, enable_ess=True), mode="bf16")
+    r.ess_mode = "skip"
+    with pytest.raises(L.NerfB200Error):
+        r.render(bc)
+
+
 def test_render_ess_skip_mode_structure_and_counts():
     sd = O.make_state_dict(6, 300.0, 6.0)
     for k in list(sd):                       # same (opaque) field for the coarse and the fine network
@@ -553,10 +631,6 @@ def test_unsupported_switches_fail_loudly():
     sd = O.make_state_dict(0)
     with pytest.raises(L.NerfB200Error):
         _renderer(sd, "fp32", use_viewdirs=False)
-    r = _renderer(sd, "fp32", raw_noise_std=1.0)
-    b = O.lego_batch(4, 4)
-    with pytest.raises(L.NerfB200Error):
-        r.render({k: (cuda(v) if torch.is_tensor(v) else v) for k, v in b.items()})
     with pytest.raises(L.NerfB200Error):   # CPU tensors are rejected: there is no CPU path
         ops.composite_forward(torch.zeros(1, 4, 4), torch.zeros(1, 4), torch.zeros(1, 3))
 

@@ -78,3 +78,28 @@ def test_train_steps_reduce_loss():
     losses = [float(step(ro.to(DEV), rd.to(DEV), target.to(DEV))) for _ in range(30)]
     assert losses[-1] < 0.7 * losses[0], losses[::5]
     assert all(torch.isfinite(p).all() for p in net.parameters())
+
+
+def test_training_with_density_noise():
+    """raw_noise_std > 0 (volume_renderer.py:310-314) in the training path: the noise is added in place to the
+    MLP output, so forward and analytic backward see the same density; maps and gradients stay finite, differ
+    from the noise-free step, and the optimisation still reduces the loss."""
+    sd, net, r, ro, rd, target = _setup(seed=5, gain=10.0, bias=0.0, n=256)
+    out0 = T.render_rays_train(r, ro.to(DEV), rd.to(DEV))
+    T.nerf_loss(out0, target.to(DEV)).backward()
+    g0 = net.model_fine.alpha_linear.weight.grad.clone()
+    net.zero_grad()
+    r.raw_noise_std = 1.0
+    out1 = T.render_rays_train(r, ro.to(DEV), rd.to(DEV))
+    T.nerf_loss(out1, target.to(DEV)).backward()
+    g1 = net.model_fine.alpha_linear.weight.grad.clone()
+    assert torch.isfinite(out1["rgb_map"]).all() and torch.isfinite(g1).all()
+    assert float((out1["acc_map"] - out0["acc_map"]).abs().max()) > 1e-3
+    assert float((g1 - g0).norm()) > 1e-3 * float(g0.norm())
+    net.zero_grad()
+    net.train()
+    r.perturb = 1
+    step = T.TrainStep(r)
+    losses = [float(step(ro.to(DEV), rd.to(DEV), target.to(DEV))) for _ in range(30)]
+    assert losses[-1] < 0.8 * losses[0], losses[::5]
+    assert all(torch.isfinite(p).all() for p in net.parameters())
