@@ -33,16 +33,43 @@ __device__ __forceinline__ float ray_norm(const float* __restrict__ d) {
   return __fsqrt_rn(__fmaf_rn(d[2], d[2], __fmaf_rn(d[1], d[1], __fmul_rn(d[0], d[0]))));
 }
 
-__device__ __forceinline__ double warp_excl_prod(double local, int lane, double* total) {
-  double v = local;
+// A = double in the exact variants (torch CPU's cumprod / sum accumulate in double), float in the fast-math
+// variant: there the fp64 path is pure overhead -- two SHFLs per scan step, eight F2F conversions per sample
+// (quarter-rate pipe) -- and made the kernel instruction-bound at the same 1.2 ms per frame whether or not the
+// samples were skipped (ncu launch lists of the dense and the sparse frame).
+template <typename A>
+__device__ __forceinline__ A warp_excl_prod(A local, int lane) {
+  A v = local;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
-    double o = __shfl_up_sync(0xffffffffu, v, d);
+    A o = __shfl_up_sync(0xffffffffu, v, d);
     if (lane >= d) v *= o;
   }
-  *total = __shfl_sync(0xffffffffu, v, 31);
-  double ex = __shfl_up_sync(0xffffffffu, v, 1);
-  return lane == 0 ? 1.0 : ex;
+  A ex = __shfl_up_sync(0xffffffffu, v, 1);
+  return lane == 0 ? (A)1 : ex;
+}
+
+// Sums of eight per-lane values over the warp with 9 shuffles instead of 8 x 5: each butterfly step keeps half of
+// the slots and sends the other half.  Returns the total of slot (lane >> 2), replicated over the slot's 4 lanes.
+__device__ __forceinline__ float warp_reduce8(float (&v)[8], int lane) {
+  bool up = (lane & 16) != 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float send = up ? v[j] : v[4 + j], keep = up ? v[4 + j] : v[j];
+    v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+  up = (lane & 8) != 0;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    float send = up ? v[j] : v[2 + j], keep = up ? v[2 + j] : v[j];
+    v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  up = (lane & 4) != 0;
+  float send = up ? v[0] : v[1], keep = up ? v[1] : v[0];
+  float t = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  t += __shfl_xor_sync(0xffffffffu, t, 2);
+  t += __shfl_xor_sync(0xffffffffu, t, 1);
+  return t;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -50,6 +77,9 @@ __device__ __forceinline__ double warp_sum(double v) {
   for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
   return v;
 }
+
+template <bool kFast> struct AccT { typedef double type; };
+template <> struct AccT<true> { typedef float type; };
 
 struct RaySamples {
   float alpha[kMaxPer];
@@ -67,7 +97,8 @@ __device__ __forceinline__ void ray_alpha_T(const float* __restrict__ raw_row,
                                             const float* __restrict__ z_row, float dnorm, int S,
                                             int per, int lane, float thr, RaySamples& rs,
                                             const uint32_t* __restrict__ keep_bits = nullptr, size_t bit_base = 0) {
-  double local = 1.0;
+  using A = typename AccT<kFast>::type;
+  A local = (A)1;
   float fac[kMaxPer];
 #pragma unroll
   for (int j = 0; j < kMaxPer; ++j) {
@@ -86,20 +117,19 @@ __device__ __forceinline__ void ray_alpha_T(const float* __restrict__ raw_row,
       // sigma == 0 (empty / skipped sample): exp(-0) = 1 and alpha = 0 exactly -- no fp64 exp needed
       a = sig == 0.f ? 0.f : __fsub_rn(1.f, exp_cr<kFast>(__fmul_rn(-sig, dist)));
       f = kErt ? __fsub_rn(1.f, a) : __fadd_rn(__fsub_rn(1.f, a), 1e-10f);
-      local *= (double)f;
+      local *= (A)f;
     }
     rs.alpha[j] = a;
     fac[j] = f;
   }
-  double total;
-  double run = warp_excl_prod(local, lane, &total);
+  A run = warp_excl_prod<A>(local, lane);
   int first = 1 << 30;
 #pragma unroll
   for (int j = 0; j < kMaxPer; ++j) {
     int i = lane * per + j;
     rs.T[j] = (float)run;
     if (kErt && j < per && i < S && rs.T[j] < thr) first = min(first, i);
-    run *= (double)fac[j];
+    run *= (A)fac[j];
   }
   if (kErt) {
 #pragma unroll
@@ -120,7 +150,8 @@ __device__ __forceinline__ void ray_outputs(const RaySamples& rs, const float* _
                                             float* __restrict__ rgb_map, float* __restrict__ disp_map,
                                             float* __restrict__ acc_map, float* __restrict__ depth_map,
                                             float* __restrict__ weights) {
-  double sr = 0, sg = 0, sb = 0, sd = 0, sa = 0;
+  using A = typename AccT<kFast>::type;
+  A sr = 0, sg = 0, sb = 0, sd = 0, sa = 0;
 #pragma unroll
   for (int j = 0; j < kMaxPer; ++j) {
     int i = lane * per + j;
@@ -130,14 +161,34 @@ __device__ __forceinline__ void ray_outputs(const RaySamples& rs, const float* _
       if (w != 0.f) {   // w == +0: every product below is +0 exactly (sigmoid and z are finite), skip the three exps
         float4 r4 = *reinterpret_cast<const float4*>(raw_row + (size_t)i * 4);
         float cr = sigmoid_ref<kFast>(r4.x), cg = sigmoid_ref<kFast>(r4.y), cb = sigmoid_ref<kFast>(r4.z);
-        sr += (double)__fmul_rn(w, cr);
-        sg += (double)__fmul_rn(w, cg);
-        sb += (double)__fmul_rn(w, cb);
-        sd += (double)__fmul_rn(w, z_row[i]);
-        sa += (double)w;
+        sr += (A)__fmul_rn(w, cr);
+        sg += (A)__fmul_rn(w, cg);
+        sb += (A)__fmul_rn(w, cb);
+        sd += (A)__fmul_rn(w, z_row[i]);
+        sa += (A)w;
       }
       if (weights) weights[ray * S + i] = w;
     }
+  }
+  if constexpr (kFast) {
+    // slots 0..4 = r, g, b, depth, acc; slot k's total ends up in lanes 4k..4k+3, which write their own output
+    float v[8] = {(float)sr, (float)sg, (float)sb, (float)sd, (float)sa, 0.f, 0.f, 0.f};
+    const float tot = warp_reduce8(v, lane);
+    const float acc = __shfl_sync(0xffffffffu, tot, 16);
+    if ((lane & 3) == 0) {
+      const int slot = lane >> 2;
+      if (slot < 3) {
+        rgb_map[ray * 3 + slot] = white_bkgd ? tot + (1.f - acc) : tot;
+      } else if (slot == 3) {
+        float q = __fdiv_rn(tot, acc);
+        float m = (q != q) ? q : fmaxf(1e-10f, q);  // torch.max propagates NaN (acc == 0)
+        depth_map[ray] = tot;
+        disp_map[ray] = __fdiv_rn(1.f, m);
+      } else if (slot == 4) {
+        acc_map[ray] = tot;
+      }
+    }
+    return;
   }
   sr = warp_sum(sr); sg = warp_sum(sg); sb = warp_sum(sb); sd = warp_sum(sd); sa = warp_sum(sa);
   if (lane == 0) {

@@ -15,7 +15,8 @@ constexpr int kEssMaxS = 256;
 
 __device__ __forceinline__ int grid_index(float p, int res) {
   // :996-1000: ((p - min) / (max - min)).clamp(0,1) * (res-1) -> long (truncation) -> clamp
-  float n = __fdiv_rn(__fsub_rn(p, -2.0f), __fsub_rn(2.0f, -2.0f));
+  // (max - min) = 4: scaling by a power of two is exact, so the multiply rounds exactly like the division
+  float n = __fmul_rn(__fsub_rn(p, -2.0f), 0.25f);
   n = fminf(fmaxf(n, 0.f), 1.f);
   int c = (int)__fmul_rn(n, (float)(res - 1));
   return min(max(c, 0), res - 1);
@@ -129,12 +130,12 @@ ess_compact_kernel(const uint8_t* __restrict__ grid, int res, const float* __res
     const long long idx = row0 + j * 32;
     bool keep = false;
     if (idx < total) {
-      long long ray = idx / S;
+      const unsigned ray = (unsigned)idx / (unsigned)S;   // total < 2^31 (checked by the entry point): 32-bit division
       float z = z_vals[idx];
       int g[3];
 #pragma unroll
       for (int c = 0; c < 3; ++c)
-        g[c] = grid_index(__fadd_rn(rays_o[ray * 3 + c], __fmul_rn(rays_d[ray * 3 + c], z)), res);
+        g[c] = grid_index(__fadd_rn(rays_o[ray * 3u + c], __fmul_rn(rays_d[ray * 3u + c], z)), res);
       keep = grid[((size_t)g[0] * res + g[1]) * res + g[2]] != 0;
       if (keep && z_term != nullptr) keep = z <= z_term[ray];
     }
