@@ -78,6 +78,21 @@ __global__ void pack_bf16_kernel(nerfb200_mlp_weights w, StageTable tab, unsigne
   }
 }
 
+// W'[n][k] = sum_j Wv[n][j] Wf[j][k] (and the analogous b'): a 256-term fp32 dot per output element.  Four
+// independent accumulators instead of one dependent FMA chain -- the re-pack runs after every optimizer step and the
+// single chain made the two tail packs the slowest of the small kernels of the training step (31 us each).
+__device__ __forceinline__ float dot256_strided(const float* __restrict__ a, const float* __restrict__ b, int b_stride) {
+  float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+#pragma unroll 4
+  for (int j = 0; j < 256; j += 4) {
+    v0 = fmaf(a[j + 0], b[(size_t)(j + 0) * b_stride], v0);
+    v1 = fmaf(a[j + 1], b[(size_t)(j + 1) * b_stride], v1);
+    v2 = fmaf(a[j + 2], b[(size_t)(j + 2) * b_stride], v2);
+    v3 = fmaf(a[j + 3], b[(size_t)(j + 3) * b_stride], v3);
+  }
+  return (v0 + v1) + (v2 + v3);
+}
+
 // fused stage 8F (mlp_layout.cuh): one thread per (n, k) of the [144][320] operand + the bias row
 __global__ void pack_bf16_fused_kernel(nerfb200_mlp_weights w, unsigned char* __restrict__ dst) {
   const int total = kFusedN * kFusedChunks * 64;
@@ -86,8 +101,7 @@ __global__ void pack_bf16_fused_kernel(nerfb200_mlp_weights w, unsigned char* __
       int n = i - total;
       float v = 0.f;
       if (n < 128) {
-        v = w.views_b[n];
-        for (int j = 0; j < 256; ++j) v = fmaf(w.views_w[(size_t)n * 283 + j], w.feature_b[j], v);
+        v = w.views_b[n] + dot256_strided(w.views_w + (size_t)n * 283, w.feature_b, 1);
       } else if (n == 128) {
         v = w.alpha_b[0];
       }
@@ -101,7 +115,7 @@ __global__ void pack_bf16_fused_kernel(nerfb200_mlp_weights w, unsigned char* __
     float v = 0.f;
     if (n < 128) {
       if (k < 256) {
-        for (int j = 0; j < 256; ++j) v = fmaf(w.views_w[(size_t)n * 283 + j], w.feature_w[(size_t)j * 256 + k], v);
+        v = dot256_strided(w.views_w + (size_t)n * 283, w.feature_w + k, 256);
       } else if (k - 256 < kChD) {
         v = w.views_w[(size_t)n * 283 + k];
       }
@@ -136,8 +150,8 @@ __global__ void pack_bf16_bwd_kernel(nerfb200_mlp_weights w, unsigned char* __re
     if (b == 0) { n = i % 256; kk = (i / 256) % 64; c = i / (256 * 64); }   // n fastest: coalesced reads of Wf rows
     const int k = c * 64 + kk;   // output index of the layer = K of the dgrad GEMM
     float v = 0.f;
-    if (b == 0) {   // fused tail W'[k][n] = sum_j Wv[k][j] Wf[j][n]  (same fp32 chain as pack_bf16_fused_kernel)
-      for (int j = 0; j < 256; ++j) v = fmaf(w.views_w[(size_t)k * 283 + j], w.feature_w[(size_t)j * 256 + n], v);
+    if (b == 0) {   // fused tail W'[k][n] = sum_j Wv[k][j] Wf[j][n]  (same fp32 arithmetic as pack_bf16_fused_kernel)
+      v = dot256_strided(w.views_w + (size_t)k * 283, w.feature_w + n, 256);
     } else {
       const int layer = 8 - b;   // 7..1
       v = layer == 5 ? w.pts_w[5][(size_t)k * 319 + kChX + n] : w.pts_w[layer][(size_t)k * 256 + n];

@@ -117,13 +117,24 @@ class TrainStep:
         self.models = (("coarse", renderer.coarse_model), ("fine", renderer.fine_model))
         self.params = [p for _, m in self.models for p in model_params(m)]
         dev = self.params[0].device
-        self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=dev)
+        n_total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(n_total, dtype=torch.float32, device=dev)
+        # The parameters themselves are re-pointed at slices of one flat fp32 buffer as well (names, shapes and values of
+        # the state_dict are unchanged), and Adam runs on that single tensor: torch's fused Adam over the 48 small
+        # tensors took 84 + 48 us per step (multi_tensor_apply chunks), over one 1.19 M-element tensor it is one
+        # short launch.  The update rule is elementwise, so the result is identical.
+        self.flat_param = torch.nn.Parameter(torch.empty(n_total, dtype=torch.float32, device=dev), requires_grad=True)
         off = 0
-        for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
+        with torch.no_grad():
+            for p in self.params:
+                n = p.numel()
+                self.flat_param.data[off:off + n].copy_(p.data.reshape(-1))
+                p.data = self.flat_param.data[off:off + n].view_as(p)
+                p.grad = self.flat[off:off + n].view_as(p)
+                off += n
+        self.flat_param.grad = self.flat
         self.grad_views = {name: [p.grad for p in model_params(m)] for name, m in self.models}
-        self.opt = torch.optim.Adam(self.params, lr=lr, eps=1e-8, fused=True)
+        self.opt = torch.optim.Adam([self.flat_param], lr=lr, eps=1e-8, fused=True)
         self.allreduce = FlatGradAllReduce(self.params, flat=self.flat)
 
     def __call__(self, rays_o, rays_d, target_rgb):
