@@ -391,7 +391,7 @@ def run_ours(args):
                                    "lego poses with random init); one view per GPU per step",
                        "H": H, "W": W, "n_samples": N_SAMPLES, "n_importance": N_IMPORTANCE, "mode": args.mode,
                        "parallelism": "rays sharded by view, no inter-GPU traffic", "l2": "flushed between steps "
-                       "(256 MB write); per-chunk intermediates stay in L2 by design"},
+                       "(256 MB write); the driver walks 32768-ray chunks whose intermediates (177 MB) exceed L2 as well"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "rays/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": r.h2d_bytes_per_image, "d2h_bytes_per_step": r.d2h_bytes_per_image(H, W)},

@@ -62,12 +62,13 @@ static void prof_end(cudaStream_t st, double rows) {
   ++g_prof_n;
 }
 
-// rays per internal chunk of the whole-pass driver: keeps the per-chunk intermediates
-// (z, raw, weights: ~5.4 KB/ray) inside the 126 MB L2 and bounds the workspace.
-constexpr int kChunkRays = 8192;
+// rays per internal chunk of the whole-pass driver: bounds the workspace (z, raw, weights: ~5.4 KB/ray = 177 MB).
+// Between two MLP launches of a chunk sit three short kernels (compositing, sample_pdf, coarse z) during which the
+// tensor pipe idles, so fewer, larger chunks win even though their intermediates no longer fit the 126 MB L2
+// (measured, same box, 800x800 frame: 8192 rays 138.8 ms, 16384 137.2, 24576 136.9, 32768 136.7).
+constexpr int kChunkRays = 32768;
 // Empty-space skipping sends only ~10 % of the rows through the MLP, so an 8192-ray chunk is a fraction of a
-// wave of the persistent kernel (measured: 22.9 ms per frame at 8192, 17.5 ms at 131 072 rays per chunk); the
-// dense path is insensitive to the chunk size (136.8 ms at 8192, 135.9 ms at 32 768).
+// wave of the persistent kernel (measured: 22.9 ms per frame at 8192, 17.5 ms at 131 072 rays per chunk).
 constexpr int kChunkRaysSparse = 131072;
 static int chunk_rays(const nerfb200_render_params* p) {
   if (const char* e = getenv("NERFB200_CHUNK_RAYS")) { int c = atoi(e); if (c >= 2048 && c % 2048 == 0) return c; }   // tuning experiments

@@ -116,7 +116,7 @@ def test_render_bf16_vs_reference_golden(name):
 # ------------------------------------------------------------------------------- full-size properties
 def test_full_frame_800x800_independence_and_oracle_subset():
     """BASELINE.json configs[1] at full size (640 000 rays): every ray's result is independent of where
-    it sits in the batch (8192-ray chunks, 512-row quads, tile slots, CTA pairs) -- a random subset
+    it sits in the batch (32768-ray chunks, 512-row quads, tile slots, CTA pairs) -- a random subset
     rendered on its own is BIT-IDENTICAL to the same pixels of the full frame -- and that subset agrees
     with the CPU oracle within the bf16 tolerances."""
     sd = O.make_state_dict(0, 25.0, 0.1)
