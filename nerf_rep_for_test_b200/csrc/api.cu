@@ -72,7 +72,21 @@ constexpr int kChunkRays = 32768;
 constexpr int kChunkRaysSparse = 131072;
 static int chunk_rays(const nerfb200_render_params* p) {
   if (const char* e = getenv("NERFB200_CHUNK_RAYS")) { int c = atoi(e); if (c >= 2048 && c % 2048 == 0) return c; }   // tuning experiments
-  return (p->occupancy_grid && p->ess_skip) ? kChunkRaysSparse : kChunkRays;
+  if (p->occupancy_grid && p->ess_skip) return kChunkRaysSparse;
+  // The literal ERT_COMPAT compositor groups rays in compat_chunk blocks, which must tile the chunk.
+  if ((p->variant & ~NERFB200_COMPOSITE_FAST_MATH) == NERFB200_COMPOSITE_ERT_COMPAT || p->mode != NERFB200_MODE_BF16) return kChunkRays;
+  // bf16 dense path: the persistent MLP kernel deals 512-row quads to (SMs / 2) CTA pairs, so a chunk whose coarse
+  // launch (n*S/512 quads) is a whole number of rounds wastes no partial last round; with S = 64 and S + U = 192
+  // that holds for the fine launch too (32 560 rays on 148 SMs: 55 and 165 full rounds instead of 55.35 and 166.05).
+  static int unit = 0;
+  if (unit == 0) {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 2)
+      sms = 148;
+    unit = (sms / 2) * 8;   // rays per round of the coarse launch at S = 64
+  }
+  const int c = kChunkRays / unit * unit;
+  return c > 0 ? c : kChunkRays;
 }
 
 struct Workspace {
