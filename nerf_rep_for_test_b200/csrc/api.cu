@@ -278,10 +278,16 @@ extern "C" size_t nerfb200_render_workspace_bytes(int n_rays, const nerfb200_ren
   return carve(nullptr, chunk, p->n_samples, p->n_importance).bytes;
 }
 
-extern "C" int nerfb200_render_rays(const void* packed_coarse, const void* packed_fine, const float* rays_o,
-                                    const float* rays_d, int n_rays, const float* z_table, const float* u,
-                                    const nerfb200_render_params* p, void* workspace, size_t workspace_bytes,
-                                    const nerfb200_maps* mc, const nerfb200_maps* mf, void* stream) {
+// called after the last kernel of every chunk has been enqueued (rays [r0, r0 + n) of the call are final once the
+// stream reaches this point); used by the host-buffer entry to start the device-to-host copies early
+struct ChunkHook {
+  virtual int done(int r0, int n) = 0;
+};
+
+static int render_rays_impl(const void* packed_coarse, const void* packed_fine, const float* rays_o,
+                            const float* rays_d, int n_rays, const float* z_table, const float* u,
+                            const nerfb200_render_params* p, void* workspace, size_t workspace_bytes,
+                            const nerfb200_maps* mc, const nerfb200_maps* mf, void* stream, ChunkHook* hook) {
   if (int e = check_params(p)) return e;
   if (n_rays == 0) return 0;
   NB_CHECK_ARG(packed_coarse && rays_o && rays_d && z_table && mc, "render_rays: null pointer");
@@ -351,8 +357,17 @@ extern "C" int nerfb200_render_rays(const void* packed_coarse, const void* packe
                                                  p->white_bkgd, p->compat_chunk, mf->rgb + (size_t)r0 * 3, mf->disp + r0,
                                                  mf->acc + r0, mf->depth + r0, nullptr, stream))) return e;
     }
+    if (hook && (e = hook->done(r0, n))) return e;
   }
   return 0;
+}
+
+extern "C" int nerfb200_render_rays(const void* packed_coarse, const void* packed_fine, const float* rays_o,
+                                    const float* rays_d, int n_rays, const float* z_table, const float* u,
+                                    const nerfb200_render_params* p, void* workspace, size_t workspace_bytes,
+                                    const nerfb200_maps* mc, const nerfb200_maps* mf, void* stream) {
+  return render_rays_impl(packed_coarse, packed_fine, rays_o, rays_d, n_rays, z_table, u, p, workspace, workspace_bytes,
+                          mc, mf, stream, nullptr);
 }
 
 // ---- host-buffer entry ------------------------------------------------------------------------
@@ -413,21 +428,46 @@ extern "C" int nerfb200_render_image_host(const void* packed_coarse, const void*
   dc.rgb = m; dc.disp = m + (size_t)n * 3; dc.acc = m + (size_t)n * 4; dc.depth = m + (size_t)n * 5;
   m += (size_t)n * 6;
   df.rgb = m; df.disp = m + (size_t)n * 3; df.acc = m + (size_t)n * 4; df.depth = m + (size_t)n * 5;
-  if ((e = nerfb200_render_rays(packed_coarse, packed_fine, s.rays_o, s.rays_d, n, z_table, u, p, s.ws, s.ws_bytes, &dc,
-                                p->n_importance > 0 ? &df : nullptr, stream))) return e;
-  auto d2h = [&](float* dst, const float* src, size_t nf) -> cudaError_t {
-    return dst ? cudaMemcpyAsync(dst, src, nf * 4, cudaMemcpyDeviceToHost, st) : cudaSuccess;
-  };
-  NB_CUDA(d2h(mc_host->rgb, dc.rgb, (size_t)n * 3));
-  NB_CUDA(d2h(mc_host->disp, dc.disp, n));
-  NB_CUDA(d2h(mc_host->acc, dc.acc, n));
-  NB_CUDA(d2h(mc_host->depth, dc.depth, n));
-  if (p->n_importance > 0 && mf_host) {
-    NB_CUDA(d2h(mf_host->rgb, df.rgb, (size_t)n * 3));
-    NB_CUDA(d2h(mf_host->disp, df.disp, n));
-    NB_CUDA(d2h(mf_host->acc, df.acc, n));
-    NB_CUDA(d2h(mf_host->depth, df.depth, n));
+  // The maps of a chunk are final as soon as its last compositing kernel has run: their device-to-host copies go to
+  // a side stream behind an event, so that all but the last chunk's 1.5 MB leave while the next chunk renders
+  // (the 30.7 MB of an 800x800 frame used to trail the render by ~0.8 ms).
+  static cudaStream_t copy_stream[64] = {};
+  static cudaEvent_t chunk_event[64] = {};
+  int dev = 0;
+  NB_CUDA(cudaGetDevice(&dev));
+  NB_CHECK_ARG(dev >= 0 && dev < 64, "render_image_host: device ordinal %d out of range", dev);
+  if (!copy_stream[dev]) {
+    NB_CUDA(cudaStreamCreateWithFlags(&copy_stream[dev], cudaStreamNonBlocking));
+    NB_CUDA(cudaEventCreateWithFlags(&chunk_event[dev], cudaEventDisableTiming));
   }
+  struct CopyOut : ChunkHook {
+    cudaStream_t st, cs;
+    cudaEvent_t ev;
+    const nerfb200_maps *dc, *df, *hc, *hf;
+    int done(int r0, int n) override {
+      NB_CUDA(cudaEventRecord(ev, st));
+      NB_CUDA(cudaStreamWaitEvent(cs, ev, 0));
+      for (int pass = 0; pass < 2; ++pass) {
+        const nerfb200_maps* d = pass ? df : dc;
+        const nerfb200_maps* h = pass ? hf : hc;
+        if (!d || !h) continue;
+        if (h->rgb) NB_CUDA(cudaMemcpyAsync(h->rgb + (size_t)r0 * 3, d->rgb + (size_t)r0 * 3, (size_t)n * 12, cudaMemcpyDeviceToHost, cs));
+        if (h->disp) NB_CUDA(cudaMemcpyAsync(h->disp + r0, d->disp + r0, (size_t)n * 4, cudaMemcpyDeviceToHost, cs));
+        if (h->acc) NB_CUDA(cudaMemcpyAsync(h->acc + r0, d->acc + r0, (size_t)n * 4, cudaMemcpyDeviceToHost, cs));
+        if (h->depth) NB_CUDA(cudaMemcpyAsync(h->depth + r0, d->depth + r0, (size_t)n * 4, cudaMemcpyDeviceToHost, cs));
+      }
+      return 0;
+    }
+  } hook;
+  hook.st = st; hook.cs = copy_stream[dev]; hook.ev = chunk_event[dev];
+  hook.dc = &dc; hook.df = p->n_importance > 0 ? &df : nullptr;
+  hook.hc = mc_host; hook.hf = p->n_importance > 0 ? mf_host : nullptr;
+  if ((e = render_rays_impl(packed_coarse, packed_fine, s.rays_o, s.rays_d, n, z_table, u, p, s.ws, s.ws_bytes, &dc,
+                            p->n_importance > 0 ? &df : nullptr, stream, &hook))) {
+    cudaStreamSynchronize(copy_stream[dev]);
+    return e;
+  }
+  NB_CUDA(cudaStreamSynchronize(copy_stream[dev]));
   NB_CUDA(cudaStreamSynchronize(st));
   return 0;
 }

@@ -427,6 +427,22 @@ def test_render_fp32_vs_oracle_rays_and_host_entry():
     assert bits_equal(part["rgb_map"], out["rgb_map"].reshape(-1, 3)[:101])
 
 
+def test_host_entry_multi_chunk_copies_match_device_render():
+    """nerfb200_render_image_host streams the maps of every finished chunk to the host on a side stream while the
+    next chunk renders; a 210x200 view spans two driver chunks (32 560 / 32 768 rays) with a ragged second one."""
+    sd = O.make_state_dict(4, 30.0, 0.2)
+    b = O.lego_batch(210, 200)
+    for mode, cfg in (("bf16", {}), ("bf16", dict(enable_ert=True)), ("bf16", dict(N_importance=0))):
+        r = _renderer(sd, mode, **cfg)
+        dev_out = r.render({k: (cuda(v) if torch.is_tensor(v) else v) for k, v in b.items()})
+        for _ in range(2):                       # second call reuses the pinned buffers and the side stream
+            host = r.render_host(b)
+            assert set(host) == set(dev_out)
+            for k in dev_out:
+                assert not host[k].is_cuda and host[k].shape == dev_out[k].shape
+                assert bits_equal(host[k], dev_out[k]), (cfg, k)
+
+
 def test_render_ess_noop_on_lego_pose():
     """with the initial grid no ray of a lego pose is highly empty -> identical output."""
     sd = O.make_state_dict(0)
