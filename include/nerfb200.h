@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define NERFB200_ABI_VERSION 2
+#define NERFB200_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define NERFB200_API __attribute__((visibility("default")))
@@ -219,6 +219,10 @@ NERFB200_API int nerfb200_ess_compact(const uint8_t* grid, int res, const float*
 NERFB200_API int nerfb200_mlp_forward_sparse(const void* packed, int mode, const float* rays_o,
                                 const float* rays_d, const float* z_vals, int n_rays, int n_samples,
                                 const int32_t* row_ids, const int32_t* n_active, float* raw, void* stream);
+/* ray_active[r] = 1 when the segment o + d*z, z in [z_table[0], z_table[n_samples-1]] (widened by 1e-3), meets
+ * the axis-aligned box [box_lo, box_hi] (3 floats each, HOST memory, +-INFINITY allowed), else 0. */
+NERFB200_API int nerfb200_ray_cull(const float* rays_o, const float* rays_d, int n_rays, const float* z_table,
+                      int n_samples, const float* box_lo, const float* box_hi, uint8_t* ray_active, void* stream);
 /* depth at which the transmittance implied by `weights` (T_i = 1 - sum_{j<i} w_j) first drops below
  * thr; +inf when it never does.  Used to cut the fine pass behind opaque surfaces (ERT). */
 NERFB200_API int nerfb200_ert_depth(const float* weights, const float* z_vals, int n_rays, int n_samples,
@@ -300,6 +304,13 @@ typedef struct nerfb200_render_params {
    * is 0.  eval_counts (device int64[2], may be NULL) accumulates the evaluated coarse / fine rows. */
   int ess_skip;
   int64_t* eval_counts;
+  /* ess_skip only.  cull_rays != 0: rays whose segment [z_table[0], z_table[n_samples-1]] misses the box
+   * [cull_lo, cull_hi] (world units) are culled before any per-sample work (nerfb200_ray_cull).  The caller must pass
+   * a box that contains every point whose grid lookup can be non-empty -- the occupied cells' bounds, +-INFINITY on a
+   * side whose boundary cell is occupied (lookups clamp), plus a margin; Renderer derives it from the grid. */
+  int cull_rays;
+  float cull_lo[3];
+  float cull_hi[3];
 } nerfb200_render_params;
 
 /* maps for one pass: rgb [n,3], disp/acc/depth [n] */

@@ -10,7 +10,7 @@
 #include "train_layout.cuh"
 
 // the ctypes binding (nerf_rep_for_test_b200/lib.py) mirrors these layouts field by field
-static_assert(sizeof(nerfb200_render_params) == 72, "nerfb200_render_params layout changed: update lib.py");
+static_assert(sizeof(nerfb200_render_params) == 104, "nerfb200_render_params layout changed: update lib.py");
 static_assert(sizeof(nerfb200_mlp_weights) == 24 * sizeof(void*), "nerfb200_mlp_weights layout changed");
 static_assert(sizeof(nerfb200_maps) == 4 * sizeof(void*), "nerfb200_maps layout changed");
 
@@ -99,6 +99,7 @@ struct Workspace {
   int32_t* counters;// [2] active-row counts of the coarse / fine pass
   float* z_term;    // [c] ERT depth from the coarse pass
   uint32_t* keep_bits;  // [ceil(c*(S+U)/32)] bit m = row m was evaluated (sparse ESS mode)
+  uint8_t* ray_active;  // [c] ray-level cull flags (sparse ESS mode with cull_rays)
   size_t bytes;
 };
 
@@ -121,6 +122,7 @@ static Workspace carve(void* base, int chunk, int S, int U) {
   w.counters = reinterpret_cast<int32_t*>(take(64));
   w.z_term = take((size_t)chunk);
   w.keep_bits = reinterpret_cast<uint32_t*>(take(((size_t)chunk * (S + U) + 31) / 32));
+  w.ray_active = reinterpret_cast<uint8_t*>(take(((size_t)chunk + 3) / 4));
   w.bytes = off;
   return w;
 }
@@ -319,32 +321,37 @@ static int render_rays_impl(const void* packed_coarse, const void* packed_fine, 
     // (the literal ERT_COMPAT compositor has no masked form: that combination keeps the zero fill)
     const bool masked = sparse && (p->variant & ~NERFB200_COMPOSITE_FAST_MATH) != NERFB200_COMPOSITE_ERT_COMPAT;
     const uint32_t* keep = masked ? ws.keep_bits : nullptr;
+    // ray-level culling against the occupied box, before any per-sample work
+    const uint8_t* active = nullptr;
+    if (masked && p->cull_rays) {
+      if ((e = nerfb200_ray_cull(ro, rd, n, z_table, S, p->cull_lo, p->cull_hi, ws.ray_active, stream))) return e;
+      active = ws.ray_active;
+    }
     const uint64_t noise_seed = p->seed ^ ((uint64_t)r0 * 0xD6E8FEB86659FD93ull);
     if (sparse) {
-      if ((e = nerfb200_ess_compact(p->occupancy_grid, p->grid_res, ro, rd, ws.z_coarse, nullptr, n, S, ws.row_ids,
-                                    ws.counters + 0, ws.keep_bits, stream))) return e;
+      if ((e = ess_compact_culled(p->occupancy_grid, p->grid_res, ro, rd, ws.z_coarse, nullptr, active, n, S, ws.row_ids,
+                                  ws.counters + 0, ws.keep_bits, stream))) return e;
       if ((e = mlp_forward_sparse_impl(packed_coarse, p->mode, ro, rd, ws.z_coarse, n, S, ws.row_ids, ws.counters + 0,
                                        ws.raw_c, !masked, stream))) return e;
     } else if ((e = nerfb200_mlp_forward(packed_coarse, p->mode, ro, rd, ws.z_coarse, n, S, ws.raw_c, stream))) return e;
     if (p->raw_noise_std > 0.f &&
         (e = nerfb200_sigma_noise(ws.raw_c, (long long)n * S, p->raw_noise_std, noise_seed + 0x632BE59BD9B4E019ull, stream))) return e;
-    if ((e = nerfb200_composite_forward_masked(ws.raw_c, ws.z_coarse, rd, keep, n, S, p->variant, p->ert_threshold,
-                                               p->white_bkgd, p->compat_chunk, mc->rgb + (size_t)r0 * 3, mc->disp + r0,
-                                               mc->acc + r0, mc->depth + r0, ws.weights, stream))) return e;
+    if ((e = composite_forward_culled(ws.raw_c, ws.z_coarse, rd, keep, active, n, S, p->variant, p->ert_threshold,
+                                      p->white_bkgd, p->compat_chunk, mc->rgb + (size_t)r0 * 3, mc->disp + r0,
+                                      mc->acc + r0, mc->depth + r0, ws.weights, stream))) return e;
     if (U > 0) {
       const float* uu = p->u_per_ray ? u + (size_t)r0 * U : u;
-      if ((e = nerfb200_sample_pdf_merge(ws.z_coarse, ws.weights, uu, p->u_per_ray, n, S, U, ws.z_all, nullptr, nullptr,
-                                         nullptr, stream))) return e;
+      if ((e = sample_pdf_merge_culled(ws.z_coarse, ws.weights, uu, p->u_per_ray, active, n, S, U, ws.z_all, stream))) return e;
       if (sparse) {
         // fine pass: skip samples in empty cells and, with ERT, samples behind the depth at which the
         // coarse transmittance fell below the threshold
         const float* zt = nullptr;
         if ((p->variant & ~NERFB200_COMPOSITE_FAST_MATH) != NERFB200_COMPOSITE_PLAIN) {
-          if ((e = nerfb200_ert_depth(ws.weights, ws.z_coarse, n, S, p->ert_threshold, ws.z_term, stream))) return e;
+          if ((e = ert_depth_culled(ws.weights, ws.z_coarse, active, n, S, p->ert_threshold, ws.z_term, stream))) return e;
           zt = ws.z_term;
         }
-        if ((e = nerfb200_ess_compact(p->occupancy_grid, p->grid_res, ro, rd, ws.z_all, zt, n, S + U, ws.row_ids,
-                                      ws.counters + 1, ws.keep_bits, stream))) return e;
+        if ((e = ess_compact_culled(p->occupancy_grid, p->grid_res, ro, rd, ws.z_all, zt, active, n, S + U, ws.row_ids,
+                                    ws.counters + 1, ws.keep_bits, stream))) return e;
         if ((e = mlp_forward_sparse_impl(packed_fine, p->mode, ro, rd, ws.z_all, n, S + U, ws.row_ids, ws.counters + 1,
                                          ws.raw_f, !masked, stream))) return e;
         if (p->eval_counts) {   // optional statistics: evaluated rows per pass, accumulated over the call
@@ -353,9 +360,9 @@ static int render_rays_impl(const void* packed_coarse, const void* packed_fine, 
       } else if ((e = nerfb200_mlp_forward(packed_fine, p->mode, ro, rd, ws.z_all, n, S + U, ws.raw_f, stream))) return e;
       if (p->raw_noise_std > 0.f &&
           (e = nerfb200_sigma_noise(ws.raw_f, (long long)n * (S + U), p->raw_noise_std, noise_seed + 0x94D049BB133111EBull, stream))) return e;
-      if ((e = nerfb200_composite_forward_masked(ws.raw_f, ws.z_all, rd, keep, n, S + U, p->variant, p->ert_threshold,
-                                                 p->white_bkgd, p->compat_chunk, mf->rgb + (size_t)r0 * 3, mf->disp + r0,
-                                                 mf->acc + r0, mf->depth + r0, nullptr, stream))) return e;
+      if ((e = composite_forward_culled(ws.raw_f, ws.z_all, rd, keep, active, n, S + U, p->variant, p->ert_threshold,
+                                        p->white_bkgd, p->compat_chunk, mf->rgb + (size_t)r0 * 3, mf->disp + r0,
+                                        mf->acc + r0, mf->depth + r0, nullptr, stream))) return e;
     }
     if (hook && (e = hook->done(r0, n))) return e;
   }

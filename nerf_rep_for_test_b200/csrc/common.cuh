@@ -52,6 +52,21 @@ void count_launch(int n = 1);
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Internal variants of public entry points that take the per-ray flags of nerfb200_ray_cull (NULL = every ray):
+// a culled ray is skipped by the kernel (the compositor writes the background maps for it).  Used by the sparse
+// whole-pass driver only; the public signatures stay as they are.
+int composite_forward_culled(const float* raw, const float* z_vals, const float* rays_d, const uint32_t* keep_bits,
+                             const uint8_t* ray_active, int n_rays, int n_samples, int variant, float ert_threshold,
+                             int white_bkgd, int compat_chunk, float* rgb_map, float* disp_map, float* acc_map,
+                             float* depth_map, float* weights, void* stream);
+int sample_pdf_merge_culled(const float* z_coarse, const float* weights, const float* u, int u_per_ray,
+                            const uint8_t* ray_active, int n_rays, int n_samples, int n_u, float* z_all, void* stream);
+int ess_compact_culled(const uint8_t* grid, int res, const float* rays_o, const float* rays_d, const float* z_vals,
+                       const float* z_term, const uint8_t* ray_active, int n_rays, int n_samples, int32_t* row_ids,
+                       int32_t* n_active, uint32_t* keep_bits, void* stream);
+int ert_depth_culled(const float* weights, const float* z_vals, const uint8_t* ray_active, int n_rays, int n_samples,
+                     float thr, float* z_term, void* stream);
+
 // Counter-based RNG shared by the stratified jitter (a2) and the density noise (a5): a uniform in
 // [0,1) keyed on (seed, a, b).  The reference draws from torch's global generator, whose stream a
 // kernel cannot reproduce; only the distribution is matched.

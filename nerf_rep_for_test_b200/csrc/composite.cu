@@ -214,10 +214,24 @@ composite_kernel(const float* __restrict__ raw, const float* __restrict__ z_vals
                  const float* __restrict__ rays_d, int n_rays, int S, float thr, int white_bkgd,
                  float* __restrict__ rgb_map, float* __restrict__ disp_map,
                  float* __restrict__ acc_map, float* __restrict__ depth_map,
-                 float* __restrict__ weights, const uint32_t* __restrict__ keep_bits) {
+                 float* __restrict__ weights, const uint32_t* __restrict__ keep_bits,
+                 const uint8_t* __restrict__ ray_active) {
   int lane = threadIdx.x & 31;
   size_t ray = (size_t)blockIdx.x * kCompWarps + (threadIdx.x >> 5);
   if (ray >= (size_t)n_rays) return;
+  if (ray_active != nullptr && !ray_active[ray]) {
+    // ray culled against the occupied region (nerfb200_ray_cull): every sample would be skipped, all weights are
+    // 0 -- the maps below are exactly what the code path underneath produces for such a ray (0/0 -> NaN disparity
+    // included); the weights row is not written (nothing downstream reads it for a culled ray)
+    if (lane == 0) {
+      const float bg = white_bkgd ? 1.f : 0.f;
+      rgb_map[ray * 3 + 0] = bg; rgb_map[ray * 3 + 1] = bg; rgb_map[ray * 3 + 2] = bg;
+      disp_map[ray] = __fdiv_rn(1.f, __fdiv_rn(0.f, 0.f));
+      acc_map[ray] = 0.f;
+      depth_map[ray] = 0.f;
+    }
+    return;
+  }
   int per = (S + 31) / 32;
   const float* raw_row = raw + ray * S * 4;
   const float* z_row = z_vals + ray * S;
@@ -383,6 +397,15 @@ extern "C" int nerfb200_composite_forward_masked(const float* raw, const float* 
                                                  float ert_threshold, int white_bkgd, int compat_chunk,
                                                  float* rgb_map, float* disp_map, float* acc_map, float* depth_map,
                                                  float* weights, void* stream) {
+  return nb::composite_forward_culled(raw, z_vals, rays_d, keep_bits, nullptr, n_rays, n_samples, variant, ert_threshold,
+                                      white_bkgd, compat_chunk, rgb_map, disp_map, acc_map, depth_map, weights, stream);
+}
+
+// + ray_active (may be NULL): per-ray flags of nerfb200_ray_cull; internal to the whole-pass driver
+int nb::composite_forward_culled(const float* raw, const float* z_vals, const float* rays_d, const uint32_t* keep_bits,
+                                 const uint8_t* ray_active, int n_rays, int n_samples, int variant, float ert_threshold,
+                                 int white_bkgd, int compat_chunk, float* rgb_map, float* disp_map, float* acc_map,
+                                 float* depth_map, float* weights, void* stream) {
   NB_CHECK_ARG(n_rays <= 0 || (raw && z_vals && rays_d && rgb_map && disp_map && acc_map && depth_map),
                "composite_forward: null pointer");
   NB_CHECK_ARG(n_samples >= 1 && n_samples <= 32 * kMaxPer, "composite_forward: n_samples=%d out of range [1,%d]",
@@ -396,14 +419,14 @@ extern "C" int nerfb200_composite_forward_masked(const float* raw, const float* 
   int blocks = ceil_div(n_rays, kCompWarps);
 #define NB_COMPOSITE(ERT, FAST, THR)                                                                              \
   composite_kernel<ERT, FAST><<<blocks, kCompWarps * 32, 0, st>>>(raw, z_vals, rays_d, n_rays, n_samples, THR, white_bkgd, \
-                                                                  rgb_map, disp_map, acc_map, depth_map, weights, keep_bits)
+                                                                  rgb_map, disp_map, acc_map, depth_map, weights, keep_bits, ray_active)
   if (variant == NERFB200_COMPOSITE_PLAIN) {
     if (fast) NB_COMPOSITE(false, true, 0.f); else NB_COMPOSITE(false, false, 0.f);
   } else if (variant == NERFB200_COMPOSITE_ERT) {
     if (fast) NB_COMPOSITE(true, true, ert_threshold); else NB_COMPOSITE(true, false, ert_threshold);
   } else {
     NB_CHECK_ARG(compat_chunk > 0, "composite_forward: compat_chunk must be > 0");
-    NB_CHECK_ARG(keep_bits == nullptr, "composite_forward: the ERT_COMPAT variant has no masked form");
+    NB_CHECK_ARG(keep_bits == nullptr && ray_active == nullptr, "composite_forward: the ERT_COMPAT variant has no masked form");
     composite_ert_compat_kernel<<<ceil_div(n_rays, compat_chunk), 1024, 0, st>>>(
         raw, z_vals, rays_d, n_rays, n_samples, ert_threshold, white_bkgd, compat_chunk, rgb_map, disp_map, acc_map,
         depth_map, weights);

@@ -119,7 +119,7 @@ ess_compact_kernel(const uint8_t* __restrict__ grid, int res, const float* __res
                    const float* __restrict__ rays_d, const float* __restrict__ z_vals,
                    const float* __restrict__ z_term, long long total, int S,
                    int32_t* __restrict__ row_ids, int32_t* __restrict__ n_active,
-                   uint32_t* __restrict__ keep_bits) {
+                   uint32_t* __restrict__ keep_bits, const uint8_t* __restrict__ ray_active) {
   __shared__ int s_off[32];
   __shared__ int s_base;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -131,13 +131,15 @@ ess_compact_kernel(const uint8_t* __restrict__ grid, int res, const float* __res
     bool keep = false;
     if (idx < total) {
       const unsigned ray = (unsigned)idx / (unsigned)S;   // total < 2^31 (checked by the entry point): 32-bit division
-      float z = z_vals[idx];
-      int g[3];
+      if (ray_active == nullptr || ray_active[ray]) {     // a culled ray has no sample in an occupied cell
+        float z = z_vals[idx];
+        int g[3];
 #pragma unroll
-      for (int c = 0; c < 3; ++c)
-        g[c] = grid_index(__fadd_rn(rays_o[ray * 3u + c], __fmul_rn(rays_d[ray * 3u + c], z)), res);
-      keep = grid[((size_t)g[0] * res + g[1]) * res + g[2]] != 0;
-      if (keep && z_term != nullptr) keep = z <= z_term[ray];
+        for (int c = 0; c < 3; ++c)
+          g[c] = grid_index(__fadd_rn(rays_o[ray * 3u + c], __fmul_rn(rays_d[ray * 3u + c], z)), res);
+        keep = grid[((size_t)g[0] * res + g[1]) * res + g[2]] != 0;
+        if (keep && z_term != nullptr) keep = z <= z_term[ray];
+      }
     }
     m[j] = __ballot_sync(0xffffffffu, keep);
     if (lane == 0) {
@@ -166,15 +168,48 @@ ess_compact_kernel(const uint8_t* __restrict__ grid, int res, const float* __res
 }
 
 __global__ void ert_depth_kernel(const float* __restrict__ weights, const float* __restrict__ z_vals, int n_rays,
-                                 int S, float thr, float* __restrict__ z_term) {
+                                 int S, float thr, float* __restrict__ z_term, const uint8_t* __restrict__ ray_active) {
   int ray = blockIdx.x * blockDim.x + threadIdx.x;
   if (ray >= n_rays) return;
+  if (ray_active != nullptr && !ray_active[ray]) return;   // culled ray: z_term is never read
   float acc = 0.f, zt = __int_as_float(0x7f800000);
   for (int i = 0; i < S; ++i) {
     if (1.f - acc < thr) { zt = z_vals[(size_t)ray * S + i]; break; }
     acc += weights[(size_t)ray * S + i];
   }
   z_term[ray] = zt;
+}
+
+// Ray-level culling for the skipping mode: slab test of the segment o + d*z, z in [z_near, z_far], against the
+// axis-aligned box of the occupied cells.  The box comes from the caller (Renderer: min / max occupied cell index per
+// axis, widened by a margin, open-ended on a side whose boundary cell is occupied because grid_index clamps), so the
+// test is conservative with respect to the per-sample lookup: a culled ray has no sample in an occupied cell, at any
+// z of the coarse or the fine pass.  On a scene that fills a fraction of the frame most rays stop here and never reach
+// the compaction, sample_pdf or the compositor's per-sample work.
+__global__ void ray_cull_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, int n_rays,
+                                const float* __restrict__ z_table, int S, float lx, float ly, float lz, float hx, float hy,
+                                float hz, uint8_t* __restrict__ ray_active) {
+  int ray = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ray >= n_rays) return;
+  const float lo[3] = {lx, ly, lz}, hi[3] = {hx, hy, hz};
+  float t0 = z_table[0], t1 = z_table[S - 1];
+  if (t0 > t1) { float t = t0; t0 = t1; t1 = t; }
+  const float pad = 1e-3f * fmaxf(1.f, fabsf(t1));   // rounding of o + d*z in the lookups is ~1e-6
+  t0 -= pad; t1 += pad;
+  bool hit = true;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float o = rays_o[(size_t)ray * 3 + c], d = rays_d[(size_t)ray * 3 + c];
+    if (fabsf(d) < 1e-12f) {
+      hit = hit && (o >= lo[c]) && (o <= hi[c]);
+    } else {
+      float ta = (lo[c] - o) / d, tb = (hi[c] - o) / d;   // +-inf for an open side
+      if (ta > tb) { float t = ta; ta = tb; tb = t; }
+      t0 = fmaxf(t0, ta);
+      t1 = fminf(t1, tb);
+    }
+  }
+  ray_active[ray] = (hit && t0 <= t1) ? 1 : 0;
 }
 
 __global__ void accumulate_counts_kernel(const int32_t* __restrict__ counts, long long* __restrict__ totals) {
@@ -188,6 +223,13 @@ using namespace nb;
 extern "C" int nerfb200_ess_compact(const uint8_t* grid, int res, const float* rays_o, const float* rays_d,
                                     const float* z_vals, const float* z_term, int n_rays, int n_samples,
                                     int32_t* row_ids, int32_t* n_active, uint32_t* keep_bits, void* stream) {
+  return ess_compact_culled(grid, res, rays_o, rays_d, z_vals, z_term, nullptr, n_rays, n_samples, row_ids, n_active,
+                            keep_bits, stream);
+}
+
+int nb::ess_compact_culled(const uint8_t* grid, int res, const float* rays_o, const float* rays_d, const float* z_vals,
+                           const float* z_term, const uint8_t* ray_active, int n_rays, int n_samples, int32_t* row_ids,
+                           int32_t* n_active, uint32_t* keep_bits, void* stream) {
   NB_CHECK_ARG(n_active, "ess_compact: null counter");
   NB_CHECK_ARG(n_rays <= 0 || (grid && rays_o && rays_d && z_vals && row_ids), "ess_compact: null pointer");
   NB_CHECK_ARG(res >= 1 && res <= 1024, "ess_compact: bad grid resolution %d", res);
@@ -196,17 +238,36 @@ extern "C" int nerfb200_ess_compact(const uint8_t* grid, int res, const float* r
   if (n_rays == 0) return 0;
   long long total = (long long)n_rays * n_samples;
   ess_compact_kernel<<<ceil_div(total, kCompactRows), kCompactThreads, 0, (cudaStream_t)stream>>>(
-      grid, res, rays_o, rays_d, z_vals, z_term, total, n_samples, row_ids, n_active, keep_bits);
+      grid, res, rays_o, rays_d, z_vals, z_term, total, n_samples, row_ids, n_active, keep_bits, ray_active);
   NB_LAUNCH_OK("ess_compact_kernel");
   return 0;
 }
 
 extern "C" int nerfb200_ert_depth(const float* weights, const float* z_vals, int n_rays, int n_samples, float thr,
                                   float* z_term, void* stream) {
+  return ert_depth_culled(weights, z_vals, nullptr, n_rays, n_samples, thr, z_term, stream);
+}
+
+extern "C" int nerfb200_ray_cull(const float* rays_o, const float* rays_d, int n_rays, const float* z_table, int n_samples,
+                                 const float* box_lo, const float* box_hi, uint8_t* ray_active, void* stream) {
+  NB_CHECK_ARG(n_rays <= 0 || (rays_o && rays_d && z_table && ray_active), "ray_cull: null pointer");
+  NB_CHECK_ARG(box_lo && box_hi, "ray_cull: null box");
+  NB_CHECK_ARG(n_rays >= 0 && n_samples >= 1, "ray_cull: bad sizes");
+  if (n_rays == 0) return 0;
+  ray_cull_kernel<<<ceil_div(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, n_rays, z_table, n_samples, box_lo[0],
+                                                                         box_lo[1], box_lo[2], box_hi[0], box_hi[1],
+                                                                         box_hi[2], ray_active);
+  NB_LAUNCH_OK("ray_cull_kernel");
+  return 0;
+}
+
+int nb::ert_depth_culled(const float* weights, const float* z_vals, const uint8_t* ray_active, int n_rays, int n_samples,
+                         float thr, float* z_term, void* stream) {
   NB_CHECK_ARG(n_rays <= 0 || (weights && z_vals && z_term), "ert_depth: null pointer");
   NB_CHECK_ARG(n_rays >= 0 && n_samples >= 1, "ert_depth: bad sizes");
   if (n_rays == 0) return 0;
-  ert_depth_kernel<<<ceil_div(n_rays, 128), 128, 0, (cudaStream_t)stream>>>(weights, z_vals, n_rays, n_samples, thr, z_term);
+  ert_depth_kernel<<<ceil_div(n_rays, 128), 128, 0, (cudaStream_t)stream>>>(weights, z_vals, n_rays, n_samples, thr, z_term,
+                                                                            ray_active);
   NB_LAUNCH_OK("ert_depth_kernel");
   return 0;
 }

@@ -157,7 +157,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 sample_pdf_merge_kernel(const float* __restrict__ z_coarse, const float* __restrict__ weights,
                         const float* __restrict__ u_g, int u_per_ray, int n_rays, int S, int n_u,
                         float* __restrict__ z_all, float* __restrict__ z_samples,
-                        int32_t* __restrict__ inds, float* __restrict__ cdf_out) {
+                        int32_t* __restrict__ inds, float* __restrict__ cdf_out,
+                        const uint8_t* __restrict__ ray_active) {
   __shared__ float s_z[kWarpsPerBlock][kMaxS];
   __shared__ float s_cdf[kWarpsPerBlock][kMaxS];
   __shared__ float s_bins[kWarpsPerBlock][kMaxS];
@@ -165,6 +166,7 @@ sample_pdf_merge_kernel(const float* __restrict__ z_coarse, const float* __restr
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int ray = blockIdx.x * kWarpsPerBlock + warp;
   if (ray >= n_rays) return;
+  if (ray_active != nullptr && !ray_active[ray]) return;   // culled ray: its fine samples are never looked at
   const int nbins = S - 1;   // cdf / t_mid entries (63)
   const int nw = S - 2;      // interior weights (62)
   float* zr = s_z[warp];
@@ -248,6 +250,10 @@ sample_pdf_merge_kernel(const float* __restrict__ z_coarse, const float* __restr
 
 using namespace nb;
 
+static int sample_pdf_merge_impl(const float* z_coarse, const float* weights, const float* u, int u_per_ray,
+                                 const uint8_t* ray_active, int n_rays, int n_samples, int n_u, float* z_all,
+                                 float* z_samples, int32_t* inds, float* cdf, void* stream);
+
 extern "C" int nerfb200_raygen(const float* pose, const float* intrinsics, int H, int W,
                                float* rays_o, float* rays_d, void* stream) {
   NB_CHECK_ARG(pose && intrinsics && rays_o && rays_d, "raygen: null pointer");
@@ -286,13 +292,26 @@ extern "C" int nerfb200_sample_pdf_merge(const float* z_coarse, const float* wei
                                          int u_per_ray, int n_rays, int n_samples, int n_u,
                                          float* z_all, float* z_samples, int32_t* inds, float* cdf,
                                          void* stream) {
+  return sample_pdf_merge_impl(z_coarse, weights, u, u_per_ray, nullptr, n_rays, n_samples, n_u, z_all, z_samples, inds,
+                               cdf, stream);
+}
+
+int nb::sample_pdf_merge_culled(const float* z_coarse, const float* weights, const float* u, int u_per_ray,
+                                const uint8_t* ray_active, int n_rays, int n_samples, int n_u, float* z_all, void* stream) {
+  return sample_pdf_merge_impl(z_coarse, weights, u, u_per_ray, ray_active, n_rays, n_samples, n_u, z_all, nullptr,
+                               nullptr, nullptr, stream);
+}
+
+static int sample_pdf_merge_impl(const float* z_coarse, const float* weights, const float* u, int u_per_ray,
+                                 const uint8_t* ray_active, int n_rays, int n_samples, int n_u, float* z_all,
+                                 float* z_samples, int32_t* inds, float* cdf, void* stream) {
   NB_CHECK_ARG(n_rays <= 0 || (z_coarse && weights && u && z_all), "sample_pdf_merge: null pointer");
   NB_CHECK_ARG(n_samples >= 3 && n_samples <= kMaxS, "sample_pdf_merge: n_samples=%d out of range [3,%d]", n_samples, kMaxS);
   NB_CHECK_ARG(n_u >= 1 && n_u <= kMaxU, "sample_pdf_merge: n_u=%d out of range [1,%d]", n_u, kMaxU);
   NB_CHECK_ARG(n_rays >= 0, "sample_pdf_merge: negative n_rays");
   if (n_rays == 0) return 0;
   sample_pdf_merge_kernel<<<ceil_div(n_rays, kWarpsPerBlock), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-      z_coarse, weights, u, u_per_ray, n_rays, n_samples, n_u, z_all, z_samples, inds, cdf);
+      z_coarse, weights, u, u_per_ray, n_rays, n_samples, n_u, z_all, z_samples, inds, cdf, ray_active);
   NB_LAUNCH_OK("sample_pdf_merge_kernel");
   return 0;
 }

@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("NERFB200_LIB") or os.path.join(HERE, "libnerfb200.so"
 MODE_FP32, MODE_BF16 = 0, 1
 COMPOSITE_PLAIN, COMPOSITE_ERT, COMPOSITE_ERT_COMPAT = 0, 1, 2
 COMPOSITE_FAST_MATH = 0x10          # OR-ed into PLAIN / ERT (include/nerfb200.h)
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _f = C.POINTER(C.c_float)
 _vp = C.c_void_p
@@ -38,7 +38,7 @@ class RenderParams(C.Structure):
                 ("variant", C.c_int), ("white_bkgd", C.c_int), ("perturb", C.c_int),
                 ("u_per_ray", C.c_int), ("compat_chunk", C.c_int), ("ert_threshold", C.c_float),
                 ("raw_noise_std", C.c_float), ("seed", C.c_uint64), ("occupancy_grid", _vp), ("grid_res", C.c_int), ("ess_skip", C.c_int),
-                ("eval_counts", _vp)]
+                ("eval_counts", _vp), ("cull_rays", C.c_int), ("cull_lo", C.c_float * 3), ("cull_hi", C.c_float * 3)]
 
 
 class KiloCamera(C.Structure):
@@ -95,6 +95,7 @@ SIGNATURES = {
     "nerfb200_ess_update": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     "nerfb200_ess_compact": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "nerfb200_mlp_forward_sparse": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    "nerfb200_ray_cull": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), _vp, _vp]),
     "nerfb200_ert_depth": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_float, _vp, _vp]),
     "nerfb200_accumulate_counts": (C.c_int, [_vp, _vp, _vp]),
     "nerfb200_kilo_param_size": (C.c_int, []),

@@ -290,6 +290,18 @@ def mlp_forward_sparse(packed, rays_o, rays_d, z_vals, row_ids, n_active):
     return raw
 
 
+def ray_cull(rays_o, rays_d, z_table, box_lo, box_hi):
+    """uint8 [n]: 1 where the ray segment over [z_table[0], z_table[-1]] meets the box (nerfb200_ray_cull)."""
+    import ctypes as C
+    rays_o, rays_d, z_table = _f(rays_o), _f(rays_d), _f(z_table)
+    n = rays_o.shape[0]
+    active = torch.empty(n, dtype=torch.uint8, device=rays_o.device)
+    lo, hi = (C.c_float * 3)(*[float(v) for v in box_lo]), (C.c_float * 3)(*[float(v) for v in box_hi])
+    L.check(L.load().nerfb200_ray_cull(L.dev(rays_o), L.dev(rays_d), n, L.dev(z_table), z_table.numel(), lo, hi,
+                                      L.dev(active, torch.uint8), L.stream_ptr()), "ray_cull")
+    return active
+
+
 def ert_depth(weights, z_vals, thr):
     weights, z_vals = _f(weights), _f(z_vals)
     n, S = z_vals.shape

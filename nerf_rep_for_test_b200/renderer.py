@@ -147,6 +147,8 @@ class Renderer(PathRenderingMixin):
         # "resample" = the reference's ESS (:1009-1087); "skip" = samples in empty cells (and, with ERT,
         # fine samples behind the coarse termination depth) are never sent through the MLP
         self.ess_mode = "resample"
+        self.cull_rays = True      # ess_mode="skip": rays that miss the box of the occupied cells stop before any per-sample work
+        self._box = None
         self.eval_counts = None
         self.use_cuda_kernels = True
         self.seed = 0
@@ -285,9 +287,39 @@ class Renderer(PathRenderingMixin):
                 if self.eval_counts is None:
                     self.eval_counts = torch.zeros(2, dtype=torch.int64, device=self.device)
                 p.eval_counts = self.eval_counts.data_ptr()
+                if self.cull_rays:
+                    lo, hi = self._occupied_box()
+                    p.cull_rays = 1
+                    for c in range(3):
+                        p.cull_lo[c], p.cull_hi[c] = lo[c], hi[c]
         if self.mode == "bf16" and p.variant != L.COMPOSITE_ERT_COMPAT:
             p.variant |= L.COMPOSITE_FAST_MATH     # the bf16 MLP output carries 1e-3 already: MUFU exp / sigmoid
         return p
+
+    def _occupied_box(self):
+        """World-space box that contains every point whose occupancy lookup can be non-empty (ess_mode='skip').
+        The lookup (:992-1007) maps p to cell clamp(int(clamp((p + 2) / 4, 0, 1) * (R - 1)), 0, R - 1): cell i covers
+        [-2 + 4 i / (R-1), -2 + 4 (i+1) / (R-1)), cell 0 also everything below -2 and cell R-1 everything from +2 up,
+        so a side whose boundary cell is occupied is left open.  A margin of one hundredth of a cell covers the
+        rounding of o + d z."""
+        g = self.occupancy_grid
+        key = (g.data_ptr(), g._version, tuple(g.shape))
+        if self._box is not None and self._box[0] == key:
+            return self._box[1]
+        R = g.shape[0]
+        inf = float("inf")
+        lo, hi = [inf] * 3, [-inf] * 3
+        gb = g.bool()
+        for c in range(3):
+            occ = gb.any(dim=tuple(d for d in range(3) if d != c)).nonzero().flatten()
+            if occ.numel() == 0:
+                continue                         # empty grid: lo > hi, every ray is culled
+            i0, i1 = int(occ[0]), int(occ[-1])
+            cell = 4.0 / (R - 1)
+            lo[c] = -inf if i0 == 0 else -2.0 + cell * i0 - 0.01 * cell
+            hi[c] = inf if i1 == R - 1 else -2.0 + cell * (i1 + 1) + 0.01 * cell
+        self._box = (key, (lo, hi))
+        return lo, hi
 
     def _workspace(self, nbytes):
         if self._ws is None or self._ws.numel() < nbytes:

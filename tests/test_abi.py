@@ -42,7 +42,7 @@ def test_struct_sizes_match_c_layout():
     from nerf_rep_for_test_b200 import lib as L
     assert ctypes.sizeof(L.MlpWeights) == 24 * 8
     assert ctypes.sizeof(L.Maps) == 32
-    assert ctypes.sizeof(L.RenderParams) == 72   # 8 ints, float, pad, u64, ptr, 2 ints, ptr (static_assert in api.cu)
+    assert ctypes.sizeof(L.RenderParams) == 104  # 8 ints, 2 floats, u64, ptr, 2 ints, ptr, int, 6 floats, pad (static_assert in api.cu)
 
 
 def test_argument_errors_are_reported_not_fatal(built_lib):

@@ -569,6 +569,53 @@ def test_sigma_noise_distribution_and_render_switch():
         r.render(bc)
 
 
+def test_ray_culling_is_conservative_and_changes_nothing():
+    """ess_mode='skip': rays that miss the box of the occupied cells are culled before any per-sample work.  The cull
+    is conservative (no culled ray has a sample in an occupied cell, coarse or fine, also for grids that touch the
+    boundary, where lookups clamp) and the rendered maps are bit-identical with and without it."""
+    from nerf_rep_for_test_b200 import Network, RenderConfig, Renderer
+    sd = O.make_state_dict(6, 300.0, 6.0)
+    for k in list(sd):
+        if k.startswith("model_fine."):
+            sd[k] = sd["model." + k[len("model_fine."):]].clone()
+    net = Network(device=DEV)
+    net.load_state_dict(sd)
+    net.to(DEV).eval()
+    b = O.lego_batch(64, 64)
+    bc = {k: (cuda(v) if torch.is_tensor(v) else v) for k, v in b.items()}
+    ro, rd = O.get_rays(64, 64, b["pose"][0], b["intrinsics"][0])
+    res = 128
+    gc = torch.stack(torch.meshgrid([torch.arange(res)] * 3, indexing="ij"), -1).float() / (res - 1) * 2 - 1
+    slab = gc[..., 0] >= 0.98                                  # occupied up to (and including) the +x boundary cells
+    off_centre = torch.norm(gc - torch.tensor([0.2, -0.15, 0.1]), dim=-1) <= 0.2
+    empty = torch.zeros(res, res, res, dtype=torch.bool)
+    seen_partial = 0
+    for grid in (_blob_grid(), off_centre, slab, empty):
+        outs, counts, active = {}, {}, None
+        for cull in (False, True):
+            r = Renderer(net, RenderConfig(perturb=0, enable_ess=True, enable_ert=True), mode="bf16")
+            r.occupancy_grid = grid.to(DEV)
+            r.ess_mode = "skip"
+            r.cull_rays = cull
+            outs[cull] = r.render(bc)
+            counts[cull] = r.eval_counts.cpu().tolist()
+            if cull:
+                lo, hi = r._occupied_box()
+                active = ops.ray_cull(cuda(ro), cuda(rd), r._table("z"), lo, hi).cpu().bool()
+        assert counts[True] == counts[False]                    # the same rows went through the MLP
+        for k in outs[True]:
+            assert bits_equal(outs[True][k], outs[False][k]), k
+        # dense sampling of every ray: no point of a culled ray may look up an occupied cell
+        zz = torch.linspace(2.0, 6.0, 513)
+        pts = ro[~active][:, None, :] + rd[~active][:, None, :] * zz[None, :, None]
+        if pts.numel():
+            assert bool(O.is_empty_space(grid, pts.reshape(-1, 3)).all())
+        seen_partial += int(0 < int(active.sum()) < active.numel())
+        if grid is empty:
+            assert int(active.sum()) == 0
+    assert seen_partial >= 2                                    # the cull actually removed rays in the blob cases
+
+
 def test_render_ess_skip_mode_structure_and_counts():
     sd = O.make_state_dict(6, 300.0, 6.0)
     for k in list(sd):                       # same (opaque) field for the coarse and the fine network
