@@ -99,7 +99,7 @@ struct Workspace {
   int32_t* counters;// [2] active-row counts of the coarse / fine pass
   float* z_term;    // [c] ERT depth from the coarse pass
   uint32_t* keep_bits;  // [ceil(c*(S+U)/32)] bit m = row m was evaluated (sparse ESS mode)
-  uint8_t* ray_active;  // [c] ray-level cull flags (sparse ESS mode with cull_rays)
+  int32_t* ray_list;    // [c] rays that survived the culling (sparse ESS mode with cull_rays); count = counters[2]
   size_t bytes;
 };
 
@@ -122,7 +122,7 @@ static Workspace carve(void* base, int chunk, int S, int U) {
   w.counters = reinterpret_cast<int32_t*>(take(64));
   w.z_term = take((size_t)chunk);
   w.keep_bits = reinterpret_cast<uint32_t*>(take(((size_t)chunk * (S + U) + 31) / 32));
-  w.ray_active = reinterpret_cast<uint8_t*>(take(((size_t)chunk + 3) / 4));
+  w.ray_list = reinterpret_cast<int32_t*>(take((size_t)chunk));
   w.bytes = off;
   return w;
 }
@@ -322,10 +322,16 @@ static int render_rays_impl(const void* packed_coarse, const void* packed_fine, 
     const bool masked = sparse && (p->variant & ~NERFB200_COMPOSITE_FAST_MATH) != NERFB200_COMPOSITE_ERT_COMPAT;
     const uint32_t* keep = masked ? ws.keep_bits : nullptr;
     // ray-level culling against the occupied box, before any per-sample work
-    const uint8_t* active = nullptr;
-    if (masked && p->cull_rays) {
-      if ((e = nerfb200_ray_cull(ro, rd, n, z_table, S, p->cull_lo, p->cull_hi, ws.ray_active, stream))) return e;
-      active = ws.ray_active;
+    // (list-driven kernels need whole 32-sample words per ray)
+    RayList active = {nullptr, nullptr};
+    if (masked && p->cull_rays && S % 32 == 0 && (S + U) % 32 == 0) {
+      NB_CUDA(cudaMemsetAsync(ws.counters + 2, 0, sizeof(int32_t), (cudaStream_t)stream));
+      nerfb200_maps c_maps = {mc->rgb + (size_t)r0 * 3, mc->disp + r0, mc->acc + r0, mc->depth + r0};
+      nerfb200_maps f_maps = {nullptr, nullptr, nullptr, nullptr};
+      if (U > 0) f_maps = nerfb200_maps{mf->rgb + (size_t)r0 * 3, mf->disp + r0, mf->acc + r0, mf->depth + r0};
+      if ((e = ray_cull_list(ro, rd, n, z_table, S, p->cull_lo, p->cull_hi, nullptr, ws.ray_list, ws.counters + 2, &c_maps,
+                             &f_maps, p->white_bkgd, stream))) return e;
+      active = RayList{ws.ray_list, ws.counters + 2};
     }
     const uint64_t noise_seed = p->seed ^ ((uint64_t)r0 * 0xD6E8FEB86659FD93ull);
     if (sparse) {

@@ -52,20 +52,32 @@ void count_launch(int n = 1);
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
-// Internal variants of public entry points that take the per-ray flags of nerfb200_ray_cull (NULL = every ray):
-// a culled ray is skipped by the kernel (the compositor writes the background maps for it).  Used by the sparse
-// whole-pass driver only; the public signatures stay as they are.
+// Internal variants of public entry points that work on a LIST of rays (ray indices + a device-side count, both NULL
+// = every ray 0..n_rays-1), as produced by the ray culling of the skipping mode (ess.cu).  The kernels then run as
+// persistent grids that loop over the list, so culled rays cost neither a launch slot nor a memory access.  Used by
+// the sparse whole-pass driver only; the public signatures stay as they are.
+struct RayList {
+  const int32_t* rays;
+  const int32_t* count;
+};
+constexpr int kPersistentBlocks = 148 * 16;   // grid cap of the list-driven launches
 int composite_forward_culled(const float* raw, const float* z_vals, const float* rays_d, const uint32_t* keep_bits,
-                             const uint8_t* ray_active, int n_rays, int n_samples, int variant, float ert_threshold,
+                             RayList rl, int n_rays, int n_samples, int variant, float ert_threshold,
                              int white_bkgd, int compat_chunk, float* rgb_map, float* disp_map, float* acc_map,
                              float* depth_map, float* weights, void* stream);
 int sample_pdf_merge_culled(const float* z_coarse, const float* weights, const float* u, int u_per_ray,
-                            const uint8_t* ray_active, int n_rays, int n_samples, int n_u, float* z_all, void* stream);
+                            RayList rl, int n_rays, int n_samples, int n_u, float* z_all, void* stream);
 int ess_compact_culled(const uint8_t* grid, int res, const float* rays_o, const float* rays_d, const float* z_vals,
-                       const float* z_term, const uint8_t* ray_active, int n_rays, int n_samples, int32_t* row_ids,
+                       const float* z_term, RayList rl, int n_rays, int n_samples, int32_t* row_ids,
                        int32_t* n_active, uint32_t* keep_bits, void* stream);
-int ert_depth_culled(const float* weights, const float* z_vals, const uint8_t* ray_active, int n_rays, int n_samples,
+int ert_depth_culled(const float* weights, const float* z_vals, RayList rl, int n_rays, int n_samples,
                      float thr, float* z_term, void* stream);
+// slab test of every ray against the box; flags (may be NULL) get 0/1 per ray; when list/count are given the hit rays
+// are appended to list (count must be zeroed by the caller) and every culled ray gets its background maps written
+// (maps_c / maps_f: rgb, disp, acc, depth pointers, entries may be NULL)
+int ray_cull_list(const float* rays_o, const float* rays_d, int n_rays, const float* z_table, int n_samples,
+                  const float* box_lo, const float* box_hi, uint8_t* flags, int32_t* list, int32_t* count,
+                  const nerfb200_maps* maps_c, const nerfb200_maps* maps_f, int white_bkgd, void* stream);
 
 // Counter-based RNG shared by the stratified jitter (a2) and the density noise (a5): a uniform in
 // [0,1) keyed on (seed, a, b).  The reference draws from torch's global generator, whose stream a

@@ -215,30 +215,20 @@ composite_kernel(const float* __restrict__ raw, const float* __restrict__ z_vals
                  float* __restrict__ rgb_map, float* __restrict__ disp_map,
                  float* __restrict__ acc_map, float* __restrict__ depth_map,
                  float* __restrict__ weights, const uint32_t* __restrict__ keep_bits,
-                 const uint8_t* __restrict__ ray_active) {
-  int lane = threadIdx.x & 31;
-  size_t ray = (size_t)blockIdx.x * kCompWarps + (threadIdx.x >> 5);
-  if (ray >= (size_t)n_rays) return;
-  if (ray_active != nullptr && !ray_active[ray]) {
-    // ray culled against the occupied region (nerfb200_ray_cull): every sample would be skipped, all weights are
-    // 0 -- the maps below are exactly what the code path underneath produces for such a ray (0/0 -> NaN disparity
-    // included); the weights row is not written (nothing downstream reads it for a culled ray)
-    if (lane == 0) {
-      const float bg = white_bkgd ? 1.f : 0.f;
-      rgb_map[ray * 3 + 0] = bg; rgb_map[ray * 3 + 1] = bg; rgb_map[ray * 3 + 2] = bg;
-      disp_map[ray] = __fdiv_rn(1.f, __fdiv_rn(0.f, 0.f));
-      acc_map[ray] = 0.f;
-      depth_map[ray] = 0.f;
-    }
-    return;
+                 const int32_t* __restrict__ ray_list, const int32_t* __restrict__ n_list) {
+  const int lane = threadIdx.x & 31;
+  const int per = (S + 31) / 32;
+  // ray_list != NULL: persistent grid over the rays that survived the culling (common.cuh: RayList)
+  const size_t n_eff = ray_list != nullptr ? (size_t)*n_list : (size_t)n_rays;
+  for (size_t i = (size_t)blockIdx.x * kCompWarps + (threadIdx.x >> 5); i < n_eff; i += (size_t)gridDim.x * kCompWarps) {
+    const size_t ray = ray_list != nullptr ? (size_t)ray_list[i] : i;
+    const float* raw_row = raw + ray * S * 4;
+    const float* z_row = z_vals + ray * S;
+    RaySamples rs;
+    ray_alpha_T<kErt, kFast>(raw_row, z_row, ray_norm(rays_d + ray * 3), S, per, lane, thr, rs, keep_bits, ray * S);
+    ray_outputs<kFast>(rs, raw_row, z_row, S, per, lane, rs.first_low, white_bkgd, ray, rgb_map, disp_map,
+                       acc_map, depth_map, weights);
   }
-  int per = (S + 31) / 32;
-  const float* raw_row = raw + ray * S * 4;
-  const float* z_row = z_vals + ray * S;
-  RaySamples rs;
-  ray_alpha_T<kErt, kFast>(raw_row, z_row, ray_norm(rays_d + ray * 3), S, per, lane, thr, rs, keep_bits, ray * S);
-  ray_outputs<kFast>(rs, raw_row, z_row, S, per, lane, rs.first_low, white_bkgd, ray, rgb_map, disp_map,
-                     acc_map, depth_map, weights);
 }
 
 // ERT_COMPAT: literal :1115-1123.  `if low.any()` is evaluated over the whole call (a
@@ -397,13 +387,13 @@ extern "C" int nerfb200_composite_forward_masked(const float* raw, const float* 
                                                  float ert_threshold, int white_bkgd, int compat_chunk,
                                                  float* rgb_map, float* disp_map, float* acc_map, float* depth_map,
                                                  float* weights, void* stream) {
-  return nb::composite_forward_culled(raw, z_vals, rays_d, keep_bits, nullptr, n_rays, n_samples, variant, ert_threshold,
+  return nb::composite_forward_culled(raw, z_vals, rays_d, keep_bits, RayList{nullptr, nullptr}, n_rays, n_samples, variant, ert_threshold,
                                       white_bkgd, compat_chunk, rgb_map, disp_map, acc_map, depth_map, weights, stream);
 }
 
-// + ray_active (may be NULL): per-ray flags of nerfb200_ray_cull; internal to the whole-pass driver
+// + ray list (common.cuh: RayList); internal to the whole-pass driver
 int nb::composite_forward_culled(const float* raw, const float* z_vals, const float* rays_d, const uint32_t* keep_bits,
-                                 const uint8_t* ray_active, int n_rays, int n_samples, int variant, float ert_threshold,
+                                 RayList rl, int n_rays, int n_samples, int variant, float ert_threshold,
                                  int white_bkgd, int compat_chunk, float* rgb_map, float* disp_map, float* acc_map,
                                  float* depth_map, float* weights, void* stream) {
   NB_CHECK_ARG(n_rays <= 0 || (raw && z_vals && rays_d && rgb_map && disp_map && acc_map && depth_map),
@@ -417,16 +407,17 @@ int nb::composite_forward_culled(const float* raw, const float* z_vals, const fl
   if (n_rays == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   int blocks = ceil_div(n_rays, kCompWarps);
+  if (rl.rays != nullptr && blocks > kPersistentBlocks) blocks = kPersistentBlocks;
 #define NB_COMPOSITE(ERT, FAST, THR)                                                                              \
   composite_kernel<ERT, FAST><<<blocks, kCompWarps * 32, 0, st>>>(raw, z_vals, rays_d, n_rays, n_samples, THR, white_bkgd, \
-                                                                  rgb_map, disp_map, acc_map, depth_map, weights, keep_bits, ray_active)
+                                                                  rgb_map, disp_map, acc_map, depth_map, weights, keep_bits, rl.rays, rl.count)
   if (variant == NERFB200_COMPOSITE_PLAIN) {
     if (fast) NB_COMPOSITE(false, true, 0.f); else NB_COMPOSITE(false, false, 0.f);
   } else if (variant == NERFB200_COMPOSITE_ERT) {
     if (fast) NB_COMPOSITE(true, true, ert_threshold); else NB_COMPOSITE(true, false, ert_threshold);
   } else {
     NB_CHECK_ARG(compat_chunk > 0, "composite_forward: compat_chunk must be > 0");
-    NB_CHECK_ARG(keep_bits == nullptr && ray_active == nullptr, "composite_forward: the ERT_COMPAT variant has no masked form");
+    NB_CHECK_ARG(keep_bits == nullptr && rl.rays == nullptr, "composite_forward: the ERT_COMPAT variant has no masked form");
     composite_ert_compat_kernel<<<ceil_div(n_rays, compat_chunk), 1024, 0, st>>>(
         raw, z_vals, rays_d, n_rays, n_samples, ert_threshold, white_bkgd, compat_chunk, rgb_map, disp_map, acc_map,
         depth_map, weights);

@@ -119,20 +119,29 @@ ess_compact_kernel(const uint8_t* __restrict__ grid, int res, const float* __res
                    const float* __restrict__ rays_d, const float* __restrict__ z_vals,
                    const float* __restrict__ z_term, long long total, int S,
                    int32_t* __restrict__ row_ids, int32_t* __restrict__ n_active,
-                   uint32_t* __restrict__ keep_bits, const uint8_t* __restrict__ ray_active) {
+                   uint32_t* __restrict__ keep_bits, const int32_t* __restrict__ ray_list,
+                   const int32_t* __restrict__ n_list) {
   __shared__ int s_off[32];
   __shared__ int s_base;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long row0 = (long long)blockIdx.x * kCompactRows + (long long)warp * (kCompactWords * 32) + lane;
-  unsigned m[kCompactWords];
+  // ray_list != NULL (S % 32 == 0, checked by the launcher): persistent grid over the samples of the listed rays;
+  // position idx of that sequence is sample idx % S of ray ray_list[idx / S], and a 32-sample word of the
+  // sequence is a 32-row word of the full row space
+  const long long total_eff = ray_list != nullptr ? (long long)*n_list * S : total;
+  for (long long blk0 = (long long)blockIdx.x * kCompactRows; blk0 < total_eff; blk0 += (long long)gridDim.x * kCompactRows) {
+    const long long pos0 = blk0 + (long long)warp * (kCompactWords * 32) + lane;
+    unsigned m[kCompactWords];
+    int row[kCompactWords];
 #pragma unroll
-  for (int j = 0; j < kCompactWords; ++j) {
-    const long long idx = row0 + j * 32;
-    bool keep = false;
-    if (idx < total) {
-      const unsigned ray = (unsigned)idx / (unsigned)S;   // total < 2^31 (checked by the entry point): 32-bit division
-      if (ray_active == nullptr || ray_active[ray]) {     // a culled ray has no sample in an occupied cell
-        float z = z_vals[idx];
+    for (int j = 0; j < kCompactWords; ++j) {
+      const long long idx = pos0 + j * 32;
+      bool keep = false;
+      row[j] = 0;
+      if (idx < total_eff) {
+        const unsigned li = (unsigned)idx / (unsigned)S;   // total < 2^31 (checked by the entry point): 32-bit division
+        const unsigned ray = ray_list != nullptr ? (unsigned)ray_list[li] : li;
+        row[j] = (int)(ray * (unsigned)S + ((unsigned)idx - li * (unsigned)S));
+        float z = z_vals[row[j]];
         int g[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c)
@@ -140,44 +149,47 @@ ess_compact_kernel(const uint8_t* __restrict__ grid, int res, const float* __res
         keep = grid[((size_t)g[0] * res + g[1]) * res + g[2]] != 0;
         if (keep && z_term != nullptr) keep = z <= z_term[ray];
       }
+      m[j] = __ballot_sync(0xffffffffu, keep);
+      if (lane == 0) {
+        s_off[warp * kCompactWords + j] = __popc(m[j]);
+        if (keep_bits != nullptr && idx < total_eff) keep_bits[row[j] >> 5] = m[j];
+      }
     }
-    m[j] = __ballot_sync(0xffffffffu, keep);
-    if (lane == 0) {
-      s_off[warp * kCompactWords + j] = __popc(m[j]);
-      if (keep_bits != nullptr && idx < total) keep_bits[idx >> 5] = m[j];
-    }
-  }
-  __syncthreads();
-  if (warp == 0) {   // exclusive scan of the 32 word counts, one reservation for the block
-    const int c = s_off[lane];
-    int incl = c;
+    __syncthreads();
+    if (warp == 0) {   // exclusive scan of the 32 word counts, one reservation for the block
+      const int c = s_off[lane];
+      int incl = c;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      int o = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += o;
+      for (int d = 1; d < 32; d <<= 1) {
+        int o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+      }
+      s_off[lane] = incl - c;
+      if (lane == 31) s_base = incl ? atomicAdd(n_active, incl) : 0;
     }
-    s_off[lane] = incl - c;
-    if (lane == 31) s_base = incl ? atomicAdd(n_active, incl) : 0;
-  }
-  __syncthreads();
-  const int base = s_base;
+    __syncthreads();
+    const int base = s_base;
 #pragma unroll
-  for (int j = 0; j < kCompactWords; ++j)
-    if ((m[j] >> lane) & 1u)
-      row_ids[base + s_off[warp * kCompactWords + j] + __popc(m[j] & ((1u << lane) - 1))] = (int32_t)(row0 + j * 32);
+    for (int j = 0; j < kCompactWords; ++j)
+      if ((m[j] >> lane) & 1u)
+        row_ids[base + s_off[warp * kCompactWords + j] + __popc(m[j] & ((1u << lane) - 1))] = row[j];
+    __syncthreads();   // s_off / s_base are rewritten by the next round
+  }
 }
 
 __global__ void ert_depth_kernel(const float* __restrict__ weights, const float* __restrict__ z_vals, int n_rays,
-                                 int S, float thr, float* __restrict__ z_term, const uint8_t* __restrict__ ray_active) {
-  int ray = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ray >= n_rays) return;
-  if (ray_active != nullptr && !ray_active[ray]) return;   // culled ray: z_term is never read
+                                 int S, float thr, float* __restrict__ z_term, const int32_t* __restrict__ ray_list,
+                                 const int32_t* __restrict__ n_list) {
+  const int n_eff = ray_list != nullptr ? *n_list : n_rays;
+  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < n_eff; it += gridDim.x * blockDim.x) {
+  const int ray = ray_list != nullptr ? ray_list[it] : it;
   float acc = 0.f, zt = __int_as_float(0x7f800000);
   for (int i = 0; i < S; ++i) {
     if (1.f - acc < thr) { zt = z_vals[(size_t)ray * S + i]; break; }
     acc += weights[(size_t)ray * S + i];
   }
   z_term[ray] = zt;
+  }
 }
 
 // Ray-level culling for the skipping mode: slab test of the segment o + d*z, z in [z_near, z_far], against the
@@ -186,30 +198,65 @@ __global__ void ert_depth_kernel(const float* __restrict__ weights, const float*
 // test is conservative with respect to the per-sample lookup: a culled ray has no sample in an occupied cell, at any
 // z of the coarse or the fine pass.  On a scene that fills a fraction of the frame most rays stop here and never reach
 // the compaction, sample_pdf or the compositor's per-sample work.
-__global__ void ray_cull_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, int n_rays,
-                                const float* __restrict__ z_table, int S, float lx, float ly, float lz, float hx, float hy,
-                                float hz, uint8_t* __restrict__ ray_active) {
-  int ray = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ray >= n_rays) return;
-  const float lo[3] = {lx, ly, lz}, hi[3] = {hx, hy, hz};
-  float t0 = z_table[0], t1 = z_table[S - 1];
-  if (t0 > t1) { float t = t0; t0 = t1; t1 = t; }
-  const float pad = 1e-3f * fmaxf(1.f, fabsf(t1));   // rounding of o + d*z in the lookups is ~1e-6
-  t0 -= pad; t1 += pad;
-  bool hit = true;
+__global__ void __launch_bounds__(256)
+ray_cull_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, int n_rays,
+                const float* __restrict__ z_table, int S, float lx, float ly, float lz, float hx, float hy,
+                float hz, uint8_t* __restrict__ flags, int32_t* __restrict__ list, int32_t* __restrict__ count,
+                nerfb200_maps mc, nerfb200_maps mf, int white_bkgd) {
+  __shared__ int s_cnt[8];
+  __shared__ int s_base;
+  const int ray = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  bool hit = false;
+  if (ray < n_rays) {
+    const float lo[3] = {lx, ly, lz}, hi[3] = {hx, hy, hz};
+    float t0 = z_table[0], t1 = z_table[S - 1];
+    if (t0 > t1) { float t = t0; t0 = t1; t1 = t; }
+    const float pad = 1e-3f * fmaxf(1.f, fabsf(t1));   // rounding of o + d*z in the lookups is ~1e-6
+    t0 -= pad; t1 += pad;
+    hit = true;
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const float o = rays_o[(size_t)ray * 3 + c], d = rays_d[(size_t)ray * 3 + c];
-    if (fabsf(d) < 1e-12f) {
-      hit = hit && (o >= lo[c]) && (o <= hi[c]);
-    } else {
-      float ta = (lo[c] - o) / d, tb = (hi[c] - o) / d;   // +-inf for an open side
-      if (ta > tb) { float t = ta; ta = tb; tb = t; }
-      t0 = fmaxf(t0, ta);
-      t1 = fminf(t1, tb);
+    for (int c = 0; c < 3; ++c) {
+      const float o = rays_o[(size_t)ray * 3 + c], d = rays_d[(size_t)ray * 3 + c];
+      if (!(lo[c] <= hi[c])) hit = false;   // empty box (no occupied cell)
+      if (fabsf(d) < 1e-12f) {
+        hit = hit && (o >= lo[c]) && (o <= hi[c]);
+      } else {
+        float ta = (lo[c] - o) / d, tb = (hi[c] - o) / d;   // +-inf for an open side
+        if (ta > tb) { float t = ta; ta = tb; tb = t; }
+        t0 = fmaxf(t0, ta);
+        t1 = fminf(t1, tb);
+      }
+    }
+    hit = hit && t0 <= t1;
+    if (flags != nullptr) flags[ray] = hit ? 1 : 0;
+    if (!hit && list != nullptr) {
+      // every sample of a culled ray would be skipped and all its weights are 0: these are exactly the maps the
+      // compositor produces for such a ray (0/0 -> NaN disparity included)
+      const float bg = white_bkgd ? 1.f : 0.f;
+      const float nan_disp = __fdiv_rn(1.f, __fdiv_rn(0.f, 0.f));
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+        const nerfb200_maps& mp = pass ? mf : mc;
+        if (mp.rgb) { mp.rgb[(size_t)ray * 3 + 0] = bg; mp.rgb[(size_t)ray * 3 + 1] = bg; mp.rgb[(size_t)ray * 3 + 2] = bg; }
+        if (mp.disp) mp.disp[ray] = nan_disp;
+        if (mp.acc) mp.acc[ray] = 0.f;
+        if (mp.depth) mp.depth[ray] = 0.f;
+      }
     }
   }
-  ray_active[ray] = (hit && t0 <= t1) ? 1 : 0;
+  if (list == nullptr) return;
+  // append the surviving rays: one atomic per block, ray order kept inside the block
+  const unsigned m = __ballot_sync(0xffffffffu, hit);
+  if (lane == 0) s_cnt[warp] = __popc(m);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < 8; ++w) { const int c = s_cnt[w]; s_cnt[w] = t; t += c; }
+    s_base = t ? atomicAdd(count, t) : 0;
+  }
+  __syncthreads();
+  if (hit) list[s_base + s_cnt[warp] + __popc(m & ((1u << lane) - 1))] = ray;
 }
 
 __global__ void accumulate_counts_kernel(const int32_t* __restrict__ counts, long long* __restrict__ totals) {
@@ -223,13 +270,14 @@ using namespace nb;
 extern "C" int nerfb200_ess_compact(const uint8_t* grid, int res, const float* rays_o, const float* rays_d,
                                     const float* z_vals, const float* z_term, int n_rays, int n_samples,
                                     int32_t* row_ids, int32_t* n_active, uint32_t* keep_bits, void* stream) {
-  return ess_compact_culled(grid, res, rays_o, rays_d, z_vals, z_term, nullptr, n_rays, n_samples, row_ids, n_active,
-                            keep_bits, stream);
+  return ess_compact_culled(grid, res, rays_o, rays_d, z_vals, z_term, RayList{nullptr, nullptr}, n_rays, n_samples, row_ids,
+                            n_active, keep_bits, stream);
 }
 
 int nb::ess_compact_culled(const uint8_t* grid, int res, const float* rays_o, const float* rays_d, const float* z_vals,
-                           const float* z_term, const uint8_t* ray_active, int n_rays, int n_samples, int32_t* row_ids,
+                           const float* z_term, RayList rl, int n_rays, int n_samples, int32_t* row_ids,
                            int32_t* n_active, uint32_t* keep_bits, void* stream) {
+  NB_CHECK_ARG(rl.rays == nullptr || n_samples % 32 == 0, "ess_compact: a ray list needs n_samples %% 32 == 0 (got %d)", n_samples);
   NB_CHECK_ARG(n_active, "ess_compact: null counter");
   NB_CHECK_ARG(n_rays <= 0 || (grid && rays_o && rays_d && z_vals && row_ids), "ess_compact: null pointer");
   NB_CHECK_ARG(res >= 1 && res <= 1024, "ess_compact: bad grid resolution %d", res);
@@ -237,37 +285,50 @@ int nb::ess_compact_culled(const uint8_t* grid, int res, const float* rays_o, co
   NB_CUDA(cudaMemsetAsync(n_active, 0, sizeof(int32_t), (cudaStream_t)stream));
   if (n_rays == 0) return 0;
   long long total = (long long)n_rays * n_samples;
-  ess_compact_kernel<<<ceil_div(total, kCompactRows), kCompactThreads, 0, (cudaStream_t)stream>>>(
-      grid, res, rays_o, rays_d, z_vals, z_term, total, n_samples, row_ids, n_active, keep_bits, ray_active);
+  int blocks = ceil_div(total, kCompactRows);
+  if (rl.rays != nullptr && blocks > kPersistentBlocks) blocks = kPersistentBlocks;
+  ess_compact_kernel<<<blocks, kCompactThreads, 0, (cudaStream_t)stream>>>(
+      grid, res, rays_o, rays_d, z_vals, z_term, total, n_samples, row_ids, n_active, keep_bits, rl.rays, rl.count);
   NB_LAUNCH_OK("ess_compact_kernel");
   return 0;
 }
 
 extern "C" int nerfb200_ert_depth(const float* weights, const float* z_vals, int n_rays, int n_samples, float thr,
                                   float* z_term, void* stream) {
-  return ert_depth_culled(weights, z_vals, nullptr, n_rays, n_samples, thr, z_term, stream);
+  return ert_depth_culled(weights, z_vals, RayList{nullptr, nullptr}, n_rays, n_samples, thr, z_term, stream);
 }
 
 extern "C" int nerfb200_ray_cull(const float* rays_o, const float* rays_d, int n_rays, const float* z_table, int n_samples,
                                  const float* box_lo, const float* box_hi, uint8_t* ray_active, void* stream) {
-  NB_CHECK_ARG(n_rays <= 0 || (rays_o && rays_d && z_table && ray_active), "ray_cull: null pointer");
+  NB_CHECK_ARG(n_rays <= 0 || ray_active, "ray_cull: null pointer");
+  return ray_cull_list(rays_o, rays_d, n_rays, z_table, n_samples, box_lo, box_hi, ray_active, nullptr, nullptr, nullptr,
+                       nullptr, 0, stream);
+}
+
+int nb::ray_cull_list(const float* rays_o, const float* rays_d, int n_rays, const float* z_table, int n_samples,
+                      const float* box_lo, const float* box_hi, uint8_t* flags, int32_t* list, int32_t* count,
+                      const nerfb200_maps* maps_c, const nerfb200_maps* maps_f, int white_bkgd, void* stream) {
+  NB_CHECK_ARG(n_rays <= 0 || (rays_o && rays_d && z_table), "ray_cull: null pointer");
   NB_CHECK_ARG(box_lo && box_hi, "ray_cull: null box");
   NB_CHECK_ARG(n_rays >= 0 && n_samples >= 1, "ray_cull: bad sizes");
+  NB_CHECK_ARG((list == nullptr) == (count == nullptr), "ray_cull: list and count go together");
   if (n_rays == 0) return 0;
-  ray_cull_kernel<<<ceil_div(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, n_rays, z_table, n_samples, box_lo[0],
-                                                                         box_lo[1], box_lo[2], box_hi[0], box_hi[1],
-                                                                         box_hi[2], ray_active);
+  const nerfb200_maps none = {nullptr, nullptr, nullptr, nullptr};
+  ray_cull_kernel<<<ceil_div(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(
+      rays_o, rays_d, n_rays, z_table, n_samples, box_lo[0], box_lo[1], box_lo[2], box_hi[0], box_hi[1], box_hi[2], flags,
+      list, count, maps_c ? *maps_c : none, maps_f ? *maps_f : none, white_bkgd);
   NB_LAUNCH_OK("ray_cull_kernel");
   return 0;
 }
 
-int nb::ert_depth_culled(const float* weights, const float* z_vals, const uint8_t* ray_active, int n_rays, int n_samples,
+int nb::ert_depth_culled(const float* weights, const float* z_vals, RayList rl, int n_rays, int n_samples,
                          float thr, float* z_term, void* stream) {
   NB_CHECK_ARG(n_rays <= 0 || (weights && z_vals && z_term), "ert_depth: null pointer");
   NB_CHECK_ARG(n_rays >= 0 && n_samples >= 1, "ert_depth: bad sizes");
   if (n_rays == 0) return 0;
-  ert_depth_kernel<<<ceil_div(n_rays, 128), 128, 0, (cudaStream_t)stream>>>(weights, z_vals, n_rays, n_samples, thr, z_term,
-                                                                            ray_active);
+  int blocks = ceil_div(n_rays, 128);
+  if (rl.rays != nullptr && blocks > kPersistentBlocks) blocks = kPersistentBlocks;
+  ert_depth_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(weights, z_vals, n_rays, n_samples, thr, z_term, rl.rays, rl.count);
   NB_LAUNCH_OK("ert_depth_kernel");
   return 0;
 }

@@ -158,15 +158,16 @@ sample_pdf_merge_kernel(const float* __restrict__ z_coarse, const float* __restr
                         const float* __restrict__ u_g, int u_per_ray, int n_rays, int S, int n_u,
                         float* __restrict__ z_all, float* __restrict__ z_samples,
                         int32_t* __restrict__ inds, float* __restrict__ cdf_out,
-                        const uint8_t* __restrict__ ray_active) {
+                        const int32_t* __restrict__ ray_list, const int32_t* __restrict__ n_list) {
   __shared__ float s_z[kWarpsPerBlock][kMaxS];
   __shared__ float s_cdf[kWarpsPerBlock][kMaxS];
   __shared__ float s_bins[kWarpsPerBlock][kMaxS];
   __shared__ float s_smp[kWarpsPerBlock][kMaxU];
-  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int ray = blockIdx.x * kWarpsPerBlock + warp;
-  if (ray >= n_rays) return;
-  if (ray_active != nullptr && !ray_active[ray]) return;   // culled ray: its fine samples are never looked at
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // ray_list != NULL: persistent grid over the rays that survived the culling (common.cuh: RayList)
+  const int n_eff = ray_list != nullptr ? *n_list : n_rays;
+  for (int it = blockIdx.x * kWarpsPerBlock + warp; it < n_eff; it += gridDim.x * kWarpsPerBlock) {
+  const int ray = ray_list != nullptr ? ray_list[it] : it;
   const int nbins = S - 1;   // cdf / t_mid entries (63)
   const int nw = S - 2;      // interior weights (62)
   float* zr = s_z[warp];
@@ -244,6 +245,8 @@ sample_pdf_merge_kernel(const float* __restrict__ z_coarse, const float* __restr
       out[c] = x;
     }
   }
+  __syncwarp();   // the per-warp rows are reused by the next ray of the list
+  }
 }
 
 }  // namespace nb
@@ -251,7 +254,7 @@ sample_pdf_merge_kernel(const float* __restrict__ z_coarse, const float* __restr
 using namespace nb;
 
 static int sample_pdf_merge_impl(const float* z_coarse, const float* weights, const float* u, int u_per_ray,
-                                 const uint8_t* ray_active, int n_rays, int n_samples, int n_u, float* z_all,
+                                 RayList rl, int n_rays, int n_samples, int n_u, float* z_all,
                                  float* z_samples, int32_t* inds, float* cdf, void* stream);
 
 extern "C" int nerfb200_raygen(const float* pose, const float* intrinsics, int H, int W,
@@ -292,26 +295,28 @@ extern "C" int nerfb200_sample_pdf_merge(const float* z_coarse, const float* wei
                                          int u_per_ray, int n_rays, int n_samples, int n_u,
                                          float* z_all, float* z_samples, int32_t* inds, float* cdf,
                                          void* stream) {
-  return sample_pdf_merge_impl(z_coarse, weights, u, u_per_ray, nullptr, n_rays, n_samples, n_u, z_all, z_samples, inds,
-                               cdf, stream);
+  return sample_pdf_merge_impl(z_coarse, weights, u, u_per_ray, RayList{nullptr, nullptr}, n_rays, n_samples, n_u, z_all,
+                               z_samples, inds, cdf, stream);
 }
 
 int nb::sample_pdf_merge_culled(const float* z_coarse, const float* weights, const float* u, int u_per_ray,
-                                const uint8_t* ray_active, int n_rays, int n_samples, int n_u, float* z_all, void* stream) {
-  return sample_pdf_merge_impl(z_coarse, weights, u, u_per_ray, ray_active, n_rays, n_samples, n_u, z_all, nullptr,
+                                RayList rl, int n_rays, int n_samples, int n_u, float* z_all, void* stream) {
+  return sample_pdf_merge_impl(z_coarse, weights, u, u_per_ray, rl, n_rays, n_samples, n_u, z_all, nullptr,
                                nullptr, nullptr, stream);
 }
 
 static int sample_pdf_merge_impl(const float* z_coarse, const float* weights, const float* u, int u_per_ray,
-                                 const uint8_t* ray_active, int n_rays, int n_samples, int n_u, float* z_all,
+                                 RayList rl, int n_rays, int n_samples, int n_u, float* z_all,
                                  float* z_samples, int32_t* inds, float* cdf, void* stream) {
   NB_CHECK_ARG(n_rays <= 0 || (z_coarse && weights && u && z_all), "sample_pdf_merge: null pointer");
   NB_CHECK_ARG(n_samples >= 3 && n_samples <= kMaxS, "sample_pdf_merge: n_samples=%d out of range [3,%d]", n_samples, kMaxS);
   NB_CHECK_ARG(n_u >= 1 && n_u <= kMaxU, "sample_pdf_merge: n_u=%d out of range [1,%d]", n_u, kMaxU);
   NB_CHECK_ARG(n_rays >= 0, "sample_pdf_merge: negative n_rays");
   if (n_rays == 0) return 0;
-  sample_pdf_merge_kernel<<<ceil_div(n_rays, kWarpsPerBlock), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-      z_coarse, weights, u, u_per_ray, n_rays, n_samples, n_u, z_all, z_samples, inds, cdf, ray_active);
+  int blocks = ceil_div(n_rays, kWarpsPerBlock);
+  if (rl.rays != nullptr && blocks > kPersistentBlocks) blocks = kPersistentBlocks;
+  sample_pdf_merge_kernel<<<blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      z_coarse, weights, u, u_per_ray, n_rays, n_samples, n_u, z_all, z_samples, inds, cdf, rl.rays, rl.count);
   NB_LAUNCH_OK("sample_pdf_merge_kernel");
   return 0;
 }
