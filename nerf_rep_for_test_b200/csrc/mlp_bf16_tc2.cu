@@ -443,11 +443,15 @@ int launch_mlp_bf16(const void* packed, const float* rays_o, const float* rays_d
   int dev = 0, sms = 0;
   NB_CUDA(cudaGetDevice(&dev));
   NB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-  NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-  NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<true, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-  NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-  NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<false, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  static int attr_dev = -1;   // the opt-in to 226 KB of dynamic shared memory is per device and sticky: once is enough
+  if (attr_dev != dev) {
+    NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<true, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<false, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    attr_dev = dev;
+  }
   const char* tl_env = getenv("NERFB200_TIMELINE");
   unsigned long long* tl = nullptr;
   if (tl_env && !stage_dump) {
