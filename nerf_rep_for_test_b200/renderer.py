@@ -95,6 +95,27 @@ def _model_weight_struct(model):
     return w, keep
 
 
+def occupied_box(grid):
+    """World-space box (lo[3], hi[3]) that contains every point whose occupancy lookup can be non-empty (used by the
+    ray culling of ess_mode='skip').  The lookup (volume_renderer.py:992-1007) maps p to cell
+    clamp(int(clamp((p + 2) / 4, 0, 1) * (R - 1)), 0, R - 1): cell i covers [-2 + 4 i / (R-1), -2 + 4 (i+1) / (R-1)),
+    cell 0 also everything below -2 and cell R-1 everything from +2 up, so a side whose boundary cell is occupied is
+    left open (+-inf).  A margin of one hundredth of a cell covers the rounding of o + d z.  Empty grid: lo > hi."""
+    R = grid.shape[0]
+    inf = float("inf")
+    lo, hi = [inf] * 3, [-inf] * 3
+    gb = grid.bool()
+    cell = 4.0 / (R - 1)
+    for c in range(3):
+        occ = gb.any(dim=tuple(d for d in range(3) if d != c)).nonzero().flatten()
+        if occ.numel() == 0:
+            continue
+        i0, i1 = int(occ[0]), int(occ[-1])
+        lo[c] = -inf if i0 == 0 else -2.0 + cell * i0 - 0.01 * cell
+        hi[c] = inf if i1 == R - 1 else -2.0 + cell * (i1 + 1) + 0.01 * cell
+    return lo, hi
+
+
 class Renderer(PathRenderingMixin):
     MODES = {"fp32": L.MODE_FP32, "bf16": L.MODE_BF16}
 
@@ -297,29 +318,12 @@ class Renderer(PathRenderingMixin):
         return p
 
     def _occupied_box(self):
-        """World-space box that contains every point whose occupancy lookup can be non-empty (ess_mode='skip').
-        The lookup (:992-1007) maps p to cell clamp(int(clamp((p + 2) / 4, 0, 1) * (R - 1)), 0, R - 1): cell i covers
-        [-2 + 4 i / (R-1), -2 + 4 (i+1) / (R-1)), cell 0 also everything below -2 and cell R-1 everything from +2 up,
-        so a side whose boundary cell is occupied is left open.  A margin of one hundredth of a cell covers the
-        rounding of o + d z."""
+        """occupied_box() of the current grid, cached per grid version."""
         g = self.occupancy_grid
         key = (g.data_ptr(), g._version, tuple(g.shape))
-        if self._box is not None and self._box[0] == key:
-            return self._box[1]
-        R = g.shape[0]
-        inf = float("inf")
-        lo, hi = [inf] * 3, [-inf] * 3
-        gb = g.bool()
-        for c in range(3):
-            occ = gb.any(dim=tuple(d for d in range(3) if d != c)).nonzero().flatten()
-            if occ.numel() == 0:
-                continue                         # empty grid: lo > hi, every ray is culled
-            i0, i1 = int(occ[0]), int(occ[-1])
-            cell = 4.0 / (R - 1)
-            lo[c] = -inf if i0 == 0 else -2.0 + cell * i0 - 0.01 * cell
-            hi[c] = inf if i1 == R - 1 else -2.0 + cell * (i1 + 1) + 0.01 * cell
-        self._box = (key, (lo, hi))
-        return lo, hi
+        if self._box is None or self._box[0] != key:
+            self._box = (key, occupied_box(g))
+        return self._box[1]
 
     def _workspace(self, nbytes):
         if self._ws is None or self._ws.numel() < nbytes:
