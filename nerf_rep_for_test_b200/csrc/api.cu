@@ -100,6 +100,8 @@ struct Workspace {
   float* z_term;    // [c] ERT depth from the coarse pass
   uint32_t* keep_bits;  // [ceil(c*(S+U)/32)] bit m = row m was evaluated (sparse ESS mode)
   int32_t* ray_list;    // [c] rays that survived the culling (sparse ESS mode with cull_rays); count = counters[2]
+                        //     (ERT_COMPAT, never combined with culling: per-ray "went low" flags, as bytes)
+  int32_t* compat_any;  // [c] ERT_COMPAT: per-compat-chunk "somebody went low" flags
   size_t bytes;
 };
 
@@ -123,6 +125,7 @@ static Workspace carve(void* base, int chunk, int S, int U) {
   w.z_term = take((size_t)chunk);
   w.keep_bits = reinterpret_cast<uint32_t*>(take(((size_t)chunk * (S + U) + 31) / 32));
   w.ray_list = reinterpret_cast<int32_t*>(take((size_t)chunk));
+  w.compat_any = reinterpret_cast<int32_t*>(take((size_t)chunk));
   w.bytes = off;
   return w;
 }
@@ -342,7 +345,14 @@ static int render_rays_impl(const void* packed_coarse, const void* packed_fine, 
     } else if ((e = nerfb200_mlp_forward(packed_coarse, p->mode, ro, rd, ws.z_coarse, n, S, ws.raw_c, stream))) return e;
     if (p->raw_noise_std > 0.f &&
         (e = nerfb200_sigma_noise(ws.raw_c, (long long)n * S, p->raw_noise_std, noise_seed + 0x632BE59BD9B4E019ull, stream))) return e;
-    if ((e = composite_forward_culled(ws.raw_c, ws.z_coarse, rd, keep, active, n, S, p->variant, p->ert_threshold,
+    const bool compat = (p->variant & ~NERFB200_COMPOSITE_FAST_MATH) == NERFB200_COMPOSITE_ERT_COMPAT;
+    const int fast = (p->variant & NERFB200_COMPOSITE_FAST_MATH) != 0;
+    if (compat) {
+      if ((e = composite_forward_compat2(ws.raw_c, ws.z_coarse, rd, n, S, fast, p->ert_threshold, p->white_bkgd,
+                                         p->compat_chunk, mc->rgb + (size_t)r0 * 3, mc->disp + r0, mc->acc + r0,
+                                         mc->depth + r0, ws.weights, reinterpret_cast<uint8_t*>(ws.ray_list),
+                                         ws.compat_any, stream))) return e;
+    } else if ((e = composite_forward_culled(ws.raw_c, ws.z_coarse, rd, keep, active, n, S, p->variant, p->ert_threshold,
                                       p->white_bkgd, p->compat_chunk, mc->rgb + (size_t)r0 * 3, mc->disp + r0,
                                       mc->acc + r0, mc->depth + r0, ws.weights, stream))) return e;
     if (U > 0) {
@@ -366,7 +376,12 @@ static int render_rays_impl(const void* packed_coarse, const void* packed_fine, 
       } else if ((e = nerfb200_mlp_forward(packed_fine, p->mode, ro, rd, ws.z_all, n, S + U, ws.raw_f, stream))) return e;
       if (p->raw_noise_std > 0.f &&
           (e = nerfb200_sigma_noise(ws.raw_f, (long long)n * (S + U), p->raw_noise_std, noise_seed + 0x94D049BB133111EBull, stream))) return e;
-      if ((e = composite_forward_culled(ws.raw_f, ws.z_all, rd, keep, active, n, S + U, p->variant, p->ert_threshold,
+      if (compat) {
+        if ((e = composite_forward_compat2(ws.raw_f, ws.z_all, rd, n, S + U, fast, p->ert_threshold, p->white_bkgd,
+                                           p->compat_chunk, mf->rgb + (size_t)r0 * 3, mf->disp + r0, mf->acc + r0,
+                                           mf->depth + r0, nullptr, reinterpret_cast<uint8_t*>(ws.ray_list),
+                                           ws.compat_any, stream))) return e;
+      } else if ((e = composite_forward_culled(ws.raw_f, ws.z_all, rd, keep, active, n, S + U, p->variant, p->ert_threshold,
                                         p->white_bkgd, p->compat_chunk, mf->rgb + (size_t)r0 * 3, mf->disp + r0,
                                         mf->acc + r0, mf->depth + r0, nullptr, stream))) return e;
     }

@@ -65,6 +65,12 @@ int composite_forward_culled(const float* raw, const float* z_vals, const float*
                              RayList rl, int n_rays, int n_samples, int variant, float ert_threshold,
                              int white_bkgd, int compat_chunk, float* rgb_map, float* disp_map, float* acc_map,
                              float* depth_map, float* weights, void* stream);
+// ERT_COMPAT (reference chunk quirk) as two fully parallel launches; low_flag [n_rays] bytes and chunk_any
+// [ceil(n_rays / compat_chunk)] ints are scratch
+int composite_forward_compat2(const float* raw, const float* z_vals, const float* rays_d, int n_rays, int n_samples,
+                              int fast, float ert_threshold, int white_bkgd, int compat_chunk, float* rgb_map,
+                              float* disp_map, float* acc_map, float* depth_map, float* weights, uint8_t* low_flag,
+                              int32_t* chunk_any, void* stream);
 int sample_pdf_merge_culled(const float* z_coarse, const float* weights, const float* u, int u_per_ray,
                             RayList rl, int n_rays, int n_samples, int n_u, float* z_all, void* stream);
 int ess_compact_culled(const uint8_t* grid, int res, const float* rays_o, const float* rays_d, const float* z_vals,

@@ -215,7 +215,8 @@ composite_kernel(const float* __restrict__ raw, const float* __restrict__ z_vals
                  float* __restrict__ rgb_map, float* __restrict__ disp_map,
                  float* __restrict__ acc_map, float* __restrict__ depth_map,
                  float* __restrict__ weights, const uint32_t* __restrict__ keep_bits,
-                 const int32_t* __restrict__ ray_list, const int32_t* __restrict__ n_list) {
+                 const int32_t* __restrict__ ray_list, const int32_t* __restrict__ n_list,
+                 uint8_t* __restrict__ low_flag = nullptr, int32_t* __restrict__ chunk_any = nullptr, int compat_chunk = 1) {
   const int lane = threadIdx.x & 31;
   const int per = (S + 31) / 32;
   // ray_list != NULL: persistent grid over the rays that survived the culling (common.cuh: RayList)
@@ -226,9 +227,41 @@ composite_kernel(const float* __restrict__ raw, const float* __restrict__ z_vals
     const float* z_row = z_vals + ray * S;
     RaySamples rs;
     ray_alpha_T<kErt, kFast>(raw_row, z_row, ray_norm(rays_d + ray * 3), S, per, lane, thr, rs, keep_bits, ray * S);
+    if (kErt && low_flag != nullptr && lane == 0) {   // first pass of the two-kernel ERT_COMPAT path below
+      low_flag[ray] = rs.low_any ? 1 : 0;
+      if (rs.low_any) chunk_any[ray / (size_t)compat_chunk] = 1;   // same value from every writer
+    }
     ray_outputs<kFast>(rs, raw_row, z_row, S, per, lane, rs.first_low, white_bkgd, ray, rgb_map, disp_map,
                        acc_map, depth_map, weights);
   }
+}
+
+// ERT_COMPAT in two launches (whole-pass driver; the single-kernel version below serialises a 2048-ray chunk in one
+// thread block and made the reference's DEFAULT configuration -- lego.yaml: enable_ert = True -- 19 ms per frame
+// slower than the plain compositor).  The quirk (:1115-1123): `if low.any()` is evaluated over the chunk; when it
+// fires, first = argmax(low) is 0 for the rays that never go low, so those rays lose all their weights.  Pass 1 =
+// composite_kernel<ERT> (every ray truncated at its own first low sample -- already the final answer for the rays that
+// go low and for chunks where nobody does) + one flag per ray and per chunk; pass 2 redoes, with cut = 0, only the
+// rays that never went low inside a chunk where somebody did.
+template <bool kFast>
+__global__ void __launch_bounds__(kCompWarps * 32)
+composite_compat_fixup_kernel(const float* __restrict__ raw, const float* __restrict__ z_vals,
+                              const float* __restrict__ rays_d, int n_rays, int S, float thr, int white_bkgd,
+                              int compat_chunk, float* __restrict__ rgb_map, float* __restrict__ disp_map,
+                              float* __restrict__ acc_map, float* __restrict__ depth_map,
+                              float* __restrict__ weights, const uint8_t* __restrict__ low_flag,
+                              const int32_t* __restrict__ chunk_any) {
+  const int lane = threadIdx.x & 31;
+  const size_t ray = (size_t)blockIdx.x * kCompWarps + (threadIdx.x >> 5);
+  if (ray >= (size_t)n_rays) return;
+  if (low_flag[ray] || !chunk_any[ray / (size_t)compat_chunk]) return;
+  const int per = (S + 31) / 32;
+  const float* raw_row = raw + ray * S * 4;
+  const float* z_row = z_vals + ray * S;
+  RaySamples rs;
+  ray_alpha_T<true, kFast>(raw_row, z_row, ray_norm(rays_d + ray * 3), S, per, lane, thr, rs);
+  ray_outputs<kFast>(rs, raw_row, z_row, S, per, lane, /*cut=*/0, white_bkgd, ray, rgb_map, disp_map, acc_map,
+                     depth_map, weights);
 }
 
 // ERT_COMPAT: literal :1115-1123.  `if low.any()` is evaluated over the whole call (a
@@ -389,6 +422,34 @@ extern "C" int nerfb200_composite_forward_masked(const float* raw, const float* 
                                                  float* weights, void* stream) {
   return nb::composite_forward_culled(raw, z_vals, rays_d, keep_bits, RayList{nullptr, nullptr}, n_rays, n_samples, variant, ert_threshold,
                                       white_bkgd, compat_chunk, rgb_map, disp_map, acc_map, depth_map, weights, stream);
+}
+
+int nb::composite_forward_compat2(const float* raw, const float* z_vals, const float* rays_d, int n_rays, int n_samples,
+                                  int fast, float ert_threshold, int white_bkgd, int compat_chunk, float* rgb_map,
+                                  float* disp_map, float* acc_map, float* depth_map, float* weights,
+                                  uint8_t* low_flag, int32_t* chunk_any, void* stream) {
+  NB_CHECK_ARG(n_rays <= 0 || (raw && z_vals && rays_d && rgb_map && disp_map && acc_map && depth_map && low_flag && chunk_any),
+               "composite_forward (compat): null pointer");
+  NB_CHECK_ARG(n_samples >= 1 && n_samples <= 32 * kMaxPer && compat_chunk > 0 && n_rays >= 0, "composite_forward (compat): bad sizes");
+  if (n_rays == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = ceil_div(n_rays, kCompWarps);
+  NB_CUDA(cudaMemsetAsync(chunk_any, 0, (size_t)ceil_div(n_rays, compat_chunk) * sizeof(int32_t), st));
+  if (fast) {
+    composite_kernel<true, true><<<blocks, kCompWarps * 32, 0, st>>>(raw, z_vals, rays_d, n_rays, n_samples, ert_threshold,
+        white_bkgd, rgb_map, disp_map, acc_map, depth_map, weights, nullptr, nullptr, nullptr, low_flag, chunk_any, compat_chunk);
+    NB_LAUNCH_OK("composite_kernel");
+    composite_compat_fixup_kernel<true><<<blocks, kCompWarps * 32, 0, st>>>(raw, z_vals, rays_d, n_rays, n_samples,
+        ert_threshold, white_bkgd, compat_chunk, rgb_map, disp_map, acc_map, depth_map, weights, low_flag, chunk_any);
+  } else {
+    composite_kernel<true, false><<<blocks, kCompWarps * 32, 0, st>>>(raw, z_vals, rays_d, n_rays, n_samples, ert_threshold,
+        white_bkgd, rgb_map, disp_map, acc_map, depth_map, weights, nullptr, nullptr, nullptr, low_flag, chunk_any, compat_chunk);
+    NB_LAUNCH_OK("composite_kernel");
+    composite_compat_fixup_kernel<false><<<blocks, kCompWarps * 32, 0, st>>>(raw, z_vals, rays_d, n_rays, n_samples,
+        ert_threshold, white_bkgd, compat_chunk, rgb_map, disp_map, acc_map, depth_map, weights, low_flag, chunk_any);
+  }
+  NB_LAUNCH_OK("composite_compat_fixup_kernel");
+  return 0;
 }
 
 // + ray list (common.cuh: RayList); internal to the whole-pass driver

@@ -313,7 +313,7 @@ class Renderer(PathRenderingMixin):
                     p.cull_rays = 1
                     for c in range(3):
                         p.cull_lo[c], p.cull_hi[c] = lo[c], hi[c]
-        if self.mode == "bf16" and p.variant != L.COMPOSITE_ERT_COMPAT:
+        if self.mode == "bf16":
             p.variant |= L.COMPOSITE_FAST_MATH     # the bf16 MLP output carries 1e-3 already: MUFU exp / sigmoid
         return p
 

@@ -226,6 +226,33 @@ def test_composite_ert_quirk_and_intended_semantics():
     assert float(acc[0]) == 0.0 and float(acc[3000]) > 0.0
 
 
+@pytest.mark.parametrize("gain,bias", [(40.0, 0.0), (40.0, 0.5)])
+def test_driver_ert_compat_two_launch_path_equals_single_kernel(gain, bias):
+    """The whole-pass driver runs the reference's ERT chunk quirk (:1115-1123) as two parallel launches (per-ray ERT +
+    a fix-up of the rays the quirk zeroes); the public entry keeps the literal one-block-per-chunk kernel.  Both must
+    agree bit for bit.  80x80 view = three full 2048-ray chunks + a ragged one; with (40, 0) a few rays per chunk go
+    low (so almost every ray is zeroed by the quirk) and the last chunk has none; with (40, 0.5) almost all go low."""
+    sd = O.make_state_dict(6, gain, bias)
+    b = O.lego_batch(80, 80)
+    bc = {k: (cuda(v) if torch.is_tensor(v) else v) for k, v in b.items()}
+    r = _renderer(sd, "fp32", enable_ert=True)
+    out = r.render(bc)
+    ro, rd = ops.raygen(bc["pose"], bc["intrinsics"], 80, 80)
+    n = ro.shape[0]
+    z = ops.sample_coarse(r._table("z"), n)
+    raw_c = ops.mlp_forward(r.packed("coarse"), ro, rd, z)
+    rgb0, disp0, acc0, w, depth0 = ops.composite_forward(raw_c, z, rd, L.COMPOSITE_ERT_COMPAT, 0.01)
+    z_all = ops.sample_pdf_merge(z, w, r._table("u"), want_aux=False)[0]
+    raw_f = ops.mlp_forward(r.packed("fine"), ro, rd, z_all)
+    rgb, disp, acc, _, depth = ops.composite_forward(raw_f, z_all, rd, L.COMPOSITE_ERT_COMPAT, 0.01, want_weights=False)
+    ref = {"rgb_map_0": rgb0, "disp_map_0": disp0, "acc_map_0": acc0, "depth_map_0": depth0,
+           "rgb_map": rgb, "disp_map": disp, "acc_map": acc, "depth_map": depth}
+    for k, v in ref.items():
+        assert bits_equal(out[k].reshape(v.shape), v), k
+    a0 = acc0.cpu()
+    assert int((a0 == 0).sum()) > 0 and int((a0 > 0.5).sum()) > 0      # zeroed rays and terminated rays both occur
+
+
 def test_composite_edge_cases():
     d = cuda([[0., 0., 1.]])
     # single sample, zero density -> acc 0, disp NaN (0/0), white background rgb 1
