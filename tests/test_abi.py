@@ -65,3 +65,30 @@ def test_renderer_fails_loudly_without_gpu(built_lib):
     from nerf_rep_for_test_b200 import NerfB200Error, Network, Renderer
     with pytest.raises(NerfB200Error):
         Renderer(Network(device="cpu"))
+
+
+def test_argument_errors_of_the_skipping_and_noise_entries(built_lib):
+    """Entry points added for empty-space skipping (keep bits, ray culling) and raw_noise_std reject bad arguments
+    before touching the device."""
+    from nerf_rep_for_test_b200 import lib as L
+    lib = L.load()
+    p8 = ctypes.c_void_p(8)
+    assert lib.nerfb200_sigma_noise(None, 5, 1.0, 0, None) != 0 and b"null" in lib.nerfb200_get_last_error_string()
+    assert lib.nerfb200_sigma_noise(p8, 5, -1.0, 0, None) != 0 and b"std" in lib.nerfb200_get_last_error_string()
+    assert lib.nerfb200_sigma_noise(p8, 0, 1.0, 0, None) == 0                      # empty batch: nothing to do
+    box = (ctypes.c_float * 3)(0, 0, 0)
+    assert lib.nerfb200_ray_cull(p8, p8, 4, p8, 64, box, box, None, None) != 0 and b"null" in lib.nerfb200_get_last_error_string()
+    assert lib.nerfb200_ray_cull(p8, p8, 4, p8, 64, None, box, p8, None) != 0 and b"box" in lib.nerfb200_get_last_error_string()
+    assert lib.nerfb200_ray_cull(p8, p8, 0, p8, 64, box, box, p8, None) == 0
+    # masked compositor: the literal ERT_COMPAT variant has no masked form
+    rc = lib.nerfb200_composite_forward_masked(p8, p8, p8, p8, 4, 64, L.COMPOSITE_ERT_COMPAT, 0.01, 1, 2048, p8, p8, p8, p8,
+                                               None, None)
+    assert rc != 0 and b"masked" in lib.nerfb200_get_last_error_string()
+    # render params: noise cannot be combined with skipping
+    prm = L.RenderParams()
+    prm.n_samples, prm.n_importance, prm.mode, prm.compat_chunk = 64, 128, L.MODE_BF16, 2048
+    prm.raw_noise_std, prm.ess_skip, prm.occupancy_grid, prm.grid_res = 1.0, 1, 8, 128
+    maps = L.Maps(p8, p8, p8, p8)
+    rc = lib.nerfb200_render_rays(p8, p8, p8, p8, 4, p8, p8, ctypes.byref(prm), p8, 1 << 30, ctypes.byref(maps),
+                                  ctypes.byref(maps), None)
+    assert rc != 0 and b"raw_noise_std" in lib.nerfb200_get_last_error_string()
