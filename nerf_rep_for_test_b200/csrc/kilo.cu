@@ -26,8 +26,7 @@
 namespace nb {
 namespace kilo {
 
-constexpr int kHidden = 32;
-constexpr int kPosEmb = 63, kDirEmb = 27;
+// micro-MLP geometry (network_eval.cu:48-52): hidden width 32, 63 position / 27 direction embedding channels
 constexpr int kParamSize = 6212;
 constexpr int kOffL0 = 0;                                   // bias[32] | W[63][32]
 constexpr int kOffL1 = kOffL0 + 32 + 63 * 32;               // bias[32] | W[32][32]

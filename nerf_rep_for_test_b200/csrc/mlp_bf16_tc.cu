@@ -83,7 +83,6 @@ mlp_bf16_tc_kernel(const unsigned char* __restrict__ packed, const float* __rest
     const int slot = warp >> 2;
     const int w4 = warp & 3;
     const int row = w4 * 32 + lane;
-    const uint32_t a_base = smem_base + kOffA + (uint32_t)slot * kABytes;
     const uint32_t pe_base = smem_base + kOffPe + (uint32_t)slot * kPeBytes;
     const uint32_t t_acc = tmem_base + ((uint32_t)(w4 * 32) << 16) + (uint32_t)slot * 256u;
     const uint32_t b_ready = bar(BAR_AREADY + slot), b_full = bar(BAR_ACCFULL + slot);
