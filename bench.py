@@ -255,11 +255,12 @@ def run_ours(args):
     # ---- training step (BASELINE.json configs[2]): 4096 rays per GPU, fwd + bwd + gradient all-reduce +
     # clip + Adam; stratified jitter and random u (net.train()); random target colours
     train_ms = 0.0
+    train_graph = False
     if args.train_steps > 0:
         from nerf_rep_for_test_b200 import training as T
         net.train()
         r.perturb = 1
-        step = T.TrainStep(r)
+        step = T.TrainStep(r, graph=True)   # single process: one CUDA graph per step; N > 1 keeps the eager step
         g = torch.Generator().manual_seed(rank)
         ro_all, rd_all = ops.raygen(lego_pose(rank).to(dev), K0[0].to(dev), H, W)
         sel = torch.randint(0, H * W, (args.train_rays,), generator=g).to(dev)
@@ -275,6 +276,7 @@ def run_ours(args):
         te1.record()
         torch.cuda.synchronize()
         train_ms = te0.elapsed_time(te1)
+        train_graph = step._graph is not None      # the whole step replayed as one CUDA graph (single process only)
         barrier()
         net.eval()
         r.perturb = 0
@@ -420,7 +422,7 @@ def run_ours(args):
                 "value": 1e3 / it_ms, "unit": "it/s", "ms_per_iter": it_ms, "steps": args.train_steps,
                 "warmup": args.train_warmup, "rays_per_iter_per_gpu": args.train_rays,
                 "rays_per_s_total": world * args.train_rays * 1e3 / it_ms, "scaling": "weak",
-                "allreduce_bytes": 1191688 * 4,
+                "allreduce_bytes": 1191688 * 4, "cuda_graph": train_graph,
                 "algorithmic_tflops": 3 * args.train_rays * ROWS_PER_RAY * FLOP_PER_ROW / (it_ms * 1e-3) / 1e12,
                 "note": "every kernel on the path is this repo's: tcgen05 forward with activation store, compositing "
                         "backward, tcgen05 dgrad chain + split-K wgrad GEMMs (nerfb200_mlp_backward); torch supplies "

@@ -312,7 +312,11 @@ int launch_mlp_bwd_dgrad(const void* packed_bwd, const float* g_raw, const void*
   int dev = 0, sms = 0;
   NB_CUDA(cudaGetDevice(&dev));
   NB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  NB_CUDA(cudaFuncSetAttribute(mlp_bwd_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  static int attr_dev = -1;   // per-device, sticky: set once (also keeps the call out of CUDA-graph captures)
+  if (attr_dev != dev) {
+    NB_CUDA(cudaFuncSetAttribute(mlp_bwd_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    attr_dev = dev;
+  }
   long long quads = (M + 511) / 512;
   int clusters = (int)(quads < sms / 2 ? quads : sms / 2);
   mlp_bwd_dgrad_kernel<<<2 * clusters, kThreads, kSmemBytes, st>>>((const unsigned char*)packed_bwd, g_raw,

@@ -294,7 +294,11 @@ int launch_mlp_bwd_wgrad(const void* acts, const void* dacts, long long M, float
   int dev = 0, sms = 0;
   NB_CUDA(cudaGetDevice(&dev));
   NB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  NB_CUDA(cudaFuncSetAttribute(mlp_bwd_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  static int attr_dev = -1;   // per-device, sticky: set once (also keeps the call out of CUDA-graph captures)
+  if (attr_dev != dev) {
+    NB_CUDA(cudaFuncSetAttribute(mlp_bwd_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    attr_dev = dev;
+  }
   NB_CUDA(cudaMemsetAsync(scratch, 0, kGradScratchFloats * sizeof(float), st));
   const int n_tiles = (int)((M + 127) / 128);
   const int clusters = n_tiles < sms / 2 ? n_tiles : sms / 2;

@@ -104,3 +104,39 @@ def test_training_with_density_noise():
     losses = [float(step(ro.to(DEV), rd.to(DEV), target.to(DEV))) for _ in range(30)]
     assert losses[-1] < 0.9 * losses[0], losses[::5]
     assert all(torch.isfinite(p).all() for p in net.parameters())
+
+
+def test_graph_captured_step_equals_eager_step():
+    """TrainStep(graph=True): after three eager warm-up steps the whole step is one CUDA graph.  With jitter off and
+    the network in eval mode (u table) the step is deterministic, so graph replays must reproduce the eager steps bit
+    for bit -- parameters and losses -- including the weight re-packs inside the graph."""
+    outs = []
+    for graph in (False, True):
+        sd, net, r, ro, rd, target = _setup(seed=5, gain=10.0, bias=0.0, n=256)
+        net.eval()
+        r.perturb = 0
+        step = T.TrainStep(r, graph=graph)
+        losses = [float(step(ro.to(DEV), rd.to(DEV), target.to(DEV))) for _ in range(8)]
+        if graph:
+            assert step._graph is not None, "capture fell back to the eager step"
+        outs.append((losses, [p.detach().clone() for p in net.parameters()]))
+    assert outs[0][0] == outs[1][0], (outs[0][0], outs[1][0])
+    for a, b in zip(outs[0][1], outs[1][1]):
+        assert torch.equal(a, b)
+    assert outs[0][0][-1] < outs[0][0][0]
+
+
+def test_graph_captured_step_trains_with_jitter_and_lr_tensor():
+    sd, net, r, ro, rd, target = _setup(seed=5, gain=10.0, bias=0.0, n=256)
+    net.train()
+    r.perturb = 1
+    step = T.TrainStep(r, graph=True)
+    losses = [float(step(ro.to(DEV), rd.to(DEV), target.to(DEV))) for _ in range(30)]
+    assert step._graph is not None
+    assert losses[-1] < 0.7 * losses[0], losses[::5]
+    assert len(set(losses[5:10])) > 1                       # the jitter differs between replays
+    step.set_lr(0.0)                                        # learning rate lives in a device tensor: takes effect in the graph
+    before = [p.detach().clone() for p in net.parameters()]
+    step(ro.to(DEV), rd.to(DEV), target.to(DEV))
+    for a, b in zip(before, net.parameters()):
+        assert torch.equal(a, b)
