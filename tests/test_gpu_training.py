@@ -124,7 +124,9 @@ def test_graph_captured_step_equals_eager_step():
     for le, lg in zip(*[o[0] for o in outs]):
         assert abs(le - lg) <= 2e-5 * max(abs(le), 1e-3), (outs[0][0], outs[1][0])
     for a, b in zip(outs[0][1], outs[1][1]):
-        assert float((a - b).abs().max()) <= 2e-4 * max(float(a.abs().max()), 1e-3)    # 8 Adam steps of lr 5e-4
+        # Adam normalises the gradient: where it is ~0 a last-digit difference can flip a step of size lr, so the bound
+        # is a fraction of the 8 x lr = 4e-3 a parameter can move in these steps (observed: 1.5e-4)
+        assert float((a - b).abs().max()) <= 1e-3
     assert outs[0][0][-1] < outs[0][0][0]
 
 
