@@ -260,7 +260,7 @@ def run_ours(args):
         from nerf_rep_for_test_b200 import training as T
         net.train()
         r.perturb = 1
-        step = T.TrainStep(r, graph=True)   # single process: one CUDA graph per step; N > 1 keeps the eager step
+        step = T.TrainStep(r)   # eager step: the CUDA-graph variant (graph=True) measured the same
         g = torch.Generator().manual_seed(rank)
         ro_all, rd_all = ops.raygen(lego_pose(rank).to(dev), K0[0].to(dev), H, W)
         sel = torch.randint(0, H * W, (args.train_rays,), generator=g).to(dev)

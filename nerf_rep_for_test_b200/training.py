@@ -113,8 +113,10 @@ class TrainStep:
 
     graph=True (single process only): after three eager warm-up steps the whole step -- weight re-packs, sampling,
     both MLP forwards with their activation stores, compositing, loss, both backward chains, clip and Adam -- is
-    captured into ONE CUDA graph and replayed: the ~50 short launches of a step then cost the graph's launch latency
-    instead of a stream launch each (the step is 4.45 ms of kernels in 4.74 ms eager).  Everything random inside the
+    captured into ONE CUDA graph and replayed.  Measured on B200: 213 / 208 / 206 it/s against 209 / 211 / 210 it/s
+    eager on boxes of the same pool, i.e. no gain -- the eager step's host side is three times ahead of the device
+    (1.5 ms of enqueue for 4.7 ms of kernels), and the ~0.3 ms the step spends outside its kernels are dependency
+    bubbles between ~50 short kernels that a graph does not remove.  Kept as an opt-in (slow hosts).  Everything random inside the
     graph comes from torch's graph-aware generator: the stratified jitter is torch.rand through the reference's own
     formula (:228-235) instead of the kernel's hash, u is torch.rand as before.  The learning rate lives in a device
     tensor (set_lr); raw_noise_std > 0 falls back to the eager step (its seed is a kernel argument).  Inputs must keep
