@@ -13,9 +13,12 @@
  *  - plain pointers and sizes only; no torch / C++ types cross this boundary.
  *  - every pointer is a DEVICE pointer unless the name ends in _host.
  *  - the caller allocates every buffer (outputs, packed weights, workspace);
- *    the library allocates nothing, frees nothing, keeps no user pointer after
- *    the call returns and has no global mutable state except the thread-local
- *    last-error string.
+ *    the library allocates no device memory, frees nothing and keeps no user
+ *    pointer after the call returns.  Its only process-wide state: the
+ *    thread-local last-error string, the launch counter, the optional profiling
+ *    events (nerfb200_profile_*), one-time per-device kernel attributes, and the
+ *    copy stream + event that nerfb200_render_image_host creates on first use.
+ *    One host thread per device.
  *  - all work is enqueued on `stream` (a cudaStream_t passed as void*), no
  *    host synchronisation inside unless stated.
  *  - return 0 on success, non-zero on failure with a message available from
@@ -49,8 +52,10 @@ extern "C" {
 #define NERFB200_COMPOSITE_PLAIN 0     /* _raw2outputs, volume_renderer.py:286-357 (T uses 1-alpha+1e-10) */
 #define NERFB200_COMPOSITE_ERT 1       /* _raw2outputs_with_ert intended semantics: zero weights from first T<thr */
 #define NERFB200_COMPOSITE_ERT_COMPAT 2 /* ... literal :1115-1123 incl. the chunk-wide argmax quirk (2048-ray chunks) */
-/* OR-ed into PLAIN / ERT: fast exp / sigmoid (MUFU) instead of the fp64-exact ones that reproduce the CPU
- * reference bit for bit; differences <= 1e-6 on the maps.  The bf16 mode uses it, the fp32 parity mode does not. */
+/* OR-ed into a variant: fast exp / sigmoid (MUFU) and fp32 prefix product / sums instead of the fp64-exact
+ * arithmetic that reproduces the CPU reference bit for bit; differences <= 1e-5 of the map's scale (measured
+ * 1.2e-6).  The bf16 mode uses it, the fp32 parity mode does not.  With ERT_COMPAT it takes effect in the
+ * whole-pass entries only (nerfb200_composite_forward's literal kernel is always exact). */
 #define NERFB200_COMPOSITE_FAST_MATH 0x10
 
 /* network.py:22-47 -- the 24 fp32 tensors of ONE NeRF model in nn.Linear layout

@@ -92,3 +92,32 @@ def test_argument_errors_of_the_skipping_and_noise_entries(built_lib):
     rc = lib.nerfb200_render_rays(p8, p8, p8, p8, 4, p8, p8, ctypes.byref(prm), p8, 1 << 30, ctypes.byref(maps),
                                   ctypes.byref(maps), None)
     assert rc != 0 and b"raw_noise_std" in lib.nerfb200_get_last_error_string()
+
+
+def test_ctypes_structs_match_the_c_header_field_by_field(tmp_path):
+    """Offsets of every field the Python binding mirrors, taken from the C compiler's view of include/nerfb200.h."""
+    import shutil
+    import subprocess
+    from nerf_rep_for_test_b200 import lib as L
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    structs = {"nerfb200_render_params": L.RenderParams, "nerfb200_maps": L.Maps, "nerfb200_mlp_weights": L.MlpWeights,
+               "nerfb200_mlp_grads": L.MlpGrads, "nerfb200_kilo_camera": L.KiloCamera, "nerfb200_kilo_grid": L.KiloGrid,
+               "nerfb200_kilo_march_params": L.KiloMarchParams}
+    lines = ['#include <stdio.h>', '#include "nerfb200.h"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append('  printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('  printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "offsets.c"
+    src.write_text("\n".join(lines) + "\n")
+    exe = tmp_path / "offsets"
+    subprocess.run([gcc, "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    c_view = dict(zip(out[0::2], (int(v) for v in out[1::2])))
+    for cname, cls in structs.items():
+        assert c_view[cname] == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert c_view["%s.%s" % (cname, fname)] == getattr(cls, fname).offset, (cname, fname)
