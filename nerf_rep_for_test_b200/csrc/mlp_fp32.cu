@@ -49,11 +49,13 @@ __device__ __forceinline__ void dense_stage(const float* in0, int ld0, int K0, c
   constexpr int NV = CPT / 4;   // float4 groups per thread: 2 or 1
   const int warp = tid >> 5, lane = tid & 31;
   const int row0 = warp * 8;
-  float acc[8][CPT];
+  // accumulators as fp32 pairs: Blackwell's packed FFMA2 (fma.rn.f32x2) does two independent IEEE fmas per issue
+  // slot -- same arithmetic, same order per accumulator, half the FMA instructions (the scalar version was issue-bound)
+  float2 acc[8][CPT / 2];
 #pragma unroll
   for (int r = 0; r < 8; ++r)
 #pragma unroll
-    for (int c = 0; c < CPT; ++c) acc[r][c] = 0.f;
+    for (int c = 0; c < CPT / 2; ++c) acc[r][c] = make_float2(0.f, 0.f);
   const int nchunks = (K0 + K1) / kKC;
   float* wb0 = &wbuf[0][0][0];
   float* wb1 = &wbuf[1][0][0];
@@ -79,17 +81,19 @@ __device__ __forceinline__ void dense_stage(const float* in0, int ld0, int K0, c
       for (int r = 0; r < 8; ++r) a[r] = *reinterpret_cast<const float4*>(in + (size_t)(row0 + r) * ld + kk);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        float wv[CPT];
+        float2 wv[CPT / 2];
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
           float4 t = *reinterpret_cast<const float4*>(cur + (kk + i) * N + v * 128 + lane * 4);
-          wv[v * 4 + 0] = t.x; wv[v * 4 + 1] = t.y; wv[v * 4 + 2] = t.z; wv[v * 4 + 3] = t.w;
+          wv[v * 2 + 0] = make_float2(t.x, t.y);
+          wv[v * 2 + 1] = make_float2(t.z, t.w);
         }
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-          float av = i == 0 ? a[r].x : (i == 1 ? a[r].y : (i == 2 ? a[r].z : a[r].w));
+          const float av = i == 0 ? a[r].x : (i == 1 ? a[r].y : (i == 2 ? a[r].z : a[r].w));
+          const float2 av2 = make_float2(av, av);
 #pragma unroll
-          for (int cc = 0; cc < CPT; ++cc) acc[r][cc] = fmaf(av, wv[cc], acc[r][cc]);
+          for (int cc = 0; cc < CPT / 2; ++cc) acc[r][cc] = __ffma2_rn(av2, wv[cc], acc[r][cc]);
         }
       }
     }
@@ -101,8 +105,8 @@ __device__ __forceinline__ void dense_stage(const float* in0, int ld0, int K0, c
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       float4 o;
-      o.x = acc[r][v * 4 + 0] + b.x; o.y = acc[r][v * 4 + 1] + b.y;
-      o.z = acc[r][v * 4 + 2] + b.z; o.w = acc[r][v * 4 + 3] + b.w;
+      o.x = acc[r][v * 2 + 0].x + b.x; o.y = acc[r][v * 2 + 0].y + b.y;
+      o.z = acc[r][v * 2 + 1].x + b.z; o.w = acc[r][v * 2 + 1].y + b.w;
       if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
       *reinterpret_cast<float4*>(out + (size_t)(row0 + r) * ldo + v * 128 + lane * 4) = o;
     }
