@@ -3,8 +3,12 @@
 //
 // This is the 1e-5-relative parity mode (true fp32 FFMA, full-range sinf/cosf), not the
 // performance mode (mlp_bf16_tc.cu).  One CTA owns a tile of 64 sample points and walks the ten
-// stages of mlp_layout.cuh with activations resident in shared memory ([64][256] fp32 ping-pong)
-// while W^T streams from L2 through a cp.async double buffer in k-chunks of 16.  Each warp owns
+// stages of mlp_layout.cuh with activations resident in shared memory (ONE [64][256] fp32 buffer: a
+// stage's outputs overwrite its inputs after the barrier that ends its k loop -- the accumulators live
+// in registers) while W^T streams from L2 through a cp.async double buffer in k-chunks of 8.  That is
+// 104 KB per CTA, so two CTAs share an SM and one's barriers / weight waits hide behind the other's
+// FMAs (the first version ping-ponged two activation buffers with 16-wide chunks: 184 KB, one CTA per
+// SM, 8 warps).  Each warp owns
 // 8 rows, each lane 8 (or 4) output columns: per k, 2 broadcast LDS.128 of activations + 2
 // conflict-free LDS.128 of weights feed 64 FFMAs.  HBM sees only rays, z and the 16 B/row result.
 #include "mlp_layout.cuh"
@@ -13,14 +17,13 @@ namespace nb {
 
 constexpr int kTileM = 64;
 constexpr int kThreads = 256;
-constexpr int kKC = 16;
+constexpr int kKC = 8;
 
 struct SmemF32 {
   float pe[kTileM][kPeK];      // 16 KB
   float dpe[kTileM][kDpeK];    //  8 KB
-  float hA[kTileM][kW];        // 64 KB
-  float hB[kTileM][kW];        // 64 KB
-  float wbuf[2][kKC][kW];      // 32 KB
+  float h[kTileM][kW];         // 64 KB
+  float wbuf[2][kKC][kW];      // 16 KB
   float sigma[kTileM];
 };
 
@@ -114,7 +117,7 @@ __device__ __forceinline__ void dense_stage(const float* in0, int ld0, int K0, c
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 mlp_fp32_kernel(const float* __restrict__ packed, const float* __restrict__ rays_o,
                 const float* __restrict__ rays_d, const float* __restrict__ z_vals, long long M, int S,
                 float* __restrict__ raw) {
@@ -161,8 +164,8 @@ mlp_fp32_kernel(const float* __restrict__ packed, const float* __restrict__ rays
   __syncthreads();
 
   const float* bias = packed + kF32BiasOff;
-  float* hA = &sm.hA[0][0];
-  float* hB = &sm.hB[0][0];
+  float* hA = &sm.h[0][0];   // in-place stages: "A" and "B" are the same buffer
+  float* hB = hA;
   float* pe = &sm.pe[0][0];
   float* dpe = &sm.dpe[0][0];
 #define NB_WT(s) (packed + f32_wt_off(s))
@@ -179,7 +182,7 @@ mlp_fp32_kernel(const float* __restrict__ packed, const float* __restrict__ rays
     int r = tid >> 2, q = tid & 3;
     const float* aw = packed + kF32AlphaWOff;
     float s = 0.f;
-    for (int k = q * 64; k < q * 64 + 64; ++k) s = fmaf(sm.hB[r][k], aw[k], s);
+    for (int k = q * 64; k < q * 64 + 64; ++k) s = fmaf(sm.h[r][k], aw[k], s);
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     if (q == 0) sm.sigma[r] = s + packed[kF32AlphaBOff];
@@ -193,7 +196,7 @@ mlp_fp32_kernel(const float* __restrict__ packed, const float* __restrict__ rays
     const float* rw = packed + kF32RgbWOff;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
     for (int k = q * 32; k < q * 32 + 32; ++k) {
-      float h = sm.hB[r][k];
+      float h = sm.h[r][k];
       s0 = fmaf(h, rw[k], s0); s1 = fmaf(h, rw[128 + k], s1); s2 = fmaf(h, rw[256 + k], s2);
     }
 #pragma unroll
