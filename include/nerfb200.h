@@ -47,6 +47,15 @@ extern "C" {
 /* arithmetic modes of the MLP query (SURVEY 8a3 / BASELINE north_star tolerances) */
 #define NERFB200_MODE_FP32 0 /* CUDA-core FFMA, full-range sinf/cosf: 1e-5-relative parity mode */
 #define NERFB200_MODE_BF16 1 /* tcgen05.mma kind::f16 (bf16 in, fp32 accumulate in TMEM): performance mode */
+/* fp32-accurate tensor-core mode: every operand split into two fp16 numbers (22 significand bits), three
+ * tcgen05.mma kind::f16 per K step, fp32 accumulate in TMEM, full-range sincosf -- meets the same 1e-5 gates as
+ * NERFB200_MODE_FP32 (requires |activation| < 65504). */
+#define NERFB200_MODE_FP32_TC 2
+/* nerfb200_render_params.mode only: bits 0-7 = mode of the FINE pass; bits 8-15, when non-zero, = 1 + mode of the
+ * COARSE pass (each model packed for its own mode).  NERFB200_MODE_BF16 | NERFB200_MODE_COARSE(NERFB200_MODE_FP32_TC)
+ * puts the importance samples where the fp32 reference puts them and spends bf16 on the 75 % of the rows that only
+ * feed the final colour; the coarse compositor then runs without NERFB200_COMPOSITE_FAST_MATH. */
+#define NERFB200_MODE_COARSE(m) (((m) + 1) << 8)
 
 /* compositing variants */
 #define NERFB200_COMPOSITE_PLAIN 0     /* _raw2outputs, volume_renderer.py:286-357 (T uses 1-alpha+1e-10) */

@@ -32,6 +32,9 @@ int launch_mlp_fp32(const void* packed, const float* rays_o, const float* rays_d
 int launch_mlp_bf16(const void* packed, const float* rays_o, const float* rays_d, const float* z_vals,
                     int n_rays, int n_samples, float* raw, float* stage_dump, void* acts, void* masks,
                     const int* row_ids, const int* n_active, cudaStream_t st);
+int launch_mlp_f16x2(const void* packed, const float* rays_o, const float* rays_d, const float* z_vals, int n_rays,
+                     int n_samples, float* raw, float* stage_dump, const int* row_ids, const int* n_active,
+                     cudaStream_t st);
 int launch_mlp_bwd_dgrad(const void* packed_bwd, const float* g_raw, const void* masks, void* dacts, long long M,
                          cudaStream_t st);
 int launch_mlp_bwd_wgrad(const void* acts, const void* dacts, long long M, float* scratch, const nerfb200_mlp_weights* weights,
@@ -70,12 +73,20 @@ constexpr int kChunkRays = 32768;
 // Empty-space skipping sends only ~10 % of the rows through the MLP, so an 8192-ray chunk is a fraction of a
 // wave of the persistent kernel (measured: 22.9 ms per frame at 8192, 17.5 ms at 131 072 rays per chunk).
 constexpr int kChunkRaysSparse = 131072;
+// nerfb200_render_params.mode: bits 0-7 = fine-pass mode, bits 8-15 = 1 + coarse-pass mode (0: same as fine)
+static int mode_fine(int mode) { return mode & 0xFF; }
+static int mode_coarse(int mode) { return (mode >> 8) & 0xFF ? ((mode >> 8) & 0xFF) - 1 : (mode & 0xFF); }
+static bool mode_known(int m) { return m == NERFB200_MODE_FP32 || m == NERFB200_MODE_BF16 || m == NERFB200_MODE_FP32_TC; }
+static bool mode_tensor(int m) { return m == NERFB200_MODE_BF16 || m == NERFB200_MODE_FP32_TC; }   // persistent CTA-pair kernels
+
 static int chunk_rays(const nerfb200_render_params* p) {
   if (const char* e = getenv("NERFB200_CHUNK_RAYS")) { int c = atoi(e); if (c >= 2048 && c % 2048 == 0) return c; }   // tuning experiments
   if (p->occupancy_grid && p->ess_skip) return kChunkRaysSparse;
   // The literal ERT_COMPAT compositor groups rays in compat_chunk blocks, which must tile the chunk.
-  if ((p->variant & ~NERFB200_COMPOSITE_FAST_MATH) == NERFB200_COMPOSITE_ERT_COMPAT || p->mode != NERFB200_MODE_BF16) return kChunkRays;
-  // bf16 dense path: the persistent MLP kernel deals 512-row quads to (SMs / 2) CTA pairs, so a chunk whose coarse
+  if ((p->variant & ~NERFB200_COMPOSITE_FAST_MATH) == NERFB200_COMPOSITE_ERT_COMPAT || !mode_tensor(mode_fine(p->mode)) ||
+      !mode_tensor(mode_coarse(p->mode))) return kChunkRays;
+  // tensor-core dense path: the persistent MLP kernel deals 512-row quads (256-row pairs in the split-fp16 mode) to
+  // (SMs / 2) CTA pairs, so a chunk whose coarse
   // launch (n*S/512 quads) is a whole number of rounds wastes no partial last round; with S = 64 and S + U = 192
   // that holds for the fine launch too (32 560 rays on 148 SMs: 55 and 165 full rounds instead of 55.35 and 166.05).
   static int unit = 0;
@@ -135,7 +146,10 @@ static int check_params(const nerfb200_render_params* p) {
   NB_CHECK_ARG(p->n_samples >= 3 && p->n_samples <= 256, "render: n_samples=%d out of range [3,256]", p->n_samples);
   NB_CHECK_ARG(p->n_importance >= 0 && p->n_importance <= 256 && p->n_samples + p->n_importance <= 256,
                "render: n_importance=%d out of range (n_samples+n_importance <= 256)", p->n_importance);
-  NB_CHECK_ARG(p->mode == NERFB200_MODE_FP32 || p->mode == NERFB200_MODE_BF16, "render: unknown mode %d", p->mode);
+  NB_CHECK_ARG((p->mode >> 16) == 0 && mode_known(mode_fine(p->mode)) && mode_known(mode_coarse(p->mode)),
+               "render: unknown mode 0x%x", p->mode);
+  NB_CHECK_ARG(!(p->occupancy_grid && p->ess_skip) || (mode_tensor(mode_fine(p->mode)) && mode_tensor(mode_coarse(p->mode))),
+               "render: ess_skip needs a tensor-core mode (sparse MLP launch)");
   NB_CHECK_ARG((p->variant & ~NERFB200_COMPOSITE_FAST_MATH) >= 0 && (p->variant & ~NERFB200_COMPOSITE_FAST_MATH) <= 2,
                "render: unknown composite variant %d", p->variant);
   NB_CHECK_ARG((p->variant & ~NERFB200_COMPOSITE_FAST_MATH) != NERFB200_COMPOSITE_ERT_COMPAT || (p->compat_chunk > 0 && kChunkRays % p->compat_chunk == 0),
@@ -161,11 +175,12 @@ extern "C" int nerfb200_mlp_forward(const void* packed, int mode, const float* r
   NB_CHECK_ARG(n_rays >= 0 && n_samples >= 1, "mlp_forward: bad sizes n_rays=%d n_samples=%d", n_rays, n_samples);
   NB_CHECK_ARG(((uintptr_t)packed & 1023) == 0, "mlp_forward: packed weights must be 1024-byte aligned");
   if (n_rays == 0) return 0;
-  NB_CHECK_ARG(mode == NERFB200_MODE_FP32 || mode == NERFB200_MODE_BF16, "mlp_forward: unknown mode %d", mode);
+  NB_CHECK_ARG(mode_known(mode), "mlp_forward: unknown mode %d", mode);
   cudaStream_t st = (cudaStream_t)stream;
   bool prof = prof_begin(st);
   int rc = mode == NERFB200_MODE_FP32 ? launch_mlp_fp32(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, st)
-                                      : launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, nullptr, nullptr, nullptr, nullptr, nullptr, st);
+           : mode == NERFB200_MODE_FP32_TC ? launch_mlp_f16x2(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, nullptr, nullptr, nullptr, st)
+                                           : launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, nullptr, nullptr, nullptr, nullptr, nullptr, st);
   if (prof) prof_end(st, (double)n_rays * n_samples);
   return rc;
 }
@@ -226,14 +241,16 @@ static int mlp_forward_sparse_impl(const void* packed, int mode, const float* ra
   NB_CHECK_ARG(n_rays <= 0 || (packed && rays_o && rays_d && z_vals && raw && row_ids && n_active),
                "mlp_forward_sparse: null pointer");
   NB_CHECK_ARG(n_rays >= 0 && n_samples >= 1, "mlp_forward_sparse: bad sizes");
-  NB_CHECK_ARG(mode == NERFB200_MODE_BF16, "mlp_forward_sparse: only NERFB200_MODE_BF16 has the sparse launch");
+  NB_CHECK_ARG(mode_tensor(mode), "mlp_forward_sparse: only the tensor-core modes have the sparse launch");
   NB_CHECK_ARG(((uintptr_t)packed & 1023) == 0, "mlp_forward_sparse: packed weights must be 1024-byte aligned");
   if (n_rays == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   // skipped rows keep raw = 0: sigma_raw = 0 -> alpha = 0 -> no contribution (and rgb_raw is never used)
   if (zero_fill) NB_CUDA(cudaMemsetAsync(raw, 0, (size_t)n_rays * n_samples * 16, st));
   bool prof = prof_begin(st);
-  int rc = launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, nullptr, nullptr, nullptr, row_ids, n_active, st);
+  int rc = mode == NERFB200_MODE_FP32_TC
+               ? launch_mlp_f16x2(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, nullptr, row_ids, n_active, st)
+               : launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, nullptr, nullptr, nullptr, row_ids, n_active, st);
   if (prof) prof_end(st, 0.0);   // evaluated rows are data dependent; counted by the caller from n_active
   return rc;
 }
@@ -271,8 +288,10 @@ extern "C" int nerfb200_mlp_forward_stages(const void* packed, int mode, const f
                                            float* stage_dump, void* stream) {
   NB_CHECK_ARG(packed && rays_o && rays_d && z_vals && raw && stage_dump, "mlp_forward_stages: null pointer");
   NB_CHECK_ARG(n_rays >= 1 && n_samples >= 1, "mlp_forward_stages: bad sizes");
-  NB_CHECK_ARG(mode == NERFB200_MODE_BF16, "mlp_forward_stages: only NERFB200_MODE_BF16 has a stage dump");
+  NB_CHECK_ARG(mode_tensor(mode), "mlp_forward_stages: only the tensor-core modes have a stage dump");
   NB_CHECK_ARG(((uintptr_t)packed & 1023) == 0, "mlp_forward_stages: packed weights must be 1024-byte aligned");
+  if (mode == NERFB200_MODE_FP32_TC)
+    return launch_mlp_f16x2(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, stage_dump, nullptr, nullptr, (cudaStream_t)stream);
   return launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, stage_dump, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
@@ -299,6 +318,9 @@ static int render_rays_impl(const void* packed_coarse, const void* packed_fine, 
   NB_CHECK_ARG(mc->rgb && mc->disp && mc->acc && mc->depth, "render_rays: null coarse map");
   NB_CHECK_ARG(n_rays >= 0, "render_rays: negative n_rays");
   const int S = p->n_samples, U = p->n_importance;
+  const int mode_c = mode_coarse(p->mode), mode_f = mode_fine(p->mode);
+  // mixed precision: an accurate coarse pass keeps its exact compositor (its weights place the fine samples)
+  const int variant_c = (mode_c != NERFB200_MODE_BF16) ? (p->variant & ~NERFB200_COMPOSITE_FAST_MATH) : p->variant;
   if (U > 0) {
     NB_CHECK_ARG(packed_fine && u && mf && mf->rgb && mf->disp && mf->acc && mf->depth,
                  "render_rays: fine pass needs packed_fine, u and fine maps");
@@ -340,19 +362,20 @@ static int render_rays_impl(const void* packed_coarse, const void* packed_fine, 
     if (sparse) {
       if ((e = ess_compact_culled(p->occupancy_grid, p->grid_res, ro, rd, ws.z_coarse, nullptr, active, n, S, ws.row_ids,
                                   ws.counters + 0, ws.keep_bits, stream))) return e;
-      if ((e = mlp_forward_sparse_impl(packed_coarse, p->mode, ro, rd, ws.z_coarse, n, S, ws.row_ids, ws.counters + 0,
+      if ((e = mlp_forward_sparse_impl(packed_coarse, mode_c, ro, rd, ws.z_coarse, n, S, ws.row_ids, ws.counters + 0,
                                        ws.raw_c, !masked, stream))) return e;
-    } else if ((e = nerfb200_mlp_forward(packed_coarse, p->mode, ro, rd, ws.z_coarse, n, S, ws.raw_c, stream))) return e;
+    } else if ((e = nerfb200_mlp_forward(packed_coarse, mode_c, ro, rd, ws.z_coarse, n, S, ws.raw_c, stream))) return e;
     if (p->raw_noise_std > 0.f &&
         (e = nerfb200_sigma_noise(ws.raw_c, (long long)n * S, p->raw_noise_std, noise_seed + 0x632BE59BD9B4E019ull, stream))) return e;
     const bool compat = (p->variant & ~NERFB200_COMPOSITE_FAST_MATH) == NERFB200_COMPOSITE_ERT_COMPAT;
     const int fast = (p->variant & NERFB200_COMPOSITE_FAST_MATH) != 0;
+    const int fast_c = (variant_c & NERFB200_COMPOSITE_FAST_MATH) != 0;
     if (compat) {
-      if ((e = composite_forward_compat2(ws.raw_c, ws.z_coarse, rd, n, S, fast, p->ert_threshold, p->white_bkgd,
+      if ((e = composite_forward_compat2(ws.raw_c, ws.z_coarse, rd, n, S, fast_c, p->ert_threshold, p->white_bkgd,
                                          p->compat_chunk, mc->rgb + (size_t)r0 * 3, mc->disp + r0, mc->acc + r0,
                                          mc->depth + r0, ws.weights, reinterpret_cast<uint8_t*>(ws.ray_list),
                                          ws.compat_any, stream))) return e;
-    } else if ((e = composite_forward_culled(ws.raw_c, ws.z_coarse, rd, keep, active, n, S, p->variant, p->ert_threshold,
+    } else if ((e = composite_forward_culled(ws.raw_c, ws.z_coarse, rd, keep, active, n, S, variant_c, p->ert_threshold,
                                       p->white_bkgd, p->compat_chunk, mc->rgb + (size_t)r0 * 3, mc->disp + r0,
                                       mc->acc + r0, mc->depth + r0, ws.weights, stream))) return e;
     if (U > 0) {
@@ -368,12 +391,12 @@ static int render_rays_impl(const void* packed_coarse, const void* packed_fine, 
         }
         if ((e = ess_compact_culled(p->occupancy_grid, p->grid_res, ro, rd, ws.z_all, zt, active, n, S + U, ws.row_ids,
                                     ws.counters + 1, ws.keep_bits, stream))) return e;
-        if ((e = mlp_forward_sparse_impl(packed_fine, p->mode, ro, rd, ws.z_all, n, S + U, ws.row_ids, ws.counters + 1,
+        if ((e = mlp_forward_sparse_impl(packed_fine, mode_f, ro, rd, ws.z_all, n, S + U, ws.row_ids, ws.counters + 1,
                                          ws.raw_f, !masked, stream))) return e;
         if (p->eval_counts) {   // optional statistics: evaluated rows per pass, accumulated over the call
           if ((e = nerfb200_accumulate_counts(ws.counters, p->eval_counts, stream))) return e;
         }
-      } else if ((e = nerfb200_mlp_forward(packed_fine, p->mode, ro, rd, ws.z_all, n, S + U, ws.raw_f, stream))) return e;
+      } else if ((e = nerfb200_mlp_forward(packed_fine, mode_f, ro, rd, ws.z_all, n, S + U, ws.raw_f, stream))) return e;
       if (p->raw_noise_std > 0.f &&
           (e = nerfb200_sigma_noise(ws.raw_f, (long long)n * (S + U), p->raw_noise_std, noise_seed + 0x94D049BB133111EBull, stream))) return e;
       if (compat) {

@@ -72,6 +72,20 @@ constexpr int kFusedStageOff = (kBf16TotalBytes + 1023) / 1024 * 1024;
 constexpr int kFusedTailOff = kFusedStageOff + kFusedChunks * kFusedChunkBytes;   // fp32 [256]: b'(128), alpha_b, 0...
 constexpr int kBf16PackedBytes = kFusedTailOff + 256 * 4;
 
+// ---- split-fp16 layout (NERFB200_MODE_FP32_TC, bytes): the ten UNFUSED stages, every K-chunk as TWO images of the
+// bf16 geometry above -- [hi | lo], each N rows x 128 B, pre-swizzled -- holding w_hi = fp16(w * 2^e_s) and
+// w_lo = fp16(w * 2^e_s - w_hi): 22 significand bits per weight.  e_s is a per-stage power of two chosen at pack time
+// so that max|w| * 2^e_s lies in [2^13, 2^14) (the residuals of all weights within 2^-16 of the largest stay normal
+// fp16 numbers); the epilogue multiplies the accumulator by 2^-e_s (exact).  The fp32 tail is the bf16 tail followed by
+// inv_scale[16] = 2^-e_s and fwd_scale[16] = 2^e_s.
+__host__ __device__ constexpr int x2_chunk_bytes(int s) { return 2 * bf16_chunk_bytes(s); }
+__host__ __device__ constexpr int x2_stage_off(int s) { return 2 * bf16_stage_off(s); }
+constexpr int kX2TailOff = 2 * kBf16TailOff;
+constexpr int kTailInvScale = kTailFloats;
+constexpr int kTailFwdScale = kTailFloats + 16;
+constexpr int kX2TailFloats = kTailFloats + 32;
+constexpr int kX2PackedBytes = kX2TailOff + kX2TailFloats * 4;
+
 // source element of stage s, output n, padded input k (returns false when the slot is padding)
 struct SrcRef { int tensor; int col; };  // tensor: 0..7 pts, 8 feature, 9 views
 __host__ __device__ inline bool stage_src(int s, int k, SrcRef* r) {

@@ -1,6 +1,7 @@
 // Weight repacking: nn.Linear fp32 state_dict tensors (network.py:22-47, layout frozen) ->
 // the streaming layouts of mlp_layout.cuh.  Re-run after every optimizer step.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "mlp_layout.cuh"
 #include "train_layout.cuh"
@@ -75,6 +76,59 @@ __global__ void pack_bf16_kernel(nerfb200_mlp_weights w, StageTable tab, unsigne
     size_t off = (size_t)tab.bf16_off[s] + (size_t)c * (N * 128) + (size_t)n * 128 +
                  (size_t)(((kk >> 3) ^ (n & 7)) << 4) + (size_t)(kk & 7) * 2;
     *reinterpret_cast<__nv_bfloat16*>(dst + off) = __float2bfloat16_rn(v);
+  }
+}
+
+// split-fp16 image (NERFB200_MODE_FP32_TC, mlp_layout.cuh): one block per stage finds max|w| of the stage's tensor and
+// writes the power-of-two scale 2^e (max|w| * 2^e in [2^13, 2^14)) and its inverse into the tail
+__global__ void stage_scale_kernel(nerfb200_mlp_weights w, float* __restrict__ tail) {
+  const int s = blockIdx.x;   // stage index = tensor index (0..7 pts_linears, 8 feature_linear, 9 views_linears.0)
+  const float* W = tensor_w(w, s);
+  const int count = stage_n(s) * tensor_in_features(s);
+  float mx = 0.f;
+  for (int i = threadIdx.x; i < count; i += blockDim.x) mx = fmaxf(mx, fabsf(W[i]));
+  __shared__ float red[32];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
+    int e = 0;
+    if (mx > 0.f && mx <= 3.0e38f) {
+      int ex;
+      frexpf(mx, &ex);   // mx = m * 2^ex, m in [0.5, 1)
+      e = 14 - ex;
+    }
+    e = e < -60 ? -60 : (e > 60 ? 60 : e);
+    tail[kTailInvScale + s] = ldexpf(1.f, -e);
+    tail[kTailFwdScale + s] = ldexpf(1.f, e);
+  }
+}
+
+__global__ void pack_f16x2_kernel(nerfb200_mlp_weights w, unsigned char* __restrict__ dst) {
+  const int s = blockIdx.y;
+  float* tail = reinterpret_cast<float*>(dst + kX2TailOff);
+  if (s == kStages) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kTailFloats; i += gridDim.x * blockDim.x) pack_tail(w, tail, i);
+    return;
+  }
+  const float scale = tail[kTailFwdScale + s];   // written by stage_scale_kernel, earlier on the same stream
+  const int N = stage_n(s), K = stage_k(s), chunks = stage_chunks(s);
+  const int total = chunks * N * 64;
+  const size_t part = (size_t)N * 128;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i / (N * 64), n = (i / 64) % N, kk = i % 64;
+    const int k = c * 64 + kk;
+    SrcRef r;
+    float v = 0.f;
+    if (k < K && stage_src(s, k, &r)) v = tensor_w(w, r.tensor)[(size_t)n * tensor_in_features(r.tensor) + r.col] * scale;
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn(v - __half2float(hi));
+    const size_t off = (size_t)x2_stage_off(s) + (size_t)c * (2 * part) + (size_t)n * 128 +
+                       (size_t)(((kk >> 3) ^ (n & 7)) << 4) + (size_t)(kk & 7) * 2;
+    *reinterpret_cast<__half*>(dst + off) = hi;
+    *reinterpret_cast<__half*>(dst + off + part) = lo;
   }
 }
 
@@ -169,12 +223,14 @@ using namespace nb;
 extern "C" size_t nerfb200_packed_weights_bytes(int mode) {
   if (mode == NERFB200_MODE_FP32) return (size_t)kF32TotalFloats * 4;
   if (mode == NERFB200_MODE_BF16) return (size_t)kBf16PackedBytes;
+  if (mode == NERFB200_MODE_FP32_TC) return (size_t)kX2PackedBytes;
   return 0;
 }
 
 extern "C" int nerfb200_pack_weights(const nerfb200_mlp_weights* w, int mode, void* packed, void* stream) {
   NB_CHECK_ARG(w && packed, "pack_weights: null pointer");
-  NB_CHECK_ARG(mode == NERFB200_MODE_FP32 || mode == NERFB200_MODE_BF16, "pack_weights: unknown mode %d", mode);
+  NB_CHECK_ARG(mode == NERFB200_MODE_FP32 || mode == NERFB200_MODE_BF16 || mode == NERFB200_MODE_FP32_TC,
+               "pack_weights: unknown mode %d", mode);
   NB_CHECK_ARG(((uintptr_t)packed & 1023) == 0, "pack_weights: packed buffer must be 1024-byte aligned");
   for (int i = 0; i < 8; ++i) NB_CHECK_ARG(w->pts_w[i] && w->pts_b[i], "pack_weights: null pts_linears.%d", i);
   NB_CHECK_ARG(w->views_w && w->views_b && w->feature_w && w->feature_b && w->alpha_w && w->alpha_b && w->rgb_w &&
@@ -187,7 +243,11 @@ extern "C" int nerfb200_pack_weights(const nerfb200_mlp_weights* w, int mode, vo
   dim3 grid(64, kStages + 1);
   if (mode == NERFB200_MODE_FP32)
     pack_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*w, tab, (float*)packed);
-  else {
+  else if (mode == NERFB200_MODE_FP32_TC) {
+    stage_scale_kernel<<<kStages, 256, 0, (cudaStream_t)stream>>>(*w, reinterpret_cast<float*>((unsigned char*)packed + kX2TailOff));
+    NB_LAUNCH_OK("stage_scale_kernel");
+    pack_f16x2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*w, (unsigned char*)packed);
+  } else {
     pack_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*w, tab, (unsigned char*)packed);
     NB_LAUNCH_OK("pack_bf16_kernel");
     pack_bf16_fused_kernel<<<96, 256, 0, (cudaStream_t)stream>>>(*w, (unsigned char*)packed);

@@ -10,7 +10,14 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NERFB200_LIB") or os.path.join(HERE, "libnerfb200.so")   # env override: A/B experiments only
 
-MODE_FP32, MODE_BF16 = 0, 1
+MODE_FP32, MODE_BF16, MODE_FP32_TC = 0, 1, 2
+
+
+def mode_coarse(m):
+    """NERFB200_MODE_COARSE(m): OR-ed into RenderParams.mode to give the coarse pass its own arithmetic mode."""
+    return (m + 1) << 8
+
+
 COMPOSITE_PLAIN, COMPOSITE_ERT, COMPOSITE_ERT_COMPAT = 0, 1, 2
 COMPOSITE_FAST_MATH = 0x10          # OR-ed into PLAIN / ERT (include/nerfb200.h)
 ABI_VERSION = 3

@@ -117,14 +117,19 @@ def occupied_box(grid):
 
 
 class Renderer(PathRenderingMixin):
-    MODES = {"fp32": L.MODE_FP32, "bf16": L.MODE_BF16}
+    # name -> (coarse-pass mode, fine-pass mode).  "fp32tc": split-fp16 tensor-core arithmetic, as accurate as "fp32"
+    # (the CUDA-core kernel) at a fraction of its time; "mixed": fp32tc for the coarse network (so the importance
+    # samples land where the fp32 reference puts them), bf16 for the fine network.
+    MODES = {"fp32": (L.MODE_FP32, L.MODE_FP32), "bf16": (L.MODE_BF16, L.MODE_BF16),
+             "fp32tc": (L.MODE_FP32_TC, L.MODE_FP32_TC), "mixed": (L.MODE_FP32_TC, L.MODE_BF16)}
 
     def __init__(self, net, cfg=None, mode=None, ref_compat=True):
         """net: a Network with `.model`, `.model_fine` (reference network.py or ours).
 
         cfg: RenderConfig, a scaffold yacs cfg, or None (then `src.config.cfg` when the scaffold is
-        importable, else lego.yaml defaults).  mode: 'bf16' (tcgen05 performance mode) or 'fp32'
-        (parity mode).  ref_compat: reproduce the reference's ERT chunk quirk (:1115-1123).
+        importable, else lego.yaml defaults).  mode: 'bf16' (tcgen05 performance mode), 'fp32tc' (fp32-accurate
+        tensor-core mode), 'mixed' (coarse fp32tc + fine bf16) or 'fp32' (CUDA-core parity mode).
+        ref_compat: reproduce the reference's ERT chunk quirk (:1115-1123).
         """
         self.lib = L.load()
         if not torch.cuda.is_available():
@@ -163,7 +168,7 @@ class Renderer(PathRenderingMixin):
             raise L.NerfB200Error("use_viewdirs=False is not implemented by the B200 path")
         self.mode = mode or "bf16"
         if self.mode not in self.MODES:
-            raise ValueError("mode must be 'bf16' or 'fp32'")
+            raise ValueError("mode must be one of %s" % sorted(self.MODES))
         self.ref_compat = bool(ref_compat)
         # "resample" = the reference's ESS (:1009-1087); "skip" = samples in empty cells (and, with ERT,
         # fine samples behind the coarse termination depth) are never sent through the MLP
@@ -202,7 +207,7 @@ class Renderer(PathRenderingMixin):
     # ------------------------------------------------------------------ plumbing
     def _packed_weights(self, which):
         model = self.coarse_model if which == "coarse" else self.fine_model
-        mode = self.MODES[self.mode]
+        mode = self.MODES[self.mode][0 if which == "coarse" else 1]
         key = tuple((p.data_ptr(), p._version) for p in model.parameters()) + (mode,)
         ent = self._packed.get(which)
         if ent is not None and ent[0] == key:
@@ -254,7 +259,7 @@ class Renderer(PathRenderingMixin):
         try:
             h = _Handle()
             h.ptr = self._packed_ptr(which)
-            h.mode = self.MODES[self.mode]
+            h.mode = self.MODES[self.mode][0 if which == "coarse" else 1]
         finally:
             self.mode = old_mode
         return h
@@ -280,7 +285,8 @@ class Renderer(PathRenderingMixin):
         p = L.RenderParams()
         p.raw_noise_std = max(float(self.raw_noise_std or 0.0), 0.0)   # :310-314 (lego.yaml:23 uses 0)
         p.n_samples, p.n_importance = self.N_samples, self.N_importance
-        p.mode = self.MODES[self.mode]
+        mode_c, mode_f = self.MODES[self.mode]
+        p.mode = mode_f | (L.mode_coarse(mode_c) if mode_c != mode_f else 0)
         if self.enable_ert:
             p.variant = L.COMPOSITE_ERT_COMPAT if self.ref_compat else L.COMPOSITE_ERT
         else:
@@ -297,8 +303,8 @@ class Renderer(PathRenderingMixin):
             p.occupancy_grid = self._grid_u8.data_ptr()
             p.grid_res = self.occupancy_grid.shape[0]
             if self.ess_mode == "skip":
-                if self.mode != "bf16":
-                    raise L.NerfB200Error("ess_mode='skip' needs mode='bf16' (sparse MLP launch)")
+                if self.mode == "fp32":
+                    raise L.NerfB200Error("ess_mode='skip' needs a tensor-core mode (sparse MLP launch)")
                 if p.raw_noise_std > 0:
                     raise L.NerfB200Error("raw_noise_std > 0 cannot be combined with ess_mode='skip' "
                                           "(skipped samples have zero density by definition)")
@@ -313,8 +319,10 @@ class Renderer(PathRenderingMixin):
                     p.cull_rays = 1
                     for c in range(3):
                         p.cull_lo[c], p.cull_hi[c] = lo[c], hi[c]
-        if self.mode == "bf16":
-            p.variant |= L.COMPOSITE_FAST_MATH     # the bf16 MLP output carries 1e-3 already: MUFU exp / sigmoid
+        if mode_f == L.MODE_BF16:
+            # the bf16 MLP output carries 1e-3 already: MUFU exp / sigmoid (an fp32-accurate coarse pass of the mixed
+            # mode keeps its exact compositor inside the library)
+            p.variant |= L.COMPOSITE_FAST_MATH
         return p
 
     def _occupied_box(self):

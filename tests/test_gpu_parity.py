@@ -322,24 +322,33 @@ def _mlp_ref(sd, prefix, ro, rd, z):
         return O.query_network(sd, prefix, pts, rd)
 
 
+ACCURATE = ["fp32", "fp32tc"]     # CUDA-core FFMA kernel / split-fp16 tensor-core kernel: same gates
+
+
+def _mode_id(name):
+    return {"fp32": L.MODE_FP32, "fp32tc": L.MODE_FP32_TC, "bf16": L.MODE_BF16}[name]
+
+
+@pytest.mark.parametrize("mode", ACCURATE)
 @pytest.mark.parametrize("prefix,n,S", [("model.", 64, 64), ("model_fine.", 37, 192), ("model.", 3, 5)])
-def test_mlp_fp32_vs_oracle(prefix, n, S):
+def test_mlp_fp32_vs_oracle(prefix, n, S, mode):
     sd = O.make_state_dict(0)
     b = O.lego_batch(16, 16)
     ro, rd = O.get_rays(16, 16, b["pose"][0], b["intrinsics"][0])
     ro, rd = ro[:n].contiguous(), rd[:n].contiguous()
     z, _ = torch.sort(torch.rand(n, S, generator=torch.Generator().manual_seed(S)) * 4 + 2, -1)
-    packed = ops.pack_from_state_dict(sd, prefix, L.MODE_FP32, DEV)
+    packed = ops.pack_from_state_dict(sd, prefix, _mode_id(mode), DEV)
     raw = ops.mlp_forward(packed, cuda(ro), cuda(rd), cuda(z))
     ref = _mlp_ref(sd, prefix, ro, rd, z)
-    # fp32 FFMA vs MKL sgemm: different summation order only
+    # fp32 FFMA (or split-fp16 MMA with fp32 accumulation) vs MKL sgemm: different summation order only
     rel_close(raw, ref, 2e-5, 2e-6)
 
 
-def test_mlp_fp32_vs_reference_golden_raw():
+@pytest.mark.parametrize("mode", ACCURATE)
+def test_mlp_fp32_vs_reference_golden_raw(mode):
     g = golden("lego16_randinit")
     sd = O.make_state_dict(0)
-    packed = ops.pack_from_state_dict(sd, "model_fine.", L.MODE_FP32, DEV)
+    packed = ops.pack_from_state_dict(sd, "model_fine.", _mode_id(mode), DEV)
     raw = ops.mlp_forward(packed, cuda(g["rays_o"]), cuda(g["rays_d"]), cuda(g["aux_z_all"]))
     rel_close(raw, g["aux_raw_fine"], 2e-5, 2e-6)
 
@@ -401,12 +410,13 @@ def _renderer(sd, mode, **cfg):
 MAPS = ["rgb_map_0", "depth_map_0", "acc_map_0", "disp_map_0", "rgb_map", "depth_map", "acc_map", "disp_map"]
 
 
+@pytest.mark.parametrize("mode", ACCURATE)
 @pytest.mark.parametrize("name", ["lego16_randinit", "lego16_randinit_ert", "lego8_dense", "lego8_dense_ert"])
-def test_render_fp32_vs_reference_golden(name):
+def test_render_fp32_vs_reference_golden(name, mode):
     g = golden(name)
     H, W, seed, gain, bias, ert = g["meta"]
     sd = O.make_state_dict(int(seed), float(gain), float(bias))
-    r = _renderer(sd, "fp32", enable_ert=bool(ert))
+    r = _renderer(sd, mode, enable_ert=bool(ert))
     out = r.render({"pose": cuda(g["pose"]), "intrinsics": cuda(g["intrinsics"]), "H": int(H), "W": int(W)})
     assert sorted(out) == sorted(MAPS)
     assert out["rgb_map"].shape == (int(H), int(W), 3) and out["depth_map"].shape == (int(H), int(W))
@@ -426,17 +436,18 @@ def test_render_fp32_vs_reference_golden(name):
         pure = (err / ref.abs().clamp_min(1e-3)).flatten()
         q = lambda t, f: float(t.kthvalue(max(1, int(f * t.numel())))[0])
         med, p99, mx = q(rel, 0.5), q(rel, 0.99), float(rel.max())
-        print("%s %-12s err/scale median %.2e p99 %.2e max %.2e | per-ray relative median %.2e p99 %.2e" % (
-            name, k, med, p99, mx, q(pure, 0.5), q(pure, 0.99)))
+        print("%s %s %-12s err/scale median %.2e p99 %.2e max %.2e | per-ray relative median %.2e p99 %.2e" % (
+            mode, name, k, med, p99, mx, q(pure, 0.5), q(pure, 0.99)))
         if "disp" in k:
             continue    # 1/(depth/acc): unbounded when acc ~ 0 (NaN at acc == 0); reported only
         assert p99 <= 1e-5 and mx <= 2e-4, (k, med, p99, mx)
 
 
-def test_render_fp32_vs_oracle_rays_and_host_entry():
+@pytest.mark.parametrize("mode", ACCURATE)
+def test_render_fp32_vs_oracle_rays_and_host_entry(mode):
     sd = O.make_state_dict(2, 30.0, 0.2)
     b = O.lego_batch(12, 20)
-    r = _renderer(sd, "fp32")
+    r = _renderer(sd, mode)
     out = r.render({k: (cuda(v) if torch.is_tensor(v) else v) for k, v in b.items()})
     with torch.no_grad():
         ref = O.render(sd, b)
@@ -688,14 +699,15 @@ def test_render_ess_skip_mode_structure_and_counts():
 
 
 # ------------------------------------------------------------------------------- config switches of the reference
+@pytest.mark.parametrize("mode", ACCURATE)
 @pytest.mark.parametrize("cfg", [dict(white_bkgd=0), dict(lindisp=True), dict(N_importance=0),
                                  dict(N_samples=32, N_importance=64), dict(near=1.0, far=5.0)])
-def test_render_fp32_config_switches_vs_oracle(cfg):
+def test_render_fp32_config_switches_vs_oracle(cfg, mode):
     """white_bkgd / lindisp / N_importance=0 / other sample counts and bounds (volume_renderer.py:31-48,
     :223-224, :179, :352-354) against the oracle with the same switches."""
     sd = O.make_state_dict(7, 30.0, 0.2)
     b = O.lego_batch(10, 14)
-    r = _renderer(sd, "fp32", **cfg)
+    r = _renderer(sd, mode, **cfg)
     out = r.render({k: (cuda(v) if torch.is_tensor(v) else v) for k, v in b.items()})
     ro, rd = O.get_rays(10, 14, b["pose"][0], b["intrinsics"][0])
     S, U = cfg.get("N_samples", 64), cfg.get("N_importance", 128)
