@@ -60,19 +60,44 @@ def test_fp32tc_stages_vs_oracle_hidden():
 @pytest.mark.parametrize("n,S", [(1, 1), (5, 51), (300, 64), (1000, 192), (20000, 64)])
 def test_fp32tc_matches_cuda_core_fp32_kernel(n, S):
     """Ragged and multi-round sizes (20000 x 64 rows = 5000 CTA-pair tiles over 74 clusters): the tensor-core
-    kernel against the CUDA-core fp32 kernel on the same inputs, within fp32 summation-order noise."""
+    kernel against the CUDA-core fp32 kernel on the same inputs, within fp32 summation-order noise (2e-5 of each
+    output channel's magnitude: sigma_raw is a 256-term dot product with 30x-scaled weights that cancels)."""
     sd = O.make_state_dict(5, 30.0, 0.2)
     ro, rd, z = _rays(n, S, seed=n)
     p32 = ops.pack_from_state_dict(sd, "model_fine.", L.MODE_FP32, DEV)
     ptc = ops.pack_from_state_dict(sd, "model_fine.", L.MODE_FP32_TC, DEV)
     a = ops.mlp_forward(p32, cuda(ro), cuda(rd), cuda(z))
     b = ops.mlp_forward(ptc, cuda(ro), cuda(rd), cuda(z))
-    err = (a - b).abs()
-    bound = 2e-6 + 2e-5 * a.abs()
-    assert bool((err <= bound).all()), (float(err.max()), float((err / bound).max()))
+    err = (a - b).abs().reshape(-1, 4)
+    scale = a.abs().reshape(-1, 4).max(0)[0].clamp_min(0.1)
+    assert bool((err <= 2e-5 * scale).all()), (err.max(0)[0].tolist(), scale.tolist())
     # and run to run bit-identical (no dependence on which cluster picked a tile up)
     b2 = ops.mlp_forward(ptc, cuda(ro), cuda(rd), cuda(z))
     assert torch.equal(b, b2)
+
+
+def test_fp32tc_is_as_accurate_as_fp32_against_float64():
+    """The claim of the mode: against a float64 evaluation of the same network the split-fp16 tensor-core kernel is
+    no further away than true fp32 arithmetic is (the CUDA-core FFMA kernel and the torch-CPU fp32 oracle)."""
+    sd = O.make_state_dict(5, 30.0, 0.2)
+    n, S = 300, 64
+    ro, rd, z = _rays(n, S, seed=11)
+    pts = (ro[:, None] + rd[:, None] * z[..., None]).reshape(-1, 3)
+    vd = rd[:, None].expand(n, S, 3).reshape(-1, 3)
+    emb = torch.cat([O.pos_enc(pts, 10), O.pos_enc(vd, 4)], -1)
+    with torch.no_grad():
+        ref32 = O.nerf_mlp(sd, "model_fine.", emb)
+        ref64 = O.nerf_mlp({k: v.double() for k, v in sd.items()}, "model_fine.", emb.double())
+    got = {}
+    for name, mode in (("fp32", L.MODE_FP32), ("fp32tc", L.MODE_FP32_TC)):
+        packed = ops.pack_from_state_dict(sd, "model_fine.", mode, DEV)
+        got[name] = ops.mlp_forward(packed, cuda(ro), cuda(rd), cuda(z)).cpu().reshape(-1, 4).double()
+    e_cpu = (ref32.double() - ref64).abs().max(0)[0]
+    e_f32 = (got["fp32"] - ref64).abs().max(0)[0]
+    e_tc = (got["fp32tc"] - ref64).abs().max(0)[0]
+    print("max |err| vs float64 per channel: torch-CPU fp32 %s | CUDA-core fp32 %s | fp32tc %s" % (
+        ["%.2e" % v for v in e_cpu.tolist()], ["%.2e" % v for v in e_f32.tolist()], ["%.2e" % v for v in e_tc.tolist()]))
+    assert bool((e_tc <= 2.0 * torch.maximum(e_cpu, e_f32) + 1e-7).all())
 
 
 def test_fp32tc_large_weights_and_activations():
