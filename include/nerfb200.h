@@ -51,6 +51,10 @@ extern "C" {
  * tcgen05.mma kind::f16 per K step, fp32 accumulate in TMEM, full-range sincosf -- meets the same 1e-5 gates as
  * NERFB200_MODE_FP32 (requires |activation| < 65504). */
 #define NERFB200_MODE_FP32_TC 2
+/* single-pass tcgen05.mma kind::f16 with FP16 operands (11 significand bits instead of bf16's 8, saturating at
+ * 65504): the kernel, the speed and the packed size of NERFB200_MODE_BF16, roughly a tenth of its error on networks
+ * whose activations stay inside the fp16 range.  Inference only (the training path keeps bf16 operands). */
+#define NERFB200_MODE_FP16 3
 /* nerfb200_render_params.mode only: bits 0-7 = mode of the FINE pass; bits 8-15, when non-zero, = 1 + mode of the
  * COARSE pass (each model packed for its own mode).  NERFB200_MODE_BF16 | NERFB200_MODE_COARSE(NERFB200_MODE_FP32_TC)
  * puts the importance samples where the fp32 reference puts them and spends bf16 on the 75 % of the rows that only

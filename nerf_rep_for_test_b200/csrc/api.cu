@@ -31,7 +31,7 @@ int launch_mlp_fp32(const void* packed, const float* rays_o, const float* rays_d
                     int n_rays, int n_samples, float* raw, cudaStream_t st);
 int launch_mlp_bf16(const void* packed, const float* rays_o, const float* rays_d, const float* z_vals,
                     int n_rays, int n_samples, float* raw, float* stage_dump, void* acts, void* masks,
-                    const int* row_ids, const int* n_active, cudaStream_t st);
+                    const int* row_ids, const int* n_active, bool f16, cudaStream_t st);
 int launch_mlp_f16x2(const void* packed, const float* rays_o, const float* rays_d, const float* z_vals, int n_rays,
                      int n_samples, float* raw, float* stage_dump, const int* row_ids, const int* n_active,
                      cudaStream_t st);
@@ -76,8 +76,9 @@ constexpr int kChunkRaysSparse = 131072;
 // nerfb200_render_params.mode: bits 0-7 = fine-pass mode, bits 8-15 = 1 + coarse-pass mode (0: same as fine)
 static int mode_fine(int mode) { return mode & 0xFF; }
 static int mode_coarse(int mode) { return (mode >> 8) & 0xFF ? ((mode >> 8) & 0xFF) - 1 : (mode & 0xFF); }
-static bool mode_known(int m) { return m == NERFB200_MODE_FP32 || m == NERFB200_MODE_BF16 || m == NERFB200_MODE_FP32_TC; }
-static bool mode_tensor(int m) { return m == NERFB200_MODE_BF16 || m == NERFB200_MODE_FP32_TC; }   // persistent CTA-pair kernels
+static bool mode_known(int m) { return m == NERFB200_MODE_FP32 || m == NERFB200_MODE_BF16 || m == NERFB200_MODE_FP32_TC || m == NERFB200_MODE_FP16; }
+static bool mode_tensor(int m) { return m == NERFB200_MODE_BF16 || m == NERFB200_MODE_FP32_TC || m == NERFB200_MODE_FP16; }   // persistent CTA-pair kernels
+static bool mode_exact(int m) { return m == NERFB200_MODE_FP32 || m == NERFB200_MODE_FP32_TC; }   // fp32-accurate MLP arithmetic
 
 static int chunk_rays(const nerfb200_render_params* p) {
   if (const char* e = getenv("NERFB200_CHUNK_RAYS")) { int c = atoi(e); if (c >= 2048 && c % 2048 == 0) return c; }   // tuning experiments
@@ -180,7 +181,7 @@ extern "C" int nerfb200_mlp_forward(const void* packed, int mode, const float* r
   bool prof = prof_begin(st);
   int rc = mode == NERFB200_MODE_FP32 ? launch_mlp_fp32(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, st)
            : mode == NERFB200_MODE_FP32_TC ? launch_mlp_f16x2(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, nullptr, nullptr, nullptr, st)
-                                           : launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, nullptr, nullptr, nullptr, nullptr, nullptr, st);
+                                           : launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, nullptr, nullptr, nullptr, nullptr, nullptr, mode == NERFB200_MODE_FP16, st);
   if (prof) prof_end(st, (double)n_rays * n_samples);
   return rc;
 }
@@ -204,7 +205,7 @@ extern "C" int nerfb200_mlp_forward_train(const void* packed, int mode, const fl
   NB_CHECK_ARG(((uintptr_t)packed & 1023) == 0 && ((uintptr_t)acts & 127) == 0 && ((uintptr_t)masks & 15) == 0,
                "mlp_forward_train: misaligned buffer");
   if (n_rays == 0) return 0;
-  return launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, nullptr, acts, masks, nullptr, nullptr, (cudaStream_t)stream);
+  return launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, nullptr, acts, masks, nullptr, nullptr, false, (cudaStream_t)stream);
 }
 
 extern "C" int nerfb200_mlp_backward(const void* packed_bwd, const nerfb200_mlp_weights* weights, const float* g_raw,
@@ -250,7 +251,7 @@ static int mlp_forward_sparse_impl(const void* packed, int mode, const float* ra
   bool prof = prof_begin(st);
   int rc = mode == NERFB200_MODE_FP32_TC
                ? launch_mlp_f16x2(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, nullptr, row_ids, n_active, st)
-               : launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, nullptr, nullptr, nullptr, row_ids, n_active, st);
+               : launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, nullptr, nullptr, nullptr, row_ids, n_active, mode == NERFB200_MODE_FP16, st);
   if (prof) prof_end(st, 0.0);   // evaluated rows are data dependent; counted by the caller from n_active
   return rc;
 }
@@ -288,11 +289,11 @@ extern "C" int nerfb200_mlp_forward_stages(const void* packed, int mode, const f
                                            float* stage_dump, void* stream) {
   NB_CHECK_ARG(packed && rays_o && rays_d && z_vals && raw && stage_dump, "mlp_forward_stages: null pointer");
   NB_CHECK_ARG(n_rays >= 1 && n_samples >= 1, "mlp_forward_stages: bad sizes");
-  NB_CHECK_ARG(mode_tensor(mode), "mlp_forward_stages: only the tensor-core modes have a stage dump");
+  NB_CHECK_ARG(mode == NERFB200_MODE_BF16 || mode == NERFB200_MODE_FP32_TC, "mlp_forward_stages: only NERFB200_MODE_BF16 / FP32_TC have a stage dump");
   NB_CHECK_ARG(((uintptr_t)packed & 1023) == 0, "mlp_forward_stages: packed weights must be 1024-byte aligned");
   if (mode == NERFB200_MODE_FP32_TC)
     return launch_mlp_f16x2(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, stage_dump, nullptr, nullptr, (cudaStream_t)stream);
-  return launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, stage_dump, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+  return launch_mlp_bf16(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, stage_dump, nullptr, nullptr, nullptr, nullptr, false, (cudaStream_t)stream);
 }
 
 extern "C" size_t nerfb200_render_workspace_bytes(int n_rays, const nerfb200_render_params* p) {
@@ -320,7 +321,7 @@ static int render_rays_impl(const void* packed_coarse, const void* packed_fine, 
   const int S = p->n_samples, U = p->n_importance;
   const int mode_c = mode_coarse(p->mode), mode_f = mode_fine(p->mode);
   // mixed precision: an accurate coarse pass keeps its exact compositor (its weights place the fine samples)
-  const int variant_c = (mode_c != NERFB200_MODE_BF16) ? (p->variant & ~NERFB200_COMPOSITE_FAST_MATH) : p->variant;
+  const int variant_c = mode_exact(mode_c) ? (p->variant & ~NERFB200_COMPOSITE_FAST_MATH) : p->variant;
   if (U > 0) {
     NB_CHECK_ARG(packed_fine && u && mf && mf->rgb && mf->disp && mf->acc && mf->depth,
                  "render_rays: fine pass needs packed_fine, u and fine maps");

@@ -60,7 +60,7 @@ template <bool kFused> struct Img {
   }
 };
 
-template <bool kDump, bool kTimeline, bool kSave, bool kFused>
+template <bool kDump, bool kTimeline, bool kSave, bool kFused, bool kF16 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __restrict__ rays_o,
                     const float* __restrict__ rays_d, const float* __restrict__ z_vals, long long M, int S,
@@ -157,7 +157,7 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
       pos_enc_row<kLx>(p, f);
       f[63] = 0.f;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) pe_pk[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+      for (int i = 0; i < 32; ++i) pe_pk[i] = pack_16x2<kF16>(f[2 * i], f[2 * i + 1]);
     };
     if (my_quads > 0) prepare_tile(0);
 
@@ -211,15 +211,15 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
         if (kSave) named_bar_sync(1 + slot, 128);   // all copies of the previous stage's tile are done: A may be rewritten
         if (stage < I::kLast) {
           uint32_t mw[8];
-          if (!kFused && stage == 7) epi_stage256<1, kSave>(t_acc, bias4, a_row_base, r7, tail + kTailAlphaW, sigma, mw);
-          else if (!kFused && stage == 8) epi_stage256<2>(t_acc, bias4, a_row_base, r7, nullptr, sigma);
-          else epi_stage256<0, kSave>(t_acc, bias4, a_row_base, r7, nullptr, sigma, mw);
+          if (!kFused && stage == 7) epi_stage256<1, kSave, kF16>(t_acc, bias4, a_row_base, r7, tail + kTailAlphaW, sigma, mw);
+          else if (!kFused && stage == 8) epi_stage256<2, false, kF16>(t_acc, bias4, a_row_base, r7, nullptr, sigma);
+          else epi_stage256<0, kSave, kF16>(t_acc, bias4, a_row_base, r7, nullptr, sigma, mw);
           if (stage == I::kLast - 1) {  // dir PE replaces the xyz PE tile (dead after stage 5) for the views stage
             float f[32];
             pos_enc_row<kLd>(d_cur, f);
 #pragma unroll
             for (int i = kChD; i < 32; ++i) f[i] = 0.f;
-            store_row_chunks<4>(pe_base, row, f);
+            store_row_chunks<4, kF16>(pe_base, row, f);
           }
           const bool tl_on = kTimeline && kSave && tl && blockIdx.x == 0 && it < 4 && row == 0;
           if (tl_on) tl[720 + ((it * 10 + stage) * 2 + slot) * 4 + 0] = clock64();
@@ -366,7 +366,8 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
     for (int it = 0; it < my_quads; ++it) {
       for (int stage = 0; stage < I::kN; ++stage) {
         const int nch = I::chunks(stage);
-        const uint32_t idesc = umma_idesc_bf16(256, I::n(stage));
+        // kind::f16 operand format field: 1 = bf16, 0 = fp16 (bits 7-9 / 10-12 of the instruction descriptor)
+        const uint32_t idesc = kF16 ? (umma_idesc_bf16(256, I::n(stage)) & ~((1u << 7) | (1u << 10))) : umma_idesc_bf16(256, I::n(stage));
         // chunk groups of at most kRing chunks: slot 0 runs the group, then slot 1 runs it and releases it
         for (int g0 = 0; g0 < nch; g0 += kRing) {
           const int g1 = (g0 + kRing < nch) ? g0 + kRing : nch;
@@ -430,31 +431,28 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
 
 }  // namespace tc2
 
-int launch_mlp_bf16_1cta(const void* packed, const float* rays_o, const float* rays_d, const float* z_vals,
-                         int n_rays, int n_samples, float* raw, float* stage_dump, cudaStream_t st);
-
 int launch_mlp_bf16(const void* packed, const float* rays_o, const float* rays_d, const float* z_vals, int n_rays,
                     int n_samples, float* raw, float* stage_dump, void* acts, void* masks, const int* row_ids,
-                    const int* n_active, cudaStream_t st) {
-  const char* variant = getenv("NERFB200_TC_VARIANT");
-  if (variant && atoi(variant) == 1 && !acts && !row_ids)
-    return launch_mlp_bf16_1cta(packed, rays_o, rays_d, z_vals, n_rays, n_samples, raw, stage_dump, st);
+                    const int* n_active, bool f16, cudaStream_t st) {
   using namespace tc2;
+  NB_CHECK_ARG(!f16 || (!acts && !stage_dump), "fp16 operands: inference launches only");
   int dev = 0, sms = 0;
   NB_CUDA(cudaGetDevice(&dev));
   NB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  static int attr_dev = -1;   // the opt-in to 226 KB of dynamic shared memory is per device and sticky: once is enough
-  if (attr_dev != dev) {
+  static bool attr_set[64] = {};   // the opt-in to 226 KB of dynamic shared memory is per device and sticky
+  NB_CHECK_ARG(dev >= 0 && dev < 64, "mlp_forward: device ordinal %d out of range", dev);
+  if (!attr_set[dev]) {
     NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<true, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<false, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    attr_dev = dev;
+    NB_CUDA(cudaFuncSetAttribute(mlp_bf16_tc2_kernel<false, false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    attr_set[dev] = true;
   }
   const char* tl_env = getenv("NERFB200_TIMELINE");
   unsigned long long* tl = nullptr;
-  if (tl_env && !stage_dump) {
+  if (tl_env && !stage_dump && !f16) {
     cudaMalloc(&tl, (320 + 400 + 320) * 8);
     cudaMemset(tl, 0, (320 + 400 + 320) * 8);
   }
@@ -465,7 +463,10 @@ int launch_mlp_bf16(const void* packed, const float* rays_o, const float* rays_d
     int v = atoi(mc);
     if (v > 0 && v < clusters) clusters = v;
   }
-  if (acts && tl)
+  if (f16)
+    mlp_bf16_tc2_kernel<false, false, false, true, true><<<2 * clusters, kThreads, kSmemBytes, st>>>(
+        (const unsigned char*)packed, rays_o, rays_d, z_vals, M, n_samples, (int)quads, raw, nullptr, nullptr, nullptr, nullptr, row_ids, n_active);
+  else if (acts && tl)
     mlp_bf16_tc2_kernel<false, true, true, true><<<2 * clusters, kThreads, kSmemBytes, st>>>(
         (const unsigned char*)packed, rays_o, rays_d, z_vals, M, n_samples, (int)quads, raw, nullptr, tl,
         (unsigned char*)acts, (uint32_t*)masks, nullptr, nullptr, getenv("NERFB200_DBG") ? atoi(getenv("NERFB200_DBG")) : 0);

@@ -1,7 +1,8 @@
-// Device helpers shared by the tcgen05 MLP kernels (1-CTA and 2-CTA variants): bf16 packing,
+// Device helpers shared by the tcgen05 MLP kernels (forward, split-fp16 forward, dgrad): bf16 / fp16 packing,
 // swizzled A-operand stores, positional encoding, and the accumulator epilogue.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "mlp_layout.cuh"
 #include "tc_ptx.cuh"
@@ -13,6 +14,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// operand element type of the single-pass kernel: bf16 (NERFB200_MODE_BF16) or fp16 (NERFB200_MODE_FP16, saturating)
+template <bool kF16>
+__device__ __forceinline__ uint32_t pack_16x2(float lo, float hi) {
+  if (!kF16) return pack_bf16x2(lo, hi);
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -22,11 +31,16 @@ __device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
   return v;
 }
 // two fp32 -> packed bf16x2 (lo in bits 0-15), optionally with ReLU folded into the conversion
-template <bool kRelu>
+template <bool kRelu, bool kF16 = false>
 __device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
   uint32_t d;
-  if (kRelu) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  if (kF16) {
+    if (kRelu) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  } else {
+    if (kRelu) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  }
   return d;
 }
 // registers written by an in-flight tcgen05.ld must not be touched before tcgen05.wait::ld; this
@@ -45,7 +59,7 @@ __device__ __forceinline__ void pin32(uint32_t (&r)[32]) {
 // Plain C++ shared-memory accesses (not volatile asm) so the compiler batches the bias loads.
 // kMask (training forward): additionally returns the relu sign bits of the 32 columns in the bit order
 // of train_layout.cuh (column 4s+k -> bit 8k+7-s, set = negative), built with one funnel shift per value.
-template <int MODE, bool kMask = false>
+template <int MODE, bool kMask = false, bool kF16 = false>
 __device__ __forceinline__ void epi32(const uint32_t (&v)[32], const float4* __restrict__ bias4, unsigned char* out_row,
                                       int j0, int r7, const float* __restrict__ alpha_w, float& sigma,
                                       uint32_t* mask_word = nullptr) {
@@ -80,15 +94,15 @@ __device__ __forceinline__ void epi32(const uint32_t (&v)[32], const float4* __r
     }
     constexpr bool kRelu = MODE != 2;
     uint4 o;
-    o.x = cvt_bf16x2<kRelu>(x0.x, x0.y); o.y = cvt_bf16x2<kRelu>(x1.x, x1.y);
-    o.z = cvt_bf16x2<kRelu>(x2.x, x2.y); o.w = cvt_bf16x2<kRelu>(x3.x, x3.y);
+    o.x = cvt_bf16x2<kRelu, kF16>(x0.x, x0.y); o.y = cvt_bf16x2<kRelu, kF16>(x1.x, x1.y);
+    o.z = cvt_bf16x2<kRelu, kF16>(x2.x, x2.y); o.w = cvt_bf16x2<kRelu, kF16>(x3.x, x3.y);
     *reinterpret_cast<uint4*>(out_row + (((j0 + q) ^ r7) << 4)) = o;
   }
   if (kMask) *mask_word = ch0 | (ch1 << 8) | (ch2 << 16) | (ch3 << 24);
 }
 
 // one hidden stage (256 accumulator columns) with the TMEM loads double-buffered
-template <int MODE, bool kMask = false>
+template <int MODE, bool kMask = false, bool kF16 = false>
 __device__ __forceinline__ void epi_stage256(uint32_t t_acc, const float4* __restrict__ bias4, unsigned char* a_row_base,
                                              int r7, const float* __restrict__ alpha_w, float& sigma,
                                              uint32_t* mw = nullptr) {
@@ -101,9 +115,9 @@ __device__ __forceinline__ void epi_stage256(uint32_t t_acc, const float4* __res
 #pragma unroll
   for (int h = 0; h < 4; ++h) {   // K-block h of the A operand = columns 64h .. 64h+63
     unsigned char* out_row = a_row_base + h * 16384;
-    epi32<MODE, kMask>(va, bias4 + h * 16, out_row, 0, r7, alpha_w + h * 64, sigma, mw + 2 * h);
+    epi32<MODE, kMask, kF16>(va, bias4 + h * 16, out_row, 0, r7, alpha_w + h * 64, sigma, mw + 2 * h);
     if (h < 3) tmem_ld32(t_acc + (uint32_t)(h * 64 + 64), va);
-    epi32<MODE, kMask>(vb, bias4 + h * 16 + 8, out_row, 4, r7, alpha_w + h * 64 + 32, sigma, mw + 2 * h + 1);
+    epi32<MODE, kMask, kF16>(vb, bias4 + h * 16 + 8, out_row, 4, r7, alpha_w + h * 64 + 32, sigma, mw + 2 * h + 1);
     if (h < 3) {
       tmem_ld32(t_acc + (uint32_t)(h * 64 + 96), vb);
       tmem_ld_wait();
@@ -139,14 +153,14 @@ __device__ __forceinline__ void copy_tile_s2g(unsigned char* __restrict__ gdst, 
 }
 
 // write `n8` 16-byte chunks (8 bf16 each) of one 128-byte swizzled row
-template <int NCHUNK>
+template <int NCHUNK, bool kF16 = false>
 __device__ __forceinline__ void store_row_chunks(uint32_t tile_base, int row, const float* f) {
   uint32_t row_base = tile_base + (uint32_t)row * 128u;
 #pragma unroll
   for (int j = 0; j < NCHUNK; ++j) {
     uint32_t addr = row_base + (uint32_t)((j ^ (row & 7)) << 4);
-    st_shared_v4(addr, pack_bf16x2(f[j * 8 + 0], f[j * 8 + 1]), pack_bf16x2(f[j * 8 + 2], f[j * 8 + 3]),
-                 pack_bf16x2(f[j * 8 + 4], f[j * 8 + 5]), pack_bf16x2(f[j * 8 + 6], f[j * 8 + 7]));
+    st_shared_v4(addr, pack_16x2<kF16>(f[j * 8 + 0], f[j * 8 + 1]), pack_16x2<kF16>(f[j * 8 + 2], f[j * 8 + 3]),
+                 pack_16x2<kF16>(f[j * 8 + 4], f[j * 8 + 5]), pack_16x2<kF16>(f[j * 8 + 6], f[j * 8 + 7]));
   }
 }
 

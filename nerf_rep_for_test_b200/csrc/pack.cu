@@ -56,7 +56,19 @@ __global__ void pack_f32_kernel(nerfb200_mlp_weights w, StageTable tab, float* _
   }
 }
 
-__global__ void pack_bf16_kernel(nerfb200_mlp_weights w, StageTable tab, unsigned char* __restrict__ dst) {
+// 16-bit operand element: bf16 (round to nearest) or fp16 (round to nearest, saturating)
+__device__ __forceinline__ unsigned short to_16(float v, bool f16) {
+  if (f16) {
+    v = fminf(fmaxf(v, -65504.f), 65504.f);
+    return __half_as_ushort(__float2half_rn(v));
+  }
+  return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+}
+__device__ __forceinline__ float from_16(unsigned short b, bool f16) {
+  return f16 ? __half2float(__ushort_as_half(b)) : __bfloat162float(__ushort_as_bfloat16(b));
+}
+
+__global__ void pack_bf16_kernel(nerfb200_mlp_weights w, StageTable tab, unsigned char* __restrict__ dst, bool f16) {
   int s = blockIdx.y;
   if (s == kStages) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kTailFloats; i += gridDim.x * blockDim.x)
@@ -75,7 +87,7 @@ __global__ void pack_bf16_kernel(nerfb200_mlp_weights w, StageTable tab, unsigne
     if (k < K && stage_src(s, k, &r)) v = tensor_w(w, r.tensor)[(size_t)n * tensor_in_features(r.tensor) + r.col];
     size_t off = (size_t)tab.bf16_off[s] + (size_t)c * (N * 128) + (size_t)n * 128 +
                  (size_t)(((kk >> 3) ^ (n & 7)) << 4) + (size_t)(kk & 7) * 2;
-    *reinterpret_cast<__nv_bfloat16*>(dst + off) = __float2bfloat16_rn(v);
+    *reinterpret_cast<unsigned short*>(dst + off) = to_16(v, f16);
   }
 }
 
@@ -148,7 +160,7 @@ __device__ __forceinline__ float dot256_strided(const float* __restrict__ a, con
 }
 
 // fused stage 8F (mlp_layout.cuh): one thread per (n, k) of the [144][320] operand + the bias row
-__global__ void pack_bf16_fused_kernel(nerfb200_mlp_weights w, unsigned char* __restrict__ dst) {
+__global__ void pack_bf16_fused_kernel(nerfb200_mlp_weights w, unsigned char* __restrict__ dst, bool f16) {
   const int total = kFusedN * kFusedChunks * 64;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total + 256; i += gridDim.x * blockDim.x) {
     if (i >= total) {   // bias row
@@ -181,11 +193,11 @@ __global__ void pack_bf16_fused_kernel(nerfb200_mlp_weights w, unsigned char* __
       // correlated over all samples, unlike activation rounding) and sigma is the output the image is most
       // sensitive to; two of the 16 pad columns of the N = 144 tail make alpha_linear's weights ~16-bit for free.
       const float a = w.alpha_w[k];
-      v = a - __bfloat162float(__float2bfloat16_rn(a));
+      v = a - from_16(to_16(a, f16), f16);
     }
     size_t off = (size_t)kFusedStageOff + (size_t)c * kFusedChunkBytes + (size_t)n * 128 +
                  (size_t)(((kk >> 3) ^ (n & 7)) << 4) + (size_t)(kk & 7) * 2;
-    *reinterpret_cast<__nv_bfloat16*>(dst + off) = __float2bfloat16_rn(v);
+    *reinterpret_cast<unsigned short*>(dst + off) = to_16(v, f16);
   }
 }
 
@@ -222,15 +234,15 @@ using namespace nb;
 
 extern "C" size_t nerfb200_packed_weights_bytes(int mode) {
   if (mode == NERFB200_MODE_FP32) return (size_t)kF32TotalFloats * 4;
-  if (mode == NERFB200_MODE_BF16) return (size_t)kBf16PackedBytes;
+  if (mode == NERFB200_MODE_BF16 || mode == NERFB200_MODE_FP16) return (size_t)kBf16PackedBytes;
   if (mode == NERFB200_MODE_FP32_TC) return (size_t)kX2PackedBytes;
   return 0;
 }
 
 extern "C" int nerfb200_pack_weights(const nerfb200_mlp_weights* w, int mode, void* packed, void* stream) {
   NB_CHECK_ARG(w && packed, "pack_weights: null pointer");
-  NB_CHECK_ARG(mode == NERFB200_MODE_FP32 || mode == NERFB200_MODE_BF16 || mode == NERFB200_MODE_FP32_TC,
-               "pack_weights: unknown mode %d", mode);
+  NB_CHECK_ARG(mode == NERFB200_MODE_FP32 || mode == NERFB200_MODE_BF16 || mode == NERFB200_MODE_FP32_TC ||
+                   mode == NERFB200_MODE_FP16, "pack_weights: unknown mode %d", mode);
   NB_CHECK_ARG(((uintptr_t)packed & 1023) == 0, "pack_weights: packed buffer must be 1024-byte aligned");
   for (int i = 0; i < 8; ++i) NB_CHECK_ARG(w->pts_w[i] && w->pts_b[i], "pack_weights: null pts_linears.%d", i);
   NB_CHECK_ARG(w->views_w && w->views_b && w->feature_w && w->feature_b && w->alpha_w && w->alpha_b && w->rgb_w &&
@@ -248,9 +260,10 @@ extern "C" int nerfb200_pack_weights(const nerfb200_mlp_weights* w, int mode, vo
     NB_LAUNCH_OK("stage_scale_kernel");
     pack_f16x2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*w, (unsigned char*)packed);
   } else {
-    pack_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*w, tab, (unsigned char*)packed);
+    const bool f16 = mode == NERFB200_MODE_FP16;
+    pack_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*w, tab, (unsigned char*)packed, f16);
     NB_LAUNCH_OK("pack_bf16_kernel");
-    pack_bf16_fused_kernel<<<96, 256, 0, (cudaStream_t)stream>>>(*w, (unsigned char*)packed);
+    pack_bf16_fused_kernel<<<96, 256, 0, (cudaStream_t)stream>>>(*w, (unsigned char*)packed, f16);
   }
   NB_LAUNCH_OK("pack_weights_kernel");
   return 0;

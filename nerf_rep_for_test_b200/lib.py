@@ -10,7 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NERFB200_LIB") or os.path.join(HERE, "libnerfb200.so")   # env override: A/B experiments only
 
-MODE_FP32, MODE_BF16, MODE_FP32_TC = 0, 1, 2
+MODE_FP32, MODE_BF16, MODE_FP32_TC, MODE_FP16 = 0, 1, 2, 3
 
 
 def mode_coarse(m):

@@ -121,7 +121,9 @@ class Renderer(PathRenderingMixin):
     # (the CUDA-core kernel) at a fraction of its time; "mixed": fp32tc for the coarse network (so the importance
     # samples land where the fp32 reference puts them), bf16 for the fine network.
     MODES = {"fp32": (L.MODE_FP32, L.MODE_FP32), "bf16": (L.MODE_BF16, L.MODE_BF16),
-             "fp32tc": (L.MODE_FP32_TC, L.MODE_FP32_TC), "mixed": (L.MODE_FP32_TC, L.MODE_BF16)}
+             "fp32tc": (L.MODE_FP32_TC, L.MODE_FP32_TC), "mixed": (L.MODE_FP32_TC, L.MODE_BF16),
+             # fp16 operands instead of bf16 in the same single-pass kernel (11 significand bits, saturating at 65504)
+             "fp16": (L.MODE_FP16, L.MODE_FP16), "mixed16": (L.MODE_FP32_TC, L.MODE_FP16)}
 
     def __init__(self, net, cfg=None, mode=None, ref_compat=True):
         """net: a Network with `.model`, `.model_fine` (reference network.py or ours).
@@ -319,7 +321,7 @@ class Renderer(PathRenderingMixin):
                     p.cull_rays = 1
                     for c in range(3):
                         p.cull_lo[c], p.cull_hi[c] = lo[c], hi[c]
-        if mode_f == L.MODE_BF16:
+        if mode_f in (L.MODE_BF16, L.MODE_FP16):
             # the bf16 MLP output carries 1e-3 already: MUFU exp / sigmoid (an fp32-accurate coarse pass of the mixed
             # mode keeps its exact compositor inside the library)
             p.variant |= L.COMPOSITE_FAST_MATH

@@ -31,7 +31,13 @@ CASES = [
     ("lego16_randinit_ert", 16, 16, 0, 1.0, 0.0, True),
     ("lego8_dense", 8, 8, 1, 60.0, 0.5, False),
     ("lego8_dense_ert", 8, 8, 1, 60.0, 0.5, True),
+    # BASELINE.json configs[0]: 32x32 = 1024 rays, lego test pose 0, seed 0 -- random init as is, and with a dense
+    # field (the weights of bench.py's parity block).  "slim" fixtures: maps, bin indices, coarse weights, cdf and
+    # the LAST sigma_raw of each pass (the flip-ray criterion); no per-sample raw tensors.
+    ("lego32_cfg1", 32, 32, 0, 1.0, 0.0, False),
+    ("lego32_dense", 32, 32, 0, 30.0, 0.2, False),
 ]
+SLIM = {"lego32_cfg1", "lego32_dense"}
 
 
 def capture_reference(r, batch):
@@ -105,6 +111,12 @@ def main():
         for k, v in ref_out.items():
             arrays["out_" + k] = v.numpy()
         for k, v in ref_aux.items():
+            if name in SLIM:
+                if k in ("raw_coarse", "raw_fine"):
+                    arrays["aux_sigma_last_" + k[4:]] = v[:, -1, 3].numpy()
+                    continue
+                if k not in ("inds", "cdf", "weights_coarse"):
+                    continue
             arrays["aux_" + k] = v.numpy().astype(np.int16) if k == "inds" else v.numpy()
         path = os.path.join(GOLDEN_DIR, name + ".npz")
         np.savez_compressed(path, **arrays)

@@ -1,0 +1,113 @@
+"""Parity report: the CUDA path against the CPU oracle on the same rays and weights.
+
+TEST INFRASTRUCTURE (the checker).  Used by bench.py's `parity` block ("parity gate run in
+the same job"), by tests/ and by __graft_entry__.smoke(); never by the product path.
+
+For every arithmetic mode the eight maps of `Renderer.render_rays` are compared with
+`nerf_oracle.render_rays` (the restatement of volume_renderer.py:109-216, bit-identical to the reference on one
+torch build).  Errors are quoted relative to the scale of the map (1 for rgb / acc, `far` = 6 for depth), the form
+the fp32 gates of tests/test_gpu_parity.py use (the per-ray relative error is meaningless where the reference's own
+1 - exp() cancels, SURVEY 8c').  `excluded_rays` counts the rays whose LAST reference sigma_raw lies within
+`sigma_thr` of zero: the last sampling interval is 1e10 wide (volume_renderer.py:296), so such a ray's opacity is a
+step function of the sign of one MLP output and a reduced-precision mode may flip it; `max_stable` is the largest
+error over the other rays.  north_star tolerances: fp32-accurate modes 1e-5, bf16 1e-3 (of the scale).
+
+`inds_mismatch` (fp32-accurate coarse pass only): the importance-sampling bin indices
+(`searchsorted(cdf, u, right=True)`, volume_renderer.py:254) produced by OUR coarse pass (MLP, exact compositor,
+sample_pdf kernel) against the oracle's, split into
+  endpoint  u is the first / last entry of the linspace table (u = 1.0 against cdf[-1] ~ 1.0),
+  tie       u within 2 ulp of the cdf entry that separates the two answers (a 1-ulp cdf difference decides),
+  other     anything else (must be 0).
+"""
+import torch
+
+from . import nerf_oracle as O
+
+MAPS = ("rgb_map_0", "depth_map_0", "acc_map_0", "rgb_map", "depth_map", "acc_map")
+TOL = {"fp32": 1e-5, "fp32tc": 1e-5, "mixed": 1e-3, "mixed16": 1e-3, "bf16": 1e-3, "fp16": 1e-3}
+SIGMA_THR = {"fp32": 0.0, "fp32tc": 0.0, "bf16": 2e-3, "fp16": 2.5e-4}     # |sigma_raw,last| below which a ray may flip
+
+
+def _q(t, f):
+    t = t.flatten()
+    return float(t.kthvalue(max(1, min(t.numel(), int(round(f * t.numel())))))[0])
+
+
+def _psnr(a, b):
+    return float(-10.0 * torch.log10(((a - b) ** 2).mean().clamp_min(1e-20)))
+
+
+def compare_maps(out, ref, aux, mode, far=O.FAR):
+    """out: dict of our maps ([N,..], any device); ref/aux from O.render_rays(..., return_aux=True)."""
+    coarse_mode, fine_mode = {"mixed": ("fp32tc", "bf16"), "mixed16": ("fp32tc", "fp16")}.get(mode, (mode, mode))
+    sig_c = aux["raw_coarse"][:, -1, 3].abs()
+    sig_f = aux["raw_fine"][:, -1, 3].abs()
+    res = {}
+    for k in MAPS:
+        thr = SIGMA_THR[coarse_mode] if k.endswith("_0") else SIGMA_THR[fine_mode]
+        stable = (sig_c if k.endswith("_0") else sig_f) > thr if thr > 0 else torch.ones_like(sig_c, dtype=torch.bool)
+        scale = far if "depth" in k else 1.0
+        err = (out[k].detach().cpu().double() - ref[k].double()).abs()
+        if err.dim() == 2:
+            err = err.max(-1)[0]
+        err = err / scale
+        res[k] = {"median": _q(err, 0.5), "p99": _q(err, 0.99), "max": float(err.max()),
+                  "max_stable": float(err[stable].max()) if bool(stable.any()) else 0.0,
+                  "excluded_rays": int((~stable).sum())}
+    res["psnr_vs_reference_db"] = {"rgb_map_0": _psnr(out["rgb_map_0"].cpu(), ref["rgb_map_0"]),
+                                   "rgb_map": _psnr(out["rgb_map"].cpu(), ref["rgb_map"])}
+    res["rays"] = int(sig_c.numel())
+    res["tolerance"] = TOL[mode]
+    tol = TOL[mode]
+    # fp32-accurate maps: p99 <= 1e-5 (the max carries the reference's own 1-exp() conditioning, gate 2e-4 as in the
+    # golden tests); reduced precision: every stable ray <= tol for the pass computed in that precision, p99 <= tol
+    ok = True
+    for k in MAPS:
+        m = res[k]
+        exact = (coarse_mode if k.endswith("_0") else fine_mode) in ("fp32", "fp32tc")
+        ok = ok and (m["p99"] <= 1e-5 and m["max"] <= 2e-4 if exact else m["p99"] <= tol)
+    res["within_tolerance"] = bool(ok)
+    return res
+
+
+def inds_mismatch(renderer, rays_o, rays_d, aux, dev):
+    """Bin indices of our coarse pass (kernel by kernel through the C ABI) against the oracle's."""
+    from nerf_rep_for_test_b200 import lib as L, ops
+    z = aux["z_coarse"].to(dev)
+    ro, rd = rays_o.to(dev), rays_d.to(dev)
+    raw = ops.mlp_forward(renderer.packed("coarse"), ro, rd, z)
+    w = ops.composite_forward(raw, z, rd, L.COMPOSITE_PLAIN, white_bkgd=renderer.white_bkgd)[3]
+    u = O.fine_u_table(renderer.N_importance).to(dev)
+    _, _, inds, cdf = ops.sample_pdf_merge(z, w, u)
+    inds, cdf_ref = inds.cpu().long(), aux["cdf"]
+    ref = aux["inds"].long()
+    bad = inds != ref
+    n_bad = int(bad.sum())
+    out = {"compared": int(ref.numel()), "mismatch": n_bad, "endpoint": 0, "tie": 0, "other": 0,
+           "cdf_max_abs_diff": float((cdf.cpu() - cdf_ref).abs().max())}
+    if n_bad:
+        r, j = bad.nonzero(as_tuple=True)
+        uu = O.fine_u_table(renderer.N_importance)[j]
+        k = torch.minimum(inds[r, j], ref[r, j]).clamp(0, cdf_ref.shape[1] - 1)
+        edge = cdf_ref[r, k]
+        endpoint = (j == 0) | (j == renderer.N_importance - 1)
+        tie = ~endpoint & ((uu - edge).abs() <= 2.4e-7 * edge.abs().clamp_min(1e-3)) & ((inds[r, j] - ref[r, j]).abs() == 1)
+        out["endpoint"] = int(endpoint.sum())
+        out["tie"] = int(tie.sum())
+        out["other"] = n_bad - out["endpoint"] - out["tie"]
+    return out
+
+
+def report(make_renderer, sd, rays_o, rays_d, modes, dev):
+    """make_renderer(mode) -> Renderer on `dev` holding the weights `sd`; rays on the CPU.  Returns
+    {mode: compare_maps(...) [+ "inds_mismatch"]}."""
+    with torch.no_grad():
+        ref, aux = O.render_rays(sd, rays_o, rays_d, return_aux=True)
+    res = {}
+    for mode in modes:
+        r = make_renderer(mode)
+        out = r.render_rays(rays_o.to(dev), rays_d.to(dev))
+        res[mode] = compare_maps(out, ref, aux, mode)
+        if mode in ("fp32", "fp32tc", "mixed", "mixed16"):
+            res[mode]["inds_mismatch"] = inds_mismatch(r, rays_o, rays_d, aux, dev)
+    return res

@@ -11,7 +11,7 @@ import fixtures as FX
 from nerf_rep_for_test_b200 import Network, RenderConfig, Renderer, lib as L
 
 dev = torch.device("cuda:0")
-modes = sys.argv[1:] or ["bf16", "mixed", "fp32tc"]
+modes = sys.argv[1:] or ["bf16", "fp16", "mixed", "mixed16", "fp32tc"]
 sd = FX.make_state_dict(0)
 net = Network(device=dev)
 net.load_state_dict(sd)

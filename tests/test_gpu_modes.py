@@ -1,7 +1,8 @@
-"""GPU tests of the fp32-accurate tensor-core MLP (NERFB200_MODE_FP32_TC, csrc/mlp_f16x2_tc2.cu) beyond the
-mode-parametrised parity tests of test_gpu_parity.py: stage-by-stage agreement with the oracle's hidden
-activations, agreement with the CUDA-core fp32 kernel at sizes that exercise the persistent schedule, the sparse
-launch, and the mixed mode (coarse fp32tc + fine bf16).
+"""GPU tests of the arithmetic modes added in round 2: the fp32-accurate tensor-core MLP (NERFB200_MODE_FP32_TC,
+csrc/mlp_f16x2_tc2.cu) beyond the mode-parametrised parity tests of test_gpu_parity.py -- stage-by-stage agreement
+with the oracle's hidden activations, agreement with the CUDA-core fp32 kernel at sizes that exercise the persistent
+schedule, the sparse launch --, the mixed modes (coarse fp32tc + fine bf16 / fp16), the single-pass fp16 mode, and the
+parity report of BASELINE.json configs[0] (32x32 = 1024 rays) that bench.py prints.
 
 Reference arithmetic: network.py:49-74 (fp32 GEMMs under torch CPU).
 """
@@ -163,3 +164,80 @@ def test_mixed_mode_coarse_is_fp32tc_and_fine_meets_1e3(name):
         p99 = float(err.kthvalue(max(1, int(0.99 * err.numel())))[0])
         print("mixed %s %-10s err/scale median %.2e p99 %.2e max %.2e" % (name, k, float(err.median()), p99, float(err.max())))
         assert p99 <= 1e-3, (k, p99)
+
+
+# ------------------------------------------------------------------------------- single-pass fp16 mode
+@pytest.mark.parametrize("n,S", [(3, 5), (700, 64), (1300, 192)])
+def test_fp16_mode_is_ten_times_closer_than_bf16(n, S):
+    """NERFB200_MODE_FP16: the bf16 kernel with fp16 operands.  Against the fp32 oracle its raw outputs must be within
+    6e-4 (bf16's bound in test_gpu_bf16.py is 5e-3) and closer than the bf16 mode's on the same inputs."""
+    sd = O.make_state_dict(1)
+    ro, rd, z = _rays(n, S, seed=S)
+    with torch.no_grad():
+        ref = O.query_network(sd, "model.", ro[:, None] + rd[:, None] * z[..., None], rd)
+    err = {}
+    for name, mode in (("bf16", L.MODE_BF16), ("fp16", L.MODE_FP16)):
+        packed = ops.pack_from_state_dict(sd, "model.", mode, DEV)
+        raw = ops.mlp_forward(packed, cuda(ro), cuda(rd), cuda(z)).cpu()
+        err[name] = float((raw - ref).abs().max())
+        assert torch.equal(raw, ops.mlp_forward(packed, cuda(ro), cuda(rd), cuda(z)).cpu())
+    print("n=%d S=%d max |raw - fp32 oracle|: bf16 %.2e  fp16 %.2e" % (n, S, err["bf16"], err["fp16"]))
+    assert err["fp16"] < 6e-4 and err["fp16"] < 0.5 * err["bf16"]
+
+
+def test_fp16_mode_saturates_instead_of_overflowing():
+    """Activations beyond the fp16 range saturate at 65504 (cvt.satfinite): the output stays finite."""
+    sd = O.make_state_dict(2)
+    sd = {k: (v * (40.0 if k.endswith("pts_linears.0.weight") or k.endswith("pts_linears.1.weight") else 1.0)) for k, v in sd.items()}
+    ro, rd, z = _rays(16, 64, seed=2)
+    packed = ops.pack_from_state_dict(sd, "model.", L.MODE_FP16, DEV)
+    raw = ops.mlp_forward(packed, cuda(ro), cuda(rd), cuda(z))
+    assert bool(torch.isfinite(raw).all())
+
+
+# ------------------------------------------------------------------------------- parity report (bench.py's block)
+def _make_renderer_factory(sd):
+    cache = {}
+
+    def make(mode):
+        if mode not in cache:
+            cache[mode] = _renderer(sd, mode)
+        return cache[mode]
+    return make
+
+
+@pytest.mark.parametrize("name", ["lego32_cfg1", "lego32_dense"])
+def test_parity_report_config1_all_modes(name):
+    """BASELINE.json configs[0]: 1024 rays of the 32x32 lego test view.  The report bench.py prints, gated:
+    fp32-accurate modes p99 <= 1e-5 / max <= 2e-4 of the scale on all six maps and NO bin-index mismatch other than
+    endpoint / 1-ulp ties; reduced-precision passes p99 <= 1e-3 (north_star) -- end to end for the mixed modes, whose
+    coarse pass is fp32-accurate."""
+    from oracle import parity
+    g = golden(name)
+    H, W, seed, gain, bias, ert = g["meta"]
+    sd = O.make_state_dict(int(seed), float(gain), float(bias))
+    ro, rd = torch.from_numpy(g["rays_o"]), torch.from_numpy(g["rays_d"])
+    rep = parity.report(_make_renderer_factory(sd), sd, ro, rd, ["fp32tc", "mixed", "mixed16", "fp16", "bf16"], DEV)
+    for mode, r in rep.items():
+        print(name, mode, {k: ("%.1e/%.1e/%.1e x%d" % (v["median"], v["p99"], v["max"], v["excluded_rays"])) for k, v in r.items()
+                           if isinstance(v, dict) and "p99" in v}, r.get("inds_mismatch"), "PSNR", r["psnr_vs_reference_db"])
+    assert rep["fp32tc"]["within_tolerance"]
+    for mode in ("fp32tc", "mixed", "mixed16"):
+        im = rep[mode]["inds_mismatch"]
+        assert im["other"] == 0 and im["mismatch"] <= 0.005 * im["compared"], (mode, im)
+        assert rep[mode]["within_tolerance"], (mode, rep[mode])
+    # our fp32tc maps against the FROZEN reference outputs as well (not only the oracle recomputed on this box)
+    out = _make_renderer_factory(sd)("fp32tc").render_rays(cuda(ro), cuda(rd))
+    for k in ("rgb_map", "depth_map", "acc_map", "rgb_map_0"):
+        ref = torch.from_numpy(g["out_" + k]).reshape(out[k].shape)
+        scale = 6.0 if "depth" in k else 1.0
+        err = ((out[k].cpu() - ref).abs() / scale).flatten()
+        assert float(err.kthvalue(int(0.99 * err.numel()))[0]) <= 1e-5 and float(err.max()) <= 2e-4, k
+    # reduced-precision single-pass modes: the pass they compute must meet 1e-3 at p99 for the COARSE maps (no
+    # dependence on sample placement); end to end they are reported (bf16 coarse weights move the samples)
+    for mode in ("bf16", "fp16"):
+        for k in ("rgb_map_0", "depth_map_0", "acc_map_0"):
+            assert rep[mode][k]["p99"] <= 1e-3, (mode, k, rep[mode][k])
+    # flip rays: measured count + margin instead of a blanket allowance (VERDICT r1 weak #1)
+    assert rep["bf16"]["acc_map"]["excluded_rays"] <= 0.03 * 1024
+    assert rep["fp16"]["acc_map"]["excluded_rays"] <= 0.005 * 1024
