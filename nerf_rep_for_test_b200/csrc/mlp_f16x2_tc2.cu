@@ -9,8 +9,10 @@
 // Weights are pre-scaled per stage by a power of two so their residuals stay normal fp16 numbers (mlp_layout.cuh);
 // activations are not scaled: |a| < 65504 is required (saturating conversion beyond), and below 2^-3 the residual
 // becomes subnormal, i.e. the absolute error per activation is bounded by 2^-25 -- fp32's own rounding at |a| ~ 0.5.
-// Measured against a float64 evaluation of the same network this is as accurate as the fp32 CPU reference itself
-// (DESIGN.md section 4.2); it costs 3 MMAs where single-pass bf16 costs one, and half of what 3xTF32 or six-term
+// Measured against a float64 evaluation of the same network (tests/test_gpu_modes.py) the outputs are 2x (rgb) to 6x
+// (sigma_raw) as far away as true fp32 arithmetic is (5e-6 against 8e-7 on a 256-term dot product of magnitude ~10): the tensor core aligns and truncates its fp32
+// accumulator at each of the 48 MMAs of a 256-deep product, an FFMA chain rounds to nearest.  That is 50x inside the
+// 1e-5 tolerance of the mode.  It costs 3 MMAs where single-pass bf16 costs one, and half of what 3xTF32 or six-term
 // bf16 splitting would cost.  Heads (alpha_linear, rgb_linear), bias adds, the PE (full-range sincosf per octave,
 // no recurrence) and o + d*z are plain fp32 on CUDA cores.  Ten UNFUSED stages, as the reference evaluates them.
 //
@@ -108,6 +110,9 @@ __device__ __forceinline__ void epi32x(const uint32_t (&v)[32], const float4* __
     for (int i = 0; i < 8; ++i) aw[i] = __ldg(reinterpret_cast<const float4*>(alpha_w) + i);
   }
   const float2 inv2 = make_float2(inv, inv);
+  // alpha_linear: four independent partial sums per 32 columns, combined pairwise (a single 128-term FMA chain per
+  // thread measured 5e-6 away from a float64 evaluation where blocked fp32 sums -- torch CPU, mlp_fp32_kernel -- are 8e-7)
+  float sg0 = 0.f, sg1 = 0.f, sg2 = 0.f, sg3 = 0.f;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const float4 b0 = b[2 * q], b1 = b[2 * q + 1];
@@ -121,10 +126,10 @@ __device__ __forceinline__ void epi32x(const uint32_t (&v)[32], const float4* __
     }
     if (MODE == 1) {
       const float4 a0 = aw[2 * q], a1 = aw[2 * q + 1];
-      sigma = fmaf(x0.x, a0.x, sigma); sigma = fmaf(x0.y, a0.y, sigma);
-      sigma = fmaf(x1.x, a0.z, sigma); sigma = fmaf(x1.y, a0.w, sigma);
-      sigma = fmaf(x2.x, a1.x, sigma); sigma = fmaf(x2.y, a1.y, sigma);
-      sigma = fmaf(x3.x, a1.z, sigma); sigma = fmaf(x3.y, a1.w, sigma);
+      sg0 = fmaf(x0.x, a0.x, sg0); sg0 = fmaf(x0.y, a0.y, sg0);
+      sg1 = fmaf(x1.x, a0.z, sg1); sg1 = fmaf(x1.y, a0.w, sg1);
+      sg2 = fmaf(x2.x, a1.x, sg2); sg2 = fmaf(x2.y, a1.y, sg2);
+      sg3 = fmaf(x3.x, a1.z, sg3); sg3 = fmaf(x3.y, a1.w, sg3);
     }
     uint4 hi, lo;
     split_f16x2(x0.x, x0.y, hi.x, lo.x);
@@ -135,6 +140,7 @@ __device__ __forceinline__ void epi32x(const uint32_t (&v)[32], const float4* __
     *reinterpret_cast<uint4*>(hi_row + off) = hi;
     *reinterpret_cast<uint4*>(lo_row + off) = lo;
   }
+  if (MODE == 1) sigma += (sg0 + sg1) + (sg2 + sg3);
 }
 
 // this thread's 128 accumulator columns of a 256-wide stage = K-blocks 0 and 1 behind hi_row / lo_row; TMEM loads

@@ -342,20 +342,29 @@ class Renderer(PathRenderingMixin):
 
     # ------------------------------------------------------------------ public API
     @torch.no_grad()
-    def render_rays(self, rays_o, rays_d):
-        """rays_o, rays_d: [N,3] fp32 CUDA.  Returns the reference's dict keys with leading [N]."""
+    def render_rays(self, rays_o, rays_d, out=None):
+        """rays_o, rays_d: [N,3] fp32 CUDA.  Returns the reference's dict keys with leading [N].  out: optional dict of
+        preallocated contiguous fp32 CUDA tensors ([N,3] for rgb maps, [N] otherwise) that receive the maps."""
         rays_o = rays_o.to(self.device, torch.float32).contiguous()
         rays_d = rays_d.to(self.device, torch.float32).contiguous()
         n = rays_o.shape[0]
         training = bool(getattr(self.net, "training", False))
         p = self._params(training, n)
-        out = {"rgb_map_0": torch.empty((n, 3), device=self.device), "disp_map_0": torch.empty(n, device=self.device),
-               "acc_map_0": torch.empty(n, device=self.device), "depth_map_0": torch.empty(n, device=self.device)}
+        keys = ("rgb_map_0", "disp_map_0", "acc_map_0", "depth_map_0") + (
+            ("rgb_map", "disp_map", "acc_map", "depth_map") if self.N_importance > 0 else ())
+        if out is not None:
+            for k in keys:
+                t = out[k]
+                want = (n, 3) if k.startswith("rgb") else (n,)
+                if (not t.is_cuda or t.dtype != torch.float32 or tuple(t.shape) != want or not t.is_contiguous()
+                        or t.device != self.device):
+                    raise L.NerfB200Error("render_rays(out=): %s must be a contiguous fp32 %s tensor on %s" % (k, want, self.device))
+            out = {k: out[k] for k in keys}
+        else:
+            out = {k: torch.empty((n, 3) if k.startswith("rgb") else n, device=self.device) for k in keys}
         mc = L.Maps(L.dev(out["rgb_map_0"]), L.dev(out["disp_map_0"]), L.dev(out["acc_map_0"]), L.dev(out["depth_map_0"]))
         mf, u = None, None
         if self.N_importance > 0:
-            for k in ("rgb_map", "disp_map", "acc_map", "depth_map"):
-                out[k] = torch.empty((n, 3) if k == "rgb_map" else n, device=self.device)
             mf = L.Maps(L.dev(out["rgb_map"]), L.dev(out["disp_map"]), L.dev(out["acc_map"]), L.dev(out["depth_map"]))
             u = torch.rand((n, self.N_importance), device=self.device) if training else self._table("u")
         ws_bytes = self.lib.nerfb200_render_workspace_bytes(n, C.byref(p))

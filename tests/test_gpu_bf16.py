@@ -66,36 +66,46 @@ def test_mlp_bf16_vs_emulation_and_oracle(n, S):
     assert torch.equal(raw, raw2)
 
 
-def _renderer(sd, **cfg):
+def _renderer(sd, mode="bf16", **cfg):
     from nerf_rep_for_test_b200 import Network, RenderConfig, Renderer
     net = Network(device=DEV)
     net.load_state_dict(sd)
     net.to(DEV).eval()
     base = dict(perturb=0, enable_ess=False, enable_ert=False)
     base.update(cfg)
-    return Renderer(net, RenderConfig(**base), mode="bf16")
+    return Renderer(net, RenderConfig(**base), mode=mode)
 
 
 def _psnr(a, b):
     return float(-10.0 * torch.log10(((a - b) ** 2).mean().clamp_min(1e-20)))
 
 
+# rays of each golden whose LAST reference sigma_raw (coarse, fine pass) lies within the mode's sigma error bound of
+# zero -- a property of the frozen reference outputs, so the counts are pinned, not bounded by a blanket allowance
+FLIP_CANDIDATES = {("bf16", "lego16_randinit"): (1, 28), ("bf16", "lego8_dense"): (0, 0),
+                   ("fp16", "lego16_randinit"): (0, 4), ("fp16", "lego8_dense"): (0, 0)}
+SIGMA_BOUND = {"bf16": 2e-3, "fp16": 2.5e-4}
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp16"])
 @pytest.mark.parametrize("name", ["lego16_randinit", "lego8_dense"])
-def test_render_bf16_vs_reference_golden(name):
+def test_render_bf16_vs_reference_golden(name, mode):
     g = golden(name)
     H, W, seed, gain, bias, ert = g["meta"]
     sd = O.make_state_dict(int(seed), float(gain), float(bias))
-    out = _renderer(sd).render({"pose": torch.from_numpy(g["pose"]).to(DEV),
-                                "intrinsics": torch.from_numpy(g["intrinsics"]).to(DEV), "H": int(H), "W": int(W)})
+    out = _renderer(sd, mode=mode).render({"pose": torch.from_numpy(g["pose"]).to(DEV),
+                                           "intrinsics": torch.from_numpy(g["intrinsics"]).to(DEV), "H": int(H), "W": int(W)})
     # outlier rule (SURVEY 8c' item 3): the last interval is 1e10 wide, so alpha_last = [sigma_last > 0]
-    # is a step function of an MLP output; rays whose reference |sigma_raw_last| is below the bf16
-    # sigma error bound (2e-3) can flip acc by ~1 and are excluded and counted.
+    # is a step function of an MLP output; rays whose reference |sigma_raw_last| is below the mode's
+    # sigma error bound (bf16 2e-3, fp16 2.5e-4) can flip acc by ~1 and are excluded and counted.
     sig_last_f = torch.from_numpy(g["aux_raw_fine"])[:, -1, 3].abs()
     sig_last_c = torch.from_numpy(g["aux_raw_coarse"])[:, -1, 3].abs()
+    thr = SIGMA_BOUND[mode]
+    assert (int((sig_last_c <= thr).sum()), int((sig_last_f <= thr).sum())) == FLIP_CANDIDATES[(mode, name)]
     for k in ("rgb_map_0", "acc_map_0", "depth_map_0", "rgb_map", "acc_map", "depth_map"):
         ref = torch.from_numpy(g["out_" + k])
         a = out[k].cpu()
-        stable = ((sig_last_c if k.endswith("_0") else sig_last_f) > 2e-3).reshape(ref.shape[:2])
+        stable = ((sig_last_c if k.endswith("_0") else sig_last_f) > thr).reshape(ref.shape[:2])
         err = (a - ref).abs()
         if err.dim() == 3:
             err = err.max(-1)[0]
@@ -104,9 +114,8 @@ def test_render_bf16_vs_reference_golden(name):
             name, k, float(err.median()) / scale, float(err.flatten().kthvalue(int(0.99 * err.numel()))[0]) / scale,
             float(err[stable].max()) / scale, int((~stable).sum()), stable.numel()))
         assert float(err[stable].max()) <= 1e-3 * scale, k
-        assert int((~stable).sum()) <= 0.15 * stable.numel()
     ref_rgb = torch.from_numpy(g["out_rgb_map"])
-    stable = (sig_last_f > 2e-3).reshape(ref_rgb.shape[:2])
+    stable = (sig_last_f > thr).reshape(ref_rgb.shape[:2])
     # PSNR of our image against the reference's image; "< 0.05 dB" is about PSNR vs ground truth,
     # which needs a trained checkpoint (absent); the image-to-image PSNR is reported instead
     print("%s PSNR(ours, reference) over stable rays: %.1f dB" % (name, _psnr(out["rgb_map"].cpu()[stable], ref_rgb[stable])))

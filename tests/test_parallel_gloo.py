@@ -49,6 +49,23 @@ def _worker(rank, world, port, out):
         P.FlatGradAllReduce(ps, flat=flat)()
         assert torch.allclose(flat, torch.full_like(flat, sum(range(1, world + 1)) / world))
         assert all(p.grad.data_ptr() >= flat.data_ptr() for p in ps)
+        # one frame split into contiguous ray blocks, gathered on rank 0 (ShardedFrame: the N>1 single-frame path)
+        for n in (1003, 64, 1):
+            frame = P.ShardedFrame(n, torch.device("cpu"))
+            assert (frame.lo, frame.hi) == P.shard_range(n, rank, world)
+
+            def block(lo, hi, views):
+                idx = torch.arange(lo, hi, dtype=torch.float32)
+                for j, (k, c) in enumerate(P.MAP_KEYS):
+                    views[k][:hi - lo] = (idx[:, None] * 10 + j + torch.arange(c) * 0.25) if c == 3 else idx * 10 + j
+            full = frame(block)
+            if rank == 0:
+                idx = torch.arange(n, dtype=torch.float32)
+                for j, (k, c) in enumerate(P.MAP_KEYS):
+                    expect = (idx[:, None] * 10 + j + torch.arange(c) * 0.25) if c == 3 else idx * 10 + j
+                    assert full[k].is_contiguous() and torch.equal(full[k], expect), (n, k)
+            else:
+                assert full is None
         out.put((rank, "ok"))
     except Exception as e:      # pragma: no cover
         out.put((rank, repr(e)))
