@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define NERFB200_ABI_VERSION 3
+#define NERFB200_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define NERFB200_API __attribute__((visibility("default")))
@@ -163,6 +163,23 @@ NERFB200_API int nerfb200_mlp_backward(const void* packed_bwd, const nerfb200_ml
                           const void* acts, const void* masks, long long n_rows, void* workspace,
                           size_t workspace_bytes, const nerfb200_mlp_grads* grads, void* stream);
 
+/* fp32-ACCURATE training twin (true fp32 FFMA arithmetic, layer by layer, csrc/mlp_fp32_train.cu): what the reference
+ * computes under autograd (network.py:49-74, trainer.py:56-60).  Reads the fp32 nn.Linear tensors directly (no packed
+ * image).  acts: nerfb200_train_fp32_acts_bytes(n_rows) bytes, 16-byte aligned -- row-major fp32 planes
+ * PE[.,64] | dirPE[.,32] | relu(h0..h7)[.,256] x 8 | feature[.,256] | relu(views)[.,128]. */
+NERFB200_API size_t nerfb200_train_fp32_acts_bytes(long long n_rows);
+NERFB200_API size_t nerfb200_train_fp32_workspace_bytes(long long n_rows);
+NERFB200_API int nerfb200_mlp_forward_train_fp32(const nerfb200_mlp_weights* weights, const float* rays_o,
+                                    const float* rays_d, const float* z_vals, int n_rays, int n_samples,
+                                    float* raw, void* acts, void* stream);
+/* Gradients of the 24 tensors (OVERWRITTEN) given g_raw = dL/d raw [n_rows,4] and the acts of the call above.
+ * g_z (may be NULL): dL/d z_vals [n_rays,n_samples] through the MLP input x = o + d z and its positional encoding
+ * (freq.py:23-26) -- the path by which the reference's fine loss reaches the coarse network (its sampler is not
+ * detached, volume_renderer.py:181-183); the caller adds the compositor's own dL/dz (nerfb200_composite_backward_z). */
+NERFB200_API int nerfb200_mlp_backward_fp32(const nerfb200_mlp_weights* weights, const float* g_raw, const void* acts,
+                               const float* rays_d, int n_rays, int n_samples, void* workspace,
+                               size_t workspace_bytes, const nerfb200_mlp_grads* grads, float* g_z, void* stream);
+
 /* diagnostic twin of mlp_forward (BF16 mode): additionally writes the fp32 post-activation output
  * of each of the ten stages (mlp_layout.cuh) for rows 0..127 into stage_dump [10][128][256];
  * used by the stage-level parity tests. */
@@ -199,6 +216,13 @@ NERFB200_API int nerfb200_composite_backward(const float* raw, const float* z_va
                                 const float* g_acc_map, const float* g_depth_map,
                                 const float* g_weights, float* g_raw, void* stream);
 
+/* Same, additionally g_z [n_rays,S] (may be NULL): dL/d z_vals through the interval lengths
+ * dists = z[i+1]-z[i] (:295-297) and through depth_map = sum w z (:339). */
+NERFB200_API int nerfb200_composite_backward_z(const float* raw, const float* z_vals, const float* rays_d,
+                                  int n_rays, int n_samples, int white_bkgd, const float* g_rgb_map,
+                                  const float* g_acc_map, const float* g_depth_map,
+                                  const float* g_weights, float* g_raw, float* g_z, void* stream);
+
 /* ---- a4: sample_pdf + merge (volume_renderer.py:239-268, :181-183) ----------------------- */
 /* kernel-level inverse-CDF lookup: cdf,bins [n_rays,n_bins]; u is [n_u] (u_per_ray==0, the
  * eval-mode linspace table) or [n_rays,n_u]; inds = searchsorted(cdf,u,right=True) (int32). */
@@ -211,6 +235,14 @@ NERFB200_API int nerfb200_sample_from_cdf(const float* cdf, const float* bins, c
 NERFB200_API int nerfb200_sample_pdf_merge(const float* z_coarse, const float* weights, const float* u,
                               int u_per_ray, int n_rays, int n_samples, int n_u, float* z_all,
                               float* z_samples, int32_t* inds, float* cdf, void* stream);
+
+/* a7 through a4: the reference does not detach the importance samples (:181-183), so dL/d z_all reaches the coarse
+ * weights.  Given g_z_all [n_rays,S+n_u] (gradient of the merged, sorted depths) writes g_weights [n_rays,S] (the
+ * gradient of the coarse weights; entries 0 and S-1 are 0, :181 uses weights[...,1:-1]).  The forward is recomputed
+ * inside (same arithmetic as nerfb200_sample_pdf_merge); z_coarse, weights, u as passed to the forward. */
+NERFB200_API int nerfb200_sample_pdf_backward(const float* z_coarse, const float* weights, const float* u,
+                                 int u_per_ray, int n_rays, int n_samples, int n_u, const float* g_z_all,
+                                 float* g_weights, void* stream);
 
 /* ---- a8: occupancy grid / empty-space skipping (volume_renderer.py:830-873, :963-1087) --- */
 /* grid: uint8 [R,R,R] (1 = occupied), bbox [-2,2]^3.  Per ray: if more than half of the

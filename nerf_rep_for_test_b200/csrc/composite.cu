@@ -313,7 +313,7 @@ composite_backward_kernel(const float* __restrict__ raw, const float* __restrict
                           const float* __restrict__ rays_d, int n_rays, int S, int white_bkgd,
                           const float* __restrict__ g_rgb_map, const float* __restrict__ g_acc_map,
                           const float* __restrict__ g_depth_map, const float* __restrict__ g_weights,
-                          float* __restrict__ g_raw) {
+                          float* __restrict__ g_raw, float* __restrict__ g_z) {
   int lane = threadIdx.x & 31;
   size_t ray = (size_t)blockIdx.x * kCompWarps + (threadIdx.x >> 5);
   if (ray >= (size_t)n_rays) return;
@@ -357,9 +357,12 @@ composite_backward_kernel(const float* __restrict__ raw, const float* __restrict
   double after = total - incl;  // sum over samples owned by later lanes
   // walk own samples from last to first
   double suffix = after;
+  float gdist[kMaxPer];   // dL/d(z[i+1] - z[i]) of the interval that starts at own sample j (g_z only)
+  float gdist_last = 0.f; // ... of this lane's last interval, handed to the next lane
 #pragma unroll
   for (int j = kMaxPer - 1; j >= 0; --j) {
     int i = lane * per + j;
+    gdist[j] = 0.f;
     if (j < per && i < S) {
       float z0 = z_row[i];
       float dist = ((i + 1 < S) ? (z_row[i + 1] - z0) : 1e10f) * dnorm;
@@ -367,14 +370,31 @@ composite_backward_kernel(const float* __restrict__ raw, const float* __restrict
       float sig = fmaxf(sraw, 0.f);
       float f = (1.f - rs.alpha[j]) + 1e-10f;
       double dalpha = (double)G[j] * (double)rs.T[j] - suffix / (double)f;
-      float dsig = (sraw > 0.f) ? dist * expf(-sig * dist) : 0.f;
+      float e = (sraw > 0.f) ? expf(-sig * dist) : 0.f;
+      float dsig = dist * e;
       float4 o;
       o.x = w[j] * gr * c[j][0] * (1.f - c[j][0]);
       o.y = w[j] * gg * c[j][1] * (1.f - c[j][1]);
       o.z = w[j] * gb * c[j][2] * (1.f - c[j][2]);
       o.w = (float)(dalpha * (double)dsig);
       *reinterpret_cast<float4*>(g_raw + (ray * S + i) * 4) = o;
+      // dalpha/ddist = sigma exp(-sigma dist); the last interval (1e10) does not depend on z
+      if (i + 1 < S) gdist[j] = (float)(dalpha * (double)(sig * e)) * dnorm;
+      if (j == per - 1 || i == S - 1) gdist_last = gdist[j];
       suffix += (double)G[j] * (double)w[j];
+    }
+  }
+  if (g_z != nullptr) {
+    // z_i enters dist_i with -1 and dist_{i-1} with +1 (volume_renderer.py:295-297), and depth_map = sum w z (:339)
+    float prev = __shfl_up_sync(0xffffffffu, gdist_last, 1);
+    if (lane == 0) prev = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxPer; ++j) {
+      int i = lane * per + j;
+      if (j < per && i < S) {
+        g_z[ray * S + i] = gd * w[j] - gdist[j] + prev;
+        prev = gdist[j];
+      }
     }
   }
 }
@@ -487,17 +507,26 @@ int nb::composite_forward_culled(const float* raw, const float* z_vals, const fl
   return 0;
 }
 
-extern "C" int nerfb200_composite_backward(const float* raw, const float* z_vals, const float* rays_d,
-                                           int n_rays, int n_samples, int white_bkgd,
-                                           const float* g_rgb_map, const float* g_acc_map,
-                                           const float* g_depth_map, const float* g_weights,
-                                           float* g_raw, void* stream) {
+extern "C" int nerfb200_composite_backward_z(const float* raw, const float* z_vals, const float* rays_d,
+                                             int n_rays, int n_samples, int white_bkgd,
+                                             const float* g_rgb_map, const float* g_acc_map,
+                                             const float* g_depth_map, const float* g_weights,
+                                             float* g_raw, float* g_z, void* stream) {
   NB_CHECK_ARG(n_rays <= 0 || (raw && z_vals && rays_d && g_raw), "composite_backward: null pointer");
   NB_CHECK_ARG(n_samples >= 1 && n_samples <= 32 * kMaxPer, "composite_backward: n_samples=%d out of range", n_samples);
   NB_CHECK_ARG(n_rays >= 0, "composite_backward: negative n_rays");
   if (n_rays == 0) return 0;
   composite_backward_kernel<<<ceil_div(n_rays, kCompWarps), kCompWarps * 32, 0, (cudaStream_t)stream>>>(
-      raw, z_vals, rays_d, n_rays, n_samples, white_bkgd, g_rgb_map, g_acc_map, g_depth_map, g_weights, g_raw);
+      raw, z_vals, rays_d, n_rays, n_samples, white_bkgd, g_rgb_map, g_acc_map, g_depth_map, g_weights, g_raw, g_z);
   NB_LAUNCH_OK("composite_backward_kernel");
   return 0;
+}
+
+extern "C" int nerfb200_composite_backward(const float* raw, const float* z_vals, const float* rays_d,
+                                           int n_rays, int n_samples, int white_bkgd,
+                                           const float* g_rgb_map, const float* g_acc_map,
+                                           const float* g_depth_map, const float* g_weights,
+                                           float* g_raw, void* stream) {
+  return nerfb200_composite_backward_z(raw, z_vals, rays_d, n_rays, n_samples, white_bkgd, g_rgb_map, g_acc_map,
+                                       g_depth_map, g_weights, g_raw, nullptr, stream);
 }

@@ -249,6 +249,135 @@ sample_pdf_merge_kernel(const float* __restrict__ z_coarse, const float* __restr
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// a7 with the reference's NON-detached sampler (volume_renderer.py:181-183 feeds sample_pdf's output, :239-268,
+// into the fine pass under autograd): gradient of the merged depths z_all with respect to the coarse weights.
+//   samples_j = b0 + t (b1 - b0),  t = (u_j - c0) / denom,  denom = c1 - c0 (replaced by the constant 1 below 1e-5)
+//   cdf = [0, cumsum(pdf)],  pdf = (w + 1e-5) / sum(w + 1e-5)
+// The kernel recomputes the forward (cdf, samples, merge positions) exactly as sample_pdf_merge_kernel does, so
+// nothing has to be saved, then:  g_cdf (shared-memory fp64 atomics: several u fall into one bin) -> reverse
+// cumulative sum -> g_pdf -> quotient rule -> g_weights[:, 1:-1]; the first and last coarse weight get 0.
+// The coarse depths inside z_all are constants (no parameter reaches them) and receive no gradient.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+sample_pdf_backward_kernel(const float* __restrict__ z_coarse, const float* __restrict__ weights,
+                           const float* __restrict__ u_g, int u_per_ray, int n_rays, int S, int n_u,
+                           const float* __restrict__ g_z_all, float* __restrict__ g_weights) {
+  __shared__ float s_z[kWarpsPerBlock][kMaxS];
+  __shared__ float s_cdf[kWarpsPerBlock][kMaxS];
+  __shared__ float s_bins[kWarpsPerBlock][kMaxS];
+  __shared__ float s_smp[kWarpsPerBlock][kMaxU];
+  __shared__ double s_gcdf[kWarpsPerBlock][kMaxS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ray = blockIdx.x * kWarpsPerBlock + warp;
+  if (ray >= n_rays) return;
+  const int nbins = S - 1, nw = S - 2;
+  float* zr = s_z[warp];
+  float* cdf = s_cdf[warp];
+  float* bins = s_bins[warp];
+  float* smp = s_smp[warp];
+  double* gcdf = s_gcdf[warp];
+  for (int i = lane; i < S; i += 32) { zr[i] = z_coarse[(size_t)ray * S + i]; gcdf[i] = 0.0; }
+  __syncwarp();
+  for (int i = lane; i < nbins; i += 32) bins[i] = __fmul_rn(0.5f, __fadd_rn(zr[i + 1], zr[i]));
+  // ---- forward recompute (same arithmetic as sample_pdf_merge_kernel)
+  double part = 0.0;
+  for (int i = lane; i < nw; i += 32) part += (double)__fadd_rn(weights[(size_t)ray * S + 1 + i], 1e-5f);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+  const float wsum = (float)part;
+  const int per = (nw + 31) / 32;
+  double local = 0.0;
+  float pdf_loc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int i = lane * per + j;
+    float p = 0.f;
+    if (j < per && i < nw) p = __fdiv_rn(__fadd_rn(weights[(size_t)ray * S + 1 + i], 1e-5f), wsum);
+    pdf_loc[j] = p;
+    local += (double)p;
+  }
+  double incl = warp_incl_scan(local, lane);
+  double run = incl - local;
+  if (lane == 0) cdf[0] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int i = lane * per + j;
+    if (j < per && i < nw) {
+      run += (double)pdf_loc[j];
+      cdf[i + 1] = (float)run;
+    }
+  }
+  __syncwarp();
+  const float* u_row = u_per_ray ? u_g + (size_t)ray * n_u : u_g;
+  for (int i = lane; i < n_u; i += 32) {
+    int ind;
+    smp[i] = invert_cdf(cdf, bins, nbins, u_row[i], &ind);
+  }
+  __syncwarp();
+  bool unsorted = false;
+  for (int i = lane + 1; i < n_u; i += 32) unsorted |= (smp[i] < smp[i - 1]);
+  unsorted = __any_sync(0xffffffffu, unsorted);
+  // ---- d samples / d cdf
+  const float* gz_row = g_z_all + (size_t)ray * (S + n_u);
+  for (int i = lane; i < n_u; i += 32) {
+    const float x = smp[i];
+    int pos = count_less(zr, S, x, true);
+    if (!unsorted) pos += i;
+    else
+      for (int j = 0; j < n_u; ++j) pos += (smp[j] < x) || (smp[j] == x && j < i);
+    const float gz = gz_row[pos];
+    const float u = u_row[i];
+    const int ind = upper_bound_row(cdf, nbins, u);
+    const int below = max(ind - 1, 0), above = min(nbins - 1, ind);
+    const float c0 = cdf[below], c1 = cdf[above];
+    const float db = __fsub_rn(bins[above], bins[below]);
+    float denom = __fsub_rn(c1, c0);
+    const bool repl = denom < 1e-5f;
+    if (repl) denom = 1.0f;
+    const float t = __fdiv_rn(__fsub_rn(u, c0), denom);
+    const double gt = (double)gz * (double)db;           // dL/dt
+    if (repl) {
+      atomicAdd(&gcdf[below], -gt);
+    } else {
+      atomicAdd(&gcdf[below], gt * ((double)t - 1.0) / (double)denom);
+      atomicAdd(&gcdf[above], -gt * (double)t / (double)denom);
+    }
+  }
+  __syncwarp();
+  // ---- g_pdf[m] = sum_{k > m} g_cdf[k]  (cdf[k] = sum_{m < k} pdf[m]);  own segment m = lane*per + j
+  double seg = 0.0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int m = lane * per + j;
+    if (j < per && m < nw) seg += gcdf[m + 1];
+  }
+  double seg_incl = warp_incl_scan(seg, lane);
+  double total = __shfl_sync(0xffffffffu, seg_incl, 31);
+  double suffix = total - seg_incl;     // g_cdf of the entries owned by later lanes
+  double gpdf[8];
+  double dot = 0.0;
+#pragma unroll
+  for (int j = 7; j >= 0; --j) {
+    int m = lane * per + j;
+    gpdf[j] = 0.0;
+    if (j < per && m < nw) {
+      suffix += gcdf[m + 1];
+      gpdf[j] = suffix;
+      dot += suffix * (double)pdf_loc[j];
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, d);
+  float* gw = g_weights + (size_t)ray * S;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int m = lane * per + j;
+    if (j < per && m < nw) gw[1 + m] = (float)((gpdf[j] - dot) / (double)wsum);
+  }
+  if (lane == 0) { gw[0] = 0.f; gw[S - 1] = 0.f; }
+}
+
 }  // namespace nb
 
 using namespace nb;
@@ -318,5 +447,19 @@ static int sample_pdf_merge_impl(const float* z_coarse, const float* weights, co
   sample_pdf_merge_kernel<<<blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
       z_coarse, weights, u, u_per_ray, n_rays, n_samples, n_u, z_all, z_samples, inds, cdf, rl.rays, rl.count);
   NB_LAUNCH_OK("sample_pdf_merge_kernel");
+  return 0;
+}
+
+extern "C" int nerfb200_sample_pdf_backward(const float* z_coarse, const float* weights, const float* u, int u_per_ray,
+                                            int n_rays, int n_samples, int n_u, const float* g_z_all,
+                                            float* g_weights, void* stream) {
+  NB_CHECK_ARG(n_rays <= 0 || (z_coarse && weights && u && g_z_all && g_weights), "sample_pdf_backward: null pointer");
+  NB_CHECK_ARG(n_samples >= 3 && n_samples <= kMaxS, "sample_pdf_backward: n_samples=%d out of range [3,%d]", n_samples, kMaxS);
+  NB_CHECK_ARG(n_u >= 1 && n_u <= kMaxU, "sample_pdf_backward: n_u=%d out of range [1,%d]", n_u, kMaxU);
+  NB_CHECK_ARG(n_rays >= 0, "sample_pdf_backward: negative n_rays");
+  if (n_rays == 0) return 0;
+  sample_pdf_backward_kernel<<<ceil_div(n_rays, kWarpsPerBlock), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      z_coarse, weights, u, u_per_ray, n_rays, n_samples, n_u, g_z_all, g_weights);
+  NB_LAUNCH_OK("sample_pdf_backward_kernel");
   return 0;
 }

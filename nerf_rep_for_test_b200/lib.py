@@ -20,7 +20,7 @@ def mode_coarse(m):
 
 COMPOSITE_PLAIN, COMPOSITE_ERT, COMPOSITE_ERT_COMPAT = 0, 1, 2
 COMPOSITE_FAST_MATH = 0x10          # OR-ed into PLAIN / ERT (include/nerfb200.h)
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _f = C.POINTER(C.c_float)
 _vp = C.c_void_p
@@ -87,6 +87,14 @@ SIGNATURES = {
     "nerfb200_pack_weights_bwd": (C.c_int, [C.POINTER(MlpWeights), _vp, _vp]),
     "nerfb200_mlp_backward": (C.c_int, [_vp, C.POINTER(MlpWeights), _vp, _vp, _vp, C.c_longlong, _vp, C.c_size_t,
                                         C.POINTER(MlpGrads), _vp]),
+    "nerfb200_train_fp32_acts_bytes": (C.c_size_t, [C.c_longlong]),
+    "nerfb200_train_fp32_workspace_bytes": (C.c_size_t, [C.c_longlong]),
+    "nerfb200_mlp_forward_train_fp32": (C.c_int, [C.POINTER(MlpWeights), _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "nerfb200_mlp_backward_fp32": (C.c_int, [C.POINTER(MlpWeights), _vp, _vp, _vp, C.c_int, C.c_int, _vp, C.c_size_t,
+                                             C.POINTER(MlpGrads), _vp, _vp]),
+    "nerfb200_composite_backward_z": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp,
+                                                _vp, _vp, _vp]),
+    "nerfb200_sample_pdf_backward": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
     "nerfb200_mlp_forward_stages": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "nerfb200_composite_forward": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
                                              C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),

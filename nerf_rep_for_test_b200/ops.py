@@ -219,6 +219,79 @@ def composite_backward(raw, z_vals, rays_d, g_rgb=None, g_acc=None, g_depth=None
     return g_raw
 
 
+def composite_backward_z(raw, z_vals, rays_d, g_rgb=None, g_acc=None, g_depth=None, g_weights=None, white_bkgd=True):
+    """(g_raw, g_z): composite_backward plus dL/d z_vals through the interval lengths and depth_map."""
+    raw, z_vals, rays_d = _f(raw), _f(z_vals), _f(rays_d)
+    n, S = z_vals.shape
+    g_raw = torch.empty_like(raw)
+    g_z = torch.empty_like(z_vals)
+    L.check(L.load().nerfb200_composite_backward_z(L.dev(raw), L.dev(z_vals), L.dev(rays_d), n, S, int(white_bkgd),
+                                                  L.dev(_f(g_rgb)), L.dev(_f(g_acc)), L.dev(_f(g_depth)),
+                                                  L.dev(_f(g_weights)), L.dev(g_raw), L.dev(g_z), L.stream_ptr()),
+            "composite_backward_z")
+    return g_raw, g_z
+
+
+def sample_pdf_backward(z_coarse, weights, u, g_z_all):
+    """g_weights [n,S] of the coarse pass given dL/d z_all [n,S+n_u] (reference graph: sampler not detached)."""
+    z_coarse, weights, u, g_z_all = _f(z_coarse), _f(weights), _f(u), _f(g_z_all)
+    n, S = z_coarse.shape
+    n_u = u.shape[-1]
+    if tuple(g_z_all.shape) != (n, S + n_u):
+        raise L.NerfB200Error("sample_pdf_backward: g_z_all must be [%d,%d]" % (n, S + n_u))
+    g_w = torch.empty((n, S), device=z_coarse.device)
+    L.check(L.load().nerfb200_sample_pdf_backward(L.dev(z_coarse), L.dev(weights), L.dev(u), int(u.dim() == 2), n, S, n_u,
+                                                 L.dev(g_z_all), L.dev(g_w), L.stream_ptr()), "sample_pdf_backward")
+    return g_w
+
+
+def weights_struct(tensors):
+    """nerfb200_mlp_weights over a list of the 24 fp32 CUDA tensors of one model (order of training._NAMES)."""
+    w = L.MlpWeights()
+    ts = [_f(t.detach()) for t in tensors]
+    for i in range(8):
+        w.pts_w[i], w.pts_b[i] = ts[2 * i].data_ptr(), ts[2 * i + 1].data_ptr()
+    (w.views_w, w.views_b, w.feature_w, w.feature_b, w.alpha_w, w.alpha_b, w.rgb_w, w.rgb_b) = [t.data_ptr() for t in ts[16:24]]
+    return w, ts
+
+
+def mlp_forward_train_fp32(tensors, rays_o, rays_d, z_vals):
+    """fp32-accurate training forward: (raw [n,S,4], acts buffer).  tensors: the 24 fp32 tensors of one model."""
+    rays_o, rays_d, z_vals = _f(rays_o), _f(rays_d), _f(z_vals)
+    n, S = z_vals.shape
+    lib = L.load()
+    raw = torch.empty((n, S, 4), device=z_vals.device)
+    acts = torch.empty(lib.nerfb200_train_fp32_acts_bytes(n * S), dtype=torch.uint8, device=z_vals.device)
+    w, keep = weights_struct(tensors)
+    L.check(lib.nerfb200_mlp_forward_train_fp32(C.byref(w), L.dev(rays_o), L.dev(rays_d), L.dev(z_vals), n, S, L.dev(raw),
+                                                L.dev(acts), L.stream_ptr()), "mlp_forward_train_fp32")
+    return raw, acts
+
+
+def mlp_backward_fp32(tensors, g_raw, acts, rays_d, n, S, grads=None, want_g_z=False):
+    """(24 gradients, g_z [n,S] or None) of nerfb200_mlp_backward_fp32."""
+    lib = L.load()
+    g_raw = _f(g_raw).reshape(-1, 4)
+    rays_d = _f(rays_d)
+    dev = g_raw.device
+    if g_raw.shape[0] != n * S:
+        raise L.NerfB200Error("mlp_backward_fp32: g_raw has %d rows, expected %d" % (g_raw.shape[0], n * S))
+    ws_bytes = lib.nerfb200_train_fp32_workspace_bytes(n * S)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    if grads is None:
+        grads = [torch.empty(sh, device=dev) for sh in GRAD_SHAPES]
+    g = L.MlpGrads()
+    for i in range(8):
+        g.pts_w[i], g.pts_b[i] = grads[2 * i].data_ptr(), grads[2 * i + 1].data_ptr()
+    (g.views_w, g.views_b, g.feature_w, g.feature_b, g.alpha_w, g.alpha_b, g.rgb_w, g.rgb_b) = \
+        [t.data_ptr() for t in grads[16:24]]
+    g_z = torch.empty((n, S), device=dev) if want_g_z else None
+    w, keep = weights_struct(tensors)
+    L.check(lib.nerfb200_mlp_backward_fp32(C.byref(w), L.dev(g_raw), L.dev(acts), L.dev(rays_d), n, S, L.dev(ws), ws_bytes,
+                                           C.byref(g), L.dev(g_z), L.stream_ptr()), "mlp_backward_fp32")
+    return grads, g_z
+
+
 def sample_from_cdf(cdf, bins, u):
     cdf, bins, u = _f(cdf), _f(bins), _f(u)
     n, nb = cdf.shape

@@ -1,15 +1,21 @@
 """Differentiable ray rendering for training.
 
-Forward = the same CUDA kernels as inference (stratified sampling, fused PE+MLP on tcgen05, compositing,
-sample_pdf + merge); the training forward additionally leaves every stage's bf16 output in HBM as
-operand-ready tile images plus the relu sign bits (csrc/train_layout.cuh).  Backward:
-  * compositing: the analytic kernel `nerfb200_composite_backward` (a7);
-  * MLP: `nerfb200_mlp_backward` -- a tcgen05 activation-gradient chain (csrc/mlp_bwd_dgrad.cu) and ten
-    split-K weight-gradient GEMMs with the bias / head gradients riding along (csrc/mlp_bwd_wgrad.cu);
-    bf16 operands, fp32 accumulation in TMEM, fp32 gradients.  No library GEMM is involved.
-  * the hierarchical sampler is detached (original-NeRF semantics).  The reference does not detach
-    (volume_renderer.py:181-183), so its fine loss also leaks into the coarse network
-    through sample_pdf; that path is not reproduced.
+Forward = the same CUDA kernels as inference (stratified sampling, fused PE+MLP, compositing, sample_pdf + merge).
+Two arithmetic paths, selected with `precision`:
+  * "bf16" (performance): tcgen05 forward that leaves every stage's bf16 output in HBM as operand-ready tile images
+    plus the relu sign bits (csrc/train_layout.cuh); backward = `nerfb200_mlp_backward` -- a tcgen05
+    activation-gradient chain (csrc/mlp_bwd_dgrad.cu) and nine split-K weight-gradient GEMMs with the bias / head
+    gradients riding along (csrc/mlp_bwd_wgrad.cu); bf16 operands, fp32 accumulation in TMEM, fp32 gradients.
+  * "fp32" (parity): true fp32 FFMA arithmetic layer by layer (csrc/mlp_fp32_train.cu) -- what the reference computes
+    under autograd (network.py:49-74, trainer.py:56-60); gradients agree with the reference's autograd to ~1e-5.
+Compositing backward: the analytic kernel `nerfb200_composite_backward[_z]` (a7).  No library GEMM is involved.
+
+`ref_compat_sampler`: the reference does NOT detach its hierarchical sampler (volume_renderer.py:181-183 passes
+sample_pdf's output, :239-268, straight into the fine pass), so the fine loss also reaches the COARSE network:
+dL/dz of the merged depths -- through the fine MLP's input x = o + d z (positional-encoding backward) and through the
+fine compositor's interval lengths -- flows through the inverse-CDF sampling (`nerfb200_sample_pdf_backward`) into the
+coarse weights and on into the coarse compositor / MLP.  True reproduces that graph (fp32 path); False (default) is
+the original-NeRF semantics with the sampler detached.
 
 Loss used by the benchmark: mse(rgb_map_0, t) + mse(rgb_map, t) (src/train/trainers/nerf.py:52-65).
 """
@@ -38,44 +44,83 @@ def _density_noise(renderer, raw, which):
         ops.sigma_noise(raw, std, seed=renderer.seed * 0x9E3779B97F4A7C15 + which)
 
 
-class _RenderRays(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, renderer, rays_o, rays_d, *params):
-        r = renderer
-        dev = rays_o.device
-        n = rays_o.shape[0]
-        S, U = r.N_samples, r.N_importance
+def _tensors(model):
+    return [p.detach() for p in model_params(model)]
+
+
+def _forward_passes(r, rays_o, rays_d, precision, z_c=None):
+    """Coarse + fine forward with everything the backward needs.  Returns a dict."""
+    dev = rays_o.device
+    n = rays_o.shape[0]
+    if z_c is None:
         r.seed += 1
         z_c = ops.sample_coarse(r._table("z"), n, perturb=float(r.perturb) > 0, seed=r.seed)
-        pk_c, pk_f = r.packed("coarse", "bf16"), r.packed("fine", "bf16")   # cached per parameter version
-        raw_c, store_c = ops.mlp_forward_train(pk_c, rays_o, rays_d, z_c)
-        _density_noise(r, raw_c, 1)
-        rgb0, disp0, acc0, w_c, depth0 = ops.composite_forward(raw_c, z_c, rays_d, L.COMPOSITE_PLAIN,
-                                                               white_bkgd=r.white_bkgd)
-        u = torch.rand((n, U), device=dev) if r.net.training else r._table("u")
-        z_all, _, _, _ = ops.sample_pdf_merge(z_c, w_c, u, want_aux=False)
-        raw_f, store_f = ops.mlp_forward_train(pk_f, rays_o, rays_d, z_all)
-        _density_noise(r, raw_f, 2)
-        rgb, disp, acc, _, depth = ops.composite_forward(raw_f, z_all, rays_d, L.COMPOSITE_PLAIN,
-                                                         white_bkgd=r.white_bkgd, want_weights=False)
-        ctx.renderer = r
-        ctx.stores = (store_c, store_f)
-        ctx.save_for_backward(rays_d, z_c, z_all, raw_c, raw_f)
+    st = {"z_c": z_c, "precision": precision}
+    if precision == "bf16":
+        raw_c, st["store_c"] = ops.mlp_forward_train(r.packed("coarse", "bf16"), rays_o, rays_d, z_c)
+    else:
+        raw_c, st["store_c"] = ops.mlp_forward_train_fp32(_tensors(r.coarse_model), rays_o, rays_d, z_c)
+    _density_noise(r, raw_c, 1)
+    rgb0, disp0, acc0, w_c, depth0 = ops.composite_forward(raw_c, z_c, rays_d, L.COMPOSITE_PLAIN, white_bkgd=r.white_bkgd)
+    u = torch.rand((n, r.N_importance), device=dev) if r.net.training else r._table("u")
+    z_all = ops.sample_pdf_merge(z_c, w_c, u, want_aux=False)[0]
+    if precision == "bf16":
+        raw_f, st["store_f"] = ops.mlp_forward_train(r.packed("fine", "bf16"), rays_o, rays_d, z_all)
+    else:
+        raw_f, st["store_f"] = ops.mlp_forward_train_fp32(_tensors(r.fine_model), rays_o, rays_d, z_all)
+    _density_noise(r, raw_f, 2)
+    rgb, disp, acc, _, depth = ops.composite_forward(raw_f, z_all, rays_d, L.COMPOSITE_PLAIN, white_bkgd=r.white_bkgd,
+                                                     want_weights=False)
+    st.update(raw_c=raw_c, raw_f=raw_f, w_c=w_c, u=u, z_all=z_all,
+              maps=(rgb0, acc0, depth0, disp0, rgb, acc, depth, disp))
+    return st
+
+
+def _mlp_backward(r, which, precision, g_raw, store, rays_d, n, S, grads, want_g_z=False):
+    if precision == "bf16":
+        if want_g_z:
+            raise L.NerfB200Error("ref_compat_sampler=True needs precision='fp32' (the bf16 backward has no input gradient)")
+        return ops.mlp_backward(r.packed_bwd(which), g_raw, store, grads=grads), None
+    model = r.coarse_model if which == "coarse" else r.fine_model
+    return ops.mlp_backward_fp32(_tensors(model), g_raw, store, rays_d, n, S, grads=grads, want_g_z=want_g_z)
+
+
+def _backward_passes(r, st, rays_d, g_coarse, g_fine, ref_compat_sampler, grads_c=None, grads_f=None):
+    """g_coarse / g_fine: (g_rgb, g_acc, g_depth) of the two passes (entries may be None).  Fine pass first: with the
+    reference's non-detached sampler its dL/dz feeds the coarse compositor through dL/d(coarse weights)."""
+    precision = st["precision"]
+    n, S = st["z_c"].shape
+    Sf = st["z_all"].shape[1]
+    g_w_c = None
+    if ref_compat_sampler:
+        g_raw_f, g_z = ops.composite_backward_z(st["raw_f"], st["z_all"], rays_d, *g_fine, None, white_bkgd=r.white_bkgd)
+        grads_f, g_z_mlp = _mlp_backward(r, "fine", precision, g_raw_f, st["store_f"], rays_d, n, Sf, grads_f, want_g_z=True)
+        g_z += g_z_mlp
+        g_w_c = ops.sample_pdf_backward(st["z_c"], st["w_c"], st["u"], g_z)
+    else:
+        g_raw_f = ops.composite_backward(st["raw_f"], st["z_all"], rays_d, *g_fine, None, white_bkgd=r.white_bkgd)
+        grads_f, _ = _mlp_backward(r, "fine", precision, g_raw_f, st["store_f"], rays_d, n, Sf, grads_f)
+    g_raw_c = ops.composite_backward(st["raw_c"], st["z_c"], rays_d, *g_coarse, g_w_c, white_bkgd=r.white_bkgd)
+    grads_c, _ = _mlp_backward(r, "coarse", precision, g_raw_c, st["store_c"], rays_d, n, S, grads_c)
+    return grads_c, grads_f
+
+
+class _RenderRays(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, renderer, precision, ref_compat_sampler, rays_o, rays_d, *params):
+        st = _forward_passes(renderer, rays_o, rays_d, precision)
+        rgb0, acc0, depth0, disp0, rgb, acc, depth, disp = st.pop("maps")
+        ctx.renderer, ctx.st, ctx.rays_d, ctx.ref_compat_sampler = renderer, st, rays_d, ref_compat_sampler
         ctx.mark_non_differentiable(disp0, disp)
         return rgb0, acc0, depth0, disp0, rgb, acc, depth, disp
 
     @staticmethod
     def backward(ctx, g_rgb0, g_acc0, g_depth0, _gd0, g_rgb, g_acc, g_depth, _gd):
-        r = ctx.renderer
-        rays_d, z_c, z_all, raw_c, raw_f = ctx.saved_tensors
         c = lambda t: None if t is None else t.contiguous()
-        grads = []
-        for which, z, raw, store, gr, ga, gd in (("coarse", z_c, raw_c, ctx.stores[0], g_rgb0, g_acc0, g_depth0),
-                                                 ("fine", z_all, raw_f, ctx.stores[1], g_rgb, g_acc, g_depth)):
-            g_raw = ops.composite_backward(raw, z, rays_d, c(gr), c(ga), c(gd), None, white_bkgd=r.white_bkgd)
-            grads += ops.mlp_backward(r.packed_bwd(which), g_raw, store)
-        ctx.stores = None
-        return (None, None, None) + tuple(grads)
+        grads_c, grads_f = _backward_passes(ctx.renderer, ctx.st, ctx.rays_d, (c(g_rgb0), c(g_acc0), c(g_depth0)),
+                                            (c(g_rgb), c(g_acc), c(g_depth)), ctx.ref_compat_sampler)
+        ctx.st = None
+        return (None, None, None, None, None) + tuple(grads_c) + tuple(grads_f)
 
 
 _NAMES = sum((["pts_linears.%d.weight" % i, "pts_linears.%d.bias" % i] for i in range(8)), []) + [
@@ -83,15 +128,20 @@ _NAMES = sum((["pts_linears.%d.weight" % i, "pts_linears.%d.bias" % i] for i in 
     "alpha_linear.weight", "alpha_linear.bias", "rgb_linear.weight", "rgb_linear.bias"]
 
 
-def render_rays_train(renderer, rays_o, rays_d):
+def render_rays_train(renderer, rays_o, rays_d, precision="bf16", ref_compat_sampler=False):
     """Differentiable counterpart of Renderer.render_rays: dict of [N,...] maps carrying grad to the
-    parameters of net.model and net.model_fine."""
+    parameters of net.model and net.model_fine.  precision / ref_compat_sampler: module docstring."""
     if renderer.enable_ess or renderer.enable_ert:
         raise L.NerfB200Error("training path implements the plain compositor (enable_ess/enable_ert off)")
+    if precision not in ("bf16", "fp32"):
+        raise ValueError("precision must be 'bf16' or 'fp32'")
+    if ref_compat_sampler and precision != "fp32":
+        raise L.NerfB200Error("ref_compat_sampler=True needs precision='fp32' (the bf16 backward has no input gradient)")
     params = model_params(renderer.coarse_model) + model_params(renderer.fine_model)
     rays_o = rays_o.to(renderer.device, torch.float32).contiguous()
     rays_d = rays_d.to(renderer.device, torch.float32).contiguous()
-    rgb0, acc0, depth0, disp0, rgb, acc, depth, disp = _RenderRays.apply(renderer, rays_o, rays_d, *params)
+    rgb0, acc0, depth0, disp0, rgb, acc, depth, disp = _RenderRays.apply(renderer, precision, bool(ref_compat_sampler),
+                                                                         rays_o, rays_d, *params)
     return {"rgb_map_0": rgb0, "acc_map_0": acc0, "depth_map_0": depth0, "disp_map_0": disp0,
             "rgb_map": rgb, "acc_map": acc, "depth_map": depth, "disp_map": disp}
 
@@ -122,8 +172,13 @@ class TrainStep:
     tensor (set_lr); raw_noise_std > 0 falls back to the eager step (its seed is a kernel argument).  Inputs must keep
     their shape; a capture failure falls back to the eager step with a warning."""
 
-    def __init__(self, renderer, lr=5e-4, graph=False):
+    def __init__(self, renderer, lr=5e-4, graph=False, precision="bf16", ref_compat_sampler=False):
         from .parallel import FlatGradAllReduce
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        if ref_compat_sampler and precision != "fp32":
+            raise L.NerfB200Error("ref_compat_sampler=True needs precision='fp32' (the bf16 backward has no input gradient)")
+        self.precision, self.ref_compat_sampler = precision, bool(ref_compat_sampler)
         self.r = renderer
         self.models = (("coarse", renderer.coarse_model), ("fine", renderer.fine_model))
         self.params = [p for _, m in self.models for p in model_params(m)]
@@ -172,25 +227,14 @@ class TrainStep:
 
     def _step(self, rays_o, rays_d, target_rgb, in_graph=False):
         r = self.r
-        dev = r.device
-        n = rays_o.shape[0]
-        z_c = self._coarse_z(n, in_graph)
-        pk_c, pk_f = r.packed("coarse", "bf16"), r.packed("fine", "bf16")
-        raw_c, store_c = ops.mlp_forward_train(pk_c, rays_o, rays_d, z_c)
-        _density_noise(r, raw_c, 1)
-        rgb0, _, _, w_c, _ = ops.composite_forward(raw_c, z_c, rays_d, L.COMPOSITE_PLAIN, white_bkgd=r.white_bkgd)
-        u = torch.rand((n, r.N_importance), device=dev) if r.net.training else r._table("u")
-        z_all = ops.sample_pdf_merge(z_c, w_c, u, want_aux=False)[0]
-        raw_f, store_f = ops.mlp_forward_train(pk_f, rays_o, rays_d, z_all)
-        _density_noise(r, raw_f, 2)
-        rgb = ops.composite_forward(raw_f, z_all, rays_d, L.COMPOSITE_PLAIN, white_bkgd=r.white_bkgd, want_weights=False)[0]
+        st = _forward_passes(r, rays_o, rays_d, self.precision, z_c=self._coarse_z(rays_o.shape[0], in_graph))
+        rgb0, rgb = st["maps"][0], st["maps"][4]
         # loss = mean((rgb0 - t)^2) + mean((rgb - t)^2)  (trainers/nerf.py:52-65)  ->  dL/d map = 2 (map - t) / (3 n)
         d0, d1 = rgb0 - target_rgb, rgb - target_rgb
         loss = (d0 * d0).mean() + (d1 * d1).mean()
         scale = 2.0 / d0.numel()
-        for which, z, raw, store, d in (("coarse", z_c, raw_c, store_c, d0), ("fine", z_all, raw_f, store_f, d1)):
-            g_raw = ops.composite_backward(raw, z, rays_d, d * scale, None, None, None, white_bkgd=r.white_bkgd)
-            ops.mlp_backward(r.packed_bwd(which), g_raw, store, grads=self.grad_views[which])
+        _backward_passes(r, st, rays_d, (d0 * scale, None, None), (d1 * scale, None, None), self.ref_compat_sampler,
+                         grads_c=self.grad_views["coarse"], grads_f=self.grad_views["fine"])
         self.allreduce()
         self.flat.clamp_(-40.0, 40.0)          # clip_grad_value_(params, 40) on the aliased buffer
         self.opt.step()
