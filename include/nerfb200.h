@@ -180,6 +180,15 @@ NERFB200_API int nerfb200_mlp_backward_fp32(const nerfb200_mlp_weights* weights,
                                const float* rays_d, int n_rays, int n_samples, void* workspace,
                                size_t workspace_bytes, const nerfb200_mlp_grads* grads, float* g_z, void* stream);
 
+/* bf16 training path, reference graph (sampler not detached, volume_renderer.py:181-183): dL/d z_vals [n_rays,n_samples]
+ * through the MLP input x = o + d z, computed from the activation-gradient planes nerfb200_mlp_backward left in
+ * `workspace` (call it after nerfb200_mlp_backward on the same rows, with the same workspace) and the fp32
+ * pts_linears.0 / pts_linears.5 weights: g_pe = dpre0 W0 + dpre5 W5[:, :63] on the tensor cores (bf16 operands,
+ * fp32 accumulate), then the positional-encoding backward (freq.py:23-26) in fp32. */
+NERFB200_API int nerfb200_mlp_backward_input(const nerfb200_mlp_weights* weights, const void* workspace,
+                                const float* rays_o, const float* rays_d, const float* z_vals, int n_rays,
+                                int n_samples, float* g_z, void* stream);
+
 /* diagnostic twin of mlp_forward (BF16 mode): additionally writes the fp32 post-activation output
  * of each of the ten stages (mlp_layout.cuh) for rows 0..127 into stage_dump [10][128][256];
  * used by the stage-level parity tests. */

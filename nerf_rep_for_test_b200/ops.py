@@ -163,6 +163,18 @@ def mlp_backward(bwd, g_raw, store, keep_workspace=None, grads=None):
     return grads
 
 
+def mlp_backward_input(bwd, ws, rays_o, rays_d, z_vals):
+    """g_z [n,S]: dL/d z_vals through the MLP input (bf16 path, reference graph).  `ws` is the workspace tensor of the
+    preceding mlp_backward call on the same rows (keep_workspace)."""
+    _, wstruct = bwd
+    rays_o, rays_d, z_vals = _f(rays_o), _f(rays_d), _f(z_vals)
+    n, S = z_vals.shape
+    g_z = torch.empty((n, S), device=z_vals.device)
+    L.check(L.load().nerfb200_mlp_backward_input(C.byref(wstruct), L.dev(ws), L.dev(rays_o), L.dev(rays_d), L.dev(z_vals),
+                                                n, S, L.dev(g_z), L.stream_ptr()), "mlp_backward_input")
+    return g_z
+
+
 def mlp_forward_stages(packed, rays_o, rays_d, z_vals):
     """BF16 mode diagnostic: (raw, stage_dump [10,128,256]) -- fp32 stage outputs of rows 0..127."""
     rays_o, rays_d, z_vals = _f(rays_o), _f(rays_d), _f(z_vals)

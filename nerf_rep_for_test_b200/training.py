@@ -14,8 +14,9 @@ Compositing backward: the analytic kernel `nerfb200_composite_backward[_z]` (a7)
 sample_pdf's output, :239-268, straight into the fine pass), so the fine loss also reaches the COARSE network:
 dL/dz of the merged depths -- through the fine MLP's input x = o + d z (positional-encoding backward) and through the
 fine compositor's interval lengths -- flows through the inverse-CDF sampling (`nerfb200_sample_pdf_backward`) into the
-coarse weights and on into the coarse compositor / MLP.  True reproduces that graph (fp32 path); False (default) is
-the original-NeRF semantics with the sampler detached.
+coarse weights and on into the coarse compositor / MLP.  True reproduces that graph (both precisions; the bf16 path gets
+the MLP-input gradient from `nerfb200_mlp_backward_input`); False (default) is the original-NeRF semantics with the
+sampler detached.
 
 Loss used by the benchmark: mse(rgb_map_0, t) + mse(rgb_map, t) (src/train/trainers/nerf.py:52-65).
 """
@@ -48,8 +49,10 @@ def _tensors(model):
     return [p.detach() for p in model_params(model)]
 
 
-def _forward_passes(r, rays_o, rays_d, precision, z_c=None):
-    """Coarse + fine forward with everything the backward needs.  Returns a dict."""
+def _forward_passes(r, rays_o, rays_d, precision, z_c=None, _inject=None):
+    """Coarse + fine forward with everything the backward needs.  Returns a dict.  _inject (tests only): a dict with
+    the coarse weights "w_c" and merged depths "z_all" of another run, used instead of this run's own so that two
+    arithmetic paths can be compared at identical sample positions."""
     dev = rays_o.device
     n = rays_o.shape[0]
     if z_c is None:
@@ -64,6 +67,8 @@ def _forward_passes(r, rays_o, rays_d, precision, z_c=None):
     rgb0, disp0, acc0, w_c, depth0 = ops.composite_forward(raw_c, z_c, rays_d, L.COMPOSITE_PLAIN, white_bkgd=r.white_bkgd)
     u = torch.rand((n, r.N_importance), device=dev) if r.net.training else r._table("u")
     z_all = ops.sample_pdf_merge(z_c, w_c, u, want_aux=False)[0]
+    if _inject is not None:
+        w_c, z_all = _inject["w_c"], _inject["z_all"]
     if precision == "bf16":
         raw_f, st["store_f"] = ops.mlp_forward_train(r.packed("fine", "bf16"), rays_o, rays_d, z_all)
     else:
@@ -76,32 +81,34 @@ def _forward_passes(r, rays_o, rays_d, precision, z_c=None):
     return st
 
 
-def _mlp_backward(r, which, precision, g_raw, store, rays_d, n, S, grads, want_g_z=False):
+def _mlp_backward(r, which, precision, g_raw, store, rays_o, rays_d, z, grads, want_g_z=False):
+    """-> (24 gradients, g_z or None).  g_z = dL/dz through the MLP input (reference graph only)."""
+    n, S = z.shape
     if precision == "bf16":
-        if want_g_z:
-            raise L.NerfB200Error("ref_compat_sampler=True needs precision='fp32' (the bf16 backward has no input gradient)")
-        return ops.mlp_backward(r.packed_bwd(which), g_raw, store, grads=grads), None
+        keep = {} if want_g_z else None
+        bwd = r.packed_bwd(which)
+        grads = ops.mlp_backward(bwd, g_raw, store, grads=grads, keep_workspace=keep)
+        return grads, (ops.mlp_backward_input(bwd, keep["ws"], rays_o, rays_d, z) if want_g_z else None)
     model = r.coarse_model if which == "coarse" else r.fine_model
     return ops.mlp_backward_fp32(_tensors(model), g_raw, store, rays_d, n, S, grads=grads, want_g_z=want_g_z)
 
 
-def _backward_passes(r, st, rays_d, g_coarse, g_fine, ref_compat_sampler, grads_c=None, grads_f=None):
+def _backward_passes(r, st, rays_o, rays_d, g_coarse, g_fine, ref_compat_sampler, grads_c=None, grads_f=None):
     """g_coarse / g_fine: (g_rgb, g_acc, g_depth) of the two passes (entries may be None).  Fine pass first: with the
     reference's non-detached sampler its dL/dz feeds the coarse compositor through dL/d(coarse weights)."""
     precision = st["precision"]
-    n, S = st["z_c"].shape
-    Sf = st["z_all"].shape[1]
     g_w_c = None
     if ref_compat_sampler:
         g_raw_f, g_z = ops.composite_backward_z(st["raw_f"], st["z_all"], rays_d, *g_fine, None, white_bkgd=r.white_bkgd)
-        grads_f, g_z_mlp = _mlp_backward(r, "fine", precision, g_raw_f, st["store_f"], rays_d, n, Sf, grads_f, want_g_z=True)
+        grads_f, g_z_mlp = _mlp_backward(r, "fine", precision, g_raw_f, st["store_f"], rays_o, rays_d, st["z_all"], grads_f,
+                                         want_g_z=True)
         g_z += g_z_mlp
         g_w_c = ops.sample_pdf_backward(st["z_c"], st["w_c"], st["u"], g_z)
     else:
         g_raw_f = ops.composite_backward(st["raw_f"], st["z_all"], rays_d, *g_fine, None, white_bkgd=r.white_bkgd)
-        grads_f, _ = _mlp_backward(r, "fine", precision, g_raw_f, st["store_f"], rays_d, n, Sf, grads_f)
+        grads_f, _ = _mlp_backward(r, "fine", precision, g_raw_f, st["store_f"], rays_o, rays_d, st["z_all"], grads_f)
     g_raw_c = ops.composite_backward(st["raw_c"], st["z_c"], rays_d, *g_coarse, g_w_c, white_bkgd=r.white_bkgd)
-    grads_c, _ = _mlp_backward(r, "coarse", precision, g_raw_c, st["store_c"], rays_d, n, S, grads_c)
+    grads_c, _ = _mlp_backward(r, "coarse", precision, g_raw_c, st["store_c"], rays_o, rays_d, st["z_c"], grads_c)
     return grads_c, grads_f
 
 
@@ -110,14 +117,14 @@ class _RenderRays(torch.autograd.Function):
     def forward(ctx, renderer, precision, ref_compat_sampler, rays_o, rays_d, *params):
         st = _forward_passes(renderer, rays_o, rays_d, precision)
         rgb0, acc0, depth0, disp0, rgb, acc, depth, disp = st.pop("maps")
-        ctx.renderer, ctx.st, ctx.rays_d, ctx.ref_compat_sampler = renderer, st, rays_d, ref_compat_sampler
+        ctx.renderer, ctx.st, ctx.rays_o, ctx.rays_d, ctx.ref_compat_sampler = renderer, st, rays_o, rays_d, ref_compat_sampler
         ctx.mark_non_differentiable(disp0, disp)
         return rgb0, acc0, depth0, disp0, rgb, acc, depth, disp
 
     @staticmethod
     def backward(ctx, g_rgb0, g_acc0, g_depth0, _gd0, g_rgb, g_acc, g_depth, _gd):
         c = lambda t: None if t is None else t.contiguous()
-        grads_c, grads_f = _backward_passes(ctx.renderer, ctx.st, ctx.rays_d, (c(g_rgb0), c(g_acc0), c(g_depth0)),
+        grads_c, grads_f = _backward_passes(ctx.renderer, ctx.st, ctx.rays_o, ctx.rays_d, (c(g_rgb0), c(g_acc0), c(g_depth0)),
                                             (c(g_rgb), c(g_acc), c(g_depth)), ctx.ref_compat_sampler)
         ctx.st = None
         return (None, None, None, None, None) + tuple(grads_c) + tuple(grads_f)
@@ -135,8 +142,6 @@ def render_rays_train(renderer, rays_o, rays_d, precision="bf16", ref_compat_sam
         raise L.NerfB200Error("training path implements the plain compositor (enable_ess/enable_ert off)")
     if precision not in ("bf16", "fp32"):
         raise ValueError("precision must be 'bf16' or 'fp32'")
-    if ref_compat_sampler and precision != "fp32":
-        raise L.NerfB200Error("ref_compat_sampler=True needs precision='fp32' (the bf16 backward has no input gradient)")
     params = model_params(renderer.coarse_model) + model_params(renderer.fine_model)
     rays_o = rays_o.to(renderer.device, torch.float32).contiguous()
     rays_d = rays_d.to(renderer.device, torch.float32).contiguous()
@@ -176,8 +181,6 @@ class TrainStep:
         from .parallel import FlatGradAllReduce
         if precision not in ("bf16", "fp32"):
             raise ValueError("precision must be 'bf16' or 'fp32'")
-        if ref_compat_sampler and precision != "fp32":
-            raise L.NerfB200Error("ref_compat_sampler=True needs precision='fp32' (the bf16 backward has no input gradient)")
         self.precision, self.ref_compat_sampler = precision, bool(ref_compat_sampler)
         self.r = renderer
         self.models = (("coarse", renderer.coarse_model), ("fine", renderer.fine_model))
@@ -233,7 +236,7 @@ class TrainStep:
         d0, d1 = rgb0 - target_rgb, rgb - target_rgb
         loss = (d0 * d0).mean() + (d1 * d1).mean()
         scale = 2.0 / d0.numel()
-        _backward_passes(r, st, rays_d, (d0 * scale, None, None), (d1 * scale, None, None), self.ref_compat_sampler,
+        _backward_passes(r, st, rays_o, rays_d, (d0 * scale, None, None), (d1 * scale, None, None), self.ref_compat_sampler,
                          grads_c=self.grad_views["coarse"], grads_f=self.grad_views["fine"])
         self.allreduce()
         self.flat.clamp_(-40.0, 40.0)          # clip_grad_value_(params, 40) on the aliased buffer

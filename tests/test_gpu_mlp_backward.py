@@ -203,3 +203,35 @@ def test_mlp_backward_full_batch_is_additive_over_rays():
         rel = float((g - want).norm() / (want.norm() + 1e-30))
         assert rel < 2e-4, (name, rel)
         assert bool(torch.isfinite(g).all()), name
+
+
+@pytest.mark.parametrize("n,S", [(3, 64), (37, 192), (700, 64)])
+def test_mlp_backward_input_vs_torch(n, S):
+    """nerfb200_mlp_backward_input (reference graph, bf16 path): g_z = d . PE'(x)^T (dpre0 W0 + dpre5 W5[:, :63]) from the
+    dgrad planes the backward left in its workspace, against a float64 torch evaluation on the SAME bf16 planes (so the
+    only differences are the bf16 rounding of the two weight blocks and fp32 accumulation)."""
+    sd, r = _renderer()
+    ro, rd, z = _rays(n, S, seed=3)
+    raw, store = ops.mlp_forward_train(r.packed("fine", "bf16"), ro, rd, z)
+    M = n * S
+    g_raw = torch.randn(M, 4, generator=torch.Generator().manual_seed(11)).to(DEV) * 0.1
+    keep = {}
+    bwd = r.packed_bwd("fine")
+    ops.mlp_backward(bwd, g_raw, store, keep_workspace=keep)
+    g_z = ops.mlp_backward_input(bwd, keep["ws"], ro, rd, z)
+    n_tiles = (M + 127) // 128
+    dacts = keep["ws"][: n_tiles * store.DACT_BLOCKS * 16384]
+    d0 = ops.untile(dacts, M, store.DACT_BLOCKS, *store.DACT_PLANES["dpre0"]).double().cpu()
+    d5 = ops.untile(dacts, M, store.DACT_BLOCKS, *store.DACT_PLANES["dpre5"]).double().cpu()
+    W0 = sd["model_fine.pts_linears.0.weight"].bfloat16().double()
+    W5 = sd["model_fine.pts_linears.5.weight"][:, :63].bfloat16().double()
+    g_pe = d0 @ W0 + d5 @ W5                                                  # [M, 63]
+    x = (ro.cpu()[:, None, :] + rd.cpu()[:, None, :] * z.cpu()[..., None]).reshape(M, 3).double()
+    gx = g_pe[:, :3].clone()
+    for l in range(10):
+        f = 2.0 ** l
+        gx += f * (g_pe[:, 3 + 6 * l: 6 + 6 * l] * torch.cos(f * x) - g_pe[:, 6 + 6 * l: 9 + 6 * l] * torch.sin(f * x))
+    want = (gx * rd.cpu().double()[:, None, :].expand(n, S, 3).reshape(M, 3)).sum(-1).reshape(n, S)
+    err = float((g_z.cpu().double() - want).abs().max() / want.abs().max())
+    print("mlp_backward_input n=%d S=%d: max err / max |g_z| = %.2e" % (n, S, err))
+    assert err <= 2e-4

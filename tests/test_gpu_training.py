@@ -330,3 +330,52 @@ def test_sample_pdf_backward_vs_autograd(per_ray_u):
     # a coarse depth and a sample) permute two entries of g_z_all: allowed on < 2 % of the rays
     assert float(err.median()) <= 1e-4
     assert float((err > 1e-3).float().mean()) <= 0.02
+
+
+def test_bf16_training_with_the_reference_graph():
+    """precision='bf16', ref_compat_sampler=True: the tensor-core training path with the reference's non-detached sampler
+    (nerfb200_mlp_backward_input supplies dL/dz through the MLP input).  Checked against the fp32 path -- itself pinned
+    to the reference's autograd above -- AT IDENTICAL SAMPLE POSITIONS (the fp32 run is handed the bf16 run's coarse
+    weights and merged depths): dL/dz of a random-init field with a 2^9 positional-encoding octave decorrelates under
+    the 1e-3 displacement that bf16 coarse weights cause, which says nothing about the backward.  The fine model and
+    the coarse heads then agree as bf16 operands allow (cosine > 0.99); the coarse trunk, whose gradient arrives almost
+    entirely through sample_pdf, agrees to cosine > 0.85 (see the comment at the assertion)."""
+    sd, net, r, ro, rd, target = _setup(n=192)
+    rod, rdd, tgt = ro.to(DEV), rd.to(DEV), target.to(DEV)
+    names = ["model." + k for k in T._NAMES] + ["model_fine." + k for k in T._NAMES]
+
+    def run(prec, compat, inject=None):
+        st = T._forward_passes(r, rod, rdd, prec, _inject=inject)
+        rgb0, rgb = st["maps"][0], st["maps"][4]
+        scale = 2.0 / rgb0.numel()
+        gc, gf = T._backward_passes(r, st, rod, rdd, ((rgb0 - tgt) * scale, None, None), ((rgb - tgt) * scale, None, None), compat)
+        return st, dict(zip(names, [g.clone() for g in list(gc) + list(gf)]))
+
+    st16, g16 = run("bf16", True)
+    _, g16_detached = run("bf16", False)
+    _, g32 = run("fp32", True, inject={"w_c": st16["w_c"], "z_all": st16["z_all"]})
+    rows = []
+    for name in names:
+        a, b, c = g16[name], g32[name], g16_detached[name]
+        cos = float((a * b).sum() / (a.norm() * b.norm() + 1e-30))
+        rel = float((a - b).norm() / (b.norm() + 1e-30))
+        via = float((a - c).norm() / (a.norm() + 1e-30))
+        rows.append((name, cos, rel, via))
+        print("bf16 compat %-36s cos %.5f rel %.3f   share arriving through the sampler %.3f" % (name, cos, rel, via))
+    for name, cos, rel, via in rows:
+        if name.startswith("model_fine.") or via == 0.0:
+            assert cos > 0.99 and rel < 0.15, (name, cos, rel)       # direct gradients: bf16 operand accuracy
+        elif name.endswith("weight") and "pts_linears" in name:
+            # through the sampler: dL/dz of the fine pass is bf16-accurate (cos 0.997, scripts/debug_gz.py), dL/d(coarse
+            # weights) still 0.992, but the coarse compositor's backward then takes differences of suffix sums of a
+            # g_weights 300x larger than the direct dL/dw, which amplifies the 12 % to 20-50 % (the reference's own
+            # fp32 rounding already shows 1-2 % on these tensors, test_fp32_training_gradients_...[True])
+            assert cos > 0.85, (name, cos, rel)
+    # the sampler path carries most of the coarse trunk's gradient in the reference graph
+    assert dict((x[0], x[3]) for x in rows)["model.pts_linears.7.weight"] > 0.1
+    step = T.TrainStep(r, precision="bf16", ref_compat_sampler=True)
+    net.train()
+    r.perturb = 1
+    losses = [float(step(rod, rdd, tgt)) for _ in range(30)]
+    assert losses[-1] < 0.8 * losses[0], losses[::5]
+    assert all(torch.isfinite(p).all() for p in net.parameters())
