@@ -259,6 +259,17 @@ NERFB200_API int nerfb200_sample_pdf_backward(const float* z_coarse, const float
  * linspace(min_occ,max_occ,S-n_keep), sorted (intended per-ray semantics of :1037-1077). */
 NERFB200_API int nerfb200_ess_resample(const uint8_t* grid, int res, const float* rays_o, const float* rays_d,
                           int n_rays, int n_samples, float* z_vals, int32_t* n_empty, void* stream);
+/* The reference's literal ESS (:1009-1077 with the stride-0 aliasing of :1020,1077): within every block of `chunk`
+ * consecutive rays (the reference calls the sampler once per 2048-ray chunk, :147) each highly-empty ray, in order,
+ * rewrites the ONE shared row -- keep the entries its own occupancy mask (taken at the z_table depths) marks occupied,
+ * refill with linspace(min, max, n_add), sort -- and all rays of the block get the final row.  z_table [n_samples]
+ * (the unperturbed depths), z_vals [n_rays,n_samples] out, scratch: n_rays uint64 (8-byte aligned).  n_samples <= 64. */
+NERFB200_API int nerfb200_ess_resample_compat(const uint8_t* grid, int res, const float* rays_o, const float* rays_d,
+                                 int n_rays, int n_samples, int chunk, const float* z_table, float* z_vals,
+                                 uint64_t* scratch, void* stream);
+/* :1079-1085: stratified jitter of already placed per-ray depths, from each row's own mid-points (the reference
+ * jitters AFTER the ESS resampling); in place, counter-based RNG keyed on (seed, ray, sample). */
+NERFB200_API int nerfb200_jitter_rows(float* z_vals, int n_rays, int n_samples, uint64_t seed, void* stream);
 /* :963-985 as called from :1147-1155: mark cells of samples with weight>1e-4 and
  * relu(sigma_raw)>0.01; points are rays_d*z (ray origin omitted, as in the reference) unless
  * use_origin!=0. */
@@ -354,7 +365,8 @@ typedef struct nerfb200_render_params {
   float ert_threshold;
   float raw_noise_std; /* lego.yaml:23 uses 0; > 0: N(0,1)*std added to sigma_raw before the relu (:310-314) */
   uint64_t seed;
-  /* a8: when non-NULL the coarse z's of every ray are passed through nerfb200_ess_resample */
+  /* a8: when non-NULL the coarse z's of every ray are passed through nerfb200_ess_resample (unperturbed depths are
+   * tested and resampled first, the stratified jitter is applied afterwards from each row's mid-points, :1079-1085) */
   const uint8_t* occupancy_grid; /* uint8 [grid_res]^3, device */
   int grid_res;
   /* ess_skip = 0: reference semantics (resample highly-empty rays, nerfb200_ess_resample).
@@ -370,6 +382,10 @@ typedef struct nerfb200_render_params {
   int cull_rays;
   float cull_lo[3];
   float cull_hi[3];
+  /* ess_skip = 0 only.  0: per-ray resampling (the intended semantics of :1037-1077).  1: the reference's LITERAL
+   * behaviour -- z_vals is a stride-0 expand()ed view (:1020), so every highly-empty ray rewrites the one row all rays
+   * of a compat_chunk-ray call share (nerfb200_ess_resample_compat); needs n_samples <= 64. */
+  int ess_ref_compat;
 } nerfb200_render_params;
 
 /* maps for one pass: rgb [n,3], disp/acc/depth [n] */

@@ -83,6 +83,7 @@ static bool mode_exact(int m) { return m == NERFB200_MODE_FP32 || m == NERFB200_
 static int chunk_rays(const nerfb200_render_params* p) {
   if (const char* e = getenv("NERFB200_CHUNK_RAYS")) { int c = atoi(e); if (c >= 2048 && c % 2048 == 0) return c; }   // tuning experiments
   if (p->occupancy_grid && p->ess_skip) return kChunkRaysSparse;
+  if (p->occupancy_grid && p->ess_ref_compat) return kChunkRays;   // the shared-row blocks (compat_chunk rays) must tile the chunk
   // The literal ERT_COMPAT compositor groups rays in compat_chunk blocks, which must tile the chunk.
   if ((p->variant & ~NERFB200_COMPOSITE_FAST_MATH) == NERFB200_COMPOSITE_ERT_COMPAT || !mode_tensor(mode_fine(p->mode)) ||
       !mode_tensor(mode_coarse(p->mode))) return kChunkRays;
@@ -155,6 +156,9 @@ static int check_params(const nerfb200_render_params* p) {
                "render: unknown composite variant %d", p->variant);
   NB_CHECK_ARG((p->variant & ~NERFB200_COMPOSITE_FAST_MATH) != NERFB200_COMPOSITE_ERT_COMPAT || (p->compat_chunk > 0 && kChunkRays % p->compat_chunk == 0),
                "render: compat_chunk=%d must divide %d", p->compat_chunk, kChunkRays);
+  NB_CHECK_ARG(!(p->occupancy_grid && p->ess_ref_compat && !p->ess_skip) ||
+                   (p->compat_chunk > 0 && kChunkRays % p->compat_chunk == 0 && p->n_samples <= 64),
+               "render: ess_ref_compat needs n_samples <= 64 and a compat_chunk that divides %d", kChunkRays);
   static_assert(kChunkRaysSparse % kChunkRays == 0, "chunk sizes");
   NB_CHECK_ARG(p->raw_noise_std >= 0.f, "render: raw_noise_std=%g must be >= 0", (double)p->raw_noise_std);
   NB_CHECK_ARG(!(p->raw_noise_std > 0.f && p->occupancy_grid && p->ess_skip),
@@ -338,10 +342,19 @@ static int render_rays_impl(const void* packed_coarse, const void* packed_fine, 
     const float* rd = rays_d + (size_t)r0 * 3;
     int e;
     // per-ray jitter is keyed on the ray index inside the call: offset the seed per chunk
-    if ((e = nerfb200_sample_coarse(z_table, n, S, p->perturb, p->seed + (uint64_t)r0 * 0x9E3779B97F4A7C15ull, ws.z_coarse, stream))) return e;
     const bool sparse = p->occupancy_grid && p->ess_skip;
-    if (p->occupancy_grid && !sparse &&
-        (e = nerfb200_ess_resample(p->occupancy_grid, p->grid_res, ro, rd, n, S, ws.z_coarse, nullptr, stream))) return e;
+    const bool resample = p->occupancy_grid && !sparse;
+    const uint64_t jitter_seed = p->seed + (uint64_t)r0 * 0x9E3779B97F4A7C15ull;
+    // reference order (:1009-1085): occupancy is tested at the UNPERTURBED depths, highly-empty rays are resampled, and
+    // only then is the stratified jitter applied, from each row's own mid-points
+    if ((e = nerfb200_sample_coarse(z_table, n, S, resample ? 0 : p->perturb, jitter_seed, ws.z_coarse, stream))) return e;
+    if (resample) {
+      if (p->ess_ref_compat) {
+        if ((e = nerfb200_ess_resample_compat(p->occupancy_grid, p->grid_res, ro, rd, n, S, p->compat_chunk, z_table, ws.z_coarse,
+                                              reinterpret_cast<uint64_t*>(ws.row_ids), stream))) return e;
+      } else if ((e = nerfb200_ess_resample(p->occupancy_grid, p->grid_res, ro, rd, n, S, ws.z_coarse, nullptr, stream))) return e;
+      if (p->perturb && (e = nerfb200_jitter_rows(ws.z_coarse, n, S, jitter_seed, stream))) return e;
+    }
     // sparse: the compaction leaves one keep bit per row; the MLP writes only the listed rows and the masked
     // compositor never touches the others (no zero fill of raw, no 16 B read per skipped row)
     // (the literal ERT_COMPAT compositor has no masked form: that combination keeps the zero fill)

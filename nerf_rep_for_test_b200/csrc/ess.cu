@@ -83,6 +83,116 @@ ess_resample_kernel(const uint8_t* __restrict__ grid, int res, const float* __re
   }
 }
 
+// ---- the reference's LITERAL ESS (volume_renderer.py:1009-1077): z_vals is an expand()ed stride-0 view (:1020), so
+// `z_vals[i] = combined_z_vals` (:1077) writes the ONE row every ray of the call shares.  Each highly-empty ray i, in
+// order, reads the current shared row, keeps the entries where ITS occupancy mask -- evaluated up front at the
+// unmodified linspace depths (:1024-1028) -- says "occupied", refills with linspace(min, max, n_add), sorts, and writes
+// the row back; all rays of the call (a 2048-ray chunk, :147) end up with the row the last such ray left.
+// Pass 1 (parallel): per ray a 64-bit EMPTY mask at the table depths (bit 63 of word... see below) + the flag.
+// Pass 2 (one warp per chunk, sequential over its flagged rays): the row lives in shared memory.
+// S <= 64 (the mask is one 64-bit word; the reference's N_samples is 64).
+__global__ void __launch_bounds__(256)
+ess_masks_kernel(const uint8_t* __restrict__ grid, int res, const float* __restrict__ rays_o,
+                 const float* __restrict__ rays_d, const float* __restrict__ z_table, int n_rays, int S,
+                 unsigned long long* __restrict__ masks) {
+  int ray = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ray >= n_rays) return;
+  float o[3], d[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { o[c] = rays_o[(size_t)ray * 3 + c]; d[c] = rays_d[(size_t)ray * 3 + c]; }
+  unsigned long long empty = 0ull;
+  for (int i = 0; i < S; ++i) {
+    const float z = z_table[i];
+    int gx = grid_index(__fadd_rn(o[0], __fmul_rn(d[0], z)), res);
+    int gy = grid_index(__fadd_rn(o[1], __fmul_rn(d[1], z)), res);
+    int gz = grid_index(__fadd_rn(o[2], __fmul_rn(d[2], z)), res);
+    if (grid[((size_t)gx * res + gy) * res + gz] == 0) empty |= 1ull << i;
+  }
+  masks[ray] = empty;
+}
+
+__global__ void __launch_bounds__(32)
+ess_resample_compat_kernel(const unsigned long long* __restrict__ masks, const float* __restrict__ z_table, int n_rays,
+                           int S, int chunk, float* __restrict__ z_vals) {
+  __shared__ float row[64], keep[64], next[64];
+  const int lane = threadIdx.x;
+  const int r0 = blockIdx.x * chunk;
+  const int r1 = min(n_rays, r0 + chunk);
+  for (int i = lane; i < S; i += 32) row[i] = z_table[i];
+  __syncwarp();
+  const unsigned long long valid = S >= 64 ? ~0ull : ((1ull << S) - 1ull);
+  for (int base = r0; base < r1; base += 32) {
+    // 32 rays' masks at a time; the flagged ones are then processed strictly in ray order
+    const int ray = base + lane;
+    unsigned long long m = ray < r1 ? masks[ray] : 0ull;
+    const bool flag = ray < r1 && ((float)__popcll(m & valid) / (float)S > 0.5f) && (~m & valid) != 0ull;   // :1031-1033, :1045
+    unsigned todo = __ballot_sync(0xffffffffu, flag);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const unsigned long long em = __shfl_sync(0xffffffffu, m, src);
+      const unsigned long long occ = ~em & valid;
+      const int n_keep = __popcll(occ), n_add = S - n_keep;
+      // ordered compaction of the occupied entries of the CURRENT row
+      for (int i = lane; i < S; i += 32)
+        if ((occ >> i) & 1ull) keep[__popcll(occ & ((1ull << i) - 1ull))] = row[i];
+      __syncwarp();
+      const float lo = keep[0], hi = keep[n_keep - 1];      // the row is ascending
+      const float step = n_add > 1 ? __fdiv_rn(__fsub_rn(hi, lo), (float)(n_add - 1)) : 0.f;
+      auto added = [&](int j) {   // torch.linspace(lo, hi, n_add), as in ess_resample_kernel
+        if (n_add == 1) return lo;
+        return (j < n_add / 2) ? __fadd_rn(lo, __fmul_rn(step, (float)j)) : __fsub_rn(hi, __fmul_rn(step, (float)(n_add - 1 - j)));
+      };
+      for (int i = lane; i < n_keep; i += 32) {
+        const float x = keep[i];
+        int l = 0, h = n_add;
+        while (l < h) { int mid = (l + h) >> 1; if (added(mid) < x) l = mid + 1; else h = mid; }
+        next[i + l] = x;
+      }
+      for (int j = lane; j < n_add; j += 32) {
+        const float x = added(j);
+        int l = 0, h = n_keep;
+        while (l < h) { int mid = (l + h) >> 1; if (keep[mid] <= x) l = mid + 1; else h = mid; }
+        next[j + l] = x;
+      }
+      __syncwarp();
+      for (int i = lane; i < S; i += 32) row[i] = next[i];
+      __syncwarp();
+    }
+  }
+  // every ray of the chunk gets the shared row
+  for (long long e = lane; e < (long long)(r1 - r0) * S; e += 32) z_vals[(size_t)r0 * S + e] = row[e % S];
+}
+
+// stratified jitter of ALREADY PLACED per-ray depths (volume_renderer.py:1079-1085: the reference jitters after the ESS
+// resampling, from each row's own mid-points): z_i <- lower_i + (upper_i - lower_i) u,  u keyed on (seed, ray, i)
+constexpr int kJitWarps = 8;
+__global__ void __launch_bounds__(kJitWarps * 32)
+jitter_rows_kernel(float* __restrict__ z_vals, int n_rays, int S, uint64_t seed) {
+  const int lane = threadIdx.x & 31;
+  const int ray = blockIdx.x * kJitWarps + (threadIdx.x >> 5);
+  if (ray >= n_rays) return;
+  float* z = z_vals + (size_t)ray * S;
+  float out[kEssMaxS / 32];
+#pragma unroll
+  for (int k = 0; k < kEssMaxS / 32; ++k) {
+    const int i = k * 32 + lane;
+    out[k] = 0.f;
+    if (i < S) {
+      const float zi = z[i];
+      const float lower = i == 0 ? zi : __fmul_rn(0.5f, __fadd_rn(zi, z[i - 1]));
+      const float upper = i == S - 1 ? zi : __fmul_rn(0.5f, __fadd_rn(z[i + 1], zi));
+      out[k] = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), uniform01(seed, (uint32_t)ray, (uint32_t)i)));
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < kEssMaxS / 32; ++k) {
+    const int i = k * 32 + lane;
+    if (i < S) z[i] = out[k];
+  }
+}
+
 __global__ void ess_update_kernel(uint8_t* __restrict__ grid, int res, const float* __restrict__ rays_o,
                                   const float* __restrict__ rays_d, const float* __restrict__ z_vals,
                                   const float* __restrict__ raw, const float* __restrict__ weights,
@@ -365,5 +475,32 @@ extern "C" int nerfb200_ess_update(uint8_t* grid, int res, const float* rays_o, 
   ess_update_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(grid, res, rays_o, rays_d, z_vals, raw,
                                                                             weights, total, n_samples, use_origin);
   NB_LAUNCH_OK("ess_update_kernel");
+  return 0;
+}
+
+extern "C" int nerfb200_ess_resample_compat(const uint8_t* grid, int res, const float* rays_o, const float* rays_d,
+                                            int n_rays, int n_samples, int chunk, const float* z_table, float* z_vals,
+                                            uint64_t* scratch, void* stream) {
+  NB_CHECK_ARG(n_rays <= 0 || (grid && rays_o && rays_d && z_table && z_vals && scratch), "ess_resample_compat: null pointer");
+  NB_CHECK_ARG(res >= 1 && res <= 1024, "ess_resample_compat: bad grid resolution %d", res);
+  NB_CHECK_ARG(n_samples >= 1 && n_samples <= 64, "ess_resample_compat: n_samples=%d out of range [1,64]", n_samples);
+  NB_CHECK_ARG(n_rays >= 0 && chunk >= 1, "ess_resample_compat: bad sizes");
+  NB_CHECK_ARG(((uintptr_t)scratch & 7) == 0, "ess_resample_compat: scratch must be 8-byte aligned");
+  if (n_rays == 0) return 0;
+  ess_masks_kernel<<<ceil_div(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(grid, res, rays_o, rays_d, z_table, n_rays, n_samples,
+                                                                            reinterpret_cast<unsigned long long*>(scratch));
+  NB_LAUNCH_OK("ess_masks_kernel");
+  ess_resample_compat_kernel<<<ceil_div(n_rays, chunk), 32, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const unsigned long long*>(scratch), z_table, n_rays, n_samples, chunk, z_vals);
+  NB_LAUNCH_OK("ess_resample_compat_kernel");
+  return 0;
+}
+
+extern "C" int nerfb200_jitter_rows(float* z_vals, int n_rays, int n_samples, uint64_t seed, void* stream) {
+  NB_CHECK_ARG(n_rays <= 0 || z_vals, "jitter_rows: null pointer");
+  NB_CHECK_ARG(n_rays >= 0 && n_samples >= 1 && n_samples <= kEssMaxS, "jitter_rows: bad sizes n_rays=%d S=%d", n_rays, n_samples);
+  if (n_rays == 0) return 0;
+  jitter_rows_kernel<<<ceil_div(n_rays, kJitWarps), kJitWarps * 32, 0, (cudaStream_t)stream>>>(z_vals, n_rays, n_samples, seed);
+  NB_LAUNCH_OK("jitter_rows_kernel");
   return 0;
 }

@@ -7,7 +7,8 @@ f2  psnr / mse_to_psnr   -- the evaluator's image metric on the device (src/eval
                             computes it on the CPU after a synchronising copy).
 f3  save_model / load_model / load_network -- the reference's checkpoint format (src/utils/net_utils.py:288-380):
                             <dir>/{epoch}.pth or latest.pth holding {'net','optim','scheduler','recorder','epoch'},
-                            at most five numbered files kept.
+                            at most five numbered files kept.  Pass the TrainStep itself as `optim`: its state_dict() /
+                            load_state_dict() speak the reference optimizer's per-parameter layout (optimizer.py:14-19).
 f4  build_occupancy_grid -- a working version of _populate_occupancy_grid_kilonerf_method
                             (volume_renderer.py:875-961: 3x3x3 density probes per cell, occupied if any > 0.01),
                             as batched density queries through the tcgen05 MLP kernel.
@@ -111,23 +112,42 @@ def query_density(renderer, points, which="coarse", batch=1 << 21):
     return out
 
 
-def build_occupancy_grid(renderer, density_threshold=0.01, res=None, bbox_min=(-2.0, -2.0, -2.0), bbox_max=(2.0, 2.0, 2.0)):
-    """Occupancy grid bool [R,R,R] (indexed [x,y,z] like _is_empty_space, volume_renderer.py:992-1007): a cell is
-    occupied when any of its 3x3x3 probes at offsets {0, 1/2, 1} of the cell has relu(sigma) > threshold
-    (volume_renderer.py:875-961).  Neighbouring cells share their face probes, so the (2R+1)^3 lattice is
-    evaluated once and max-pooled 3x3x3 with stride 2 -- the same booleans with 3.4x fewer MLP rows."""
-    res = int(res or renderer.occupancy_grid_resolution)
-    dev = renderer.device
-    lo = torch.tensor(bbox_min, device=dev, dtype=torch.float32)
-    hi = torch.tensor(bbox_max, device=dev, dtype=torch.float32)
-    m = 2 * res + 1
-    ax = [lo[k] + (hi[k] - lo[k]) / res * (torch.arange(m, device=dev, dtype=torch.float32) * 0.5) for k in range(3)]
-    dens = torch.empty((m, m, m), device=dev)
+def occupancy_from_density(density_fn, res, density_threshold=0.01, bbox_min=(-2.0, -2.0, -2.0), bbox_max=(2.0, 2.0, 2.0),
+                           device="cpu"):
+    """Occupancy grid bool [R,R,R] in the geometry of the LOOKUP (volume_renderer.py:992-1007 and ess.cu grid_index map
+    p to cell clamp(int((p - lo) / (hi - lo) * (R - 1)), 0, R - 1)): cell i < R-1 covers [lo + i h, lo + (i+1) h) with
+    h = (hi - lo) / (R - 1), and cell R-1 is only reached by p >= hi (and by the clamp).  A cell is occupied when any of
+    its 3x3x3 probes at offsets {0, 1/2, 1} of the cell has density > threshold (the 27-probe rule of :875-961);
+    neighbouring cells share their face probes, so the (2R-1)^3 lattice is evaluated once and max-pooled 3x3x3 with
+    stride 2.  The boundary cell R-1 copies its neighbour R-2 (its own extent is the face p = hi).
+    The reference builds cell i from [lo + i (hi-lo)/R, ...) (:905-915), one cell size off the lookup at the far end of
+    the box; with ess_mode='skip' an "empty" lookup forces density 0, so the builder has to agree with the lookup.
+    density_fn(points [n,3]) -> [n] density."""
+    res = int(res)
+    lo = torch.tensor(bbox_min, device=device, dtype=torch.float32)
+    hi = torch.tensor(bbox_max, device=device, dtype=torch.float32)
+    m = 2 * (res - 1) + 1
+    ax = [lo[k] + (hi[k] - lo[k]) / (res - 1) * (torch.arange(m, device=device, dtype=torch.float32) * 0.5) for k in range(3)]
+    dens = torch.empty((m, m, m), device=device)
     for ix in range(m):      # one x-slab at a time bounds the temporary to m^2 points
         pts = torch.stack(torch.meshgrid(ax[0][ix:ix + 1], ax[1], ax[2], indexing="ij"), -1).reshape(-1, 3)
-        dens[ix] = query_density(renderer, pts).view(m, m)
-    pooled = torch.nn.functional.max_pool3d(dens[None, None], kernel_size=3, stride=2)[0, 0]
-    return pooled > density_threshold
+        dens[ix] = density_fn(pts).view(m, m)
+    pooled = torch.nn.functional.max_pool3d(dens[None, None], kernel_size=3, stride=2)[0, 0] > density_threshold   # [R-1]^3
+    grid = torch.zeros((res, res, res), dtype=torch.bool, device=device)
+    grid[:res - 1, :res - 1, :res - 1] = pooled
+    grid[res - 1, :, :] = grid[res - 2, :, :]
+    grid[:, res - 1, :] = grid[:, res - 2, :]
+    grid[:, :, res - 1] = grid[:, :, res - 2]
+    return grid
+
+
+def build_occupancy_grid(renderer, density_threshold=0.01, res=None, bbox_min=(-2.0, -2.0, -2.0), bbox_max=(2.0, 2.0, 2.0)):
+    """occupancy_from_density with relu(sigma) of the coarse network evaluated by the tensor-core MLP kernel; indexed
+    [x,y,z] like _is_empty_space.  Safe to use with ess_mode='skip': a point whose cell the lookup calls empty lies in a
+    cell none of whose 27 probes exceeded the threshold."""
+    res = int(res or renderer.occupancy_grid_resolution)
+    return occupancy_from_density(lambda pts: query_density(renderer, pts), res, density_threshold, bbox_min, bbox_max,
+                                  device=renderer.device)
 
 
 # ----------------------------------------------------------------------------------------------- f1
@@ -137,7 +157,7 @@ class RayBatchTrainer:
     (alpha is composited onto white when white_bkgd, as blender.py:101-117 does), poses [V,4,4], intrinsics [3,3]."""
 
     def __init__(self, renderer, images, poses, intrinsics, n_rays=1024, precrop_iters=0, precrop_frac=0.5, lr=5e-4,
-                 lr_decay_steps=0, lr_decay_gamma=0.1, seed=0):
+                 lr_decay_steps=0, lr_decay_gamma=0.1, seed=0, precision="bf16", ref_compat_sampler=False):
         from .training import TrainStep
         self.r = renderer
         dev = renderer.device
@@ -150,7 +170,7 @@ class RayBatchTrainer:
         K = torch.as_tensor(intrinsics, dtype=torch.float32).reshape(3, 3).to(dev)
         self.rays = [ops.raygen(torch.as_tensor(p, dtype=torch.float32).to(dev), K, self.H, self.W) for p in poses]
         self.n_rays, self.precrop_iters, self.precrop_frac = n_rays, precrop_iters, precrop_frac
-        self.step_fn = TrainStep(renderer, lr=lr)
+        self.step_fn = TrainStep(renderer, lr=lr, precision=precision, ref_compat_sampler=ref_compat_sampler)
         self.lr0, self.decay_steps, self.gamma = lr, lr_decay_steps, lr_decay_gamma
         self.gen = torch.Generator(device=dev).manual_seed(seed)
         self.iteration = 0
@@ -176,8 +196,7 @@ class RayBatchTrainer:
         target = self.images[v].reshape(-1, 3)[pix]
         if self.decay_steps:
             lr = self.lr0 * self.gamma ** (self.iteration / self.decay_steps)
-            for g in self.step_fn.opt.param_groups:
-                g["lr"] = lr
+            self.step_fn.set_lr(lr)
         loss = self.step_fn(ro[pix].contiguous(), rd[pix].contiguous(), target.contiguous())
         self.iteration += 1
         return loss

@@ -45,7 +45,8 @@ class RenderParams(C.Structure):
                 ("variant", C.c_int), ("white_bkgd", C.c_int), ("perturb", C.c_int),
                 ("u_per_ray", C.c_int), ("compat_chunk", C.c_int), ("ert_threshold", C.c_float),
                 ("raw_noise_std", C.c_float), ("seed", C.c_uint64), ("occupancy_grid", _vp), ("grid_res", C.c_int), ("ess_skip", C.c_int),
-                ("eval_counts", _vp), ("cull_rays", C.c_int), ("cull_lo", C.c_float * 3), ("cull_hi", C.c_float * 3)]
+                ("eval_counts", _vp), ("cull_rays", C.c_int), ("cull_lo", C.c_float * 3), ("cull_hi", C.c_float * 3),
+                ("ess_ref_compat", C.c_int)]
 
 
 class KiloCamera(C.Structure):
@@ -108,6 +109,8 @@ SIGNATURES = {
     "nerfb200_sample_pdf_merge": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp,
                                             _vp, _vp]),
     "nerfb200_ess_resample": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "nerfb200_ess_resample_compat": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    "nerfb200_jitter_rows": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint64, _vp]),
     "nerfb200_ess_update": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     "nerfb200_ess_compact": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "nerfb200_mlp_forward_sparse": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),

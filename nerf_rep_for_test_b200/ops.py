@@ -332,6 +332,26 @@ def sample_pdf_merge(z_coarse, weights, u, want_aux=True):
     return z_all, zs, inds, cdf
 
 
+def ess_resample_compat(grid_u8, rays_o, rays_d, z_table, chunk=2048):
+    """The reference's literal ESS resampling (one shared row per `chunk` rays): z_vals [n,S]."""
+    rays_o, rays_d, z_table = _f(rays_o), _f(rays_d), _f(z_table)
+    n, S = rays_o.shape[0], z_table.numel()
+    z = torch.empty((n, S), device=rays_o.device)
+    scratch = torch.empty(max(n, 1), dtype=torch.int64, device=rays_o.device)
+    L.check(L.load().nerfb200_ess_resample_compat(L.dev(grid_u8, torch.uint8), grid_u8.shape[0], L.dev(rays_o), L.dev(rays_d),
+                                                 n, S, chunk, L.dev(z_table), L.dev(z), L.dev(scratch), L.stream_ptr()),
+            "ess_resample_compat")
+    return z
+
+
+def jitter_rows(z_vals, seed=0):
+    """Stratified jitter of placed per-ray depths from each row's own mid-points (:1079-1085); returns a new tensor."""
+    z = _f(z_vals).clone()
+    n, S = z.shape
+    L.check(L.load().nerfb200_jitter_rows(L.dev(z), n, S, seed, L.stream_ptr()), "jitter_rows")
+    return z
+
+
 def ess_resample(grid_u8, rays_o, rays_d, z_vals):
     rays_o, rays_d = _f(rays_o), _f(rays_d)
     z = _f(z_vals).clone()

@@ -40,6 +40,27 @@ class FlatGradAllReduce:
         if self.flat.numel() != n:
             raise ValueError("flat gradient buffer has %d elements, parameters have %d" % (self.flat.numel(), n))
 
+    def start(self, lo, hi):
+        """Begin the all-reduce of flat[lo:hi] (aliased buffer only) asynchronously: with NCCL the collective runs on
+        the backend's own stream behind the work enqueued so far, so kernels launched after this call -- the coarse
+        network's backward while the fine network's gradients travel -- overlap with it.  Returns a handle for finish()."""
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        if world == 1 or hi <= lo:
+            return None
+        if not self.aliased:
+            raise RuntimeError("FlatGradAllReduce.start needs the aliased flat buffer")
+        return dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, async_op=True)
+
+    def finish(self, handles):
+        """Wait for the started pieces (the current stream waits, not the host) and turn the sums into means."""
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        if world == 1:
+            return
+        for h in handles:
+            if h is not None:
+                h.wait()
+        self.flat.mul_(1.0 / world)
+
     def __call__(self):
         world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         if world == 1:

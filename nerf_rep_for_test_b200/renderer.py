@@ -125,13 +125,16 @@ class Renderer(PathRenderingMixin):
              # fp16 operands instead of bf16 in the same single-pass kernel (11 significand bits, saturating at 65504)
              "fp16": (L.MODE_FP16, L.MODE_FP16), "mixed16": (L.MODE_FP32_TC, L.MODE_FP16)}
 
-    def __init__(self, net, cfg=None, mode=None, ref_compat=True):
+    def __init__(self, net, cfg=None, mode=None, ref_compat=True, ess_ref_compat=False):
         """net: a Network with `.model`, `.model_fine` (reference network.py or ours).
 
         cfg: RenderConfig, a scaffold yacs cfg, or None (then `src.config.cfg` when the scaffold is
         importable, else lego.yaml defaults).  mode: 'bf16' (tcgen05 performance mode), 'fp32tc' (fp32-accurate
         tensor-core mode), 'mixed' (coarse fp32tc + fine bf16) or 'fp32' (CUDA-core parity mode).
         ref_compat: reproduce the reference's ERT chunk quirk (:1115-1123).
+        ess_ref_compat: reproduce the reference's literal ESS resampling, in which every highly-empty ray rewrites the
+        one row of depths that all rays of a 2048-ray chunk share (stride-0 expand(), :1020,1077); default False = the
+        intended per-ray resampling.  The two agree whenever no ray is highly empty (lego poses, default grid).
         """
         self.lib = L.load()
         if not torch.cuda.is_available():
@@ -172,6 +175,7 @@ class Renderer(PathRenderingMixin):
         if self.mode not in self.MODES:
             raise ValueError("mode must be one of %s" % sorted(self.MODES))
         self.ref_compat = bool(ref_compat)
+        self.ess_ref_compat = bool(ess_ref_compat)
         # "resample" = the reference's ESS (:1009-1087); "skip" = samples in empty cells (and, with ERT,
         # fine samples behind the coarse termination depth) are never sent through the MLP
         self.ess_mode = "resample"
@@ -304,6 +308,7 @@ class Renderer(PathRenderingMixin):
             self._grid_u8 = self.occupancy_grid.to(torch.uint8).contiguous()
             p.occupancy_grid = self._grid_u8.data_ptr()
             p.grid_res = self.occupancy_grid.shape[0]
+            p.ess_ref_compat = int(self.ess_ref_compat and self.ess_mode != "skip")
             if self.ess_mode == "skip":
                 if self.mode == "fp32":
                     raise L.NerfB200Error("ess_mode='skip' needs a tensor-core mode (sparse MLP launch)")

@@ -93,7 +93,8 @@ def _mlp_backward(r, which, precision, g_raw, store, rays_o, rays_d, z, grads, w
     return ops.mlp_backward_fp32(_tensors(model), g_raw, store, rays_d, n, S, grads=grads, want_g_z=want_g_z)
 
 
-def _backward_passes(r, st, rays_o, rays_d, g_coarse, g_fine, ref_compat_sampler, grads_c=None, grads_f=None):
+def _backward_passes(r, st, rays_o, rays_d, g_coarse, g_fine, ref_compat_sampler, grads_c=None, grads_f=None,
+                     after_fine=None):
     """g_coarse / g_fine: (g_rgb, g_acc, g_depth) of the two passes (entries may be None).  Fine pass first: with the
     reference's non-detached sampler its dL/dz feeds the coarse compositor through dL/d(coarse weights)."""
     precision = st["precision"]
@@ -107,6 +108,8 @@ def _backward_passes(r, st, rays_o, rays_d, g_coarse, g_fine, ref_compat_sampler
     else:
         g_raw_f = ops.composite_backward(st["raw_f"], st["z_all"], rays_d, *g_fine, None, white_bkgd=r.white_bkgd)
         grads_f, _ = _mlp_backward(r, "fine", precision, g_raw_f, st["store_f"], rays_o, rays_d, st["z_all"], grads_f)
+    if after_fine is not None:
+        after_fine()        # the fine model's gradients are final: their all-reduce overlaps the coarse backward
     g_raw_c = ops.composite_backward(st["raw_c"], st["z_c"], rays_d, *g_coarse, g_w_c, white_bkgd=r.white_bkgd)
     grads_c, _ = _mlp_backward(r, "coarse", precision, g_raw_c, st["store_c"], rays_o, rays_d, st["z_c"], grads_c)
     return grads_c, grads_f
@@ -156,6 +159,56 @@ def nerf_loss(out, target_rgb):
     return torch.nn.functional.mse_loss(out["rgb_map_0"], target_rgb) + torch.nn.functional.mse_loss(out["rgb_map"], target_rgb)
 
 
+def split_adam_state(flat_sd, named_params, offsets):
+    """torch.optim.Adam.state_dict() of an optimizer over ONE flat parameter -> the layout the reference's optimizer
+    writes (src/train/optimizer.py:14-19: one param group per named parameter, in net.named_parameters() order), so that
+    net_utils.save_model / load_model (:288-343) and a stock torch.optim.Adam over those groups read it.
+    offsets: {id(param): offset into the flat tensor}."""
+    g0 = {k: (float(v) if torch.is_tensor(v) and v.numel() == 1 else v) for k, v in flat_sd["param_groups"][0].items()
+          if k != "params"}
+    fs = flat_sd["state"].get(0, {})
+    state, groups = {}, []
+    for i, (name, p) in enumerate(named_params):
+        off, n = offsets[id(p)], p.numel()
+        if fs:
+            state[i] = {"step": fs["step"].detach().clone().cpu() if torch.is_tensor(fs["step"]) else torch.tensor(float(fs["step"])),
+                        "exp_avg": fs["exp_avg"][off:off + n].view_as(p).clone(),
+                        "exp_avg_sq": fs["exp_avg_sq"][off:off + n].view_as(p).clone()}
+        groups.append(dict(g0, params=[i]))
+    return {"state": state, "param_groups": groups}
+
+
+def merge_adam_state(sd, named_params, offsets, n_total, like):
+    """Inverse of split_adam_state (also accepts the flat single-tensor layout unchanged): per-parameter Adam state in
+    net.named_parameters() order -> state_dict of an Adam over one flat tensor of n_total elements (`like`: a tensor
+    giving device / dtype of the moments)."""
+    groups = sd["param_groups"]
+    named = list(named_params)
+    if len(groups) == 1 and len(groups[0]["params"]) == 1 and len(named) != 1:
+        return sd                                               # already the flat layout
+    order = [i for g in groups for i in g["params"]]
+    if len(order) != len(named):
+        raise ValueError("optimizer state has %d parameters, the network has %d" % (len(order), len(named)))
+    g0 = {k: v for k, v in groups[0].items() if k != "params"}
+    state = {}
+    if sd["state"]:
+        ea = torch.zeros(n_total, dtype=like.dtype, device=like.device)
+        es = torch.zeros(n_total, dtype=like.dtype, device=like.device)
+        step = None
+        for idx, (name, p) in zip(order, named):
+            st = sd["state"].get(idx)
+            if st is None:
+                continue
+            off, n = offsets[id(p)], p.numel()
+            if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                raise ValueError("optimizer state of %s has shape %s, parameter has %s" % (name, tuple(st["exp_avg"].shape), tuple(p.shape)))
+            ea[off:off + n] = st["exp_avg"].reshape(-1).to(ea)
+            es[off:off + n] = st["exp_avg_sq"].reshape(-1).to(es)
+            step = st["step"] if step is None else step
+        state[0] = {"step": step if torch.is_tensor(step) else torch.tensor(float(step)), "exp_avg": ea, "exp_avg_sq": es}
+    return {"state": state, "param_groups": [dict(g0, params=[0])]}
+
+
 class TrainStep:
     """One data-parallel training step: fwd + bwd + flat-gradient all-reduce + clip_grad_value_(40)
     (trainer.py:59) + Adam(lr 5e-4, eps 1e-8) (src/train/optimizer.py:8-28).
@@ -202,6 +255,7 @@ class TrainStep:
                 p.grad = self.flat[off:off + n].view_as(p)
                 off += n
         self.flat_param.grad = self.flat
+        self.n_coarse = sum(p.numel() for p in model_params(renderer.coarse_model))
         self.grad_views = {name: [p.grad for p in model_params(m)] for name, m in self.models}
         world = torch.distributed.get_world_size() if (torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
         self.use_graph = bool(graph) and world == 1
@@ -209,6 +263,33 @@ class TrainStep:
         self.opt = torch.optim.Adam([self.flat_param], lr=lr_arg, eps=1e-8, fused=True, capturable=self.use_graph)
         self.allreduce = FlatGradAllReduce(self.params, flat=self.flat)
         self._graph, self._static, self._loss, self._warm = None, None, None, 0
+
+    # ---- checkpoint interface of the optimizer the reference hands to net_utils.save_model / load_model ------------
+    def _offsets(self):
+        off, out = 0, {}
+        for p in self.params:
+            out[id(p)] = off
+            off += p.numel()
+        return out
+
+    def state_dict(self):
+        """Adam state in the REFERENCE's layout (one param group per named parameter, net.named_parameters() order,
+        src/train/optimizer.py:14-19): pass the TrainStep itself as `optim` to extras.save_model / load_model."""
+        return split_adam_state(self.opt.state_dict(), list(self.r.net.named_parameters()), self._offsets())
+
+    def load_state_dict(self, sd):
+        """Accepts a checkpoint's `optim` entry written by the reference (per-parameter groups) or by an older
+        TrainStep.opt (one flat tensor)."""
+        flat = merge_adam_state(sd, list(self.r.net.named_parameters()), self._offsets(), self.flat_param.numel(), self.flat_param.data)
+        lr = self.opt.param_groups[0]["lr"]
+        self.opt.load_state_dict(flat)
+        if torch.is_tensor(lr):                                 # capturable / graph mode keeps lr in a device tensor
+            lr.fill_(float(self.opt.param_groups[0]["lr"]))
+            self.opt.param_groups[0]["lr"] = lr
+
+    @property
+    def param_groups(self):
+        return self.opt.param_groups
 
     def set_lr(self, lr):
         for g in self.opt.param_groups:
@@ -236,9 +317,14 @@ class TrainStep:
         d0, d1 = rgb0 - target_rgb, rgb - target_rgb
         loss = (d0 * d0).mean() + (d1 * d1).mean()
         scale = 2.0 / d0.numel()
+        # gradient all-reduce in two pieces of the flat buffer (coarse parameters first, then fine): the fine piece is
+        # started as soon as the fine backward is enqueued and overlaps the coarse network's backward
+        handles = []
         _backward_passes(r, st, rays_o, rays_d, (d0 * scale, None, None), (d1 * scale, None, None), self.ref_compat_sampler,
-                         grads_c=self.grad_views["coarse"], grads_f=self.grad_views["fine"])
-        self.allreduce()
+                         grads_c=self.grad_views["coarse"], grads_f=self.grad_views["fine"],
+                         after_fine=lambda: handles.append(self.allreduce.start(self.n_coarse, self.flat.numel())))
+        handles.append(self.allreduce.start(0, self.n_coarse))
+        self.allreduce.finish(handles)
         self.flat.clamp_(-40.0, 40.0)          # clip_grad_value_(params, 40) on the aliased buffer
         self.opt.step()
         r.invalidate_weights()

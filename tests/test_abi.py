@@ -121,3 +121,24 @@ def test_ctypes_structs_match_the_c_header_field_by_field(tmp_path):
         assert c_view[cname] == ctypes.sizeof(cls), cname
         for fname, _ in cls._fields_:
             assert c_view["%s.%s" % (cname, fname)] == getattr(cls, fname).offset, (cname, fname)
+
+
+def test_integration_md_stub_matches_the_binding():
+    """the ctypes stub in INTEGRATION.md section 3 is what a maintainer copies -- its structures must
+    be field for field (name, ctype, size) the ones lib.py binds and the header declares."""
+    import ctypes as C
+    import os
+    import re
+    from nerf_rep_for_test_b200 import lib as L
+    text = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "INTEGRATION.md")).read()
+    block = re.search(r"```python\nimport ctypes as C, torch\n(.*?)```", text, re.S).group(1)
+    classes = block[block.index("class MlpWeights"):block.index("def pack(")]
+    ns = {"C": C}
+    exec(classes, ns)
+    for stub, ours in ((ns["MlpWeights"], L.MlpWeights), (ns["RenderParams"], L.RenderParams), (ns["Maps"], L.Maps)):
+        assert [f[0] for f in stub._fields_] == [f[0] for f in ours._fields_], stub.__name__
+        for (name, a), (_, b) in zip(stub._fields_, ours._fields_):
+            assert C.sizeof(a) == C.sizeof(b), (stub.__name__, name)
+            assert getattr(stub, name).offset == getattr(ours, name).offset, (stub.__name__, name)
+        assert C.sizeof(stub) == C.sizeof(ours), stub.__name__
+    assert "ABI %d" % L.ABI_VERSION in classes

@@ -39,6 +39,74 @@ def test_checkpoint_format_roundtrip(tmp_path):
     assert torch.equal(net2.state_dict()["model.alpha_linear.weight"], O.make_state_dict(2)["model.alpha_linear.weight"])
 
 
+def test_flat_adam_state_speaks_the_reference_optimizer_layout():
+    """TrainStep runs Adam over ONE flat tensor; the reference's optimizer (src/train/optimizer.py:14-19) has
+    one param group per named parameter.  split_adam_state / merge_adam_state convert both ways: after identical steps
+    the split state equals the state of a stock per-parameter Adam, loads into it, and merges back bit for bit."""
+    from nerf_rep_for_test_b200 import training as T
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.ReLU(), torch.nn.Linear(7, 3))
+    named = list(net.named_parameters())
+    n_total = sum(p.numel() for _, p in named)
+    # a different storage order than named_parameters() (TrainStep orders by model_params, not by registration)
+    storage = [named[2][1], named[3][1], named[0][1], named[1][1]]
+    offsets, off = {}, 0
+    flat = torch.nn.Parameter(torch.zeros(n_total))
+    for p in storage:
+        offsets[id(p)] = off
+        flat.data[off:off + p.numel()] = p.data.reshape(-1)
+        off += p.numel()
+    ref_opt = torch.optim.Adam([{"params": [p], "lr": 5e-4, "weight_decay": 0.0, "eps": 1e-8} for _, p in named], 5e-4, eps=1e-8)
+    flat_opt = torch.optim.Adam([flat], lr=5e-4, eps=1e-8)
+    for it in range(3):
+        g = torch.randn(n_total, generator=torch.Generator().manual_seed(it))
+        flat.grad = g.clone()
+        for p in storage:
+            p.grad = g[offsets[id(p)]:offsets[id(p)] + p.numel()].view_as(p).clone()
+        ref_opt.step()
+        flat_opt.step()
+    split = T.split_adam_state(flat_opt.state_dict(), named, offsets)
+    ref_sd = ref_opt.state_dict()
+    assert len(split["param_groups"]) == len(ref_sd["param_groups"]) == 4
+    assert [g["params"] for g in split["param_groups"]] == [g["params"] for g in ref_sd["param_groups"]]
+    for i in range(4):
+        for k in ("exp_avg", "exp_avg_sq"):
+            assert torch.allclose(split["state"][i][k], ref_sd["state"][i][k], rtol=0, atol=0), (i, k)
+        assert float(split["state"][i]["step"]) == float(ref_sd["state"][i]["step"]) == 3.0
+    fresh = torch.optim.Adam([{"params": [p]} for _, p in named], 1.0)
+    fresh.load_state_dict(split)                                 # what the reference's load_model does (:312)
+    assert fresh.param_groups[0]["lr"] == 5e-4
+    merged = T.merge_adam_state(ref_sd, named, offsets, n_total, flat.data)
+    for k in ("exp_avg", "exp_avg_sq"):
+        assert torch.equal(merged["state"][0][k], flat_opt.state_dict()["state"][0][k])
+    flat2 = torch.optim.Adam([torch.nn.Parameter(torch.zeros(n_total))], lr=1.0)
+    flat2.load_state_dict(merged)
+    assert flat2.param_groups[0]["lr"] == 5e-4 and float(flat2.state_dict()["state"][0]["step"]) == 3.0
+    assert T.merge_adam_state(flat_opt.state_dict(), named, offsets, n_total, flat.data) is not None   # flat layout passes through
+    with pytest.raises(ValueError):
+        T.merge_adam_state({"state": {}, "param_groups": ref_sd["param_groups"][:3]}, named, offsets, n_total, flat.data)
+
+
+def test_occupancy_builder_uses_the_lookup_geometry():
+    """the grid must be built in the geometry of the lookup (cell = 4/(R-1), volume_renderer.py:992-1007),
+    otherwise ess_mode='skip' cuts geometry on the +x/+y/+z side.  Analytic density: every point with density above the
+    threshold must be found occupied by the reference's own lookup, for off-centre blobs and at the box boundary."""
+    from nerf_rep_for_test_b200 import extras as X
+    g = torch.Generator().manual_seed(0)
+    for centre, radius in (((1.3, 1.1, 1.4), 0.45), ((-1.2, 0.3, 1.7), 0.3), ((1.9, 1.9, 1.9), 0.4)):
+        c = torch.tensor(centre)
+        dens = lambda p: torch.relu(radius - (p - c).norm(dim=-1))
+        for res in (16, 33):
+            grid = X.occupancy_from_density(dens, res, density_threshold=0.01)
+            pts = c + (torch.rand(20000, 3, generator=g) * 2 - 1) * radius
+            pts = pts[(dens(pts) > 0.01) & (pts.abs().max(-1)[0] <= 2.0)]
+            assert pts.shape[0] > 100
+            assert not bool(O.is_empty_space(grid, pts).any()), (centre, res)
+            # and it is not trivially full: far from the blob the lookup says empty
+            far = -c.sign() * 1.5 + (torch.rand(1000, 3, generator=g) - 0.5) * 0.2
+            assert bool(O.is_empty_space(grid, far).all())
+
+
 gpu = pytest.mark.gpu
 
 
@@ -51,27 +119,60 @@ def _net(sd, dev):
 
 @gpu
 def test_occupancy_grid_builder_vs_reference_algorithm():
-    """build_occupancy_grid == the 27-probe rule of volume_renderer.py:875-961 evaluated with the fp32 oracle MLP
-    (cells whose maximum density sits within the bf16 error of the threshold may differ)."""
+    """build_occupancy_grid == the 27-probe rule of volume_renderer.py:875-961 evaluated with the fp32 oracle MLP on the
+    cells of the LOOKUP geometry (cells whose maximum density sits within the bf16 error of the threshold may differ)."""
     from nerf_rep_for_test_b200 import RenderConfig, Renderer
     from nerf_rep_for_test_b200 import extras as X
     dev = torch.device("cuda:0")
     sd = O.make_state_dict(7, 40.0, -1.2)
     r = Renderer(_net(sd, dev).eval(), RenderConfig(perturb=0, enable_ess=False, enable_ert=False), mode="bf16")
-    res = 10
+    res = 11
     grid = X.build_occupancy_grid(r, density_threshold=0.01, res=res).cpu()
-    lo, cell = -2.0, 4.0 / res
-    idx = torch.stack(torch.meshgrid([torch.arange(res)] * 3, indexing="ij"), -1).reshape(-1, 3).float()       # (x,y,z)
+    lo, cell = -2.0, 4.0 / (res - 1)
+    idx = torch.stack(torch.meshgrid([torch.arange(res - 1)] * 3, indexing="ij"), -1).reshape(-1, 3).float()   # (x,y,z)
     off = torch.stack(torch.meshgrid([torch.arange(3)] * 3, indexing="ij"), -1).reshape(-1, 3).float() / 2.0
-    pts = lo + (idx[:, None, :] + off[None, :, :]) * cell                                                    # [R^3,27,3]
+    pts = lo + (idx[:, None, :] + off[None, :, :]) * cell                                                    # [(R-1)^3,27,3]
     emb = O.pos_enc(pts.reshape(-1, 3), 10)
     raw = O.nerf_mlp(sd, "model.", torch.cat([emb, torch.zeros(emb.shape[0], 27)], -1))
     dens = torch.relu(raw[:, 3]).view(-1, 27).max(1)[0]
-    want = (dens > 0.01).view(res, res, res)
-    margin = (dens - 0.01).abs().view(res, res, res) < 5e-3
+    want = (dens > 0.01).view(res - 1, res - 1, res - 1)
+    margin = (dens - 0.01).abs().view(res - 1, res - 1, res - 1) < 5e-3
+    got = grid[:res - 1, :res - 1, :res - 1]
     assert 0.05 < float(want.float().mean()) < 0.95
-    assert bool(((grid == want) | margin).all())
-    assert float((grid != want).float().mean()) < 0.02
+    assert bool(((got == want) | margin).all())
+    assert float((got != want).float().mean()) < 0.02
+    assert torch.equal(grid[res - 1], grid[res - 2]) and torch.equal(grid[:, :, res - 1], grid[:, :, res - 2])
+
+
+@gpu
+def test_skip_render_with_a_built_grid_stays_close_to_the_dense_render():
+    """ess_mode='skip' with a grid produced by build_occupancy_grid.  A skipped sample's density is forced to
+    0, so the grid must cover every sample whose density matters: the skip render may differ from the dense render only by
+    what densities below the build threshold (0.01) contribute -- bounded here on an off-centre blob that reaches the +x
+    side of the box, where the old builder (cells of 4/R instead of the lookup's 4/(R-1)) cut geometry."""
+    from nerf_rep_for_test_b200 import RenderConfig, Renderer
+    from nerf_rep_for_test_b200 import extras as X
+    dev = torch.device("cuda:0")
+    sd = O.make_state_dict(6, 300.0, 6.0)
+    for k in list(sd):
+        if k.startswith("model_fine."):
+            sd[k] = sd["model." + k[len("model_fine."):]].clone()
+    net = _net(sd, dev).eval()
+    dense = Renderer(net, RenderConfig(perturb=0, enable_ess=False, enable_ert=False), mode="bf16")
+    skip = Renderer(net, RenderConfig(perturb=0, enable_ess=True, enable_ert=False), mode="bf16")
+    skip.occupancy_grid = X.build_occupancy_grid(skip, density_threshold=0.01, res=64)
+    skip.ess_mode = "skip"
+    occ = float(skip.occupancy_grid.float().mean())
+    b = O.lego_batch(48, 48)
+    gb = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in b.items()}
+    a, c = dense.render(gb), skip.render(gb)
+    for k in ("rgb_map_0", "acc_map_0", "rgb_map", "acc_map"):
+        err = (a[k] - c[k]).abs()
+        print("skip vs dense %-10s max %.2e mean %.2e (grid %.0f %% occupied, %.1f MLP rows per ray)" % (
+            k, float(err.max()), float(err.mean()), 100 * occ, float(skip.eval_counts.sum()) / (48 * 48)))
+        # coarse pass: same sample positions, only sub-threshold densities removed (64 samples x 0.01 x 0.0635 ~ 4e-2 worst case)
+        assert float(err.max()) <= (5e-2 if k.endswith("_0") else 1.5e-1), k
+        assert float(err.mean()) <= 1e-2, k
 
 
 @gpu
@@ -105,7 +206,14 @@ def test_ray_batch_trainer_improves_psnr_and_checkpoints(tmp_path):
     assert p1 > p0 + 2.0
     assert sum(losses[-10:]) < 0.6 * sum(losses[:10])
     d = str(tmp_path / "ck")
-    X.save_model(student, tr.step_fn.opt, None, None, d, 0, last=True)
+    X.save_model(student, tr.step_fn, None, None, d, 0, last=True)          # TrainStep speaks the reference's optimizer layout
+    ck = torch.load(os.path.join(d, "latest.pth"))
+    assert len(ck["optim"]["param_groups"]) == 48 and len(ck["optim"]["state"]) == 48
+    ref_opt = torch.optim.Adam([{"params": [p]} for _, p in student.named_parameters()], 5e-4)
+    ref_opt.load_state_dict(ck["optim"])                                     # what the reference's load_model does (:312)
+    m0 = tr.step_fn.opt.state_dict()["state"][0]["exp_avg"].clone()
+    tr.step_fn.load_state_dict(ck["optim"])
+    assert torch.equal(tr.step_fn.opt.state_dict()["state"][0]["exp_avg"], m0)
     student.eval()
     r.perturb = 0
     ro, rd = tr.rays[1]

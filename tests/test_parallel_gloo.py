@@ -49,6 +49,13 @@ def _worker(rank, world, port, out):
         P.FlatGradAllReduce(ps, flat=flat)()
         assert torch.allclose(flat, torch.full_like(flat, sum(range(1, world + 1)) / world))
         assert all(p.grad.data_ptr() >= flat.data_ptr() for p in ps)
+        # the two-piece overlapped variant TrainStep uses: start(fine slice) ... start(coarse slice), finish
+        flat.fill_(float(rank + 1))
+        ar = P.FlatGradAllReduce(ps, flat=flat)
+        cut = ps[0].numel()
+        hs = [ar.start(cut, flat.numel()), ar.start(0, cut)]
+        ar.finish(hs)
+        assert torch.allclose(flat, torch.full_like(flat, sum(range(1, world + 1)) / world))
         # one frame split into contiguous ray blocks, gathered on rank 0 (ShardedFrame: the N>1 single-frame path)
         for n in (1003, 64, 1):
             frame = P.ShardedFrame(n, torch.device("cpu"))
