@@ -255,7 +255,7 @@ def parity_block(net, dev, args):
                 if im is not None:
                     wrong_search += im["other"]
     # per mode and field: every map of both ray sets inside the mode's tolerance at p99 (fp32-accurate passes:
-    # p99 <= max(1e-5, the reference's own fp32 rounding on the same inputs -- "reference_fp32_rounding"), max <= 2e-4).
+    # p99 <= max(1e-5, 2 x the reference's own fp32 rounding on the same inputs -- "reference_fp32_rounding"), max <= 2e-4).
     # "randinit" is north_star's parity configuration (identical rays, random-init weights, perturb=0).
     out["within_tolerance"] = within
     out["inds_mismatch_other_total"] = wrong_search

@@ -16,9 +16,12 @@
  *    the library allocates no device memory, frees nothing and keeps no user
  *    pointer after the call returns.  Its only process-wide state: the
  *    thread-local last-error string, the launch counter, the optional profiling
- *    events (nerfb200_profile_*), one-time per-device kernel attributes, and the
- *    copy stream + event that nerfb200_render_image_host creates on first use.
- *    One host thread per device.
+ *    events (nerfb200_profile_*: a diagnostic, one host thread), one-time
+ *    PER-DEVICE kernel attributes (a process may drive several devices), and the
+ *    per-device copy stream + event that nerfb200_render_image_host creates on
+ *    first use (concurrent calls on one device are serialised by a mutex).
+ *    Every call works on the CURRENT device: the caller selects the device that
+ *    owns the buffers (the Python host side does, around every call).
  *  - all work is enqueued on `stream` (a cudaStream_t passed as void*), no
  *    host synchronisation inside unless stated.
  *  - return 0 on success, non-zero on failure with a message available from

@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <mutex>
 
 #include "common.cuh"
 #include "train_layout.cuh"
@@ -498,9 +499,11 @@ extern "C" int nerfb200_render_image_host(const void* packed_coarse, const void*
   // (the 30.7 MB of an 800x800 frame used to trail the render by ~0.8 ms).
   static cudaStream_t copy_stream[64] = {};
   static cudaEvent_t chunk_event[64] = {};
+  static std::mutex copy_mutex[64];   // the side stream and its event are per device: concurrent calls on one device take turns
   int dev = 0;
   NB_CUDA(cudaGetDevice(&dev));
   NB_CHECK_ARG(dev >= 0 && dev < 64, "render_image_host: device ordinal %d out of range", dev);
+  std::lock_guard<std::mutex> lock(copy_mutex[dev]);
   if (!copy_stream[dev]) {
     NB_CUDA(cudaStreamCreateWithFlags(&copy_stream[dev], cudaStreamNonBlocking));
     NB_CUDA(cudaEventCreateWithFlags(&chunk_event[dev], cudaEventDisableTiming));

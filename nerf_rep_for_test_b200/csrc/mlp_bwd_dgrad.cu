@@ -312,10 +312,11 @@ int launch_mlp_bwd_dgrad(const void* packed_bwd, const float* g_raw, const void*
   int dev = 0, sms = 0;
   NB_CUDA(cudaGetDevice(&dev));
   NB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  static int attr_dev = -1;   // per-device, sticky: set once (also keeps the call out of CUDA-graph captures)
-  if (attr_dev != dev) {
+  static bool attr_set[64] = {};   // per-device, sticky: set once (also keeps the call out of CUDA-graph captures)
+  NB_CHECK_ARG(dev >= 0 && dev < 64, "mlp_backward: device ordinal %d out of range", dev);
+  if (!attr_set[dev]) {
     NB_CUDA(cudaFuncSetAttribute(mlp_bwd_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    attr_dev = dev;
+    attr_set[dev] = true;
   }
   long long quads = (M + 511) / 512;
   int clusters = (int)(quads < sms / 2 ? quads : sms / 2);

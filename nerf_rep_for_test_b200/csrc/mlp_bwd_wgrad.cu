@@ -294,10 +294,11 @@ int launch_mlp_bwd_wgrad(const void* acts, const void* dacts, long long M, float
   int dev = 0, sms = 0;
   NB_CUDA(cudaGetDevice(&dev));
   NB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  static int attr_dev = -1;   // per-device, sticky: set once (also keeps the call out of CUDA-graph captures)
-  if (attr_dev != dev) {
+  static bool attr_set[64] = {};   // per-device, sticky: set once (also keeps the call out of CUDA-graph captures)
+  NB_CHECK_ARG(dev >= 0 && dev < 64, "mlp_backward: device ordinal %d out of range", dev);
+  if (!attr_set[dev]) {
     NB_CUDA(cudaFuncSetAttribute(mlp_bwd_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    attr_dev = dev;
+    attr_set[dev] = true;
   }
   NB_CUDA(cudaMemsetAsync(scratch, 0, kGradScratchFloats * sizeof(float), st));
   const int n_tiles = (int)((M + 127) / 128);

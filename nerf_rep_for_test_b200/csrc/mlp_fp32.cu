@@ -216,10 +216,13 @@ mlp_fp32_kernel(const float* __restrict__ packed, const float* __restrict__ rays
 
 int launch_mlp_fp32(const void* packed, const float* rays_o, const float* rays_d, const float* z_vals,
                     int n_rays, int n_samples, float* raw, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  int dev = 0;
+  NB_CUDA(cudaGetDevice(&dev));
+  NB_CHECK_ARG(dev >= 0 && dev < 64, "mlp_forward: device ordinal %d out of range", dev);
+  static bool attr_set[64] = {};   // the opt-in to 104 KB of dynamic shared memory is per device and sticky
+  if (!attr_set[dev]) {
     NB_CUDA(cudaFuncSetAttribute(mlp_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemF32)));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   long long M = (long long)n_rays * n_samples;
   int blocks = ceil_div(M, kTileM);

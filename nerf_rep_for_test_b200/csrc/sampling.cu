@@ -121,8 +121,8 @@ sample_from_cdf_kernel(const float* __restrict__ cdf_g, const float* __restrict_
 
 // ------------------------------------------------------------------------------------------
 // a4 whole: weights[1:-1] + 1e-5 -> pdf -> cdf -> samples -> sorted merge with the coarse z.
-//  * normaliser: fp64 sum rounded to fp32 (torch CPU's fp32 cascade order is build/ISA
-//    dependent; the fp64 sum is the correctly rounded value and is at most 1 ulp from it).
+//  * normaliser: summed in torch-CPU's own fp32 order (pdf_normaliser below), so the cdf is bit-identical to
+//    the reference's whenever the coarse weights are.
 //  * cdf: torch CPU cumsum accumulates float in DOUBLE and rounds each output (probed, 0
 //    mismatches) -- reproduced exactly with a warp scan in fp64.
 //  * merge: rank = own index + count of elements of the other list that sort before it
@@ -140,6 +140,39 @@ __device__ __forceinline__ double warp_incl_scan(double v, int lane) {
     if (lane >= d) v += o;
   }
   return v;
+}
+
+// sum_i (w[i] + 1e-5) over the n interior weights of one ray, in EXACTLY the order torch's CPU kernel uses for
+// `torch.sum(weights, -1)` on a contiguous fp32 row (volume_renderer.py:242; ATen SumKernel.cpp vectorized_inner_sum,
+// probed on torch 2.11 at the DEFAULT, AVX2 and AVX512 dispatch levels -- all three use 8-lane vectors -- for
+// n = 8..254): the row is cut into vectors of 8; vector 4i+k (i < nv/4) goes to accumulator k of four, the remaining
+// vectors to accumulator 0; the accumulators are added ((a0+a1)+a2)+a3 lane-wise; the result starts from the scalar
+// tail x[8 nv ..] summed left to right and then adds lanes 0..7 in order.  With it the cdf -- hence every bin index of
+// sample_pdf -- is bit-identical to the reference's whenever the coarse weights are (before: fp64 sum, 1 ulp off on 42 %
+// of the rows).  The 32 (accumulator, lane) chains map onto the 32 lanes of the warp.  n < 8 (n_samples < 10) takes
+// another path inside torch; the correctly rounded fp64 sum is used there.
+__device__ __forceinline__ float pdf_normaliser(const float* __restrict__ w, int n, int lane) {
+  if (n < 8) {
+    double part = 0.0;
+    for (int i = lane; i < n; i += 32) part += (double)__fadd_rn(w[i], 1e-5f);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+    return (float)part;
+  }
+  const int k = lane >> 3, v = lane & 7;
+  const int nv = n >> 3, size_ilp = nv >> 2;
+  float acc = 0.f;
+  for (int i = 0; i < size_ilp; ++i) acc = __fadd_rn(acc, __fadd_rn(w[((i << 2) + k) * 8 + v], 1e-5f));
+  if (k == 0)
+    for (int vec = size_ilp << 2; vec < nv; ++vec) acc = __fadd_rn(acc, __fadd_rn(w[vec * 8 + v], 1e-5f));
+  const float a1 = __shfl_sync(0xffffffffu, acc, v + 8), a2 = __shfl_sync(0xffffffffu, acc, v + 16),
+              a3 = __shfl_sync(0xffffffffu, acc, v + 24);
+  acc = __fadd_rn(__fadd_rn(__fadd_rn(acc, a1), a2), a3);   // meaningful on lanes 0..7
+  float fin = 0.f;
+  for (int e = nv << 3; e < n; ++e) fin = __fadd_rn(fin, __fadd_rn(w[e], 1e-5f));
+#pragma unroll
+  for (int l = 0; l < 8; ++l) fin = __fadd_rn(fin, __shfl_sync(0xffffffffu, acc, l));
+  return fin;
 }
 
 // number of entries of sorted row a[0..n) that are < x (strict) or <= x
@@ -177,13 +210,8 @@ sample_pdf_merge_kernel(const float* __restrict__ z_coarse, const float* __restr
   for (int i = lane; i < S; i += 32) zr[i] = z_coarse[(size_t)ray * S + i];
   __syncwarp();
   for (int i = lane; i < nbins; i += 32) bins[i] = __fmul_rn(0.5f, __fadd_rn(zr[i + 1], zr[i]));
-  // pdf normaliser
-  double part = 0.0;
-  for (int i = lane; i < nw; i += 32)
-    part += (double)__fadd_rn(weights[(size_t)ray * S + 1 + i], 1e-5f);
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
-  float wsum = (float)part;
+  // pdf normaliser, in torch-CPU's summation order (see pdf_normaliser)
+  const float wsum = pdf_normaliser(weights + (size_t)ray * S + 1, nw, lane);
   // cdf = [0, cumsum(pdf)] with fp64 accumulation, each lane owns a contiguous segment
   const int per = (nw + 31) / 32;
   double local = 0.0;
@@ -281,11 +309,7 @@ sample_pdf_backward_kernel(const float* __restrict__ z_coarse, const float* __re
   __syncwarp();
   for (int i = lane; i < nbins; i += 32) bins[i] = __fmul_rn(0.5f, __fadd_rn(zr[i + 1], zr[i]));
   // ---- forward recompute (same arithmetic as sample_pdf_merge_kernel)
-  double part = 0.0;
-  for (int i = lane; i < nw; i += 32) part += (double)__fadd_rn(weights[(size_t)ray * S + 1 + i], 1e-5f);
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
-  const float wsum = (float)part;
+  const float wsum = pdf_normaliser(weights + (size_t)ray * S + 1, nw, lane);
   const int per = (nw + 31) / 32;
   double local = 0.0;
   float pdf_loc[8];

@@ -414,3 +414,38 @@ def ert_depth(weights, z_vals, thr):
     L.check(L.load().nerfb200_ert_depth(L.dev(weights), L.dev(z_vals), n, S, float(thr), L.dev(zt), L.stream_ptr()),
             "ert_depth")
     return zt
+
+
+# ---- every wrapper runs on the device that owns its tensors (the C ABI works on the CURRENT device): a network on
+# cuda:1 with cuda:0 current would otherwise launch on the wrong GPU
+def _device_of(args, kwargs):
+    for a in list(args) + list(kwargs.values()):
+        if torch.is_tensor(a) and a.is_cuda:
+            return a.device
+        if isinstance(a, (list, tuple)) and a and torch.is_tensor(a[0]) and a[0].is_cuda:
+            return a[0].device
+        if isinstance(a, PackedWeights):
+            return a.buf.device
+        if isinstance(a, TrainStore):
+            return a.acts.device
+    return None
+
+
+def _on_tensor_device(fn):
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        dev = _device_of(args, kwargs)
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapped
+
+
+for _name, _fn in list(globals().items()):
+    if callable(_fn) and not _name.startswith("_") and getattr(_fn, "__module__", None) == __name__ and \
+            not isinstance(_fn, type) and _name not in ("untile",):
+        globals()[_name] = _on_tensor_device(_fn)
+del _name, _fn

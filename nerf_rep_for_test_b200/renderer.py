@@ -116,6 +116,20 @@ def occupied_box(grid):
     return lo, hi
 
 
+def _on_device(fn):
+    """Run a method with the renderer's device current: the C ABI launches on the CURRENT device and allocates its
+    stream from it, so a network on cuda:1 must not launch while cuda:0 is current."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        if self.device.index is None or self.device.index == torch.cuda.current_device():
+            return fn(self, *a, **k)
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **k)
+    return wrapped
+
+
 class Renderer(PathRenderingMixin):
     # name -> (coarse-pass mode, fine-pass mode).  "fp32tc": split-fp16 tensor-core arithmetic, as accurate as "fp32"
     # (the CUDA-core kernel) at a fraction of its time; "mixed": fp32tc for the coarse network (so the importance
@@ -236,6 +250,7 @@ class Renderer(PathRenderingMixin):
             ent = self._packed[k]
             self._packed[k] = (None,) + tuple(ent[1:])
 
+    @_on_device
     def packed_bwd(self, which):
         """W^T image for nerfb200_mlp_backward (training), cached per parameter version like _packed_weights."""
         model = self.coarse_model if which == "coarse" else self.fine_model
@@ -255,6 +270,7 @@ class Renderer(PathRenderingMixin):
         self._packed_weights(which)
         return C.c_void_p(self._packed[which][2])
 
+    @_on_device
     def packed(self, which, mode=None):
         """(ptr, mode) handle accepted by ops.mlp_forward*; repacked lazily when parameters change."""
         class _Handle:
@@ -346,6 +362,7 @@ class Renderer(PathRenderingMixin):
         return self._ws
 
     # ------------------------------------------------------------------ public API
+    @_on_device
     @torch.no_grad()
     def render_rays(self, rays_o, rays_d, out=None):
         """rays_o, rays_d: [N,3] fp32 CUDA.  Returns the reference's dict keys with leading [N].  out: optional dict of
@@ -381,6 +398,7 @@ class Renderer(PathRenderingMixin):
             L.stream_ptr()), "render_rays")
         return out
 
+    @_on_device
     @torch.no_grad()
     def render(self, batch):
         """Same contract as the reference's Renderer.render(batch) (volume_renderer.py:89-216)."""
@@ -404,6 +422,7 @@ class Renderer(PathRenderingMixin):
         nerf_rep_for_test_b200.kilo.KiloRenderer."""
         return self.render(batch)
 
+    @_on_device
     def render_host(self, batch):
         """End-to-end entry with HOST buffers: pose/intrinsics are read from host memory, the eight maps
         are returned in pinned host tensors; copies and a stream sync happen inside the C call."""

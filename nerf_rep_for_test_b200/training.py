@@ -331,6 +331,12 @@ class TrainStep:
         return loss
 
     def __call__(self, rays_o, rays_d, target_rgb):
+        if self.r.device.index is not None and self.r.device.index != torch.cuda.current_device():
+            with torch.cuda.device(self.r.device):      # the C ABI launches on the current device
+                return self._call(rays_o, rays_d, target_rgb)
+        return self._call(rays_o, rays_d, target_rgb)
+
+    def _call(self, rays_o, rays_d, target_rgb):
         r = self.r
         if r.enable_ess or r.enable_ert:
             raise L.NerfB200Error("training path implements the plain compositor (enable_ess/enable_ert off)")
