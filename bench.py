@@ -390,6 +390,7 @@ def run_ours(args):
     # clip + Adam; stratified jitter and random u (net.train()); random target colours
     train_ms = 0.0
     train_graph = False
+    train_variants = {}
     if args.train_steps > 0:
         from nerf_rep_for_test_b200 import training as T
         net.train()
@@ -412,6 +413,31 @@ def run_ours(args):
         train_ms = te0.elapsed_time(te1)
         train_graph = step._graph is not None      # the whole step replayed as one CUDA graph (single process only)
         barrier()
+        # the same step with the REFERENCE's gradient graph (sampler not detached, volume_renderer.py:181-183), and the
+        # fp32-accurate parity path (rank 0 of a single-GPU run only: it is 40x slower)
+        train_variants = {}
+        for tag, prec, compat, nsteps in (("bf16_reference_graph", "bf16", True, args.train_steps),
+                                          ("fp32_reference_graph", "fp32", True, 2 if world == 1 else 0)):
+            if nsteps <= 0:
+                continue
+            netv = Network(device=dev)
+            netv.load_state_dict(sd)
+            netv.to(dev).train()
+            rv = Renderer(netv, RenderConfig(perturb=1, enable_ess=False, enable_ert=False), mode="bf16")
+            stepv = T.TrainStep(rv, precision=prec, ref_compat_sampler=compat)
+            for _ in range(2):
+                stepv(tro, trd, target)
+            barrier()
+            v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            v0.record()
+            for _ in range(nsteps):
+                stepv(tro, trd, target)
+            v1.record()
+            torch.cuda.synchronize()
+            train_variants[tag] = {"ms_per_iter": v0.elapsed_time(v1) / nsteps, "steps": nsteps, "precision": prec,
+                                   "ref_compat_sampler": compat}
+            del stepv, rv, netv
+            barrier()
         net.eval()
         r.perturb = 0
 
@@ -585,6 +611,8 @@ def run_ours(args):
                 "warmup": args.train_warmup, "rays_per_iter_per_gpu": args.train_rays,
                 "rays_per_s_total": world * args.train_rays * 1e3 / it_ms, "scaling": "weak",
                 "allreduce_bytes": 1191688 * 4, "cuda_graph": train_graph,
+                "allreduce": "two pieces of one flat fp32 buffer; the fine model's piece overlaps the coarse model's backward",
+                "variants": train_variants,
                 "algorithmic_tflops": 3 * args.train_rays * ROWS_PER_RAY * FLOP_PER_ROW / (it_ms * 1e-3) / 1e12,
                 "note": "every kernel on the path is this repo's: tcgen05 forward with activation store, compositing "
                         "backward, tcgen05 dgrad chain + split-K wgrad GEMMs (nerfb200_mlp_backward); torch supplies "

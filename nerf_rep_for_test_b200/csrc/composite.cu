@@ -12,6 +12,13 @@
 namespace nb {
 
 constexpr int kCompWarps = 8;
+// Minimum resident blocks per SM the compositors are compiled for, i.e. a register bound: these kernels are latency
+// bound (strided row reads, shuffle scans), so warps in flight matter more than registers per thread.  Measured on
+// B200 (scripts/stream_kernels.py, 640 000 rays; unbounded = 63-80 registers, 3 blocks per SM):
+//   fast-math variants (MUFU, fp32 scans):   6 blocks (40 registers)  S=64 0.49 -> 0.38 ms,  S=192 0.76 -> 0.63 ms
+//   exact variants (fp64 exp / prefix):      4 blocks (64 registers)  S=64 0.77,  S=192 1.63 ms  (6 blocks: 0.78 / 1.83, spills)
+//   backward:                                4 blocks                 2.63 ms  (6 blocks: 3.09)
+constexpr int kMinBlocksFast = 6, kMinBlocksExact = 4;
 constexpr int kMaxPer = 8;  // ceil(S/32) <= 8  => S <= 256
 
 // exp / sigmoid as the reference's CPU sees them: torch CPU evaluates exp with SLEEF (<= 1 ulp);
@@ -209,7 +216,7 @@ __device__ __forceinline__ void ray_outputs(const RaySamples& rs, const float* _
 
 // PLAIN and ERT: one warp per ray
 template <bool kErt, bool kFast>
-__global__ void __launch_bounds__(kCompWarps * 32)
+__global__ void __launch_bounds__(kCompWarps * 32, kFast ? kMinBlocksFast : kMinBlocksExact)
 composite_kernel(const float* __restrict__ raw, const float* __restrict__ z_vals,
                  const float* __restrict__ rays_d, int n_rays, int S, float thr, int white_bkgd,
                  float* __restrict__ rgb_map, float* __restrict__ disp_map,
@@ -308,7 +315,7 @@ composite_ert_compat_kernel(const float* __restrict__ raw, const float* __restri
 //   dL/drgb_raw_c = w_i g_rgb_c c (1-c)
 // The suffix sum is a reverse warp scan in fp64.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kCompWarps * 32)
+__global__ void __launch_bounds__(kCompWarps * 32, kMinBlocksExact)
 composite_backward_kernel(const float* __restrict__ raw, const float* __restrict__ z_vals,
                           const float* __restrict__ rays_d, int n_rays, int S, int white_bkgd,
                           const float* __restrict__ g_rgb_map, const float* __restrict__ g_acc_map,

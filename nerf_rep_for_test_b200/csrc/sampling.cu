@@ -151,25 +151,55 @@ __device__ __forceinline__ double warp_incl_scan(double v, int lane) {
 // sample_pdf -- is bit-identical to the reference's whenever the coarse weights are (before: fp64 sum, 1 ulp off on 42 %
 // of the rows).  The 32 (accumulator, lane) chains map onto the 32 lanes of the warp.  n < 8 (n_samples < 10) takes
 // another path inside torch; the correctly rounded fp64 sum is used there.
+template <int Q>   // Q = ceil(n / 32) at most: the per-lane loads are unrolled (2 for the 64-sample configuration, 8 in general)
 __device__ __forceinline__ float pdf_normaliser(const float* __restrict__ w, int n, int lane) {
-  if (n < 8) {
+#ifdef NERFB200_PDF_FP64_SUM   // A/B experiments only: the round-1 normaliser (correctly rounded fp64 sum, 1 ulp from torch on 42 % of the rows)
+  const bool fp64_sum = true;
+#else
+  const bool fp64_sum = false;
+#endif
+  if (n < 8 || fp64_sum) {
     double part = 0.0;
     for (int i = lane; i < n; i += 32) part += (double)__fadd_rn(w[i], 1e-5f);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
     return (float)part;
   }
-  const int k = lane >> 3, v = lane & 7;
-  const int nv = n >> 3, size_ilp = nv >> 2;
-  float acc = 0.f;
-  for (int i = 0; i < size_ilp; ++i) acc = __fadd_rn(acc, __fadd_rn(w[((i << 2) + k) * 8 + v], 1e-5f));
-  if (k == 0)
-    for (int vec = size_ilp << 2; vec < nv; ++vec) acc = __fadd_rn(acc, __fadd_rn(w[vec * 8 + v], 1e-5f));
+  // Lane l holds x_q = w[l + 32 q] + 1e-5: element e = 8 vec + v sits in lane e % 32 = 8 (vec % 4) + v at q = vec / 4,
+  // i.e. exactly in the (accumulator k = lane / 8, vector lane v = lane % 8) chain torch assigns it to.  All loads are
+  // issued up front (independent, coalesced); what follows is a chain of register adds fed by shuffles whose sources
+  // are ready early (no loop with a data-dependent trip count: measured 1.61 -> ~1.1 ms per 640 000 rays).
+  const int v = lane & 7;
+  const int nv = n >> 3, size_ilp = nv >> 2;       // full vectors; full rows of four vectors
+  const int rem = nv - (size_ilp << 2);            // full vectors in the last, partial row (0..3)
+  const int ntail = n - (nv << 3);                 // scalar tail (0..7)
+  float x[Q];
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    const int e = lane + 32 * q;
+    x[q] = e < n ? __fadd_rn(w[e], 1e-5f) : 0.f;
+  }
+  float acc = 0.f, xr = 0.f;
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    if (q < size_ilp) acc = __fadd_rn(acc, x[q]);
+    if (q == size_ilp) xr = x[q];
+  }
+  // remaining full vectors of the partial row go to accumulator 0 (lanes 0..7), in order
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const float t = __shfl_sync(0xffffffffu, xr, 8 * r + v);
+    if (r < rem && lane < 8) acc = __fadd_rn(acc, t);
+  }
   const float a1 = __shfl_sync(0xffffffffu, acc, v + 8), a2 = __shfl_sync(0xffffffffu, acc, v + 16),
               a3 = __shfl_sync(0xffffffffu, acc, v + 24);
   acc = __fadd_rn(__fadd_rn(__fadd_rn(acc, a1), a2), a3);   // meaningful on lanes 0..7
   float fin = 0.f;
-  for (int e = nv << 3; e < n; ++e) fin = __fadd_rn(fin, __fadd_rn(w[e], 1e-5f));
+#pragma unroll
+  for (int t = 0; t < 7; ++t) {
+    const float y = __shfl_sync(0xffffffffu, xr, (8 * rem + t) & 31);
+    if (t < ntail) fin = __fadd_rn(fin, y);
+  }
 #pragma unroll
   for (int l = 0; l < 8; ++l) fin = __fadd_rn(fin, __shfl_sync(0xffffffffu, acc, l));
   return fin;
@@ -186,7 +216,8 @@ __device__ __forceinline__ int count_less(const float* a, int n, float x, bool o
   return lo;
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+template <int Q>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 6)
 sample_pdf_merge_kernel(const float* __restrict__ z_coarse, const float* __restrict__ weights,
                         const float* __restrict__ u_g, int u_per_ray, int n_rays, int S, int n_u,
                         float* __restrict__ z_all, float* __restrict__ z_samples,
@@ -211,7 +242,7 @@ sample_pdf_merge_kernel(const float* __restrict__ z_coarse, const float* __restr
   __syncwarp();
   for (int i = lane; i < nbins; i += 32) bins[i] = __fmul_rn(0.5f, __fadd_rn(zr[i + 1], zr[i]));
   // pdf normaliser, in torch-CPU's summation order (see pdf_normaliser)
-  const float wsum = pdf_normaliser(weights + (size_t)ray * S + 1, nw, lane);
+  const float wsum = pdf_normaliser<Q>(weights + (size_t)ray * S + 1, nw, lane);
   // cdf = [0, cumsum(pdf)] with fp64 accumulation, each lane owns a contiguous segment
   const int per = (nw + 31) / 32;
   double local = 0.0;
@@ -287,6 +318,7 @@ sample_pdf_merge_kernel(const float* __restrict__ z_coarse, const float* __restr
 // cumulative sum -> g_pdf -> quotient rule -> g_weights[:, 1:-1]; the first and last coarse weight get 0.
 // The coarse depths inside z_all are constants (no parameter reaches them) and receive no gradient.
 // ------------------------------------------------------------------------------------------
+template <int Q>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 sample_pdf_backward_kernel(const float* __restrict__ z_coarse, const float* __restrict__ weights,
                            const float* __restrict__ u_g, int u_per_ray, int n_rays, int S, int n_u,
@@ -309,7 +341,7 @@ sample_pdf_backward_kernel(const float* __restrict__ z_coarse, const float* __re
   __syncwarp();
   for (int i = lane; i < nbins; i += 32) bins[i] = __fmul_rn(0.5f, __fadd_rn(zr[i + 1], zr[i]));
   // ---- forward recompute (same arithmetic as sample_pdf_merge_kernel)
-  const float wsum = pdf_normaliser(weights + (size_t)ray * S + 1, nw, lane);
+  const float wsum = pdf_normaliser<Q>(weights + (size_t)ray * S + 1, nw, lane);
   const int per = (nw + 31) / 32;
   double local = 0.0;
   float pdf_loc[8];
@@ -468,8 +500,12 @@ static int sample_pdf_merge_impl(const float* z_coarse, const float* weights, co
   if (n_rays == 0) return 0;
   int blocks = ceil_div(n_rays, kWarpsPerBlock);
   if (rl.rays != nullptr && blocks > kPersistentBlocks) blocks = kPersistentBlocks;
-  sample_pdf_merge_kernel<<<blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-      z_coarse, weights, u, u_per_ray, n_rays, n_samples, n_u, z_all, z_samples, inds, cdf, rl.rays, rl.count);
+  if (n_samples - 2 <= 64)
+    sample_pdf_merge_kernel<2><<<blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+        z_coarse, weights, u, u_per_ray, n_rays, n_samples, n_u, z_all, z_samples, inds, cdf, rl.rays, rl.count);
+  else
+    sample_pdf_merge_kernel<8><<<blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+        z_coarse, weights, u, u_per_ray, n_rays, n_samples, n_u, z_all, z_samples, inds, cdf, rl.rays, rl.count);
   NB_LAUNCH_OK("sample_pdf_merge_kernel");
   return 0;
 }
@@ -482,8 +518,12 @@ extern "C" int nerfb200_sample_pdf_backward(const float* z_coarse, const float* 
   NB_CHECK_ARG(n_u >= 1 && n_u <= kMaxU, "sample_pdf_backward: n_u=%d out of range [1,%d]", n_u, kMaxU);
   NB_CHECK_ARG(n_rays >= 0, "sample_pdf_backward: negative n_rays");
   if (n_rays == 0) return 0;
-  sample_pdf_backward_kernel<<<ceil_div(n_rays, kWarpsPerBlock), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-      z_coarse, weights, u, u_per_ray, n_rays, n_samples, n_u, g_z_all, g_weights);
+  if (n_samples - 2 <= 64)
+    sample_pdf_backward_kernel<2><<<ceil_div(n_rays, kWarpsPerBlock), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+        z_coarse, weights, u, u_per_ray, n_rays, n_samples, n_u, g_z_all, g_weights);
+  else
+    sample_pdf_backward_kernel<8><<<ceil_div(n_rays, kWarpsPerBlock), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+        z_coarse, weights, u, u_per_ray, n_rays, n_samples, n_u, g_z_all, g_weights);
   NB_LAUNCH_OK("sample_pdf_backward_kernel");
   return 0;
 }

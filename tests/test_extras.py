@@ -39,6 +39,90 @@ def test_checkpoint_format_roundtrip(tmp_path):
     assert torch.equal(net2.state_dict()["model.alpha_linear.weight"], O.make_state_dict(2)["model.alpha_linear.weight"])
 
 
+def test_checkpoint_written_by_the_reference_itself(tmp_path):
+    """a checkpoint written by the reference's OWN net_utils.save_model (:323-343) from its own Network,
+    make_optimizer (optimizer.py:8-28: one param group per named parameter) and scheduler/recorder loads into our
+    Network (extras.load_network / load_model) and -- through merge_adam_state, what TrainStep.load_state_dict does --
+    into the flat single-tensor Adam of the training path; and the other way round, a state split from the flat Adam
+    loads into the reference's optimizer via the reference's own load_model."""
+    from oracle import ref_loader
+    if not ref_loader.reference_available():
+        pytest.skip("/root/reference not mounted (GPU box)")
+    import os as _os
+    import sys as _sys
+    from nerf_rep_for_test_b200 import Network
+    from nerf_rep_for_test_b200 import extras as X
+    from nerf_rep_for_test_b200 import training as T
+    cfg, ref_net, _ = ref_loader.build_reference(O.make_state_dict(4))
+    import importlib.util
+    import types
+    if "termcolor" not in _sys.modules:                  # not installed here; net_utils only colours a log line with it
+        tc = types.ModuleType("termcolor")
+        tc.colored = lambda s, *a, **k: s
+        _sys.modules["termcolor"] = tc
+
+    def _load(name, rel):                                # by file path: src/train/__init__.py pulls in the dataset stack
+        spec = importlib.util.spec_from_file_location(name, _os.path.join(ref_loader.REFERENCE_ROOT, rel))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+    make_optimizer = _load("ref_optimizer", "src/train/optimizer.py").make_optimizer
+    net_utils = _load("ref_net_utils", "src/utils/net_utils.py")
+    ref_net.train()
+    opt = make_optimizer(cfg, ref_net)
+    for it in range(2):                                   # two Adam steps so that the state is populated
+        for p in ref_net.parameters():
+            p.grad = torch.randn(p.shape, generator=torch.Generator().manual_seed(it)) * 1e-3
+        opt.step()
+
+    class _SD:                                            # scheduler / recorder stand-ins with the state_dict protocol
+        def __init__(self):
+            self.d = {"x": 1}
+
+        def state_dict(self):
+            return dict(self.d)
+
+        def load_state_dict(self, d):
+            self.d = dict(d)
+    d = str(tmp_path / "refckpt")
+    net_utils.save_model(ref_net, opt, _SD(), _SD(), d, 7, last=True)          # the reference's writer
+    ours = Network(device=torch.device("cpu"))
+    assert X.load_network(ours, d) == 8
+    for k, v in ref_net.state_dict().items():
+        assert torch.equal(v, ours.state_dict()[k]), k
+    ck = torch.load(_os.path.join(d, "latest.pth"))
+    assert len(ck["optim"]["param_groups"]) == 48
+    # -> flat Adam (what TrainStep.load_state_dict does), in TrainStep's own storage order
+    params = [p for m in (ours.model, ours.model_fine) for p in T.model_params(m)]
+    offsets, off = {}, 0
+    for p in params:
+        offsets[id(p)] = off
+        off += p.numel()
+    flat_sd = T.merge_adam_state(ck["optim"], list(ours.named_parameters()), offsets, off, torch.zeros(1))
+    flat = torch.nn.Parameter(torch.zeros(off))
+    flat_opt = torch.optim.Adam([flat], lr=1.0)
+    flat_opt.load_state_dict(flat_sd)
+    ref_state = opt.state_dict()["state"]
+    for i, (name, p) in enumerate(ours.named_parameters()):
+        o = offsets[id(p)]
+        assert torch.equal(flat_opt.state_dict()["state"][0]["exp_avg"][o:o + p.numel()].view_as(p), ref_state[i]["exp_avg"]), name
+    # <- and back: split, save with OUR writer, load with the REFERENCE's load_model into a fresh reference optimizer
+    split = T.split_adam_state(flat_opt.state_dict(), list(ours.named_parameters()), offsets)
+    d2 = str(tmp_path / "ourckpt")
+
+    class _Opt:
+        def state_dict(self):
+            return split
+    X.save_model(ours, _Opt(), _SD(), _SD(), d2, 3, last=True)
+    _, ref_net2, _ = ref_loader.build_reference(O.make_state_dict(5))
+    opt2 = make_optimizer(cfg, ref_net2)
+    assert net_utils.load_model(ref_net2, opt2, _SD(), _SD(), d2) == 4
+    for i in range(48):
+        assert torch.equal(opt2.state_dict()["state"][i]["exp_avg_sq"], ref_state[i]["exp_avg_sq"]), i
+    for k, v in ref_net.state_dict().items():
+        assert torch.equal(v, ref_net2.state_dict()[k]), k
+
+
 def test_flat_adam_state_speaks_the_reference_optimizer_layout():
     """TrainStep runs Adam over ONE flat tensor; the reference's optimizer (src/train/optimizer.py:14-19) has
     one param group per named parameter.  split_adam_state / merge_adam_state convert both ways: after identical steps
