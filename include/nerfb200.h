@@ -155,6 +155,11 @@ NERFB200_API int nerfb200_mlp_forward_train(const void* packed, int mode, const 
 /* W^T image for the backward dgrad chain; re-run after every optimizer step (1024-byte aligned). */
 NERFB200_API size_t nerfb200_packed_bwd_bytes(void);
 NERFB200_API int nerfb200_pack_weights_bwd(const nerfb200_mlp_weights* w, void* packed_bwd, void* stream);
+/* Same; packed_fwd (may be NULL): the image nerfb200_pack_weights(NERFB200_MODE_BF16) produced from the SAME weights
+ * earlier on the same stream -- the fused-tail product views_linears.0[:, :256] x feature_linear it carries is reused
+ * instead of being recomputed (the training step re-packs both images after every optimizer step). */
+NERFB200_API int nerfb200_pack_weights_bwd2(const nerfb200_mlp_weights* w, const void* packed_fwd, void* packed_bwd,
+                               void* stream);
 /* Gradients of the 24 tensors of one model given g_raw = dL/d raw [n_rows,4] (fp32) and the acts/masks of
  * nerfb200_mlp_forward_train on the same rows.  Two tcgen05 kernels: the activation-gradient chain
  * (keeps every dL/d pre-activation in the workspace) and nine split-K weight-gradient GEMMs with the bias

@@ -70,7 +70,11 @@ constexpr int kFusedChunks = 5;
 constexpr int kFusedChunkBytes = kFusedN * 128;                                   // 18432
 constexpr int kFusedStageOff = (kBf16TotalBytes + 1023) / 1024 * 1024;
 constexpr int kFusedTailOff = kFusedStageOff + kFusedChunks * kFusedChunkBytes;   // fp32 [256]: b'(128), alpha_b, 0...
-constexpr int kBf16PackedBytes = kFusedTailOff + 256 * 4;
+// fp32 scratch behind the image: the fused-tail product W' = Wv[:, :256] Wf ([128][256]) and b' ([128]), computed ONCE per
+// re-pack by fused_tail_product_kernel and read by the forward image's converter and by the backward image's pack
+constexpr int kFusedProdOff = (kFusedTailOff + 256 * 4 + 1023) / 1024 * 1024;
+constexpr int kFusedProdFloats = 128 * 256 + 128;
+constexpr int kBf16PackedBytes = kFusedProdOff + kFusedProdFloats * 4;
 
 // ---- split-fp16 layout (NERFB200_MODE_FP32_TC, bytes): the ten UNFUSED stages, every K-chunk as TWO images of the
 // bf16 geometry above -- [hi | lo], each N rows x 128 B, pre-swizzled -- holding w_hi = fp16(w * 2^e_s) and

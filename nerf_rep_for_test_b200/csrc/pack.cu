@@ -159,15 +159,50 @@ __device__ __forceinline__ float dot256_strided(const float* __restrict__ a, con
   return (v0 + v1) + (v2 + v3);
 }
 
-// fused stage 8F (mlp_layout.cuh): one thread per (n, k) of the [144][320] operand + the bias row
+// W' = Wv[:, :256] Wf and b' = Wv[:, :256] bf + bv in fp32, once per re-pack: thread = one column k of W' for four rows n
+// (Wf[j][k] is read coalesced and reused for the four rows, Wv[n][j] broadcast from shared memory).  Every element is
+// the same four-accumulator sum as dot256_strided (accumulator j % 4, increasing j, (v0+v1)+(v2+v3)), so the images are
+// bit-identical to what the per-element dots produced; the two per-element versions took 38 + 40 us per model and step.
+constexpr int kProdRows = 4;
+__global__ void __launch_bounds__(256) fused_tail_product_kernel(nerfb200_mlp_weights w, float* __restrict__ prod) {
+  __shared__ float a[kProdRows][256];
+  const int n0 = blockIdx.x * kProdRows, k = threadIdx.x;
+  for (int i = threadIdx.x; i < kProdRows * 256; i += 256) a[i >> 8][i & 255] = w.views_w[(size_t)(n0 + (i >> 8)) * 283 + (i & 255)];
+  __syncthreads();
+  float acc[kProdRows][4];
+#pragma unroll
+  for (int r = 0; r < kProdRows; ++r)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[r][q] = 0.f;
+#pragma unroll 2
+  for (int j = 0; j < 256; j += 4) {
+    float b[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) b[q] = w.feature_w[(size_t)(j + q) * 256 + k];
+#pragma unroll
+    for (int r = 0; r < kProdRows; ++r)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[r][q] = fmaf(a[r][j + q], b[q], acc[r][q]);
+  }
+#pragma unroll
+  for (int r = 0; r < kProdRows; ++r) prod[(size_t)(n0 + r) * 256 + k] = (acc[r][0] + acc[r][1]) + (acc[r][2] + acc[r][3]);
+  if (threadIdx.x < kProdRows) {   // b'[n]
+    const int n = n0 + threadIdx.x;
+    prod[128 * 256 + n] = w.views_b[n] + dot256_strided(w.views_w + (size_t)n * 283, w.feature_b, 1);
+  }
+}
+
+// fused stage 8F (mlp_layout.cuh): one thread per (n, k) of the [144][320] operand + the bias row; the product comes
+// from fused_tail_product_kernel (earlier on the same stream)
 __global__ void pack_bf16_fused_kernel(nerfb200_mlp_weights w, unsigned char* __restrict__ dst, bool f16) {
+  const float* prod = reinterpret_cast<const float*>(dst + kFusedProdOff);
   const int total = kFusedN * kFusedChunks * 64;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total + 256; i += gridDim.x * blockDim.x) {
     if (i >= total) {   // bias row
       int n = i - total;
       float v = 0.f;
       if (n < 128) {
-        v = w.views_b[n] + dot256_strided(w.views_w + (size_t)n * 283, w.feature_b, 1);
+        v = prod[128 * 256 + n];
       } else if (n == 128) {
         v = w.alpha_b[0];
       }
@@ -181,7 +216,7 @@ __global__ void pack_bf16_fused_kernel(nerfb200_mlp_weights w, unsigned char* __
     float v = 0.f;
     if (n < 128) {
       if (k < 256) {
-        v = dot256_strided(w.views_w + (size_t)n * 283, w.feature_w + k, 256);
+        v = prod[(size_t)n * 256 + k];
       } else if (k - 256 < kChD) {
         v = w.views_w[(size_t)n * 283 + k];
       }
@@ -202,7 +237,8 @@ __global__ void pack_bf16_fused_kernel(nerfb200_mlp_weights w, unsigned char* __
 }
 
 // backward image (train_layout.cuh): W^T chunks for the dgrad chain + fp32 head weights
-__global__ void pack_bf16_bwd_kernel(nerfb200_mlp_weights w, unsigned char* __restrict__ dst) {
+// prod (may be NULL): the W' product fused_tail_product_kernel left behind the forward image of the SAME weights
+__global__ void pack_bf16_bwd_kernel(nerfb200_mlp_weights w, unsigned char* __restrict__ dst, const float* __restrict__ prod) {
   const int b = blockIdx.y;
   if (b == kBwdStages) {
     float* tail = reinterpret_cast<float*>(dst + kBwdTailOff);
@@ -217,7 +253,7 @@ __global__ void pack_bf16_bwd_kernel(nerfb200_mlp_weights w, unsigned char* __re
     const int k = c * 64 + kk;   // output index of the layer = K of the dgrad GEMM
     float v = 0.f;
     if (b == 0) {   // fused tail W'[k][n] = sum_j Wv[k][j] Wf[j][n]  (same fp32 arithmetic as pack_bf16_fused_kernel)
-      v = dot256_strided(w.views_w + (size_t)k * 283, w.feature_w + n, 256);
+      v = prod != nullptr ? prod[(size_t)k * 256 + n] : dot256_strided(w.views_w + (size_t)k * 283, w.feature_w + n, 256);
     } else {
       const int layer = 8 - b;   // 7..1
       v = layer == 5 ? w.pts_w[5][(size_t)k * 319 + kChX + n] : w.pts_w[layer][(size_t)k * 256 + n];
@@ -261,6 +297,9 @@ extern "C" int nerfb200_pack_weights(const nerfb200_mlp_weights* w, int mode, vo
     pack_f16x2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*w, (unsigned char*)packed);
   } else {
     const bool f16 = mode == NERFB200_MODE_FP16;
+    fused_tail_product_kernel<<<128 / kProdRows, 256, 0, (cudaStream_t)stream>>>(
+        *w, reinterpret_cast<float*>((unsigned char*)packed + kFusedProdOff));
+    NB_LAUNCH_OK("fused_tail_product_kernel");
     pack_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*w, tab, (unsigned char*)packed, f16);
     NB_LAUNCH_OK("pack_bf16_kernel");
     pack_bf16_fused_kernel<<<96, 256, 0, (cudaStream_t)stream>>>(*w, (unsigned char*)packed, f16);
@@ -271,12 +310,17 @@ extern "C" int nerfb200_pack_weights(const nerfb200_mlp_weights* w, int mode, vo
 
 extern "C" size_t nerfb200_packed_bwd_bytes(void) { return (size_t)kBwdPackedBytes; }
 
-extern "C" int nerfb200_pack_weights_bwd(const nerfb200_mlp_weights* w, void* packed_bwd, void* stream) {
+extern "C" int nerfb200_pack_weights_bwd2(const nerfb200_mlp_weights* w, const void* packed_fwd, void* packed_bwd, void* stream) {
   NB_CHECK_ARG(w && packed_bwd, "pack_weights_bwd: null pointer");
-  NB_CHECK_ARG(((uintptr_t)packed_bwd & 1023) == 0, "pack_weights_bwd: buffer must be 1024-byte aligned");
+  NB_CHECK_ARG(((uintptr_t)packed_bwd & 1023) == 0 && ((uintptr_t)packed_fwd & 1023) == 0, "pack_weights_bwd: buffers must be 1024-byte aligned");
   for (int i = 1; i < 8; ++i) NB_CHECK_ARG(w->pts_w[i], "pack_weights_bwd: null pts_linears.%d", i);
   NB_CHECK_ARG(w->views_w && w->feature_w && w->alpha_w && w->rgb_w, "pack_weights_bwd: null head tensor");
-  pack_bf16_bwd_kernel<<<dim3(64, kBwdStages + 1), 256, 0, (cudaStream_t)stream>>>(*w, (unsigned char*)packed_bwd);
+  const float* prod = packed_fwd ? reinterpret_cast<const float*>((const unsigned char*)packed_fwd + kFusedProdOff) : nullptr;
+  pack_bf16_bwd_kernel<<<dim3(64, kBwdStages + 1), 256, 0, (cudaStream_t)stream>>>(*w, (unsigned char*)packed_bwd, prod);
   NB_LAUNCH_OK("pack_bf16_bwd_kernel");
   return 0;
+}
+
+extern "C" int nerfb200_pack_weights_bwd(const nerfb200_mlp_weights* w, void* packed_bwd, void* stream) {
+  return nerfb200_pack_weights_bwd2(w, nullptr, packed_bwd, stream);
 }

@@ -86,6 +86,7 @@ SIGNATURES = {
     "nerfb200_mlp_forward_train": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "nerfb200_packed_bwd_bytes": (C.c_size_t, []),
     "nerfb200_pack_weights_bwd": (C.c_int, [C.POINTER(MlpWeights), _vp, _vp]),
+    "nerfb200_pack_weights_bwd2": (C.c_int, [C.POINTER(MlpWeights), _vp, _vp, _vp]),
     "nerfb200_mlp_backward": (C.c_int, [_vp, C.POINTER(MlpWeights), _vp, _vp, _vp, C.c_longlong, _vp, C.c_size_t,
                                         C.POINTER(MlpGrads), _vp]),
     "nerfb200_train_fp32_acts_bytes": (C.c_size_t, [C.c_longlong]),

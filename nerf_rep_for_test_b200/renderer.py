@@ -261,7 +261,12 @@ class Renderer(PathRenderingMixin):
             buf = ent[1] if ent is not None else torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
             w, keep = _model_weight_struct(model)
             base = (buf.data_ptr() + 1023) & ~1023
-            L.check(self.lib.nerfb200_pack_weights_bwd(C.byref(w), C.c_void_p(base), L.stream_ptr()), "pack_weights_bwd")
+            # the bf16 forward image of the same parameter version carries the fused-tail product: reuse it
+            fwd = self._packed.get(which)
+            fwd_ptr = None
+            if fwd is not None and fwd[0] == key + (L.MODE_BF16,):
+                fwd_ptr = C.c_void_p(fwd[2])
+            L.check(self.lib.nerfb200_pack_weights_bwd2(C.byref(w), fwd_ptr, C.c_void_p(base), L.stream_ptr()), "pack_weights_bwd")
             ent = (key, buf, base, w, keep)     # the struct (and its tensors) are read again by mlp_backward
             self._packed["bwd_" + which] = ent
         return C.c_void_p(ent[2]), ent[3]
