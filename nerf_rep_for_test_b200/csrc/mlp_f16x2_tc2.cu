@@ -18,10 +18,13 @@
 //
 // Structure: the CTA-pair machinery of mlp_bf16_tc2.cu (cta_group::2, M = 256 = 128 rows of each CTA, each CTA
 // streams half of every weight chunk, 4-thread-role warp specialisation) with ONE tile slot per CTA: the hi and lo
-// images of a [128][256] activation tile are 128 KB of shared memory, so there is no second slot to ping-pong with
-// and a stage's epilogue is not hidden behind another slot's MMAs (it is ~20 % of the stage: 48 MMAs vs one
-// accumulator drain by eight warps).  Per CTA, 10 warps:
-//   warps 0-3 / 4-7  epilogue: row = (warp & 3) * 32 + lane, accumulator columns [0,128) / [128,256)
+// images of a [128][256] activation tile are 128 KB of shared memory, so there is no second slot to ping-pong with.
+// What hides part of the epilogue instead (it is ~20 % of a stage: 48 MMAs vs one accumulator drain by eight warps) is
+// a pipeline BETWEEN consecutive stages of the same tile: the accumulators of even / odd stages live in the two halves
+// of TMEM (512 columns), the epilogue drains a stage in two phases -- K-blocks 0,1 of the next A operand first, then
+// 2,3 -- and signals each phase separately, so the next stage's MMAs over K-blocks 0,1 run while K-blocks 2,3 are
+// still being converted.  Per CTA, 10 warps:
+//   warps 0-3 / 4-7  epilogue: row = (warp & 3) * 32 + lane, K-blocks {0, 2} / {1, 3} of the output (64 columns each)
 //   warp 8           producer: this CTA's half of the hi and lo image of every weight K-chunk (2-stage ring of 32 KB)
 //                    + the stage's fp32 bias block
 //   warp 9           rank 0: MMA issuer + TMEM allocator; rank 1: relay of "my half has landed" + allocator
@@ -49,7 +52,8 @@ constexpr uint32_t kOffBias = kOffBar + 256;
 constexpr uint32_t kSmemBytes = kOffBias + 2048;                // 231680 <= 232448
 constexpr int kLastStage = kStages - 1;                         // 9: views_linears.0
 
-enum { BAR_WFULL = 0, BAR_WEMPTY = 2, BAR_AREADY = 4, BAR_ACCFULL = 5, BAR_BFULL = 6, BAR_BEMPTY = 8, BAR_COUNT = 10 };
+// BAR_AREADY + 0: K-blocks 0,1 of the A operand (and the PE tile) are in place; + 1: K-blocks 2,3 (and the dir PE)
+enum { BAR_WFULL = 0, BAR_WEMPTY = 2, BAR_AREADY = 4, BAR_ACCFULL = 6, BAR_BFULL = 7, BAR_BEMPTY = 9, BAR_COUNT = 11 };
 
 // kind::f16 instruction descriptor: D fp32, A/B fp16 (format 0), both K-major, dense, M x N
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
@@ -143,30 +147,19 @@ __device__ __forceinline__ void epi32x(const uint32_t (&v)[32], const float4* __
   if (MODE == 1) sigma += (sg0 + sg1) + (sg2 + sg3);
 }
 
-// this thread's 128 accumulator columns of a 256-wide stage = K-blocks 0 and 1 behind hi_row / lo_row; TMEM loads
-// double-buffered
+// one K-block (64 accumulator columns at t_blk) of this thread's row -> the hi / lo image rows of that K-block
 template <int MODE>
-__device__ __forceinline__ void epi_stage128x(uint32_t t_acc, const float4* __restrict__ bias4, unsigned char* hi_row,
-                                              unsigned char* lo_row, int r7, float inv,
-                                              const float* __restrict__ alpha_w, float& sigma) {
+__device__ __forceinline__ void epi_block64x(uint32_t t_blk, const float4* __restrict__ bias4, unsigned char* hi_row,
+                                             unsigned char* lo_row, int r7, float inv,
+                                             const float* __restrict__ alpha_w, float& sigma) {
   uint32_t va[32], vb[32];
-  tmem_ld32(t_acc, va);
-  tmem_ld32(t_acc + 32u, vb);
+  tmem_ld32(t_blk, va);
+  tmem_ld32(t_blk + 32u, vb);
   tmem_ld_wait();
   pin32(va);
   pin32(vb);
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    epi32x<MODE>(va, bias4 + h * 16, hi_row + h * 16384, lo_row + h * 16384, 0, r7, inv, alpha_w + h * 64, sigma);
-    if (h < 1) tmem_ld32(t_acc + 64u, va);
-    epi32x<MODE>(vb, bias4 + h * 16 + 8, hi_row + h * 16384, lo_row + h * 16384, 4, r7, inv, alpha_w + h * 64 + 32, sigma);
-    if (h < 1) {
-      tmem_ld32(t_acc + 96u, vb);
-      tmem_ld_wait();
-      pin32(va);
-      pin32(vb);
-    }
-  }
+  epi32x<MODE>(va, bias4, hi_row, lo_row, 0, r7, inv, alpha_w, sigma);
+  epi32x<MODE>(vb, bias4 + 8, hi_row, lo_row, 4, r7, inv, alpha_w + 32, sigma);
 }
 
 // which on-chip buffer holds K-chunk c of a stage's input, and how many K = 16 steps it has
@@ -199,7 +192,8 @@ mlp_f16x2_tc2_kernel(const unsigned char* __restrict__ packed, const float* __re
       mbar_init(bar(BAR_WFULL + i), rank == 0 ? 2 : 1);   // leader: own producer + peer relay
       mbar_init(bar(BAR_WEMPTY + i), 1);
     }
-    mbar_init(bar(BAR_AREADY), 512);    // every epilogue thread of both CTAs signals the leader's copy
+    mbar_init(bar(BAR_AREADY + 0), 512);    // every epilogue thread of both CTAs signals the leader's copies
+    mbar_init(bar(BAR_AREADY + 1), 512);
     mbar_init(bar(BAR_ACCFULL), 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar(BAR_BFULL + s), 1);
@@ -207,7 +201,7 @@ mlp_f16x2_tc2_kernel(const unsigned char* __restrict__ packed, const float* __re
     }
     fence_mbar_init();
   }
-  if (warp == 9) tmem_alloc_2cta(tmem_slot, 256);
+  if (warp == 9) tmem_alloc_2cta(tmem_slot, 512);   // two accumulators: even / odd stages
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();   // peer barriers initialised before any remote arrive / multicast commit
@@ -230,12 +224,13 @@ mlp_f16x2_tc2_kernel(const unsigned char* __restrict__ packed, const float* __re
     const int w4 = warp & 3;
     const int row = w4 * 32 + lane;
     const int r7 = row & 7;
-    unsigned char* a_hi_row = smem_dyn + kOffAHi + (uint32_t)row * 128u + (uint32_t)half * 32768u;   // K-blocks 2*half, 2*half+1
-    unsigned char* a_lo_row = smem_dyn + kOffALo + (uint32_t)row * 128u + (uint32_t)half * 32768u;
+    unsigned char* a_hi_row = smem_dyn + kOffAHi + (uint32_t)row * 128u;   // + K-block * 16384
+    unsigned char* a_lo_row = smem_dyn + kOffALo + (uint32_t)row * 128u;
     const uint32_t pe_hi_row = smem_base + kOffPeHi + (uint32_t)row * 128u;
     const uint32_t pe_lo_row = smem_base + kOffPeLo + (uint32_t)row * 128u;
     const uint32_t t_acc = tmem_base + ((uint32_t)(w4 * 32) << 16);
-    const uint32_t b_ready_leader = mapa(bar(BAR_AREADY), 0);
+    const uint32_t b_ready0_leader = mapa(bar(BAR_AREADY + 0), 0);
+    const uint32_t b_ready1_leader = mapa(bar(BAR_AREADY + 1), 0);
     // partial (rgb, sigma) sums of the upper column half; aliases the first 2 KB of the A tile, which is dead
     // between the last stage's accumulator and the next tile's stage-0 epilogue
     float4* exch = reinterpret_cast<float4*>(smem_dyn + kOffAHi);
@@ -287,7 +282,8 @@ mlp_f16x2_tc2_kernel(const unsigned char* __restrict__ packed, const float* __re
             st_shared_v4(pe_lo_row + off, pe_lo[4 * q], pe_lo[4 * q + 1], pe_lo[4 * q + 2], pe_lo[4 * q + 3]);
           }
           fence_proxy_async_smem();
-          mbar_arrive_remote(b_ready_leader);
+          mbar_arrive_remote(b_ready0_leader);     // stage 0 reads the PE tile only: both phases are ready at once
+          mbar_arrive_remote(b_ready1_leader);
         }
         if (stage == kLastStage && it + 1 < my_pairs) prepare_tile(it + 1);   // overlaps the last stage's MMAs
         if (it < 0) break;
@@ -299,12 +295,13 @@ mlp_f16x2_tc2_kernel(const unsigned char* __restrict__ packed, const float* __re
         mbar_wait(bar(BAR_ACCFULL), full_phase, 0x100 + stage);
         full_phase ^= 1;
         tc_fence_after();
+        const uint32_t t_stage = t_acc + (uint32_t)(stage & 1) * 256u;   // even / odd stages use the two TMEM halves
         if (kDump && dump_tile) {   // diagnostic: fp32 post-activation outputs of rows 0..127 of the whole problem
           const int ncb = stage == kLastStage ? 2 : 4;
           const int c0 = stage == kLastStage ? half * 64 : half * 128;
           for (int cb = 0; cb < ncb; ++cb) {
             uint32_t v[32];
-            tmem_ld32(t_acc + (uint32_t)(c0 + cb * 32), v);
+            tmem_ld32(t_stage + (uint32_t)(c0 + cb * 32), v);
             tmem_ld_wait();
             pin32(v);
             for (int i = 0; i < 32; ++i) {
@@ -316,22 +313,30 @@ mlp_f16x2_tc2_kernel(const unsigned char* __restrict__ packed, const float* __re
           }
         }
         if (stage < kLastStage) {
-          const uint32_t ta = t_acc + (uint32_t)half * 128u;
-          const float4* b4 = bias4 + half * 32;
-          if (stage == 7) epi_stage128x<1>(ta, b4, a_hi_row, a_lo_row, r7, inv, tail + kTailAlphaW + half * 128, sigma);
-          else if (stage == 8) epi_stage128x<2>(ta, b4, a_hi_row, a_lo_row, r7, inv, nullptr, sigma);
-          else epi_stage128x<0>(ta, b4, a_hi_row, a_lo_row, r7, inv, nullptr, sigma);
-          if (stage == kLastStage - 1) {   // dir PE replaces the xyz PE tile (dead after stage 5): chunks 2*half, 2*half+1
+          // phase 0: K-block `half` (columns 64 half ..), phase 1: K-block 2 + half; each phase is handed to the MMA
+          // issuer on its own, so the next stage's MMAs over K-blocks 0,1 overlap the conversion of K-blocks 2,3
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              const uint32_t off = (uint32_t)(((half * 2 + q) ^ r7) << 4);
-              st_shared_v4(pe_hi_row + off, dpe_hi[4 * q], dpe_hi[4 * q + 1], dpe_hi[4 * q + 2], dpe_hi[4 * q + 3]);
-              st_shared_v4(pe_lo_row + off, dpe_lo[4 * q], dpe_lo[4 * q + 1], dpe_lo[4 * q + 2], dpe_lo[4 * q + 3]);
+          for (int ph = 0; ph < 2; ++ph) {
+            const int blk = 2 * ph + half;
+            const uint32_t tb = t_stage + (uint32_t)blk * 64u;
+            const float4* b4 = bias4 + blk * 16;
+            unsigned char* hr = a_hi_row + blk * 16384;
+            unsigned char* lr = a_lo_row + blk * 16384;
+            if (stage == 7) epi_block64x<1>(tb, b4, hr, lr, r7, inv, tail + kTailAlphaW + blk * 64, sigma);
+            else if (stage == 8) epi_block64x<2>(tb, b4, hr, lr, r7, inv, nullptr, sigma);
+            else epi_block64x<0>(tb, b4, hr, lr, r7, inv, nullptr, sigma);
+            if (ph == 1 && stage == kLastStage - 1) {   // dir PE replaces the xyz PE tile (dead after stage 5): chunks 2*half, 2*half+1
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                const uint32_t off = (uint32_t)(((half * 2 + q) ^ r7) << 4);
+                st_shared_v4(pe_hi_row + off, dpe_hi[4 * q], dpe_hi[4 * q + 1], dpe_hi[4 * q + 2], dpe_hi[4 * q + 3]);
+                st_shared_v4(pe_lo_row + off, dpe_lo[4 * q], dpe_lo[4 * q + 1], dpe_lo[4 * q + 2], dpe_lo[4 * q + 3]);
+              }
             }
+            tc_fence_before();
+            fence_proxy_async_smem();
+            mbar_arrive_remote(ph == 0 ? b_ready0_leader : b_ready1_leader);
           }
-          tc_fence_before();
-          fence_proxy_async_smem();
-          mbar_arrive_remote(b_ready_leader);
           mbar_arrive(bar(BAR_BEMPTY + bbuf));
         } else {
           // stage 9: views_linears.0 (128 wide, relu) -> rgb_linear on CUDA cores (network.py:66-69); this thread
@@ -341,7 +346,7 @@ mlp_f16x2_tc2_kernel(const unsigned char* __restrict__ packed, const float* __re
 #pragma unroll
           for (int cb = 0; cb < 2; ++cb) {
             uint32_t v[32];
-            tmem_ld32(t_acc + (uint32_t)(half * 64 + cb * 32), v);
+            tmem_ld32(t_stage + (uint32_t)(half * 64 + cb * 32), v);
             tmem_ld_wait();
             pin32(v);
 #pragma unroll
@@ -437,11 +442,18 @@ mlp_f16x2_tc2_kernel(const unsigned char* __restrict__ packed, const float* __re
       for (int stage = 0; stage < kStages; ++stage) {
         const int nch = stage_chunks(stage);
         const uint32_t idesc = umma_idesc_f16(256, stage_n(stage));
-        mbar_wait_cluster(bar(BAR_AREADY), ready_phase, 0x400 + stage);
-        ready_phase ^= 1;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(stage & 1) * 256u;
+        // chunks whose A operand is complete after the epilogue's first phase (K-blocks 0,1 + PE tile); the rest
+        // (K-blocks 2,3 and the dir PE of the last stage) wait for the second phase
+        const int first_part = stage == 0 ? 1 : (stage == 5 ? 3 : 2);
+        mbar_wait_cluster(bar(BAR_AREADY + 0), ready_phase, 0x400 + stage);
         tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < nch; ++c, ++seq) {
+          if (c == first_part) {
+            mbar_wait_cluster(bar(BAR_AREADY + 1), ready_phase, 0x480 + stage);
+            tc_fence_after();
+          }
           const uint32_t pos = seq % kRing, phase = (seq / kRing) & 1u;
           mbar_wait_cluster(bar(BAR_WFULL + pos), phase, 0x300 + stage);
           tc_fence_after();
@@ -456,15 +468,19 @@ mlp_f16x2_tc2_kernel(const unsigned char* __restrict__ packed, const float* __re
 #pragma unroll 1
             for (int k = 0; k < ksteps; ++k) {
               const uint32_t ko = 2u * (uint32_t)k;
-              umma_bf16_ss_2cta(tmem_base, hi64 | (ah + ko), hi64 | (bh + ko), idesc, (c > 0 || k > 0) ? 1u : 0u);
-              umma_bf16_ss_2cta(tmem_base, hi64 | (ah + ko), hi64 | (bl + ko), idesc, 1u);
-              umma_bf16_ss_2cta(tmem_base, hi64 | (al + ko), hi64 | (bh + ko), idesc, 1u);
+              umma_bf16_ss_2cta(d_tmem, hi64 | (ah + ko), hi64 | (bh + ko), idesc, (c > 0 || k > 0) ? 1u : 0u);
+              umma_bf16_ss_2cta(d_tmem, hi64 | (ah + ko), hi64 | (bl + ko), idesc, 1u);
+              umma_bf16_ss_2cta(d_tmem, hi64 | (al + ko), hi64 | (bh + ko), idesc, 1u);
             }
             umma_commit_2cta(bar(BAR_WEMPTY + pos), 3);                      // both CTAs' producers
             if (c == nch - 1) umma_commit_2cta(bar(BAR_ACCFULL), 3);        // both CTAs' epilogue warps
           }
           __syncwarp();
         }
+        if (nch <= first_part) {   // stage 0: a single PE chunk -- still consume the second phase of this stage
+          mbar_wait_cluster(bar(BAR_AREADY + 1), ready_phase, 0x480 + stage);
+        }
+        ready_phase ^= 1;
       }
     }
   }
@@ -473,7 +489,7 @@ mlp_f16x2_tc2_kernel(const unsigned char* __restrict__ packed, const float* __re
   cluster_sync_all();   // no CTA may exit (or free TMEM) while its peer still multicasts into it
   if (warp == 9) {
     tc_fence_after();
-    tmem_dealloc_2cta(tmem_base, 256);
+    tmem_dealloc_2cta(tmem_base, 512);
   }
 }
 
