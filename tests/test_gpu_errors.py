@@ -76,3 +76,30 @@ def test_kilo_argument_checks():
         kilo.generate_query_indices_on_ray([0, 0, 4], torch.zeros(4, 3, device=DEV), torch.zeros(4, 4, 4, dtype=torch.int32, device=DEV),
                                            torch.ones(4, dtype=torch.uint8, device=DEV), torch.zeros(4, dtype=torch.int32, device=DEV),
                                            [-1, -1, -1], [1, 1, 1], 0.01, 4, 16, 2.0, True)
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_renderer_on_a_non_current_device():
+    """the C ABI launches on the CURRENT device.  A network on cuda:1 rendered while cuda:0 is current must
+    run on cuda:1 (the Python entry points switch devices around every call; kernel attributes are per device) and give
+    the same image as the same network on cuda:0."""
+    from oracle import nerf_oracle as O
+    from nerf_rep_for_test_b200 import Network, RenderConfig, Renderer, ops
+    sd = O.make_state_dict(0, 30.0, 0.2)
+    outs = []
+    for idx in (0, 1):
+        dev = torch.device("cuda", idx)
+        net = Network(device=dev)
+        net.load_state_dict(sd)
+        net.to(dev).eval()
+        torch.cuda.set_device(0)                                  # cuda:0 stays current throughout
+        for mode in ("bf16", "fp32tc", "fp32"):
+            r = Renderer(net, RenderConfig(perturb=0, enable_ess=False, enable_ert=False), mode=mode)
+            b = O.lego_batch(12, 12)
+            out = r.render({k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in b.items()})
+            assert out["rgb_map"].device == dev
+            outs.append(out["rgb_map"].cpu())
+        z = ops.sample_coarse(torch.linspace(2, 6, 64, device=dev), 7)
+        assert z.device == dev
+    for a, b in zip(outs[:3], outs[3:]):
+        assert torch.equal(a, b)
