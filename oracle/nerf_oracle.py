@@ -8,7 +8,7 @@ library.
 Every function restates one piece of /root/reference (YuhhhZhao/NeRF-rep_for_test)
 with the SAME torch CPU ops in the SAME order, so that on one torch build the
 restatement is bit-identical to the real reference (asserted by
-tests/test_oracle_vs_reference.py whenever /root/reference is mounted, and
+tests/test_oracle.py::test_oracle_equals_live_reference whenever /root/reference is mounted, and
 pinned by the golden vectors under tests/golden/ that
 oracle/gen_golden.py produced from the real reference).
 
