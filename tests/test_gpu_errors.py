@@ -78,6 +78,57 @@ def test_kilo_argument_checks():
                                            [-1, -1, -1], [1, 1, 1], 0.01, 4, 16, 2.0, True)
 
 
+def test_round2_entry_points_empty_ragged_and_bad_arguments():
+    """The entry points added in round 2 (fp32 training twin, dL/dz, sample_pdf backward, literal ESS, jitter): empty
+    inputs are accepted and leave defined outputs, ragged sizes run, bad arguments are a non-zero return + message."""
+    from nerf_rep_for_test_b200 import training as T
+    r = _renderer()
+    lib = L.load()
+    tensors = T._tensors(r.coarse_model)
+    # ---- empty
+    e3, e64 = torch.zeros(0, 3, device=DEV), torch.zeros(0, 64, device=DEV)
+    raw, acts = ops.mlp_forward_train_fp32(tensors, e3, e3, e64)
+    assert raw.shape == (0, 64, 4) and acts.numel() == 0
+    grads, g_z = ops.mlp_backward_fp32(tensors, torch.zeros(0, 4, device=DEV), acts, e3, 0, 64, want_g_z=True)
+    torch.cuda.synchronize()
+    assert all(float(g.abs().max()) == 0.0 for g in grads) and g_z.shape == (0, 64)   # gradients are OVERWRITTEN: zeros
+    g_raw, gz = ops.composite_backward_z(torch.zeros(0, 64, 4, device=DEV), e64, e3, torch.zeros(0, 3, device=DEV))
+    assert g_raw.shape == (0, 64, 4) and gz.shape == (0, 64)
+    assert ops.sample_pdf_backward(e64, e64, torch.linspace(0, 1, 128, device=DEV), torch.zeros(0, 192, device=DEV)).shape == (0, 64)
+    grid = torch.ones(8, 8, 8, dtype=torch.uint8, device=DEV)
+    assert ops.ess_resample_compat(grid, e3, e3, torch.linspace(2, 6, 64, device=DEV)).shape == (0, 64)
+    assert ops.jitter_rows(e64).shape == (0, 64)
+    # ---- ragged: one ray, three samples (the smallest sample_pdf accepts), odd counts
+    for n, S, U in ((1, 3, 1), (5, 17, 33), (130, 64, 128)):
+        ro = torch.randn(n, 3, device=DEV) * 0.1
+        rd = torch.nn.functional.normalize(torch.randn(n, 3, device=DEV), dim=-1)
+        z = torch.sort(torch.rand(n, S, device=DEV) * 4 + 2, -1)[0]
+        raw, acts = ops.mlp_forward_train_fp32(tensors, ro, rd, z)
+        grads, g_z = ops.mlp_backward_fp32(tensors, torch.randn(n * S, 4, device=DEV), acts, rd, n, S, want_g_z=True)
+        w = ops.composite_forward(raw, z, rd)[3]
+        u = torch.linspace(0, 1, U, device=DEV)
+        z_all = ops.sample_pdf_merge(z, w, u, want_aux=False)[0]
+        g_w = ops.sample_pdf_backward(z, w, u, torch.randn(n, S + U, device=DEV))
+        torch.cuda.synchronize()
+        assert bool(torch.isfinite(g_z).all()) and bool(torch.isfinite(g_w).all()) and all(bool(torch.isfinite(g).all()) for g in grads)
+        assert bool((z_all[:, 1:] >= z_all[:, :-1]).all())
+    # ---- bad arguments
+    with pytest.raises(L.NerfB200Error):                      # g_z_all of the wrong width
+        ops.sample_pdf_backward(torch.zeros(4, 64, device=DEV), torch.zeros(4, 64, device=DEV), torch.linspace(0, 1, 128, device=DEV),
+                                torch.zeros(4, 100, device=DEV))
+    with pytest.raises(L.NerfB200Error):                      # literal ESS needs n_samples <= 64 (one 64-bit mask per ray)
+        ops.ess_resample_compat(grid, torch.zeros(2, 3, device=DEV), torch.ones(2, 3, device=DEV), torch.linspace(2, 6, 65, device=DEV))
+    with pytest.raises(L.NerfB200Error):                      # fp32 backward: g_raw of the wrong batch
+        ops.mlp_backward_fp32(tensors, torch.zeros(7, 4, device=DEV), acts, rd, n, S)
+    w_struct, keep = ops.weights_struct(tensors)
+    rc = lib.nerfb200_mlp_backward_fp32(C.byref(w_struct), L.dev(torch.zeros(64, 4, device=DEV)), L.dev(torch.zeros(1 << 20, dtype=torch.uint8, device=DEV)),
+                                        None, 1, 64, L.dev(torch.zeros(16, dtype=torch.uint8, device=DEV)), 16, C.byref(L.MlpGrads()), None, L.stream_ptr())
+    assert rc != 0 and b"null gradient" in lib.nerfb200_get_last_error_string()
+    with pytest.raises(L.NerfB200Error):                      # reference graph in bf16 needs the workspace of the backward
+        ops.mlp_backward_input(r.packed_bwd("fine"), None, torch.zeros(2, 3, device=DEV), torch.ones(2, 3, device=DEV),
+                               torch.zeros(2, 64, device=DEV))
+
+
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs two GPUs")
 def test_renderer_on_a_non_current_device():
     """the C ABI launches on the CURRENT device.  A network on cuda:1 rendered while cuda:0 is current must
