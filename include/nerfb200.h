@@ -197,6 +197,18 @@ NERFB200_API int nerfb200_mlp_backward_input(const nerfb200_mlp_weights* weights
                                 const float* rays_o, const float* rays_d, const float* z_vals, int n_rays,
                                 int n_samples, float* g_z, void* stream);
 
+/* The small end of the training step, one kernel each instead of torch's ten / its 19-block multi-tensor launch.
+ * mse_pair_grad: loss of trainers/nerf.py:52-65, loss[0] = mse(rgb_map_0, t) + mse(rgb_map, t) (device float, overwritten)
+ * and its gradients g_rgb0 = 2 (rgb_map_0 - t) / (3 n_rays), g_rgb likewise (all [n_rays,3]).
+ * adam_clip_step: clip_grad_value_(clip_value) (trainer.py:59; 0 = no clipping) + torch.optim.Adam (optimizer.py:8-28:
+ * amsgrad off, weight_decay 0) over flat fp32 buffers of n elements, in place; `step` counts from 1; grads are first
+ * multiplied by grad_scale (gradient averaging) and are written back clamped. */
+NERFB200_API int nerfb200_mse_pair_grad(const float* rgb0, const float* rgb, const float* target, int n_rays,
+                           float* g_rgb0, float* g_rgb, float* loss, void* stream);
+NERFB200_API int nerfb200_adam_clip_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n,
+                            float lr, float beta1, float beta2, float eps, long long step, float clip_value,
+                            float grad_scale, void* stream);
+
 /* diagnostic twin of mlp_forward (BF16 mode): additionally writes the fp32 post-activation output
  * of each of the ten stages (mlp_layout.cuh) for rows 0..127 into stage_dump [10][128][256];
  * used by the stage-level parity tests. */

@@ -175,6 +175,27 @@ def mlp_backward_input(bwd, ws, rays_o, rays_d, z_vals):
     return g_z
 
 
+def mse_pair_grad(rgb0, rgb, target):
+    """(loss [1], g_rgb0, g_rgb) of mse(rgb0, t) + mse(rgb, t) in one kernel."""
+    rgb0, rgb, target = _f(rgb0), _f(rgb), _f(target)
+    n = rgb0.shape[0]
+    g0, g1 = torch.empty_like(rgb0), torch.empty_like(rgb)
+    loss = torch.empty(1, device=rgb0.device)
+    L.check(L.load().nerfb200_mse_pair_grad(L.dev(rgb0), L.dev(rgb), L.dev(target), n, L.dev(g0), L.dev(g1), L.dev(loss),
+                                           L.stream_ptr()), "mse_pair_grad")
+    return loss, g0, g1
+
+
+def adam_clip_step(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, clip_value=0.0, grad_scale=1.0):
+    """clip_grad_value_ + Adam over flat fp32 CUDA buffers, in place (one kernel)."""
+    for t in (params, grads, exp_avg, exp_avg_sq):
+        if not (t.is_cuda and t.dtype == F32 and t.is_contiguous() and t.numel() == params.numel()):
+            raise L.NerfB200Error("adam_clip_step: flat contiguous fp32 CUDA buffers of equal size expected")
+    L.check(L.load().nerfb200_adam_clip_step(L.dev(params), L.dev(grads), L.dev(exp_avg), L.dev(exp_avg_sq), params.numel(),
+                                            float(lr), float(beta1), float(beta2), float(eps), int(step), float(clip_value),
+                                            float(grad_scale), L.stream_ptr()), "adam_clip_step")
+
+
 def mlp_forward_stages(packed, rays_o, rays_d, z_vals):
     """BF16 mode diagnostic: (raw, stage_dump [10,128,256]) -- fp32 stage outputs of rows 0..127."""
     rays_o, rays_d, z_vals = _f(rays_o), _f(rays_d), _f(z_vals)

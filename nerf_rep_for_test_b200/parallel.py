@@ -51,15 +51,18 @@ class FlatGradAllReduce:
             raise RuntimeError("FlatGradAllReduce.start needs the aliased flat buffer")
         return dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, async_op=True)
 
-    def finish(self, handles):
-        """Wait for the started pieces (the current stream waits, not the host) and turn the sums into means."""
+    def finish(self, handles, scale=True):
+        """Wait for the started pieces (the current stream waits, not the host) and turn the sums into means
+        (scale=False: the caller folds the 1 / world_size into its optimizer kernel).  Returns 1 / world_size."""
         world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         if world == 1:
-            return
+            return 1.0
         for h in handles:
             if h is not None:
                 h.wait()
-        self.flat.mul_(1.0 / world)
+        if scale:
+            self.flat.mul_(1.0 / world)
+        return 1.0 / world
 
     def __call__(self):
         world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1

@@ -230,7 +230,7 @@ class TrainStep:
     tensor (set_lr); raw_noise_std > 0 falls back to the eager step (its seed is a kernel argument).  Inputs must keep
     their shape; a capture failure falls back to the eager step with a warning."""
 
-    def __init__(self, renderer, lr=5e-4, graph=False, precision="bf16", ref_compat_sampler=False):
+    def __init__(self, renderer, lr=5e-4, graph=False, precision="bf16", ref_compat_sampler=False, fused_update=True):
         from .parallel import FlatGradAllReduce
         if precision not in ("bf16", "fp32"):
             raise ValueError("precision must be 'bf16' or 'fp32'")
@@ -263,6 +263,20 @@ class TrainStep:
         self.opt = torch.optim.Adam([self.flat_param], lr=lr_arg, eps=1e-8, fused=True, capturable=self.use_graph)
         self.allreduce = FlatGradAllReduce(self.params, flat=self.flat)
         self._graph, self._static, self._loss, self._warm = None, None, None, 0
+        # fused_update: the loss gradient and clip + Adam run as one kernel of this library each (nerfb200_mse_pair_grad,
+        # nerfb200_adam_clip_step) instead of ten torch launches and torch's 19-block multi-tensor Adam; the moments live
+        # in self.opt's own state tensors, so state_dict() / load_state_dict() are unchanged.  The graph-captured step
+        # keeps torch's capturable Adam (its step counter has to live on the device).
+        self.fused_update = bool(fused_update) and not self.use_graph
+        self._t = 0
+
+    def _adam_state(self):
+        st = self.opt.state[self.flat_param]
+        if "exp_avg" not in st:
+            st["step"] = torch.zeros((), dtype=torch.float32, device=self.flat_param.device)
+            st["exp_avg"] = torch.zeros_like(self.flat_param.data)
+            st["exp_avg_sq"] = torch.zeros_like(self.flat_param.data)
+        return st
 
     # ---- checkpoint interface of the optimizer the reference hands to net_utils.save_model / load_model ------------
     def _offsets(self):
@@ -275,6 +289,8 @@ class TrainStep:
     def state_dict(self):
         """Adam state in the REFERENCE's layout (one param group per named parameter, net.named_parameters() order,
         src/train/optimizer.py:14-19): pass the TrainStep itself as `optim` to extras.save_model / load_model."""
+        if self.fused_update and self._t > 0:
+            self._adam_state()["step"].fill_(float(self._t))
         return split_adam_state(self.opt.state_dict(), list(self.r.net.named_parameters()), self._offsets())
 
     def load_state_dict(self, sd):
@@ -286,6 +302,8 @@ class TrainStep:
         if torch.is_tensor(lr):                                 # capturable / graph mode keeps lr in a device tensor
             lr.fill_(float(self.opt.param_groups[0]["lr"]))
             self.opt.param_groups[0]["lr"] = lr
+        st = self.opt.state.get(self.flat_param, {})
+        self._t = int(round(float(st["step"]))) if "step" in st else 0
 
     @property
     def param_groups(self):
@@ -314,19 +332,31 @@ class TrainStep:
         st = _forward_passes(r, rays_o, rays_d, self.precision, z_c=self._coarse_z(rays_o.shape[0], in_graph))
         rgb0, rgb = st["maps"][0], st["maps"][4]
         # loss = mean((rgb0 - t)^2) + mean((rgb - t)^2)  (trainers/nerf.py:52-65)  ->  dL/d map = 2 (map - t) / (3 n)
-        d0, d1 = rgb0 - target_rgb, rgb - target_rgb
-        loss = (d0 * d0).mean() + (d1 * d1).mean()
-        scale = 2.0 / d0.numel()
+        if self.fused_update:
+            loss, g0, g1 = ops.mse_pair_grad(rgb0, rgb, target_rgb)
+            loss = loss[0]
+        else:
+            d0, d1 = rgb0 - target_rgb, rgb - target_rgb
+            loss = (d0 * d0).mean() + (d1 * d1).mean()
+            g0, g1 = d0 * (2.0 / d0.numel()), d1 * (2.0 / d0.numel())
         # gradient all-reduce in two pieces of the flat buffer (coarse parameters first, then fine): the fine piece is
         # started as soon as the fine backward is enqueued and overlaps the coarse network's backward
         handles = []
-        _backward_passes(r, st, rays_o, rays_d, (d0 * scale, None, None), (d1 * scale, None, None), self.ref_compat_sampler,
+        _backward_passes(r, st, rays_o, rays_d, (g0, None, None), (g1, None, None), self.ref_compat_sampler,
                          grads_c=self.grad_views["coarse"], grads_f=self.grad_views["fine"],
                          after_fine=lambda: handles.append(self.allreduce.start(self.n_coarse, self.flat.numel())))
         handles.append(self.allreduce.start(0, self.n_coarse))
-        self.allreduce.finish(handles)
-        self.flat.clamp_(-40.0, 40.0)          # clip_grad_value_(params, 40) on the aliased buffer
-        self.opt.step()
+        if self.fused_update:
+            # averaging over the ranks, clip_grad_value_(params, 40) (trainer.py:59) and Adam in one kernel
+            inv_world = self.allreduce.finish(handles, scale=False)
+            ast, g = self._adam_state(), self.opt.param_groups[0]
+            self._t += 1
+            ops.adam_clip_step(self.flat_param.data, self.flat, ast["exp_avg"], ast["exp_avg_sq"], g["lr"], g["betas"][0],
+                               g["betas"][1], g["eps"], self._t, clip_value=40.0, grad_scale=inv_world)
+        else:
+            self.allreduce.finish(handles)
+            self.flat.clamp_(-40.0, 40.0)          # clip_grad_value_(params, 40) on the aliased buffer
+            self.opt.step()
         r.invalidate_weights()
         return loss
 

@@ -386,3 +386,49 @@ def test_bf16_training_with_the_reference_graph():
     # 0.170 -> 0.10): the coarse trunk's update direction is dominated by the ill-conditioned sampler path
     assert losses[-1] < 0.98 * losses[0], losses[::5]
     assert all(torch.isfinite(p).all() for p in net.parameters())
+
+
+def test_fused_loss_and_adam_kernels_match_torch():
+    """nerfb200_mse_pair_grad against torch's mse + autograd, nerfb200_adam_clip_step against clip_grad_value_ +
+    torch.optim.Adam(fused=True) over five steps (same formulas: parameters agree to fp32 rounding), and a TrainStep with
+    the fused update against one with torch's optimizer."""
+    from nerf_rep_for_test_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    n = 777
+    rgb0, rgb, t = (torch.rand(n, 3, generator=g).to(DEV) for _ in range(3))
+    a, b = rgb0.clone().requires_grad_(True), rgb.clone().requires_grad_(True)
+    ref = torch.nn.functional.mse_loss(a, t) + torch.nn.functional.mse_loss(b, t)
+    ref.backward()
+    loss, g0, g1 = ops.mse_pair_grad(rgb0, rgb, t)
+    assert abs(float(loss) - float(ref)) <= 1e-6 * float(ref)
+    assert torch.allclose(g0, a.grad, rtol=1e-6, atol=1e-9) and torch.allclose(g1, b.grad, rtol=1e-6, atol=1e-9)
+    m = 100003
+    p_ref = torch.nn.Parameter(torch.randn(m, generator=g).to(DEV))
+    p, mom, var = p_ref.detach().clone(), torch.zeros(m, device=DEV), torch.zeros(m, device=DEV)
+    opt = torch.optim.Adam([p_ref], lr=5e-4, eps=1e-8, fused=True)
+    for step in range(1, 6):
+        grad = (torch.randn(m, generator=g) * (60.0 if step == 2 else 1.0)).to(DEV)     # step 2 exercises the clip
+        p_ref.grad = grad.clone()
+        torch.nn.utils.clip_grad_value_([p_ref], 40.0)
+        opt.step()
+        gbuf = grad.clone() * 2.0
+        ops.adam_clip_step(p, gbuf, mom, var, 5e-4, 0.9, 0.999, 1e-8, step, clip_value=40.0, grad_scale=0.5)
+        assert torch.equal(gbuf, p_ref.grad)                                            # scaled + clamped gradient written back
+    st = opt.state[p_ref]
+    assert torch.allclose(mom, st["exp_avg"], rtol=1e-6, atol=1e-9) and torch.allclose(var, st["exp_avg_sq"], rtol=1e-6, atol=1e-12)
+    assert float((p - p_ref.detach()).abs().max()) <= 2e-6      # a few ulp of |p| <= 4 after five updates
+    # whole step: fused update vs torch's optimizer from the same initial state
+    outs = []
+    for fused in (True, False):
+        sd, net, r, ro, rd, target = _setup(seed=5, gain=10.0, bias=0.0, n=256)
+        net.eval()
+        r.perturb = 0
+        step = T.TrainStep(r, fused_update=fused)
+        losses = [float(step(ro.to(DEV), rd.to(DEV), target.to(DEV))) for _ in range(6)]
+        outs.append((losses, [q.detach().clone() for q in net.parameters()], step))
+    for la, lb in zip(outs[0][0], outs[1][0]):
+        assert abs(la - lb) <= 2e-5 * max(abs(lb), 1e-3), (outs[0][0], outs[1][0])
+    for qa, qb in zip(outs[0][1], outs[1][1]):
+        assert float((qa - qb).abs().max()) <= 1e-3
+    sa, sb = outs[0][2].state_dict(), outs[1][2].state_dict()
+    assert float(sa["state"][0]["step"]) == float(sb["state"][0]["step"]) == 6.0 and len(sa["state"]) == 48
