@@ -202,11 +202,12 @@ NERFB200_API int nerfb200_mlp_backward_input(const nerfb200_mlp_weights* weights
  * and its gradients g_rgb0 = 2 (rgb_map_0 - t) / (3 n_rays), g_rgb likewise (all [n_rays,3]).
  * adam_clip_step: clip_grad_value_(clip_value) (trainer.py:59; 0 = no clipping) + torch.optim.Adam (optimizer.py:8-28:
  * amsgrad off, weight_decay 0) over flat fp32 buffers of n elements, in place; `step` counts from 1; grads are first
- * multiplied by grad_scale (gradient averaging) and are written back clamped. */
+ * multiplied by grad_scale (gradient averaging) and are written back clamped.  The hyper-parameters are doubles: torch forms
+ * 1 - beta and the bias corrections in double before rounding to fp32, and so does this entry. */
 NERFB200_API int nerfb200_mse_pair_grad(const float* rgb0, const float* rgb, const float* target, int n_rays,
                            float* g_rgb0, float* g_rgb, float* loss, void* stream);
 NERFB200_API int nerfb200_adam_clip_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n,
-                            float lr, float beta1, float beta2, float eps, long long step, float clip_value,
+                            double lr, double beta1, double beta2, double eps, long long step, float clip_value,
                             float grad_scale, void* stream);
 
 /* diagnostic twin of mlp_forward (BF16 mode): additionally writes the fp32 post-activation output

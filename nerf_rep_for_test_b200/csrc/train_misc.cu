@@ -37,13 +37,15 @@ __global__ void __launch_bounds__(256) mse_pair_grad_kernel(const float* __restr
 // p -= (lr / bc1) * exp_avg / (sqrt(exp_avg_sq) / sqrt(bc2) + eps).  g is first scaled (gradient averaging) and clamped
 // to [-clip, clip]; the clamped value is written back so that .grad reads as after clip_grad_value_.
 __global__ void __launch_bounds__(256) adam_clip_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
-                                                        float* __restrict__ v, long long n, float lr_over_bc1, float beta1,
-                                                        float beta2, float eps, float inv_sqrt_bc2, float clip, float grad_scale) {
+                                                        float* __restrict__ v, long long n, float lr_over_bc1, float one_minus_beta1,
+                                                        float beta2, float one_minus_beta2, float eps, float inv_sqrt_bc2, float clip,
+                                                        float grad_scale) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float gi = g[i] * grad_scale;
     if (clip > 0.f) gi = fminf(fmaxf(gi, -clip), clip);
-    const float mi = m[i] + (1.f - beta1) * (gi - m[i]);
-    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    // 1 - beta is formed in double on the host as torch does (1.f - 0.999f is 4.7e-5 off 0.001)
+    const float mi = m[i] + one_minus_beta1 * (gi - m[i]);
+    const float vi = beta2 * v[i] + one_minus_beta2 * gi * gi;
     const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
     p[i] -= lr_over_bc1 * (mi / denom);
     g[i] = gi; m[i] = mi; v[i] = vi;
@@ -69,18 +71,19 @@ extern "C" int nerfb200_mse_pair_grad(const float* rgb0, const float* rgb, const
   return 0;
 }
 
-extern "C" int nerfb200_adam_clip_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
-                                       float beta1, float beta2, float eps, long long step, float clip_value, float grad_scale,
+extern "C" int nerfb200_adam_clip_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n, double lr,
+                                       double beta1, double beta2, double eps, long long step, float clip_value, float grad_scale,
                                        void* stream) {
   NB_CHECK_ARG(n >= 0 && step >= 1, "adam_clip_step: bad n / step (step counts from 1)");
-  NB_CHECK_ARG(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f, "adam_clip_step: bad hyper-parameters");
+  NB_CHECK_ARG(beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0 && eps >= 0.0, "adam_clip_step: bad hyper-parameters");
   if (n == 0) return 0;
   NB_CHECK_ARG(params && grads && exp_avg && exp_avg_sq, "adam_clip_step: null pointer");
-  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
   int blocks = ceil_div(n, 256 * 4);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  adam_clip_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, (float)((double)lr / bc1), beta1, beta2,
-                                                            eps, (float)(1.0 / sqrt(bc2)), clip_value, grad_scale);
+  adam_clip_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, (float)(lr / bc1),
+                                                            (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps,
+                                                            (float)(1.0 / sqrt(bc2)), clip_value, grad_scale);
   NB_LAUNCH_OK("adam_clip_kernel");
   return 0;
 }

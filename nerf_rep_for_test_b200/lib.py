@@ -99,7 +99,7 @@ SIGNATURES = {
     "nerfb200_sample_pdf_backward": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
     "nerfb200_mlp_backward_input": (C.c_int, [C.POINTER(MlpWeights), _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp]),
     "nerfb200_mse_pair_grad": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp]),
-    "nerfb200_adam_clip_step": (C.c_int, [_vp, _vp, _vp, _vp, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float,
+    "nerfb200_adam_clip_step": (C.c_int, [_vp, _vp, _vp, _vp, C.c_longlong, C.c_double, C.c_double, C.c_double, C.c_double,
                                           C.c_longlong, C.c_float, C.c_float, _vp]),
     "nerfb200_mlp_forward_stages": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "nerfb200_composite_forward": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
