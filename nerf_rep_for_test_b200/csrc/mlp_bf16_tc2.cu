@@ -208,12 +208,24 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
             }
           }
         }
+#ifndef NB_SAVE_DIRECT
         if (kSave) named_bar_sync(1 + slot, 128);   // all copies of the previous stage's tile are done: A may be rewritten
+#endif
         if (stage < I::kLast) {
           uint32_t mw[8];
-          if (!kFused && stage == 7) epi_stage256<1, kSave, kF16>(t_acc, bias4, a_row_base, r7, tail + kTailAlphaW, sigma, mw);
+          // NB_SAVE_DIRECT (experiment, off): the bf16 stage output also goes straight from the epilogue's registers to
+          // its tile image in the activation store instead of being copied out of shared memory after the hand-off (the
+          // copy takes ~5000 cycles during which the group cannot start its next epilogue: per-slot period = epilogue +
+          // copy = 7000 cycles against two MMA passes = 5400).  Measured SLOWER (4.47 -> 4.87 ms per step): with one row
+          // per thread every warp-wide 16-byte store touches 32 different 128-byte lines and the epilogue grows from
+          // ~1600 to ~9500 cycles (profiles/r02_experiments_not_merged.txt).
+          unsigned char* g_row = nullptr;
+#ifdef NB_SAVE_DIRECT
+          if (kSave && tile_ok && stage < 8) g_row = acts_tile + (size_t)act_h(stage) * kBlockBytes + (size_t)row * 128u;
+#endif
+          if (!kFused && stage == 7) epi_stage256<1, kSave, kF16>(t_acc, bias4, a_row_base, r7, tail + kTailAlphaW, sigma, mw, g_row);
           else if (!kFused && stage == 8) epi_stage256<2, false, kF16>(t_acc, bias4, a_row_base, r7, nullptr, sigma);
-          else epi_stage256<0, kSave, kF16>(t_acc, bias4, a_row_base, r7, nullptr, sigma, mw);
+          else epi_stage256<0, kSave, kF16>(t_acc, bias4, a_row_base, r7, nullptr, sigma, mw, g_row);
           if (stage == I::kLast - 1) {  // dir PE replaces the xyz PE tile (dead after stage 5) for the views stage
             float f[32];
             pos_enc_row<kLd>(d_cur, f);
@@ -230,9 +242,12 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
           if (!kSave || save_leader) mbar_arrive_remote(b_ready_leader);
           mbar_arrive(bar(BAR_BEMPTY + bbuf));
           if (tl_on) tl[720 + ((it * 10 + stage) * 2 + slot) * 4 + 2] = clock64();
-          if (kSave && tile_ok) {   // stage output (= next stage's A tile) -> activation store, while the MMAs read it too
+          if (kSave && tile_ok) {
+#ifndef NB_SAVE_DIRECT
+            // stage output (= next stage's A tile) -> activation store, while the MMAs read it too
             copy_tile_s2g<4 * kBlockBytes>(acts_tile + (size_t)act_h(stage) * kBlockBytes,
                                            smem_dyn + kOffA + slot * kABytes, row, dbg);
+#endif
             if (stage == I::kLast - 1)
               copy_tile_s2g<kBlockBytes>(acts_tile + (size_t)kActDpe * kBlockBytes, smem_dyn + kOffPe + slot * kPeBytes, row);
           }

@@ -59,10 +59,12 @@ __device__ __forceinline__ void pin32(uint32_t (&r)[32]) {
 // Plain C++ shared-memory accesses (not volatile asm) so the compiler batches the bias loads.
 // kMask (training forward): additionally returns the relu sign bits of the 32 columns in the bit order
 // of train_layout.cuh (column 4s+k -> bit 8k+7-s, set = negative), built with one funnel shift per value.
+// gout_row (training forward, may be NULL): the same 16-byte chunks also go straight to this row of the activation
+// store's tile image in global memory (same swizzled position: a thread's eight chunks of a block are one 128-byte line).
 template <int MODE, bool kMask = false, bool kF16 = false>
 __device__ __forceinline__ void epi32(const uint32_t (&v)[32], const float4* __restrict__ bias4, unsigned char* out_row,
                                       int j0, int r7, const float* __restrict__ alpha_w, float& sigma,
-                                      uint32_t* mask_word = nullptr) {
+                                      uint32_t* mask_word = nullptr, unsigned char* gout_row = nullptr) {
   uint32_t ch0 = 0, ch1 = 0, ch2 = 0, ch3 = 0;
   float4 b[8];
 #pragma unroll
@@ -97,6 +99,7 @@ __device__ __forceinline__ void epi32(const uint32_t (&v)[32], const float4* __r
     o.x = cvt_bf16x2<kRelu, kF16>(x0.x, x0.y); o.y = cvt_bf16x2<kRelu, kF16>(x1.x, x1.y);
     o.z = cvt_bf16x2<kRelu, kF16>(x2.x, x2.y); o.w = cvt_bf16x2<kRelu, kF16>(x3.x, x3.y);
     *reinterpret_cast<uint4*>(out_row + (((j0 + q) ^ r7) << 4)) = o;
+    if (kMask && gout_row != nullptr) *reinterpret_cast<uint4*>(gout_row + (((j0 + q) ^ r7) << 4)) = o;
   }
   if (kMask) *mask_word = ch0 | (ch1 << 8) | (ch2 << 16) | (ch3 << 24);
 }
@@ -105,7 +108,7 @@ __device__ __forceinline__ void epi32(const uint32_t (&v)[32], const float4* __r
 template <int MODE, bool kMask = false, bool kF16 = false>
 __device__ __forceinline__ void epi_stage256(uint32_t t_acc, const float4* __restrict__ bias4, unsigned char* a_row_base,
                                              int r7, const float* __restrict__ alpha_w, float& sigma,
-                                             uint32_t* mw = nullptr) {
+                                             uint32_t* mw = nullptr, unsigned char* g_row_base = nullptr) {
   uint32_t va[32], vb[32];
   tmem_ld32(t_acc, va);
   tmem_ld32(t_acc + 32u, vb);
@@ -115,9 +118,10 @@ __device__ __forceinline__ void epi_stage256(uint32_t t_acc, const float4* __res
 #pragma unroll
   for (int h = 0; h < 4; ++h) {   // K-block h of the A operand = columns 64h .. 64h+63
     unsigned char* out_row = a_row_base + h * 16384;
-    epi32<MODE, kMask, kF16>(va, bias4 + h * 16, out_row, 0, r7, alpha_w + h * 64, sigma, mw + 2 * h);
+    unsigned char* gout_row = g_row_base != nullptr ? g_row_base + h * 16384 : nullptr;
+    epi32<MODE, kMask, kF16>(va, bias4 + h * 16, out_row, 0, r7, alpha_w + h * 64, sigma, mw + 2 * h, gout_row);
     if (h < 3) tmem_ld32(t_acc + (uint32_t)(h * 64 + 64), va);
-    epi32<MODE, kMask, kF16>(vb, bias4 + h * 16 + 8, out_row, 4, r7, alpha_w + h * 64 + 32, sigma, mw + 2 * h + 1);
+    epi32<MODE, kMask, kF16>(vb, bias4 + h * 16 + 8, out_row, 4, r7, alpha_w + h * 64 + 32, sigma, mw + 2 * h + 1, gout_row);
     if (h < 3) {
       tmem_ld32(t_acc + (uint32_t)(h * 64 + 96), vb);
       tmem_ld_wait();
