@@ -216,9 +216,10 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
           // NB_SAVE_DIRECT (experiment, off): the bf16 stage output also goes straight from the epilogue's registers to
           // its tile image in the activation store instead of being copied out of shared memory after the hand-off (the
           // copy takes ~5000 cycles during which the group cannot start its next epilogue: per-slot period = epilogue +
-          // copy = 7000 cycles against two MMA passes = 5400).  Measured SLOWER (4.47 -> 4.87 ms per step): with one row
-          // per thread every warp-wide 16-byte store touches 32 different 128-byte lines and the epilogue grows from
-          // ~1600 to ~9500 cycles (profiles/r02_experiments_not_merged.txt).
+          // copy = 7000 cycles against two MMA passes = 5400).  Measured: with 16-byte stores SLOWER (4.47 -> 4.87 ms per
+          // step: one row per thread, so every warp-wide store touches 32 different 128-byte lines and the epilogue grows
+          // from ~1600 to ~9500 cycles); with 256-bit stores (STG.256, full sectors) the epilogue takes 5700-6900 cycles
+          // and the step 4.43-4.51 ms -- the same as the copy scheme (profiles/r02_experiments_not_merged.txt).
           unsigned char* g_row = nullptr;
 #ifdef NB_SAVE_DIRECT
           if (kSave && tile_ok && stage < 8) g_row = acts_tile + (size_t)act_h(stage) * kBlockBytes + (size_t)row * 128u;

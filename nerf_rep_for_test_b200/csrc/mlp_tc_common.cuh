@@ -66,6 +66,7 @@ __device__ __forceinline__ void epi32(const uint32_t (&v)[32], const float4* __r
                                       int j0, int r7, const float* __restrict__ alpha_w, float& sigma,
                                       uint32_t* mask_word = nullptr, unsigned char* gout_row = nullptr) {
   uint32_t ch0 = 0, ch1 = 0, ch2 = 0, ch3 = 0;
+  uint4 o_even = make_uint4(0u, 0u, 0u, 0u);
   float4 b[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) b[i] = bias4[i];
@@ -99,7 +100,19 @@ __device__ __forceinline__ void epi32(const uint32_t (&v)[32], const float4* __r
     o.x = cvt_bf16x2<kRelu, kF16>(x0.x, x0.y); o.y = cvt_bf16x2<kRelu, kF16>(x1.x, x1.y);
     o.z = cvt_bf16x2<kRelu, kF16>(x2.x, x2.y); o.w = cvt_bf16x2<kRelu, kF16>(x3.x, x3.y);
     *reinterpret_cast<uint4*>(out_row + (((j0 + q) ^ r7) << 4)) = o;
-    if (kMask && gout_row != nullptr) *reinterpret_cast<uint4*>(gout_row + (((j0 + q) ^ r7) << 4)) = o;
+    if (kMask && gout_row != nullptr) {
+      // chunks j0+q (q even) and j0+q+1 share one 32-byte sector of the swizzled row (the XOR with r7 swaps them when
+      // r7 is odd): one 256-bit store per pair = full sectors, half the store instructions
+      if ((q & 1) == 0) {
+        o_even = o;
+      } else {
+        const bool swap = (r7 & 1) != 0;
+        const uint4 lo = swap ? o : o_even, hi = swap ? o_even : o;
+        unsigned char* dst = gout_row + ((((j0 + q - 1) ^ r7) >> 1) << 5);
+        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(lo.x), "r"(lo.y), "r"(lo.z),
+                     "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
+      }
+    }
   }
   if (kMask) *mask_word = ch0 | (ch1 << 8) | (ch2 << 16) | (ch3 << 24);
 }
