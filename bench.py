@@ -165,6 +165,16 @@ def cpu_reference_runner(n_rays=1024):
                         "%d rays = every %dth ray of the 800x800 frame" % (n_rays, (H * W) // n_rays))
 
 
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.lower().startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown CPU"
+
+
 def time_cpu_reference(reps, warmup, budget_s=None, n_rays=1024):
     """Median of `reps` renders after `warmup` untimed ones (the mean of a handful of unpinned runs moved 2x between
     boxes in round 1); with budget_s, as many renders as fit (at least 5)."""
@@ -182,8 +192,8 @@ def time_cpu_reference(reps, warmup, budget_s=None, n_rays=1024):
         times.append(time.perf_counter() - t0)
     times.sort()
     med = times[len(times) // 2]
-    sample = "%s; 64+128 samples, torch %s CPU fp32, %d threads; median of %d renders after %d warm-ups (min %.0f / max %.0f ms)" % (
-        what, torch.__version__, cores, len(times), warmup, times[0] * 1e3, times[-1] * 1e3)
+    sample = "%s; 64+128 samples, torch %s CPU fp32, %d threads on %s; median of %d renders after %d warm-ups (min %.0f / max %.0f ms)" % (
+        what, torch.__version__, cores, cpu_model(), len(times), warmup, times[0] * 1e3, times[-1] * 1e3)
     return med, n_rays, {"value": n_rays / med, "unit": "rays/s", "cores": cores, "kind": kind, "sample": sample,
                          "timed_renders": len(times), "warmup_renders": warmup}
 
