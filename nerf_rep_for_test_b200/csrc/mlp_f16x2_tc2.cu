@@ -14,7 +14,8 @@
 // accumulator at each of the 48 MMAs of a 256-deep product, an FFMA chain rounds to nearest.  That is 50x inside the
 // 1e-5 tolerance of the mode.  It costs 3 MMAs where single-pass bf16 costs one, and half of what 3xTF32 or six-term
 // bf16 splitting would cost.  Heads (alpha_linear, rgb_linear), bias adds, the PE (full-range sincosf per octave,
-// no recurrence) and o + d*z are plain fp32 on CUDA cores.  Ten UNFUSED stages, as the reference evaluates them.
+// no recurrence) and o + d*z are plain fp32 on CUDA cores.  Nine stages: pts_linears.0-7 and views_linears.0 with
+// feature_linear folded in at pack time (below).
 //
 // Structure: the CTA-pair machinery of mlp_bf16_tc2.cu (cta_group::2, M = 256 = 128 rows of each CTA, each CTA
 // streams half of every weight chunk, 4-thread-role warp specialisation) with ONE tile slot per CTA: the hi and lo
@@ -50,7 +51,14 @@ constexpr uint32_t kOffW = kOffPeLo + kPePartBytes;             // 163840
 constexpr uint32_t kOffBar = kOffW + kRing * 2 * kWPartBytes;   // 229376
 constexpr uint32_t kOffBias = kOffBar + 256;
 constexpr uint32_t kSmemBytes = kOffBias + 2048;                // 231680 <= 232448
-constexpr int kLastStage = kStages - 1;                         // 9: views_linears.0
+// Executed stages: pts_linears.0-7 and the FUSED tail.  feature_linear has no activation, so -- as in the bf16 inference
+// image -- the pack step folds it into views_linears.0 in fp32 (W' = Wv[:, :256] Wf, b' = Wv[:, :256] bf + bv, then split
+// into hi / lo like every other weight) and writes the result into the slot of image stage 9; image stage 8 is not
+// executed.  10 % fewer MMAs, one accumulator drain less; the change in rounding (h7 (Wf Wv) instead of (h7 Wf) Wv) is
+// of the size of an fp32 summation-order change.
+constexpr int kExec = 9;
+constexpr int kLastStage = kStages - 1;                         // 9: image stage of the (fused) views_linears.0
+__device__ __forceinline__ constexpr int exec_stage(int si) { return si < 8 ? si : kLastStage; }
 
 // BAR_AREADY + 0: K-blocks 0,1 of the A operand (and the PE tile) are in place; + 1: K-blocks 2,3 (and the dir PE)
 enum { BAR_WFULL = 0, BAR_WEMPTY = 2, BAR_AREADY = 4, BAR_ACCFULL = 6, BAR_BFULL = 7, BAR_BEMPTY = 9, BAR_COUNT = 11 };
@@ -273,7 +281,8 @@ mlp_f16x2_tc2_kernel(const unsigned char* __restrict__ packed, const float* __re
       const bool valid_cur = valid;
       const bool dump_tile = kDump && cluster_id == 0 && it == 0 && rank == 0;
       float sigma = 0.f;
-      for (int stage = (it < 0 ? kLastStage : 0); stage < kStages; ++stage) {
+      for (int si = (it < 0 ? kExec - 1 : 0); si < kExec; ++si) {
+        const int stage = exec_stage(si);
         if (stage == 0) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {   // xyz PE tile, 16-byte chunks 4*half .. 4*half+3 of this row
@@ -287,7 +296,7 @@ mlp_f16x2_tc2_kernel(const unsigned char* __restrict__ packed, const float* __re
         }
         if (stage == kLastStage && it + 1 < my_pairs) prepare_tile(it + 1);   // overlaps the last stage's MMAs
         if (it < 0) break;
-        const uint32_t bseq = (uint32_t)it * kStages + (uint32_t)stage;
+        const uint32_t bseq = (uint32_t)it * kExec + (uint32_t)si;
         const uint32_t bbuf = bseq & 1u;
         const float4* bias4 = reinterpret_cast<const float4*>(smem_dyn + kOffBias + bbuf * 1024u);
         const float inv = __ldg(tail + kTailInvScale + stage);
@@ -295,7 +304,7 @@ mlp_f16x2_tc2_kernel(const unsigned char* __restrict__ packed, const float* __re
         mbar_wait(bar(BAR_ACCFULL), full_phase, 0x100 + stage);
         full_phase ^= 1;
         tc_fence_after();
-        const uint32_t t_stage = t_acc + (uint32_t)(stage & 1) * 256u;   // even / odd stages use the two TMEM halves
+        const uint32_t t_stage = t_acc + (uint32_t)(si & 1) * 256u;   // even / odd executed stages use the two TMEM halves
         if (kDump && dump_tile) {   // diagnostic: fp32 post-activation outputs of rows 0..127 of the whole problem
           const int ncb = stage == kLastStage ? 2 : 4;
           const int c0 = stage == kLastStage ? half * 64 : half * 128;
@@ -306,8 +315,7 @@ mlp_f16x2_tc2_kernel(const unsigned char* __restrict__ packed, const float* __re
             pin32(v);
             for (int i = 0; i < 32; ++i) {
               const int n = c0 + cb * 32 + i;
-              float x = fmaf(__uint_as_float(v[i]), inv, tail[kTailBias + stage * 256 + n]);
-              if (stage != 8) x = fmaxf(x, 0.f);
+              float x = fmaxf(fmaf(__uint_as_float(v[i]), inv, tail[kTailBias + stage * 256 + n]), 0.f);
               stage_dump[((size_t)stage * 128 + row) * 256 + n] = x;
             }
           }
@@ -323,9 +331,8 @@ mlp_f16x2_tc2_kernel(const unsigned char* __restrict__ packed, const float* __re
             unsigned char* hr = a_hi_row + blk * 16384;
             unsigned char* lr = a_lo_row + blk * 16384;
             if (stage == 7) epi_block64x<1>(tb, b4, hr, lr, r7, inv, tail + kTailAlphaW + blk * 64, sigma);
-            else if (stage == 8) epi_block64x<2>(tb, b4, hr, lr, r7, inv, nullptr, sigma);
             else epi_block64x<0>(tb, b4, hr, lr, r7, inv, nullptr, sigma);
-            if (ph == 1 && stage == kLastStage - 1) {   // dir PE replaces the xyz PE tile (dead after stage 5): chunks 2*half, 2*half+1
+            if (ph == 1 && stage == 7) {   // dir PE replaces the xyz PE tile (dead after stage 5): chunks 2*half, 2*half+1
 #pragma unroll
               for (int q = 0; q < 2; ++q) {
                 const uint32_t off = (uint32_t)(((half * 2 + q) ^ r7) << 4);
@@ -381,7 +388,8 @@ mlp_f16x2_tc2_kernel(const unsigned char* __restrict__ packed, const float* __re
     // =========================== producer: bias block + this CTA's half of every weight chunk (hi, lo) ==========
     uint32_t seq = 0, bseq = 0;
     for (int it = 0; it < my_pairs; ++it) {
-      for (int stage = 0; stage < kStages; ++stage, ++bseq) {
+      for (int si = 0; si < kExec; ++si, ++bseq) {
+        const int stage = exec_stage(si);
         {
           const uint32_t bbuf = bseq & 1u;
           if (lane == 0) mbar_wait(bar(BAR_BEMPTY + bbuf), ((bseq >> 1) & 1u) ^ 1u, 0x600 + stage);
@@ -416,7 +424,8 @@ mlp_f16x2_tc2_kernel(const unsigned char* __restrict__ packed, const float* __re
     if (lane == 0) {
       uint32_t seq = 0;
       for (int it = 0; it < my_pairs; ++it)
-        for (int stage = 0; stage < kStages; ++stage) {
+        for (int si = 0; si < kExec; ++si) {
+          const int stage = exec_stage(si);
           const int nch = stage_chunks(stage);
           for (int c = 0; c < nch; ++c, ++seq) {
             const uint32_t pos = seq % kRing, phase = (seq / kRing) & 1u;
@@ -439,10 +448,11 @@ mlp_f16x2_tc2_kernel(const unsigned char* __restrict__ packed, const float* __re
     const uint32_t w0 = lo_flags | ((smem_base + kOffW) >> 4);          // + pos*2048 (+ 1024 for lo) + 2*k
     const uint64_t hi64 = (uint64_t)desc_hi << 32;
     for (int it = 0; it < my_pairs; ++it) {
-      for (int stage = 0; stage < kStages; ++stage) {
+      for (int si = 0; si < kExec; ++si) {
+        const int stage = exec_stage(si);
         const int nch = stage_chunks(stage);
         const uint32_t idesc = umma_idesc_f16(256, stage_n(stage));
-        const uint32_t d_tmem = tmem_base + (uint32_t)(stage & 1) * 256u;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(si & 1) * 256u;
         // chunks whose A operand is complete after the epilogue's first phase (K-blocks 0,1 + PE tile); the rest
         // (K-blocks 2,3 and the dir PE of the last stage) wait for the second phase
         const int first_part = stage == 0 ? 1 : (stage == 5 ? 3 : 2);

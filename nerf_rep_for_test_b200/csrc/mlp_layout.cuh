@@ -76,7 +76,7 @@ constexpr int kFusedProdOff = (kFusedTailOff + 256 * 4 + 1023) / 1024 * 1024;
 constexpr int kFusedProdFloats = 128 * 256 + 128;
 constexpr int kBf16PackedBytes = kFusedProdOff + kFusedProdFloats * 4;
 
-// ---- split-fp16 layout (NERFB200_MODE_FP32_TC, bytes): the ten UNFUSED stages, every K-chunk as TWO images of the
+// ---- split-fp16 layout (NERFB200_MODE_FP32_TC, bytes): the geometry of the ten stages above, every K-chunk as TWO images of the
 // bf16 geometry above -- [hi | lo], each N rows x 128 B, pre-swizzled -- holding w_hi = fp16(w * 2^e_s) and
 // w_lo = fp16(w * 2^e_s - w_hi): 22 significand bits per weight.  e_s is a per-stage power of two chosen at pack time
 // so that max|w| * 2^e_s lies in [2^13, 2^14) (the residuals of all weights within 2^-16 of the largest stay normal
@@ -88,7 +88,11 @@ constexpr int kX2TailOff = 2 * kBf16TailOff;
 constexpr int kTailInvScale = kTailFloats;
 constexpr int kTailFwdScale = kTailFloats + 16;
 constexpr int kX2TailFloats = kTailFloats + 32;
-constexpr int kX2PackedBytes = kX2TailOff + kX2TailFloats * 4;
+// The slot of stage 9 holds the FUSED tail (feature_linear folded into views_linears.0 in fp32: W' = Wv[:, :256] Wf in
+// columns 0..255, Wv[:, 256:283] behind, bias row 9 = b' = Wv[:, :256] bf + bv); the slot of stage 8 is unused.  The
+// fp32 product lives in a scratch area behind the tail ([128][256] + [128], fused_tail_product_kernel).
+constexpr int kX2ProdOff = (kX2TailOff + kX2TailFloats * 4 + 1023) / 1024 * 1024;
+constexpr int kX2PackedBytes = kX2ProdOff + kFusedProdFloats * 4;
 
 // source element of stage s, output n, padded input k (returns false when the slot is padding)
 struct SrcRef { int tensor; int col; };  // tensor: 0..7 pts, 8 feature, 9 views

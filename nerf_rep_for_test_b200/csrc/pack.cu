@@ -91,59 +91,6 @@ __global__ void pack_bf16_kernel(nerfb200_mlp_weights w, StageTable tab, unsigne
   }
 }
 
-// split-fp16 image (NERFB200_MODE_FP32_TC, mlp_layout.cuh): one block per stage finds max|w| of the stage's tensor and
-// writes the power-of-two scale 2^e (max|w| * 2^e in [2^13, 2^14)) and its inverse into the tail
-__global__ void stage_scale_kernel(nerfb200_mlp_weights w, float* __restrict__ tail) {
-  const int s = blockIdx.x;   // stage index = tensor index (0..7 pts_linears, 8 feature_linear, 9 views_linears.0)
-  const float* W = tensor_w(w, s);
-  const int count = stage_n(s) * tensor_in_features(s);
-  float mx = 0.f;
-  for (int i = threadIdx.x; i < count; i += blockDim.x) mx = fmaxf(mx, fabsf(W[i]));
-  __shared__ float red[32];
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
-    int e = 0;
-    if (mx > 0.f && mx <= 3.0e38f) {
-      int ex;
-      frexpf(mx, &ex);   // mx = m * 2^ex, m in [0.5, 1)
-      e = 14 - ex;
-    }
-    e = e < -60 ? -60 : (e > 60 ? 60 : e);
-    tail[kTailInvScale + s] = ldexpf(1.f, -e);
-    tail[kTailFwdScale + s] = ldexpf(1.f, e);
-  }
-}
-
-__global__ void pack_f16x2_kernel(nerfb200_mlp_weights w, unsigned char* __restrict__ dst) {
-  const int s = blockIdx.y;
-  float* tail = reinterpret_cast<float*>(dst + kX2TailOff);
-  if (s == kStages) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kTailFloats; i += gridDim.x * blockDim.x) pack_tail(w, tail, i);
-    return;
-  }
-  const float scale = tail[kTailFwdScale + s];   // written by stage_scale_kernel, earlier on the same stream
-  const int N = stage_n(s), K = stage_k(s), chunks = stage_chunks(s);
-  const int total = chunks * N * 64;
-  const size_t part = (size_t)N * 128;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int c = i / (N * 64), n = (i / 64) % N, kk = i % 64;
-    const int k = c * 64 + kk;
-    SrcRef r;
-    float v = 0.f;
-    if (k < K && stage_src(s, k, &r)) v = tensor_w(w, r.tensor)[(size_t)n * tensor_in_features(r.tensor) + r.col] * scale;
-    const __half hi = __float2half_rn(v);
-    const __half lo = __float2half_rn(v - __half2float(hi));
-    const size_t off = (size_t)x2_stage_off(s) + (size_t)c * (2 * part) + (size_t)n * 128 +
-                       (size_t)(((kk >> 3) ^ (n & 7)) << 4) + (size_t)(kk & 7) * 2;
-    *reinterpret_cast<__half*>(dst + off) = hi;
-    *reinterpret_cast<__half*>(dst + off + part) = lo;
-  }
-}
-
 // W'[n][k] = sum_j Wv[n][j] Wf[j][k] (and the analogous b'): a 256-term fp32 dot per output element.  Four
 // independent accumulators instead of one dependent FMA chain -- the re-pack runs after every optimizer step and the
 // single chain made the two tail packs the slowest of the small kernels of the training step (31 us each).
@@ -190,6 +137,72 @@ __global__ void __launch_bounds__(256) fused_tail_product_kernel(nerfb200_mlp_we
   if (threadIdx.x < kProdRows) {   // b'[n]
     const int n = n0 + threadIdx.x;
     prod[128 * 256 + n] = w.views_b[n] + dot256_strided(w.views_w + (size_t)n * 283, w.feature_b, 1);
+  }
+}
+
+// split-fp16 image (NERFB200_MODE_FP32_TC, mlp_layout.cuh): one block per stage finds max|w| of the stage's tensor and
+// writes the power-of-two scale 2^e (max|w| * 2^e in [2^13, 2^14)) and its inverse into the tail
+__global__ void stage_scale_kernel(nerfb200_mlp_weights w, float* __restrict__ tail, const float* __restrict__ prod) {
+  const int s = blockIdx.x;   // stage index = tensor index (0..7 pts_linears, 8 feature_linear (unused), 9 fused views_linears.0)
+  const float* W = tensor_w(w, s);
+  const int count = stage_n(s) * tensor_in_features(s);
+  float mx = 0.f;
+  if (s == 9) {   // fused tail: W' = Wv[:, :256] Wf (prod, [128][256]) | Wv[:, 256:283]
+    for (int i = threadIdx.x; i < 128 * 256; i += blockDim.x) mx = fmaxf(mx, fabsf(prod[i]));
+    for (int i = threadIdx.x; i < 128 * kChD; i += blockDim.x) mx = fmaxf(mx, fabsf(W[(size_t)(i / kChD) * 283 + 256 + i % kChD]));
+  } else {
+    for (int i = threadIdx.x; i < count; i += blockDim.x) mx = fmaxf(mx, fabsf(W[i]));
+  }
+  __shared__ float red[32];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
+    int e = 0;
+    if (mx > 0.f && mx <= 3.0e38f) {
+      int ex;
+      frexpf(mx, &ex);   // mx = m * 2^ex, m in [0.5, 1)
+      e = 14 - ex;
+    }
+    e = e < -60 ? -60 : (e > 60 ? 60 : e);
+    tail[kTailInvScale + s] = ldexpf(1.f, -e);
+    tail[kTailFwdScale + s] = ldexpf(1.f, e);
+  }
+}
+
+__global__ void pack_f16x2_kernel(nerfb200_mlp_weights w, unsigned char* __restrict__ dst) {
+  const int s = blockIdx.y;
+  float* tail = reinterpret_cast<float*>(dst + kX2TailOff);
+  const float* prod = reinterpret_cast<const float*>(dst + kX2ProdOff);   // fused_tail_product_kernel, earlier on the same stream
+  if (s == kStages) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kTailFloats; i += gridDim.x * blockDim.x) {
+      pack_tail(w, tail, i);
+      if (i >= kTailBias + 9 * 256 && i < kTailBias + 9 * 256 + 128) tail[i] = prod[128 * 256 + (i - (kTailBias + 9 * 256))];   // b'
+    }
+    return;
+  }
+  if (s == 8) return;                            // feature_linear is folded into the stage-9 slot
+  const float scale = tail[kTailFwdScale + s];   // written by stage_scale_kernel, earlier on the same stream
+  const int N = stage_n(s), K = stage_k(s), chunks = stage_chunks(s);
+  const int total = chunks * N * 64;
+  const size_t part = (size_t)N * 128;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i / (N * 64), n = (i / 64) % N, kk = i % 64;
+    const int k = c * 64 + kk;
+    SrcRef r;
+    float v = 0.f;
+    if (k < K && stage_src(s, k, &r)) {
+      v = (s == 9 && k < 256) ? prod[(size_t)n * 256 + k] : tensor_w(w, r.tensor)[(size_t)n * tensor_in_features(r.tensor) + r.col];
+      v *= scale;
+    }
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn(v - __half2float(hi));
+    const size_t off = (size_t)x2_stage_off(s) + (size_t)c * (2 * part) + (size_t)n * 128 +
+                       (size_t)(((kk >> 3) ^ (n & 7)) << 4) + (size_t)(kk & 7) * 2;
+    *reinterpret_cast<__half*>(dst + off) = hi;
+    *reinterpret_cast<__half*>(dst + off + part) = lo;
   }
 }
 
@@ -293,7 +306,10 @@ extern "C" int nerfb200_pack_weights(const nerfb200_mlp_weights* w, int mode, vo
   if (mode == NERFB200_MODE_FP32)
     pack_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*w, tab, (float*)packed);
   else if (mode == NERFB200_MODE_FP32_TC) {
-    stage_scale_kernel<<<kStages, 256, 0, (cudaStream_t)stream>>>(*w, reinterpret_cast<float*>((unsigned char*)packed + kX2TailOff));
+    float* prod = reinterpret_cast<float*>((unsigned char*)packed + kX2ProdOff);
+    fused_tail_product_kernel<<<128 / kProdRows, 256, 0, (cudaStream_t)stream>>>(*w, prod);
+    NB_LAUNCH_OK("fused_tail_product_kernel");
+    stage_scale_kernel<<<kStages, 256, 0, (cudaStream_t)stream>>>(*w, reinterpret_cast<float*>((unsigned char*)packed + kX2TailOff), prod);
     NB_LAUNCH_OK("stage_scale_kernel");
     pack_f16x2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*w, (unsigned char*)packed);
   } else {
