@@ -52,7 +52,8 @@ extern "C" {
 #define NERFB200_MODE_BF16 1 /* tcgen05.mma kind::f16 (bf16 in, fp32 accumulate in TMEM): performance mode */
 /* fp32-accurate tensor-core mode: every operand split into two fp16 numbers (22 significand bits), three
  * tcgen05.mma kind::f16 per K step, fp32 accumulate in TMEM, full-range sincosf -- meets the same 1e-5 gates as
- * NERFB200_MODE_FP32 (requires |activation| < 65504). */
+ * NERFB200_MODE_FP32 (requires |activation| < 65504).  feature_linear (no activation) is folded into views_linears.0
+ * in fp32 at pack time. */
 #define NERFB200_MODE_FP32_TC 2
 /* single-pass tcgen05.mma kind::f16 with FP16 operands (11 significand bits instead of bf16's 8, saturating at
  * 65504): the kernel, the speed and the packed size of NERFB200_MODE_BF16, roughly a tenth of its error on networks
@@ -210,9 +211,10 @@ NERFB200_API int nerfb200_adam_clip_step(float* params, float* grads, float* exp
                             double lr, double beta1, double beta2, double eps, long long step, float clip_value,
                             float grad_scale, void* stream);
 
-/* diagnostic twin of mlp_forward (BF16 mode): additionally writes the fp32 post-activation output
+/* diagnostic twin of mlp_forward (BF16 and FP32_TC modes): additionally writes the fp32 post-activation output
  * of each of the ten stages (mlp_layout.cuh) for rows 0..127 into stage_dump [10][128][256];
- * used by the stage-level parity tests. */
+ * used by the stage-level parity tests.  FP32_TC folds feature_linear into views_linears.0: its plane 8 is left
+ * untouched and plane 9 holds relu(views). */
 NERFB200_API int nerfb200_mlp_forward_stages(const void* packed, int mode, const float* rays_o,
                                 const float* rays_d, const float* z_vals, int n_rays, int n_samples,
                                 float* raw, float* stage_dump, void* stream);
