@@ -328,6 +328,8 @@ def run_ours(args):
 
     for b in dev_batches[:args.warmup]:
         r.render(b)
+    for _ in range(max(0, 3 - args.warmup)):          # never fewer than three untimed frames before the timed region
+        r.render(dev_batches[0])
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -362,15 +364,16 @@ def run_ours(args):
                 continue
             rm = Renderer(net, RenderConfig(perturb=0, enable_ess=False, enable_ert=False), mode=mode)
             rm.render(dev_batches[0])
+            probe = (dev_batches * 2)[:2]               # two timed frames (the same view twice when only one exists)
             L.profile_enable(True)
-            ms = timed(rm.render, dev_batches[:2]) / 2
+            ms = timed(rm.render, probe) / len(probe)
             k_ms, k_n, k_rows = L.profile_read()
             L.profile_enable(False)
             tf = k_rows * FLOP_PER_ROW / (k_ms * 1e-3) / 1e12
             mode_lines[mode] = {"ms_per_step": ms, "rays_per_s": H * W / (ms * 1e-3), "dtype": DTYPE_OF_MODE[mode],
                                 "roofline": {"bound": "tensor", "kernel": KERNEL_OF_MODE[mode], "achieved": tf,
                                              "unit": "TFLOP/s (algorithmic fp32 FLOPs of the reference MLP)",
-                                             "kernel_ms_per_step": k_ms / 2, "kernel_share_of_step": k_ms / 2 / ms}}
+                                             "kernel_ms_per_step": k_ms / len(probe), "kernel_share_of_step": k_ms / len(probe) / ms}}
             del rm
 
     # ---- parity gate in the same job: BASELINE config 1 (32x32 = 1024 rays of lego test pose
@@ -479,8 +482,8 @@ def run_ours(args):
                 rr.render(dev_batches[0])
             if rr.eval_counts is not None:
                 rr.eval_counts.zero_()
-            res5[name] = timed(rr.render, dev_batches[:3]) / 3
-        ev = r_skip.eval_counts.cpu().tolist()
+            res5[name] = timed(rr.render, (dev_batches * 3)[:3]) / 3
+        ev = r_skip.eval_counts.cpu().tolist()      # accumulated over the three timed frames
         cfg5 = {"workload": "800x800 view of a synthetic opaque blob (sphere r=0.7 in a [-2,2]^3 128^3 occupancy grid), "
                             "ESS skipping + ERT vs dense 64+128 sampling, bf16",
                 "dense_ms": res5["dense"], "skip_ms": res5["skip"], "speedup": res5["dense"] / res5["skip"],
@@ -501,7 +504,7 @@ def run_ours(args):
             kr.render(dev_batches[0])
         kr.stats.zero_()
         l0 = L.launch_count()
-        kms = timed(kr.render, dev_batches[:3]) / 3
+        kms = timed(kr.render, (dev_batches * 3)[:3]) / 3
         samples = float(kr.stats[0]) / 3
         # CPU leg: the numpy oracle of the same kernels on a 64x64 view of the same scene
         from oracle import kilo_oracle as KO
