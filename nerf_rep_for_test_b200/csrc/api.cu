@@ -73,7 +73,9 @@ static void prof_end(cudaStream_t st, double rows) {
 constexpr int kChunkRays = 32768;
 // Empty-space skipping sends only ~10 % of the rows through the MLP, so an 8192-ray chunk is a fraction of a
 // wave of the persistent kernel (measured: 22.9 ms per frame at 8192, 17.5 ms at 131 072 rays per chunk).
-constexpr int kChunkRaysSparse = 131072;
+// Round 2: 327 680 rays = two chunks per 800x800 frame, ~28 stream operations instead of ~75 (same frame time within the
+// run-to-run noise: 14.97 / 14.46 / 14.72 ms at 131 072 / 262 144 / 655 360); the workspace grows to 1.8 GB.
+constexpr int kChunkRaysSparse = 327680;
 // nerfb200_render_params.mode: bits 0-7 = fine-pass mode, bits 8-15 = 1 + coarse-pass mode (0: same as fine)
 static int mode_fine(int mode) { return mode & 0xFF; }
 static int mode_coarse(int mode) { return (mode >> 8) & 0xFF ? ((mode >> 8) & 0xFF) - 1 : (mode & 0xFF); }
