@@ -407,6 +407,7 @@ def run_ours(args):
     train_ms = 0.0
     train_graph = False
     train_variants = {}
+    train_strong_ms = 0.0
     if args.train_steps > 0:
         from nerf_rep_for_test_b200 import training as T
         net.train()
@@ -453,6 +454,22 @@ def run_ours(args):
             train_variants[tag] = {"ms_per_iter": v0.elapsed_time(v1) / nsteps, "steps": nsteps, "precision": prec,
                                    "ref_compat_sampler": compat}
             del stepv, rv, netv
+            barrier()
+        # strong scaling of the same step: the 4096 rays split over the ranks
+        train_strong_ms = 0.0
+        if world > 1:
+            per = max(1, args.train_rays // world)
+            s_ro, s_rd, s_t = tro[:per].contiguous(), trd[:per].contiguous(), target[:per].contiguous()
+            for _ in range(3):
+                step(s_ro, s_rd, s_t)
+            barrier()
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record()
+            for _ in range(args.train_steps):
+                step(s_ro, s_rd, s_t)
+            q1.record()
+            torch.cuda.synchronize()
+            train_strong_ms = q0.elapsed_time(q1) / args.train_steps
             barrier()
         net.eval()
         r.perturb = 0
@@ -543,10 +560,10 @@ def run_ours(args):
         testset_ms = s0.elapsed_time(s1)
         barrier()
 
-    t = torch.tensor([ms_total, e2e_ms, train_ms, testset_ms, frame_ms_local], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, e2e_ms, train_ms, testset_ms, frame_ms_local, train_strong_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, train_ms, testset_ms, frame_ms_max = (float(x) for x in t)
+    ms_total, e2e_ms, train_ms, testset_ms, frame_ms_max, train_strong_ms = (float(x) for x in t)
     rays_total = float(world) * args.steps * H * W
     value = rays_total / (ms_total * 1e-3)
     e2e_value = rays_total / (e2e_ms * 1e-3)
@@ -629,6 +646,9 @@ def run_ours(args):
                 "allreduce_bytes": 1191688 * 4, "cuda_graph": train_graph,
                 "allreduce": "two pieces of one flat fp32 buffer; the fine model's piece overlaps the coarse model's backward",
                 "variants": train_variants,
+                "strong": ({"rays_per_iter_total": (args.train_rays // world) * world, "rays_per_iter_per_gpu": args.train_rays // world,
+                            "ms_per_iter": train_strong_ms, "it_per_s": 1e3 / train_strong_ms, "scaling": "strong"}
+                           if train_strong_ms > 0 else None),
                 "algorithmic_tflops": 3 * args.train_rays * ROWS_PER_RAY * FLOP_PER_ROW / (it_ms * 1e-3) / 1e12,
                 "note": "every kernel on the path is this repo's: tcgen05 forward with activation store, compositing "
                         "backward, tcgen05 dgrad chain + split-K wgrad GEMMs (nerfb200_mlp_backward); torch supplies "
