@@ -2,7 +2,7 @@
 // Reference: volume_renderer.py:270-284 -> freq.py:23-26 -> network.py:49-74.
 //
 // This is the 1e-5-relative parity mode (true fp32 FFMA, full-range sinf/cosf), not the
-// performance mode (mlp_bf16_tc.cu).  One CTA owns a tile of 64 sample points and walks the ten
+// performance mode (mlp_bf16_tc2.cu).  One CTA owns a tile of 64 sample points and walks the ten
 // stages of mlp_layout.cuh with activations resident in shared memory (ONE [64][256] fp32 buffer: a
 // stage's outputs overwrite its inputs after the barrier that ends its k loop -- the accumulators live
 // in registers) while W^T streams from L2 through a cp.async double buffer in k-chunks of 8.  That is
