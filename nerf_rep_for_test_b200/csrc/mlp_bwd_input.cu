@@ -5,9 +5,9 @@
 //     g_z  = g_x . d                                                              (x = o + d z, :165)
 // read from what nerfb200_mlp_backward's activation-gradient chain already left in its workspace: the bf16 tile
 // images DPRE0 and DPRE5 (train_layout.cuh).  6 % of the MACs of one MLP pass and 1 KB of HBM reads per row, so it is
-// a plain mma.sync kernel rather than one more tcgen05 stage: one CTA per 128-row tile (persistent), the two 64 KB
-// tile images copied verbatim into shared memory (cp.async; the SWIZZLE_128B image is exactly what ldmatrix wants),
-// [W0; W5[:, :63]]^T converted to bf16 once per CTA, fp32 accumulation, then one thread per row for the positional-
+// a plain mma.sync kernel rather than one more tcgen05 stage: persistent CTAs walk 128-row tiles in two 64-row halves,
+// the tile images copied verbatim into a double-buffered shared-memory stage (cp.async; the SWIZZLE_128B image is exactly
+// what ldmatrix wants), [W0; W5[:, :63]]^T converted to bf16 once per CTA, fp32 accumulation, then the positional-
 // encoding backward with the sines and cosines recomputed in fp32 from z.
 #include <cuda_bf16.h>
 
@@ -18,11 +18,16 @@ namespace bwdin {
 
 constexpr int kThreads = 256;
 constexpr int kK = 512;                       // 256 (dpre0) + 256 (dpre5)
+constexpr int kHalfRows = 64;                 // rows per pipeline step (half a 128-row tile)
+constexpr int kHalfBlockBytes = kHalfRows * 128;              // 8 KB: 64 rows of one [128][64] block
+constexpr int kABufBytes = 8 * kHalfBlockBytes;               // 64 KB: 2 planes x 4 blocks
 constexpr int kBStride = kK * 2 + 16;         // bytes per row of Bt[n][k] (padded: conflict-free ldmatrix)
-constexpr int kOffA = 0;                      // 2 x 4 blocks of 16 KB
-constexpr int kOffB = 8 * kBlockBytes;        // 131072
-constexpr int kSmemBytes = kOffB + 64 * kBStride;   // 197 632
-constexpr int kStageStride = 65;              // floats per staged output row (aliases the A region)
+constexpr int kOffA = 0;                      // two buffers (double-buffered cp.async)
+constexpr int kOffB = 2 * kABufBytes;         // 131072
+constexpr int kOffStage = kOffB + 64 * kBStride;              // 197 632: fp32 [64][65] partial / final g_pe tile
+constexpr int kStageStride = 65;
+constexpr int kOffPart = kOffStage + kHalfRows * kStageStride * 4;   // 214 272: [64][3] per-coordinate contributions
+constexpr int kSmemBytes = kOffPart + kHalfRows * 3 * 4 + 256;       // 215 296 <= 232 448
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
@@ -35,12 +40,35 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], 
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// Round-2 revision: 64-row half tiles, double-buffered -- the copy of the next half tile overlaps the MMAs of this one
+// (the first version loaded a whole 128 KB tile, then computed: 401 us per fine launch, 2.0 TB/s); warps split the
+// contraction in halves (dpre0 / dpre5) so every B fragment feeds the same number of MMAs with half the ldmatrix
+// traffic per warp; the positional-encoding backward runs on 192 threads (row x coordinate) with two sincosf per
+// coordinate and the double-angle recurrence in between instead of 30 sincosf on 128 threads.
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_bwd_input_kernel(const unsigned char* __restrict__ dacts, const float* __restrict__ w0, const float* __restrict__ w5,
                      const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ z_vals,
                      long long M, int S, int n_tiles, float* __restrict__ g_z) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t a_base = smem_addr(smem + kOffA), b_base = smem_addr(smem + kOffB);
+  float* stage = reinterpret_cast<float*>(smem + kOffStage);
+  float* part = reinterpret_cast<float*>(smem + kOffPart);
+  const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int n_steps = 2 * my_tiles;            // half tiles of this CTA, in order
+  // cp.async of half tile `step` into buffer step & 1: 8 blocks (dpre0 0..3, dpre5 0..3) x 8 KB
+  auto prefetch = [&](int step) {
+    const long long tile = (long long)blockIdx.x + (long long)(step >> 1) * gridDim.x;
+    const unsigned char* src = dacts + (size_t)tile * kDactBlocks * kBlockBytes + (size_t)(step & 1) * kHalfBlockBytes;
+    const uint32_t dst = a_base + (uint32_t)(step & 1) * kABufBytes;
+    for (int c = tid; c < kABufBytes / 16; c += kThreads) {
+      const int blk = c >> 9;                  // 512 16-byte chunks per 8 KB half block
+      const unsigned char* g = src + (size_t)(blk < 4 ? dact_pre(0) + blk : dact_pre(5) + blk - 4) * kBlockBytes + (size_t)(c & 511) * 16;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)c * 16u), "l"(g));
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (n_steps > 0) prefetch(0);
   // Bt[n][k] = bf16 of W0[k][n] (k < 256) | W5[k - 256][n] (k >= 256), n < 63; row 63 = 0
   for (int e = tid; e < 64 * kK; e += kThreads) {
     const int k = e >> 6, n = e & 63;          // consecutive threads walk n: coalesced reads of a weight row
@@ -48,72 +76,94 @@ mlp_bwd_input_kernel(const unsigned char* __restrict__ dacts, const float* __res
     if (n < kChX) v = k < 256 ? w0[k * kChX + n] : w5[(k - 256) * (kChX + 256) + n];
     *reinterpret_cast<__nv_bfloat16*>(smem + kOffB + n * kBStride + k * 2) = __float2bfloat16_rn(v);
   }
-  const uint32_t a_base = smem_addr(smem + kOffA), b_base = smem_addr(smem + kOffB);
-  float* stage = reinterpret_cast<float*>(smem + kOffA);
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    __syncthreads();   // previous tile's staging reads done (and Bt complete on the first pass)
-    const unsigned char* src = dacts + (size_t)tile * kDactBlocks * kBlockBytes;
-    for (int c = tid; c < 8 * kBlockBytes / 16; c += kThreads) {
-      const int blk = c >> 10;                 // 1024 16-byte chunks per block
-      const unsigned char* g = src + (size_t)(blk < 4 ? dact_pre(0) + blk : dact_pre(5) + blk - 4) * kBlockBytes + (size_t)(c & 1023) * 16;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a_base + (uint32_t)c * 16u), "l"(g));
+  const int mt = warp & 3, kh = warp >> 2;     // 16-row tile of the half, half of the contraction
+  const int mi = lane >> 3, r8 = lane & 7;
+  const int a_row = mt * 16 + (mi & 1) * 8 + r8;
+  for (int step = 0; step < n_steps; ++step) {
+    if (step + 1 < n_steps) {
+      prefetch(step + 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
-    asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
+    __syncthreads();                           // this half tile (and, on the first pass, Bt) is in shared memory
+    const uint32_t a_buf = a_base + (uint32_t)(step & 1) * kABufBytes + (uint32_t)kh * 4u * kHalfBlockBytes;
     float acc[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j)
 #pragma unroll
       for (int q = 0; q < 4; ++q) acc[j][q] = 0.f;
-    const int mi = lane >> 3, r8 = lane & 7;
-    const int a_row = warp * 16 + (mi & 1) * 8 + r8;
 #pragma unroll 4
-    for (int kk = 0; kk < kK / 16; ++kk) {
+    for (int kk = 0; kk < 16; ++kk) {          // 256 of the 512 k per warp
       uint32_t a[4];
       const int unit = (kk & 3) * 2 + (mi >> 1);
-      ldmatrix_x4(a_base + (uint32_t)(kk >> 2) * kBlockBytes + (uint32_t)a_row * 128u + (uint32_t)((unit ^ (a_row & 7)) << 4), a);
+      ldmatrix_x4(a_buf + (uint32_t)(kk >> 2) * kHalfBlockBytes + (uint32_t)a_row * 128u + (uint32_t)((unit ^ (a_row & 7)) << 4), a);
 #pragma unroll
-      for (int jp = 0; jp < 4; ++jp) {         // two 8-column tiles per ldmatrix.x4
+      for (int jp = 0; jp < 4; ++jp) {
         uint32_t b[4];
         const int n = (jp * 2 + (mi >> 1)) * 8 + r8;
-        ldmatrix_x4(b_base + (uint32_t)n * kBStride + (uint32_t)(kk * 16 + (mi & 1) * 8) * 2u, b);
+        ldmatrix_x4(b_base + (uint32_t)n * kBStride + (uint32_t)(kh * 256 + kk * 16 + (mi & 1) * 8) * 2u, b);
         mma_bf16(acc[jp * 2], a, b[0], b[1]);
         mma_bf16(acc[jp * 2 + 1], a, b[2], b[3]);
       }
     }
-    __syncthreads();   // every warp is done with the A images: reuse them as the fp32 staging tile
+    // reduce the two contraction halves through the staging tile
+    const int r = mt * 16 + (lane >> 2);
+    if (kh == 1) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int r = warp * 16 + (lane >> 2), c = j * 8 + (lane & 3) * 2;
-      stage[r * kStageStride + c] = acc[j][0];
-      stage[r * kStageStride + c + 1] = acc[j][1];
-      stage[(r + 8) * kStageStride + c] = acc[j][2];
-      stage[(r + 8) * kStageStride + c + 1] = acc[j][3];
-    }
-    __syncthreads();
-    if (tid < kTileRows) {
-      const long long m = (long long)tile * kTileRows + tid;
-      if (m < M) {
-        const long long ray = m / S;
-        const float z = z_vals[m];
-        const float* g = stage + tid * kStageStride;
-        float out = 0.f;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float d = rays_d[ray * 3 + c];
-          const float x = __fadd_rn(rays_o[ray * 3 + c], __fmul_rn(d, z));
-          float gx = g[c];
-          for (int l = 0; l < kLx; ++l) {
-            float sn, cs;
-            const float f = (float)(1 << l);
-            sincosf(x * f, &sn, &cs);
-            gx += f * (g[3 + 6 * l + c] * cs - g[3 + 6 * l + 3 + c] * sn);
-          }
-          out += gx * d;
-        }
-        g_z[m] = out;
+      for (int j = 0; j < 8; ++j) {
+        const int c = j * 8 + (lane & 3) * 2;
+        stage[r * kStageStride + c] = acc[j][0];
+        stage[r * kStageStride + c + 1] = acc[j][1];
+        stage[(r + 8) * kStageStride + c] = acc[j][2];
+        stage[(r + 8) * kStageStride + c + 1] = acc[j][3];
       }
     }
+    __syncthreads();
+    if (kh == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = j * 8 + (lane & 3) * 2;
+        stage[r * kStageStride + c] += acc[j][0];
+        stage[r * kStageStride + c + 1] += acc[j][1];
+        stage[(r + 8) * kStageStride + c] += acc[j][2];
+        stage[(r + 8) * kStageStride + c + 1] += acc[j][3];
+      }
+    }
+    __syncthreads();
+    // positional-encoding backward: thread = (row, coordinate)
+    const long long tile = (long long)blockIdx.x + (long long)(step >> 1) * gridDim.x;
+    const long long m0 = tile * kTileRows + (long long)(step & 1) * kHalfRows;
+    if (tid < kHalfRows * 3) {
+      const int row = tid / 3, c = tid - row * 3;
+      const long long m = m0 + row;
+      float contrib = 0.f;
+      if (m < M) {
+        const long long ray = m / S;
+        const float d = rays_d[ray * 3 + c];
+        const float x = __fadd_rn(rays_o[ray * 3 + c], __fmul_rn(d, z_vals[m]));
+        const float* g = stage + row * kStageStride;
+        float sn = 0.f, cs = 1.f;
+        float gx = g[c], f = 1.f;
+#pragma unroll
+        for (int l = 0; l < kLx; ++l) {
+          // angle doubling (2^l x is exact in fp32), restarted from an accurate sincosf every five octaves: the
+          // recurrence's error doubles per step and the high octaves carry the weight 2^l
+          if (l % 5 == 0) sincosf(x * f, &sn, &cs);
+          gx += f * (g[3 + 6 * l + c] * cs - g[3 + 6 * l + 3 + c] * sn);
+          const float s2 = 2.f * sn * cs, c2 = 1.f - 2.f * sn * sn;
+          sn = s2; cs = c2; f *= 2.f;
+        }
+        contrib = gx * d;
+      }
+      part[row * 3 + c] = contrib;
+    }
+    __syncthreads();
+    if (tid < kHalfRows) {
+      const long long m = m0 + tid;
+      if (m < M) g_z[m] = (part[tid * 3] + part[tid * 3 + 1]) + part[tid * 3 + 2];
+    }
+    // the next iteration's first __syncthreads orders these reads before the staging tile / this A buffer are reused
   }
 }
 
