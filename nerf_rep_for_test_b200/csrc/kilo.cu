@@ -20,6 +20,7 @@
 // The arithmetic is CUDA-core fp32 (12 160 FLOP per sample): the path is bounded by FFMA issue, not by HBM
 // (16 B in / 16 B out per sample), and by design evaluates ~10x fewer samples than the dense path.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -375,6 +376,279 @@ eval_kernel(const int32_t* __restrict__ query, const int32_t* __restrict__ sorte
   }
 }
 
+// ---- micro-MLP on the tensor cores (error-compensated 3xTF32) -------------------------------------------------------
+// The same five layers as eval_kernel, as warp-level mma.sync.m16n8k8 products: M = 32 samples per warp (two 16-row
+// tiles, lane l prepares sample l), N = the layer's outputs in tiles of 8, K = its inputs in steps of 8.  fp32 accuracy
+// on tf32 tensor cores: every operand is split x = hi + lo with hi = tf32(x), lo = tf32(x - hi) and every K step issues
+//     a_lo * b_hi  +  a_hi * b_lo  +  a_hi * b_hi          (dropped: a_lo * b_lo, 2^-22 relative)
+// into the fp32 accumulator.  tf32 keeps fp32's exponent range, so arbitrary micro-MLP weights are safe (no scaling).
+// The accumulator fragment of a layer IS the A fragment of the next one: thread (g, t) = (lane / 4, lane % 4) holds
+// columns 2t, 2t+1 of output tile j for rows g, g+8, and feeds them as K slots t, t+4 of K step j -- the order of a
+// contraction's terms is free, so the weights are staged in shared memory with the matching row permutation
+// (b0 = W[8j + 2t][n], b1 = W[8j + 2t + 1][n]), in fragment order: one conflict-free LDS.64 per (K step, N tile) and lane.
+// Inputs that do not come from a previous layer (the 63 position / 27 direction embedding channels, computed per lane
+// by sincosf + the double-angle recurrence exactly as in eval_kernel) go through a feature-major staging tile per warp
+// ([64 features][36 floats], conflict-free both ways).  density (layer-2 output 0) rides in a fifth N tile so the 32
+// feature outputs stay aligned with the K steps of layer 3.
+constexpr int kTcThreads = 128;
+constexpr int kTcWarps = kTcThreads / 32;
+constexpr int kF0 = 0;                          // layer 0: 8 K steps x 4 N tiles x (32 lanes x 2)
+constexpr int kF1 = kF0 + 8 * 4 * 64;
+constexpr int kF2 = kF1 + 4 * 4 * 64;           // layer 2: 4 x 5 (tiles 0-3 = feature 1..32, tile 4 column 0 = density)
+constexpr int kF3 = kF2 + 4 * 5 * 64;           // layer 3: 8 x 4 (K steps 0-3 feature, 4-7 direction embedding)
+constexpr int kF4 = kF3 + 8 * 4 * 64;           // layer 4: 4 x 1
+constexpr int kFragFloats = kF4 + 4 * 1 * 64;   // 6656
+constexpr int kTb0 = kFragFloats, kTb1 = kTb0 + 32, kTb2 = kTb1 + 32, kTb3 = kTb2 + 40, kTb4 = kTb3 + 32;
+constexpr int kTcWFloats = kTb4 + 8;            // 6800
+constexpr int kStageStride = 36;
+constexpr int kStageFloats = 64 * kStageStride;
+constexpr size_t kTcSmemBytes = (size_t)(kTcWFloats + kTcWarps * kStageFloats + 8) * 4;   // 64 096 B
+
+// round-to-nearest tf32 (10 explicit significand bits) by integer arithmetic: two ALU instructions where cvt.rna.tf32.f32
+// compiles to five (sm_100a emulates it with an FSETP / SEL special-case path).  No inf / nan handling: those propagate
+// as garbage exactly as they would through the fp32 kernel's sums.
+__device__ __forceinline__ uint32_t tf32_of(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
+// the residual x - hi is exact in fp32 (<= 13 significant bits); the tensor core reads its upper 11
+__device__ __forceinline__ uint32_t tf32_rest(float x, uint32_t hi) { return __float_as_uint(x - __uint_as_float(hi)); }
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// one K step of a layer for both row tiles: acc[m][i] += a[m] * Wfrag[i]   (a[m] = {row g slot t, row g+8 slot t,
+// row g slot t+4, row g+8 slot t+4} in fp32; wf = this K step's NT fragments)
+template <int NT>
+__device__ __forceinline__ void mma_kstep(float (&acc)[2][NT][4], const float (&a)[2][4], const float* __restrict__ wf, int lane) {
+  uint32_t ahi[2][4], alo[2][4];
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      ahi[m][r] = tf32_of(a[m][r]);
+      alo[m][r] = tf32_rest(a[m][r], ahi[m][r]);
+    }
+#pragma unroll
+  for (int i = 0; i < NT; ++i) {
+    const float2 b = *reinterpret_cast<const float2*>(wf + (i * 32 + lane) * 2);
+    const uint32_t bh0 = tf32_of(b.x), bh1 = tf32_of(b.y);
+    const uint32_t bl0 = tf32_rest(b.x, bh0), bl1 = tf32_rest(b.y, bh1);
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      mma_tf32(acc[m][i], alo[m], bh0, bh1);
+      mma_tf32(acc[m][i], ahi[m], bl0, bl1);
+      mma_tf32(acc[m][i], ahi[m], bh0, bh1);
+    }
+  }
+}
+template <int NT>
+__device__ __forceinline__ void load_bias_frag(float (&acc)[2][NT][4], const float* __restrict__ b, int t) {
+#pragma unroll
+  for (int i = 0; i < NT; ++i) {
+    const float2 v = *reinterpret_cast<const float2*>(b + 8 * i + 2 * t);
+#pragma unroll
+    for (int m = 0; m < 2; ++m) { acc[m][i][0] = acc[m][i][2] = v.x; acc[m][i][1] = acc[m][i][3] = v.y; }
+  }
+}
+// accumulator tile j of the previous layer -> A operand of K step j (optionally through relu)
+template <bool kRelu>
+__device__ __forceinline__ void frag_c_to_a(float (&a)[2][4], const float (&c0)[4], const float (&c1)[4]) {
+  const float* c[2] = {c0, c1};
+#pragma unroll
+  for (int m = 0; m < 2; ++m) {
+    a[m][0] = kRelu ? fmaxf(c[m][0], 0.f) : c[m][0];
+    a[m][1] = kRelu ? fmaxf(c[m][2], 0.f) : c[m][2];
+    a[m][2] = kRelu ? fmaxf(c[m][1], 0.f) : c[m][1];
+    a[m][3] = kRelu ? fmaxf(c[m][3], 0.f) : c[m][3];
+  }
+}
+// staged (feature-major) inputs -> A operand of staged K step js
+__device__ __forceinline__ void frag_stage_to_a(float (&a)[2][4], const float* __restrict__ stg, int js, int g, int t) {
+  const float* r0 = stg + (8 * js + 2 * t) * kStageStride + g;
+  const float* r1 = r0 + kStageStride;
+#pragma unroll
+  for (int m = 0; m < 2; ++m) {
+    a[m][0] = r0[m * 16];
+    a[m][1] = r0[m * 16 + 8];
+    a[m][2] = r1[m * 16];
+    a[m][3] = r1[m * 16 + 8];
+  }
+}
+// packed parameters of one network -> fragment-ordered shared-memory image.  which = 0 / 1: input row 8j + 2t / + 1.
+template <int KS, int NT, typename F>
+__device__ __forceinline__ void fill_frags(float* __restrict__ dst, const float* __restrict__ src, F index_of) {
+  for (int idx = threadIdx.x; idx < KS * NT * 64; idx += kTcThreads) {
+    const int which = idx & 1, lane = (idx >> 1) & 31, tile = idx >> 6;
+    const int i = tile % NT, j = tile / NT, g = lane >> 2, t = lane & 3;
+    const int p = index_of(8 * j + 2 * t + which, i, g);
+    dst[idx] = p >= 0 ? __ldg(src + p) : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(kTcThreads, 3)
+eval_tc_kernel(const int32_t* __restrict__ query, const int32_t* __restrict__ sorted, const int32_t* __restrict__ start,
+               const int32_t* __restrict__ item_start, int num_networks, const float* __restrict__ params,
+               const float* __restrict__ domain_mins, const float* __restrict__ domain_maxs, EvalCam cam,
+               float4* __restrict__ rgb_sigma, const int32_t* __restrict__ counters) {
+  extern __shared__ __align__(16) float tc_smem[];
+  float* w = tc_smem;
+  float* dom = tc_smem + kTcWFloats + kTcWarps * kStageFloats;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  float* stg = tc_smem + kTcWFloats + warp * kStageFloats;
+  const int n_items = counters[C_ITEMS];
+  int cached_net = -1;
+  const int per_block = (n_items + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int item_end = min(n_items, ((int)blockIdx.x + 1) * per_block);
+  for (int item = (int)blockIdx.x * per_block; item < item_end; ++item) {
+    int lo = 0, hi = num_networks;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (item_start[mid] <= item) lo = mid; else hi = mid;
+    }
+    const int net = lo;
+    if (net != cached_net) {
+      __syncthreads();
+      const float* src = params + (size_t)net * kParamSize;
+      fill_frags<8, 4>(w + kF0, src, [](int in, int i, int g) { return in < 63 ? kOffL0 + 32 + in * 32 + 8 * i + g : -1; });
+      fill_frags<4, 4>(w + kF1, src, [](int in, int i, int g) { return kOffL1 + 32 + in * 32 + 8 * i + g; });
+      fill_frags<4, 5>(w + kF2, src, [](int in, int i, int g) { return i < 4 ? kOffL2 + 33 + in * 33 + 1 + 8 * i + g : (g == 0 ? kOffL2 + 33 + in * 33 : -1); });
+      fill_frags<8, 4>(w + kF3, src, [](int in, int i, int g) { return in < 59 ? kOffL3 + 32 + in * 32 + 8 * i + g : -1; });
+      fill_frags<4, 1>(w + kF4, src, [](int in, int i, int g) { return g < 3 ? kOffL4 + 3 + in * 3 + g : -1; });
+      for (int c = threadIdx.x; c < kTcWFloats - kTb0; c += kTcThreads) {
+        int p = -1;
+        if (c < 32) p = kOffL0 + c;
+        else if (c < 64) p = kOffL1 + c - 32;
+        else if (c < 104) { const int k = c - 64; p = k < 32 ? kOffL2 + 1 + k : (k == 32 ? kOffL2 : -1); }
+        else if (c < 136) p = kOffL3 + c - 104;
+        else if (c < 139) p = kOffL4 + c - 136;
+        w[kTb0 + c] = p >= 0 ? __ldg(src + p) : 0.f;
+      }
+      if (threadIdx.x < 3) dom[threadIdx.x] = domain_mins[net * 3 + threadIdx.x];
+      else if (threadIdx.x < 6) dom[threadIdx.x] = domain_maxs[net * 3 + threadIdx.x - 3];
+      __syncthreads();
+      cached_net = net;
+    }
+    const int first = start[net] + (item - item_start[net]) * kChunk;
+    const int end = start[net + 1];
+#pragma unroll 1
+    for (int sub = warp; sub < kChunk / 32; sub += kTcWarps) {
+      if (first + sub * 32 >= end) break;   // warp-uniform
+      const int idx = first + sub * 32 + lane;
+      const int slot = idx < end ? sorted[idx] : -1;
+      float pe[3], dir[3];
+      {
+        int q = slot >= 0 ? query[slot] : 0;
+        const int depth = q % cam.max_depth;
+        q /= cam.max_depth;
+        const int x = q % cam.W, y = q / cam.W;
+        const float v[3] = {__fdiv_rn((float)x - cam.cx, cam.fx), -__fdiv_rn((float)y - cam.cy, cam.fy), -1.f};
+        float d[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+          for (int k = 0; k < 3; ++k) d[k] = __fadd_rn(d[k], __fmul_rn(v[j], cam.c2w[k * 3 + j]));
+        const float dist = __fadd_rn(cam.min_distance, __fmul_rn((float)depth, cam.dbp));
+        const float norm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float p = __fadd_rn(cam.origin[k], __fmul_rn(dist, d[k]));
+          pe[k] = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, __fsub_rn(p, dom[k])), __fsub_rn(dom[3 + k], dom[k])), 1.f);
+          dir[k] = __fdiv_rn(d[k], norm);
+        }
+      }
+      // position embedding of sample `lane` -> staging tile (feature-major)
+      __syncwarp();
+#pragma unroll 1
+      for (int j = 0; j < 3; ++j) {
+        float e[21];
+        fourier<10>(pe[j], e);
+#pragma unroll
+        for (int k = 0; k < 21; ++k) stg[(j * 21 + k) * kStageStride + lane] = e[k];
+      }
+      stg[63 * kStageStride + lane] = 0.f;
+      __syncwarp();
+      // layer 0: 63 -> 32
+      float h0[2][4][4];
+      load_bias_frag<4>(h0, w + kTb0, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float a[2][4];
+        frag_stage_to_a(a, stg, j, g, t);
+        mma_kstep<4>(h0, a, w + kF0 + j * 4 * 64, lane);
+      }
+      // direction embedding replaces the (consumed) position embedding in the staging tile
+      __syncwarp();
+#pragma unroll 1
+      for (int j = 0; j < 3; ++j) {
+        float e[9];
+        fourier<4>(dir[j], e);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) stg[(j * 9 + k) * kStageStride + lane] = e[k];
+      }
+#pragma unroll
+      for (int k = 27; k < 32; ++k) stg[k * kStageStride + lane] = 0.f;
+      __syncwarp();
+      // layer 1: relu(h0) 32 -> 32
+      float h1[2][4][4];
+      load_bias_frag<4>(h1, w + kTb1, t);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a[2][4];
+        frag_c_to_a<true>(a, h0[0][j], h0[1][j]);
+        mma_kstep<4>(h1, a, w + kF1 + j * 4 * 64, lane);
+      }
+      // layer 2: relu(h1) 32 -> feature(32) | density
+      float h2[2][5][4];
+      load_bias_frag<5>(h2, w + kTb2, t);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a[2][4];
+        frag_c_to_a<true>(a, h1[0][j], h1[1][j]);
+        mma_kstep<5>(h2, a, w + kF2 + j * 5 * 64, lane);
+      }
+      // layer 3: feature(32) | direction embedding(27) -> 32
+      float (&h3)[2][4][4] = h0;
+      load_bias_frag<4>(h3, w + kTb3, t);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a[2][4];
+        frag_c_to_a<false>(a, h2[0][j], h2[1][j]);
+        mma_kstep<4>(h3, a, w + kF3 + j * 4 * 64, lane);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a[2][4];
+        frag_stage_to_a(a, stg, j, g, t);
+        mma_kstep<4>(h3, a, w + kF3 + (4 + j) * 4 * 64, lane);
+      }
+      // layer 4: relu(h3) 32 -> 3
+      float o[2][1][4];
+      load_bias_frag<1>(o, w + kTb4, t);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a[2][4];
+        frag_c_to_a<true>(a, h3[0][j], h3[1][j]);
+        mma_kstep<1>(o, a, w + kF4 + j * 64, lane);
+      }
+      // thread t = 0 of a quad holds (r, g) of rows g / g+8, t = 1 holds b; density = column 0 of tile 4 of layer 2
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        const float b_lo = __shfl_down_sync(0xffffffffu, o[m][0][0], 1);
+        const float b_hi = __shfl_down_sync(0xffffffffu, o[m][0][2], 1);
+        const int s_lo = __shfl_sync(0xffffffffu, slot, m * 16 + g);
+        const int s_hi = __shfl_sync(0xffffffffu, slot, m * 16 + g + 8);
+        if (t == 0) {
+          if (s_lo >= 0)
+            rgb_sigma[s_lo] = make_float4(1.f / (1.f + expf(-o[m][0][0])), 1.f / (1.f + expf(-o[m][0][1])),
+                                          1.f / (1.f + expf(-b_lo)), fmaxf(h2[m][4][0], 0.f));
+          if (s_hi >= 0)
+            rgb_sigma[s_hi] = make_float4(1.f / (1.f + expf(-o[m][0][2])), 1.f / (1.f + expf(-o[m][0][3])),
+                                          1.f / (1.f + expf(-b_hi)), fmaxf(h2[m][4][2], 0.f));
+        }
+      }
+    }
+  }
+}
+
 // integrate.cu:9-57, one thread per ray over the filled slots of this pass
 __global__ void integrate_kernel(const float4* __restrict__ rgb_sigma, const int16_t* __restrict__ assigned,
                                  const float* __restrict__ dists, float* __restrict__ rgb_map, float* __restrict__ acc_map,
@@ -553,9 +827,22 @@ static int eval_pass(const Work& w, const nerfb200_kilo_camera* cam, const nerfb
   int dev = 0, sms = 0;
   NB_CUDA(cudaGetDevice(&dev));
   NB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  eval_kernel<<<sms * 3, kEvalThreads, 0, st>>>(w.query, w.sorted, w.start, w.item_start, num_networks, params, domain_mins, domain_maxs, ec,
-                                                w.rgb_sigma, w.counters);
-  NB_LAUNCH_OK("kilo::eval_kernel");
+  static const bool use_ffma = getenv("NERFB200_KILO_FFMA") != nullptr;   // A/B switch: the CUDA-core kernel of round 1
+  if (use_ffma) {
+    eval_kernel<<<sms * 3, kEvalThreads, 0, st>>>(w.query, w.sorted, w.start, w.item_start, num_networks, params, domain_mins, domain_maxs, ec,
+                                                  w.rgb_sigma, w.counters);
+    NB_LAUNCH_OK("kilo::eval_kernel");
+    return 0;
+  }
+  NB_CHECK_ARG(dev >= 0 && dev < 64, "kilo: device ordinal %d out of range", dev);
+  static bool attr_set[64] = {};   // opt-in to > 48 KB of dynamic shared memory: per device, sticky
+  if (!attr_set[dev]) {
+    NB_CUDA(cudaFuncSetAttribute(eval_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+    attr_set[dev] = true;
+  }
+  eval_tc_kernel<<<sms * 3, kTcThreads, kTcSmemBytes, st>>>(w.query, w.sorted, w.start, w.item_start, num_networks, params, domain_mins,
+                                                            domain_maxs, ec, w.rgb_sigma, w.counters);
+  NB_LAUNCH_OK("kilo::eval_tc_kernel");
   return 0;
 }
 
