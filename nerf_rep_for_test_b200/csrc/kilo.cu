@@ -19,6 +19,7 @@
 //    intrinsics on arguments up to 512 rad.
 // The arithmetic is CUDA-core fp32 (12 160 FLOP per sample): the path is bounded by FFMA issue, not by HBM
 // (16 B in / 16 B out per sample), and by design evaluates ~10x fewer samples than the dense path.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdlib.h>
 
@@ -376,111 +377,133 @@ eval_kernel(const int32_t* __restrict__ query, const int32_t* __restrict__ sorte
   }
 }
 
-// ---- micro-MLP on the tensor cores (error-compensated 3xTF32) -------------------------------------------------------
-// The same five layers as eval_kernel, as warp-level mma.sync.m16n8k8 products: M = 32 samples per warp (two 16-row
-// tiles, lane l prepares sample l), N = the layer's outputs in tiles of 8, K = its inputs in steps of 8.  fp32 accuracy
-// on tf32 tensor cores: every operand is split x = hi + lo with hi = tf32(x), lo = tf32(x - hi) and every K step issues
-//     a_lo * b_hi  +  a_hi * b_lo  +  a_hi * b_hi          (dropped: a_lo * b_lo, 2^-22 relative)
-// into the fp32 accumulator.  tf32 keeps fp32's exponent range, so arbitrary micro-MLP weights are safe (no scaling).
-// The accumulator fragment of a layer IS the A fragment of the next one: thread (g, t) = (lane / 4, lane % 4) holds
-// columns 2t, 2t+1 of output tile j for rows g, g+8, and feeds them as K slots t, t+4 of K step j -- the order of a
-// contraction's terms is free, so the weights are staged in shared memory with the matching row permutation
-// (b0 = W[8j + 2t][n], b1 = W[8j + 2t + 1][n]), in fragment order: one conflict-free LDS.64 per (K step, N tile) and lane.
-// Inputs that do not come from a previous layer (the 63 position / 27 direction embedding channels, computed per lane
-// by sincosf + the double-angle recurrence exactly as in eval_kernel) go through a feature-major staging tile per warp
-// ([64 features][36 floats], conflict-free both ways).  density (layer-2 output 0) rides in a fifth N tile so the 32
-// feature outputs stay aligned with the K steps of layer 3.
+// ---- micro-MLP on the tensor cores (split-fp16 operands, fp32 accumulate) -------------------------------------------
+// The same five layers as eval_kernel, as warp-level mma.sync.m16n8k16 products: M = 32 samples per warp (two 16-row
+// tiles, lane l prepares sample l), N = the layer's outputs in tiles of 8, K = its inputs in steps of 16.  fp32 accuracy
+// on 16-bit tensor-core operands as in mlp_f16x2_tc2.cu: every operand is carried as two fp16 numbers x = hi + lo,
+// hi = fp16(x), lo = fp16(x - hi) (22 significand bits; products of fp16 numbers are exact in the fp32 accumulator) and
+// every K step issues       a_lo * b_hi  +  a_hi * b_lo  +  a_hi * b_hi          (dropped: a_lo * b_lo, 2^-22 relative).
+// (First version: 3xTF32 on m16n8k8 -- the legacy tf32 HMMA runs at ~410 MAC/clk/SM, so three of them per K = 8 only
+// matched the FFMA2 peak: 2.05 ms against 3.0 ms for the CUDA-core kernel.  fp16 halves the instruction count per MAC.)
+// Range: a network's weights are scaled by one power of two S (max |w| S < 2^14, found when the network is staged) so
+// their residuals stay normal fp16 numbers; the accumulator is un-scaled in fp32 (h = acc / S + bias).  Activations are
+// not scaled: |h| < 65504 is required (saturating conversion beyond), below 2^-3 the residual is subnormal, i.e. the
+// absolute error of an activation is bounded by 2^-25.
+// The accumulator fragment of a layer IS the A fragment of the next one (thread (g, t) = (lane / 4, lane % 4) holds
+// columns 2t, 2t+1 of output tile i for rows g, g+8 = K slots 2t, 2t+1 (tile 2j) and 2t+8, 2t+9 (tile 2j+1) of K step j),
+// so hidden activations never leave registers.  Weights are staged in shared memory already split, packed and in
+// fragment order: one conflict-free LDS.128 (b0.hi, b1.hi, b0.lo, b1.lo) per (K step, N tile) and lane, no conversion
+// work in the inner loop.  Inputs that do not come from a previous layer (the 63 position / 27 direction embedding
+// channels, computed per lane by sincosf + the double-angle recurrence exactly as in eval_kernel) go through a
+// feature-major staging tile per warp ([64 features][36 floats], conflict-free both ways).  density (layer-2 output 0)
+// rides in a fifth N tile so that the 32 feature outputs stay aligned with the K steps of layer 3.
 constexpr int kTcThreads = 128;
 constexpr int kTcWarps = kTcThreads / 32;
-constexpr int kF0 = 0;                          // layer 0: 8 K steps x 4 N tiles x (32 lanes x 2)
-constexpr int kF1 = kF0 + 8 * 4 * 64;
-constexpr int kF2 = kF1 + 4 * 4 * 64;           // layer 2: 4 x 5 (tiles 0-3 = feature 1..32, tile 4 column 0 = density)
-constexpr int kF3 = kF2 + 4 * 5 * 64;           // layer 3: 8 x 4 (K steps 0-3 feature, 4-7 direction embedding)
-constexpr int kF4 = kF3 + 8 * 4 * 64;           // layer 4: 4 x 1
-constexpr int kFragFloats = kF4 + 4 * 1 * 64;   // 6656
+// fragment tiles (512 B = 32 lanes x uint4 each): layer 0: 4 K steps x 4 N tiles, 1: 2 x 4, 2: 2 x 5 (tiles 0-3 = feature
+// 1..32, tile 4 column 0 = density), 3: 4 x 4 (K steps 0-1 feature, 2-3 direction embedding), 4: 2 x 1
+constexpr int kT0 = 0, kT1 = kT0 + 16, kT2 = kT1 + 8, kT3 = kT2 + 10, kT4 = kT3 + 16, kTiles = kT4 + 2;   // 52
+constexpr int kFragFloats = kTiles * 128;       // 6656 32-bit words
 constexpr int kTb0 = kFragFloats, kTb1 = kTb0 + 32, kTb2 = kTb1 + 32, kTb3 = kTb2 + 40, kTb4 = kTb3 + 32;
 constexpr int kTcWFloats = kTb4 + 8;            // 6800
 constexpr int kStageStride = 36;
 constexpr int kStageFloats = 64 * kStageStride;
-constexpr size_t kTcSmemBytes = (size_t)(kTcWFloats + kTcWarps * kStageFloats + 8) * 4;   // 64 096 B
+constexpr int kTcMisc = 16;                     // dom[6], scale, 1/scale, 4 partial maxima
+constexpr size_t kTcSmemBytes = (size_t)(kTcWFloats + kTcWarps * kStageFloats + kTcMisc) * 4;   // 64 128 B
 
-// round-to-nearest tf32 (10 explicit significand bits) by integer arithmetic: two ALU instructions where cvt.rna.tf32.f32
-// compiles to five (sm_100a emulates it with an FSETP / SEL special-case path).  No inf / nan handling: those propagate
-// as garbage exactly as they would through the fp32 kernel's sums.
-__device__ __forceinline__ uint32_t tf32_of(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
-// the residual x - hi is exact in fp32 (<= 13 significant bits); the tensor core reads its upper 11
-__device__ __forceinline__ uint32_t tf32_rest(float x, uint32_t hi) { return __float_as_uint(x - __uint_as_float(hi)); }
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+// x0, x1 -> packed fp16 pairs (x0 in bits 0-15) of the high parts and of the residuals
+__device__ __forceinline__ void split_h2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - h.y), "f"(x0 - h.x));
+}
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// one K step of a layer for both row tiles: acc[m][i] += a[m] * Wfrag[i]   (a[m] = {row g slot t, row g+8 slot t,
-// row g slot t+4, row g+8 slot t+4} in fp32; wf = this K step's NT fragments)
+// one K step (16 inputs) of a layer for both row tiles: acc[m][i] += a[m] * Wfrag[i].  a[m] = fp32 values of
+// {row g: slots 2t, 2t+1 | row g+8: same | row g: slots 2t+8, 2t+9 | row g+8: same}; wf = this K step's NT fragment tiles
 template <int NT>
-__device__ __forceinline__ void mma_kstep(float (&acc)[2][NT][4], const float (&a)[2][4], const float* __restrict__ wf, int lane) {
+__device__ __forceinline__ void mma_kstep(float (&acc)[2][NT][4], const float (&a)[2][8], const uint4* __restrict__ wf, int lane) {
   uint32_t ahi[2][4], alo[2][4];
 #pragma unroll
   for (int m = 0; m < 2; ++m)
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      ahi[m][r] = tf32_of(a[m][r]);
-      alo[m][r] = tf32_rest(a[m][r], ahi[m][r]);
-    }
+    for (int r = 0; r < 4; ++r) split_h2(a[m][2 * r], a[m][2 * r + 1], ahi[m][r], alo[m][r]);
 #pragma unroll
   for (int i = 0; i < NT; ++i) {
-    const float2 b = *reinterpret_cast<const float2*>(wf + (i * 32 + lane) * 2);
-    const uint32_t bh0 = tf32_of(b.x), bh1 = tf32_of(b.y);
-    const uint32_t bl0 = tf32_rest(b.x, bh0), bl1 = tf32_rest(b.y, bh1);
+    const uint4 b = wf[i * 32 + lane];
 #pragma unroll
     for (int m = 0; m < 2; ++m) {
-      mma_tf32(acc[m][i], alo[m], bh0, bh1);
-      mma_tf32(acc[m][i], ahi[m], bl0, bl1);
-      mma_tf32(acc[m][i], ahi[m], bh0, bh1);
+      mma_f16(acc[m][i], alo[m], b.x, b.y);
+      mma_f16(acc[m][i], ahi[m], b.z, b.w);
+      mma_f16(acc[m][i], ahi[m], b.x, b.y);
     }
   }
 }
 template <int NT>
-__device__ __forceinline__ void load_bias_frag(float (&acc)[2][NT][4], const float* __restrict__ b, int t) {
+__device__ __forceinline__ void zero_acc(float (&acc)[2][NT][4]) {
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int i = 0; i < NT; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[m][i][e] = 0.f;
+}
+// h = acc / S + bias (optionally through relu), in place
+template <int NT, bool kRelu>
+__device__ __forceinline__ void finish_layer(float (&acc)[2][NT][4], const float* __restrict__ bias, float inv_s, int t) {
 #pragma unroll
   for (int i = 0; i < NT; ++i) {
-    const float2 v = *reinterpret_cast<const float2*>(b + 8 * i + 2 * t);
+    const float2 v = *reinterpret_cast<const float2*>(bias + 8 * i + 2 * t);
 #pragma unroll
-    for (int m = 0; m < 2; ++m) { acc[m][i][0] = acc[m][i][2] = v.x; acc[m][i][1] = acc[m][i][3] = v.y; }
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float h = fmaf(acc[m][i][e], inv_s, (e & 1) ? v.y : v.x);
+        acc[m][i][e] = kRelu ? fmaxf(h, 0.f) : h;
+      }
   }
 }
-// accumulator tile j of the previous layer -> A operand of K step j (optionally through relu)
-template <bool kRelu>
-__device__ __forceinline__ void frag_c_to_a(float (&a)[2][4], const float (&c0)[4], const float (&c1)[4]) {
-  const float* c[2] = {c0, c1};
+// finished output tiles 2j, 2j+1 of the previous layer -> A operand of K step j
+template <int NT>
+__device__ __forceinline__ void frag_c_to_a(float (&a)[2][8], const float (&c)[2][NT][4], int j) {
 #pragma unroll
   for (int m = 0; m < 2; ++m) {
-    a[m][0] = kRelu ? fmaxf(c[m][0], 0.f) : c[m][0];
-    a[m][1] = kRelu ? fmaxf(c[m][2], 0.f) : c[m][2];
-    a[m][2] = kRelu ? fmaxf(c[m][1], 0.f) : c[m][1];
-    a[m][3] = kRelu ? fmaxf(c[m][3], 0.f) : c[m][3];
+    a[m][0] = c[m][2 * j][0];     a[m][1] = c[m][2 * j][1];
+    a[m][2] = c[m][2 * j][2];     a[m][3] = c[m][2 * j][3];
+    a[m][4] = c[m][2 * j + 1][0]; a[m][5] = c[m][2 * j + 1][1];
+    a[m][6] = c[m][2 * j + 1][2]; a[m][7] = c[m][2 * j + 1][3];
   }
 }
 // staged (feature-major) inputs -> A operand of staged K step js
-__device__ __forceinline__ void frag_stage_to_a(float (&a)[2][4], const float* __restrict__ stg, int js, int g, int t) {
-  const float* r0 = stg + (8 * js + 2 * t) * kStageStride + g;
-  const float* r1 = r0 + kStageStride;
+__device__ __forceinline__ void frag_stage_to_a(float (&a)[2][8], const float* __restrict__ stg, int js, int g, int t) {
+  const float* r = stg + (16 * js + 2 * t) * kStageStride + g;
 #pragma unroll
   for (int m = 0; m < 2; ++m) {
-    a[m][0] = r0[m * 16];
-    a[m][1] = r0[m * 16 + 8];
-    a[m][2] = r1[m * 16];
-    a[m][3] = r1[m * 16 + 8];
+    a[m][0] = r[m * 16];                          a[m][1] = r[kStageStride + m * 16];
+    a[m][2] = r[m * 16 + 8];                      a[m][3] = r[kStageStride + m * 16 + 8];
+    a[m][4] = r[8 * kStageStride + m * 16];       a[m][5] = r[9 * kStageStride + m * 16];
+    a[m][6] = r[8 * kStageStride + m * 16 + 8];   a[m][7] = r[9 * kStageStride + m * 16 + 8];
   }
 }
-// packed parameters of one network -> fragment-ordered shared-memory image.  which = 0 / 1: input row 8j + 2t / + 1.
+// packed parameters of one network -> split, scaled, fragment-ordered shared-memory image of one layer.
+// index_of(in, i, g): parameter index of W[in][output g of tile i], or -1 for padding
 template <int KS, int NT, typename F>
-__device__ __forceinline__ void fill_frags(float* __restrict__ dst, const float* __restrict__ src, F index_of) {
-  for (int idx = threadIdx.x; idx < KS * NT * 64; idx += kTcThreads) {
-    const int which = idx & 1, lane = (idx >> 1) & 31, tile = idx >> 6;
+__device__ __forceinline__ void fill_frags(uint4* __restrict__ dst, const float* __restrict__ src, float scale, F index_of) {
+  for (int idx = threadIdx.x; idx < KS * NT * 32; idx += kTcThreads) {
+    const int lane = idx & 31, tile = idx >> 5;
     const int i = tile % NT, j = tile / NT, g = lane >> 2, t = lane & 3;
-    const int p = index_of(8 * j + 2 * t + which, i, g);
-    dst[idx] = p >= 0 ? __ldg(src + p) : 0.f;
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int p = index_of(16 * j + 2 * t + (e & 1) + (e >> 1) * 8, i, g);
+      v[e] = p >= 0 ? __ldg(src + p) * scale : 0.f;
+    }
+    uint4 o;
+    split_h2(v[0], v[1], o.x, o.z);
+    split_h2(v[2], v[3], o.y, o.w);
+    dst[idx] = o;
   }
 }
 
@@ -491,7 +514,9 @@ eval_tc_kernel(const int32_t* __restrict__ query, const int32_t* __restrict__ so
                float4* __restrict__ rgb_sigma, const int32_t* __restrict__ counters) {
   extern __shared__ __align__(16) float tc_smem[];
   float* w = tc_smem;
-  float* dom = tc_smem + kTcWFloats + kTcWarps * kStageFloats;
+  const uint4* wf = reinterpret_cast<const uint4*>(tc_smem);
+  float* misc = tc_smem + kTcWFloats + kTcWarps * kStageFloats;   // dom[6] | S | 1/S | partial maxima[4]
+  const float* dom = misc;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   float* stg = tc_smem + kTcWFloats + warp * kStageFloats;
   const int n_items = counters[C_ITEMS];
@@ -508,11 +533,22 @@ eval_tc_kernel(const int32_t* __restrict__ query, const int32_t* __restrict__ so
     if (net != cached_net) {
       __syncthreads();
       const float* src = params + (size_t)net * kParamSize;
-      fill_frags<8, 4>(w + kF0, src, [](int in, int i, int g) { return in < 63 ? kOffL0 + 32 + in * 32 + 8 * i + g : -1; });
-      fill_frags<4, 4>(w + kF1, src, [](int in, int i, int g) { return kOffL1 + 32 + in * 32 + 8 * i + g; });
-      fill_frags<4, 5>(w + kF2, src, [](int in, int i, int g) { return i < 4 ? kOffL2 + 33 + in * 33 + 1 + 8 * i + g : (g == 0 ? kOffL2 + 33 + in * 33 : -1); });
-      fill_frags<8, 4>(w + kF3, src, [](int in, int i, int g) { return in < 59 ? kOffL3 + 32 + in * 32 + 8 * i + g : -1; });
-      fill_frags<4, 1>(w + kF4, src, [](int in, int i, int g) { return g < 3 ? kOffL4 + 3 + in * 3 + g : -1; });
+      float mx = 0.f;
+      for (int i = threadIdx.x; i < kParamSize; i += kTcThreads) mx = fmaxf(mx, fabsf(__ldg(src + i)));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      if (lane == 0) misc[8 + warp] = mx;
+      __syncthreads();
+      mx = fmaxf(fmaxf(misc[8], misc[9]), fmaxf(misc[10], misc[11]));
+      int ex = 0;
+      if (mx > 0.f && mx < 3.0e38f) frexpf(mx, &ex);       // mx < 2^ex
+      const float scale = ldexpf(1.f, min(max(14 - ex, -100), 100));
+      uint4* wq = reinterpret_cast<uint4*>(w);
+      fill_frags<4, 4>(wq + kT0 * 32, src, scale, [](int in, int i, int g) { return in < 63 ? kOffL0 + 32 + in * 32 + 8 * i + g : -1; });
+      fill_frags<2, 4>(wq + kT1 * 32, src, scale, [](int in, int i, int g) { return kOffL1 + 32 + in * 32 + 8 * i + g; });
+      fill_frags<2, 5>(wq + kT2 * 32, src, scale, [](int in, int i, int g) { return i < 4 ? kOffL2 + 33 + in * 33 + 1 + 8 * i + g : (g == 0 ? kOffL2 + 33 + in * 33 : -1); });
+      fill_frags<4, 4>(wq + kT3 * 32, src, scale, [](int in, int i, int g) { return in < 59 ? kOffL3 + 32 + in * 32 + 8 * i + g : -1; });
+      fill_frags<2, 1>(wq + kT4 * 32, src, scale, [](int in, int i, int g) { return g < 3 ? kOffL4 + 3 + in * 3 + g : -1; });
       for (int c = threadIdx.x; c < kTcWFloats - kTb0; c += kTcThreads) {
         int p = -1;
         if (c < 32) p = kOffL0 + c;
@@ -522,11 +558,14 @@ eval_tc_kernel(const int32_t* __restrict__ query, const int32_t* __restrict__ so
         else if (c < 139) p = kOffL4 + c - 136;
         w[kTb0 + c] = p >= 0 ? __ldg(src + p) : 0.f;
       }
-      if (threadIdx.x < 3) dom[threadIdx.x] = domain_mins[net * 3 + threadIdx.x];
-      else if (threadIdx.x < 6) dom[threadIdx.x] = domain_maxs[net * 3 + threadIdx.x - 3];
+      if (threadIdx.x < 3) misc[threadIdx.x] = domain_mins[net * 3 + threadIdx.x];
+      else if (threadIdx.x < 6) misc[threadIdx.x] = domain_maxs[net * 3 + threadIdx.x - 3];
+      else if (threadIdx.x == 6) misc[6] = scale;
+      else if (threadIdx.x == 7) misc[7] = 1.f / scale;
       __syncthreads();
       cached_net = net;
     }
+    const float inv_s = misc[7];
     const int first = start[net] + (item - item_start[net]) * kChunk;
     const int end = start[net + 1];
 #pragma unroll 1
@@ -568,13 +607,14 @@ eval_tc_kernel(const int32_t* __restrict__ query, const int32_t* __restrict__ so
       __syncwarp();
       // layer 0: 63 -> 32
       float h0[2][4][4];
-      load_bias_frag<4>(h0, w + kTb0, t);
+      zero_acc<4>(h0);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float a[2][4];
+      for (int j = 0; j < 4; ++j) {
+        float a[2][8];
         frag_stage_to_a(a, stg, j, g, t);
-        mma_kstep<4>(h0, a, w + kF0 + j * 4 * 64, lane);
+        mma_kstep<4>(h0, a, wf + (kT0 + j * 4) * 32, lane);
       }
+      finish_layer<4, true>(h0, w + kTb0, inv_s, t);
       // direction embedding replaces the (consumed) position embedding in the staging tile
       __syncwarp();
 #pragma unroll 1
@@ -589,46 +629,50 @@ eval_tc_kernel(const int32_t* __restrict__ query, const int32_t* __restrict__ so
       __syncwarp();
       // layer 1: relu(h0) 32 -> 32
       float h1[2][4][4];
-      load_bias_frag<4>(h1, w + kTb1, t);
+      zero_acc<4>(h1);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float a[2][4];
-        frag_c_to_a<true>(a, h0[0][j], h0[1][j]);
-        mma_kstep<4>(h1, a, w + kF1 + j * 4 * 64, lane);
+      for (int j = 0; j < 2; ++j) {
+        float a[2][8];
+        frag_c_to_a<4>(a, h0, j);
+        mma_kstep<4>(h1, a, wf + (kT1 + j * 4) * 32, lane);
       }
-      // layer 2: relu(h1) 32 -> feature(32) | density
+      finish_layer<4, true>(h1, w + kTb1, inv_s, t);
+      // layer 2: relu(h1) 32 -> feature(32) | density (no activation on the feature)
       float h2[2][5][4];
-      load_bias_frag<5>(h2, w + kTb2, t);
+      zero_acc<5>(h2);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float a[2][4];
-        frag_c_to_a<true>(a, h1[0][j], h1[1][j]);
-        mma_kstep<5>(h2, a, w + kF2 + j * 5 * 64, lane);
+      for (int j = 0; j < 2; ++j) {
+        float a[2][8];
+        frag_c_to_a<4>(a, h1, j);
+        mma_kstep<5>(h2, a, wf + (kT2 + j * 5) * 32, lane);
       }
+      finish_layer<5, false>(h2, w + kTb2, inv_s, t);
       // layer 3: feature(32) | direction embedding(27) -> 32
       float (&h3)[2][4][4] = h0;
-      load_bias_frag<4>(h3, w + kTb3, t);
+      zero_acc<4>(h3);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float a[2][4];
-        frag_c_to_a<false>(a, h2[0][j], h2[1][j]);
-        mma_kstep<4>(h3, a, w + kF3 + j * 4 * 64, lane);
+      for (int j = 0; j < 2; ++j) {
+        float a[2][8];
+        frag_c_to_a<5>(a, h2, j);
+        mma_kstep<4>(h3, a, wf + (kT3 + j * 4) * 32, lane);
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float a[2][4];
+      for (int j = 0; j < 2; ++j) {
+        float a[2][8];
         frag_stage_to_a(a, stg, j, g, t);
-        mma_kstep<4>(h3, a, w + kF3 + (4 + j) * 4 * 64, lane);
+        mma_kstep<4>(h3, a, wf + (kT3 + (2 + j) * 4) * 32, lane);
       }
+      finish_layer<4, true>(h3, w + kTb3, inv_s, t);
       // layer 4: relu(h3) 32 -> 3
       float o[2][1][4];
-      load_bias_frag<1>(o, w + kTb4, t);
+      zero_acc<1>(o);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float a[2][4];
-        frag_c_to_a<true>(a, h3[0][j], h3[1][j]);
-        mma_kstep<1>(o, a, w + kF4 + j * 64, lane);
+      for (int j = 0; j < 2; ++j) {
+        float a[2][8];
+        frag_c_to_a<4>(a, h3, j);
+        mma_kstep<1>(o, a, wf + (kT4 + j) * 32, lane);
       }
+      finish_layer<1, false>(o, w + kTb4, inv_s, t);
       // thread t = 0 of a quad holds (r, g) of rows g / g+8, t = 1 holds b; density = column 0 of tile 4 of layer 2
 #pragma unroll
       for (int m = 0; m < 2; ++m) {
