@@ -538,6 +538,10 @@ def run_ours(args):
                     "samples_per_s": samples / (kms * 1e-3),
                     "fp32_tflops": samples * 12160 / (kms * 1e-3) / 1e12,
                     "fp32_peak_tflops_nominal": 148 * 128 * 2 * 1.965e9 / 1e12,
+                    "micro_mlp": "tensor cores, split-fp16 operands (3 mma.sync.m16n8k16 per K step, fp32 accumulate): "
+                                 "fp32-accurate; the FLOP figure is the algorithmic fp32 count over the WHOLE frame "
+                                 "(march, sort, integrate included), the peak is the CUDA-core FFMA figure the "
+                                 "reference's arithmetic would be bound by",
                     "launches_per_frame": (L.launch_count() - l0) / 3.0,
                     "cpu_oracle": {"rays_per_s": 64 * 64 / cpu_s, "samples_per_s": ev64 / cpu_s, "sample": "64x64 view, numpy, 1 thread"},
                     "note": "throughput of the a9 path; the reference's kilonerf_cuda extension is never built or run "

@@ -12,16 +12,18 @@
 //  * grouping samples by network is a device-side counting sort (shared-memory histograms, one scan block,
 //    one scatter) instead of thrust::sort_by_key + gather/scatter (cuda/reorder.cu:12-48);
 //  * the micro-MLP kernel is persistent over (network, 256-sample chunk) work items, so a few crowded
-//    networks do not serialise on one block (the reference maps block i <-> network i); each thread carries
-//    TWO samples through the network so every weight fetched from shared memory feeds 2 FMAs x 32 outputs;
-//    results are written straight back to the ray-major slot (no scatter pass);
+//    networks do not serialise on one block (the reference maps block i <-> network i); the five layers run
+//    on the tensor cores with split-fp16 operands (fp32-accurate, see eval_tc_kernel) and the hidden
+//    activations never leave registers; results are written straight back to the ray-major slot (no
+//    scatter pass);
 //  * cos/sin by one accurate sincosf per coordinate + the double-angle recurrence instead of 20 fast-math
 //    intrinsics on arguments up to 512 rad.
-// The arithmetic is CUDA-core fp32 (12 160 FLOP per sample): the path is bounded by FFMA issue, not by HBM
-// (16 B in / 16 B out per sample), and by design evaluates ~10x fewer samples than the dense path.
+// 12 160 FLOP per sample against 16 B in / 16 B out: the path is compute-bound, and by design evaluates ~10x
+// fewer samples than the dense path.  Round 1 ran the micro-MLP on CUDA cores (packed FFMA2, two samples per
+// thread: 3.0 ms for the bench frame's 8.06 M samples, 44 % of the FFMA peak); the tensor-core kernel below takes
+// 1.25 ms (profiles/r02_kilo_ab.txt).
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
-#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -37,17 +39,7 @@ constexpr int kOffL3 = kOffL2 + 33 + 32 * 33;               // bias[32] | W[59][
 constexpr int kOffL4 = kOffL3 + 32 + 59 * 32;               // bias[3]  | W[32][3]
 static_assert(kOffL4 + 3 + 32 * 3 == kParamSize, "micro-MLP parameter layout");
 
-// shared-memory copy of one network: same order, but the 33- and 3-wide rows are padded to 36 / 4 floats so
-// every weight row is 16-byte aligned and is read as broadcast float4s
-constexpr int kSmL0 = 0;                                    // bias[32] | W[63][32]
-constexpr int kSmL1 = kSmL0 + 32 + 63 * 32;                 // bias[32] | W[32][32]
-constexpr int kSmL2 = kSmL1 + 32 + 32 * 32;                 // bias[36] | W[32][36]
-constexpr int kSmL3 = kSmL2 + 36 + 32 * 36;                 // bias[32] | W[59][32]
-constexpr int kSmL4 = kSmL3 + 32 + 59 * 32;                 // bias[4]  | W[32][4]
-constexpr int kSmFloats = kSmL4 + 4 + 32 * 4;               // 6344
-
-constexpr int kChunk = 256;        // samples per work item of the eval kernel (128 threads x 2)
-constexpr int kEvalThreads = 128;
+constexpr int kChunk = 256;        // samples per work item of the micro-MLP kernel (8 warps x 32)
 
 // counters[] (device int32): 0 = queries of this pass, 1 = work items of this pass, 2 = rays still active
 // after this pass, 3 = rays active before this pass
@@ -226,40 +218,6 @@ __device__ __forceinline__ void fourier(float x, float* e) {
   }
 }
 
-// acc[s][0..NOUT) += in[s] * W[k][0..NOUT)  for the two samples of this thread.  The W row is read as broadcast
-// float4s and consumed by packed FFMA2 (two fused multiply-adds per instruction, same rounding as FFMA): the
-// kernel was issue-bound at 53 % issue utilisation with scalar FFMA (ncu), FFMA2 halves the FMA issue slots.
-template <int NOUT>
-__device__ __forceinline__ void fma_row(float2 (&acc)[2][NOUT / 2], const float* __restrict__ wrow, float in0, float in1) {
-  static_assert(NOUT % 4 == 0, "padded row widths of the micro-MLP");
-  const float4* w4 = reinterpret_cast<const float4*>(wrow);
-  const float2 a0 = make_float2(in0, in0), a1 = make_float2(in1, in1);
-#pragma unroll
-  for (int i = 0; i < NOUT / 4; ++i) {
-    const float4 w = w4[i];
-    const float2 wlo = make_float2(w.x, w.y), whi = make_float2(w.z, w.w);
-    acc[0][2 * i] = __ffma2_rn(a0, wlo, acc[0][2 * i]);
-    acc[1][2 * i] = __ffma2_rn(a1, wlo, acc[1][2 * i]);
-    acc[0][2 * i + 1] = __ffma2_rn(a0, whi, acc[0][2 * i + 1]);
-    acc[1][2 * i + 1] = __ffma2_rn(a1, whi, acc[1][2 * i + 1]);
-  }
-}
-template <int NOUT>
-__device__ __forceinline__ void load_bias(float2 (&acc)[2][NOUT / 2], const float* __restrict__ b) {
-#pragma unroll
-  for (int i = 0; i < NOUT / 2; ++i) acc[0][i] = acc[1][i] = make_float2(b[2 * i], b[2 * i + 1]);
-}
-// element k of a float2-packed activation vector
-#define NB_EL(v, k) (((k) & 1) ? (v)[(k) >> 1].y : (v)[(k) >> 1].x)
-// packed parameter index (network_eval.cu:48-52 order) -> padded shared-memory index
-__device__ __forceinline__ int sm_index(int i) {
-  if (i < kOffL2) return i;                                  // layers 0, 1 unchanged
-  if (i < kOffL3) { const int r = i - kOffL2; return kSmL2 + (r / 33) * 36 + r % 33; }   // bias row + 32 rows of 33
-  if (i < kOffL4) return kSmL3 + (i - kOffL3);
-  const int r = i - kOffL4;
-  return kSmL4 + (r / 3) * 4 + r % 3;
-}
-
 struct EvalCam {
   float c2w[9];
   float origin[3];
@@ -268,123 +226,14 @@ struct EvalCam {
   float min_distance, dbp;
 };
 
-// persistent over work items (network, chunk); weights of the item's network staged in shared memory
-__global__ void __launch_bounds__(kEvalThreads, 3)
-eval_kernel(const int32_t* __restrict__ query, const int32_t* __restrict__ sorted, const int32_t* __restrict__ start,
-            const int32_t* __restrict__ item_start, int num_networks, const float* __restrict__ params,
-            const float* __restrict__ domain_mins, const float* __restrict__ domain_maxs, EvalCam cam,
-            float4* __restrict__ rgb_sigma, const int32_t* __restrict__ counters) {
-  __shared__ __align__(16) float w[kSmFloats];
-  __shared__ float dom[6];
-  const int n_items = counters[C_ITEMS];
-  int cached_net = -1;
-  // contiguous item ranges per block: consecutive items mostly belong to the same network, so its 25 KB of
-  // weights are staged once per run of items instead of once per item (a grid-stride walk changed network every time)
-  const int per_block = (n_items + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int item_end = min(n_items, ((int)blockIdx.x + 1) * per_block);
-  for (int item = (int)blockIdx.x * per_block; item < item_end; ++item) {
-    // network of this item: last n with item_start[n] <= item
-    int lo = 0, hi = num_networks;
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (item_start[mid] <= item) lo = mid; else hi = mid;
-    }
-    const int net = lo;
-    if (net != cached_net) {
-      __syncthreads();
-      const float* src = params + (size_t)net * kParamSize;
-      for (int i = threadIdx.x; i < kSmFloats - kSmL2; i += kEvalThreads) w[kSmL2 + i] = 0.f;   // padding lanes
-      __syncthreads();
-      for (int i = threadIdx.x; i < kParamSize; i += kEvalThreads) w[sm_index(i)] = __ldg(src + i);
-      if (threadIdx.x < 3) dom[threadIdx.x] = domain_mins[net * 3 + threadIdx.x];
-      else if (threadIdx.x < 6) dom[threadIdx.x] = domain_maxs[net * 3 + threadIdx.x - 3];
-      __syncthreads();
-      cached_net = net;
-    }
-    const int first = start[net] + (item - item_start[net]) * kChunk;
-    const int end = start[net + 1];
-    int slot[2];
-    float pe[2][3], dir[2][3];
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      const int idx = first + s * kEvalThreads + threadIdx.x;
-      slot[s] = idx < end ? sorted[idx] : -1;
-      int q = slot[s] >= 0 ? query[slot[s]] : 0;
-      const int depth = q % cam.max_depth;
-      q /= cam.max_depth;
-      const int x = q % cam.W, y = q / cam.W;
-      const float v[3] = {__fdiv_rn((float)x - cam.cx, cam.fx), -__fdiv_rn((float)y - cam.cy, cam.fy), -1.f};
-      float d[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-      for (int j = 0; j < 3; ++j)
-#pragma unroll
-        for (int k = 0; k < 3; ++k) d[k] = __fadd_rn(d[k], __fmul_rn(v[j], cam.c2w[k * 3 + j]));
-      const float dist = __fadd_rn(cam.min_distance, __fmul_rn((float)depth, cam.dbp));
-      const float norm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const float p = __fadd_rn(cam.origin[k], __fmul_rn(dist, d[k]));
-        pe[s][k] = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, __fsub_rn(p, dom[k])), __fsub_rn(dom[3 + k], dom[k])), 1.f);
-        dir[s][k] = __fdiv_rn(d[k], norm);
-      }
-    }
-    // layer 0: 63 -> 32
-    float2 h0[2][16];
-    load_bias<32>(h0, w + kSmL0);
-#pragma unroll 1
-    for (int j = 0; j < 3; ++j) {
-      float e0[21], e1[21];
-      fourier<10>(pe[0][j], e0);
-      fourier<10>(pe[1][j], e1);
-      const float* wr = w + kSmL0 + 32 + j * 21 * 32;
-#pragma unroll
-      for (int e = 0; e < 21; ++e) fma_row<32>(h0, wr + e * 32, e0[e], e1[e]);
-    }
-    // layer 1: 32 -> 32 (relu on the input)
-    float2 h1[2][16];
-    load_bias<32>(h1, w + kSmL1);
-#pragma unroll
-    for (int k = 0; k < 32; ++k) fma_row<32>(h1, w + kSmL1 + 32 + k * 32, fmaxf(NB_EL(h0[0], k), 0.f), fmaxf(NB_EL(h0[1], k), 0.f));
-    // layer 2: 32 -> 33 (output 0 = density, 1..32 = feature, no activation on the feature)
-    float2 h2[2][18];
-    load_bias<36>(h2, w + kSmL2);
-#pragma unroll
-    for (int k = 0; k < 32; ++k) fma_row<36>(h2, w + kSmL2 + 36 + k * 36, fmaxf(NB_EL(h1[0], k), 0.f), fmaxf(NB_EL(h1[1], k), 0.f));
-    // layer 3: feature(32) | dir embedding(27) -> 32
-    float2 (&h3)[2][16] = h0;
-    load_bias<32>(h3, w + kSmL3);
-#pragma unroll
-    for (int k = 0; k < 32; ++k) fma_row<32>(h3, w + kSmL3 + 32 + k * 32, NB_EL(h2[0], k + 1), NB_EL(h2[1], k + 1));
-#pragma unroll 1
-    for (int j = 0; j < 3; ++j) {
-      float e0[9], e1[9];
-      fourier<4>(dir[0][j], e0);
-      fourier<4>(dir[1][j], e1);
-      const float* wr = w + kSmL3 + 32 + (32 + j * 9) * 32;
-#pragma unroll
-      for (int e = 0; e < 9; ++e) fma_row<32>(h3, wr + e * 32, e0[e], e1[e]);
-    }
-    // layer 4: 32 -> 3, sigmoid; density relu
-    float2 rgb[2][2];
-    load_bias<4>(rgb, w + kSmL4);
-#pragma unroll
-    for (int k = 0; k < 32; ++k) fma_row<4>(rgb, w + kSmL4 + 4 + k * 4, fmaxf(NB_EL(h3[0], k), 0.f), fmaxf(NB_EL(h3[1], k), 0.f));
-#pragma unroll
-    for (int s = 0; s < 2; ++s)
-      if (slot[s] >= 0)
-        rgb_sigma[slot[s]] = make_float4(1.f / (1.f + expf(-rgb[s][0].x)), 1.f / (1.f + expf(-rgb[s][0].y)),
-                                         1.f / (1.f + expf(-rgb[s][1].x)), fmaxf(h2[s][0].x, 0.f));
-  }
-}
-
 // ---- micro-MLP on the tensor cores (split-fp16 operands, fp32 accumulate) -------------------------------------------
-// The same five layers as eval_kernel, as warp-level mma.sync.m16n8k16 products: M = 32 samples per warp (two 16-row
+// The five layers (network_eval.cu:127-254) as warp-level mma.sync.m16n8k16 products: M = 32 samples per warp (two 16-row
 // tiles, lane l prepares sample l), N = the layer's outputs in tiles of 8, K = its inputs in steps of 16.  fp32 accuracy
 // on 16-bit tensor-core operands as in mlp_f16x2_tc2.cu: every operand is carried as two fp16 numbers x = hi + lo,
 // hi = fp16(x), lo = fp16(x - hi) (22 significand bits; products of fp16 numbers are exact in the fp32 accumulator) and
 // every K step issues       a_lo * b_hi  +  a_hi * b_lo  +  a_hi * b_hi          (dropped: a_lo * b_lo, 2^-22 relative).
 // (First version: 3xTF32 on m16n8k8 -- the legacy tf32 HMMA runs at ~410 MAC/clk/SM, so three of them per K = 8 only
-// matched the FFMA2 peak: 2.05 ms against 3.0 ms for the CUDA-core kernel.  fp16 halves the instruction count per MAC.)
+// matched the FFMA2 peak: 2.05 ms against 3.0 ms for the CUDA-core kernel of round 1.  fp16 halves the instruction count per MAC.)
 // Range: a network's weights are scaled by one power of two S (max |w| S < 2^14, found when the network is staged) so
 // their residuals stay normal fp16 numbers; the accumulator is un-scaled in fp32 (h = acc / S + bias).  Activations are
 // not scaled: |h| < 65504 is required (saturating conversion beyond), below 2^-3 the residual is subnormal, i.e. the
@@ -394,10 +243,10 @@ eval_kernel(const int32_t* __restrict__ query, const int32_t* __restrict__ sorte
 // so hidden activations never leave registers.  Weights are staged in shared memory already split, packed and in
 // fragment order: one conflict-free LDS.128 (b0.hi, b1.hi, b0.lo, b1.lo) per (K step, N tile) and lane, no conversion
 // work in the inner loop.  Inputs that do not come from a previous layer (the 63 position / 27 direction embedding
-// channels, computed per lane by sincosf + the double-angle recurrence exactly as in eval_kernel) go through a
+// channels, computed per lane by sincosf + the double-angle recurrence) go through a
 // feature-major staging tile per warp ([64 features][36 floats], conflict-free both ways).  density (layer-2 output 0)
 // rides in a fifth N tile so that the 32 feature outputs stay aligned with the K steps of layer 3.
-constexpr int kTcThreads = 128;
+constexpr int kTcThreads = 256;
 constexpr int kTcWarps = kTcThreads / 32;
 // fragment tiles (512 B = 32 lanes x uint4 each): layer 0: 4 K steps x 4 N tiles, 1: 2 x 4, 2: 2 x 5 (tiles 0-3 = feature
 // 1..32, tile 4 column 0 = density), 3: 4 x 4 (K steps 0-1 feature, 2-3 direction embedding), 4: 2 x 1
@@ -407,7 +256,7 @@ constexpr int kTb0 = kFragFloats, kTb1 = kTb0 + 32, kTb2 = kTb1 + 32, kTb3 = kTb
 constexpr int kTcWFloats = kTb4 + 8;            // 6800
 constexpr int kStageStride = 36;
 constexpr int kStageFloats = 64 * kStageStride;
-constexpr int kTcMisc = 16;                     // dom[6], scale, 1/scale, 4 partial maxima
+constexpr int kTcMisc = 8 + kTcWarps;           // dom[6], scale, 1/scale, one partial maximum per warp
 constexpr size_t kTcSmemBytes = (size_t)(kTcWFloats + kTcWarps * kStageFloats + kTcMisc) * 4;   // 64 128 B
 
 // x0, x1 -> packed fp16 pairs (x0 in bits 0-15) of the high parts and of the residuals
@@ -507,7 +356,7 @@ __device__ __forceinline__ void fill_frags(uint4* __restrict__ dst, const float*
   }
 }
 
-__global__ void __launch_bounds__(kTcThreads, 3)
+__global__ void __launch_bounds__(kTcThreads, 2)
 eval_tc_kernel(const int32_t* __restrict__ query, const int32_t* __restrict__ sorted, const int32_t* __restrict__ start,
                const int32_t* __restrict__ item_start, int num_networks, const float* __restrict__ params,
                const float* __restrict__ domain_mins, const float* __restrict__ domain_maxs, EvalCam cam,
@@ -515,7 +364,7 @@ eval_tc_kernel(const int32_t* __restrict__ query, const int32_t* __restrict__ so
   extern __shared__ __align__(16) float tc_smem[];
   float* w = tc_smem;
   const uint4* wf = reinterpret_cast<const uint4*>(tc_smem);
-  float* misc = tc_smem + kTcWFloats + kTcWarps * kStageFloats;   // dom[6] | S | 1/S | partial maxima[4]
+  float* misc = tc_smem + kTcWFloats + kTcWarps * kStageFloats;   // dom[6] | S | 1/S | partial maxima
   const float* dom = misc;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   float* stg = tc_smem + kTcWFloats + warp * kStageFloats;
@@ -523,13 +372,20 @@ eval_tc_kernel(const int32_t* __restrict__ query, const int32_t* __restrict__ so
   int cached_net = -1;
   const int per_block = (n_items + (int)gridDim.x - 1) / (int)gridDim.x;
   const int item_end = min(n_items, ((int)blockIdx.x + 1) * per_block);
+  // network of an item = last n with item_start[n] <= item: one binary search for the block's first item, then a
+  // forward walk (consecutive items mostly share the network; the search was 12 dependent L2 round trips per item)
+  int net = 0, net_items_end = 0;
   for (int item = (int)blockIdx.x * per_block; item < item_end; ++item) {
-    int lo = 0, hi = num_networks;
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (item_start[mid] <= item) lo = mid; else hi = mid;
+    if (cached_net < 0) {
+      int lo = 0, hi = num_networks;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (item_start[mid] <= item) lo = mid; else hi = mid;
+      }
+      net = lo;
+      net_items_end = item_start[net + 1];
     }
-    const int net = lo;
+    while (item >= net_items_end) net_items_end = item_start[++net + 1];
     if (net != cached_net) {
       __syncthreads();
       const float* src = params + (size_t)net * kParamSize;
@@ -539,7 +395,9 @@ eval_tc_kernel(const int32_t* __restrict__ query, const int32_t* __restrict__ so
       for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
       if (lane == 0) misc[8 + warp] = mx;
       __syncthreads();
-      mx = fmaxf(fmaxf(misc[8], misc[9]), fmaxf(misc[10], misc[11]));
+      mx = 0.f;
+#pragma unroll
+      for (int k = 0; k < kTcWarps; ++k) mx = fmaxf(mx, misc[8 + k]);
       int ex = 0;
       if (mx > 0.f && mx < 3.0e38f) frexpf(mx, &ex);       // mx < 2^ex
       const float scale = ldexpf(1.f, min(max(14 - ex, -100), 100));
@@ -673,22 +531,23 @@ eval_tc_kernel(const int32_t* __restrict__ query, const int32_t* __restrict__ so
         mma_kstep<1>(o, a, wf + (kT4 + j) * 32, lane);
       }
       finish_layer<1, false>(o, w + kTb4, inv_s, t);
-      // thread t = 0 of a quad holds (r, g) of rows g / g+8, t = 1 holds b; density = column 0 of tile 4 of layer 2
+      // outputs: thread t = 0 of a quad holds (r, g) of rows g / g+8 and the density (column 0 of tile 4 of layer 2),
+      // t = 1 holds b.  Lane t of the quad finishes and stores component t of the row's float4 (one sigmoid per lane and
+      // row instead of three on a quarter of the lanes; the quad's four 4-byte stores fall into one 16-byte segment)
+      const int q0 = lane & ~3;
 #pragma unroll
-      for (int m = 0; m < 2; ++m) {
-        const float b_lo = __shfl_down_sync(0xffffffffu, o[m][0][0], 1);
-        const float b_hi = __shfl_down_sync(0xffffffffu, o[m][0][2], 1);
-        const int s_lo = __shfl_sync(0xffffffffu, slot, m * 16 + g);
-        const int s_hi = __shfl_sync(0xffffffffu, slot, m * 16 + g + 8);
-        if (t == 0) {
-          if (s_lo >= 0)
-            rgb_sigma[s_lo] = make_float4(1.f / (1.f + expf(-o[m][0][0])), 1.f / (1.f + expf(-o[m][0][1])),
-                                          1.f / (1.f + expf(-b_lo)), fmaxf(h2[m][4][0], 0.f));
-          if (s_hi >= 0)
-            rgb_sigma[s_hi] = make_float4(1.f / (1.f + expf(-o[m][0][2])), 1.f / (1.f + expf(-o[m][0][3])),
-                                          1.f / (1.f + expf(-b_hi)), fmaxf(h2[m][4][2], 0.f));
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int hrow = 0; hrow < 2; ++hrow) {
+          const float c_r = o[m][0][2 * hrow], c_g = o[m][0][2 * hrow + 1], c_s = h2[m][4][2 * hrow];
+          const float x_g = __shfl_sync(0xffffffffu, c_g, q0);
+          const float x_b = __shfl_sync(0xffffffffu, c_r, q0 + 1);
+          const float x_s = __shfl_sync(0xffffffffu, c_s, q0);
+          const int s_row = __shfl_sync(0xffffffffu, slot, m * 16 + g + 8 * hrow);
+          const float x = t == 0 ? c_r : (t == 1 ? x_g : (t == 2 ? x_b : x_s));
+          const float y = t == 3 ? fmaxf(x, 0.f) : 1.f / (1.f + expf(-x));
+          if (s_row >= 0) reinterpret_cast<float*>(rgb_sigma + s_row)[t] = y;
         }
-      }
     }
   }
 }
@@ -871,20 +730,13 @@ static int eval_pass(const Work& w, const nerfb200_kilo_camera* cam, const nerfb
   int dev = 0, sms = 0;
   NB_CUDA(cudaGetDevice(&dev));
   NB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  static const bool use_ffma = getenv("NERFB200_KILO_FFMA") != nullptr;   // A/B switch: the CUDA-core kernel of round 1
-  if (use_ffma) {
-    eval_kernel<<<sms * 3, kEvalThreads, 0, st>>>(w.query, w.sorted, w.start, w.item_start, num_networks, params, domain_mins, domain_maxs, ec,
-                                                  w.rgb_sigma, w.counters);
-    NB_LAUNCH_OK("kilo::eval_kernel");
-    return 0;
-  }
   NB_CHECK_ARG(dev >= 0 && dev < 64, "kilo: device ordinal %d out of range", dev);
   static bool attr_set[64] = {};   // opt-in to > 48 KB of dynamic shared memory: per device, sticky
   if (!attr_set[dev]) {
     NB_CUDA(cudaFuncSetAttribute(eval_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
     attr_set[dev] = true;
   }
-  eval_tc_kernel<<<sms * 3, kTcThreads, kTcSmemBytes, st>>>(w.query, w.sorted, w.start, w.item_start, num_networks, params, domain_mins,
+  eval_tc_kernel<<<sms * 2, kTcThreads, kTcSmemBytes, st>>>(w.query, w.sorted, w.start, w.item_start, num_networks, params, domain_mins,
                                                             domain_maxs, ec, w.rgb_sigma, w.counters);
   NB_LAUNCH_OK("kilo::eval_tc_kernel");
   return 0;
