@@ -71,6 +71,13 @@ __global__ void march_kernel(nerfb200_kilo_grid g, const float* __restrict__ ori
   int stride[3] = {g.res[1] * g.res[2], g.res[2], 1};
 #pragma unroll
   for (int c = 0; c < 3; ++c) voxel[c] = __fdiv_rn(__fsub_rn(g.gmax[c], g.gmin[c]), (float)g.res[c]);
+  float inv_voxel[3], lo_in[3], hi_in[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    inv_voxel[c] = __fdiv_rn(1.f, voxel[c]);
+    lo_in[c] = __fadd_rn(g.gmin[c], 0.001f);
+    hi_in[c] = __fsub_rn(g.gmax[c], 0.001f);
+  }
   int emitted = 0;
   for (int ray = blockIdx.x * blockDim.x + threadIdx.x; ray < n_rays; ray += gridDim.x * blockDim.x) {
     int out = 0;
@@ -82,15 +89,30 @@ __global__ void march_kernel(nerfb200_kilo_grid g, const float* __restrict__ ori
       int depth = initial ? 0 : depth_idx[ray];
       float dist = __fadd_rn(min_distance, __fmul_rn((float)depth, dbp));
       while (depth < max_depth && out < spp) {
-        int flat = 0;
+        float p[3];
         bool inside = true;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const float p = __fadd_rn(o[c], __fmul_rn(dist, d[c]));
-          flat += (int)__fdiv_rn(__fsub_rn(p, g.gmin[c]), voxel[c]) * stride[c];
-          inside = inside && (__fadd_rn(g.gmin[c], 0.001f) < p) && (p < __fsub_rn(g.gmax[c], 0.001f));
+          p[c] = __fadd_rn(o[c], __fmul_rn(dist, d[c]));
+          inside = inside && (lo_in[c] < p[c]) && (p[c] < hi_in[c]);
         }
-        const int net = inside ? (int)grid[flat] : -1;
+        int net = -1;
+        if (inside) {
+          // cell index = (int)((p - gmin) / voxel), the reference's IEEE division (generate_inputs.cu:100-104).  The
+          // product with the reciprocal is within 3 ulp of that quotient, so the two truncate to the same integer
+          // unless the product lies within 3 ulp of one; only then is the division itself evaluated (bit-exact
+          // either way; the three divisions were ~40 % of the loop's instructions).
+          int flat = 0;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float x = __fsub_rn(p[c], g.gmin[c]);
+            float qv = __fmul_rn(x, inv_voxel[c]);
+            const float fr = qv - truncf(qv), tol = qv * 4e-7f;
+            if (fr < tol || fr > 1.f - tol) qv = __fdiv_rn(x, voxel[c]);
+            flat += (int)qv * stride[c];
+          }
+          net = (int)grid[flat];
+        }
         if (net != -1) {
           a[out] = (int16_t)net;
           q[out] = ray * max_depth + depth;
