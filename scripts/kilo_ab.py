@@ -1,5 +1,5 @@
-"""A/B of the micro-MLP kernels of the a9 path on the bench's scene: frame time and the eval kernel's own time
-(CUDA events around kilo.network_eval_query_index on the first pass's queries), plus the difference of the outputs."""
+"""Frame time of the a9 path on the bench's scene (median of 5) and a dump of the rgb map, used for the A/B record of the
+micro-MLP kernels in profiles/r02_kilo_ab.txt (the variants were separate builds; the CUDA-core kernel is gone)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -22,5 +22,5 @@ for _ in range(5):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); out = kr.render(b); e1.record(); torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))
-print("variant", "ffma" if os.environ.get("NERFB200_KILO_FFMA") else "tc", "frame ms", np.median(ts), "samples", int(kr.stats[0]))
+print("frame ms", np.median(ts), "samples", int(kr.stats[0]))
 np.save(sys.argv[1], out["rgb_map"].cpu().numpy())
