@@ -255,34 +255,51 @@ __global__ void wgrad_finalize_kernel(const float* __restrict__ scratch, nerfb20
 // chain rule through the fused tail W' = Wv_a Wf, b' = Wv_a bf + bv (Wv_a = views_linears.0.weight[:, :256]):
 //   d Wv_a[n][j] = sum_k dW'[n][k] Wf[j][k] + db'[n] bf[j]      (blocks 0..127, one output row n each)
 //   d Wf[j][k]   = sum_n Wv_a[n][j] dW'[n][k],  d bf[j] = sum_n Wv_a[n][j] db'[n]   (blocks 128..383, row j each)
-__global__ void __launch_bounds__(256) wgrad_tail_kernel(const float* __restrict__ scratch, nerfb200_mlp_weights w, nerfb200_mlp_grads g) {
+__global__ void __launch_bounds__(1024) wgrad_tail_kernel(const float* __restrict__ scratch, nerfb200_mlp_weights w, nerfb200_mlp_grads g) {
   const float* sc = scratch + (size_t)8 * 256 * kGradCols;     // rows 0..127: dW' in cols 0..255, db' in col kGradOnes
   __shared__ float sh[256];
-  const int t = threadIdx.x;
+  __shared__ float part[4][256];
+  const int t = threadIdx.x & 255, q = threadIdx.x >> 8, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (blockIdx.x < 128) {
+    // d views_w[n][0:256] = dW'[n][:] Wf^T + db'[n] bf: warp = 8 output columns, the lanes split the contraction
+    // (coalesced rows of Wf, all loads independent), shuffle tree at the end
     const int n = blockIdx.x;
-    sh[t] = sc[(size_t)n * kGradCols + kGradMain + t];
+    if (q == 0) sh[t] = sc[(size_t)n * kGradCols + kGradMain + t];
     __syncthreads();
-    const float4* wf = reinterpret_cast<const float4*>(w.feature_w + (size_t)t * 256);   // row j = t of Wf
-    float acc = sc[(size_t)n * kGradCols + kGradOnes] * w.feature_b[t];
-#pragma unroll 4
-    for (int k4 = 0; k4 < 64; ++k4) {
-      const float4 v = __ldg(wf + k4);
-      acc = fmaf(sh[4 * k4], v.x, acc); acc = fmaf(sh[4 * k4 + 1], v.y, acc);
-      acc = fmaf(sh[4 * k4 + 2], v.z, acc); acc = fmaf(sh[4 * k4 + 3], v.w, acc);
+    const float dbn = sc[(size_t)n * kGradCols + kGradOnes];
+    float x[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) x[r] = sh[lane * 8 + r];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int col = warp * 8 + i;
+      const float4* wf = reinterpret_cast<const float4*>(w.feature_w + (size_t)col * 256 + lane * 8);
+      const float4 v0 = __ldg(wf), v1 = __ldg(wf + 1);
+      float acc = x[0] * v0.x;
+      acc = fmaf(x[1], v0.y, acc); acc = fmaf(x[2], v0.z, acc); acc = fmaf(x[3], v0.w, acc);
+      acc = fmaf(x[4], v1.x, acc); acc = fmaf(x[5], v1.y, acc); acc = fmaf(x[6], v1.z, acc); acc = fmaf(x[7], v1.w, acc);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) g.views_w[(size_t)n * 283 + col] = fmaf(dbn, w.feature_b[col], acc);
     }
-    g.views_w[(size_t)n * 283 + t] = acc;
   } else {
+    // d feature_w[j][0:256] = Wv[:, j]^T dW', d feature_b[j] = Wv[:, j]^T db': four thread groups x 32 rows each
     const int j = blockIdx.x - 128;
-    if (t < 128) sh[t] = w.views_w[(size_t)t * 283 + j];      // column j of Wv_a
+    if (threadIdx.x < 128) sh[threadIdx.x] = w.views_w[(size_t)threadIdx.x * 283 + j];      // column j of Wv_a
     __syncthreads();
     float acc = 0.f, accb = 0.f;
-    for (int n = 0; n < 128; ++n) {
+#pragma unroll 16
+    for (int n = q * 32; n < q * 32 + 32; ++n) {
       acc = fmaf(sh[n], sc[(size_t)n * kGradCols + kGradMain + t], acc);
       if (t == 0) accb = fmaf(sh[n], sc[(size_t)n * kGradCols + kGradOnes], accb);
     }
-    g.feature_w[(size_t)j * 256 + t] = acc;
-    if (t == 0) g.feature_b[j] = accb;
+    part[q][t] = acc;
+    if (t == 0) sh[128 + q] = accb;
+    __syncthreads();
+    if (q == 0) {
+      g.feature_w[(size_t)j * 256 + t] = (part[0][t] + part[1][t]) + (part[2][t] + part[3][t]);
+      if (t == 0) g.feature_b[j] = (sh[128] + sh[129]) + (sh[130] + sh[131]);
+    }
   }
 }
 
@@ -309,7 +326,7 @@ int launch_mlp_bwd_wgrad(const void* acts, const void* dacts, long long M, float
   }
   wgrad_finalize_kernel<<<dim3(40, kWgradStages), 256, 0, st>>>(scratch, *grads);
   NB_LAUNCH_OK("wgrad_finalize_kernel");
-  wgrad_tail_kernel<<<384, 256, 0, st>>>(scratch, *weights, *grads);
+  wgrad_tail_kernel<<<384, 1024, 0, st>>>(scratch, *weights, *grads);
   NB_LAUNCH_OK("wgrad_tail_kernel");
   return 0;
 }

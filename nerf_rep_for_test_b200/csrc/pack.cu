@@ -106,38 +106,26 @@ __device__ __forceinline__ float dot256_strided(const float* __restrict__ a, con
   return (v0 + v1) + (v2 + v3);
 }
 
-// W' = Wv[:, :256] Wf and b' = Wv[:, :256] bf + bv in fp32, once per re-pack: thread = one column k of W' for four rows n
-// (Wf[j][k] is read coalesced and reused for the four rows, Wv[n][j] broadcast from shared memory).  Every element is
-// the same four-accumulator sum as dot256_strided (accumulator j % 4, increasing j, (v0+v1)+(v2+v3)), so the images are
-// bit-identical to what the per-element dots produced; the two per-element versions took 38 + 40 us per model and step.
-constexpr int kProdRows = 4;
-__global__ void __launch_bounds__(256) fused_tail_product_kernel(nerfb200_mlp_weights w, float* __restrict__ prod) {
-  __shared__ float a[kProdRows][256];
-  const int n0 = blockIdx.x * kProdRows, k = threadIdx.x;
-  for (int i = threadIdx.x; i < kProdRows * 256; i += 256) a[i >> 8][i & 255] = w.views_w[(size_t)(n0 + (i >> 8)) * 283 + (i & 255)];
+// W' = Wv[:, :256] Wf and b' = Wv[:, :256] bf + bv in fp32, once per re-pack.  One block per row n of W', thread
+// (k, q) = (column, accumulator): every element is the four-accumulator sum of dot256_strided (accumulator j % 4,
+// increasing j, (v0+v1)+(v2+v3)) -- bit-identical to the per-element dots of the first version (38 + 40 us per model and
+// step) -- with the four chains on four threads.  The loop is a chain of L2 round trips (ptxas keeps ~5 loads in flight
+// whatever the source says), so the lever is threads: 128 blocks x 1024 threads instead of 32 x 256 (26 us).
+__global__ void __launch_bounds__(1024) fused_tail_product_kernel(nerfb200_mlp_weights w, float* __restrict__ prod) {
+  __shared__ float a[256];
+  __shared__ float fb[256];
+  __shared__ float part[4][256];
+  const int n = blockIdx.x, k = threadIdx.x & 255, q = threadIdx.x >> 8;
+  if (q == 0) a[k] = w.views_w[(size_t)n * 283 + k];
+  if (q == 1) fb[k] = w.feature_b[k];
   __syncthreads();
-  float acc[kProdRows][4];
-#pragma unroll
-  for (int r = 0; r < kProdRows; ++r)
-#pragma unroll
-    for (int q = 0; q < 4; ++q) acc[r][q] = 0.f;
-  // 32 loads of Wf in flight per thread (the loop is bound by L2 latency: 42 us with 8 in flight, measured)
-#pragma unroll 1
-  for (int j0 = 0; j0 < 256; j0 += 32) {
-    float b[32];
-#pragma unroll
-    for (int q = 0; q < 32; ++q) b[q] = __ldg(w.feature_w + (size_t)(j0 + q) * 256 + k);
-#pragma unroll
-    for (int q = 0; q < 32; ++q)
-#pragma unroll
-      for (int r = 0; r < kProdRows; ++r) acc[r][q & 3] = fmaf(a[r][j0 + q], b[q], acc[r][q & 3]);
-  }
-#pragma unroll
-  for (int r = 0; r < kProdRows; ++r) prod[(size_t)(n0 + r) * 256 + k] = (acc[r][0] + acc[r][1]) + (acc[r][2] + acc[r][3]);
-  if (threadIdx.x < kProdRows) {   // b'[n]
-    const int n = n0 + threadIdx.x;
-    prod[128 * 256 + n] = w.views_b[n] + dot256_strided(w.views_w + (size_t)n * 283, w.feature_b, 1);
-  }
+  float acc = 0.f;
+#pragma unroll 16
+  for (int j = q; j < 256; j += 4) acc = fmaf(a[j], __ldg(w.feature_w + (size_t)j * 256 + k), acc);
+  part[q][k] = acc;
+  __syncthreads();
+  if (q == 0) prod[(size_t)n * 256 + k] = (part[0][k] + part[1][k]) + (part[2][k] + part[3][k]);
+  if (threadIdx.x == 256) prod[128 * 256 + n] = w.views_b[n] + dot256_strided(a, fb, 1);   // b'[n]
 }
 
 // split-fp16 image (NERFB200_MODE_FP32_TC, mlp_layout.cuh): one block per stage finds max|w| of the stage's tensor and
@@ -307,14 +295,14 @@ extern "C" int nerfb200_pack_weights(const nerfb200_mlp_weights* w, int mode, vo
     pack_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*w, tab, (float*)packed);
   else if (mode == NERFB200_MODE_FP32_TC) {
     float* prod = reinterpret_cast<float*>((unsigned char*)packed + kX2ProdOff);
-    fused_tail_product_kernel<<<128 / kProdRows, 256, 0, (cudaStream_t)stream>>>(*w, prod);
+    fused_tail_product_kernel<<<128, 1024, 0, (cudaStream_t)stream>>>(*w, prod);
     NB_LAUNCH_OK("fused_tail_product_kernel");
     stage_scale_kernel<<<kStages, 256, 0, (cudaStream_t)stream>>>(*w, reinterpret_cast<float*>((unsigned char*)packed + kX2TailOff), prod);
     NB_LAUNCH_OK("stage_scale_kernel");
     pack_f16x2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*w, (unsigned char*)packed);
   } else {
     const bool f16 = mode == NERFB200_MODE_FP16;
-    fused_tail_product_kernel<<<128 / kProdRows, 256, 0, (cudaStream_t)stream>>>(
+    fused_tail_product_kernel<<<128, 1024, 0, (cudaStream_t)stream>>>(
         *w, reinterpret_cast<float*>((unsigned char*)packed + kFusedProdOff));
     NB_LAUNCH_OK("fused_tail_product_kernel");
     pack_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*w, tab, (unsigned char*)packed, f16);

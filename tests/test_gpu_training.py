@@ -123,10 +123,18 @@ def test_graph_captured_step_equals_eager_step():
         outs.append((losses, [p.detach().clone() for p in net.parameters()]))
     for le, lg in zip(*[o[0] for o in outs]):
         assert abs(le - lg) <= 2e-5 * max(abs(le), 1e-3), (outs[0][0], outs[1][0])
+    n_far = n_all = 0
     for a, b in zip(outs[0][1], outs[1][1]):
-        # Adam normalises the gradient: where it is ~0 a last-digit difference can flip a step of size lr, so the bound
-        # is a fraction of the 8 x lr = 4e-3 a parameter can move in these steps (observed: 1.5e-4)
-        assert float((a - b).abs().max()) <= 1e-3
+        # Adam normalises the gradient: where it is ~0 a last-digit difference of the (atomically summed) gradient can flip
+        # the sign of a step of size lr, and such an entry can drift by up to 8 x lr = 4e-3 in these steps.  So: no entry
+        # beyond what eight steps can move, and all but a sliver of the 1.19 M entries within a fraction of it (observed:
+        # max 1.5e-4 and no entry beyond 3e-4 in most runs; in about one run of eight one hidden unit's relu flips for a
+        # sample and the ~150 weights around it end up to 1.2e-3 apart).
+        d = (a - b).abs()
+        assert float(d.max()) <= 8 * 5e-4 * 1.05
+        n_far += int((d > 3e-4).sum())
+        n_all += d.numel()
+    assert n_far <= 1e-3 * n_all, (n_far, n_all)
     assert outs[0][0][-1] < outs[0][0][0]
 
 
