@@ -106,26 +106,34 @@ __device__ __forceinline__ float dot256_strided(const float* __restrict__ a, con
   return (v0 + v1) + (v2 + v3);
 }
 
-// W' = Wv[:, :256] Wf and b' = Wv[:, :256] bf + bv in fp32, once per re-pack.  One block per row n of W', thread
-// (k, q) = (column, accumulator): every element is the four-accumulator sum of dot256_strided (accumulator j % 4,
-// increasing j, (v0+v1)+(v2+v3)) -- bit-identical to the per-element dots of the first version (38 + 40 us per model and
-// step) -- with the four chains on four threads.  The loop is a chain of L2 round trips (ptxas keeps ~5 loads in flight
-// whatever the source says), so the lever is threads: 128 blocks x 1024 threads instead of 32 x 256 (26 us).
+// W' = Wv[:, :256] Wf and b' = Wv[:, :256] bf + bv in fp32, once per re-pack.  Every element is the four-accumulator
+// sum of dot256_strided (accumulator j % 4, increasing j, (v0+v1)+(v2+v3)) -- bit-identical to the per-element dots of the
+// first version (38 + 40 us per model and step) -- with the four chains on four threads.  Block = an 8-row x 32-column
+// tile of W' with both operand tiles in shared memory (41 KB read per block, 5 MB in all).  History: 32 blocks x 256
+// threads reading Wf through __ldg took 26-39 us (a chain of L2 round trips per thread; ptxas keeps ~5 loads in flight
+// whatever the source says); 128 blocks x 1024 threads, every block streaming all of Wf, 15-22 us (ncu: 32 MB of L2 reads
+// of the same 256 KB by all SMs at once, long-scoreboard stall 52 per issue).
 __global__ void __launch_bounds__(1024) fused_tail_product_kernel(nerfb200_mlp_weights w, float* __restrict__ prod) {
-  __shared__ float a[256];
+  __shared__ float wf[256][32];     // Wf[:, k0 .. k0+32); reused for the four partial sums
+  __shared__ float a[8][256];       // Wv[n0 .. n0+8, :256]
   __shared__ float fb[256];
-  __shared__ float part[4][256];
-  const int n = blockIdx.x, k = threadIdx.x & 255, q = threadIdx.x >> 8;
-  if (q == 0) a[k] = w.views_w[(size_t)n * 283 + k];
-  if (q == 1) fb[k] = w.feature_b[k];
+  const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 8;
+  const int kk = threadIdx.x & 31, nn = (threadIdx.x >> 5) & 7, q = threadIdx.x >> 8;
+  for (int i = threadIdx.x; i < 256 * 32; i += 1024) wf[i >> 5][i & 31] = __ldg(w.feature_w + (size_t)(i >> 5) * 256 + k0 + (i & 31));
+  for (int i = threadIdx.x; i < 8 * 256; i += 1024) a[i >> 8][i & 255] = w.views_w[(size_t)(n0 + (i >> 8)) * 283 + (i & 255)];
+  if (threadIdx.x < 256) fb[threadIdx.x] = w.feature_b[threadIdx.x];
   __syncthreads();
   float acc = 0.f;
 #pragma unroll 16
-  for (int j = q; j < 256; j += 4) acc = fmaf(a[j], __ldg(w.feature_w + (size_t)j * 256 + k), acc);
-  part[q][k] = acc;
+  for (int j = q; j < 256; j += 4) acc = fmaf(a[nn][j], wf[j][kk], acc);
   __syncthreads();
-  if (q == 0) prod[(size_t)n * 256 + k] = (part[0][k] + part[1][k]) + (part[2][k] + part[3][k]);
-  if (threadIdx.x == 256) prod[128 * 256 + n] = w.views_b[n] + dot256_strided(a, fb, 1);   // b'[n]
+  float* part = &wf[0][0];          // [4][8][32]
+  part[(q * 8 + nn) * 32 + kk] = acc;
+  __syncthreads();
+  if (q == 0)
+    prod[(size_t)(n0 + nn) * 256 + k0 + kk] = (part[nn * 32 + kk] + part[(8 + nn) * 32 + kk]) + (part[(16 + nn) * 32 + kk] + part[(24 + nn) * 32 + kk]);
+  if (blockIdx.x == 0 && threadIdx.x < 8)   // b'[n]
+    prod[128 * 256 + n0 + threadIdx.x] = w.views_b[n0 + threadIdx.x] + dot256_strided(a[threadIdx.x], fb, 1);
 }
 
 // split-fp16 image (NERFB200_MODE_FP32_TC, mlp_layout.cuh): one block per stage finds max|w| of the stage's tensor and
@@ -295,14 +303,14 @@ extern "C" int nerfb200_pack_weights(const nerfb200_mlp_weights* w, int mode, vo
     pack_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*w, tab, (float*)packed);
   else if (mode == NERFB200_MODE_FP32_TC) {
     float* prod = reinterpret_cast<float*>((unsigned char*)packed + kX2ProdOff);
-    fused_tail_product_kernel<<<128, 1024, 0, (cudaStream_t)stream>>>(*w, prod);
+    fused_tail_product_kernel<<<dim3(8, 16), 1024, 0, (cudaStream_t)stream>>>(*w, prod);
     NB_LAUNCH_OK("fused_tail_product_kernel");
     stage_scale_kernel<<<kStages, 256, 0, (cudaStream_t)stream>>>(*w, reinterpret_cast<float*>((unsigned char*)packed + kX2TailOff), prod);
     NB_LAUNCH_OK("stage_scale_kernel");
     pack_f16x2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*w, (unsigned char*)packed);
   } else {
     const bool f16 = mode == NERFB200_MODE_FP16;
-    fused_tail_product_kernel<<<128, 1024, 0, (cudaStream_t)stream>>>(
+    fused_tail_product_kernel<<<dim3(8, 16), 1024, 0, (cudaStream_t)stream>>>(
         *w, reinterpret_cast<float*>((unsigned char*)packed + kFusedProdOff));
     NB_LAUNCH_OK("fused_tail_product_kernel");
     pack_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*w, tab, (unsigned char*)packed, f16);
