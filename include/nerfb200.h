@@ -359,7 +359,10 @@ NERFB200_API int nerfb200_kilo_march(const nerfb200_kilo_grid* g, const float* o
 NERFB200_API size_t nerfb200_kilo_workspace_bytes(int n_rays, int max_samples_per_ray, int num_networks);
 /* network_eval.cu:24-254 on every filled slot: groups the queries by network on the device (counting sort,
  * replaces cuda/reorder.cu), evaluates, and writes (sigmoid rgb, relu sigma) back to the slot; unfilled slots
- * get 0.  params [num_networks,6212], domain_mins/maxs [num_networks,3]. */
+ * get 0.  params [num_networks,6212], domain_mins/maxs [num_networks,3].  Arithmetic: fp32-accurate on tensor
+ * cores (every operand carried as two fp16 numbers, three MMAs per product, fp32 accumulate; a network's weights
+ * are pre-scaled by a power of two, so their magnitude is free) -- hidden activations must stay below 65504 in
+ * magnitude (saturating conversion beyond). */
 NERFB200_API int nerfb200_kilo_network_eval(const nerfb200_kilo_camera* cam, const nerfb200_kilo_march_params* mp,
                                const int32_t* query_indices, const int16_t* assigned_networks, int n_rays,
                                const float* params, const float* domain_mins, const float* domain_maxs, int num_networks,

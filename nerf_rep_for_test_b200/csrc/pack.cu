@@ -111,8 +111,9 @@ __device__ __forceinline__ float dot256_strided(const float* __restrict__ a, con
 // first version (38 + 40 us per model and step) -- with the four chains on four threads.  Block = an 8-row x 32-column
 // tile of W' with both operand tiles in shared memory (41 KB read per block, 5 MB in all).  History: 32 blocks x 256
 // threads reading Wf through __ldg took 26-39 us (a chain of L2 round trips per thread; ptxas keeps ~5 loads in flight
-// whatever the source says); 128 blocks x 1024 threads, every block streaming all of Wf, 15-22 us (ncu: 32 MB of L2 reads
-// of the same 256 KB by all SMs at once, long-scoreboard stall 52 per issue).
+// whatever the source says); 128 blocks x 1024 threads with 64 loads per thread still 15-22 us (ncu: long-scoreboard
+// stall 52 per issue, L2 at 3 % of its throughput: latency, not bandwidth).  The tile fills below are independent
+// coalesced loads, eight per thread.
 __global__ void __launch_bounds__(1024) fused_tail_product_kernel(nerfb200_mlp_weights w, float* __restrict__ prod) {
   __shared__ float wf[256][32];     // Wf[:, k0 .. k0+32); reused for the four partial sums
   __shared__ float a[8][256];       // Wv[n0 .. n0+8, :256]

@@ -84,6 +84,61 @@ def test_network_eval_vs_oracle():
     assert err_rgb < 5e-4 and err_sig < 5e-4
 
 
+def test_network_eval_weight_magnitudes_are_free():
+    """The tensor-core micro-MLP carries every operand as two fp16 numbers and scales a network's weights by one power
+    of two (kilo.cu, eval_tc_kernel).  Rescaling layer 0 by 1/s and layer 1 by s (s a power of two, relu is positively
+    homogeneous) leaves the function unchanged in exact arithmetic while spreading the weights of ONE network over
+    s^2 in magnitude; a whole-network factor on the last layer moves them by 2^+-20 relative to fp16's range.  The
+    outputs must not move beyond fp32 rounding noise."""
+    sc = K.make_scene(seed=2, net_res=8, grid_res=64, blob_radius=1.3)
+    cam, _ = _cam(32, 32)
+    d = K.get_rays_d(cam["H"], cam["W"], cam["cx"], cam["cy"], cam["fx"], cam["fy"], cam["c2w"])
+    spp = 32
+    q, a, _, _ = K.march(cam["origin"], d, sc["grid"], None, None, sc["gmin"], sc["gmax"], SC["dbp"], spp, SC["max_depth"],
+                         SC["min_distance"], True)
+    filled = a >= 0
+
+    def run(params):
+        return kilo.network_eval_query_index(torch.from_numpy(q).to(DEV), torch.from_numpy(a).to(DEV),
+                                             torch.from_numpy(params).to(DEV), torch.from_numpy(sc["domain_mins"]).to(DEV),
+                                             torch.from_numpy(sc["domain_maxs"]).to(DEV), cam["H"], cam["W"], cam["cx"], cam["cy"],
+                                             cam["fx"], cam["fy"], cam["c2w"], cam["origin"], SC["max_depth"], SC["min_distance"],
+                                             SC["dbp"]).cpu().numpy()
+
+    base = run(sc["params"])
+    l0, l1 = 0, 32 + 63 * 32                      # layer offsets in the packed parameter vector (network_eval.cu:48-52)
+    l2 = l1 + 32 + 32 * 32
+    rs = np.random.RandomState(0)
+    for log2s in (6, -6, 9):
+        p = sc["params"].copy()
+        s = np.float32(2.0 ** log2s)
+        # per-network choice of which nets are rescaled, so neighbouring work items see different scales
+        pick = rs.rand(p.shape[0]) < 0.7
+        p[pick, l0:l1] /= s                       # bias and weights of layer 0
+        p[pick, l1 + 32:l2] *= s                  # weights (not the bias) of layer 1
+        got = run(p)
+        assert np.all(got[~filled] == 0)
+        err_rgb = np.abs(got[..., :3] - base[..., :3]).max()
+        err_sig = np.abs(got[..., 3] - base[..., 3]).max() / max(1.0, float(base[..., 3].max()))
+        print("rescaled by 2^%d: rgb %.2e sigma %.2e" % (log2s, err_rgb, err_sig))
+        assert err_rgb < 2e-5 and err_sig < 2e-5, (log2s, err_rgb, err_sig)
+    # every parameter of every network times 2^-20 / 2^20 in the LAST layer only shifts the rgb logits: compare with the
+    # oracle on those parameters (sigmoid saturates for the large factor: only finiteness and the density are checked)
+    for log2s in (-20, 12):
+        p = sc["params"].copy()
+        l4 = p.shape[1] - (3 + 32 * 3)
+        p[:, l4:] *= np.float32(2.0 ** log2s)
+        got = run(p)
+        assert np.isfinite(got).all()
+        err_sig = np.abs(got[..., 3] - base[..., 3]).max() / max(1.0, float(base[..., 3].max()))
+        assert err_sig < 2e-5, (log2s, err_sig)
+        want = np.zeros_like(got)
+        want[filled] = K.network_eval(q[filled], a[filled], p, sc["domain_mins"], sc["domain_maxs"], cam["H"], cam["W"], cam["cx"],
+                                      cam["cy"], cam["fx"], cam["fy"], cam["c2w"], cam["origin"], SC["max_depth"],
+                                      SC["min_distance"], SC["dbp"])
+        assert np.abs(got[..., :3] - want[..., :3]).max() < 5e-4, log2s
+
+
 def test_integrate_vs_oracle_two_passes():
     rs = np.random.RandomState(0)
     n, spp = 500, 12
