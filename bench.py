@@ -176,8 +176,8 @@ def cpu_model():
 
 
 def time_cpu_reference(reps, warmup, budget_s=None, n_rays=1024):
-    """Median of `reps` renders after `warmup` untimed ones (the mean of a handful of unpinned runs moved 2x between
-    boxes in round 1); with budget_s, as many renders as fit (at least 5)."""
+    """Lower quartile of `reps` renders after `warmup` untimed ones (the mean of a handful of unpinned runs moved 2x between
+    boxes in round 1, and so did the median in round 2); with budget_s, as many renders as fit (at least 5)."""
     import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -191,11 +191,15 @@ def time_cpu_reference(reps, warmup, budget_s=None, n_rays=1024):
         fn()
         times.append(time.perf_counter() - t0)
     times.sort()
-    med = times[len(times) // 2]
-    sample = "%s; 64+128 samples, torch %s CPU fp32, %d threads on %s; median of %d renders after %d warm-ups (min %.0f / max %.0f ms)" % (
-        what, torch.__version__, cores, cpu_model(), len(times), warmup, times[0] * 1e3, times[-1] * 1e3)
-    return med, n_rays, {"value": n_rays / med, "unit": "rays/s", "cores": cores, "kind": kind, "sample": sample,
-                         "timed_renders": len(times), "warmup_renders": warmup}
+    # The render time on the GPU boxes' hosts is BIMODAL (~190 ms and ~430 ms for the same 1024 rays: the median of one
+    # process landed on either mode, 5131 vs 2457 rays/s on the same box type in round 2), so the figure is the lower
+    # quartile: the reference at the speed it sustains whenever the host lets it -- the choice that favours the reference.
+    q1 = times[len(times) // 4]
+    sample = ("%s; 64+128 samples, torch %s CPU fp32, %d threads on %s; lower quartile of %d renders after %d warm-ups "
+              "(min %.0f / median %.0f / max %.0f ms)" % (what, torch.__version__, cores, cpu_model(), len(times), warmup,
+                                                         times[0] * 1e3, times[len(times) // 2] * 1e3, times[-1] * 1e3))
+    return q1, n_rays, {"value": n_rays / q1, "unit": "rays/s", "cores": cores, "kind": kind, "sample": sample,
+                        "timed_renders": len(times), "warmup_renders": warmup}
 
 
 def cpu_reference_rays_per_s(budget_s=12.0):
@@ -205,12 +209,12 @@ def cpu_reference_rays_per_s(budget_s=12.0):
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path on the host cores -- the unmodified
     reference when it is importable (build container), else the oracle port (the reference is a Python/torch program
-    that cannot travel to the GPU box).  value = rays / MEDIAN step time of max(steps, 5) steps."""
+    that cannot travel to the GPU box).  value = rays / lower-quartile step time of >= 15 steps."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     # the first renders of a fresh process are 2x slower than the steady state (thread pool, allocator, page faults:
-    # round 1's ratios moved 2x on that alone), so: at least 5 untimed renders, then the median of >= 15 timed ones
+    # round 1's ratios moved 2x on that alone), so: at least 5 untimed renders, then >= 15 timed ones
     steps = max(15, min(args.steps, 40))
     warm = max(5, min(args.warmup, 10))
     med, n_rays, cb = time_cpu_reference(steps, warm, budget_s=15.0)
