@@ -26,6 +26,13 @@ import subprocess
 import sys
 import threading
 import time
+_T0 = time.perf_counter()
+if os.environ.get("RANK", "0") == "0" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    # torchrun exports OMP_NUM_THREADS=1 to every rank, and torch.set_num_threads() does not undo it for the OpenMP / MKL
+    # pools created at import: rank 0 also runs the CPU checker of the parity block, which then took 147 s instead of
+    # ~20 s while the other ranks waited at a barrier.  Must happen before the first `import torch`.
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+    os.environ.pop("MKL_NUM_THREADS", None)
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -288,6 +295,12 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    def trace(what):                              # wall-clock section log on stderr (rank 0): where a run's minutes go
+        if rank == 0:
+            sys.stderr.write("[bench %7.1fs] %s\n" % (time.perf_counter() - _T0, what))
+            sys.stderr.flush()
+    trace("imports done")
     # stdout carries exactly ONE JSON line: native libraries (NCCL prints its version banner on fd 1) are sent to
     # stderr for the whole run and the line is written to the saved descriptor at the end
     sys.stdout.flush()
@@ -307,6 +320,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    trace("device / process group ready")
     sd = FX.make_state_dict(0)
     net = Network(device=dev)
     net.load_state_dict(sd)
@@ -382,9 +396,11 @@ def run_ours(args):
 
     # ---- parity gate in the same job: BASELINE config 1 (32x32 = 1024 rays of lego test pose
     # 0) and a 1024-ray subsample of the timed 800x800 frame, every mode against the CPU oracle (the checker)
+    trace("frame, e2e, modes timed")
     parity = None
     if args.parity and rank == 0:
         parity = parity_block(net, dev, args)
+    trace("parity block done")
 
     # ---- one 800x800 frame split into contiguous ray blocks over the ranks (SURVEY 8e, strong scaling): latency from
     # pose on the device to all eight maps in rank 0's pinned host memory, gather included
@@ -408,6 +424,7 @@ def run_ours(args):
 
     # ---- training step (BASELINE.json configs[2]): 4096 rays per GPU, fwd + bwd + gradient all-reduce +
     # clip + Adam; stratified jitter and random u (net.train()); random target colours
+    trace("sharded frame done")
     train_ms = 0.0
     train_graph = False
     train_variants = {}
@@ -514,6 +531,7 @@ def run_ours(args):
 
     # ---- BASELINE.json configs[4] part ii: the KiloNeRF-style path (a9): 16^3 micro-MLPs (32 wide, random
     # weights), 128^3 occupancy grid of network ids, fixed-step march + early ray termination; same camera.
+    trace("training, ESS/ERT done")
     kilo_cfg = None
     if args.config5 and rank == 0:
         from nerf_rep_for_test_b200 import kilo
@@ -553,6 +571,7 @@ def run_ours(args):
 
     # ---- BASELINE.json configs[3]: the 200-view 800x800 test set, views dealt round-robin to the ranks (no
     # inter-GPU traffic); time = device time of the slowest rank for its share, poses resident in HBM.
+    trace("a9 path done")
     testset_ms = 0.0
     if args.testset_views > 0:
         mine = [{"pose": lego_pose(i)[None].to(dev), "intrinsics": K0.clone().to(dev), "H": H, "W": W}
@@ -568,6 +587,7 @@ def run_ours(args):
         testset_ms = s0.elapsed_time(s1)
         barrier()
 
+    trace("test set done")
     t = torch.tensor([ms_total, e2e_ms, train_ms, testset_ms, frame_ms_local, train_strong_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
