@@ -27,12 +27,15 @@ import sys
 import threading
 import time
 _T0 = time.perf_counter()
-if os.environ.get("RANK", "0") == "0" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
-    # torchrun exports OMP_NUM_THREADS=1 to every rank, and torch.set_num_threads() does not undo it for the OpenMP / MKL
-    # pools created at import: rank 0 also runs the CPU checker of the parity block, which then took 147 s instead of
-    # ~20 s while the other ranks waited at a barrier.  Must happen before the first `import torch`.
-    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
-    os.environ.pop("MKL_NUM_THREADS", None)
+_WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+# CPU threads for the checker legs (parity block, CPU baseline) on rank 0: the box's cores divided by the ranks.  Under
+# torchrun the other ranks busy-wait at a barrier (one saturated core each) while rank 0 runs the CPU oracle; an OpenMP
+# pool as wide as the whole box then stalls every parallel region on whichever thread shares a core with a spinning
+# rank -- the parity block took 150 s instead of ~6 s at N = 2 and N = 8.  (torchrun's OMP_NUM_THREADS=1 itself is
+# harmless: torch.set_num_threads overrides it, scripts/cpu_oracle_threads.py.)
+CPU_THREADS = max(1, (os.cpu_count() or 1) // _WORLD)
+if _WORLD > 1 and os.environ.get("RANK", "0") == "0":
+    os.environ["OMP_NUM_THREADS"] = str(CPU_THREADS)      # before the first `import torch`
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -250,7 +253,7 @@ def parity_block(net, dev, args):
     from nerf_rep_for_test_b200 import Network, RenderConfig, Renderer
     from oracle import nerf_oracle as O
     from oracle import parity as PR
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(CPU_THREADS)
     modes = [m for m in args.parity.split(",") if m]
     b32 = FX.lego_batch(32, 32)
     ro32, rd32 = O.get_rays(32, 32, b32["pose"][0], b32["intrinsics"][0])
