@@ -130,8 +130,8 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
     // rays / PE of a tile are computed one tile ahead so that only the stores sit on the critical path
     long long m = 0, tile_next = 0;
     bool valid = false;
-    // training (kSave): finished operand tiles go to the activation store as tile images (train_layout.cuh);
-    // the group copies them out after the hand-off, behind a 128-thread named barrier (copy_tile_s2g)
+    // training (kSave): finished operand tiles go to the activation store as tile images (train_layout.cuh), as per-warp
+    // bulk stores issued while the epilogue produces them (mlp_tc_common.cuh, bulk_store_warp_rows)
     const long long n_tiles = (M + 127) / 128;
     const bool save_leader = kSave && w4 == 0 && lane == 0;
     float d[3] = {0.f, 0.f, 0.f};
@@ -170,7 +170,7 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
       const size_t mask_row = (size_t)tile_next * 128 + (size_t)row;
       const size_t mask_plane = (size_t)n_tiles * 128 * kMaskWords;
       float d_cur[3] = {d[0], d[1], d[2]};
-      if (kSave) named_bar_sync(1 + slot, 128);   // every thread has finished copying the previous tile out
+      if (kSave) bulk_store_warp_reads_done();    // the previous tile's stores have left this warp's rows (PE tile, A tile)
       {  // xyz PE tile -> shared memory (swizzled 16-byte chunks), then hand the slot to the MMA issuer
         const uint32_t row_base = pe_base + (uint32_t)row * 128u;
 #pragma unroll
@@ -180,7 +180,8 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
       fence_proxy_async_smem();
       if (kSave) named_bar_sync(1 + slot, 128);
       if (!kSave || save_leader) mbar_arrive_remote(b_ready_leader);
-      if (kSave && tile_ok) copy_tile_s2g<kBlockBytes>(acts_tile + (size_t)kActPe * kBlockBytes, smem_dyn + kOffPe + slot * kPeBytes, row);
+      if (kSave && tile_ok)
+        bulk_store_warp_rows(acts_tile + (size_t)kActPe * kBlockBytes + (size_t)w4 * 4096u, pe_base + (uint32_t)w4 * 4096u, 1);
       float sigma = 0.f;
       for (int stage = 0; stage < I::kN; ++stage) {
         const uint32_t bseq = (uint32_t)it * I::kN + (uint32_t)stage;
@@ -208,25 +209,18 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
             }
           }
         }
-#ifndef NB_SAVE_DIRECT
-        if (kSave) named_bar_sync(1 + slot, 128);   // all copies of the previous stage's tile are done: A may be rewritten
-#endif
+        if (kSave) bulk_store_warp_reads_done();   // the previous stage's stores have finished reading this warp's rows of A
         if (stage < I::kLast) {
           uint32_t mw[8];
-          // NB_SAVE_DIRECT (experiment, off): the bf16 stage output also goes straight from the epilogue's registers to
-          // its tile image in the activation store instead of being copied out of shared memory after the hand-off (the
-          // copy takes ~5000 cycles during which the group cannot start its next epilogue: per-slot period = epilogue +
-          // copy = 7000 cycles against two MMA passes = 5400).  Measured: with 16-byte stores SLOWER (4.47 -> 4.87 ms per
-          // step: one row per thread, so every warp-wide store touches 32 different 128-byte lines and the epilogue grows
-          // from ~1600 to ~9500 cycles); with 256-bit stores (STG.256, full sectors) the epilogue takes 5700-6900 cycles
-          // and the step 4.43-4.51 ms -- the same as the copy scheme (profiles/r02_experiments_not_merged.txt).
-          unsigned char* g_row = nullptr;
-#ifdef NB_SAVE_DIRECT
-          if (kSave && tile_ok && stage < 8) g_row = acts_tile + (size_t)act_h(stage) * kBlockBytes + (size_t)row * 128u;
-#endif
-          if (!kFused && stage == 7) epi_stage256<1, kSave, kF16>(t_acc, bias4, a_row_base, r7, tail + kTailAlphaW, sigma, mw, g_row);
+          unsigned char* bulk_g = nullptr;
+          uint32_t bulk_s = 0u;
+          if (kSave && tile_ok && stage < 8) {   // this warp's rows of the stage output (= the next A tile) in the activation store
+            bulk_g = acts_tile + (size_t)act_h(stage) * kBlockBytes + (size_t)w4 * 4096u;
+            bulk_s = smem_base + kOffA + (uint32_t)slot * kABytes + (uint32_t)w4 * 4096u;
+          }
+          if (!kFused && stage == 7) epi_stage256<1, kSave, kF16>(t_acc, bias4, a_row_base, r7, tail + kTailAlphaW, sigma, mw, bulk_g, bulk_s);
           else if (!kFused && stage == 8) epi_stage256<2, false, kF16>(t_acc, bias4, a_row_base, r7, nullptr, sigma);
-          else epi_stage256<0, kSave, kF16>(t_acc, bias4, a_row_base, r7, nullptr, sigma, mw, g_row);
+          else epi_stage256<0, kSave, kF16>(t_acc, bias4, a_row_base, r7, nullptr, sigma, mw, bulk_g, bulk_s);
           if (stage == I::kLast - 1) {  // dir PE replaces the xyz PE tile (dead after stage 5) for the views stage
             float f[32];
             pos_enc_row<kLd>(d_cur, f);
@@ -243,15 +237,8 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
           if (!kSave || save_leader) mbar_arrive_remote(b_ready_leader);
           mbar_arrive(bar(BAR_BEMPTY + bbuf));
           if (tl_on) tl[720 + ((it * 10 + stage) * 2 + slot) * 4 + 2] = clock64();
-          if (kSave && tile_ok) {
-#ifndef NB_SAVE_DIRECT
-            // stage output (= next stage's A tile) -> activation store, while the MMAs read it too
-            copy_tile_s2g<4 * kBlockBytes>(acts_tile + (size_t)act_h(stage) * kBlockBytes,
-                                           smem_dyn + kOffA + slot * kABytes, row, dbg);
-#endif
-            if (stage == I::kLast - 1)
-              copy_tile_s2g<kBlockBytes>(acts_tile + (size_t)kActDpe * kBlockBytes, smem_dyn + kOffPe + slot * kPeBytes, row);
-          }
+          if (kSave && tile_ok && stage == I::kLast - 1)   // the dir PE tile this stage's epilogue wrote (store_row_chunks above)
+            bulk_store_warp_rows(acts_tile + (size_t)kActDpe * kBlockBytes + (size_t)w4 * 4096u, pe_base + (uint32_t)w4 * 4096u, 1);
           if (kSave && mask_ok && stage < 8) {   // relu sign bits of this stage for the dgrad epilogue (after the
             // hand-off: a global store in front of the arrive would sit under its release fence)
             uint4* dst = reinterpret_cast<uint4*>(masks + (size_t)stage * mask_plane + mask_row * kMaskWords);
@@ -299,8 +286,9 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
           if (kSave) {
             if (mask_ok)
               *reinterpret_cast<uint4*>(masks + (size_t)8 * mask_plane + mask_row * kMaskWords) = make_uint4(hvm[0], hvm[1], hvm[2], hvm[3]);
-            named_bar_sync(1 + slot, 128);
-            if (tile_ok) copy_tile_s2g<2 * kBlockBytes>(acts_tile + (size_t)kActHv * kBlockBytes, smem_dyn + kOffA + slot * kABytes, row);
+            if (tile_ok)
+              bulk_store_warp_rows(acts_tile + (size_t)kActHv * kBlockBytes + (size_t)w4 * 4096u,
+                                   smem_base + kOffA + (uint32_t)slot * kABytes + (uint32_t)w4 * 4096u, 2);
           }
           if (kFused) {   // sigma_raw = accumulator column 128 (+ alpha_b, staged as bias element 128)
             uint32_t v[32];
@@ -320,6 +308,7 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
         }
       }
     }
+    if (kSave) bulk_store_warp_drain();
   } else if (warp == 8) {
     // =========================== producer: bias block + this CTA's half of every weight chunk ==========
     uint32_t seq = 0, bseq = 0;

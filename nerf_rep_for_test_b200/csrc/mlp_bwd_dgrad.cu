@@ -74,7 +74,7 @@ __device__ __forceinline__ void depi32(const uint32_t (&v)[32], unsigned char* o
 
 template <int MODE>
 __device__ __forceinline__ void depi_stage256(uint32_t t_acc, unsigned char* a_row_base, int r7, const uint32_t (&mw)[8],
-                                              float gs, const float* __restrict__ aw) {
+                                              float gs, const float* __restrict__ aw, unsigned char* bulk_g, uint32_t bulk_s) {
   uint32_t va[32], vb[32];
   tmem_ld32(t_acc, va);
   tmem_ld32(t_acc + 32u, vb);
@@ -87,6 +87,8 @@ __device__ __forceinline__ void depi_stage256(uint32_t t_acc, unsigned char* a_r
     depi32<MODE>(va, out_row, 0, r7, mw[2 * h], gs, aw + h * 64);
     if (h < 3) tmem_ld32(t_acc + (uint32_t)(h * 64 + 64), va);
     depi32<MODE>(vb, out_row, 4, r7, mw[2 * h + 1], gs, aw + h * 64 + 32);
+    // K-block h of this warp's rows -> activation-gradient store, while the epilogue goes on (mlp_tc_common.cuh)
+    if (bulk_g != nullptr) bulk_store_warp_rows(bulk_g + h * 16384, bulk_s + (uint32_t)h * 16384u, 1);
     if (h < 3) {
       tmem_ld32(t_acc + (uint32_t)(h * 64 + 96), vb);
       tmem_ld_wait();
@@ -143,7 +145,6 @@ mlp_bwd_dgrad_kernel(const unsigned char* __restrict__ packed_bwd, const float* 
     const int row = w4 * 32 + lane;
     const int r7 = row & 7;
     unsigned char* a_row_base = smem_dyn + kOffA + (uint32_t)slot * kABytes + (uint32_t)row * 128u;
-    const unsigned char* a_tile = smem_dyn + kOffA + (uint32_t)slot * kABytes;
     const uint32_t t_acc = tmem_base + ((uint32_t)(w4 * 32) << 16) + (uint32_t)slot * 256u;
     const uint32_t b_ready_leader = mapa(bar(BAR_AREADY + slot), 0);
     const uint32_t b_full = bar(BAR_ACCFULL + slot);
@@ -163,7 +164,7 @@ mlp_bwd_dgrad_kernel(const unsigned char* __restrict__ packed_bwd, const float* 
       if (m < M) g = __ldg(reinterpret_cast<const float4*>(g_raw) + m);
       uint4 hvm = make_uint4(0u, 0u, 0u, 0u);
       if (tile_ok) hvm = __ldg(reinterpret_cast<const uint4*>(masks + 8 * mask_plane + mask_row));
-      named_bar_sync(1 + slot, 128);   // every thread has finished copying the previous tile's last stage out
+      bulk_store_warp_reads_done();    // the previous tile's last stage has left this warp's rows of the A tile
       {  // D9 tile: d_hv (blocks 0,1) | g_raw as bf16 + zero pad (block 2) | zeros (block 3)
         const uint32_t hv_words[4] = {hvm.x, hvm.y, hvm.z, hvm.w};
 #pragma unroll
@@ -195,7 +196,8 @@ mlp_bwd_dgrad_kernel(const unsigned char* __restrict__ packed_bwd, const float* 
       fence_proxy_async_smem();
       named_bar_sync(1 + slot, 128);
       if (leader) mbar_arrive_remote(b_ready_leader);
-      if (tile_ok) copy_tile_s2g<4 * kBlockBytes>(dacts_tile + (size_t)kDactD9 * kBlockBytes, a_tile, row);
+      const uint32_t a_warp_s = smem_base + kOffA + (uint32_t)slot * kABytes + (uint32_t)w4 * 4096u;   // this warp's rows of block 0
+      if (tile_ok) bulk_store_warp_rows(dacts_tile + (size_t)kDactD9 * kBlockBytes + (size_t)w4 * 4096u, a_warp_s, 4);
 
       for (int bs = 0; bs < kBwdStages; ++bs) {
         uint32_t mw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
@@ -208,17 +210,17 @@ mlp_bwd_dgrad_kernel(const unsigned char* __restrict__ packed_bwd, const float* 
         mbar_wait(b_full, full_phase, 0x100 + bs);
         full_phase ^= 1;
         tc_fence_after();
-        named_bar_sync(1 + slot, 128);   // the previous stage's tile has been copied out by everyone
-        if (bs == 0) depi_stage256<1>(t_acc, a_row_base, r7, mw, g.w, alpha_w);
-        else depi_stage256<2>(t_acc, a_row_base, r7, mw, 0.f, alpha_w);
+        bulk_store_warp_reads_done();    // the previous stage's stores have finished reading this warp's rows
+        unsigned char* bulk_g = tile_ok ? dacts_tile + (size_t)dact_pre(7 - bs) * kBlockBytes + (size_t)w4 * 4096u : nullptr;
+        if (bs == 0) depi_stage256<1>(t_acc, a_row_base, r7, mw, g.w, alpha_w, bulk_g, a_warp_s);
+        else depi_stage256<2>(t_acc, a_row_base, r7, mw, 0.f, alpha_w, bulk_g, a_warp_s);
         tc_fence_before();
         fence_proxy_async_smem();
         named_bar_sync(1 + slot, 128);
         if (leader && bs + 1 < kBwdStages) mbar_arrive_remote(b_ready_leader);
-        if (tile_ok)   // while the next stage's MMAs read the same tile
-          copy_tile_s2g<4 * kBlockBytes>(dacts_tile + (size_t)dact_pre(7 - bs) * kBlockBytes, a_tile, row);
       }
     }
+    bulk_store_warp_drain();
   } else if (warp == 8) {
     // =========================== producer: this CTA's half of every W^T chunk ===========================
     if (lane == 0) {

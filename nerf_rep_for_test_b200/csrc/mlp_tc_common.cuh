@@ -59,14 +59,11 @@ __device__ __forceinline__ void pin32(uint32_t (&r)[32]) {
 // Plain C++ shared-memory accesses (not volatile asm) so the compiler batches the bias loads.
 // kMask (training forward): additionally returns the relu sign bits of the 32 columns in the bit order
 // of train_layout.cuh (column 4s+k -> bit 8k+7-s, set = negative), built with one funnel shift per value.
-// gout_row (training forward, may be NULL): the same 16-byte chunks also go straight to this row of the activation
-// store's tile image in global memory (same swizzled position: a thread's eight chunks of a block are one 128-byte line).
 template <int MODE, bool kMask = false, bool kF16 = false>
 __device__ __forceinline__ void epi32(const uint32_t (&v)[32], const float4* __restrict__ bias4, unsigned char* out_row,
                                       int j0, int r7, const float* __restrict__ alpha_w, float& sigma,
-                                      uint32_t* mask_word = nullptr, unsigned char* gout_row = nullptr) {
+                                      uint32_t* mask_word = nullptr) {
   uint32_t ch0 = 0, ch1 = 0, ch2 = 0, ch3 = 0;
-  uint4 o_even = make_uint4(0u, 0u, 0u, 0u);
   float4 b[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) b[i] = bias4[i];
@@ -100,28 +97,48 @@ __device__ __forceinline__ void epi32(const uint32_t (&v)[32], const float4* __r
     o.x = cvt_bf16x2<kRelu, kF16>(x0.x, x0.y); o.y = cvt_bf16x2<kRelu, kF16>(x1.x, x1.y);
     o.z = cvt_bf16x2<kRelu, kF16>(x2.x, x2.y); o.w = cvt_bf16x2<kRelu, kF16>(x3.x, x3.y);
     *reinterpret_cast<uint4*>(out_row + (((j0 + q) ^ r7) << 4)) = o;
-    if (kMask && gout_row != nullptr) {
-      // chunks j0+q (q even) and j0+q+1 share one 32-byte sector of the swizzled row (the XOR with r7 swaps them when
-      // r7 is odd): one 256-bit store per pair = full sectors, half the store instructions
-      if ((q & 1) == 0) {
-        o_even = o;
-      } else {
-        const bool swap = (r7 & 1) != 0;
-        const uint4 lo = swap ? o : o_even, hi = swap ? o_even : o;
-        unsigned char* dst = gout_row + ((((j0 + q - 1) ^ r7) >> 1) << 5);
-        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(lo.x), "r"(lo.y), "r"(lo.z),
-                     "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
-      }
-    }
   }
   if (kMask) *mask_word = ch0 | (ch1 << 8) | (ch2 << 16) | (ch3 << 24);
 }
 
-// one hidden stage (256 accumulator columns) with the TMEM loads double-buffered
+// ---- activation store of the training kernels: tile images leave shared memory as per-warp bulk stores ----------------
+// A tile image block is [128 rows][128 B] (train_layout.cuh); row r sits at r * 128 and the 128-byte swizzle permutes
+// inside the row, so the 32 rows a warp owns (row = (warp & 3) * 32 + lane) are 4 KB contiguous in shared AND in global
+// memory.  Once the warp has written its rows of a block, lane 0 hands them to the TMA engine (cp.async.bulk shared ->
+// global); the store then streams out in the background.  Because a warp only ever rewrites its OWN rows, the only
+// synchronisation is the warp's own cp.async.bulk.wait_group.read before it touches those rows again.
+// History (round 1 / 2): the epilogue group's 128 threads copied the finished 64 KB tile out after the hand-off to the
+// MMA issuer -- LDS.128 + coalesced STG.128 -- which put epilogue + copy on each slot's critical chain (in-kernel
+// timeline: MMA 3300 + epilogue 3700 cycles per stage and slot, tensor pipe 36 %, stores 3.4 TB/s); a single 64 KB bulk
+// store issued after the hand-off had the same window and stalled the next epilogue just the same.  Issuing 4 KB pieces
+// as the epilogue produces them widens the window by the epilogue itself and frees the threads: training step
+// 4.41 -> 4.03-4.13 ms with the forward alone converted (profiles/r02_experiments_not_merged.txt has the dead ends).
+// `nblocks` consecutive blocks (stride 16 KB in both address spaces), each 4 KB of this warp's rows.
+__device__ __forceinline__ void bulk_store_warp_rows(unsigned char* gdst, uint32_t ssrc, int nblocks) {
+  fence_proxy_async_smem();           // this thread's rows -> visible to the async proxy
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) {
+    for (int b = 0; b < nblocks; ++b) bulk_s2g(gdst + (size_t)b * 16384, ssrc + (uint32_t)b * 16384u, 4096u);
+    bulk_commit();
+  }
+}
+// all bulk stores this warp has issued have finished READING shared memory: its rows may be rewritten
+__device__ __forceinline__ void bulk_store_warp_reads_done() {
+  if ((threadIdx.x & 31) == 0) bulk_wait_read0();
+  __syncwarp();
+}
+// before the CTA exits: shared memory must outlive the stores
+__device__ __forceinline__ void bulk_store_warp_drain() {
+  if ((threadIdx.x & 31) == 0) bulk_wait0();
+}
+
+// one hidden stage (256 accumulator columns) with the TMEM loads double-buffered.  bulk_g / bulk_s (training, may be
+// 0): global / shared address of THIS WARP's 32 rows of K-block 0 of the stage's tile image -- K-block h is stored as soon
+// as the warp has written it (bulk_store_warp_rows).
 template <int MODE, bool kMask = false, bool kF16 = false>
 __device__ __forceinline__ void epi_stage256(uint32_t t_acc, const float4* __restrict__ bias4, unsigned char* a_row_base,
                                              int r7, const float* __restrict__ alpha_w, float& sigma,
-                                             uint32_t* mw = nullptr, unsigned char* g_row_base = nullptr) {
+                                             uint32_t* mw = nullptr, unsigned char* bulk_g = nullptr, uint32_t bulk_s = 0u) {
   uint32_t va[32], vb[32];
   tmem_ld32(t_acc, va);
   tmem_ld32(t_acc + 32u, vb);
@@ -131,41 +148,16 @@ __device__ __forceinline__ void epi_stage256(uint32_t t_acc, const float4* __res
 #pragma unroll
   for (int h = 0; h < 4; ++h) {   // K-block h of the A operand = columns 64h .. 64h+63
     unsigned char* out_row = a_row_base + h * 16384;
-    unsigned char* gout_row = g_row_base != nullptr ? g_row_base + h * 16384 : nullptr;
-    epi32<MODE, kMask, kF16>(va, bias4 + h * 16, out_row, 0, r7, alpha_w + h * 64, sigma, mw + 2 * h, gout_row);
+    epi32<MODE, kMask, kF16>(va, bias4 + h * 16, out_row, 0, r7, alpha_w + h * 64, sigma, mw + 2 * h);
     if (h < 3) tmem_ld32(t_acc + (uint32_t)(h * 64 + 64), va);
-    epi32<MODE, kMask, kF16>(vb, bias4 + h * 16 + 8, out_row, 4, r7, alpha_w + h * 64 + 32, sigma, mw + 2 * h + 1, gout_row);
+    epi32<MODE, kMask, kF16>(vb, bias4 + h * 16 + 8, out_row, 4, r7, alpha_w + h * 64 + 32, sigma, mw + 2 * h + 1);
+    if (kMask && bulk_g != nullptr) bulk_store_warp_rows(bulk_g + h * 16384, bulk_s + (uint32_t)h * 16384u, 1);
     if (h < 3) {
       tmem_ld32(t_acc + (uint32_t)(h * 64 + 96), vb);
       tmem_ld_wait();
       pin32(va);
       pin32(vb);
     }
-  }
-}
-
-// Copy a finished operand tile (multiple of 2048 B) from shared memory to its tile image in global memory
-// with the 128 threads of one epilogue group: thread t moves 16 B at t*16 + k*2048, so a warp reads 512
-// contiguous bytes of shared memory (conflict-free) and writes four full 128-byte lines.  Done AFTER the
-// hand-off to the MMA issuer, while this group would otherwise wait for its next accumulator; a TMA bulk
-// store of the same tile kept the tile busy for > 2500 cycles (L2 path shared with the weight stream) and
-// stalled the next epilogue (measured: +2300 cycles per stage).
-template <int BYTES>
-__device__ __forceinline__ void copy_tile_s2g(unsigned char* __restrict__ gdst, const unsigned char* ssrc, int t128, int dbg = 0) {
-  static_assert(BYTES % 8192 == 0, "tile copy works in batches of 4 x 2048 B");
-#pragma unroll 1
-  for (int k = 0; k < BYTES / 8192; ++k) {
-    uint4 v[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      v[j] = (dbg & 8) ? make_uint4(k, j, t128, 0) : *reinterpret_cast<const uint4*>(ssrc + k * 8192 + j * 2048 + t128 * 16);
-    if (dbg & 4) {   // experiment: no global stores (keep the loads alive)
-      if ((v[0].x ^ v[1].y ^ v[2].z ^ v[3].w) == 0x12345678u) gdst[0] = 1;
-      continue;
-    }
-#pragma unroll
-    // (st.global.cs / .wt instead of the default policy made no difference: measured A/B)
-    for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(gdst + k * 8192 + j * 2048 + t128 * 16) = v[j];
   }
 }
 
