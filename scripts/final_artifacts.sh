@@ -1,4 +1,4 @@
-V=v37
+V=v42
 python -m pytest tests -m gpu -x -q > gpurun_out/r02_gpu_tests_$V.txt 2>&1; tail -1 gpurun_out/r02_gpu_tests_$V.txt
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_smoke_$V.txt 2>&1; tail -1 gpurun_out/r02_smoke_$V.txt
 python bench.py > gpurun_out/r02_bench_n1_$V.json 2> gpurun_out/bench_$V.err; echo bench rc=$?
