@@ -85,9 +85,9 @@ mlp_bf16_tc2_kernel(const unsigned char* __restrict__ packed, const float* __res
     }
     for (int s = 0; s < 2; ++s) {
       // both CTAs' epilogue groups signal the leader's copy: every thread in inference; in training only the
-      // group's first thread, behind the named barrier that precedes the bulk store (the release fence of
-      // the remote arrive waits for the warp's pending global stores, which is what made the first training
-      // forward 2x slower than inference)
+      // group's first thread, behind a 128-thread named barrier (the release fence of the remote arrive waits for
+      // the warp's pending global stores -- the relu-mask rows here --, which is what made the first training forward
+      // 2x slower than inference)
       mbar_init(bar(BAR_AREADY + s), kSave ? 2 : 256);
       mbar_init(bar(BAR_ACCFULL + s), 1);
       mbar_init(bar(BAR_BFULL + s), 1);

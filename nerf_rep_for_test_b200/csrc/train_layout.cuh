@@ -5,7 +5,8 @@
 // [128 rows][64 bf16 columns] cut, laid out exactly like the shared-memory operand of tcgen05.mma with
 // SWIZZLE_128B (row r at r*128 B, 16-byte unit u of the row at ((u ^ (r & 7)) << 4)).  One block is
 // 16 384 contiguous bytes, so
-//   * the producing kernel copies a finished operand tile out with fully coalesced 16-byte stores,
+//   * the producing kernel sends a finished operand tile out as flat bulk stores (cp.async.bulk shared -> global, one
+//     per warp and block: a warp's 32 rows are 4 KB contiguous; mlp_tc_common.cuh, bulk_store_warp_rows),
 //   * the wgrad kernel streams blocks back with flat bulk copies (no tensor maps), and consumes the SAME
 //     image either K-major (K = columns: forward / dgrad) or MN-major (K = rows: wgrad) -- only the
 //     descriptor changes.
